@@ -1,0 +1,146 @@
+// api_gemm.cu — C-ABI entry points for the tcgen05 GEMMs (forward/dgrad and wgrad).
+#include "gemm_tn.cuh"
+#include "gemm_wgrad.cuh"
+#include "srk_host.h"
+
+namespace srk {
+
+template <int BN, int EPI>
+static int launch_gemm_tn(const GemmArgs& a, const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC,
+                          const CUtensorMap& tC2, const CUtensorMap& tX1, const CUtensorMap& tX2,
+                          cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    SRK_CUDA_OK(cudaFuncSetAttribute(gemm_tn_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int tiles = (a.M / GEMM_BM) * (a.N / BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_tn_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(tA, tB, tC, tC2, tX1, tX2, a);
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+static int pick_bn(int epi, int N) {
+  if (epi == EPI_RES_LN || epi == EPI_LNBWD) return (N == 192) ? 192 : (N == 128 ? 128 : -1);
+  if (epi == EPI_GELU2 || epi == EPI_MUL) return (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : -1);
+  if (N % 192 == 0) return 192;
+  if (N % 256 == 0) return 256;
+  if (N % 128 == 0) return 128;
+  if (N % 64 == 0) return 64;
+  return -1;
+}
+
+}  // namespace srk
+
+using namespace srk;
+
+extern "C" const char* srk_version(void) { return "libsrk 0.1 (sm_100a: tcgen05/TMEM/TMA)"; }
+
+extern "C" int srk_gemm_grid(int M, int N) {
+  (void)N;
+  const int tiles = M / GEMM_BM;  // row epilogues have a single N tile
+  return tiles < num_sms() ? tiles : num_sms();
+}
+
+extern "C" int srk_gemm_tn(int epi, int M, int N, int K, const void* A, int lda, const void* B, int ldb, void* C,
+                           int ldc, void* C2, int ldc2, const void* X1, int ldx1, const void* X2, int ldx2,
+                           const SrkLnArgs* ln, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (M <= 0 || N <= 0 || K <= 0 || M % GEMM_BM != 0 || K % GEMM_BK != 0)
+    return fail(SRK_ERR_ARG, "srk_gemm_tn: M must be a multiple of 128 and K of 64");
+  const int bn = pick_bn(epi, N);
+  if (bn < 0) return fail(SRK_ERR_UNSUPPORTED, "srk_gemm_tn: unsupported N for this epilogue");
+  if (!A || !B || !C) return fail(SRK_ERR_ARG, "srk_gemm_tn: null operand");
+  GemmArgs a{};
+  a.M = M; a.N = N; a.K = K;
+  a.n_real = N; a.ones_col = -1; a.gamma = nullptr; a.beta = nullptr; a.stats = nullptr; a.partials = nullptr;
+  a.eps = 1e-5f;
+  if (ln) {
+    a.n_real = ln->n_real; a.ones_col = ln->ones_col; a.gamma = ln->gamma; a.beta = ln->beta;
+    a.stats = ln->stats; a.partials = ln->partials; a.eps = ln->eps;
+  }
+  if ((epi == EPI_RES_LN || epi == EPI_LNBWD) && (!ln || !ln->gamma)) return fail(SRK_ERR_ARG, "LN epilogue needs SrkLnArgs");
+  if (epi == EPI_LNBWD && (!ln->stats || !ln->partials || !X1 || !X2)) return fail(SRK_ERR_ARG, "LNBWD needs stats, partials, X1, X2");
+  if (epi == EPI_RES_LN && (!X1 || !C2)) return fail(SRK_ERR_ARG, "RES_LN needs X1 and C2");
+  if (epi == EPI_GELU2 && !C2) return fail(SRK_ERR_ARG, "GELU2 needs C2");
+  if (epi == EPI_MUL && !X1) return fail(SRK_ERR_ARG, "MUL needs X1");
+
+  CUtensorMap tA, tB, tC, tC2, tX1, tX2;
+  int rc;
+  if ((rc = make_tmap_2d(&tA, A, M, K, lda, GEMM_BM))) return rc;
+  if ((rc = make_tmap_2d(&tB, B, N, K, ldb, bn))) return rc;
+  if ((rc = make_tmap_2d(&tC, C, M, N, ldc, GEMM_BM))) return rc;
+  tC2 = tC; tX1 = tC; tX2 = tC;
+  if (C2 && (rc = make_tmap_2d(&tC2, C2, M, N, ldc2, GEMM_BM))) return rc;
+  if (X1 && (rc = make_tmap_2d(&tX1, X1, M, N, ldx1, GEMM_BM))) return rc;
+  if (X2 && (rc = make_tmap_2d(&tX2, X2, M, N, ldx2, GEMM_BM))) return rc;
+
+#define SRK_CASE(BN_, EPI_) \
+  if (bn == BN_ && epi == EPI_) return launch_gemm_tn<BN_, EPI_>(a, tA, tB, tC, tC2, tX1, tX2, stream);
+  SRK_CASE(64, EPI_STORE)
+  SRK_CASE(128, EPI_STORE)
+  SRK_CASE(192, EPI_STORE)
+  SRK_CASE(256, EPI_STORE)
+  SRK_CASE(128, EPI_GELU2)
+  SRK_CASE(256, EPI_GELU2)
+  SRK_CASE(128, EPI_MUL)
+  SRK_CASE(256, EPI_MUL)
+  SRK_CASE(128, EPI_RES_LN)
+  SRK_CASE(192, EPI_RES_LN)
+  SRK_CASE(128, EPI_LNBWD)
+  SRK_CASE(192, EPI_LNBWD)
+#undef SRK_CASE
+  return fail(SRK_ERR_UNSUPPORTED, "srk_gemm_tn: no kernel instance for (BN, epilogue)");
+}
+
+template <int BNW>
+static int launch_wgrad(const WgradArgs& a, const CUtensorMap& tA, const CUtensorMap& tB, cudaStream_t stream) {
+  using Cfg = WgradCfg<BNW>;
+  static bool configured = false;
+  if (!configured) {
+    SRK_CUDA_OK(cudaFuncSetAttribute(gemm_wgrad_kernel<BNW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg::kSmemBytes));
+    configured = true;
+  }
+  gemm_wgrad_kernel<BNW><<<a.ca_tiles * a.splits, WG_THREADS, Cfg::kSmemBytes, stream>>>(tA, tB, a);
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+extern "C" int srk_gemm_wgrad_dbg(int T, int Ca, int Cb, const void* A, int lda, const void* B, int ldb,
+                                  float* workspace, int splits, float* out, int lbo_bytes, int sbo_bytes,
+                                  void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (splits <= 0 || T <= 0 || T % (WG_TOK * splits) != 0)
+    return fail(SRK_ERR_ARG, "srk_gemm_wgrad: T must be a multiple of 64*splits");
+  if (!A || !B || !workspace || !out) return fail(SRK_ERR_ARG, "srk_gemm_wgrad: null pointer");
+  WgradArgs a{};
+  a.T = T; a.Ca = Ca; a.Cb = Cb; a.ca_tiles = (Ca + 127) / 128; a.splits = splits; a.partials = workspace;
+  a.lbo_bytes = lbo_bytes; a.sbo_bytes = sbo_bytes;
+  CUtensorMap tA, tB;
+  int rc;
+  if ((rc = make_tmap_2d(&tA, A, T, Ca, lda, WG_TOK))) return rc;
+  if ((rc = make_tmap_2d(&tB, B, T, Cb, ldb, WG_TOK))) return rc;
+  switch (Cb) {
+    case 64: rc = launch_wgrad<64>(a, tA, tB, stream); break;
+    case 128: rc = launch_wgrad<128>(a, tA, tB, stream); break;
+    case 192: rc = launch_wgrad<192>(a, tA, tB, stream); break;
+    case 256: rc = launch_wgrad<256>(a, tA, tB, stream); break;
+    default: return fail(SRK_ERR_UNSUPPORTED, "srk_gemm_wgrad: Cb must be 64/128/192/256");
+  }
+  if (rc) return rc;
+  const int n = a.ca_tiles * 128 * Cb;
+  wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, stream>>>(workspace, out, splits, n);
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+extern "C" int srk_gemm_wgrad(int T, int Ca, int Cb, const void* A, int lda, const void* B, int ldb,
+                              float* workspace, int splits, float* out, void* stream) {
+  // MN-major, 128B swizzle: LBO = distance between 64-channel groups (one [64 tok x 128 B] box),
+  // SBO = distance between 8-token groups (8 rows x 128 B).
+  return srk_gemm_wgrad_dbg(T, Ca, Cb, A, lda, B, ldb, workspace, splits, out, WG_SUBBOX, 1024, stream);
+}

@@ -1,0 +1,540 @@
+// gemm_tn.cuh — persistent warp-specialised tcgen05 GEMM for the token-major linears of the
+// Swin/HAT blocks:  C[M,N] = epilogue( A[M,K] * B[N,K]^T ),  bf16 operands, fp32 accumulate in TMEM.
+//
+// Replaces (reference): nn.Linear calls in WindowAttention.qkv/proj (models/architecture_swin.py:73,94),
+// Mlp.fc1/fc2 (:19-25), and their autograd input-gradients; the fused epilogues replace
+// LayerNorm (:127,150), GELU (:20), the residual adds (:149-150) and their backward passes.
+//
+// Roles (192 threads, 1 CTA/SM, persistent over output tiles):
+//   warp 0   : TMA producer   (A [128 x 64] + B [BN x 64] bf16 boxes, 128B swizzle, mbarrier ring)
+//   warp 1   : MMA issuer     (one lane issues tcgen05.mma 128 x BN x 16; accumulators double-buffered in TMEM)
+//   warps 2-5: epilogue       (tcgen05.ld -> registers -> math -> swizzled smem -> TMA store)
+#pragma once
+#include "srk_ptx.cuh"
+
+namespace srk {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_EPI_THREADS = 128;
+constexpr int BOX_BYTES = 128 * 128;  // one [128 rows x 64 bf16] swizzled box
+
+enum GemmEpilogue : int {
+  EPI_STORE = 0,   // C = bf16(acc)
+  EPI_GELU2 = 1,   // C = gelu(u), C2 = gelu'(u), u = bf16(acc)                 (fc1 forward)
+  EPI_MUL = 2,     // C = bf16(acc * X1)                                        (fc2 dgrad -> dU)
+  EPI_RES_LN = 3,  // C = v = bf16(bf16(acc) + X1); C2 = LayerNorm(v)           (proj / fc2 forward)
+  EPI_LNBWD = 4,   // C = X2 + LayerNormBackward(acc | X1, stats)               (fc1 / qkv dgrad)
+};
+
+struct GemmArgs {
+  int M, N, K;        // padded sizes: M % 128 == 0, N % BN == 0, K % 64 == 0
+  int n_real;         // number of real channels normalised by the LN epilogues (e.g. 180)
+  int ones_col;       // column forced to 1.0 in the LN output / GELU output (bias-folding column), -1: none
+  const float* gamma; // LN weight [n_real]
+  const float* beta;  // LN bias   [n_real]
+  float* stats;       // [M][2] (mean, rstd): written by EPI_RES_LN, read by EPI_LNBWD
+  float* partials;    // EPI_LNBWD: [gridDim.x][2][BN] per-CTA column sums (dgamma, dbeta)
+  float eps;
+};
+
+template <int BN, int EPI>
+struct GemmCfg {
+  static constexpr int kStageBytes = GEMM_BM * 128 + BN * 128;
+  static constexpr int kBoxes = BN / 64;
+  static constexpr int kEpiBytes = (EPI == EPI_STORE)   ? 2 * BOX_BYTES
+                                   : (EPI == EPI_GELU2) ? 4 * BOX_BYTES
+                                   : (EPI == EPI_MUL)   ? 4 * BOX_BYTES
+                                                        : 2 * kBoxes * BOX_BYTES;
+  static constexpr int kBudget = 232448 - 1024 /*align slack*/ - 512 /*barriers*/ - 2304 /*static smem*/;
+  static constexpr int kStagesRaw = (kBudget - kEpiBytes) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 512 + 1024;
+  static_assert(kStages >= 2, "not enough shared memory for a 2-stage pipeline");
+  static_assert(BN % 64 == 0 && BN <= 256, "BN must be a multiple of 64, <= 256");
+};
+
+__device__ __forceinline__ float gelu_erf(float u) {
+  return 0.5f * u * (1.0f + erff(u * 0.70710678118654752f));
+}
+__device__ __forceinline__ float gelu_erf_grad(float u) {
+  const float cdf = 0.5f * (1.0f + erff(u * 0.70710678118654752f));
+  const float pdf = 0.3989422804014327f * __expf(-0.5f * u * u);
+  return cdf + u * pdf;
+}
+
+// Transposing butterfly: on entry lane l holds v[0..31] (32 columns of its row); on exit v[0] of
+// lane l is the sum over the 32 lanes of column l.  31 shuffles instead of 32*5.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? v[i] : v[i + off];
+      const float keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// byte offset of 16-byte chunk `ch` (0..7) of row `r` inside a 128B-swizzled [rows x 128 B] box
+__device__ __forceinline__ uint32_t swz(int r, int ch) { return uint32_t(r) * 128u + (uint32_t(ch ^ (r & 7)) << 4); }
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
+               const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmX2,
+               const GemmArgs args) {
+  using Cfg = GemmCfg<BN, EPI>;
+  constexpr int S = Cfg::kStages;
+  constexpr int NBOX = Cfg::kBoxes;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t epi_base = smem_base + S * Cfg::kStageBytes;
+  const uint32_t bar_base = epi_base + Cfg::kEpiBytes;
+  // barrier slots (8 B each)
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * S + 2 + a); };
+  auto aux_bar = [&](int b) { return bar_base + 8u * (2 * S + 4 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * S + 6);
+
+  __shared__ float s_gamma[256];
+  __shared__ float s_beta[256];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = args.M / GEMM_BM;
+  const int n_tiles = args.N / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int k_iters = args.K / GEMM_BK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+      mbar_init(aux_bar(a), 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  if constexpr (EPI == EPI_RES_LN || EPI == EPI_LNBWD) {
+    for (int i = threadIdx.x; i < 256; i += GEMM_THREADS) {
+      s_gamma[i] = (i < args.n_real) ? args.gamma[i] : 0.f;
+      s_beta[i] = (i < args.n_real && args.beta != nullptr) ? args.beta[i] : 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * GEMM_BM;
+        const int n0 = (tile % n_tiles) * BN;
+        for (int kb = 0; kb < k_iters; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          const uint32_t sb = sa + GEMM_BM * 128;
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+          tma_load_2d(sa, &tmA, full_bar(stage), kb * GEMM_BK, m0);
+          tma_load_2d(sb, &tmB, full_bar(stage), kb * GEMM_BK, n0);
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
+        for (int kb = 0; kb < k_iters; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          const uint32_t sb = sa + GEMM_BM * 128;
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            const uint64_t adesc = make_smem_desc(sa + k * 32, 16, 1024);
+            const uint64_t bdesc = make_smem_desc(sb + k * 32, 16, 1024);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;             // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;      // accumulator row owned by this thread
+    const bool elected = (threadIdx.x == 64);
+    const uint32_t lane_sel = uint32_t(q * 32) << 16;
+    int it = 0;
+    uint32_t box_counter = 0;           // box-granular staging ring position
+    uint32_t aux_count = 0;             // number of aux loads consumed (parity tracking)
+    float acc_g[(EPI == EPI_LNBWD) ? (BN / 32) : 1];
+    float acc_b[(EPI == EPI_LNBWD) ? (BN / 32) : 1];
+#pragma unroll
+    for (int i = 0; i < ((EPI == EPI_LNBWD) ? (BN / 32) : 1); ++i) { acc_g[i] = 0.f; acc_b[i] = 0.f; }
+
+    // aux prefetch for the first tile
+    if constexpr (EPI == EPI_MUL) {
+      if (elected && blockIdx.x < num_tiles) {
+        const int m0 = (blockIdx.x / n_tiles) * GEMM_BM, n0 = (blockIdx.x % n_tiles) * BN;
+        mbar_arrive_expect_tx(aux_bar(0), BOX_BYTES);
+        tma_load_2d(epi_base, &tmX1, aux_bar(0), n0, m0);
+      }
+    }
+    if constexpr (EPI == EPI_RES_LN || EPI == EPI_LNBWD) {
+      if (elected && blockIdx.x < num_tiles) {
+        const int m0 = (blockIdx.x / n_tiles) * GEMM_BM, n0 = (blockIdx.x % n_tiles) * BN;
+        constexpr int nload = (EPI == EPI_LNBWD) ? 2 : 1;
+        mbar_arrive_expect_tx(aux_bar(0), nload * NBOX * BOX_BYTES);
+        for (int b = 0; b < NBOX; ++b) tma_load_2d(epi_base + b * BOX_BYTES, &tmX1, aux_bar(0), n0 + b * 64, m0);
+        if constexpr (EPI == EPI_LNBWD)
+          for (int b = 0; b < NBOX; ++b)
+            tma_load_2d(epi_base + (NBOX + b) * BOX_BYTES, &tmX2, aux_bar(0), n0 + b * 64, m0);
+      }
+    }
+
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m0 = (tile / n_tiles) * GEMM_BM;
+      const int n0 = (tile % n_tiles) * BN;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      const uint32_t taddr = tmem_base + lane_sel + uint32_t(acc * BN);
+      const int next_tile = tile + gridDim.x;
+
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+
+      if constexpr (EPI == EPI_STORE || EPI == EPI_GELU2 || EPI == EPI_MUL) {
+        // ---------------------------------------------------------- box-granular elementwise epilogues
+        constexpr int kAuxOff = 0;                                     // MUL: 2 aux boxes first
+        constexpr int kOutOff = (EPI == EPI_MUL) ? 2 * BOX_BYTES : 0;  // then staging ring
+        constexpr int kOutPerBox = (EPI == EPI_GELU2) ? 2 : 1;
+#pragma unroll 1
+        for (int j = 0; j < NBOX; ++j) {
+          const uint32_t ring = box_counter & 1u;
+          const uint32_t out0 = epi_base + kOutOff + ring * (kOutPerBox * BOX_BYTES);
+          if (elected) {
+            tma_store_wait_read<1>();
+            if constexpr (EPI == EPI_MUL) {
+              // prefetch the next aux box (next box of this tile, or box 0 of the next tile)
+              int nm0 = m0, nn0 = n0 + (j + 1) * 64;
+              bool have = true;
+              if (j + 1 == NBOX) {
+                have = next_tile < num_tiles;
+                nm0 = (next_tile / n_tiles) * GEMM_BM;
+                nn0 = (next_tile % n_tiles) * BN;
+              }
+              if (have) {
+                const uint32_t nb = (aux_count + 1) & 1u;
+                mbar_arrive_expect_tx(aux_bar(nb), BOX_BYTES);
+                tma_load_2d(epi_base + kAuxOff + nb * BOX_BYTES, &tmX1, aux_bar(nb), nn0, nm0);
+              }
+            }
+          }
+          named_bar_sync(1, GEMM_EPI_THREADS);
+          uint32_t aux_addr = 0;
+          if constexpr (EPI == EPI_MUL) {
+            const uint32_t ab = aux_count & 1u;
+            mbar_wait(aux_bar(ab), (aux_count >> 1) & 1u);
+            aux_addr = epi_base + kAuxOff + ab * BOX_BYTES;
+          }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t r[32];
+            tmem_ld_x32(taddr + uint32_t(j * 64 + h * 32), r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int ch = h * 4 + i;
+              const uint32_t off = swz(row, ch);
+              float v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[i * 8 + e]);
+              if constexpr (EPI == EPI_STORE) {
+                sts128(out0 + off, make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
+                                              pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7])));
+              } else if constexpr (EPI == EPI_MUL) {
+                const uint4 g = lds128(aux_addr + off);
+                const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+                uint32_t o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  o[e] = pack_bf16(round_bf16(v[2 * e]) * bf16_lo(gw[e]), round_bf16(v[2 * e + 1]) * bf16_hi(gw[e]));
+                sts128(out0 + off, make_uint4(o[0], o[1], o[2], o[3]));
+              } else {  // EPI_GELU2
+                float a[8], g[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const float u = round_bf16(v[e]);
+                  a[e] = gelu_erf(u);
+                  g[e] = gelu_erf_grad(u);
+                  const int col = n0 + j * 64 + ch * 8 + e;
+                  if (col == args.ones_col) { a[e] = 1.0f; g[e] = 0.0f; }
+                }
+                sts128(out0 + off, make_uint4(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]),
+                                              pack_bf16(a[4], a[5]), pack_bf16(a[6], a[7])));
+                sts128(out0 + BOX_BYTES + off, make_uint4(pack_bf16(g[0], g[1]), pack_bf16(g[2], g[3]),
+                                                          pack_bf16(g[4], g[5]), pack_bf16(g[6], g[7])));
+              }
+            }
+          }
+          if (j == NBOX - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+          }
+          fence_proxy_async();
+          named_bar_sync(1, GEMM_EPI_THREADS);
+          if (elected) {
+            tma_store_2d(&tmC, out0, n0 + j * 64, m0);
+            if constexpr (EPI == EPI_GELU2) tma_store_2d(&tmC2, out0 + BOX_BYTES, n0 + j * 64, m0);
+            tma_store_commit();
+          }
+          ++box_counter;
+          if constexpr (EPI == EPI_MUL) ++aux_count;
+        }
+      } else {
+        // ---------------------------------------------------------- full-row epilogues (BN covers the row)
+        const uint32_t T0 = epi_base;                      // RES_LN: residual -> v ; LNBWD: x (LN input)
+        const uint32_t T1 = epi_base + NBOX * BOX_BYTES;   // RES_LN: LN output   ; LNBWD: dres -> out
+        const float inv_n = 1.0f / float(args.n_real);
+        mbar_wait(aux_bar(0), aux_count & 1u);
+        ++aux_count;
+        if constexpr (EPI == EPI_RES_LN) {
+          float sum = 0.f;
+#pragma unroll 1
+          for (int c32 = 0; c32 < BN / 32; ++c32) {
+            uint32_t r[32];
+            tmem_ld_x32(taddr + uint32_t(c32 * 32), r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int c = c32 * 32 + i * 8;
+              const uint32_t addr = T0 + (c >> 6) * BOX_BYTES + swz(row, (c & 63) >> 3);
+              const uint4 rv = lds128(addr);
+              const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+              uint32_t o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float v0 = round_bf16(round_bf16(__uint_as_float(r[i * 8 + 2 * e])) + bf16_lo(rw[e]));
+                const float v1 = round_bf16(round_bf16(__uint_as_float(r[i * 8 + 2 * e + 1])) + bf16_hi(rw[e]));
+                sum += v0 + v1;
+                o[e] = pack_bf16(v0, v1);
+              }
+              sts128(addr, make_uint4(o[0], o[1], o[2], o[3]));
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+          const float mean = sum * inv_n;
+          float var = 0.f;
+#pragma unroll 1
+          for (int c = 0; c < BN; c += 8) {
+            const uint4 xv = lds128(T0 + (c >> 6) * BOX_BYTES + swz(row, (c & 63) >> 3));
+            const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float d0 = bf16_lo(xw[e]) - mean, d1 = bf16_hi(xw[e]) - mean;
+              if (c + 2 * e < args.n_real) var += d0 * d0;
+              if (c + 2 * e + 1 < args.n_real) var += d1 * d1;
+            }
+          }
+          const float rstd = rsqrtf(var * inv_n + args.eps);
+          if (args.stats != nullptr) {
+            reinterpret_cast<float2*>(args.stats)[m0 + row] = make_float2(mean, rstd);
+          }
+          fence_proxy_async();
+          named_bar_sync(1, GEMM_EPI_THREADS);
+          if (elected) {
+            for (int b = 0; b < NBOX; ++b) tma_store_2d(&tmC, T0 + b * BOX_BYTES, n0 + b * 64, m0);
+            tma_store_commit();
+          }
+#pragma unroll 1
+          for (int c = 0; c < BN; c += 8) {
+            const uint32_t boff = (c >> 6) * BOX_BYTES + swz(row, (c & 63) >> 3);
+            const uint4 xv = lds128(T0 + boff);
+            const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+            float y[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int cc = c + e;
+              const float x = (e & 1) ? bf16_hi(xw[e >> 1]) : bf16_lo(xw[e >> 1]);
+              float o = (x - mean) * rstd * s_gamma[cc & 255] + s_beta[cc & 255];
+              if (cc >= args.n_real) o = (cc == args.ones_col) ? 1.0f : 0.0f;
+              y[e] = o;
+            }
+            sts128(T1 + boff, make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]),
+                                         pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7])));
+          }
+          fence_proxy_async();
+          named_bar_sync(1, GEMM_EPI_THREADS);
+          if (elected) {
+            for (int b = 0; b < NBOX; ++b) tma_store_2d(&tmC2, T1 + b * BOX_BYTES, n0 + b * 64, m0);
+            tma_store_commit();
+            tma_store_wait_read<0>();
+            if (next_tile < num_tiles) {
+              const int nm0 = (next_tile / n_tiles) * GEMM_BM, nn0 = (next_tile % n_tiles) * BN;
+              mbar_arrive_expect_tx(aux_bar(0), NBOX * BOX_BYTES);
+              for (int b = 0; b < NBOX; ++b) tma_load_2d(T0 + b * BOX_BYTES, &tmX1, aux_bar(0), nn0 + b * 64, nm0);
+            }
+          }
+        } else {  // EPI_LNBWD
+          const float2 st = reinterpret_cast<const float2*>(args.stats)[m0 + row];
+          const float mean = st.x, rstd = st.y;
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+          for (int c32 = 0; c32 < BN / 32; ++c32) {
+            uint32_t r[32];
+            tmem_ld_x32(taddr + uint32_t(c32 * 32), r);
+            tmem_ld_wait();
+            float pg[32], pb[32];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int c = c32 * 32 + i * 8;
+              const uint4 xv = lds128(T0 + (c >> 6) * BOX_BYTES + swz(row, (c & 63) >> 3));
+              const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int cc = c + e;
+                const float x = (e & 1) ? bf16_hi(xw[e >> 1]) : bf16_lo(xw[e >> 1]);
+                const float xhat = (x - mean) * rstd;
+                float dxn = round_bf16(__uint_as_float(r[i * 8 + e]));
+                if (cc >= args.n_real) dxn = 0.f;
+                const float dxh = dxn * s_gamma[cc & 255];
+                s1 += dxh;
+                s2 += dxh * xhat;
+                pg[i * 8 + e] = dxn * xhat;
+                pb[i * 8 + e] = dxn;
+              }
+            }
+            const float cg = warp_colsum32(pg, lane);
+            const float cb = warp_colsum32(pb, lane);
+#pragma unroll
+            for (int k = 0; k < BN / 32; ++k)
+              if (k == c32) { acc_g[k] += cg; acc_b[k] += cb; }
+          }
+          const float c1 = s1 * inv_n, c2 = s2 * inv_n;
+#pragma unroll 1
+          for (int c32 = 0; c32 < BN / 32; ++c32) {
+            uint32_t r[32];
+            tmem_ld_x32(taddr + uint32_t(c32 * 32), r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int c = c32 * 32 + i * 8;
+              const uint32_t boff = (c >> 6) * BOX_BYTES + swz(row, (c & 63) >> 3);
+              const uint4 xv = lds128(T0 + boff);
+              const uint4 dv = lds128(T1 + boff);
+              const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+              const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w};
+              float o[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int cc = c + e;
+                const float x = (e & 1) ? bf16_hi(xw[e >> 1]) : bf16_lo(xw[e >> 1]);
+                const float dres = (e & 1) ? bf16_hi(dw[e >> 1]) : bf16_lo(dw[e >> 1]);
+                const float xhat = (x - mean) * rstd;
+                const float dxn = round_bf16(__uint_as_float(r[i * 8 + e]));
+                const float dx = rstd * (dxn * s_gamma[cc & 255] - c1 - xhat * c2);
+                o[e] = (cc < args.n_real) ? (dres + round_bf16(dx)) : 0.f;
+              }
+              sts128(T1 + boff, make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]),
+                                           pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7])));
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+          fence_proxy_async();
+          named_bar_sync(1, GEMM_EPI_THREADS);
+          if (elected) {
+            for (int b = 0; b < NBOX; ++b) tma_store_2d(&tmC, T1 + b * BOX_BYTES, n0 + b * 64, m0);
+            tma_store_commit();
+            tma_store_wait_read<0>();
+            if (next_tile < num_tiles) {
+              const int nm0 = (next_tile / n_tiles) * GEMM_BM, nn0 = (next_tile % n_tiles) * BN;
+              mbar_arrive_expect_tx(aux_bar(0), 2 * NBOX * BOX_BYTES);
+              for (int b = 0; b < NBOX; ++b) tma_load_2d(T0 + b * BOX_BYTES, &tmX1, aux_bar(0), nn0 + b * 64, nm0);
+              for (int b = 0; b < NBOX; ++b) tma_load_2d(T1 + b * BOX_BYTES, &tmX2, aux_bar(0), nn0 + b * 64, nm0);
+            }
+          }
+        }
+        // all epilogue threads must not touch T0/T1 of the next tile before the elected thread has
+        // re-armed them; the aux mbarrier wait at the top of the next iteration provides that order,
+        // but the *writes* of this iteration must be complete first:
+        named_bar_sync(1, GEMM_EPI_THREADS);
+      }
+    }
+    if constexpr (EPI == EPI_LNBWD) {
+      // per-CTA column sums: 4 warps -> smem (re-using the idle tile buffers) -> one row of partials per CTA
+      float* s_part = reinterpret_cast<float*>(smem_raw + (epi_base - smem_u32(smem_raw)));  // [4][2][BN]
+#pragma unroll
+      for (int k = 0; k < BN / 32; ++k) {
+        s_part[(q * 2 + 0) * BN + k * 32 + lane] = acc_g[k];
+        s_part[(q * 2 + 1) * BN + k * 32 + lane] = acc_b[k];
+      }
+      named_bar_sync(1, GEMM_EPI_THREADS);
+      const int e = threadIdx.x - 64;
+      for (int i = e; i < 2 * BN; i += GEMM_EPI_THREADS) {
+        const int w = i / BN, c = i % BN;
+        args.partials[(size_t(blockIdx.x) * 2 + w) * BN + c] =
+            s_part[(0 * 2 + w) * BN + c] + s_part[(1 * 2 + w) * BN + c] + s_part[(2 * 2 + w) * BN + c] +
+            s_part[(3 * 2 + w) * BN + c];
+      }
+    }
+    if (elected) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace srk

@@ -54,13 +54,102 @@ int srk_gemm_grid(int M, int N);
 
 /* dW[Ca,Cb] (fp32) = sum_t A[t,ca] * B[t,cb] over T tokens: tcgen05 GEMM with MN-major operands.
  * Replaces autograd's weight/bias gradient of nn.Linear (same lines as above).
- * Cb in {64,128,192,256}; T % (64*splits) == 0; workspace >= splits*ceil(Ca/128)*128*Cb floats;
+ * Cb in {64,128,192,256}; T % 64 == 0, 1 <= splits <= T/64; workspace >= splits*ceil(Ca/128)*128*Cb floats;
  * out is [ceil(Ca/128)*128, Cb] fp32 (rows >= Ca are zero). */
 int srk_gemm_wgrad(int T, int Ca, int Cb, const void* A, int lda, const void* B, int ldb, float* workspace,
                    int splits, float* out, void* stream);
 /* debug variant with explicit UMMA descriptor byte offsets (used once to validate the layout on hardware) */
 int srk_gemm_wgrad_dbg(int T, int Ca, int Cb, const void* A, int lda, const void* B, int ldb, float* workspace,
                        int splits, float* out, int lbo_bytes, int sbo_bytes, void* stream);
+
+/* ======================================================================================================
+ * Swin / HAT transformer-block level API (what the mirrored nn.Modules call).
+ * ====================================================================================================== */
+
+typedef struct SrkBlockDims {
+  int C;      /* real channels (embed_dim: 180)                                  */
+  int Cp;     /* padded channels (192); column C of normalised activations is 1.0 */
+  int heads;  /* 6                                                               */
+  int dh;     /* real head dim (30)                                              */
+  int ds;     /* padded head slot (32)                                           */
+  int hidden; /* MLP hidden (720)                                                */
+  int Hp;     /* padded hidden (768); column `hidden` of the activation is 1.0    */
+} SrkBlockDims;
+
+typedef struct SrkGeom { int B, H, W, ws, shift; } SrkGeom; /* tokens T = B*H*W, row-major (b,y,x) */
+
+/* fp32 master parameters of one block, reference shapes (SwinTransformerBlock, architecture_swin.py:113-121) */
+typedef struct SrkBlockParams {
+  const float *norm1_w, *norm1_b, *rpb_table, *qkv_w, *qkv_b, *proj_w, *proj_b, *norm2_w, *norm2_b, *fc1_w, *fc1_b,
+      *fc2_w, *fc2_b;
+} SrkBlockParams;
+typedef struct SrkBlockGrads {
+  float *norm1_w, *norm1_b, *rpb_table, *qkv_w, *qkv_b, *proj_w, *proj_b, *norm2_w, *norm2_b, *fc1_w, *fc1_b, *fc2_w,
+      *fc2_b;
+} SrkBlockGrads;
+/* bf16 GEMM operands derived from the parameters (see srk_block_weight_elems for sizes) */
+typedef struct SrkBlockWeights { void *qkv_f, *qkv_t, *proj_f, *proj_t, *fc1_f, *fc1_t, *fc2_f, *fc2_t; } SrkBlockWeights;
+
+/* activations of one block (all bf16 token-major unless noted); the forward fills qkv..stats_out */
+typedef struct SrkBlockActs {
+  const void* x_in;  /* [T,Cp] residual stream entering the block                     */
+  const void* xn1;   /* [T,Cp] LayerNorm1(x_in) (+ ones column)                       */
+  const float* stats1; /* [T,2] mean,rstd of LayerNorm1 (needed by the backward only)  */
+  void* qkv;         /* [T,3*heads*ds]                                                */
+  void* ao;          /* [T,heads*ds] attention output before proj                     */
+  void* x_mid;       /* [T,Cp] x_in + proj(ao)                                        */
+  void* xn2;         /* [T,Cp] LayerNorm2(x_mid)                                      */
+  float* stats2;     /* [T,2]                                                         */
+  void* act;         /* [T,Hp] gelu(fc1)                                              */
+  void* dact;        /* [T,Hp] gelu'(fc1)                                             */
+  void* x_out;       /* [T,Cp] x_mid + fc2(act)                                       */
+  void* xn_out;      /* [T,Cp] LayerNorm_next(x_out): next block's norm1 or the model's final norm */
+  float* stats_out;  /* [T,2]                                                         */
+} SrkBlockActs;
+
+typedef struct SrkBlockScratch { /* backward scratch, caller-owned, reusable across blocks */
+  void* d_act;     /* [T,Hp]  bf16  dU                                   */
+  void* d_ao;      /* [T,heads*ds] bf16                                  */
+  void* d_qkv;     /* [T,3*heads*ds] bf16                                */
+  void* g_mid;     /* [T,Cp] bf16 gradient at x_mid                      */
+  float* wg_ws;    /* srk_block_bwd_scratch_floats(...) floats           */
+} SrkBlockScratch;
+
+/* number of bf16 elements in the 8 operand buffers of SrkBlockWeights, in struct order */
+void srk_block_weight_elems(const SrkBlockDims* d, long long out[8]);
+/* floats needed for SrkBlockScratch.wg_ws */
+long long srk_block_bwd_scratch_floats(const SrkBlockDims* d, const SrkGeom* g);
+
+/* params -> bf16 operands (bias folding, head padding, q pre-scaling, transposes for dgrad) */
+int srk_block_prep_weights(const SrkBlockDims* d, const SrkBlockParams* p, const SrkBlockWeights* w, void* stream);
+
+/* Forward of one SwinTransformerBlock (architecture_swin.py:123-151) given x_in and xn1 = LN1(x_in).
+ * next_norm_w/b: affine of the LayerNorm that consumes x_out (next block's norm1, or SwinIR.norm :247). */
+int srk_swin_block_fwd(const SrkBlockDims* d, const SrkGeom* g, const SrkBlockWeights* w, const SrkBlockParams* p,
+                       const float* next_norm_w, const float* next_norm_b, const SrkBlockActs* a, void* stream);
+/* Backward: g_out = dL/dx_out [T,Cp] bf16 -> g_in = dL/dx_in [T,Cp] bf16 and all 13 parameter gradients
+ * (written, or accumulated when accumulate != 0). */
+int srk_swin_block_bwd(const SrkBlockDims* d, const SrkGeom* g, const SrkBlockWeights* w, const SrkBlockParams* p,
+                       const SrkBlockActs* a, const void* g_out, const SrkBlockScratch* s, void* g_in,
+                       const SrkBlockGrads* grads, int accumulate, void* stream);
+
+/* Window attention core on packed qkv (shift/partition/reverse as address arithmetic), ws == 8.
+ * Replaces architecture_swin.py:27-37 (partition/reverse), :130-146 (roll), :75-93 (attention math). */
+int srk_win_attn_fwd(const SrkGeom* g, int heads, const void* qkv, int ld_qkv, const float* rpb_table, void* out,
+                     int ld_out, int ones_col, void* stream);
+/* dbias_ws: srk_win_attn_bwd_ws_floats(heads) floats; d_rpb_table [225,heads] written if non-NULL */
+int srk_win_attn_bwd(const SrkGeom* g, int heads, const void* qkv, int ld_qkv, const float* rpb_table,
+                     const void* d_out, int ld_out, void* d_qkv, float* dbias_ws, float* d_rpb_table, void* stream);
+long long srk_win_attn_bwd_ws_floats(int heads);
+
+/* Stand-alone LayerNorm over token-major bf16 rows (nn.LayerNorm, architecture_swin.py:113,119,221). */
+int srk_layernorm_fwd(const void* x, int ldx, void* y, int ldy, float* stats, const float* gamma, const float* beta,
+                      int rows, int C, int Cp, int ones_col, float eps, void* stream);
+/* part_ws: srk_layernorm_bwd_ws_floats(Cp) floats */
+int srk_layernorm_bwd(const void* dy, int lddy, const void* x, int ldx, const float* stats, const float* gamma,
+                      const void* dres, int lddres, void* dx, int lddx, float* part_ws, float* dgamma, float* dbeta,
+                      int rows, int C, int Cp, void* stream);
+long long srk_layernorm_bwd_ws_floats(int Cp);
 
 #ifdef __cplusplus
 }

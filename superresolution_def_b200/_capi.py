@@ -125,3 +125,139 @@ def gemm_wgrad(A, B, workspace, splits, out, dbg=None):
         rc = _gemm_wgrad_dbg(T, Ca, Cb, _ptr(A), _ld(A), _ptr(B), _ld(B), _ptr(workspace), splits, _ptr(out),
                              dbg[0], dbg[1], _stream())
     _check(rc, "srk_gemm_wgrad")
+
+
+# ---------------------------------------------------------------------------------------------------
+# Block-level API (include/srk.h, second half)
+# ---------------------------------------------------------------------------------------------------
+from ctypes import c_longlong  # noqa: E402
+
+
+class SrkBlockDims(Structure):
+    _fields_ = [(n, c_int) for n in ("C", "Cp", "heads", "dh", "ds", "hidden", "Hp")]
+
+
+class SrkGeom(Structure):
+    _fields_ = [(n, c_int) for n in ("B", "H", "W", "ws", "shift")]
+
+
+PARAM_NAMES = ("norm1_w", "norm1_b", "rpb_table", "qkv_w", "qkv_b", "proj_w", "proj_b", "norm2_w", "norm2_b",
+               "fc1_w", "fc1_b", "fc2_w", "fc2_b")
+WEIGHT_NAMES = ("qkv_f", "qkv_t", "proj_f", "proj_t", "fc1_f", "fc1_t", "fc2_f", "fc2_t")
+ACT_NAMES = ("x_in", "xn1", "stats1", "qkv", "ao", "x_mid", "xn2", "stats2", "act", "dact", "x_out", "xn_out",
+             "stats_out")
+SCRATCH_NAMES = ("d_act", "d_ao", "d_qkv", "g_mid", "wg_ws")
+
+
+class SrkBlockParams(Structure):
+    _fields_ = [(n, c_void_p) for n in PARAM_NAMES]
+
+
+class SrkBlockGrads(Structure):
+    _fields_ = [(n, c_void_p) for n in PARAM_NAMES]
+
+
+class SrkBlockWeights(Structure):
+    _fields_ = [(n, c_void_p) for n in WEIGHT_NAMES]
+
+
+class SrkBlockActs(Structure):
+    _fields_ = [(n, c_void_p) for n in ACT_NAMES]
+
+
+class SrkBlockScratch(Structure):
+    _fields_ = [(n, c_void_p) for n in SCRATCH_NAMES]
+
+
+lib.srk_block_weight_elems.restype = None
+lib.srk_block_weight_elems.argtypes = [POINTER(SrkBlockDims), POINTER(c_longlong * 8)]
+lib.srk_block_bwd_scratch_floats.restype = c_longlong
+lib.srk_block_bwd_scratch_floats.argtypes = [POINTER(SrkBlockDims), POINTER(SrkGeom)]
+lib.srk_win_attn_bwd_ws_floats.restype = c_longlong
+lib.srk_win_attn_bwd_ws_floats.argtypes = [c_int]
+lib.srk_layernorm_bwd_ws_floats.restype = c_longlong
+lib.srk_layernorm_bwd_ws_floats.argtypes = [c_int]
+_block_prep = _sig("srk_block_prep_weights", [POINTER(SrkBlockDims), POINTER(SrkBlockParams), POINTER(SrkBlockWeights),
+                                              c_void_p])
+_block_fwd = _sig("srk_swin_block_fwd", [POINTER(SrkBlockDims), POINTER(SrkGeom), POINTER(SrkBlockWeights),
+                                         POINTER(SrkBlockParams), c_void_p, c_void_p, POINTER(SrkBlockActs), c_void_p])
+_block_bwd = _sig("srk_swin_block_bwd", [POINTER(SrkBlockDims), POINTER(SrkGeom), POINTER(SrkBlockWeights),
+                                         POINTER(SrkBlockParams), POINTER(SrkBlockActs), c_void_p,
+                                         POINTER(SrkBlockScratch), c_void_p, POINTER(SrkBlockGrads), c_int, c_void_p])
+_attn_fwd = _sig("srk_win_attn_fwd", [POINTER(SrkGeom), c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
+                                      c_void_p])
+_attn_bwd = _sig("srk_win_attn_bwd", [POINTER(SrkGeom), c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                                      c_void_p, c_void_p, c_void_p])
+_ln_fwd = _sig("srk_layernorm_fwd", [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                     c_int, c_int, c_float, c_void_p])
+_ln_bwd = _sig("srk_layernorm_bwd", [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                     c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p])
+
+
+def block_weight_elems(dims: SrkBlockDims):
+    out = (c_longlong * 8)()
+    lib.srk_block_weight_elems(ctypes.byref(dims), ctypes.byref(out))
+    return list(out)
+
+
+def block_bwd_scratch_floats(dims: SrkBlockDims, geom: SrkGeom) -> int:
+    return int(lib.srk_block_bwd_scratch_floats(ctypes.byref(dims), ctypes.byref(geom)))
+
+
+def _fill(struct_cls, names, tensors: dict):
+    s = struct_cls()
+    for n in names:
+        t = tensors.get(n)
+        setattr(s, n, _ptr(t) if t is not None else None)
+    return s
+
+
+def block_prep_weights(dims, params: dict, weights: dict):
+    rc = _block_prep(ctypes.byref(dims), ctypes.byref(_fill(SrkBlockParams, PARAM_NAMES, params)),
+                     ctypes.byref(_fill(SrkBlockWeights, WEIGHT_NAMES, weights)), _stream())
+    _check(rc, "srk_block_prep_weights")
+
+
+def swin_block_fwd(dims, geom, weights: dict, params: dict, next_norm_w, next_norm_b, acts: dict):
+    rc = _block_fwd(ctypes.byref(dims), ctypes.byref(geom), ctypes.byref(_fill(SrkBlockWeights, WEIGHT_NAMES, weights)),
+                    ctypes.byref(_fill(SrkBlockParams, PARAM_NAMES, params)), _ptr(next_norm_w), _ptr(next_norm_b),
+                    ctypes.byref(_fill(SrkBlockActs, ACT_NAMES, acts)), _stream())
+    _check(rc, "srk_swin_block_fwd")
+
+
+def swin_block_bwd(dims, geom, weights: dict, params: dict, acts: dict, g_out, scratch: dict, g_in, grads: dict,
+                   accumulate=False):
+    rc = _block_bwd(ctypes.byref(dims), ctypes.byref(geom), ctypes.byref(_fill(SrkBlockWeights, WEIGHT_NAMES, weights)),
+                    ctypes.byref(_fill(SrkBlockParams, PARAM_NAMES, params)),
+                    ctypes.byref(_fill(SrkBlockActs, ACT_NAMES, acts)), _ptr(g_out),
+                    ctypes.byref(_fill(SrkBlockScratch, SCRATCH_NAMES, scratch)), _ptr(g_in),
+                    ctypes.byref(_fill(SrkBlockGrads, PARAM_NAMES, grads)), int(accumulate), _stream())
+    _check(rc, "srk_swin_block_bwd")
+
+
+def win_attn_fwd(geom, heads, qkv, rpb_table, out, ones_col=-1):
+    rc = _attn_fwd(ctypes.byref(geom), heads, _ptr(qkv), _ld(qkv), _ptr(rpb_table), _ptr(out), _ld(out), ones_col,
+                   _stream())
+    _check(rc, "srk_win_attn_fwd")
+
+
+def win_attn_bwd(geom, heads, qkv, rpb_table, d_out, d_qkv, d_rpb_table=None):
+    ws = torch.empty(int(lib.srk_win_attn_bwd_ws_floats(heads)), device=qkv.device, dtype=torch.float32)
+    rc = _attn_bwd(ctypes.byref(geom), heads, _ptr(qkv), _ld(qkv), _ptr(rpb_table), _ptr(d_out), _ld(d_out),
+                   _ptr(d_qkv), _ptr(ws), _ptr(d_rpb_table), _stream())
+    _check(rc, "srk_win_attn_bwd")
+
+
+def layernorm_fwd(x, y, stats, gamma, beta, C, ones_col=-1, eps=1e-5):
+    rows, Cp = x.shape
+    rc = _ln_fwd(_ptr(x), _ld(x), _ptr(y), _ld(y), _ptr(stats), _ptr(gamma), _ptr(beta), rows, C, Cp, ones_col, eps,
+                 _stream())
+    _check(rc, "srk_layernorm_fwd")
+
+
+def layernorm_bwd(dy, x, stats, gamma, dres, dx, dgamma, dbeta, C):
+    rows, Cp = x.shape
+    ws = torch.empty(int(lib.srk_layernorm_bwd_ws_floats(Cp)), device=x.device, dtype=torch.float32)
+    rc = _ln_bwd(_ptr(dy), _ld(dy), _ptr(x), _ld(x), _ptr(stats), _ptr(gamma), _ptr(dres), _ld(dres) if dres is not None else 0,
+                 _ptr(dx), _ld(dx), _ptr(ws), _ptr(dgamma), _ptr(dbeta), rows, C, Cp, _stream())
+    _check(rc, "srk_layernorm_bwd")

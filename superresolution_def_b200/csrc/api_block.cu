@@ -1,0 +1,296 @@
+// api_block.cu — C-ABI entry points at Swin-block granularity: weight prep, block forward / backward
+// (a fixed sequence of the tcgen05 GEMMs, the window-attention core and the small aux kernels), plus the
+// stand-alone window-attention and LayerNorm ops.  Host code only orchestrates launches on the caller's
+// stream; it never allocates or synchronises.
+#include "attn_ws8.cuh"
+#include "block_aux.cuh"
+#include "srk_host.h"
+
+using namespace srk;
+
+namespace {
+
+inline BlockDims to_dims(const SrkBlockDims* d) {
+  BlockDims o;
+  o.C = d->C; o.Cp = d->Cp; o.heads = d->heads; o.dh = d->dh; o.ds = d->ds; o.hidden = d->hidden; o.Hp = d->Hp;
+  return o;
+}
+
+int check_dims(const SrkBlockDims* d, const SrkGeom* g) {
+  if (!d) return fail(SRK_ERR_ARG, "null dims");
+  if (d->Cp != 192 || d->heads * d->ds != 192 || d->ds != 32)
+    return fail(SRK_ERR_UNSUPPORTED, "block kernels are specialised for Cp == heads*ds == 192, ds == 32");
+  if (d->C >= d->Cp || d->dh >= d->ds || d->hidden >= d->Hp || d->Hp % 256 != 0 || d->C != d->heads * d->dh)
+    return fail(SRK_ERR_UNSUPPORTED, "need C < Cp, dh < ds, hidden < Hp, Hp % 256 == 0, C == heads*dh");
+  if (g) {
+    if (g->ws != 8) return fail(SRK_ERR_UNSUPPORTED, "window attention core is specialised for ws == 8");
+    if (g->H % 8 || g->W % 8 || g->shift < 0 || g->shift >= 8) return fail(SRK_ERR_ARG, "bad geometry");
+    if ((long long)g->B * g->H * g->W % 128 != 0) return fail(SRK_ERR_ARG, "B*H*W must be a multiple of 128");
+  }
+  return SRK_OK;
+}
+
+int wgrad_splits(int T, int ca_tiles) {
+  int s = num_sms() / ca_tiles;
+  const int iters = T / 64;
+  if (s > iters) s = iters;
+  return s < 1 ? 1 : s;
+}
+
+struct WsLayout {  // offsets (floats) into SrkBlockScratch.wg_ws
+  long long partials, ext_qkv, ext_proj, ext_fc1, ext_fc2, ln1, ln2, rpb, total;
+  int rpb_gx, ln_grid;
+};
+
+int attn_bwd_gx(int nwin, int heads) {
+  int gx = num_sms() * 3 / heads;
+  if (gx > nwin) gx = nwin;
+  return gx < 1 ? 1 : gx;
+}
+int attn_fwd_gx(int nwin, int heads) {
+  int gx = num_sms() * 6 / heads;
+  if (gx > nwin) gx = nwin;
+  return gx < 1 ? 1 : gx;
+}
+
+WsLayout ws_layout(const SrkBlockDims* d, const SrkGeom* g) {
+  WsLayout L{};
+  const int QW = 3 * d->heads * d->ds, AW = d->heads * d->ds;
+  const long long T = (long long)g->B * g->H * g->W;
+  const long long part = (long long)num_sms() * 128 * 256;  // ca_tiles*splits <= num_sms, Cb <= 256
+  long long o = 0;
+  L.partials = o; o += part;
+  L.ext_qkv = o; o += (long long)((QW + 127) / 128 * 128) * d->Cp;
+  L.ext_proj = o; o += (long long)((d->Cp + 127) / 128 * 128) * AW;
+  L.ext_fc1 = o; o += (long long)d->Hp * d->Cp;
+  L.ext_fc2 = o; o += (long long)d->Hp * d->Cp;
+  L.ln_grid = srk_gemm_grid(int(T), d->Cp);
+  L.ln1 = o; o += (long long)L.ln_grid * 2 * d->Cp;
+  L.ln2 = o; o += (long long)L.ln_grid * 2 * d->Cp;
+  L.rpb_gx = attn_bwd_gx(g->B * (g->H / 8) * (g->W / 8), d->heads);
+  L.rpb = o; o += (long long)L.rpb_gx * d->heads * 225;
+  L.total = o;
+  return L;
+}
+
+int launch_attn_fwd(const SrkGeom* g, int heads, const void* qkv, int ld_qkv, const float* table, void* out, int ld_o,
+                    int ones_col, cudaStream_t stream) {
+  AttnArgs a{};
+  a.qkv = static_cast<const __nv_bfloat16*>(qkv);
+  a.out = static_cast<__nv_bfloat16*>(out);
+  a.bias_table = table;
+  a.B = g->B; a.H = g->H; a.W = g->W; a.heads = heads; a.shift = g->shift;
+  a.ld_qkv = ld_qkv; a.ld_o = ld_o; a.ones_col = ones_col;
+  const int nwin = g->B * (g->H / 8) * (g->W / 8);
+  dim3 grid(attn_fwd_gx(nwin, heads), heads);
+  win_attn_ws8_fwd_kernel<<<grid, ATT_THREADS, 0, stream>>>(a);
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+int launch_attn_bwd(const SrkGeom* g, int heads, const void* qkv, int ld_qkv, const float* table, const void* dout,
+                    int ld_o, void* dqkv, float* partials, int gx, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    SRK_CUDA_OK(cudaFuncSetAttribute(win_attn_ws8_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     int(sizeof(AttnBwdSmem))));
+    configured = true;
+  }
+  AttnArgs a{};
+  a.qkv = static_cast<const __nv_bfloat16*>(qkv);
+  a.dout = static_cast<const __nv_bfloat16*>(dout);
+  a.dqkv = static_cast<__nv_bfloat16*>(dqkv);
+  a.bias_table = table;
+  a.dbias_partials = partials;
+  a.B = g->B; a.H = g->H; a.W = g->W; a.heads = heads; a.shift = g->shift;
+  a.ld_qkv = ld_qkv; a.ld_o = ld_o; a.ones_col = -1;
+  dim3 grid(gx, heads);
+  win_attn_ws8_bwd_kernel<<<grid, ATT_THREADS, sizeof(AttnBwdSmem), stream>>>(a);
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+__global__ void rpb_partials_reduce_kernel(const float* __restrict__ part, int nparts, int heads, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // i = t*heads + h (reference layout)
+  if (i >= 225 * heads) return;
+  const int t = i / heads, h = i % heads;
+  float acc = 0.f;
+  for (int k = 0; k < nparts; ++k) acc += part[(size_t(k) * heads + h) * 225 + t];
+  out[i] = acc;
+}
+
+}  // namespace
+
+extern "C" void srk_block_weight_elems(const SrkBlockDims* d, long long out[8]) {
+  const long long QW = 3LL * d->heads * d->ds, AW = 1LL * d->heads * d->ds;
+  out[0] = QW * d->Cp; out[1] = d->Cp * QW;
+  out[2] = d->Cp * AW; out[3] = AW * d->Cp;
+  out[4] = 1LL * d->Hp * d->Cp; out[5] = 1LL * d->Cp * d->Hp;
+  out[6] = 1LL * d->Cp * d->Hp; out[7] = 1LL * d->Hp * d->Cp;
+}
+
+extern "C" long long srk_block_bwd_scratch_floats(const SrkBlockDims* d, const SrkGeom* g) {
+  return ws_layout(d, g).total;
+}
+
+extern "C" int srk_block_prep_weights(const SrkBlockDims* d, const SrkBlockParams* p, const SrkBlockWeights* w,
+                                      void* stream_) {
+  int rc = check_dims(d, nullptr);
+  if (rc) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BlockParamPtrs pp{p->norm1_w, p->norm1_b, p->rpb_table, p->qkv_w, p->qkv_b, p->proj_w, p->proj_b,
+                    p->norm2_w, p->norm2_b, p->fc1_w,     p->fc1_b, p->fc2_w,  p->fc2_b};
+  BlockWeightPtrs ww{static_cast<__nv_bfloat16*>(w->qkv_f),  static_cast<__nv_bfloat16*>(w->qkv_t),
+                     static_cast<__nv_bfloat16*>(w->proj_f), static_cast<__nv_bfloat16*>(w->proj_t),
+                     static_cast<__nv_bfloat16*>(w->fc1_f),  static_cast<__nv_bfloat16*>(w->fc1_t),
+                     static_cast<__nv_bfloat16*>(w->fc2_f),  static_cast<__nv_bfloat16*>(w->fc2_t)};
+  prep_block_weights_kernel<<<296, 256, 0, stream>>>(to_dims(d), pp, ww);
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+extern "C" int srk_swin_block_fwd(const SrkBlockDims* d, const SrkGeom* g, const SrkBlockWeights* w,
+                                  const SrkBlockParams* p, const float* next_norm_w, const float* next_norm_b,
+                                  const SrkBlockActs* a, void* stream) {
+  int rc = check_dims(d, g);
+  if (rc) return rc;
+  const int T = g->B * g->H * g->W;
+  const int QW = 3 * d->heads * d->ds, AW = d->heads * d->ds, Cp = d->Cp, Hp = d->Hp;
+  // qkv = xn1 @ Wqkv^T (+bias via ones column)
+  if ((rc = srk_gemm_tn(SRK_EPI_STORE, T, QW, Cp, a->xn1, Cp, w->qkv_f, Cp, a->qkv, QW, nullptr, 0, nullptr, 0,
+                        nullptr, 0, nullptr, stream)))
+    return rc;
+  // attention core (shift / partition / reverse by address arithmetic); ao[:, dh] = 1 (proj bias column)
+  if ((rc = launch_attn_fwd(g, d->heads, a->qkv, QW, p->rpb_table, a->ao, AW, d->dh, static_cast<cudaStream_t>(stream))))
+    return rc;
+  // x_mid = x_in + proj(ao); xn2 = LN2(x_mid)
+  SrkLnArgs ln2{d->C, d->C, p->norm2_w, p->norm2_b, a->stats2, nullptr, 1e-5f};
+  if ((rc = srk_gemm_tn(SRK_EPI_RES_LN, T, Cp, AW, a->ao, AW, w->proj_f, AW, a->x_mid, Cp, a->xn2, Cp, a->x_in, Cp,
+                        nullptr, 0, &ln2, stream)))
+    return rc;
+  // act = gelu(fc1(xn2)), dact = gelu'(.)
+  SrkLnArgs ge{Hp, d->hidden, nullptr, nullptr, nullptr, nullptr, 0.f};
+  if ((rc = srk_gemm_tn(SRK_EPI_GELU2, T, Hp, Cp, a->xn2, Cp, w->fc1_f, Cp, a->act, Hp, a->dact, Hp, nullptr, 0, nullptr,
+                        0, &ge, stream)))
+    return rc;
+  // x_out = x_mid + fc2(act); xn_out = LN_next(x_out)
+  SrkLnArgs lnn{d->C, d->C, next_norm_w, next_norm_b, a->stats_out, nullptr, 1e-5f};
+  if ((rc = srk_gemm_tn(SRK_EPI_RES_LN, T, Cp, Hp, a->act, Hp, w->fc2_f, Hp, a->x_out, Cp, a->xn_out, Cp, a->x_mid, Cp,
+                        nullptr, 0, &lnn, stream)))
+    return rc;
+  return SRK_OK;
+}
+
+extern "C" int srk_swin_block_bwd(const SrkBlockDims* d, const SrkGeom* g, const SrkBlockWeights* w,
+                                  const SrkBlockParams* p, const SrkBlockActs* a, const void* g_out,
+                                  const SrkBlockScratch* s, void* g_in, const SrkBlockGrads* grads, int accumulate,
+                                  void* stream_) {
+  int rc = check_dims(d, g);
+  if (rc) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int T = g->B * g->H * g->W;
+  const int QW = 3 * d->heads * d->ds, AW = d->heads * d->ds, Cp = d->Cp, Hp = d->Hp;
+  const WsLayout L = ws_layout(d, g);
+  float* ws = s->wg_ws;
+
+  // dU = (g_out @ W2) * gelu'(u)
+  if ((rc = srk_gemm_tn(SRK_EPI_MUL, T, Hp, Cp, g_out, Cp, w->fc2_t, Cp, s->d_act, Hp, nullptr, 0, a->dact, Hp, nullptr,
+                        0, nullptr, stream_)))
+    return rc;
+  // dW2^T (+db2 in row `hidden`) = act^T @ g_out
+  const int s_fc = wgrad_splits(T, Hp / 128);
+  if ((rc = srk_gemm_wgrad(T, Hp, Cp, a->act, Hp, g_out, Cp, ws + L.partials, s_fc, ws + L.ext_fc2, stream_))) return rc;
+  // g_mid = g_out + LN2bwd(dU @ W1)
+  SrkLnArgs ln2{d->C, -1, p->norm2_w, nullptr, a->stats2, ws + L.ln2, 1e-5f};
+  if ((rc = srk_gemm_tn(SRK_EPI_LNBWD, T, Cp, Hp, s->d_act, Hp, w->fc1_t, Hp, s->g_mid, Cp, nullptr, 0, a->x_mid, Cp,
+                        g_out, Cp, &ln2, stream_)))
+    return rc;
+  // dW1 (+db1 in column C) = dU^T @ xn2
+  if ((rc = srk_gemm_wgrad(T, Hp, Cp, s->d_act, Hp, a->xn2, Cp, ws + L.partials, s_fc, ws + L.ext_fc1, stream_))) return rc;
+  // d_ao = g_mid @ Wproj
+  if ((rc = srk_gemm_tn(SRK_EPI_STORE, T, AW, Cp, s->g_mid, Cp, w->proj_t, Cp, s->d_ao, AW, nullptr, 0, nullptr, 0,
+                        nullptr, 0, nullptr, stream_)))
+    return rc;
+  // dWproj (+dbproj in column dh) = g_mid^T @ ao
+  if ((rc = srk_gemm_wgrad(T, Cp, AW, s->g_mid, Cp, a->ao, AW, ws + L.partials, wgrad_splits(T, (Cp + 127) / 128),
+                           ws + L.ext_proj, stream_)))
+    return rc;
+  // attention backward -> d_qkv, rpb-table partials
+  if ((rc = launch_attn_bwd(g, d->heads, a->qkv, QW, p->rpb_table, s->d_ao, AW, s->d_qkv, ws + L.rpb, L.rpb_gx, stream)))
+    return rc;
+  // g_in = g_mid + LN1bwd(d_qkv @ Wqkv)
+  SrkLnArgs ln1{d->C, -1, p->norm1_w, nullptr, const_cast<float*>(a->stats1), ws + L.ln1, 1e-5f};
+  if ((rc = srk_gemm_tn(SRK_EPI_LNBWD, T, Cp, QW, s->d_qkv, QW, w->qkv_t, QW, g_in, Cp, nullptr, 0, a->x_in, Cp,
+                        s->g_mid, Cp, &ln1, stream_)))
+    return rc;
+  // dWqkv (+dbqkv in column C) = d_qkv^T @ xn1
+  if ((rc = srk_gemm_wgrad(T, QW, Cp, s->d_qkv, QW, a->xn1, Cp, ws + L.partials, wgrad_splits(T, (QW + 127) / 128),
+                           ws + L.ext_qkv, stream_)))
+    return rc;
+  // scatter everything into reference-shaped fp32 gradients
+  UnpackSrc us{ws + L.ext_qkv, ws + L.ext_proj, ws + L.ext_fc1, ws + L.ext_fc2, ws + L.ln1, ws + L.ln2, ws + L.rpb,
+               L.ln_grid, L.rpb_gx, 225};
+  BlockGradPtrs gp{grads->norm1_w, grads->norm1_b, grads->rpb_table, grads->qkv_w, grads->qkv_b, grads->proj_w,
+                   grads->proj_b,  grads->norm2_w, grads->norm2_b,   grads->fc1_w, grads->fc1_b, grads->fc2_w,
+                   grads->fc2_b};
+  unpack_block_grads_kernel<<<296, 256, 0, stream>>>(to_dims(d), us, gp, accumulate ? 1.f : 0.f);
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+extern "C" int srk_win_attn_fwd(const SrkGeom* g, int heads, const void* qkv, int ld_qkv, const float* rpb_table,
+                                void* out, int ld_out, int ones_col, void* stream) {
+  if (!g || g->ws != 8 || g->H % 8 || g->W % 8) return fail(SRK_ERR_UNSUPPORTED, "srk_win_attn_fwd: ws must be 8");
+  if (ld_qkv % 8 || ld_out % 8) return fail(SRK_ERR_ARG, "srk_win_attn_fwd: rows must be 16-byte aligned");
+  return launch_attn_fwd(g, heads, qkv, ld_qkv, rpb_table, out, ld_out, ones_col, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" long long srk_win_attn_bwd_ws_floats(int heads) { return (long long)num_sms() * 3 * 225 + 225LL * heads; }
+
+extern "C" int srk_win_attn_bwd(const SrkGeom* g, int heads, const void* qkv, int ld_qkv, const float* rpb_table,
+                                const void* d_out, int ld_out, void* d_qkv, float* dbias_ws, float* d_rpb_table,
+                                void* stream_) {
+  if (!g || g->ws != 8 || g->H % 8 || g->W % 8) return fail(SRK_ERR_UNSUPPORTED, "srk_win_attn_bwd: ws must be 8");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int gx = attn_bwd_gx(g->B * (g->H / 8) * (g->W / 8), heads);
+  int rc = launch_attn_bwd(g, heads, qkv, ld_qkv, rpb_table, d_out, ld_out, d_qkv, dbias_ws, gx, stream);
+  if (rc) return rc;
+  if (d_rpb_table) {
+    rpb_partials_reduce_kernel<<<(225 * heads + 127) / 128, 128, 0, stream>>>(dbias_ws, gx, heads, d_rpb_table);
+    SRK_CUDA_OK(cudaGetLastError());
+  }
+  return SRK_OK;
+}
+
+extern "C" int srk_layernorm_fwd(const void* x, int ldx, void* y, int ldy, float* stats, const float* gamma,
+                                 const float* beta, int rows, int C, int Cp, int ones_col, float eps, void* stream_) {
+  if (Cp > 256 || C > Cp) return fail(SRK_ERR_UNSUPPORTED, "srk_layernorm_fwd: Cp <= 256");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int wpb = 8;
+  ln_fwd_rows_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(y), ldy, stats, gamma, beta, rows, C, Cp,
+      ones_col, eps);
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+extern "C" long long srk_layernorm_bwd_ws_floats(int Cp) { return (long long)num_sms() * 4 * 2 * Cp; }
+
+extern "C" int srk_layernorm_bwd(const void* dy, int lddy, const void* x, int ldx, const float* stats,
+                                 const float* gamma, const void* dres, int lddres, void* dx, int lddx, float* part_ws,
+                                 float* dgamma, float* dbeta, int rows, int C, int Cp, void* stream_) {
+  if (Cp > 256 || C > Cp) return fail(SRK_ERR_UNSUPPORTED, "srk_layernorm_bwd: Cp <= 256");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int grid = num_sms() * 4;
+  if (grid > (rows + 7) / 8) grid = (rows + 7) / 8;
+  ln_bwd_rows_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(dy), lddy,
+                                               static_cast<const __nv_bfloat16*>(x), ldx, stats, gamma,
+                                               static_cast<const __nv_bfloat16*>(dres), lddres,
+                                               static_cast<__nv_bfloat16*>(dx), lddx, part_ws, rows, C, Cp);
+  SRK_CUDA_OK(cudaGetLastError());
+  if (dgamma && dbeta) {
+    ln_param_grad_reduce_kernel<<<(2 * C + 127) / 128, 128, 0, stream>>>(part_ws, grid, Cp, C, dgamma, dbeta);
+    SRK_CUDA_OK(cudaGetLastError());
+  }
+  return SRK_OK;
+}

@@ -114,8 +114,8 @@ extern "C" int srk_gemm_wgrad_dbg(int T, int Ca, int Cb, const void* A, int lda,
                                   float* workspace, int splits, float* out, int lbo_bytes, int sbo_bytes,
                                   void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (splits <= 0 || T <= 0 || T % (WG_TOK * splits) != 0)
-    return fail(SRK_ERR_ARG, "srk_gemm_wgrad: T must be a multiple of 64*splits");
+  if (splits <= 0 || T <= 0 || T % WG_TOK != 0 || splits > T / WG_TOK)
+    return fail(SRK_ERR_ARG, "srk_gemm_wgrad: T must be a multiple of 64 and 1 <= splits <= T/64");
   if (!A || !B || !workspace || !out) return fail(SRK_ERR_ARG, "srk_gemm_wgrad: null pointer");
   WgradArgs a{};
   a.T = T; a.Ca = Ca; a.Cb = Cb; a.ca_tiles = (Ca + 127) / 128; a.splits = splits; a.partials = workspace;

@@ -1,0 +1,394 @@
+// attn_ws8.cuh — fused (shifted-)window attention core for 8x8 windows (64 tokens), forward + backward.
+//
+// Replaces (reference, models/architecture_swin.py): torch.roll :130-133,143-146; window_partition :27-31;
+// window_reverse :33-37; and inside WindowAttention.forward :75-93 the q@k^T bmm, relative-position-bias
+// gather+add, softmax, attn@v bmm and the head-merge transpose.  Shift / partition / reverse are pure
+// address arithmetic here; S and P never touch HBM.
+//
+// Layouts (token-major, bf16):  qkv [T, 3*heads*32]  (q|k|v, each head padded 30->32 with zeros, q already
+// scaled by head_dim^-0.5 through the projection weights);  out [T, heads*32].
+// This kernel is HBM-bound by construction (32 FLOP/B), so it uses register-resident
+// mma.sync tiles: a 64x64 logit tile fits the register file and needs no TMEM round trip.
+// Grid: (window groups, heads); each CTA keeps one head and walks windows, double-buffering its loads.
+#pragma once
+#include "srk_ptx.cuh"
+
+namespace srk {
+
+struct AttnArgs {
+  const __nv_bfloat16* qkv;   // [T, ld_qkv]
+  const __nv_bfloat16* dout;  // bwd: [T, ld_o] gradient of out
+  __nv_bfloat16* out;         // fwd: [T, ld_o]
+  __nv_bfloat16* dqkv;        // bwd: [T, ld_qkv]
+  const float* bias_table;    // [(2*8-1)^2 = 225][heads] fp32 (reference layout)
+  float* dbias_partials;      // bwd: [gridDim.x][heads][225]
+  int B, H, W, heads, shift;
+  int ld_qkv, ld_o;
+  int ones_col;               // fwd: column of `out` forced to 1.0 (bias-folding column), -1: none
+};
+
+constexpr int ATT_THREADS = 128;
+constexpr int ATT_TILE = 64 * 32 * 2;  // one [64 tokens x 32] bf16 tile (4 KB)
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// [64 x 32] bf16 tile, 64-byte rows, 16-byte chunks XOR-swizzled so ldmatrix is conflict-free.
+__device__ __forceinline__ uint32_t t32_off(int row, int chunk) {
+  return uint32_t(row) * 64u + (uint32_t(chunk ^ ((row >> 1) & 3)) << 4);
+}
+// [64 x 64] bf16 tile, 128-byte rows.
+__device__ __forceinline__ uint32_t t64_off(int row, int chunk) {
+  return uint32_t(row) * 128u + (uint32_t(chunk ^ (row & 7)) << 4);
+}
+
+// token row index (in the un-shifted [B,H,W] token grid) of local token i of window w
+__device__ __forceinline__ int window_token(const AttnArgs& a, int w, int i) {
+  const int nwx = a.W >> 3, nwy = a.H >> 3;
+  const int b = w / (nwx * nwy);
+  const int r = w - b * nwx * nwy;
+  const int wy = r / nwx, wx = r - wy * nwx;
+  int y = wy * 8 + (i >> 3) + a.shift;
+  int x = wx * 8 + (i & 7) + a.shift;
+  if (y >= a.H) y -= a.H;
+  if (x >= a.W) x -= a.W;
+  return (b * a.H + y) * a.W + x;
+}
+
+__device__ __forceinline__ int rel_index(int i, int j) {
+  return ((i >> 3) - (j >> 3) + 7) * 15 + ((i & 7) - (j & 7) + 7);
+}
+
+// S[16 x 64] (this warp's 16 query rows) = Q K^T + bias ; returns fp32 logits in s[nt][4]
+__device__ __forceinline__ void qk_logits(uint32_t q_tile, uint32_t k_tile, const float* s_bias, int r0, int lane,
+                                          float (&s)[8][4]) {
+  uint32_t aq[2][4];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    const int row = r0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+    const int chunk = ks * 2 + (lane >> 4);
+    ldsm_x4(q_tile + t32_off(row, chunk), aq[ks][0], aq[ks][1], aq[ks][2], aq[ks][3]);
+  }
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    uint32_t b0, b1, b2, b3;
+    ldsm_x4(k_tile + t32_off(nt * 8 + (lane & 7), lane >> 3), b0, b1, b2, b3);
+    s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+    mma_bf16(s[nt], aq[0], b0, b1);
+    mma_bf16(s[nt], aq[1], b2, b3);
+    const int i0 = r0 + g, j0 = nt * 8 + 2 * t;
+    s[nt][0] += s_bias[rel_index(i0, j0)];
+    s[nt][1] += s_bias[rel_index(i0, j0 + 1)];
+    s[nt][2] += s_bias[rel_index(i0 + 8, j0)];
+    s[nt][3] += s_bias[rel_index(i0 + 8, j0 + 1)];
+  }
+}
+
+// in-place row softmax of the 16x64 fragment tile (rows g and g+8 of the quad)
+__device__ __forceinline__ void softmax_rows(float (&s)[8][4]) {
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
+    m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
+  }
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+  float l0 = 0.f, l1 = 0.f;
+  constexpr float kLog2e = 1.4426950408889634f;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    s[nt][0] = exp2f((s[nt][0] - m0) * kLog2e);
+    s[nt][1] = exp2f((s[nt][1] - m0) * kLog2e);
+    s[nt][2] = exp2f((s[nt][2] - m1) * kLog2e);
+    s[nt][3] = exp2f((s[nt][3] - m1) * kLog2e);
+    l0 += s[nt][0] + s[nt][1];
+    l1 += s[nt][2] + s[nt][3];
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    s[nt][0] *= i0; s[nt][1] *= i0; s[nt][2] *= i1; s[nt][3] *= i1;
+  }
+}
+
+// O[16 x 32] = A[16 x 64] (bf16 fragments built from fp32 s) * Bt[64 x 32] where Bt is a [key][d] tile
+__device__ __forceinline__ void frag_times_tile(const float (&s)[8][4], uint32_t bt_tile, int lane, float (&o)[4][4]) {
+#pragma unroll
+  for (int n = 0; n < 4; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+#pragma unroll
+  for (int kt = 0; kt < 4; ++kt) {
+    uint32_t a[4];
+    a[0] = pack_bf16(s[2 * kt][0], s[2 * kt][1]);
+    a[1] = pack_bf16(s[2 * kt][2], s[2 * kt][3]);
+    a[2] = pack_bf16(s[2 * kt + 1][0], s[2 * kt + 1][1]);
+    a[3] = pack_bf16(s[2 * kt + 1][2], s[2 * kt + 1][3]);
+    const int row = kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+    for (int np = 0; np < 2; ++np) {
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4_t(bt_tile + t32_off(row, np * 2 + (lane >> 4)), b0, b1, b2, b3);
+      mma_bf16(o[2 * np], a, b0, b1);
+      mma_bf16(o[2 * np + 1], a, b2, b3);
+    }
+  }
+}
+
+// store a [16 x 32] fp32 fragment tile as bf16 into a swizzled t32 tile (rows r0..r0+15)
+__device__ __forceinline__ void store_frag_t32(uint32_t tile, int r0, int lane, const float (&o)[4][4]) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int n = 0; n < 4; ++n) {
+    const uint32_t lo = pack_bf16(o[n][0], o[n][1]);
+    const uint32_t hi = pack_bf16(o[n][2], o[n][3]);
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(tile + t32_off(r0 + g, n) + t * 4), "r"(lo) : "memory");
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(tile + t32_off(r0 + g + 8, n) + t * 4), "r"(hi) : "memory");
+  }
+}
+
+// async-load `ntiles` per-head [64 x 32] tiles of window w: tile k comes from column offset col_off[k] of `src`
+__device__ __forceinline__ void load_window_tiles(const AttnArgs& a, int w, uint32_t dst, const __nv_bfloat16* src0,
+                                                  int ld0, int col0, int ntiles_from_qkv, const __nv_bfloat16* src1,
+                                                  int ld1, int col1) {
+  // qkv tiles: q,k,v at col0 + {0, heads*32, 2*heads*32}
+  const int hw = a.heads * 32;
+  for (int c = threadIdx.x; c < (ntiles_from_qkv + (src1 ? 1 : 0)) * 256; c += ATT_THREADS) {
+    const int tile = c >> 8, rem = c & 255, i = rem >> 2, ch = rem & 3;
+    const int tok = window_token(a, w, i);
+    const __nv_bfloat16* p = (tile < ntiles_from_qkv) ? (src0 + size_t(tok) * ld0 + col0 + tile * hw + ch * 8)
+                                                      : (src1 + size_t(tok) * ld1 + col1 + ch * 8);
+    cp_async16(dst + tile * ATT_TILE + t32_off(i, ch), p);
+  }
+}
+
+// ============================================================================ forward
+__global__ void __launch_bounds__(ATT_THREADS) win_attn_ws8_fwd_kernel(const AttnArgs a) {
+  __shared__ __align__(128) uint8_t s_in[2][3 * ATT_TILE];
+  __shared__ __align__(128) uint8_t s_out[ATT_TILE];
+  __shared__ float s_bias[225];
+  const int h = blockIdx.y;
+  const int nwin = a.B * (a.H >> 3) * (a.W >> 3);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 225; i += ATT_THREADS) s_bias[i] = a.bias_table[i * a.heads + h];
+  const bool ones_here = a.ones_col >= h * 32 && a.ones_col < h * 32 + 32;
+  const int ones_c = a.ones_col - h * 32;
+
+  int w = blockIdx.x;
+  int buf = 0;
+  if (w < nwin) load_window_tiles(a, w, smem_u32(s_in[0]), a.qkv, a.ld_qkv, h * 32, 3, nullptr, 0, 0);
+  cp_async_commit();
+  for (; w < nwin; w += gridDim.x, buf ^= 1) {
+    const int wn = w + gridDim.x;
+    if (wn < nwin) load_window_tiles(a, wn, smem_u32(s_in[buf ^ 1]), a.qkv, a.ld_qkv, h * 32, 3, nullptr, 0, 0);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const uint32_t qt = smem_u32(s_in[buf]), kt = qt + ATT_TILE, vt = qt + 2 * ATT_TILE;
+    const int r0 = warp * 16;
+    float s[8][4];
+    qk_logits(qt, kt, s_bias, r0, lane, s);
+    softmax_rows(s);
+    float o[4][4];
+    frag_times_tile(s, vt, lane, o);
+    store_frag_t32(smem_u32(s_out), r0, lane, o);
+    __syncthreads();
+    for (int c = threadIdx.x; c < 256; c += ATT_THREADS) {
+      const int i = c >> 2, ch = c & 3;
+      const int tok = window_token(a, w, i);
+      uint4 v = *reinterpret_cast<const uint4*>(s_out + t32_off(i, ch));
+      if (ones_here && ch == (ones_c >> 3)) {  // bias-folding column of the following projection := 1.0
+        const int word = (ones_c & 7) >> 1;
+        const uint32_t keep = (ones_c & 1) ? 0x0000FFFFu : 0xFFFF0000u;
+        const uint32_t one = (ones_c & 1) ? 0x3F800000u : 0x00003F80u;
+        v.x = (word == 0) ? ((v.x & keep) | one) : v.x;
+        v.y = (word == 1) ? ((v.y & keep) | one) : v.y;
+        v.z = (word == 2) ? ((v.z & keep) | one) : v.z;
+        v.w = (word == 3) ? ((v.w & keep) | one) : v.w;
+      }
+      *reinterpret_cast<uint4*>(a.out + size_t(tok) * a.ld_o + h * 32 + ch * 8) = v;
+    }
+    // s_out / s_in[buf] are rewritten only after the next iteration's __syncthreads or by loads issued
+    // at the top of the next iteration into buf (which every thread has finished reading: barrier below)
+    __syncthreads();
+  }
+  cp_async_wait<0>();
+}
+
+// ============================================================================ backward
+struct AttnBwdSmem {
+  uint8_t in[2][4 * ATT_TILE];  // q, k, v, dO
+  uint8_t p[64 * 128];          // P  (bf16) [q][key]
+  uint8_t ds[64 * 128];         // dS (bf16) [q][key]
+  uint8_t out[3 * ATT_TILE];    // dq, dk, dv
+  float bias[225];
+  float dbias[225];
+};
+
+// C[16 keys x 32] += A^T * B  with A stored as a t64 tile [q][key] (this warp's keys k0..k0+15) and
+// B a t32 tile [q][d]; contraction over the 64 queries.
+__device__ __forceinline__ void tileT_times_tile(uint32_t a_tile, uint32_t b_tile, int k0, int lane, float (&o)[4][4]) {
+#pragma unroll
+  for (int n = 0; n < 4; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+#pragma unroll
+  for (int kt = 0; kt < 4; ++kt) {
+    uint32_t af[4];
+    {
+      const int i = lane >> 3;
+      const int row = kt * 16 + (lane & 7) + ((i >> 1) & 1) * 8;  // query
+      const int col = k0 + (i & 1) * 8;                           // key
+      ldsm_x4_t(a_tile + t64_off(row, col >> 3), af[0], af[1], af[2], af[3]);
+    }
+    const int row = kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+    for (int np = 0; np < 2; ++np) {
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4_t(b_tile + t32_off(row, np * 2 + (lane >> 4)), b0, b1, b2, b3);
+      mma_bf16(o[2 * np], af, b0, b1);
+      mma_bf16(o[2 * np + 1], af, b2, b3);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(ATT_THREADS) win_attn_ws8_bwd_kernel(const AttnArgs a) {
+  extern __shared__ __align__(128) uint8_t smem_dyn[];
+  AttnBwdSmem& sm = *reinterpret_cast<AttnBwdSmem*>(smem_dyn);
+  const int h = blockIdx.y;
+  const int nwin = a.B * (a.H >> 3) * (a.W >> 3);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  for (int i = threadIdx.x; i < 225; i += ATT_THREADS) {
+    sm.bias[i] = a.bias_table[i * a.heads + h];
+    sm.dbias[i] = 0.f;
+  }
+  float dbacc[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) dbacc[nt][0] = dbacc[nt][1] = dbacc[nt][2] = dbacc[nt][3] = 0.f;
+
+  int w = blockIdx.x;
+  int buf = 0;
+  if (w < nwin) load_window_tiles(a, w, smem_u32(sm.in[0]), a.qkv, a.ld_qkv, h * 32, 3, a.dout, a.ld_o, h * 32);
+  cp_async_commit();
+  for (; w < nwin; w += gridDim.x, buf ^= 1) {
+    const int wn = w + gridDim.x;
+    if (wn < nwin)
+      load_window_tiles(a, wn, smem_u32(sm.in[buf ^ 1]), a.qkv, a.ld_qkv, h * 32, 3, a.dout, a.ld_o, h * 32);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const uint32_t qt = smem_u32(sm.in[buf]), kt = qt + ATT_TILE, vt = qt + 2 * ATT_TILE, dot = qt + 3 * ATT_TILE;
+    const uint32_t pt = smem_u32(sm.p), dst = smem_u32(sm.ds), outt = smem_u32(sm.out);
+    const int r0 = warp * 16;
+    // ---- phase A: this warp's 16 query rows
+    float s[8][4];
+    qk_logits(qt, kt, sm.bias, r0, lane, s);
+    softmax_rows(s);  // s = P (fp32)
+    // dP = dO V^T  (A = dO rows, B = V as [key][d], same access pattern as K in QK^T)
+    float dp[8][4];
+    {
+      uint32_t ad[2][4];
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const int row = r0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        ldsm_x4(dot + t32_off(row, ks * 2 + (lane >> 4)), ad[ks][0], ad[ks][1], ad[ks][2], ad[ks][3]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4(vt + t32_off(nt * 8 + (lane & 7), lane >> 3), b0, b1, b2, b3);
+        dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
+        mma_bf16(dp[nt], ad[0], b0, b1);
+        mma_bf16(dp[nt], ad[1], b2, b3);
+      }
+    }
+    // P (bf16) -> smem; delta = rowsum(dP * P); dS = P * (dP - delta)
+    float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      // the forward multiplies V by bf16(P); its gradient dP is therefore taken w.r.t. the rounded P
+      d0 += dp[nt][0] * s[nt][0] + dp[nt][1] * s[nt][1];
+      d1 += dp[nt][2] * s[nt][2] + dp[nt][3] * s[nt][3];
+      const uint32_t lo = pack_bf16(s[nt][0], s[nt][1]), hi = pack_bf16(s[nt][2], s[nt][3]);
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(pt + t64_off(r0 + g, nt) + t * 4), "r"(lo) : "memory");
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(pt + t64_off(r0 + g + 8, nt) + t * 4), "r"(hi) : "memory");
+    }
+    d0 += __shfl_xor_sync(0xffffffffu, d0, 1);
+    d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
+    d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
+    d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] *= (dp[nt][0] - d0);
+      s[nt][1] *= (dp[nt][1] - d0);
+      s[nt][2] *= (dp[nt][2] - d1);
+      s[nt][3] *= (dp[nt][3] - d1);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) dbacc[nt][e] += s[nt][e];
+      const uint32_t lo = pack_bf16(s[nt][0], s[nt][1]), hi = pack_bf16(s[nt][2], s[nt][3]);
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(dst + t64_off(r0 + g, nt) + t * 4), "r"(lo) : "memory");
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(dst + t64_off(r0 + g + 8, nt) + t * 4), "r"(hi) : "memory");
+    }
+    // dQ rows = dS (bf16) * K
+    float o[4][4];
+    frag_times_tile(s, kt, lane, o);
+    store_frag_t32(outt, r0, lane, o);
+    __syncthreads();
+    // ---- phase B: this warp's 16 key rows
+    tileT_times_tile(dst, qt, r0, lane, o);   // dK = dS^T Q
+    store_frag_t32(outt + ATT_TILE, r0, lane, o);
+    tileT_times_tile(pt, dot, r0, lane, o);   // dV = P^T dO
+    store_frag_t32(outt + 2 * ATT_TILE, r0, lane, o);
+    __syncthreads();
+    const int hw = a.heads * 32;
+    for (int c = threadIdx.x; c < 3 * 256; c += ATT_THREADS) {
+      const int tile = c >> 8, rem = c & 255, i = rem >> 2, ch = rem & 3;
+      const int tok = window_token(a, w, i);
+      const uint4 v = *reinterpret_cast<const uint4*>(sm.out + tile * ATT_TILE + t32_off(i, ch));
+      *reinterpret_cast<uint4*>(a.dqkv + size_t(tok) * a.ld_qkv + tile * hw + h * 32 + ch * 8) = v;
+    }
+    __syncthreads();
+  }
+  cp_async_wait<0>();
+  // fold the per-thread dS sums into the (2*8-1)^2 table entries of this head
+  {
+    const int r0 = warp * 16;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int i0 = r0 + g, j0 = nt * 8 + 2 * t;
+      atomicAdd(&sm.dbias[rel_index(i0, j0)], dbacc[nt][0]);
+      atomicAdd(&sm.dbias[rel_index(i0, j0 + 1)], dbacc[nt][1]);
+      atomicAdd(&sm.dbias[rel_index(i0 + 8, j0)], dbacc[nt][2]);
+      atomicAdd(&sm.dbias[rel_index(i0 + 8, j0 + 1)], dbacc[nt][3]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 225; i += ATT_THREADS)
+    a.dbias_partials[(size_t(blockIdx.x) * a.heads + h) * 225 + i] = sm.dbias[i];
+}
+
+}  // namespace srk

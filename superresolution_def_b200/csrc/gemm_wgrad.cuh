@@ -17,7 +17,7 @@ constexpr int WG_TOK = 64;                     // tokens per pipeline stage
 constexpr int WG_SUBBOX = 64 * 128;            // one [64 tokens x 64 channels] swizzled box (8 KB)
 
 struct WgradArgs {
-  int T;        // tokens (multiple of 64 * splits)
+  int T;        // tokens (multiple of 64); split s owns k-iterations [s*I/splits, (s+1)*I/splits), I = T/64
   int Ca, Cb;   // channel counts (Cb == BNW)
   int ca_tiles; // ceil(Ca / 128)
   int splits;
@@ -52,9 +52,11 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int lane = threadIdx.x & 31;
   const int a_tile = blockIdx.x % args.ca_tiles;
   const int split = blockIdx.x / args.ca_tiles;
-  const int tok_per_split = args.T / args.splits;
-  const int t_begin = split * tok_per_split;
-  const int k_iters = tok_per_split / WG_TOK;
+  const int total_iters = args.T / WG_TOK;
+  const int it_begin = int((long long)split * total_iters / args.splits);
+  const int it_end = int((long long)(split + 1) * total_iters / args.splits);
+  const int t_begin = it_begin * WG_TOK;
+  const int k_iters = it_end - it_begin;  // >= 1 because splits <= total_iters
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);

@@ -1,0 +1,250 @@
+"""Host-side engine for runs of Swin transformer blocks on libsrk (tcgen05 GEMMs + fused window attention).
+
+The residual stream lives in HBM as token-major bf16 [T, Cp] (T = B*H*W tokens, Cp = 192 for C = 180: the 12 pad
+channels are zero, and normalised copies carry 1.0 in column C so that every Linear bias is a weight column).
+`SwinStackFunction` is one autograd node for a run of consecutive blocks: it owns the saved activations and calls
+srk_swin_block_fwd / srk_swin_block_bwd once per block.  PyTorch is used for memory, streams and autograd plumbing
+only — all arithmetic happens in the library, and there is no fallback path.
+
+Reference being replaced: SwinTransformerBlock.forward / WindowAttention.forward / Mlp.forward
+(models/architecture_swin.py:123-151, :71-96, :19-25) and their autograd backward.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from . import _capi as capi
+
+BF16 = torch.bfloat16
+BLOCK_PARAM_KEYS = ("norm1.weight", "norm1.bias", "attn.relative_position_bias_table", "attn.qkv.weight",
+                    "attn.qkv.bias", "attn.proj.weight", "attn.proj.bias", "norm2.weight", "norm2.bias",
+                    "mlp.fc1.weight", "mlp.fc1.bias", "mlp.fc2.weight", "mlp.fc2.bias")
+N_BLOCK_PARAMS = len(BLOCK_PARAM_KEYS)
+
+
+@dataclass(frozen=True)
+class BlockCfg:
+    C: int = 180
+    heads: int = 6
+    hidden: int = 720
+    ws: int = 8
+    Cp: int = 192
+    ds: int = 32
+    Hp: int = 768
+
+    @property
+    def dh(self) -> int:
+        return self.C // self.heads
+
+    @property
+    def QW(self) -> int:
+        return 3 * self.heads * self.ds
+
+    @property
+    def AW(self) -> int:
+        return self.heads * self.ds
+
+    def dims(self) -> capi.SrkBlockDims:
+        return capi.SrkBlockDims(self.C, self.Cp, self.heads, self.dh, self.ds, self.hidden, self.Hp)
+
+    @staticmethod
+    def for_model(C: int, heads: int, hidden: int, ws: int) -> "BlockCfg":
+        if C % heads != 0:
+            raise capi.SrkError(f"embed_dim {C} not divisible by heads {heads}")
+        cfg = BlockCfg(C=C, heads=heads, hidden=hidden, ws=ws, Cp=192, ds=32, Hp=((hidden + 1 + 255) // 256) * 256)
+        if not (C < 192 and heads * 32 == 192 and C // heads < 32 and ws == 8):
+            raise capi.SrkError(
+                f"libsrk block kernels are specialised for heads=6, head_dim<32, embed_dim<192, window 8; got "
+                f"C={C} heads={heads} ws={ws}")
+        return cfg
+
+
+def block_params_of(block: torch.nn.Module) -> list[torch.Tensor]:
+    """The 13 parameters of a SwinTransformerBlock-shaped module, in the C ABI's order."""
+    sd = dict(block.named_parameters())
+    return [sd[k] for k in BLOCK_PARAM_KEYS]
+
+
+class _WeightCache:
+    """bf16 GEMM operands of one block, refreshed when any master parameter changed (in-place version bump)."""
+
+    def __init__(self, cfg: BlockCfg, device):
+        self.cfg = cfg
+        elems = capi.block_weight_elems(cfg.dims())
+        self.t = {n: torch.empty(e, device=device, dtype=BF16) for n, e in zip(capi.WEIGHT_NAMES, elems)}
+        self.key = None
+
+    def get(self, params: list[torch.Tensor]) -> dict:
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if key != self.key:
+            capi.block_prep_weights(self.cfg.dims(), dict(zip(capi.PARAM_NAMES, params)), self.t)
+            self.key = key
+        return self.t
+
+
+_weight_caches: dict = {}
+
+
+def _weights_for(cfg: BlockCfg, params: list[torch.Tensor]) -> dict:
+    k = (cfg, params[3].data_ptr())  # keyed by the qkv weight storage
+    wc = _weight_caches.get(k)
+    if wc is None:
+        wc = _weight_caches[k] = _WeightCache(cfg, params[3].device)
+    return wc.get(params)
+
+
+def _check_param(p: torch.Tensor):
+    if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
+        raise capi.SrkError("libsrk needs contiguous fp32 CUDA parameters (no CPU / fallback path exists)")
+
+
+def _alloc_acts(cfg: BlockCfg, T: int, device) -> dict:
+    e = lambda w: torch.empty(T, w, device=device, dtype=BF16)  # noqa: E731
+    return {"qkv": e(cfg.QW), "ao": e(cfg.AW), "x_mid": e(cfg.Cp), "xn2": e(cfg.Cp),
+            "stats2": torch.empty(T, 2, device=device, dtype=torch.float32), "act": e(cfg.Hp), "dact": e(cfg.Hp),
+            "x_out": e(cfg.Cp), "xn_out": e(cfg.Cp),
+            "stats_out": torch.empty(T, 2, device=device, dtype=torch.float32)}
+
+
+def layernorm_tokens(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, C: int):
+    """xn, stats = LN(x[:, :C]) with the ones column at C.  x: [T, Cp] bf16."""
+    xn = torch.empty_like(x)
+    stats = torch.empty(x.shape[0], 2, device=x.device, dtype=torch.float32)
+    capi.layernorm_fwd(x, xn, stats, weight.detach(), bias.detach(), C, ones_col=C)
+    return xn, stats
+
+
+class SwinStackFunction(torch.autograd.Function):
+    """(x, xn, stats) -> (x_out, xn_out, stats_out) through `len(shifts)` consecutive Swin blocks.
+
+    tensors = 13 params per block (BLOCK_PARAM_KEYS order) followed by (next_norm_weight, next_norm_bias): the
+    affine of the LayerNorm that consumes the stack's output (its gradient belongs to the consumer, not to us).
+    The gradient returned for `x` is the complete dL/dx (residual path + LayerNorm-1 path); `xn`/`stats` are
+    derived data and carry no gradient of their own.
+    """
+
+    @staticmethod
+    def forward(ctx, x, xn, stats, cfg: BlockCfg, geom: tuple, shifts: tuple, *tensors):
+        B, H, W = geom
+        T = B * H * W
+        nb = len(shifts)
+        assert len(tensors) == nb * N_BLOCK_PARAMS + 2
+        for t in tensors:
+            _check_param(t)
+        assert x.dtype == BF16 and x.shape == (T, cfg.Cp) and x.is_contiguous() and xn.is_contiguous()
+        need_grad = torch.is_grad_enabled() and (x.requires_grad or any(t.requires_grad for t in tensors))
+        dims = cfg.dims()
+        saved = []
+        cur_x, cur_xn, cur_stats = x, xn, stats
+        # inference: two activation sets are ping-ponged (block i reads set i-1's outputs while writing set i)
+        pingpong = None if need_grad else [_alloc_acts(cfg, T, x.device) for _ in range(min(nb, 2))]
+        for i in range(nb):
+            params = [t.detach() for t in tensors[i * N_BLOCK_PARAMS:(i + 1) * N_BLOCK_PARAMS]]
+            if i + 1 < nb:
+                nw, nbias = tensors[(i + 1) * N_BLOCK_PARAMS].detach(), tensors[(i + 1) * N_BLOCK_PARAMS + 1].detach()
+            else:
+                nw, nbias = tensors[-2].detach(), tensors[-1].detach()
+            weights = _weights_for(cfg, params)
+            acts = dict(_alloc_acts(cfg, T, x.device) if need_grad else pingpong[i & 1])
+            acts.update(x_in=cur_x, xn1=cur_xn, stats1=cur_stats)
+            g = capi.SrkGeom(B, H, W, cfg.ws, shifts[i])
+            capi.swin_block_fwd(dims, g, weights, dict(zip(capi.PARAM_NAMES, params)), nw, nbias, acts)
+            if need_grad:
+                saved.append(acts)
+            cur_x, cur_xn, cur_stats = acts["x_out"], acts["xn_out"], acts["stats_out"]
+        ctx.cfg, ctx.geom, ctx.shifts, ctx.saved_acts = cfg, geom, shifts, saved
+        ctx.params = tensors
+        ctx.mark_non_differentiable(cur_xn, cur_stats)
+        return cur_x, cur_xn, cur_stats
+
+    @staticmethod
+    def backward(ctx, g_x, _g_xn, _g_stats):
+        cfg, (B, H, W), shifts, tensors = ctx.cfg, ctx.geom, ctx.shifts, ctx.params
+        T = B * H * W
+        dev = g_x.device
+        dims = cfg.dims()
+        nb = len(shifts)
+        g = g_x.contiguous()
+        if g.dtype != BF16:
+            g = g.to(BF16)
+        scratch = _bwd_scratch(cfg, B, H, W, dev)
+        grads: list = [None] * len(tensors)
+        bufs = [torch.empty(T, cfg.Cp, device=dev, dtype=BF16), torch.empty(T, cfg.Cp, device=dev, dtype=BF16)]
+        for i in reversed(range(nb)):
+            params = [t.detach() for t in tensors[i * N_BLOCK_PARAMS:(i + 1) * N_BLOCK_PARAMS]]
+            weights = _weights_for(cfg, params)
+            acts = ctx.saved_acts[i]
+            gdict = {n: torch.empty_like(p) for n, p in zip(capi.PARAM_NAMES, params)}
+            g_in = bufs[i & 1]
+            geom = capi.SrkGeom(B, H, W, cfg.ws, shifts[i])
+            capi.swin_block_bwd(dims, geom, weights, dict(zip(capi.PARAM_NAMES, params)), acts, g, scratch, g_in, gdict)
+            for j, n in enumerate(capi.PARAM_NAMES):
+                grads[i * N_BLOCK_PARAMS + j] = gdict[n]
+            ctx.saved_acts[i] = None  # release this block's activations as soon as they are consumed
+            g = g_in
+        return (g, None, None, None, None, None, *grads)
+
+
+_scratch_cache: dict = {}
+
+
+def _bwd_scratch(cfg: BlockCfg, B: int, H: int, W: int, device) -> dict:
+    key = (cfg, B, H, W, str(device))
+    s = _scratch_cache.get(key)
+    if s is None:
+        T = B * H * W
+        n = capi.block_bwd_scratch_floats(cfg.dims(), capi.SrkGeom(B, H, W, cfg.ws, 0))
+        s = {"d_act": torch.empty(T, cfg.Hp, device=device, dtype=BF16),
+             "d_ao": torch.empty(T, cfg.AW, device=device, dtype=BF16),
+             "d_qkv": torch.empty(T, cfg.QW, device=device, dtype=BF16),
+             "g_mid": torch.empty(T, cfg.Cp, device=device, dtype=BF16),
+             "wg_ws": torch.empty(n, device=device, dtype=torch.float32)}
+        _scratch_cache.clear()  # one geometry at a time keeps the scratch footprint bounded
+        _scratch_cache[key] = s
+    return s
+
+
+class FusedNormOutput(torch.autograd.Function):
+    """Identity on the already-computed xn = LayerNorm(x) that makes it differentiable w.r.t. x, weight and bias.
+    The forward value was produced by the epilogue of the last block's fc2 GEMM (SwinIR.norm, :247)."""
+
+    @staticmethod
+    def forward(ctx, x, xn, stats, weight, bias, C: int):
+        ctx.save_for_backward(x, stats, weight)
+        ctx.C = C
+        return xn.detach()
+
+    @staticmethod
+    def backward(ctx, g_xn):
+        x, stats, weight = ctx.saved_tensors
+        g_xn = g_xn.contiguous().to(BF16)
+        dx = torch.empty_like(x)
+        dgamma = torch.empty_like(weight)
+        dbeta = torch.empty_like(weight)
+        capi.layernorm_bwd(g_xn, x, stats, weight.detach(), None, dx, dgamma, dbeta, ctx.C)
+        return dx, None, None, dgamma, dbeta, None
+
+
+def pack_tokens(t: torch.Tensor, Cp: int) -> torch.Tensor:
+    """(B, L, C) any float dtype -> [B*L, Cp] bf16 with zero pad channels (plumbing; differentiable)."""
+    B, L, C = t.shape
+    out = t.new_zeros((B * L, Cp), dtype=BF16)
+    out[:, :C] = t.reshape(B * L, C).to(BF16)
+    return out
+
+
+def unpack_tokens(t: torch.Tensor, B: int, C: int, dtype) -> torch.Tensor:
+    return t[:, :C].reshape(B, -1, C).to(dtype)
+
+
+_ident_cache: dict = {}
+
+
+def identity_norm(C: int, device):
+    """(ones, zeros) affine used when a stack's output is not consumed by a LayerNorm (stand-alone block)."""
+    k = (C, str(device))
+    if k not in _ident_cache:
+        _ident_cache[k] = (torch.ones(C, device=device), torch.zeros(C, device=device))
+    return _ident_cache[k]

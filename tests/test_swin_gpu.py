@@ -1,0 +1,115 @@
+"""-m gpu parity tests: CUDA path (through the C ABI) vs the oracle on the same seeded inputs.
+Tolerances (bf16 tensor-core math vs fp32 oracle): outputs rel-L2 <= 2e-2, gradients rel-L2 <= 4e-2."""
+import math
+
+import pytest
+import torch
+
+from tests.util import rel_l2, max_abs, randomize_
+
+pytestmark = pytest.mark.gpu
+OUT_TOL = 2e-2
+GRAD_TOL = 4e-2
+
+
+def _oracle():
+    from oracle import swinir_oracle as o
+    return o
+
+
+def test_attention_core_matches_torch():
+    """srk_win_attn_fwd/bwd on packed qkv vs a direct torch evaluation (shifted windows, 2 images)."""
+    from superresolution_def_b200 import _capi as capi
+    torch.manual_seed(1)
+    B, H, W, heads, dh, ds, shift = 2, 16, 24, 6, 30, 32, 4
+    T = B * H * W
+    qkv = torch.zeros(T, 3 * heads * ds, device="cuda")
+    real = torch.randn(T, 3, heads, dh, device="cuda")
+    qkv.view(T, 3, heads, ds)[..., :dh] = real
+    qkv = qkv.to(torch.bfloat16)
+    table = torch.randn(225, heads, device="cuda")
+    out = torch.zeros(T, heads * ds, device="cuda", dtype=torch.bfloat16)
+    geom = capi.SrkGeom(B, H, W, 8, shift)
+    capi.win_attn_fwd(geom, heads, qkv, table, out, ones_col=dh)
+    torch.cuda.synchronize()
+
+    o = _oracle()
+    q = qkv.float().view(B, H, W, 3, heads, ds).requires_grad_(True)
+
+    def ref_attn(qv):
+        x = torch.roll(qv, shifts=(-shift, -shift), dims=(1, 2)).reshape(B, H, W, -1)
+        win = o.window_partition(x, 8).reshape(-1, 64, 3, heads, ds).permute(2, 0, 3, 1, 4)
+        logits = win[0] @ win[1].transpose(-2, -1)
+        idx = o.relative_position_index(8).to("cuda")
+        logits = logits + table[idx.reshape(-1)].reshape(64, 64, heads).permute(2, 0, 1)[None]
+        p = torch.softmax(logits, -1)
+        y = (p @ win[2]).transpose(1, 2).reshape(-1, 8, 8, heads * ds)
+        y = o.window_reverse(y, 8, H, W)
+        return torch.roll(y, shifts=(shift, shift), dims=(1, 2)).reshape(T, heads * ds)
+
+    ref = ref_attn(q)
+    ref_out = ref.detach().clone()
+    ref_out[:, dh] = 1.0
+    assert rel_l2(out, ref_out) < 1e-2, (rel_l2(out, ref_out), max_abs(out, ref_out))
+
+    dout = torch.zeros(T, heads, ds, device="cuda")
+    dout[..., :dh] = torch.randn(T, heads, dh, device="cuda")
+    dout = dout.view(T, heads * ds).to(torch.bfloat16)
+    table_r = table.clone().requires_grad_(True)
+    table_saved, table = table, table_r
+    ref = ref_attn(q)
+    ref.backward(dout.float())
+    dqkv = torch.zeros_like(qkv)
+    dtab = torch.zeros(225, heads, device="cuda")
+    capi.win_attn_bwd(geom, heads, qkv, table_saved, dout, dqkv, dtab)
+    torch.cuda.synchronize()
+    e = rel_l2(dqkv, q.grad.reshape(T, -1))
+    assert e < 2e-2, e
+    e = rel_l2(dtab, table_r.grad)
+    assert e < 2e-2, e
+
+
+@pytest.mark.parametrize("shift", [0, 4])
+def test_swin_block_matches_oracle(shift):
+    from superresolution_def_b200.architecture_swin import SwinTransformerBlock
+    o = _oracle()
+    torch.manual_seed(2)
+    B, R, C, heads = 2, 16, 180, 6
+    blk = randomize_(SwinTransformerBlock(C, (R, R), heads, window_size=8, shift_size=shift), seed=3).cuda()
+    x = torch.randn(B, R * R, C, device="cuda")
+    xr = x.clone().requires_grad_(True)
+    xm = x.clone().requires_grad_(True)
+    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in blk.state_dict().items()}
+    ref = o.swin_block(xr, sd, "", (R, R), heads, 8, shift)
+    got = blk(xm)
+    assert got.shape == ref.shape and got.dtype == x.dtype
+    assert rel_l2(got, ref) < OUT_TOL, rel_l2(got, ref)
+    w = torch.randn_like(ref)
+    (ref * w).sum().backward()
+    (got * w).sum().backward()
+    assert rel_l2(xm.grad, xr.grad) < GRAD_TOL, rel_l2(xm.grad, xr.grad)
+    worst = {}
+    for name, p in blk.named_parameters():
+        worst[name] = rel_l2(p.grad, sd[name].grad)
+    bad = {k: v for k, v in worst.items() if v > GRAD_TOL}
+    assert not bad, worst
+
+
+def test_swinir_small_matches_oracle():
+    from superresolution_def_b200.architecture_swin import SwinIR
+    o = _oracle()
+    torch.manual_seed(4)
+    kw = dict(img_size=16, window_size=8, depths=[2, 2], num_heads=[6, 6])
+    net = randomize_(SwinIR(upscale=4, in_chans=1, embed_dim=180, mlp_ratio=2, **kw), seed=5, table_std=0.5).cuda()
+    x = torch.rand(2, 1, 16, 16, device="cuda")
+    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in net.state_dict().items()}
+    ref = o.swinir_forward(x, sd, upscale=4, **kw)
+    got = net(x)
+    assert got.shape == ref.shape == (2, 1, 64, 64)
+    assert rel_l2(got, ref) < OUT_TOL, rel_l2(got, ref)
+    w = torch.randn_like(ref)
+    (ref * w).mean().backward()
+    (got.float() * w).mean().backward()
+    worst = {n: rel_l2(p.grad, sd[n].grad) for n, p in net.named_parameters()}
+    bad = {k: v for k, v in worst.items() if v > 6e-2}
+    assert not bad, {k: round(v, 4) for k, v in sorted(worst.items(), key=lambda kv: -kv[1])[:12]}

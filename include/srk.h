@@ -25,6 +25,8 @@ extern "C" {
 
 /* Library / build identification ("sm_100a tcgen05"). */
 const char* srk_version(void);
+/* Number of CUDA kernels this library has launched since it was loaded (bench.py's gpu_launches). */
+long long srk_launch_count(void);
 
 /* ---- epilogues of srk_gemm_tn (values match csrc/gemm_tn.cuh) ---- */
 #define SRK_EPI_STORE 0  /* C = bf16(acc)                                                       */

@@ -143,34 +143,45 @@ def psnr(sr: Tensor, hr: Tensor) -> float:
     return 10.0 * math.log10(1.0 / (mse + 1e-8))
 
 
-def synthetic_pairs(n: int, seed: int = 1234, hr_size: int = 512, scale: int = 4):
-    """Seeded synthetic 16-bit-normalised star-field pairs: returns (lr, hr) float32 in [0,1],
-    shapes (n,1,hr/scale,hr/scale), (n,1,hr,hr), both quantised to uint16 levels as the reference's
-    dataset does (dataset/astronomical_dataset_swin.py:34-39; misc/Dataset_step4_normalization.py:159-172)."""
+# --------------------------------------------------------------------------- parameter construction
+def init_state_dict(*, img_size: int, window_size: int, embed_dim: int, depths: Sequence[int],
+                    num_heads: Sequence[int], in_chans: int = 1, mlp_ratio: float = 4.0, seed: int = 0):
+    """A state_dict with the reference's keys/shapes (SwinIR.__init__, models/architecture_swin.py:193-230) and
+    PyTorch-default-like initial values (uniform +-1/sqrt(fan_in) for conv/linear, LN = (1, 0), bias tables
+    trunc-normal 0.02).  Used where the oracle must run without a reference checkpoint (bench CPU baseline)."""
     g = torch.Generator().manual_seed(seed)
-    ys, xs = torch.meshgrid(torch.arange(hr_size, dtype=torch.float32), torch.arange(hr_size, dtype=torch.float32),
-                            indexing="ij")
-    hrs = []
-    for _ in range(n):
-        img = 0.08 + 0.01 * torch.randn(hr_size, hr_size, generator=g)
-        nstars = int(torch.randint(20, 61, (1,), generator=g))
-        for _s in range(nstars):
-            cy, cx = (torch.rand(2, generator=g) * hr_size).tolist()
-            sig = 1.0 + 3.0 * float(torch.rand(1, generator=g))
-            amp = math.exp(math.log(0.05) + float(torch.rand(1, generator=g)) * (math.log(1.0) - math.log(0.05)))
-            img = img + amp * torch.exp(-((ys - cy) ** 2 + (xs - cx) ** 2) / (2 * sig * sig))
-        neb = torch.randn(1, 1, hr_size // 32, hr_size // 32, generator=g)
-        neb = F.interpolate(neb, size=(hr_size, hr_size), mode="bicubic", align_corners=False)[0, 0]
-        img = img + 0.3 * (neb - neb.min()) / (neb.max() - neb.min() + 1e-6) * 0.5
-        img = torch.log1p(img.clamp_min(0)) / math.log(2.0)
-        hrs.append(img.clamp(0, 1))
-    hr = torch.stack(hrs)[:, None]
-    hr = torch.round(hr * 65535.0) / 65535.0
-    lr = F.avg_pool2d(hr, scale)
-    k = torch.arange(-4, 5, dtype=torch.float32)
-    gk = torch.exp(-(k ** 2) / (2 * 1.5 ** 2)); gk = gk / gk.sum()
-    lr = F.conv2d(F.pad(lr, (4, 4, 4, 4), mode="reflect"), gk.reshape(1, 1, 1, 9))
-    lr = F.conv2d(lr, gk.reshape(1, 1, 9, 1))
-    lr = lr + 0.005 * torch.randn(lr.shape, generator=g)
-    lr = torch.round(lr.clamp(0, 1) * 65535.0) / 65535.0
-    return lr, hr
+    sd: dict[str, Tensor] = {}
+
+    def dense(name, *shape):
+        fan_in = 1
+        for s in shape[1:]:
+            fan_in *= s
+        bound = 1.0 / math.sqrt(fan_in)
+        sd[name + ".weight"] = (torch.rand(shape, generator=g) * 2 - 1) * bound
+        sd[name + ".bias"] = (torch.rand(shape[0], generator=g) * 2 - 1) * bound
+
+    def ln(name, c):
+        sd[name + ".weight"] = torch.ones(c)
+        sd[name + ".bias"] = torch.zeros(c)
+
+    c, hidden = embed_dim, int(embed_dim * mlp_ratio)
+    dense("conv_first", c, in_chans, 3, 3)
+    for i, depth in enumerate(depths):
+        for j in range(depth):
+            p = f"layers.{i}.{j}."
+            ln(p + "norm1", c)
+            sd[p + "attn.relative_position_bias_table"] = (
+                torch.randn((2 * window_size - 1) ** 2, num_heads[i], generator=g) * 0.02).clamp(-0.04, 0.04)
+            sd[p + "attn.relative_position_index"] = relative_position_index(window_size)
+            dense(p + "attn.qkv", 3 * c, c)
+            dense(p + "attn.proj", c, c)
+            ln(p + "norm2", c)
+            dense(p + "mlp.fc1", hidden, c)
+            dense(p + "mlp.fc2", c, hidden)
+    ln("norm", c)
+    dense("conv_after_body", c, c, 3, 3)
+    dense("conv_before_upsample.0", 64, c, 3, 3)
+    dense("upsample.0", 256, 64, 3, 3)
+    dense("upsample.2", 256, 64, 3, 3)
+    dense("conv_last", in_chans, 64, 3, 3)
+    return sd

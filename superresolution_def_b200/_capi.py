@@ -39,6 +39,7 @@ def _load() -> ctypes.CDLL:
 
 lib = _load()
 lib.srk_version.restype = c_char_p
+lib.srk_launch_count.restype = ctypes.c_longlong
 
 
 def _sig(name, argtypes):
@@ -57,6 +58,10 @@ _gemm_wgrad_dbg = _sig("srk_gemm_wgrad_dbg", [c_int, c_int, c_int, c_void_p, c_i
                                                c_int, c_void_p, c_int, c_int, c_void_p])
 
 EPI_STORE, EPI_GELU2, EPI_MUL, EPI_RES_LN, EPI_LNBWD = range(5)
+
+
+def launch_count() -> int:
+    return int(lib.srk_launch_count())
 
 
 def version() -> str:

@@ -84,6 +84,7 @@ int launch_attn_fwd(const SrkGeom* g, int heads, const void* qkv, int ld_qkv, co
   const int nwin = g->B * (g->H / 8) * (g->W / 8);
   dim3 grid(attn_fwd_gx(nwin, heads), heads);
   win_attn_ws8_fwd_kernel<<<grid, ATT_THREADS, 0, stream>>>(a);
+  SRK_LAUNCHED(1);
   SRK_CUDA_OK(cudaGetLastError());
   return SRK_OK;
 }
@@ -106,6 +107,7 @@ int launch_attn_bwd(const SrkGeom* g, int heads, const void* qkv, int ld_qkv, co
   a.ld_qkv = ld_qkv; a.ld_o = ld_o; a.ones_col = -1;
   dim3 grid(gx, heads);
   win_attn_ws8_bwd_kernel<<<grid, ATT_THREADS, sizeof(AttnBwdSmem), stream>>>(a);
+  SRK_LAUNCHED(1);
   SRK_CUDA_OK(cudaGetLastError());
   return SRK_OK;
 }
@@ -145,6 +147,7 @@ extern "C" int srk_block_prep_weights(const SrkBlockDims* d, const SrkBlockParam
                      static_cast<__nv_bfloat16*>(w->fc1_f),  static_cast<__nv_bfloat16*>(w->fc1_t),
                      static_cast<__nv_bfloat16*>(w->fc2_f),  static_cast<__nv_bfloat16*>(w->fc2_t)};
   prep_block_weights_kernel<<<296, 256, 0, stream>>>(to_dims(d), pp, ww);
+  SRK_LAUNCHED(1);
   SRK_CUDA_OK(cudaGetLastError());
   return SRK_OK;
 }
@@ -234,6 +237,7 @@ extern "C" int srk_swin_block_bwd(const SrkBlockDims* d, const SrkGeom* g, const
                    grads->proj_b,  grads->norm2_w, grads->norm2_b,   grads->fc1_w, grads->fc1_b, grads->fc2_w,
                    grads->fc2_b};
   unpack_block_grads_kernel<<<296, 256, 0, stream>>>(to_dims(d), us, gp, accumulate ? 1.f : 0.f);
+  SRK_LAUNCHED(1);
   SRK_CUDA_OK(cudaGetLastError());
   return SRK_OK;
 }
@@ -257,6 +261,7 @@ extern "C" int srk_win_attn_bwd(const SrkGeom* g, int heads, const void* qkv, in
   if (rc) return rc;
   if (d_rpb_table) {
     rpb_partials_reduce_kernel<<<(225 * heads + 127) / 128, 128, 0, stream>>>(dbias_ws, gx, heads, d_rpb_table);
+    SRK_LAUNCHED(1);
     SRK_CUDA_OK(cudaGetLastError());
   }
   return SRK_OK;
@@ -270,6 +275,7 @@ extern "C" int srk_layernorm_fwd(const void* x, int ldx, void* y, int ldy, float
   ln_fwd_rows_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(y), ldy, stats, gamma, beta, rows, C, Cp,
       ones_col, eps);
+  SRK_LAUNCHED(1);
   SRK_CUDA_OK(cudaGetLastError());
   return SRK_OK;
 }
@@ -287,9 +293,11 @@ extern "C" int srk_layernorm_bwd(const void* dy, int lddy, const void* x, int ld
                                                static_cast<const __nv_bfloat16*>(x), ldx, stats, gamma,
                                                static_cast<const __nv_bfloat16*>(dres), lddres,
                                                static_cast<__nv_bfloat16*>(dx), lddx, part_ws, rows, C, Cp);
+  SRK_LAUNCHED(1);
   SRK_CUDA_OK(cudaGetLastError());
   if (dgamma && dbeta) {
     ln_param_grad_reduce_kernel<<<(2 * C + 127) / 128, 128, 0, stream>>>(part_ws, grid, Cp, C, dgamma, dbeta);
+    SRK_LAUNCHED(1);
     SRK_CUDA_OK(cudaGetLastError());
   }
   return SRK_OK;

@@ -5,6 +5,8 @@
 
 namespace srk {
 
+std::atomic<long long> g_launches{0};
+
 template <int BN, int EPI>
 static int launch_gemm_tn(const GemmArgs& a, const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC,
                           const CUtensorMap& tC2, const CUtensorMap& tX1, const CUtensorMap& tX2,
@@ -19,6 +21,7 @@ static int launch_gemm_tn(const GemmArgs& a, const CUtensorMap& tA, const CUtens
   const int tiles = (a.M / GEMM_BM) * (a.N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   gemm_tn_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(tA, tB, tC, tC2, tX1, tX2, a);
+  SRK_LAUNCHED(1);
   SRK_CUDA_OK(cudaGetLastError());
   return SRK_OK;
 }
@@ -38,6 +41,8 @@ static int pick_bn(int epi, int N) {
 using namespace srk;
 
 extern "C" const char* srk_version(void) { return "libsrk 0.1 (sm_100a: tcgen05/TMEM/TMA)"; }
+
+extern "C" long long srk_launch_count(void) { return g_launches.load(); }
 
 extern "C" int srk_gemm_grid(int M, int N) {
   (void)N;
@@ -106,6 +111,7 @@ static int launch_wgrad(const WgradArgs& a, const CUtensorMap& tA, const CUtenso
     configured = true;
   }
   gemm_wgrad_kernel<BNW><<<a.ca_tiles * a.splits, WG_THREADS, Cfg::kSmemBytes, stream>>>(tA, tB, a);
+  SRK_LAUNCHED(1);
   SRK_CUDA_OK(cudaGetLastError());
   return SRK_OK;
 }
@@ -134,6 +140,7 @@ extern "C" int srk_gemm_wgrad_dbg(int T, int Ca, int Cb, const void* A, int lda,
   if (rc) return rc;
   const int n = a.ca_tiles * 128 * Cb;
   wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, stream>>>(workspace, out, splits, n);
+  SRK_LAUNCHED(1);
   SRK_CUDA_OK(cudaGetLastError());
   return SRK_OK;
 }

@@ -6,11 +6,16 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 
 #include "../../include/srk.h"
 
 namespace srk {
+
+// number of kernels launched by this library since load (reported by srk_launch_count)
+extern std::atomic<long long> g_launches;
+#define SRK_LAUNCHED(n) (::srk::g_launches.fetch_add((n), std::memory_order_relaxed))
 
 inline int fail(int code, const char* what) {
   fprintf(stderr, "[srk] error %d: %s\n", code, what);

@@ -1,0 +1,71 @@
+"""Data-parallel gradient exchange for one process per GPU (NCCL over NVLink 5 / NVSwitch).
+
+Replaces the reference's `DDP(net_g)` wrap (train_swin.py:152, train_hat.py:148): parameters' gradients live in
+flat fp32 buckets laid out in *reverse execution order* (tail convs first, then layers 5..0, then conv_first), and a
+bucket's all-reduce (mean) is launched asynchronously the moment its last gradient has been accumulated, so the
+exchange of layer group k overlaps the backward kernels of group k-1.  Unlike the reference launchers
+(start_swin.py:131-135) NCCL P2P/NVLS stay enabled.  Patches are independent, so there is no other collective.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+class BucketedGradReducer:
+    def __init__(self, groups: list[list[torch.nn.Parameter]], world_size: int):
+        """groups: parameter groups in the order their gradients become ready during backward."""
+        self.world = world_size
+        self.buckets = []
+        self.handles = []
+        self._pending = []
+        for params in groups:
+            params = [p for p in params if p.requires_grad]
+            if not params:
+                continue
+            n = sum(p.numel() for p in params)
+            flat = torch.zeros(n, device=params[0].device, dtype=torch.float32)
+            off = 0
+            for p in params:
+                p.grad = flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+            bi = len(self.buckets)
+            self.buckets.append(flat)
+            self._pending.append(len(params))
+            if world_size > 1:
+                for p in params:
+                    p.register_post_accumulate_grad_hook(self._make_hook(bi))
+        self._count = list(self._pending)
+
+    def _make_hook(self, bi: int):
+        def hook(_p):
+            self._count[bi] -= 1
+            if self._count[bi] == 0:
+                self.handles.append(dist.all_reduce(self.buckets[bi], op=dist.ReduceOp.AVG, async_op=True))
+        return hook
+
+    def zero_grad(self):
+        for b in self.buckets:
+            b.zero_()
+        self._count = list(self._pending)
+
+    def finish(self):
+        """Block the current stream on every outstanding bucket exchange (call after backward())."""
+        for h in self.handles:
+            h.wait()
+        self.handles.clear()
+
+    @property
+    def nbytes(self) -> int:
+        return sum(b.numel() * 4 for b in self.buckets)
+
+
+def swinir_grad_groups(net) -> list[list[torch.nn.Parameter]]:
+    """Reverse-execution-order parameter groups of a SwinIR-shaped module."""
+    groups = [list(net.conv_last.parameters()) + list(net.upsample.parameters())
+              + list(net.conv_before_upsample.parameters()) + list(net.conv_after_body.parameters())
+              + list(net.norm.parameters())]
+    for layer in reversed(list(net.layers)):
+        groups.append([p for blk in layer for p in blk.parameters()])
+    groups.append(list(net.conv_first.parameters()))
+    return groups

@@ -134,7 +134,7 @@ class SwinStackFunction(torch.autograd.Function):
         for t in tensors:
             _check_param(t)
         assert x.dtype == BF16 and x.shape == (T, cfg.Cp) and x.is_contiguous() and xn.is_contiguous()
-        need_grad = torch.is_grad_enabled() and (x.requires_grad or any(t.requires_grad for t in tensors))
+        need_grad = any(ctx.needs_input_grad)  # grad mode is always off inside Function.forward
         dims = cfg.dims()
         saved = []
         cur_x, cur_xn, cur_stats = x, xn, stats

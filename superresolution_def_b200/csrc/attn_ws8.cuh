@@ -120,10 +120,10 @@ __device__ __forceinline__ void softmax_rows(float (&s)[8][4]) {
   constexpr float kLog2e = 1.4426950408889634f;
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
-    s[nt][0] = exp2f((s[nt][0] - m0) * kLog2e);
-    s[nt][1] = exp2f((s[nt][1] - m0) * kLog2e);
-    s[nt][2] = exp2f((s[nt][2] - m1) * kLog2e);
-    s[nt][3] = exp2f((s[nt][3] - m1) * kLog2e);
+    s[nt][0] = fast_ex2((s[nt][0] - m0) * kLog2e);
+    s[nt][1] = fast_ex2((s[nt][1] - m0) * kLog2e);
+    s[nt][2] = fast_ex2((s[nt][2] - m1) * kLog2e);
+    s[nt][3] = fast_ex2((s[nt][3] - m1) * kLog2e);
     l0 += s[nt][0] + s[nt][1];
     l1 += s[nt][2] + s[nt][3];
   }
@@ -131,7 +131,7 @@ __device__ __forceinline__ void softmax_rows(float (&s)[8][4]) {
   l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+  const float i0 = fast_rcp(l0), i1 = fast_rcp(l1);
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
     s[nt][0] *= i0; s[nt][1] *= i0; s[nt][2] *= i1; s[nt][3] *= i1;

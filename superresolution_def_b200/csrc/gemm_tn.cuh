@@ -5,10 +5,10 @@
 // Mlp.fc1/fc2 (:19-25), and their autograd input-gradients; the fused epilogues replace
 // LayerNorm (:127,150), GELU (:20), the residual adds (:149-150) and their backward passes.
 //
-// Roles (192 threads, 1 CTA/SM, persistent over output tiles):
+// Roles (320 threads, 1 CTA/SM, persistent over output tiles):
 //   warp 0   : TMA producer   (A [128 x 64] + B [BN x 64] bf16 boxes, 128B swizzle, mbarrier ring)
 //   warp 1   : MMA issuer     (one lane issues tcgen05.mma 128 x BN x 16; accumulators double-buffered in TMEM)
-//   warps 2-5: epilogue       (tcgen05.ld -> registers -> math -> swizzled smem -> TMA store)
+//   warps 2-9: epilogue       (tcgen05.ld -> registers -> math -> swizzled smem -> TMA store)
 #pragma once
 #include "srk_ptx.cuh"
 
@@ -16,8 +16,8 @@ namespace srk {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 192;
-constexpr int GEMM_EPI_THREADS = 128;
+constexpr int GEMM_THREADS = 320;      // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int GEMM_EPI_THREADS = 256;
 constexpr int BOX_BYTES = 128 * 128;  // one [128 rows x 64 bf16] swizzled box
 
 enum GemmEpilogue : int {
@@ -47,21 +47,30 @@ struct GemmCfg {
                                    : (EPI == EPI_GELU2) ? 4 * BOX_BYTES
                                    : (EPI == EPI_MUL)   ? 4 * BOX_BYTES
                                                         : 2 * kBoxes * BOX_BYTES;
-  static constexpr int kBudget = 232448 - 1024 /*align slack*/ - 512 /*barriers*/ - 2304 /*static smem*/;
+  static constexpr int kRedBytes = 2 * 2 * 128 * 4;  // cross-half row reductions
+  static constexpr int kBudget = 232448 - 1024 /*align slack*/ - 512 /*barriers*/ - 2304 /*static smem*/ - kRedBytes;
   static constexpr int kStagesRaw = (kBudget - kEpiBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 512 + 1024;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 512 + kRedBytes + 1024;
   static_assert(kStages >= 2, "not enough shared memory for a 2-stage pipeline");
   static_assert(BN % 64 == 0 && BN <= 256, "BN must be a multiple of 64, <= 256");
 };
 
-__device__ __forceinline__ float gelu_erf(float u) {
-  return 0.5f * u * (1.0f + erff(u * 0.70710678118654752f));
-}
-__device__ __forceinline__ float gelu_erf_grad(float u) {
-  const float cdf = 0.5f * (1.0f + erff(u * 0.70710678118654752f));
-  const float pdf = 0.3989422804014327f * __expf(-0.5f * u * u);
-  return cdf + u * pdf;
+// Exact-erf GELU and its derivative from one exp: erf via Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below
+// the bf16 output resolution); exp(-z^2) with z = u/sqrt(2) is also the Gaussian pdf factor of gelu'.
+//   gelu(u) = u * Phi(u),  gelu'(u) = Phi(u) + u * phi(u),  Phi = 0.5 (1 + erf(u/sqrt2)),  phi = exp(-u^2/2)/sqrt(2 pi)
+__device__ __forceinline__ void gelu_pair(float u, float& a, float& g) {
+  const float z = fabsf(u) * 0.70710678118654752f;
+  const float k = fast_rcp(fmaf(0.3275911f, z, 1.0f));
+  const float e = fast_ex2(-1.4426950408889634f * z * z);  // exp(-z^2) = exp(-u^2/2)
+  float poly = fmaf(1.061405429f, k, -1.453152027f);
+  poly = fmaf(poly, k, 1.421413741f);
+  poly = fmaf(poly, k, -0.284496736f);
+  poly = fmaf(poly, k, 0.254829592f);
+  const float erf_abs = fmaf(-poly * k, e, 1.0f);        // erf(|z|)
+  const float cdf = 0.5f + copysignf(0.5f * erf_abs, u); // Phi(u)
+  a = u * cdf;
+  g = fmaf(u * 0.3989422804014327f, e, cdf);
 }
 
 // Transposing butterfly: on entry lane l holds v[0..31] (32 columns of its row); on exit v[0] of
@@ -111,6 +120,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * S + 2 + a); };
   auto aux_bar = [&](int b) { return bar_base + 8u * (2 * S + 4 + b); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * S + 6);
+  const uint32_t red_base = bar_base + 512;
 
   __shared__ float s_gamma[256];
   __shared__ float s_beta[256];
@@ -132,7 +142,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), GEMM_EPI_THREADS / 32);
       mbar_init(aux_bar(a), 1);
     }
     fence_mbar_init();
@@ -203,18 +213,25 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
-    const int q = warp & 3;             // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;      // accumulator row owned by this thread
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    // Two warps share each TMEM lane quarter (hardware: a warp reaches lanes 32*(warp%4)..+31) and split the
+    // columns between them ("half"), so every SM sub-partition hosts two epilogue warps.
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;   // 0: warps 2-5, 1: warps 6-9
+    const int row = q * 32 + lane;      // accumulator row owned by this thread (shared with the other half)
     const bool elected = (threadIdx.x == 64);
     const uint32_t lane_sel = uint32_t(q * 32) << 16;
     int it = 0;
     uint32_t box_counter = 0;           // box-granular staging ring position
     uint32_t aux_count = 0;             // number of aux loads consumed (parity tracking)
-    float acc_g[(EPI == EPI_LNBWD) ? (BN / 32) : 1];
-    float acc_b[(EPI == EPI_LNBWD) ? (BN / 32) : 1];
+    constexpr int NC = BN / 32;         // 32-column chunks per row
+    constexpr int NCH = NC / 2;         // chunks per half (row epilogues need an even chunk count)
+    float acc_g[(EPI == EPI_LNBWD) ? NCH : 1];
+    float acc_b[(EPI == EPI_LNBWD) ? NCH : 1];
 #pragma unroll
-    for (int i = 0; i < ((EPI == EPI_LNBWD) ? (BN / 32) : 1); ++i) { acc_g[i] = 0.f; acc_b[i] = 0.f; }
+    for (int i = 0; i < ((EPI == EPI_LNBWD) ? NCH : 1); ++i) { acc_g[i] = 0.f; acc_b[i] = 0.f; }
+    // cross-half row reductions (row epilogues): red[k][half][row]
+    float* s_red = reinterpret_cast<float*>(smem_raw + (red_base - smem_u32(smem_raw)));
 
     // aux prefetch for the first tile
     if constexpr (EPI == EPI_MUL) {
@@ -281,14 +298,18 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(aux_bar(ab), (aux_count >> 1) & 1u);
             aux_addr = epi_base + kAuxOff + ab * BOX_BYTES;
           }
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
+          {
             uint32_t r[32];
-            tmem_ld_x32(taddr + uint32_t(j * 64 + h * 32), r);
+            tmem_ld_x32(taddr + uint32_t(j * 64 + half * 32), r);
             tmem_ld_wait();
+            if (j == NBOX - 1) {  // accumulator fully drained into registers: hand TMEM back to the MMA warp
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(tempty_bar(acc));
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const int ch = h * 4 + i;
+              const int ch = half * 4 + i;
               const uint32_t off = swz(row, ch);
               float v[8];
 #pragma unroll
@@ -307,12 +328,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               } else {  // EPI_GELU2
                 float a[8], g[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  const float u = round_bf16(v[e]);
-                  a[e] = gelu_erf(u);
-                  g[e] = gelu_erf_grad(u);
-                  const int col = n0 + j * 64 + ch * 8 + e;
-                  if (col == args.ones_col) { a[e] = 1.0f; g[e] = 0.0f; }
+                for (int e = 0; e < 8; ++e) gelu_pair(round_bf16(v[e]), a[e], g[e]);
+                const int col0 = n0 + j * 64 + ch * 8;
+                if (args.ones_col >= col0 && args.ones_col < col0 + 8) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e)
+                    if (col0 + e == args.ones_col) { a[e] = 1.0f; g[e] = 0.0f; }
                 }
                 sts128(out0 + off, make_uint4(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]),
                                               pack_bf16(a[4], a[5]), pack_bf16(a[6], a[7])));
@@ -320,11 +341,6 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                                           pack_bf16(g[4], g[5]), pack_bf16(g[6], g[7])));
               }
             }
-          }
-          if (j == NBOX - 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
           }
           fence_proxy_async();
           named_bar_sync(1, GEMM_EPI_THREADS);
@@ -341,12 +357,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t T0 = epi_base;                      // RES_LN: residual -> v ; LNBWD: x (LN input)
         const uint32_t T1 = epi_base + NBOX * BOX_BYTES;   // RES_LN: LN output   ; LNBWD: dres -> out
         const float inv_n = 1.0f / float(args.n_real);
+        const int c_begin = half * NCH * 32, c_end = c_begin + NCH * 32;  // this thread's column range
         mbar_wait(aux_bar(0), aux_count & 1u);
         ++aux_count;
         if constexpr (EPI == EPI_RES_LN) {
           float sum = 0.f;
 #pragma unroll 1
-          for (int c32 = 0; c32 < BN / 32; ++c32) {
+          for (int c32 = half * NCH; c32 < (half + 1) * NCH; ++c32) {
             uint32_t r[32];
             tmem_ld_x32(taddr + uint32_t(c32 * 32), r);
             tmem_ld_wait();
@@ -370,10 +387,17 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(acc));
-          const float mean = sum * inv_n;
+          s_red[(0 * 2 + half) * 128 + row] = sum;
+          fence_proxy_async();
+          named_bar_sync(1, GEMM_EPI_THREADS);
+          if (elected) {  // v (= new residual stream) is complete in T0
+            for (int b = 0; b < NBOX; ++b) tma_store_2d(&tmC, T0 + b * BOX_BYTES, n0 + b * 64, m0);
+            tma_store_commit();
+          }
+          const float mean = (s_red[(0 * 2 + 0) * 128 + row] + s_red[(0 * 2 + 1) * 128 + row]) * inv_n;
           float var = 0.f;
 #pragma unroll 1
-          for (int c = 0; c < BN; c += 8) {
+          for (int c = c_begin; c < c_end; c += 8) {
             const uint4 xv = lds128(T0 + (c >> 6) * BOX_BYTES + swz(row, (c & 63) >> 3));
             const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
@@ -383,18 +407,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (c + 2 * e + 1 < args.n_real) var += d1 * d1;
             }
           }
-          const float rstd = rsqrtf(var * inv_n + args.eps);
-          if (args.stats != nullptr) {
-            reinterpret_cast<float2*>(args.stats)[m0 + row] = make_float2(mean, rstd);
-          }
-          fence_proxy_async();
+          s_red[(1 * 2 + half) * 128 + row] = var;
           named_bar_sync(1, GEMM_EPI_THREADS);
-          if (elected) {
-            for (int b = 0; b < NBOX; ++b) tma_store_2d(&tmC, T0 + b * BOX_BYTES, n0 + b * 64, m0);
-            tma_store_commit();
-          }
+          var = s_red[(1 * 2 + 0) * 128 + row] + s_red[(1 * 2 + 1) * 128 + row];
+          const float rstd = rsqrtf(var * inv_n + args.eps);
+          if (half == 0 && args.stats != nullptr)
+            reinterpret_cast<float2*>(args.stats)[m0 + row] = make_float2(mean, rstd);
 #pragma unroll 1
-          for (int c = 0; c < BN; c += 8) {
+          for (int c = c_begin; c < c_end; c += 8) {
             const uint32_t boff = (c >> 6) * BOX_BYTES + swz(row, (c & 63) >> 3);
             const uint4 xv = lds128(T0 + boff);
             const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
@@ -427,7 +447,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const float mean = st.x, rstd = st.y;
           float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
-          for (int c32 = 0; c32 < BN / 32; ++c32) {
+          for (int c32 = half * NCH; c32 < (half + 1) * NCH; ++c32) {
             uint32_t r[32];
             tmem_ld_x32(taddr + uint32_t(c32 * 32), r);
             tmem_ld_wait();
@@ -454,12 +474,16 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const float cg = warp_colsum32(pg, lane);
             const float cb = warp_colsum32(pb, lane);
 #pragma unroll
-            for (int k = 0; k < BN / 32; ++k)
-              if (k == c32) { acc_g[k] += cg; acc_b[k] += cb; }
+            for (int k = 0; k < NCH; ++k)
+              if (k == c32 - half * NCH) { acc_g[k] += cg; acc_b[k] += cb; }
           }
-          const float c1 = s1 * inv_n, c2 = s2 * inv_n;
+          s_red[(0 * 2 + half) * 128 + row] = s1;
+          s_red[(1 * 2 + half) * 128 + row] = s2;
+          named_bar_sync(1, GEMM_EPI_THREADS);
+          const float c1 = (s_red[(0 * 2 + 0) * 128 + row] + s_red[(0 * 2 + 1) * 128 + row]) * inv_n;
+          const float c2 = (s_red[(1 * 2 + 0) * 128 + row] + s_red[(1 * 2 + 1) * 128 + row]) * inv_n;
 #pragma unroll 1
-          for (int c32 = 0; c32 < BN / 32; ++c32) {
+          for (int c32 = half * NCH; c32 < (half + 1) * NCH; ++c32) {
             uint32_t r[32];
             tmem_ld_x32(taddr + uint32_t(c32 * 32), r);
             tmem_ld_wait();
@@ -503,19 +527,18 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
-        // all epilogue threads must not touch T0/T1 of the next tile before the elected thread has
-        // re-armed them; the aux mbarrier wait at the top of the next iteration provides that order,
-        // but the *writes* of this iteration must be complete first:
+        // s_red is rewritten by the next tile only after its first named barrier... not guaranteed: a fast
+        // thread could overwrite s_red[0] while a slow one still reads it, so close the tile with a barrier.
         named_bar_sync(1, GEMM_EPI_THREADS);
       }
     }
     if constexpr (EPI == EPI_LNBWD) {
-      // per-CTA column sums: 4 warps -> smem (re-using the idle tile buffers) -> one row of partials per CTA
+      // per-CTA column sums: 8 warps -> smem (re-using the idle tile buffers) -> one row of partials per CTA
       float* s_part = reinterpret_cast<float*>(smem_raw + (epi_base - smem_u32(smem_raw)));  // [4][2][BN]
 #pragma unroll
-      for (int k = 0; k < BN / 32; ++k) {
-        s_part[(q * 2 + 0) * BN + k * 32 + lane] = acc_g[k];
-        s_part[(q * 2 + 1) * BN + k * 32 + lane] = acc_b[k];
+      for (int k = 0; k < NCH; ++k) {
+        s_part[(q * 2 + 0) * BN + (half * NCH + k) * 32 + lane] = acc_g[k];
+        s_part[(q * 2 + 1) * BN + (half * NCH + k) * 32 + lane] = acc_b[k];
       }
       named_bar_sync(1, GEMM_EPI_THREADS);
       const int e = threadIdx.x - 64;

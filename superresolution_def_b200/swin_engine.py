@@ -157,6 +157,7 @@ class SwinStackFunction(torch.autograd.Function):
         ctx.cfg, ctx.geom, ctx.shifts, ctx.saved_acts = cfg, geom, shifts, saved
         ctx.params = tensors
         ctx.mark_non_differentiable(cur_xn, cur_stats)
+        ctx.set_materialize_grads(False)
         return cur_x, cur_xn, cur_stats
 
     @staticmethod

@@ -1,0 +1,42 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/srk.h declares (no compute calls)."""
+import ctypes
+import re
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _declared_symbols():
+    text = (ROOT / "include" / "srk.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(srk_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from superresolution_def_b200 import _build
+    lib = ctypes.CDLL(str(_build.build()))
+    syms = _declared_symbols()
+    assert len(syms) >= 15
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+    lib.srk_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.srk_version()
+
+
+def test_binding_rejects_cpu_tensors():
+    import pytest
+    import torch
+    from superresolution_def_b200 import _capi as capi
+    from superresolution_def_b200.architecture_swin import SwinTransformerBlock
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    blk = SwinTransformerBlock(180, (16, 16), 6, window_size=8)
+    with pytest.raises((capi.SrkError, AssertionError, RuntimeError)):
+        blk(torch.randn(1, 256, 180))  # no CPU fallback: must fail loudly
+
+
+def test_shape_helpers_without_gpu():
+    from superresolution_def_b200 import _capi as capi
+    d = capi.SrkBlockDims(180, 192, 6, 30, 32, 720, 768)
+    assert capi.block_weight_elems(d) == [110592, 110592, 36864, 36864, 147456, 147456, 147456, 147456]
+    assert capi.block_bwd_scratch_floats(d, capi.SrkGeom(16, 128, 128, 8, 0)) > 0

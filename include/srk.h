@@ -153,6 +153,48 @@ int srk_layernorm_bwd(const void* dy, int lddy, const void* x, int ldx, const fl
                       int rows, int C, int Cp, void* stream);
 long long srk_layernorm_bwd_ws_floats(int Cp);
 
+/* ======================================================================================================
+ * Convolutional paths: 3x3 / stride 1 / pad 1 on NHWC bf16 activations, implicit GEMM on tcgen05.
+ * Replace nn.Conv2d(3x3) + nn.LeakyReLU + nn.PixelShuffle + residual adds in SwinIR's head/tail
+ * (architecture_swin.py:202,222-230,175-190) and HAT's CAB / RHAG / head (hat_arch.py:66-74,608,859-869).
+ * ====================================================================================================== */
+#define SRK_CEPI_BIAS 0       /* y = conv + bias                                         */
+#define SRK_CEPI_BIAS_LRELU 1 /* y = leaky_relu(conv + bias, slope)                      */
+#define SRK_CEPI_BIAS_RES 2   /* y = conv + bias + r                                     */
+#define SRK_CEPI_MASK_LRELU 3 /* y = conv * (r > 0 ? 1 : slope)   (LeakyReLU backward)   */
+#define SRK_CEPI_BIAS_GELU 4  /* y = gelu(conv + bias), y2 = gelu'(conv + bias)          */
+#define SRK_CEPI_MUL 5        /* y = conv * r                     (GELU backward)        */
+
+/* w [Cout,Cin,3,3] fp32 -> wf [Cout_p, 9*Cin_p] bf16 (forward operand), wt [Cin_p, 9*Cout_p] bf16 (flipped /
+ * transposed operand of the input gradient, may be NULL), bias_packed [Cout_p] fp32 (may be NULL).
+ * ps != 0: output channels are permuted so that a following PixelShuffle(2) becomes a strided store. */
+int srk_conv3x3_prep_weights(const float* w, const float* bias, int Cout, int Cin, int Cout_p, int Cin_p, int ps,
+                             void* wf, void* wt, float* bias_packed, void* stream);
+/* y = epilogue(conv3x3(x, wk)).  x: [B,H,W,Cin_p]; if x_ps, x is a pixel-shuffled tensor [B,2H,2W,64] read as
+ * 256 channels (input-gradient of a PixelShuffle layer).  y: [B,H,W,Cout_p]; if y_ps (Cout_p == 256), y is written
+ * directly in pixel-shuffled form [B,2H,2W,64].  H % 8 == 0, W % 16 == 0, channels multiples of 64 (<= 256). */
+int srk_conv3x3_igemm(int epi, int B, int H, int W, int Cin_p, int Cout_p, int n_real, const void* x, int x_ps,
+                      const void* wk, const float* bias, float slope, void* y, int y_ps, void* y2, const void* r,
+                      void* stream);
+/* dw [Cout,Cin,3,3] fp32 = weight gradient; dy: [B,H,W,Cout_p] (or pixel-shuffled if ps), x: [B,H,W,Cin_p]. */
+int srk_conv3x3_wgrad(int B, int H, int W, int Cin, int Cout, int Cin_p, int Cout_p, int ps, const void* dy,
+                      const void* x, float* ws, float* dw, void* stream);
+long long srk_conv3x3_wgrad_ws_floats(int Cin_p, int Cout_p);
+/* db[n_out] = sum over pixels of dy ([B,H,W,C] bf16, or pixel-shuffled [B,2H,2W,C/4] if ps). ws: srk_small_ws_floats */
+int srk_bias_grad_nhwc(const void* dy, int B, int H, int W, int C, int ps, float* ws, float* db, int n_out,
+                       void* stream);
+long long srk_small_ws_floats(void);
+/* conv_first (1 -> C): x fp32 [B,H,W] -> y token-major bf16 [B*H*W, Cp]; and its weight/bias gradient */
+int srk_conv_in1_fwd(const float* x, const float* w, const float* bias, void* y, int B, int H, int W, int C, int Cp,
+                     void* stream);
+int srk_conv_in1_wgrad(const float* x, const void* dy, float* ws, float* dw, float* db, int B, int H, int W, int C,
+                       int Cp, void* stream);
+/* conv_last (64 -> 1): x NHWC bf16 [B,H,W,64] -> y fp32 [B,H,W]; backward gives dx (bf16), dw [1,64,3,3], db [1] */
+int srk_conv_out1_fwd(const void* x, const float* w, const float* bias, float* y, int B, int H, int W, int C,
+                      void* stream);
+int srk_conv_out1_bwd(const float* dy, const void* x, const float* w, void* dx, float* ws, float* dw, float* db, int B,
+                      int H, int W, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

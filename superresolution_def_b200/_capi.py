@@ -266,3 +266,85 @@ def layernorm_bwd(dy, x, stats, gamma, dres, dx, dgamma, dbeta, C):
     rc = _ln_bwd(_ptr(dy), _ld(dy), _ptr(x), _ld(x), _ptr(stats), _ptr(gamma), _ptr(dres), _ld(dres) if dres is not None else 0,
                  _ptr(dx), _ld(dx), _ptr(ws), _ptr(dgamma), _ptr(dbeta), rows, C, Cp, _stream())
     _check(rc, "srk_layernorm_bwd")
+
+
+# ---------------------------------------------------------------------------------------------------
+# Convolution API (include/srk.h, third part)
+# ---------------------------------------------------------------------------------------------------
+CEPI_BIAS, CEPI_BIAS_LRELU, CEPI_BIAS_RES, CEPI_MASK_LRELU, CEPI_BIAS_GELU, CEPI_MUL = range(6)
+_conv_prep = _sig("srk_conv3x3_prep_weights", [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                               c_void_p, c_void_p, c_void_p])
+_conv_igemm = _sig("srk_conv3x3_igemm", [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
+                                         c_void_p, c_float, c_void_p, c_int, c_void_p, c_void_p, c_void_p])
+_conv_wgrad = _sig("srk_conv3x3_wgrad", [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_void_p])
+lib.srk_conv3x3_wgrad_ws_floats.restype = c_longlong
+lib.srk_conv3x3_wgrad_ws_floats.argtypes = [c_int, c_int]
+lib.srk_small_ws_floats.restype = c_longlong
+_bias_grad = _sig("srk_bias_grad_nhwc", [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                                         c_void_p])
+_conv_in1_fwd = _sig("srk_conv_in1_fwd", [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                          c_void_p])
+_conv_in1_wgrad = _sig("srk_conv_in1_wgrad", [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                              c_int, c_int, c_void_p])
+_conv_out1_fwd = _sig("srk_conv_out1_fwd", [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                            c_void_p])
+_conv_out1_bwd = _sig("srk_conv_out1_bwd", [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                            c_int, c_int, c_int, c_int, c_void_p])
+
+_ws_cache: dict = {}
+
+
+def _ws(n: int, device) -> torch.Tensor:
+    """A reusable fp32 workspace of at least n floats (same-stream reuse is ordered by the stream)."""
+    k = str(device)
+    t = _ws_cache.get(k)
+    if t is None or t.numel() < n:
+        t = _ws_cache[k] = torch.empty(max(n, 1 << 22), device=device, dtype=torch.float32)
+    return t
+
+
+def conv3x3_prep_weights(w, bias, Cout_p, Cin_p, ps, wf, wt, bias_packed):
+    Cout, Cin = w.shape[0], w.shape[1]
+    rc = _conv_prep(_ptr(w), _ptr(bias), Cout, Cin, Cout_p, Cin_p, int(ps), _ptr(wf), _ptr(wt), _ptr(bias_packed),
+                    _stream())
+    _check(rc, "srk_conv3x3_prep_weights")
+
+
+def conv3x3_igemm(epi, B, H, W, Cin_p, Cout_p, n_real, x, wk, bias, y, x_ps=False, y_ps=False, y2=None, r=None,
+                  slope=0.01):
+    rc = _conv_igemm(epi, B, H, W, Cin_p, Cout_p, n_real, _ptr(x), int(x_ps), _ptr(wk), _ptr(bias), slope, _ptr(y),
+                     int(y_ps), _ptr(y2), _ptr(r), _stream())
+    _check(rc, "srk_conv3x3_igemm")
+
+
+def conv3x3_wgrad(B, H, W, Cin, Cout, Cin_p, Cout_p, ps, dy, x, dw):
+    ws = _ws(int(lib.srk_conv3x3_wgrad_ws_floats(Cin_p, Cout_p)), x.device)
+    rc = _conv_wgrad(B, H, W, Cin, Cout, Cin_p, Cout_p, int(ps), _ptr(dy), _ptr(x), _ptr(ws), _ptr(dw), _stream())
+    _check(rc, "srk_conv3x3_wgrad")
+
+
+def bias_grad_nhwc(dy, B, H, W, C, ps, db):
+    ws = _ws(int(lib.srk_small_ws_floats()), dy.device)
+    rc = _bias_grad(_ptr(dy), B, H, W, C, int(ps), _ptr(ws), _ptr(db), db.numel(), _stream())
+    _check(rc, "srk_bias_grad_nhwc")
+
+
+def conv_in1_fwd(x, w, bias, y, B, H, W, C, Cp):
+    _check(_conv_in1_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(y), B, H, W, C, Cp, _stream()), "srk_conv_in1_fwd")
+
+
+def conv_in1_wgrad(x, dy, dw, db, B, H, W, C, Cp):
+    ws = _ws(int(lib.srk_small_ws_floats()), dy.device)
+    _check(_conv_in1_wgrad(_ptr(x), _ptr(dy), _ptr(ws), _ptr(dw), _ptr(db), B, H, W, C, Cp, _stream()),
+           "srk_conv_in1_wgrad")
+
+
+def conv_out1_fwd(x, w, bias, y, B, H, W, C):
+    _check(_conv_out1_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(y), B, H, W, C, _stream()), "srk_conv_out1_fwd")
+
+
+def conv_out1_bwd(dy, x, w, dx, dw, db, B, H, W, C):
+    ws = _ws(int(lib.srk_small_ws_floats()), dy.device)
+    _check(_conv_out1_bwd(_ptr(dy), _ptr(x), _ptr(w), _ptr(dx), _ptr(ws), _ptr(dw), _ptr(db), B, H, W, C, _stream()),
+           "srk_conv_out1_bwd")

@@ -1,0 +1,225 @@
+// api_conv.cu — C-ABI entry points for the convolutional paths (implicit-GEMM conv3x3 fwd/dgrad/wgrad with
+// fused bias / LeakyReLU / residual / PixelShuffle / GELU epilogues, and the 1-channel head/tail convolutions).
+#include "conv3x3.cuh"
+#include "conv_aux.cuh"
+#include "srk_host.h"
+
+using namespace srk;
+
+namespace {
+
+// maps for an NHWC tensor [B,H,W,Cp]; when `ps`, the memory is the pixel-shuffled tensor [B,2H,2W,Cp/4] and the
+// four maps view its sub-pixel lattices (i,j) with 64 channels each.
+int make_act_maps(CUtensorMap* m4, const void* ptr, int B, int H, int W, int Cp, int ps, int bw, int bh) {
+  if (!ps) return make_tmap_nhwc(&m4[0], ptr, Cp, W, H, B, Cp, (uint64_t)W * Cp, (uint64_t)H * W * Cp, bw, bh);
+  if (Cp != 256) return fail(SRK_ERR_UNSUPPORTED, "pixel-shuffle views need 256 conv channels (4 x 64)");
+  const uint64_t Cg = 64, W2 = 2 * (uint64_t)W, H2 = 2 * (uint64_t)H;
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 2; ++j) {
+      const char* base = static_cast<const char*>(ptr) + ((uint64_t)i * W2 + j) * Cg * 2;
+      int rc = make_tmap_nhwc(&m4[i * 2 + j], base, Cg, W, H, B, 2 * Cg, 2 * W2 * Cg, H2 * W2 * Cg, bw, bh);
+      if (rc) return rc;
+    }
+  return SRK_OK;
+}
+
+template <int BN, int EPI>
+int launch_conv(const ConvMaps& maps, const ConvArgs& a, cudaStream_t stream) {
+  using Cfg = ConvCfg<BN, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    SRK_CUDA_OK(cudaFuncSetAttribute(conv3x3_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int tiles = a.B * (a.H / CONV_TH) * (a.W / CONV_TW) * (a.Cout_p / BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  conv3x3_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(maps, a);
+  SRK_LAUNCHED(1);
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+template <int BNW>
+int launch_conv_wgrad(const ConvWgradMaps& maps, const ConvWgradArgs& a, cudaStream_t stream) {
+  using Cfg = WgradCfg<BNW>;
+  static bool configured = false;
+  if (!configured) {
+    SRK_CUDA_OK(cudaFuncSetAttribute(conv3x3_wgrad_kernel<BNW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg::kSmemBytes));
+    configured = true;
+  }
+  conv3x3_wgrad_kernel<BNW><<<a.co_tiles * 9 * a.splits, WG_THREADS, Cfg::kSmemBytes, stream>>>(maps, a);
+  SRK_LAUNCHED(1);
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+int conv_wgrad_splits(int B, int H, int W, int co_tiles) {
+  int s = num_sms() / (co_tiles * 9);
+  const int iters = B * (H / 4) * (W / 16);
+  if (s > iters) s = iters;
+  return s < 1 ? 1 : s;
+}
+
+}  // namespace
+
+extern "C" int srk_conv3x3_prep_weights(const float* w, const float* bias, int Cout, int Cin, int Cout_p, int Cin_p,
+                                        int ps, void* wf, void* wt, float* bias_packed, void* stream_) {
+  if (Cout_p % 64 || Cin_p % 64 || Cout > Cout_p || Cin > Cin_p) return fail(SRK_ERR_ARG, "conv prep: bad padding");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  conv_prep_weights_kernel<<<num_sms() * 2, 256, 0, stream>>>(w, bias, static_cast<__nv_bfloat16*>(wf),
+                                                              static_cast<__nv_bfloat16*>(wt), bias_packed, Cout, Cin,
+                                                              Cout_p, Cin_p, ps);
+  SRK_LAUNCHED(1);
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+extern "C" int srk_conv3x3_igemm(int epi, int B, int H, int W, int Cin_p, int Cout_p, int n_real, const void* x,
+                                 int x_ps, const void* wk, const float* bias, float slope, void* y, int y_ps,
+                                 void* y2, const void* r, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (H % CONV_TH || W % CONV_TW) return fail(SRK_ERR_UNSUPPORTED, "conv3x3: H % 8 == 0 and W % 16 == 0 required");
+  if (Cin_p % 64 || Cout_p % 64 || Cout_p > 256 || Cin_p > 256) return fail(SRK_ERR_UNSUPPORTED, "conv3x3: channels must be multiples of 64, <= 256");
+  if (!x || !wk || !y) return fail(SRK_ERR_ARG, "conv3x3: null pointer");
+  ConvMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  int rc;
+  if ((rc = make_act_maps(maps.a, x, B, H, W, Cin_p, x_ps, CONV_TW, CONV_TH))) return rc;
+  if ((rc = make_act_maps(maps.c, y, B, H, W, Cout_p, y_ps, CONV_TW, CONV_TH))) return rc;
+  for (int i = 1; i < 4; ++i) {
+    if (!x_ps) maps.a[i] = maps.a[0];
+    if (!y_ps) maps.c[i] = maps.c[0];
+  }
+  maps.c2 = maps.c[0];
+  maps.r = maps.c[0];
+  if (y2 && (rc = make_tmap_nhwc(&maps.c2, y2, Cout_p, W, H, B, Cout_p, (uint64_t)W * Cout_p, (uint64_t)H * W * Cout_p, CONV_TW, CONV_TH))) return rc;
+  if (r && (rc = make_tmap_nhwc(&maps.r, r, Cout_p, W, H, B, Cout_p, (uint64_t)W * Cout_p, (uint64_t)H * W * Cout_p, CONV_TW, CONV_TH))) return rc;
+  const int bn = Cout_p;  // one N tile covers all output channels (64 / 128 / 192 / 256)
+  if ((rc = make_tmap_2d(&maps.w, wk, Cout_p, 9 * (uint64_t)Cin_p, 9 * (uint64_t)Cin_p, bn))) return rc;
+  ConvArgs a{};
+  a.B = B; a.H = H; a.W = W; a.Cin_p = Cin_p; a.Cout_p = Cout_p; a.n_real = n_real; a.bias = bias; a.slope = slope;
+  a.a_split = x_ps; a.c_split = y_ps;
+  const bool need_r = (epi == CEPI_BIAS_RES || epi == CEPI_MASK_LRELU || epi == CEPI_MUL);
+  if (need_r && (!r || y_ps)) return fail(SRK_ERR_ARG, "conv3x3: epilogue needs an aux tensor (and a plain output)");
+  if (epi == CEPI_BIAS_GELU && (!y2 || y_ps)) return fail(SRK_ERR_ARG, "conv3x3: GELU epilogue needs y2");
+#define SRK_CCASE(BN_, EPI_) if (bn == BN_ && epi == EPI_) return launch_conv<BN_, EPI_>(maps, a, stream);
+  SRK_CCASE(64, CEPI_BIAS) SRK_CCASE(128, CEPI_BIAS) SRK_CCASE(192, CEPI_BIAS) SRK_CCASE(256, CEPI_BIAS)
+  SRK_CCASE(64, CEPI_BIAS_LRELU) SRK_CCASE(192, CEPI_BIAS_LRELU)
+  SRK_CCASE(192, CEPI_BIAS_RES) SRK_CCASE(64, CEPI_BIAS_RES)
+  SRK_CCASE(64, CEPI_MASK_LRELU) SRK_CCASE(192, CEPI_MASK_LRELU)
+  SRK_CCASE(64, CEPI_BIAS_GELU) SRK_CCASE(128, CEPI_BIAS_GELU)
+  SRK_CCASE(64, CEPI_MUL) SRK_CCASE(128, CEPI_MUL)
+#undef SRK_CCASE
+  return fail(SRK_ERR_UNSUPPORTED, "conv3x3: no kernel instance for (Cout_p, epilogue)");
+}
+
+extern "C" long long srk_conv3x3_wgrad_ws_floats(int Cin_p, int Cout_p) {
+  return (long long)num_sms() * 128 * Cin_p + 16;  // co_tiles*9*splits <= num_sms tiles of [128 x Cin_p]
+}
+
+extern "C" int srk_conv3x3_wgrad(int B, int H, int W, int Cin, int Cout, int Cin_p, int Cout_p, int ps,
+                                 const void* dy, const void* x, float* ws, float* dw, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (H % 4 || W % 16 || Cin_p % 64 || Cout_p % 64 || Cin_p > 256) return fail(SRK_ERR_UNSUPPORTED, "conv wgrad: shape");
+  ConvWgradMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  int rc;
+  if ((rc = make_act_maps(maps.a, dy, B, H, W, Cout_p, ps, 16, 4))) return rc;
+  if (!ps) for (int i = 1; i < 4; ++i) maps.a[i] = maps.a[0];
+  if ((rc = make_tmap_nhwc(&maps.b, x, Cin_p, W, H, B, Cin_p, (uint64_t)W * Cin_p, (uint64_t)H * W * Cin_p, 16, 4))) return rc;
+  ConvWgradArgs a{};
+  a.B = B; a.H = H; a.W = W; a.Cin_p = Cin_p; a.Cout_p = Cout_p; a.co_tiles = (Cout_p + 127) / 128;
+  a.splits = conv_wgrad_splits(B, H, W, a.co_tiles); a.partials = ws; a.a_split = ps;
+  switch (Cin_p) {
+    case 64: rc = launch_conv_wgrad<64>(maps, a, stream); break;
+    case 128: rc = launch_conv_wgrad<128>(maps, a, stream); break;
+    case 192: rc = launch_conv_wgrad<192>(maps, a, stream); break;
+    case 256: rc = launch_conv_wgrad<256>(maps, a, stream); break;
+    default: return fail(SRK_ERR_UNSUPPORTED, "conv wgrad: Cin_p");
+  }
+  if (rc) return rc;
+  const int total = Cout * Cin * 9;
+  conv_unpack_wgrad_kernel<<<(total + 255) / 256, 256, 0, stream>>>(ws, a.splits, a.co_tiles * 128, Cin_p, dw, Cout, Cin,
+                                                                    Cout_p, ps);
+  SRK_LAUNCHED(1);
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+extern "C" int srk_bias_grad_nhwc(const void* dy, int B, int H, int W, int C, int ps, float* ws, float* db, int n_out,
+                                  void* stream_) {
+  // dy: [B,H,W,C] bf16, or when ps the shuffled [B,2H,2W,C/4]; db[n_out]
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int grid = num_sms() * 2;
+  if (!ps) {
+    const int threads = (C / 2) * (C >= 128 ? 4 : 8);
+    colsum_nhwc_kernel<<<grid, threads, C * sizeof(float), stream>>>(static_cast<const __nv_bfloat16*>(dy),
+                                                                       (long long)B * H * W, C, C, ws);
+    SRK_LAUNCHED(1);
+    colsum_finish_kernel<<<(n_out + 127) / 128, 128, 0, stream>>>(ws, grid, C, db, n_out);
+  } else {
+    const int Cg = C / 4;
+    colsum_ps_kernel<<<grid, (Cg / 2) * 8, 4 * Cg * sizeof(float), stream>>>(static_cast<const __nv_bfloat16*>(dy), B,
+                                                                              2 * H, 2 * W, Cg, ws);
+    SRK_LAUNCHED(1);
+    colsum_finish_kernel<<<(n_out + 127) / 128, 128, 0, stream>>>(ws, grid, C, db, n_out);
+  }
+  SRK_LAUNCHED(1);
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+extern "C" long long srk_small_ws_floats(void) { return (long long)num_sms() * 2 * 4096; }
+
+extern "C" int srk_conv_in1_fwd(const float* x, const float* w, const float* bias, void* y, int B, int H, int W, int C,
+                                int Cp, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  conv_in1_fwd_kernel<<<num_sms() * 8, 256, Cp * 10 * sizeof(float), stream>>>(x, w, bias, static_cast<__nv_bfloat16*>(y),
+                                                                               B, H, W, C, Cp);
+  SRK_LAUNCHED(1);
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+extern "C" int srk_conv_in1_wgrad(const float* x, const void* dy, float* ws, float* dw, float* db, int B, int H, int W,
+                                  int C, int Cp, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int grid = num_sms();
+  const int threads = (Cp / 8) * 8;  // 8 pixels in flight per block
+  conv_in1_wgrad_kernel<<<grid, threads, Cp * 10 * sizeof(float), stream>>>(x, static_cast<const __nv_bfloat16*>(dy), ws,
+                                                                            B, H, W, Cp);
+  SRK_LAUNCHED(1);
+  conv_in1_wgrad_finish_kernel<<<(C * 10 + 127) / 128, 128, 0, stream>>>(ws, grid, C, Cp, dw, db);
+  SRK_LAUNCHED(1);
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+extern "C" int srk_conv_out1_fwd(const void* x, const float* w, const float* bias, float* y, int B, int H, int W, int C,
+                                 void* stream_) {
+  if (C != 64) return fail(SRK_ERR_UNSUPPORTED, "conv_out1: 64 input channels");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  conv_out1_fwd_kernel<64><<<num_sms() * 8, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), w, bias, y, B, H, W);
+  SRK_LAUNCHED(1);
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+extern "C" int srk_conv_out1_bwd(const float* dy, const void* x, const float* w, void* dx, float* ws, float* dw, float* db,
+                                 int B, int H, int W, int C, void* stream_) {
+  if (C != 64) return fail(SRK_ERR_UNSUPPORTED, "conv_out1: 64 input channels");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  conv_out1_dgrad_kernel<64><<<num_sms() * 8, 256, 0, stream>>>(dy, w, static_cast<__nv_bfloat16*>(dx), B, H, W);
+  SRK_LAUNCHED(1);
+  const int grid = num_sms() * 2;
+  conv_out1_wgrad_kernel<64><<<grid, 256, 0, stream>>>(dy, static_cast<const __nv_bfloat16*>(x), ws, B, H, W);
+  SRK_LAUNCHED(1);
+  colsum_finish_kernel<<<(64 * 9 + 1 + 127) / 128, 128, 0, stream>>>(ws, grid, 64 * 9 + 1, ws + (size_t)grid * (64 * 9 + 1), 64 * 9 + 1);
+  SRK_LAUNCHED(1);
+  SRK_CUDA_OK(cudaMemcpyAsync(dw, ws + (size_t)grid * (64 * 9 + 1), 64 * 9 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  SRK_CUDA_OK(cudaMemcpyAsync(db, ws + (size_t)grid * (64 * 9 + 1) + 64 * 9, sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}

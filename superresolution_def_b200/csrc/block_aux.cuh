@@ -47,7 +47,7 @@ struct BlockWeightPtrs {  // prepared bf16 operands
 };
 
 // ------------------------------------------------------------------ weight preparation
-__global__ void prep_block_weights_kernel(BlockDims d, BlockParamPtrs p, BlockWeightPtrs w) {
+static __global__ void prep_block_weights_kernel(BlockDims d, BlockParamPtrs p, BlockWeightPtrs w) {
   const int QW = 3 * d.heads * d.ds, AW = d.heads * d.ds;
   const int n0 = QW * d.Cp, n1 = d.Cp * AW, n2 = d.Hp * d.Cp, n3 = d.Cp * d.Hp;
   const int total = n0 + n1 + n2 + n3;
@@ -109,7 +109,7 @@ struct UnpackSrc {
   int n_ln_part, n_rpb_part, table_rows;  // table_rows = (2ws-1)^2
 };
 
-__global__ void unpack_block_grads_kernel(BlockDims d, UnpackSrc s, BlockGradPtrs g, float accumulate) {
+static __global__ void unpack_block_grads_kernel(BlockDims d, UnpackSrc s, BlockGradPtrs g, float accumulate) {
   const int C = d.C, AW = d.heads * d.ds;
   const int n_qkv_w = 3 * C * C, n_qkv_b = 3 * C, n_proj_w = C * C, n_proj_b = C;
   const int n_fc1_w = d.hidden * C, n_fc1_b = d.hidden, n_fc2_w = C * d.hidden, n_fc2_b = C;
@@ -164,7 +164,7 @@ __global__ void unpack_block_grads_kernel(BlockDims d, UnpackSrc s, BlockGradPtr
 
 // ------------------------------------------------------------------ standalone LayerNorm (warp per row)
 // y = LN(x[:, :C]) * gamma + beta, y[:, C] = 1 (ones column, if ones_col >= 0), other pads 0; stats = (mean, rstd)
-__global__ void ln_fwd_rows_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ y,
+static __global__ void ln_fwd_rows_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ y,
                                    int ldy, float* __restrict__ stats, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, int rows, int C, int Cp, int ones_col, float eps) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -206,7 +206,7 @@ __global__ void ln_fwd_rows_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
 }
 
 // dx = (dres ? dres : 0) + LNbackward(dy | x, stats, gamma); partial dgamma/dbeta per CTA: part[blockIdx][2][Cp]
-__global__ void ln_bwd_rows_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, const __nv_bfloat16* __restrict__ x,
+static __global__ void ln_bwd_rows_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, const __nv_bfloat16* __restrict__ x,
                                    int ldx, const float* __restrict__ stats, const float* __restrict__ gamma,
                                    const __nv_bfloat16* __restrict__ dres, int lddres, __nv_bfloat16* __restrict__ dx,
                                    int lddx, float* __restrict__ part, int rows, int C, int Cp) {
@@ -274,7 +274,7 @@ __global__ void ln_bwd_rows_kernel(const __nv_bfloat16* __restrict__ dy, int ldd
 }
 
 // out[which][c] = sum_k part[k][which][c]  (tiny finishing reduction for the standalone LN backward)
-__global__ void ln_param_grad_reduce_kernel(const float* __restrict__ part, int nparts, int Cp, int C,
+static __global__ void ln_param_grad_reduce_kernel(const float* __restrict__ part, int nparts, int Cp, int C,
                                             float* __restrict__ dgamma, float* __restrict__ dbeta) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 2 * C) return;

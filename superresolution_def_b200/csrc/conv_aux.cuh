@@ -1,0 +1,320 @@
+// conv_aux.cuh — memory-bound helpers around the implicit-GEMM convolution:
+//   weight packing / gradient unpacking (incl. the PixelShuffle channel permutation), bias gradients,
+//   and the two degenerate convolutions of the SR head/tail that have a single input or output channel
+//   (conv_first 1->C and conv_last 64->1: no GEMM shape to speak of; they are pure HBM streams).
+// Reference: models/architecture_swin.py:202 (conv_first), :230 (conv_last), :175-190 (Upsample).
+#pragma once
+#include "srk_ptx.cuh"
+
+namespace srk {
+
+// PixelShuffle(2) channel permutation: conv output channel n = c*4 + i*2 + j  <->  packed n' = (i*2+j)*64 + c
+__device__ __forceinline__ int ps_pack(int n, int cgrp) { return (n & 3) * cgrp + (n >> 2); }
+
+// W[Cout][Cin][3][3] fp32 -> Wf [Cout_p][9*Cin_p] (k = tap*Cin_p + ci) and Wt [Cin_p][9*Cout_p]
+// (flipped taps, for the input gradient).  ps: permute output channels for a fused PixelShuffle(2).
+static __global__ void conv_prep_weights_kernel(const float* __restrict__ w, const float* __restrict__ bias,
+                                         __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wt,
+                                         float* __restrict__ bias_packed, int Cout, int Cin, int Cout_p, int Cin_p,
+                                         int ps) {
+  const int total = Cout_p * 9 * Cin_p;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int np = idx / (9 * Cin_p), rem = idx % (9 * Cin_p), tap = rem / Cin_p, ci = rem % Cin_p;
+    // which real output channel lives in packed row np?
+    int n = np;
+    if (ps) { const int grp = np / (Cout_p / 4), c = np % (Cout_p / 4); n = c * 4 + grp; }
+    float v = 0.f;
+    if (n < Cout && ci < Cin) v = w[(size_t(n) * Cin + ci) * 9 + tap];
+    wf[idx] = __float2bfloat16_rn(v);
+    if (wt) wt[size_t(ci) * 9 * Cout_p + (8 - tap) * Cout_p + np] = __float2bfloat16_rn(v);
+    if (bias_packed && tap == 0 && ci == 0) bias_packed[np] = (bias && n < Cout) ? bias[n] : 0.f;
+  }
+}
+
+// partials [splits][9][co_pad][Cin_p] -> dW [Cout][Cin][3][3]
+static __global__ void conv_unpack_wgrad_kernel(const float* __restrict__ part, int splits, int co_pad, int Cin_p,
+                                         float* __restrict__ dw, int Cout, int Cin, int Cout_p, int ps) {
+  const int total = Cout * Cin * 9;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int n = i / (Cin * 9), ci = (i / 9) % Cin, tap = i % 9;
+  const int np = ps ? ps_pack(n, Cout_p / 4) : n;
+  float acc = 0.f;
+  for (int s = 0; s < splits; ++s) acc += part[((size_t(s) * 9 + tap) * co_pad + np) * Cin_p + ci];
+  dw[i] = acc;
+}
+
+// db[n] = sum over pixels of dY; dY is NHWC [B,H,W,C] or, when ps, the shuffled tensor [B,2H,2W,C/4]
+// (n = c*4 + i*2 + j).  One block per channel group; two-stage via atomics on a zeroed output is avoided:
+// grid = (nblocks), partial[blockIdx][C] then reduced by colsum_finish_kernel.
+static __global__ void colsum_nhwc_kernel(const __nv_bfloat16* __restrict__ dy, long long npix, int C, int ld,
+                                   float* __restrict__ partial) {
+  // thread t handles channel pair (t % (C/2)); rows strided by blockDim/(C/2) * gridDim
+  const int pairs = C / 2;
+  const int lanes_per_row = pairs;
+  const int rows_per_block = blockDim.x / lanes_per_row;
+  const int cp = threadIdx.x % lanes_per_row, rl = threadIdx.x / lanes_per_row;
+  float a0 = 0.f, a1 = 0.f;
+  if (rl < rows_per_block) {
+    for (long long r = (long long)blockIdx.x * rows_per_block + rl; r < npix; r += (long long)gridDim.x * rows_per_block) {
+      const uint32_t v = *reinterpret_cast<const uint32_t*>(dy + r * ld + cp * 2);
+      a0 += bf16_lo(v);
+      a1 += bf16_hi(v);
+    }
+  }
+  extern __shared__ float s_cs[];  // [C]
+  for (int i = threadIdx.x; i < C; i += blockDim.x) s_cs[i] = 0.f;
+  __syncthreads();
+  if (rl < rows_per_block) {
+    atomicAdd(&s_cs[cp * 2], a0);
+    atomicAdd(&s_cs[cp * 2 + 1], a1);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) partial[size_t(blockIdx.x) * C + i] = s_cs[i];
+}
+// ps layout: pixel index p of the shuffled image -> sub-pixel (i,j) = (Y&1, X&1); handled by running
+// colsum_nhwc_kernel per sub-pixel view is wasteful, so the finish kernel receives 4 partial sets instead.
+static __global__ void colsum_finish_kernel(const float* __restrict__ partial, int nparts, int C, float* __restrict__ out,
+                                     int n_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_out) return;
+  float acc = 0.f;
+  for (int k = 0; k < nparts; ++k) acc += partial[size_t(k) * C + i];
+  out[i] = acc;
+}
+// shuffled-gradient bias sum: dYs [B,2H,2W,Cg]; out[c*4 + i*2 + j] = sum over pixels with (Y&1,X&1) == (i,j)
+static __global__ void colsum_ps_kernel(const __nv_bfloat16* __restrict__ dys, int B, int H2, int W2, int Cg,
+                                 float* __restrict__ partial /*[grid][4*Cg]*/) {
+  extern __shared__ float s_cs[];  // [4*Cg]
+  for (int i = threadIdx.x; i < 4 * Cg; i += blockDim.x) s_cs[i] = 0.f;
+  __syncthreads();
+  const int pairs = Cg / 2;
+  const int rows_per_block = blockDim.x / pairs;
+  const int cp = threadIdx.x % pairs, rl = threadIdx.x / pairs;
+  float acc[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+  const long long npix = (long long)B * H2 * W2;
+  if (rl < rows_per_block) {
+    for (long long r = (long long)blockIdx.x * rows_per_block + rl; r < npix; r += (long long)gridDim.x * rows_per_block) {
+      const int X = int(r % W2), Y = int((r / W2) % H2);
+      const int sub = (Y & 1) * 2 + (X & 1);
+      const uint32_t v = *reinterpret_cast<const uint32_t*>(dys + r * Cg + cp * 2);
+#pragma unroll
+      for (int s = 0; s < 4; ++s)
+        if (s == sub) { acc[s][0] += bf16_lo(v); acc[s][1] += bf16_hi(v); }
+    }
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      atomicAdd(&s_cs[(cp * 2) * 4 + s], acc[s][0]);
+      atomicAdd(&s_cs[(cp * 2 + 1) * 4 + s], acc[s][1]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 4 * Cg; i += blockDim.x) partial[size_t(blockIdx.x) * 4 * Cg + i] = s_cs[i];
+}
+
+// ------------------------------------------------------------------ conv_first: Cin = 1 -> C, output token-major
+// y[p][co] = b[co] + sum_tap x[p + tap] * w[co][tap];  y: [B*H*W, Cp] bf16 (pads zero), x: [B,H,W] fp32
+static __global__ void conv_in1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                    const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int B, int H, int W,
+                                    int C, int Cp) {
+  extern __shared__ float s_w[];  // [Cp][10]: 9 taps + bias
+  for (int i = threadIdx.x; i < Cp * 10; i += blockDim.x) {
+    const int co = i / 10, t = i % 10;
+    s_w[i] = (co < C) ? (t < 9 ? w[co * 9 + t] : bias[co]) : 0.f;
+  }
+  __syncthreads();
+  const int groups = Cp / 8;
+  const long long total = (long long)B * H * W * groups;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int g = int(idx % groups);
+    const long long p = idx / groups;
+    const int xx = int(p % W), yy = int((p / W) % H);
+    const long long base = p - (long long)yy * W - xx;  // start of image b
+    float v[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int sy = yy + t / 3 - 1, sx = xx + t % 3 - 1;
+      v[t] = (sy >= 0 && sy < H && sx >= 0 && sx < W) ? x[base + (long long)sy * W + sx] : 0.f;
+    }
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float* ww = s_w + (g * 8 + e) * 10;
+      float a = ww[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) a = fmaf(v[t], ww[t], a);
+      o[e] = a;
+    }
+    *reinterpret_cast<uint4*>(y + p * Cp + g * 8) =
+        make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+  }
+}
+
+// dW[co][tap] = sum_p dY[p][co] * x[p+tap], db[co] = sum_p dY[p][co]; partial[blockIdx][Cp][10]
+static __global__ void conv_in1_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                      float* __restrict__ partial, int B, int H, int W, int Cp) {
+  extern __shared__ float s_acc[];  // [Cp][10]
+  for (int i = threadIdx.x; i < Cp * 10; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  const int groups = Cp / 8;
+  const int pix_per_block = blockDim.x / groups;
+  const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
+  float acc[8][10];
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+#pragma unroll
+    for (int t = 0; t < 10; ++t) acc[e][t] = 0.f;
+  const long long npix = (long long)B * H * W;
+  if (pl < pix_per_block) {
+    for (long long p = (long long)blockIdx.x * pix_per_block + pl; p < npix; p += (long long)gridDim.x * pix_per_block) {
+      const int xx = int(p % W), yy = int((p / W) % H);
+      const long long base = p - (long long)yy * W - xx;
+      float v[10];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int sy = yy + t / 3 - 1, sx = xx + t % 3 - 1;
+        v[t] = (sy >= 0 && sy < H && sx >= 0 && sx < W) ? x[base + (long long)sy * W + sx] : 0.f;
+      }
+      v[9] = 1.f;
+      const uint4 d = *reinterpret_cast<const uint4*>(dy + p * Cp + g * 8);
+      const uint32_t dw[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float dv = (e & 1) ? bf16_hi(dw[e >> 1]) : bf16_lo(dw[e >> 1]);
+#pragma unroll
+        for (int t = 0; t < 10; ++t) acc[e][t] = fmaf(dv, v[t], acc[e][t]);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+#pragma unroll
+      for (int t = 0; t < 10; ++t) atomicAdd(&s_acc[(g * 8 + e) * 10 + t], acc[e][t]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < Cp * 10; i += blockDim.x) partial[size_t(blockIdx.x) * Cp * 10 + i] = s_acc[i];
+}
+static __global__ void conv_in1_wgrad_finish_kernel(const float* __restrict__ partial, int nparts, int C, int Cp,
+                                             float* __restrict__ dw, float* __restrict__ db) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * 10) return;
+  const int co = i / 10, t = i % 10;
+  float acc = 0.f;
+  for (int k = 0; k < nparts; ++k) acc += partial[size_t(k) * Cp * 10 + i];
+  if (t < 9) dw[co * 9 + t] = acc; else db[co] = acc;
+}
+
+// ------------------------------------------------------------------ conv_last: C(=64) -> 1, NHWC bf16 in, fp32 out
+// 8 lanes per output pixel, each lane owns 8 input channels; 4 pixels per warp.
+template <int C>
+static __global__ void conv_out1_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w /*[1][C][3][3]*/,
+                                     const float* __restrict__ bias, float* __restrict__ y, int B, int H, int W) {
+  static_assert(C == 64, "conv_out1 is specialised for 64 input channels");
+  __shared__ float s_w[9][C];
+  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) s_w[i / C][i % C] = w[(i % C) * 9 + i / C];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, sub = lane >> 3, cl = lane & 7;
+  const long long npix = (long long)B * H * W;
+  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const float b0 = bias[0];
+  for (long long p0 = warp_id * 4; p0 < npix; p0 += nwarps * 4) {
+    const long long p = p0 + sub;
+    float acc = 0.f;
+    if (p < npix) {
+      const int xx = int(p % W), yy = int((p / W) % H);
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int sy = yy + t / 3 - 1, sx = xx + t % 3 - 1;
+        if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
+          const long long q = p + (long long)(t / 3 - 1) * W + (t % 3 - 1);
+          const uint4 v = *reinterpret_cast<const uint4*>(x + q * C + cl * 8);
+          const uint32_t vw[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            acc = fmaf(bf16_lo(vw[e]), s_w[t][cl * 8 + 2 * e], acc);
+            acc = fmaf(bf16_hi(vw[e]), s_w[t][cl * 8 + 2 * e + 1], acc);
+          }
+        }
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (cl == 0 && p < npix) y[p] = acc + b0;
+  }
+}
+
+// dX[p][c] = sum_tap dY[p - off(tap)] * w[c][tap]   (dY fp32 [B,H,W], dX NHWC bf16)
+template <int C>
+static __global__ void conv_out1_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                       __nv_bfloat16* __restrict__ dx, int B, int H, int W) {
+  __shared__ float s_w[9][C];
+  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) s_w[i / C][i % C] = w[(i % C) * 9 + i / C];
+  __syncthreads();
+  constexpr int G = C / 8;
+  const long long total = (long long)B * H * W * G;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int g = int(idx % G);
+    const long long p = idx / G;
+    const int xx = int(p % W), yy = int((p / W) % H);
+    float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      // output pixel q = p - off(tap) received x[p] through tap t
+      const int sy = yy - (t / 3 - 1), sx = xx - (t % 3 - 1);
+      if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
+        const float d = dy[p - (long long)(t / 3 - 1) * W - (t % 3 - 1)];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = fmaf(d, s_w[t][g * 8 + e], o[e]);
+      }
+    }
+    *reinterpret_cast<uint4*>(dx + p * C + g * 8) =
+        make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+  }
+}
+
+// dW[c][tap] = sum_p dY[p] * x[p + off(tap)][c], db = sum_p dY[p]; partial[blockIdx][C*9 + 1]
+template <int C>
+static __global__ void conv_out1_wgrad_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                                       float* __restrict__ partial, int B, int H, int W) {
+  __shared__ float s_acc[C * 9 + 1];
+  for (int i = threadIdx.x; i < C * 9 + 1; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  constexpr int G = C / 8;
+  const int g = threadIdx.x % G, pl = threadIdx.x / G, ppb = blockDim.x / G;
+  float acc[8][9];
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[e][t] = 0.f;
+  float accb = 0.f;
+  const long long npix = (long long)B * H * W;
+  for (long long p = (long long)blockIdx.x * ppb + pl; p < npix; p += (long long)gridDim.x * ppb) {
+    // gather form: input pixel p contributes to output pixel q = p - off(tap) through tap t
+    const int xx = int(p % W), yy = int((p / W) % H);
+    const uint4 v = *reinterpret_cast<const uint4*>(x + p * C + g * 8);
+    const uint32_t vw[4] = {v.x, v.y, v.z, v.w};
+    float xv[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) xv[e] = (e & 1) ? bf16_hi(vw[e >> 1]) : bf16_lo(vw[e >> 1]);
+    if (g == 0) accb += dy[p];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int sy = yy - (t / 3 - 1), sx = xx - (t % 3 - 1);
+      if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
+        const float d = dy[p - (long long)(t / 3 - 1) * W - (t % 3 - 1)];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e][t] = fmaf(d, xv[e], acc[e][t]);
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) atomicAdd(&s_acc[(g * 8 + e) * 9 + t], acc[e][t]);
+  if (g == 0) atomicAdd(&s_acc[C * 9], accb);
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * 9 + 1; i += blockDim.x) partial[size_t(blockIdx.x) * (C * 9 + 1) + i] = s_acc[i];
+}
+
+}  // namespace srk

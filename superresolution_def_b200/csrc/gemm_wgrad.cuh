@@ -143,7 +143,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 }
 
 // Sum the per-split partials: out[r][c] = sum_s partials[s][r][c]   (rows = ca_tiles*128, cols = Cb)
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partials, float* __restrict__ out,
+static __global__ void wgrad_reduce_kernel(const float* __restrict__ partials, float* __restrict__ out,
                                     int splits, int n_elems) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_elems) return;

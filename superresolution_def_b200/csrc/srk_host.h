@@ -74,6 +74,27 @@ inline int make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64
   return SRK_OK;
 }
 
+// 4-D bf16 NHWC view [B,H,W,C] with arbitrary pixel / row / image pitches (elements); box = (64 ch, bw, bh, 1).
+inline int make_tmap_nhwc(CUtensorMap* out, const void* ptr, uint64_t C, uint64_t W, uint64_t H, uint64_t B,
+                          uint64_t pix_pitch, uint64_t row_pitch, uint64_t img_pitch, uint32_t bw, uint32_t bh) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(SRK_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (pix_pitch * 2) % 16 != 0)
+    return fail(SRK_ERR_ARG, "NHWC tensor must be 16-byte aligned with 16-byte-multiple pixel pitch");
+  cuuint64_t dims[4] = {C, W, H, B};
+  cuuint64_t strides[3] = {pix_pitch * 2, row_pitch * 2, img_pitch * 2};
+  cuuint32_t box[4] = {64, bw, bh, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "[srk] cuTensorMapEncodeTiled(4d) failed: %d\n", int(r));
+    return SRK_ERR_CUDA;
+  }
+  return SRK_OK;
+}
+
 inline int num_sms() {
   static int n = 0;
   if (n == 0) {

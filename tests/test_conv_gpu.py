@@ -1,0 +1,67 @@
+"""-m gpu parity tests of the convolutional head/tail kernels against plain torch fp32 on the same (bf16-rounded)
+inputs.  Tolerances: outputs rel-L2 <= 1e-2, gradients rel-L2 <= 3e-2 (bf16 activations, fp32 accumulate)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.util import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(shape, scale=1.0, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).cuda()
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 16, 16), (1, 24, 48)])
+def test_tail_matches_torch(B, H, W):
+    from superresolution_def_b200.conv_engine import SwinIRTailFunction
+    C, Cp = 180, 192
+    T = B * H * W
+    body = torch.zeros(T, Cp, device="cuda"); body[:, :C] = _mk((T, C), seed=1); body[:, C] = 1.0
+    first = torch.zeros(T, Cp, device="cuda"); first[:, :C] = _mk((T, C), seed=2)
+    body, first = body.to(torch.bfloat16), first.to(torch.bfloat16)
+    ws = [_mk((180, 180, 3, 3), 0.03, 3), _mk((180,), 0.1, 4), _mk((64, 180, 3, 3), 0.03, 5), _mk((64,), 0.1, 6),
+          _mk((256, 64, 3, 3), 0.05, 7), _mk((256,), 0.1, 8), _mk((256, 64, 3, 3), 0.05, 9), _mk((256,), 0.1, 10),
+          _mk((1, 64, 3, 3), 0.05, 11), _mk((1,), 0.1, 12)]
+    mine = [w.clone().requires_grad_(True) for w in ws]
+    ref = [w.clone().requires_grad_(True) for w in ws]
+    bm, fm = body.clone().requires_grad_(True), first.clone().requires_grad_(True)
+    out = SwinIRTailFunction.apply(bm, fm, (B, H, W), C, *mine)
+
+    def nchw(t):
+        return t.float()[:, :C].reshape(B, H, W, C).permute(0, 3, 1, 2)
+    br, fr = body.float().clone().requires_grad_(True), first.float().clone().requires_grad_(True)
+    x = F.conv2d(nchw(br), ref[0], ref[1], padding=1) + nchw(fr)
+    x = F.leaky_relu(F.conv2d(x, ref[2], ref[3], padding=1), 0.01)
+    x = F.pixel_shuffle(F.conv2d(x, ref[4], ref[5], padding=1), 2)
+    x = F.pixel_shuffle(F.conv2d(x, ref[6], ref[7], padding=1), 2)
+    ro = F.conv2d(x, ref[8], ref[9], padding=1)
+    assert out.shape == ro.shape
+    assert rel_l2(out, ro) < 1e-2, rel_l2(out, ro)
+    w = torch.randn_like(ro)
+    (out * w).sum().backward()
+    (ro * w).sum().backward()
+    errs = {i: rel_l2(a.grad, b.grad) for i, (a, b) in enumerate(zip(mine, ref))}
+    errs["body"] = rel_l2(bm.grad[:, :C], br.grad[:, :C])
+    errs["first"] = rel_l2(fm.grad[:, :C], fr.grad[:, :C])
+    assert all(v < 3e-2 for v in errs.values()), errs
+    assert bm.grad[:, C:].abs().max() == 0 and fm.grad[:, C:].abs().max() == 0
+
+
+def test_conv_first_matches_torch():
+    from superresolution_def_b200.conv_engine import ConvFirstFunction
+    B, H, W, C, Cp = 2, 16, 24, 180, 192
+    x = torch.rand(B, 1, H, W, device="cuda")
+    w, b = _mk((C, 1, 3, 3), 0.3, 1), _mk((C,), 0.1, 2)
+    wm, bm = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    y = ConvFirstFunction.apply(x, wm, bm, Cp)
+    ref = F.conv2d(x, wr, br, padding=1).permute(0, 2, 3, 1).reshape(B * H * W, C)
+    assert rel_l2(y[:, :C], ref) < 5e-3 and y[:, C:].abs().max() == 0
+    g = torch.zeros(B * H * W, Cp, device="cuda"); g[:, :C] = torch.randn(B * H * W, C, device="cuda")
+    g = g.to(torch.bfloat16)
+    (y.float() * g.float()).sum().backward()
+    (ref * g.float()[:, :C]).sum().backward()
+    assert rel_l2(wm.grad, wr.grad) < 1e-2 and rel_l2(bm.grad, br.grad) < 1e-2

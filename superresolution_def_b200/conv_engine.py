@@ -25,34 +25,34 @@ def _pad64(c: int) -> int:
 
 
 class _ConvWeightCache:
-    """bf16 implicit-GEMM operands of one Conv2d(3x3), refreshed when the master weight / bias changed."""
+    """bf16 implicit-GEMM operands of one Conv2d(3x3); re-derived from the fp32 master weights on every forward
+    (see swin_engine._WeightCache for why no staleness test is trusted)."""
 
     def __init__(self):
-        self.key = None
         self.wf = self.wt = self.bias = None
 
-    def get(self, w, b, Cout_p, Cin_p, ps):
-        key = (w.data_ptr(), w._version, None if b is None else b._version, Cout_p, Cin_p, ps)
-        if key != self.key:
-            if self.wf is None or self.wf.numel() != Cout_p * 9 * Cin_p:
-                self.wf = torch.empty(Cout_p * 9 * Cin_p, device=w.device, dtype=BF16)
-                self.wt = torch.empty(Cin_p * 9 * Cout_p, device=w.device, dtype=BF16)
-                self.bias = torch.empty(Cout_p, device=w.device, dtype=torch.float32)
+    def get(self, w, b, Cout_p, Cin_p, ps, refresh):
+        if self.wf is None or self.wf.numel() != Cout_p * 9 * Cin_p:
+            self.wf = torch.empty(Cout_p * 9 * Cin_p, device=w.device, dtype=BF16)
+            self.wt = torch.empty(Cin_p * 9 * Cout_p, device=w.device, dtype=BF16)
+            self.bias = torch.empty(Cout_p, device=w.device, dtype=torch.float32)
+            refresh = True
+        if refresh:
             capi.conv3x3_prep_weights(w.detach(), None if b is None else b.detach(), Cout_p, Cin_p, ps, self.wf, self.wt,
                                       self.bias)
-            self.key = key
         return self.wf, self.wt, self.bias
 
 
 _conv_caches: dict = {}
 
 
-def conv_weights(w, b, Cout_p, Cin_p, ps=False):
+def conv_weights(w, b, Cout_p, Cin_p, ps=False, refresh=True):
+    """refresh=True in every forward; the backward of the same step passes refresh=False to reuse them."""
     k = (w.data_ptr(), Cout_p, Cin_p, ps)
     c = _conv_caches.get(k)
     if c is None:
         c = _conv_caches[k] = _ConvWeightCache()
-    return c.get(w, b, Cout_p, Cin_p, ps)
+    return c.get(w, b, Cout_p, Cin_p, ps, refresh)
 
 
 class ConvFirstFunction(torch.autograd.Function):
@@ -127,14 +127,14 @@ class SwinIRTailFunction(torch.autograd.Function):
         dw_last, db_last = torch.empty_like(w_last), torch.empty_like(b_last)
         capi.conv_out1_bwd(dout, u1, w_last.detach(), d_u1, dw_last, db_last, B, 4 * H, 4 * W, 64)
         # upsample.2 (input u0 at 2H x 2W, gradient arrives pixel-shuffled at 4H x 4W)
-        _, wt_u2, _ = conv_weights(w_u2, b_u2, 256, 64, ps=True)
+        _, wt_u2, _ = conv_weights(w_u2, b_u2, 256, 64, ps=True, refresh=False)
         d_u0 = torch.empty_like(u0)
         capi.conv3x3_igemm(capi.CEPI_BIAS, B, 2 * H, 2 * W, 256, 64, 64, d_u1, wt_u2, None, d_u0, x_ps=True)
         dw_u2, db_u2 = torch.empty_like(w_u2), torch.empty_like(b_u2)
         capi.conv3x3_wgrad(B, 2 * H, 2 * W, 64, 256, 64, 256, True, d_u1, u0, dw_u2)
         capi.bias_grad_nhwc(d_u1, B, 2 * H, 2 * W, 256, True, db_u2)
         # upsample.0 (+ LeakyReLU backward fused into the input-gradient epilogue)
-        _, wt_u0, _ = conv_weights(w_u0, b_u0, 256, 64, ps=True)
+        _, wt_u0, _ = conv_weights(w_u0, b_u0, 256, 64, ps=True, refresh=False)
         d_t64 = torch.empty_like(t64)
         capi.conv3x3_igemm(capi.CEPI_MASK_LRELU, B, H, W, 256, 64, 64, d_u0, wt_u0, None, d_t64, x_ps=True, r=t64,
                            slope=0.01)
@@ -142,14 +142,14 @@ class SwinIRTailFunction(torch.autograd.Function):
         capi.conv3x3_wgrad(B, H, W, 64, 256, 64, 256, True, d_u0, t64, dw_u0)
         capi.bias_grad_nhwc(d_u0, B, H, W, 256, True, db_u0)
         # conv_before_upsample
-        _, wt_bu, _ = conv_weights(w_bu, b_bu, 64, Cp)
+        _, wt_bu, _ = conv_weights(w_bu, b_bu, 64, Cp, refresh=False)
         d_res = torch.empty_like(res)
         capi.conv3x3_igemm(capi.CEPI_BIAS, B, H, W, 64, Cp, Cp, d_t64, wt_bu, None, d_res)
         dw_bu, db_bu = torch.empty_like(w_bu), torch.empty_like(b_bu)
         capi.conv3x3_wgrad(B, H, W, w_bu.shape[1], 64, Cp, 64, False, d_t64, res, dw_bu)
         capi.bias_grad_nhwc(d_t64, B, H, W, 64, False, db_bu)
         # conv_after_body (+ residual: d_first = d_res)
-        _, wt_ab, _ = conv_weights(w_ab, b_ab, Cp, Cp)
+        _, wt_ab, _ = conv_weights(w_ab, b_ab, Cp, Cp, refresh=False)
         d_body = torch.empty_like(body)
         capi.conv3x3_igemm(capi.CEPI_BIAS, B, H, W, Cp, Cp, Cp, d_res, wt_ab, None, d_body)
         dw_ab, db_ab = torch.empty_like(w_ab), torch.empty_like(b_ab)

@@ -68,31 +68,42 @@ def block_params_of(block: torch.nn.Module) -> list[torch.Tensor]:
 
 
 class _WeightCache:
-    """bf16 GEMM operands of one block, refreshed when any master parameter changed (in-place version bump)."""
+    """bf16 GEMM operands of one block.  They are re-derived from the fp32 master parameters on every forward
+    (one small kernel per block): fused / foreach optimizers update parameters without bumping the autograd version
+    counter, so no host-side staleness test is reliable.  `freeze_weights(True)` opts into reuse for pure inference."""
 
     def __init__(self, cfg: BlockCfg, device):
         self.cfg = cfg
         elems = capi.block_weight_elems(cfg.dims())
         self.t = {n: torch.empty(e, device=device, dtype=BF16) for n, e in zip(capi.WEIGHT_NAMES, elems)}
-        self.key = None
+        self.ready = False
 
-    def get(self, params: list[torch.Tensor]) -> dict:
-        key = tuple((p.data_ptr(), p._version) for p in params)
-        if key != self.key:
+    def get(self, params: list[torch.Tensor], refresh: bool) -> dict:
+        if refresh or not self.ready or not _frozen:
             capi.block_prep_weights(self.cfg.dims(), dict(zip(capi.PARAM_NAMES, params)), self.t)
-            self.key = key
+            self.ready = True
         return self.t
 
 
 _weight_caches: dict = {}
+_frozen = False
 
 
-def _weights_for(cfg: BlockCfg, params: list[torch.Tensor]) -> dict:
+def freeze_weights(flag: bool = True):
+    """Inference-only opt-in: keep the prepared bf16 operands between forwards (call again with False, or after
+    loading new weights, to drop them)."""
+    global _frozen
+    _frozen = bool(flag)
+    for wc in _weight_caches.values():
+        wc.ready = False
+
+
+def _weights_for(cfg: BlockCfg, params: list[torch.Tensor], refresh: bool = True) -> dict:
     k = (cfg, params[3].data_ptr())  # keyed by the qkv weight storage
     wc = _weight_caches.get(k)
     if wc is None:
         wc = _weight_caches[k] = _WeightCache(cfg, params[3].device)
-    return wc.get(params)
+    return wc.get(params, refresh)
 
 
 def _check_param(p: torch.Tensor):
@@ -146,7 +157,7 @@ class SwinStackFunction(torch.autograd.Function):
                 nw, nbias = tensors[(i + 1) * N_BLOCK_PARAMS].detach(), tensors[(i + 1) * N_BLOCK_PARAMS + 1].detach()
             else:
                 nw, nbias = tensors[-2].detach(), tensors[-1].detach()
-            weights = _weights_for(cfg, params)
+            weights = _weights_for(cfg, params, refresh=need_grad)
             acts = dict(_alloc_acts(cfg, T, x.device) if need_grad else pingpong[i & 1])
             acts.update(x_in=cur_x, xn1=cur_xn, stats1=cur_stats)
             g = capi.SrkGeom(B, H, W, cfg.ws, shifts[i])
@@ -175,7 +186,7 @@ class SwinStackFunction(torch.autograd.Function):
         bufs = [torch.empty(T, cfg.Cp, device=dev, dtype=BF16), torch.empty(T, cfg.Cp, device=dev, dtype=BF16)]
         for i in reversed(range(nb)):
             params = [t.detach() for t in tensors[i * N_BLOCK_PARAMS:(i + 1) * N_BLOCK_PARAMS]]
-            weights = _weights_for(cfg, params)
+            weights = _weight_caches[(cfg, params[3].data_ptr())].t  # prepared by this step's forward
             acts = ctx.saved_acts[i]
             gdict = {n: torch.empty_like(p) for n, p in zip(capi.PARAM_NAMES, params)}
             g_in = bufs[i & 1]

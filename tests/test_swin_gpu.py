@@ -96,20 +96,34 @@ def test_swin_block_matches_oracle(shift):
 
 
 def test_swinir_small_matches_oracle():
+    """Whole generator, forward + every parameter gradient.  Two pins: the fp32 oracle (absolute tolerance) and the
+    same oracle under bf16 autocast — the reference's own training dtype — whose distance to fp32 calibrates what
+    bf16 arithmetic can deliver through this depth: ours must stay within 1.6x of it (+1e-2)."""
     from superresolution_def_b200.architecture_swin import SwinIR
     o = _oracle()
     torch.manual_seed(4)
     kw = dict(img_size=16, window_size=8, depths=[2, 2], num_heads=[6, 6])
     net = randomize_(SwinIR(upscale=4, in_chans=1, embed_dim=180, mlp_ratio=2, **kw), seed=5, table_std=0.5).cuda()
     x = torch.rand(2, 1, 16, 16, device="cuda")
-    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in net.state_dict().items()}
-    ref = o.swinir_forward(x, sd, upscale=4, **kw)
+    w = torch.randn(2, 1, 64, 64, device="cuda")
+
+    def run_oracle(autocast):
+        sd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in net.state_dict().items()}
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            out = o.swinir_forward(x, sd, upscale=4, **kw)
+        (out.float() * w).mean().backward()
+        return out, sd
+
+    ref, sd32 = run_oracle(False)
+    r16, sd16 = run_oracle(True)
     got = net(x)
     assert got.shape == ref.shape == (2, 1, 64, 64)
     assert rel_l2(got, ref) < OUT_TOL, rel_l2(got, ref)
-    w = torch.randn_like(ref)
-    (ref * w).mean().backward()
+    assert rel_l2(got, ref) < 1.6 * rel_l2(r16, ref) + 1e-2
     (got.float() * w).mean().backward()
-    worst = {n: rel_l2(p.grad, sd[n].grad) for n, p in net.named_parameters()}
-    bad = {k: v for k, v in worst.items() if v > 6e-2}
-    assert not bad, {k: round(v, 4) for k, v in sorted(worst.items(), key=lambda kv: -kv[1])[:12]}
+    bad = {}
+    for n, p in net.named_parameters():
+        mine, auto = rel_l2(p.grad, sd32[n].grad), rel_l2(sd16[n].grad, sd32[n].grad)
+        if mine > 1.6 * auto + 1e-2:
+            bad[n] = (round(mine, 4), round(auto, 4))
+    assert not bad, bad

@@ -260,3 +260,148 @@ def identity_norm(C: int, device):
     if k not in _ident_cache:
         _ident_cache[k] = (torch.ones(C, device=device), torch.zeros(C, device=device))
     return _ident_cache[k]
+
+
+# ---------------------------------------------------------------------------------------------------
+# Stand-alone module forwards (WindowAttention.forward / Mlp.forward called outside a block).
+# Same kernels as the fused block path; only the packing / gradient unpacking is done with torch indexing.
+# ---------------------------------------------------------------------------------------------------
+_zero_cache: dict = {}
+
+
+def _zeros(shape, device):
+    k = (tuple(shape), str(device))
+    if k not in _zero_cache:
+        _zero_cache[k] = torch.zeros(shape, device=device)
+    return _zero_cache[k]
+
+
+def _partial_weights(cfg: BlockCfg, device, **given) -> dict:
+    """Prepared operands when only some of a block's parameters exist (missing ones are zeros)."""
+    C, hid, T2 = cfg.C, cfg.hidden, (2 * cfg.ws - 1) ** 2
+    shapes = {"norm1_w": (C,), "norm1_b": (C,), "rpb_table": (T2, cfg.heads), "qkv_w": (3 * C, C), "qkv_b": (3 * C,),
+              "proj_w": (C, C), "proj_b": (C,), "norm2_w": (C,), "norm2_b": (C,), "fc1_w": (hid, C), "fc1_b": (hid,),
+              "fc2_w": (C, hid), "fc2_b": (C,)}
+    params = {n: (given[n].detach() if n in given else _zeros(s, device)) for n, s in shapes.items()}
+    for p in params.values():
+        _check_param(p)
+    elems = capi.block_weight_elems(cfg.dims())
+    w = {n: torch.empty(e, device=device, dtype=BF16) for n, e in zip(capi.WEIGHT_NAMES, elems)}
+    capi.block_prep_weights(cfg.dims(), params, w)
+    return w
+
+
+def _pack_rows(x2d: torch.Tensor, Cp: int, ones_col: int, rows_pad: int) -> torch.Tensor:
+    T, C = x2d.shape
+    out = x2d.new_zeros((rows_pad, Cp), dtype=BF16)
+    out[:T, :C] = x2d.to(BF16)
+    if ones_col >= 0:
+        out[:T, ones_col] = 1.0
+    return out
+
+
+def _wgrad(A, B, rows_a):
+    """fp32 [ceil128(Ca), Cb] = A^T @ B (tcgen05, MN-major operands)."""
+    T, Ca = A.shape
+    Cb = B.shape[1]
+    tiles = (Ca + 127) // 128
+    splits = max(1, min(148 // tiles, T // 64))
+    ws = torch.empty(capi.wgrad_workspace_elems(Ca, Cb, splits), device=A.device, dtype=torch.float32)
+    out = torch.empty(tiles * 128, Cb, device=A.device, dtype=torch.float32)
+    capi.gemm_wgrad(A, B, ws, splits, out)
+    return out[:rows_a]
+
+
+class MlpFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, fc1_w, fc1_b, fc2_w, fc2_b):
+        C, hid = fc1_w.shape[1], fc1_w.shape[0]
+        cfg = BlockCfg.for_model(C, 6, hid, 8)
+        lead = x.shape[:-1]
+        x2 = x.reshape(-1, C)
+        T = x2.shape[0]
+        Tp = (T + 127) // 128 * 128
+        w = _partial_weights(cfg, x.device, fc1_w=fc1_w, fc1_b=fc1_b, fc2_w=fc2_w, fc2_b=fc2_b)
+        xp = _pack_rows(x2, cfg.Cp, C, Tp)
+        act = torch.empty(Tp, cfg.Hp, device=x.device, dtype=BF16)
+        dact = torch.empty_like(act)
+        capi.gemm_tn(capi.EPI_GELU2, xp, w["fc1_f"].view(cfg.Hp, cfg.Cp), act, C2=dact,
+                     ln=capi.make_ln_args(cfg.Hp, hid, None))
+        y = torch.empty(Tp, cfg.Cp, device=x.device, dtype=BF16)
+        capi.gemm_tn(capi.EPI_STORE, act, w["fc2_f"].view(cfg.Cp, cfg.Hp), y)
+        ctx.saved = (xp, act, dact, w, cfg, T, lead, x.dtype)
+        return y[:T, :C].reshape(*lead, C).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xp, act, dact, w, cfg, T, lead, dtype = ctx.saved
+        C, hid = cfg.C, cfg.hidden
+        Tp = xp.shape[0]
+        dyp = _pack_rows(dy.reshape(-1, C), cfg.Cp, -1, Tp)
+        dU = torch.empty(Tp, cfg.Hp, device=dy.device, dtype=BF16)
+        capi.gemm_tn(capi.EPI_MUL, dyp, w["fc2_t"].view(cfg.Hp, cfg.Cp), dU, X1=dact)
+        dx = torch.empty(Tp, cfg.Cp, device=dy.device, dtype=BF16)
+        capi.gemm_tn(capi.EPI_STORE, dU, w["fc1_t"].view(cfg.Cp, cfg.Hp), dx)
+        e2 = _wgrad(act, dyp, cfg.Hp)     # [Hp, Cp]: rows hidden (+ones row), cols out channels
+        e1 = _wgrad(dU, xp, cfg.Hp)       # [Hp, Cp]: rows hidden, cols in channels (+ones col)
+        return (dx[:T, :C].reshape(*lead, C).to(dtype), e1[:hid, :C].contiguous(), e1[:hid, C].contiguous(),
+                e2[:hid, :C].t().contiguous(), e2[hid, :C].contiguous())
+
+
+def mlp_forward(x, fc1_w, fc1_b, fc2_w, fc2_b):
+    if not x.is_cuda:
+        raise capi.SrkError("libsrk Mlp runs on CUDA only")
+    return MlpFunction.apply(x, fc1_w, fc1_b, fc2_w, fc2_b)
+
+
+class WindowAttentionFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, ws, heads, table, qkv_w, qkv_b, proj_w, proj_b):
+        B_, N, C = x.shape
+        if ws != 8 or N != 64:
+            raise capi.SrkError("stand-alone WindowAttention kernel: window 8x8 (64 tokens)")
+        cfg = BlockCfg.for_model(C, heads, 4 * C, ws)
+        Bp = B_ + (B_ & 1)  # 64-token windows, 128-row GEMM tiles
+        w = _partial_weights(cfg, x.device, rpb_table=table, qkv_w=qkv_w, qkv_b=qkv_b, proj_w=proj_w, proj_b=proj_b)
+        xp = _pack_rows(x.reshape(-1, C), cfg.Cp, C, Bp * 64)
+        qkv = torch.empty(Bp * 64, cfg.QW, device=x.device, dtype=BF16)
+        capi.gemm_tn(capi.EPI_STORE, xp, w["qkv_f"].view(cfg.QW, cfg.Cp), qkv)
+        geom = capi.SrkGeom(Bp, 8, 8, 8, 0)  # already-partitioned windows: one 8x8 "image" per window
+        ao = torch.empty(Bp * 64, cfg.AW, device=x.device, dtype=BF16)
+        capi.win_attn_fwd(geom, heads, qkv, table.detach(), ao, ones_col=cfg.dh)
+        y = torch.empty(Bp * 64, cfg.Cp, device=x.device, dtype=BF16)
+        capi.gemm_tn(capi.EPI_STORE, ao, w["proj_f"].view(cfg.Cp, cfg.AW), y)
+        ctx.saved = (xp, qkv, ao, w, cfg, table.detach(), B_, Bp, x.dtype)
+        return y[:B_ * 64, :C].reshape(B_, N, C).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xp, qkv, ao, w, cfg, table, B_, Bp, dtype = ctx.saved
+        C, heads, dh, ds = cfg.C, cfg.heads, cfg.dh, cfg.ds
+        dev = dy.device
+        dyp = _pack_rows(dy.reshape(-1, C), cfg.Cp, -1, Bp * 64)
+        d_ao = torch.empty(Bp * 64, cfg.AW, device=dev, dtype=BF16)
+        capi.gemm_tn(capi.EPI_STORE, dyp, w["proj_t"].view(cfg.AW, cfg.Cp), d_ao)
+        d_qkv = torch.empty_like(qkv)
+        d_table = torch.empty_like(table)
+        capi.win_attn_bwd(capi.SrkGeom(Bp, 8, 8, 8, 0), heads, qkv, table, d_ao, d_qkv, d_table)
+        dx = torch.empty(Bp * 64, cfg.Cp, device=dev, dtype=BF16)
+        capi.gemm_tn(capi.EPI_STORE, d_qkv, w["qkv_t"].view(cfg.Cp, cfg.QW), dx)
+        ep = _wgrad(dyp, ao, cfg.Cp)       # [Cp, AW]
+        eq = _wgrad(d_qkv, xp, cfg.QW)     # [QW, Cp]
+        scale = torch.ones(3, 1, 1, 1, device=dev)
+        scale[0] = dh ** -0.5               # q rows were pre-scaled in the forward operand
+        eq = eq.view(3, heads, ds, cfg.Cp)[:, :, :dh] * scale
+        d_qkv_w = eq[..., :C].reshape(3 * C, C).contiguous()
+        d_qkv_b = eq[..., C].reshape(3 * C).contiguous()
+        epv = ep[:C].view(C, heads, ds)
+        d_proj_w = epv[:, :, :dh].reshape(C, C).contiguous()
+        d_proj_b = epv[:, 0, dh].contiguous()
+        return (dx[:B_ * 64, :C].reshape(B_, 64, C).to(dtype), None, None, d_table, d_qkv_w, d_qkv_b, d_proj_w,
+                d_proj_b)
+
+
+def window_attention_forward(x, ws, heads, table, qkv_w, qkv_b, proj_w, proj_b):
+    if not x.is_cuda:
+        raise capi.SrkError("libsrk WindowAttention runs on CUDA only")
+    return WindowAttentionFunction.apply(x, ws, heads, table, qkv_w, qkv_b, proj_w, proj_b)

@@ -127,3 +127,33 @@ def test_swinir_small_matches_oracle():
         if mine > 1.6 * auto + 1e-2:
             bad[n] = (round(mine, 4), round(auto, 4))
     assert not bad, bad
+
+
+def test_standalone_window_attention_and_mlp_modules():
+    """The module-level interfaces WindowAttention.forward(x, mask=None) and Mlp.forward(x) (reference
+    architecture_swin.py:71-96, :19-25) called on their own, outputs + all gradients vs the oracle."""
+    from superresolution_def_b200.architecture_swin import WindowAttention, Mlp
+    o = _oracle()
+    torch.manual_seed(7)
+    att = randomize_(WindowAttention(180, (8, 8), 6), seed=11).cuda()
+    x = torch.randn(5, 64, 180, device="cuda")
+    xm, xr = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in att.state_dict().items()}
+    got, ref = att(xm), o.window_attention(xr, sd, "", 6, 8)
+    assert rel_l2(got, ref) < OUT_TOL
+    w = torch.randn_like(ref)
+    (got * w).sum().backward(); (ref * w).sum().backward()
+    assert rel_l2(xm.grad, xr.grad) < GRAD_TOL
+    for n, p in att.named_parameters():
+        assert rel_l2(p.grad, sd[n].grad) < GRAD_TOL, n
+    mlp = randomize_(Mlp(180, 720), seed=12).cuda()
+    x = torch.randn(3, 50, 180, device="cuda")
+    xm, xr = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in mlp.state_dict().items()}
+    got, ref = mlp(xm), o.mlp(xr, sd, "")
+    assert rel_l2(got, ref) < OUT_TOL
+    w = torch.randn_like(ref)
+    (got * w).sum().backward(); (ref * w).sum().backward()
+    assert rel_l2(xm.grad, xr.grad) < GRAD_TOL
+    for n, p in mlp.named_parameters():
+        assert rel_l2(p.grad, sd[n].grad) < GRAD_TOL, n

@@ -1,0 +1,34 @@
+"""Launch one libsrk kernel a few times at the bench shapes (for `ncu --set full`).  Usage: gpu_kernel_loop.py <which>"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from superresolution_def_b200 import _capi as capi
+
+which = sys.argv[1] if len(sys.argv) > 1 else "gelu2"
+B = 16
+T = B * 16384
+bf = torch.bfloat16
+dev = "cuda"
+torch.manual_seed(0)
+reps = 3
+if which == "gelu2":
+    A = torch.randn(T, 192, device=dev).to(bf); W = (torch.randn(768, 192, device=dev) / 14).to(bf)
+    C = torch.empty(T, 768, device=dev, dtype=bf); C2 = torch.empty_like(C)
+    ln = capi.make_ln_args(768, 720, None)
+    for _ in range(reps): capi.gemm_tn(capi.EPI_GELU2, A, W, C, C2=C2, ln=ln)
+elif which == "res_ln":
+    A = torch.randn(T, 768, device=dev).to(bf); W = (torch.randn(192, 768, device=dev) / 28).to(bf)
+    R = torch.randn(T, 192, device=dev).to(bf); C = torch.empty(T, 192, device=dev, dtype=bf); C2 = torch.empty_like(C)
+    st = torch.empty(T, 2, device=dev); g = torch.ones(180, device=dev); b = torch.zeros(180, device=dev)
+    ln = capi.make_ln_args(180, 180, g, b, stats=st)
+    for _ in range(reps): capi.gemm_tn(capi.EPI_RES_LN, A, W, C, C2=C2, X1=R, ln=ln)
+elif which == "attn_fwd":
+    qkv = torch.randn(T, 576, device=dev).to(bf); tab = torch.randn(225, 6, device=dev)
+    out = torch.empty(T, 192, device=dev, dtype=bf)
+    for _ in range(reps): capi.win_attn_fwd(capi.SrkGeom(B, 128, 128, 8, 4), 6, qkv, tab, out, ones_col=30)
+elif which == "attn_bwd":
+    qkv = torch.randn(T, 576, device=dev).to(bf); tab = torch.randn(225, 6, device=dev)
+    do = torch.randn(T, 192, device=dev).to(bf); dq = torch.empty_like(qkv); dt = torch.empty_like(tab)
+    for _ in range(reps): capi.win_attn_bwd(capi.SrkGeom(B, 128, 128, 8, 4), 6, qkv, tab, do, dq, dt)
+torch.cuda.synchronize()
+print("done", which)

@@ -48,3 +48,36 @@ def test_product_module_schema_matches_reference():
     assert [n for n, _ in ref.named_parameters()] == [n for n, _ in mine.named_parameters()]
     mine.load_state_dict(a, strict=True)
     assert all(torch.equal(a[k], b[k]) for k in a if "index" in k)
+
+
+def test_hab_and_ocab_c180_ws16_match_reference():
+    """HAT blocks at the BASELINE configs[2] dimensions (C=180, 6 heads, window 16, OCAB 24x24 keys), 32x32 tokens."""
+    from tools import ref_shim
+    from oracle import hat_oracle as ho
+    m = ref_shim.hat_module()
+    torch.manual_seed(1)
+    hat = m.HAT(img_size=32, in_chans=1, embed_dim=180, depths=(1,), num_heads=(6,), window_size=16, upscale=4,
+                upsampler="pixelshuffle", drop_path_rate=0.0)
+    assert torch.equal(ho.rpi_sa(16), hat.relative_position_index_SA)
+    assert torch.equal(ho.rpi_oca(16), hat.relative_position_index_OCA)
+    mask = hat.calculate_mask((32, 32))
+    assert torch.equal(ho.shift_mask(32, 32, 16, 8), mask)
+    for kind in ("hab", "ocab"):
+        if kind == "hab":
+            blk = randomize_(m.HAB(180, (32, 32), 6, window_size=16, shift_size=8), seed=2)
+        else:
+            blk = randomize_(m.OCAB(180, (32, 32), 16, 0.5, 6, mlp_ratio=4), seed=3)
+        x = torch.randn(1, 1024, 180, requires_grad=True)
+        y = blk(x, (32, 32), hat.relative_position_index_SA, mask) if kind == "hab" else \
+            blk(x, (32, 32), hat.relative_position_index_OCA)
+        w = torch.randn_like(y)
+        (y * w).sum().backward()
+        sd = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() else v)
+              for k, v in blk.state_dict().items()}
+        x2 = x.detach().clone().requires_grad_(True)
+        y2 = ho.hab(x2, sd, "", (32, 32), 6, 16, 8, ho.rpi_sa(16), mask) if kind == "hab" else \
+            ho.ocab(x2, sd, "", (32, 32), 6, 16, ho.rpi_oca(16))
+        (y2 * w).sum().backward()
+        assert rel_l2(y2, y) < 1e-5 and rel_l2(x2.grad, x.grad) < 1e-4, kind
+        for n, p in blk.named_parameters():
+            assert rel_l2(sd[n].grad, p.grad) < 2e-4, (kind, n)

@@ -72,7 +72,81 @@ def swin_fixtures():
                 "x_pad": xpad, "y_pad": net(xpad).detach()}, f"{OUT}/swinir_tiny.pt")
 
 
+def hat_fixtures():
+    """HAT (models/hat_arch/hat_arch.py, imported unmodified through tools/ref_shim.py) and the hybrid wrapper."""
+    from tools import ref_shim
+    m = ref_shim.hat_module()
+    ws, heads, dim = 4, 3, 36
+    # index / mask builders are methods of HAT: instantiate a tiny one
+    torch.manual_seed(40)
+    kw = dict(img_size=8, in_chans=1, embed_dim=dim, depths=(2, 2), num_heads=(heads, heads), window_size=ws,
+              compress_ratio=3, squeeze_factor=6, upscale=4, upsampler="pixelshuffle", drop_path_rate=0.0)
+    net = randomize_(m.HAT(**kw), seed=41, table_std=0.5)
+    torch.save({"ws": ws, "rpi_sa": net.relative_position_index_SA, "rpi_oca": net.relative_position_index_OCA,
+                "mask_8x12": net.calculate_mask((8, 12)), "mask_8x8": net.calculate_mask((8, 8))},
+               f"{OUT}/hat_rpi_mask.pt")
+    rpi_sa, rpi_oca = net.relative_position_index_SA, net.relative_position_index_OCA
+    mask = net.calculate_mask((8, 12))
+    # window attention with rpi + mask
+    att = randomize_(m.WindowAttention(dim, (ws, ws), heads), seed=42)
+    xa = torch.randn(12, ws * ws, dim, requires_grad=True)
+    ya = att(xa, rpi_sa, mask)
+    ga, gxa = grads_of(att, ya, torch.ones_like(ya) * torch.linspace(-1, 1, dim), xa)
+    torch.save({"sd": att.state_dict(), "x": xa.detach(), "y": ya.detach(), "y_nomask": att(xa, rpi_sa, None).detach(),
+                "grads": ga, "gx": gxa, "heads": heads}, f"{OUT}/hat_window_attention.pt")
+    # CAB
+    cab = randomize_(m.CAB(dim, 3, 6), seed=43)
+    xc = torch.randn(2, dim, 8, 12, requires_grad=True)
+    yc = cab(xc)
+    wc = torch.randn_like(yc)
+    gc, gxc = grads_of(cab, yc, wc, xc)
+    torch.save({"sd": cab.state_dict(), "x": xc.detach(), "y": yc.detach(), "w": wc, "grads": gc, "gx": gxc},
+               f"{OUT}/hat_cab.pt")
+    # HAB shifted / unshifted, OCAB
+    for shift in (0, 2):
+        torch.manual_seed(44 + shift)
+        blk = randomize_(m.HAB(dim, (8, 12), heads, window_size=ws, shift_size=shift, compress_ratio=3, squeeze_factor=6),
+                         seed=45 + shift)
+        xb = torch.randn(2, 96, dim, requires_grad=True)
+        yb = blk(xb, (8, 12), rpi_sa, mask)
+        w = torch.randn_like(yb)
+        gb, gxb = grads_of(blk, yb, w, xb)
+        torch.save({"kw": dict(dim=dim, res=(8, 12), heads=heads, ws=ws, shift=shift), "sd": blk.state_dict(),
+                    "x": xb.detach(), "y": yb.detach(), "w": w, "grads": gb, "gx": gxb}, f"{OUT}/hat_hab_shift{shift}.pt")
+    torch.manual_seed(48)
+    oc = randomize_(m.OCAB(dim, (8, 12), ws, 0.5, heads, mlp_ratio=2), seed=49)
+    xo = torch.randn(2, 96, dim, requires_grad=True)
+    yo = oc(xo, (8, 12), rpi_oca)
+    w = torch.randn_like(yo)
+    go, gxo = grads_of(oc, yo, w, xo)
+    torch.save({"kw": dict(dim=dim, res=(8, 12), heads=heads, ws=ws), "sd": oc.state_dict(), "x": xo.detach(),
+                "y": yo.detach(), "w": w, "grads": go, "gx": gxo}, f"{OUT}/hat_ocab.pt")
+    # whole HAT (tiny), eval-equivalent (drop_path_rate 0)
+    xi = torch.rand(2, 1, 8, 8, requires_grad=True)
+    yo = net(xi)
+    w = torch.randn_like(yo)
+    gn, gxi = grads_of(net, yo, w, xi)
+    torch.save({"kw": {k: v for k, v in kw.items()}, "sd": net.state_dict(), "x": xi.detach(), "y": yo.detach(), "w": w,
+                "grads": gn, "gx": gxi}, f"{OUT}/hat_tiny.pt")
+    # hybrid wrapper (HAT x2 -> RRDB trunk -> nearest x2 -> convs)
+    h = ref_shim.hybrid_module()
+    torch.manual_seed(50)
+    hkw = dict(img_size=8, in_chans=1, embed_dim=36, depths=(2,), num_heads=(3,), window_size=4, upscale=4, num_rrdb=2,
+               num_feat=8, num_grow_ch=4)
+    hyb = randomize_(h.HybridHATRealESRGAN(**hkw), seed=51, table_std=0.5).eval()  # eval: HAT default drop_path 0.1
+    xh = torch.rand(1, 1, 8, 8, requires_grad=True)
+    yh = hyb(xh)
+    w = torch.randn_like(yh)
+    gh, gxh = grads_of(hyb, yh, w, xh)
+    torch.save({"kw": hkw, "sd": hyb.state_dict(), "x": xh.detach(), "y": yh.detach(), "w": w, "grads": gh, "gx": gxh},
+               f"{OUT}/hybrid_tiny.pt")
+
+
 if __name__ == "__main__":
-    swin_fixtures()
+    which = sys.argv[1:] or ["swin", "hat"]
+    if "swin" in which:
+        swin_fixtures()
+    if "hat" in which:
+        hat_fixtures()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -195,6 +195,57 @@ int srk_conv_out1_fwd(const void* x, const float* w, const float* bias, float* y
 int srk_conv_out1_bwd(const float* dy, const void* x, const float* w, void* dx, float* ws, float* dw, float* db, int B,
                       int H, int W, int C, void* stream);
 
+
+/* ======================================================================================================
+ * HAT (models/hat_arch/hat_arch.py): 16x16-window attention cores, block orchestration, channel attention.
+ * ====================================================================================================== */
+#define SRK_ATTN_SELF 0 /* (S)W-MSA of HAB: keys = same window, shift mask 0/-100 from coordinates (:183-187,921-940) */
+#define SRK_ATTN_OCA 1  /* OCAB: keys/values = 24x24 halo window, zero outside the image, no mask (:400-428)          */
+
+/* Window attention core on packed qkv for ws == 16 (g->ws must be 16; g->shift in {0, 8} for SELF, 0 for OCA).
+ * Replaces window_partition/reverse (hat_arch.py:97-126), torch.roll (:280-302), nn.Unfold + rearrange (:408-409),
+ * and the attention math of WindowAttention.forward (:175-193) / OCAB.forward (:419-428).
+ * rpb_table: [(16+wse-1)^2, heads] fp32 (961 / 1521 rows); lse: [heads][T] fp32 written by fwd, read by bwd. */
+int srk_win_attn16_fwd(const SrkGeom* g, int mode, int heads, const void* qkv, int ld_qkv, const float* rpb_table,
+                       void* out, int ld_out, float* lse, int ones_col, void* stream);
+/* out: the forward output (for the softmax-gradient row term); ws: srk_win_attn16_bwd_ws_bytes(...) bytes;
+ * d_rpb_table [(16+wse-1)^2, heads] written if non-NULL. */
+int srk_win_attn16_bwd(const SrkGeom* g, int mode, int heads, const void* qkv, int ld_qkv, const float* rpb_table,
+                       const void* out, const void* d_out, int ld_out, const float* lse, void* d_qkv, void* ws,
+                       float* d_rpb_table, void* stream);
+long long srk_win_attn16_bwd_ws_bytes(const SrkGeom* g, int mode, int heads);
+
+/* What distinguishes a HAT block from a Swin block at the orchestration level. */
+typedef struct SrkHatExtra {
+  int mode;           /* SRK_ATTN_SELF (HAB) or SRK_ATTN_OCA (OCAB)                                                  */
+  const void* res_in; /* [T,Cp] residual added by the proj epilogue: HAB x_in + conv_scale*CAB(xn1) (:306), OCAB x_in */
+  float* lse;         /* [heads][T]                                                                                   */
+  void* attn_ws;      /* backward only: srk_win_attn16_bwd_ws_bytes bytes                                             */
+  void* d_xn1;        /* backward, optional: if non-NULL receives d_qkv @ Wqkv ([T,Cp] bf16) and the LayerNorm-1
+                         backward (g_in, norm1 grads) is left to the caller, who first adds the CAB branch gradient    */
+} SrkHatExtra;
+
+/* Forward / backward of one HAB or OCAB given xn1 = LN1(x_in): same GEMM chain as srk_swin_block_fwd/bwd
+ * (HAB.forward hat_arch.py:266-309 minus the CAB branch, OCAB.forward :392-438). */
+int srk_hat_block_fwd(const SrkBlockDims* d, const SrkGeom* g, const SrkBlockWeights* w, const SrkBlockParams* p,
+                      const float* next_norm_w, const float* next_norm_b, const SrkBlockActs* a, const SrkHatExtra* x,
+                      void* stream);
+int srk_hat_block_bwd(const SrkBlockDims* d, const SrkGeom* g, const SrkBlockWeights* w, const SrkBlockParams* p,
+                      const SrkBlockActs* a, const void* g_out, const SrkBlockScratch* s, void* g_in,
+                      const SrkBlockGrads* grads, const SrkHatExtra* x, void* stream);
+
+/* Channel attention of CAB (ChannelAttention hat_arch.py:40-58) on token-major bf16 y = conv2 output [B*HW, Cp]:
+ *   pool[b,c] = mean_p y; hidden = relu(W1 pool + b1); scale = sigmoid(W2 hidden + b2);
+ *   out = x + alpha * y * scale   (alpha = HAB.conv_scale, x = the block's shortcut; :306)
+ * w1 [S,C], w2 [C,S] are the 1x1 conv weights viewed as matrices.  ws: srk_small_ws_floats() floats. */
+int srk_cab_se_fwd(const void* y, const void* x, int B, int HW, int C, int Cp, int S, const float* w1, const float* b1,
+                   const float* w2, const float* b2, float alpha, float* ws, float* pool, float* hidden, float* scale,
+                   void* out, void* stream);
+/* Backward: g = dL/dout [B*HW,Cp] -> dy (bf16 [B*HW,Cp]) and the four parameter gradients (dL/dx = g, by identity). */
+int srk_cab_se_bwd(const void* g, const void* y, int B, int HW, int C, int Cp, int S, const float* w1, const float* w2,
+                   float alpha, const float* pool, const float* hidden, const float* scale, float* ws, void* dy,
+                   float* dw1, float* db1, float* dw2, float* db2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

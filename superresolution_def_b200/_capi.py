@@ -348,3 +348,85 @@ def conv_out1_bwd(dy, x, w, dx, dw, db, B, H, W, C):
     ws = _ws(int(lib.srk_small_ws_floats()), dy.device)
     _check(_conv_out1_bwd(_ptr(dy), _ptr(x), _ptr(w), _ptr(dx), _ptr(ws), _ptr(dw), _ptr(db), B, H, W, C, _stream()),
            "srk_conv_out1_bwd")
+
+
+# ---------------------------------------------------------------------------------------------------
+# HAT API (include/srk.h, fourth part): 16x16-window attention cores, HAB/OCAB orchestration, channel attention
+# ---------------------------------------------------------------------------------------------------
+ATTN_SELF, ATTN_OCA = 0, 1
+
+
+class SrkHatExtra(Structure):
+    _fields_ = [("mode", c_int), ("res_in", c_void_p), ("lse", c_void_p), ("attn_ws", c_void_p), ("d_xn1", c_void_p)]
+
+
+_attn16_fwd = _sig("srk_win_attn16_fwd", [POINTER(SrkGeom), c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
+                                          c_void_p, c_int, c_void_p])
+_attn16_bwd = _sig("srk_win_attn16_bwd", [POINTER(SrkGeom), c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                          c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p])
+lib.srk_win_attn16_bwd_ws_bytes.restype = c_longlong
+lib.srk_win_attn16_bwd_ws_bytes.argtypes = [POINTER(SrkGeom), c_int, c_int]
+_hat_fwd = _sig("srk_hat_block_fwd", [POINTER(SrkBlockDims), POINTER(SrkGeom), POINTER(SrkBlockWeights),
+                                      POINTER(SrkBlockParams), c_void_p, c_void_p, POINTER(SrkBlockActs),
+                                      POINTER(SrkHatExtra), c_void_p])
+_hat_bwd = _sig("srk_hat_block_bwd", [POINTER(SrkBlockDims), POINTER(SrkGeom), POINTER(SrkBlockWeights),
+                                      POINTER(SrkBlockParams), POINTER(SrkBlockActs), c_void_p, POINTER(SrkBlockScratch),
+                                      c_void_p, POINTER(SrkBlockGrads), POINTER(SrkHatExtra), c_void_p])
+_cab_se_fwd = _sig("srk_cab_se_fwd", [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p])
+_cab_se_bwd = _sig("srk_cab_se_bwd", [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p])
+
+
+def attn16_bwd_ws_bytes(geom, mode, heads) -> int:
+    return int(lib.srk_win_attn16_bwd_ws_bytes(ctypes.byref(geom), mode, heads))
+
+
+def win_attn16_fwd(geom, mode, heads, qkv, rpb_table, out, lse, ones_col=-1):
+    rc = _attn16_fwd(ctypes.byref(geom), mode, heads, _ptr(qkv), _ld(qkv), _ptr(rpb_table), _ptr(out), _ld(out),
+                     _ptr(lse), ones_col, _stream())
+    _check(rc, "srk_win_attn16_fwd")
+
+
+def win_attn16_bwd(geom, mode, heads, qkv, rpb_table, out, d_out, lse, d_qkv, ws, d_rpb_table=None):
+    rc = _attn16_bwd(ctypes.byref(geom), mode, heads, _ptr(qkv), _ld(qkv), _ptr(rpb_table), _ptr(out), _ptr(d_out),
+                     _ld(d_out), _ptr(lse), _ptr(d_qkv), _ptr(ws), _ptr(d_rpb_table), _stream())
+    _check(rc, "srk_win_attn16_bwd")
+
+
+def _hat_extra(mode, res_in, lse, attn_ws=None, d_xn1=None):
+    return SrkHatExtra(mode, _ptr(res_in), _ptr(lse), _ptr(attn_ws), _ptr(d_xn1))
+
+
+def hat_block_fwd(dims, geom, weights: dict, params: dict, next_norm_w, next_norm_b, acts: dict, mode, res_in, lse):
+    x = _hat_extra(mode, res_in, lse)
+    rc = _hat_fwd(ctypes.byref(dims), ctypes.byref(geom), ctypes.byref(_fill(SrkBlockWeights, WEIGHT_NAMES, weights)),
+                  ctypes.byref(_fill(SrkBlockParams, PARAM_NAMES, params)), _ptr(next_norm_w), _ptr(next_norm_b),
+                  ctypes.byref(_fill(SrkBlockActs, ACT_NAMES, acts)), ctypes.byref(x), _stream())
+    _check(rc, "srk_hat_block_fwd")
+
+
+def hat_block_bwd(dims, geom, weights: dict, params: dict, acts: dict, g_out, scratch: dict, g_in, grads: dict, mode, lse,
+                  attn_ws, d_xn1=None):
+    x = _hat_extra(mode, None, lse, attn_ws, d_xn1)
+    rc = _hat_bwd(ctypes.byref(dims), ctypes.byref(geom), ctypes.byref(_fill(SrkBlockWeights, WEIGHT_NAMES, weights)),
+                  ctypes.byref(_fill(SrkBlockParams, PARAM_NAMES, params)),
+                  ctypes.byref(_fill(SrkBlockActs, ACT_NAMES, acts)), _ptr(g_out),
+                  ctypes.byref(_fill(SrkBlockScratch, SCRATCH_NAMES, scratch)), _ptr(g_in),
+                  ctypes.byref(_fill(SrkBlockGrads, PARAM_NAMES, grads)), ctypes.byref(x), _stream())
+    _check(rc, "srk_hat_block_bwd")
+
+
+def cab_se_fwd(y, x, B, HW, C, S, w1, b1, w2, b2, alpha, pool, hidden, scale, out):
+    ws = _ws(int(lib.srk_small_ws_floats()), y.device)
+    rc = _cab_se_fwd(_ptr(y), _ptr(x), B, HW, C, y.shape[1], S, _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), alpha, _ptr(ws),
+                     _ptr(pool), _ptr(hidden), _ptr(scale), _ptr(out), _stream())
+    _check(rc, "srk_cab_se_fwd")
+
+
+def cab_se_bwd(g, y, B, HW, C, S, w1, w2, alpha, pool, hidden, scale, dy, dw1, db1, dw2, db2):
+    ws = _ws(int(lib.srk_small_ws_floats()), y.device)
+    rc = _cab_se_bwd(_ptr(g), _ptr(y), B, HW, C, y.shape[1], S, _ptr(w1), _ptr(w2), alpha, _ptr(pool), _ptr(hidden),
+                     _ptr(scale), _ptr(ws), _ptr(dy), _ptr(dw1), _ptr(db1), _ptr(dw2), _ptr(db2), _stream())
+    _check(rc, "srk_cab_se_bwd")

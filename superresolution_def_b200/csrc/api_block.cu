@@ -2,7 +2,8 @@
 // (a fixed sequence of the tcgen05 GEMMs, the window-attention core and the small aux kernels), plus the
 // stand-alone window-attention and LayerNorm ops.  Host code only orchestrates launches on the caller's
 // stream; it never allocates or synchronises.
-#include "attn_ws8.cuh"
+#include "attn_win16.cuh"
+#include "cab_aux.cuh"
 #include "block_aux.cuh"
 #include "srk_host.h"
 
@@ -16,15 +17,15 @@ inline BlockDims to_dims(const SrkBlockDims* d) {
   return o;
 }
 
-int check_dims(const SrkBlockDims* d, const SrkGeom* g) {
+int check_dims(const SrkBlockDims* d, const SrkGeom* g, int ws = 8) {
   if (!d) return fail(SRK_ERR_ARG, "null dims");
   if (d->Cp != 192 || d->heads * d->ds != 192 || d->ds != 32)
     return fail(SRK_ERR_UNSUPPORTED, "block kernels are specialised for Cp == heads*ds == 192, ds == 32");
   if (d->C >= d->Cp || d->dh >= d->ds || d->hidden >= d->Hp || d->Hp % 256 != 0 || d->C != d->heads * d->dh)
     return fail(SRK_ERR_UNSUPPORTED, "need C < Cp, dh < ds, hidden < Hp, Hp % 256 == 0, C == heads*dh");
   if (g) {
-    if (g->ws != 8) return fail(SRK_ERR_UNSUPPORTED, "window attention core is specialised for ws == 8");
-    if (g->H % 8 || g->W % 8 || g->shift < 0 || g->shift >= 8) return fail(SRK_ERR_ARG, "bad geometry");
+    if (g->ws != ws) return fail(SRK_ERR_UNSUPPORTED, "window attention cores are specialised for ws == 8 (Swin) / 16 (HAT)");
+    if (g->H % ws || g->W % ws || g->shift < 0 || g->shift >= ws) return fail(SRK_ERR_ARG, "bad geometry");
     if ((long long)g->B * g->H * g->W % 128 != 0) return fail(SRK_ERR_ARG, "B*H*W must be a multiple of 128");
   }
   return SRK_OK;
@@ -112,6 +113,112 @@ int launch_attn_bwd(const SrkGeom* g, int heads, const void* qkv, int ld_qkv, co
   return SRK_OK;
 }
 
+
+template <int MODE>
+int launch_attn16_fwd_t(const Attn16Args& a, cudaStream_t stream) {
+  static bool configured = false;
+  constexpr int smem = a16_fwd_smem<MODE>();
+  if (!configured) {
+    SRK_CUDA_OK(cudaFuncSetAttribute(win_attn16_fwd_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int nitems = a.B * (a.H / 16) * (a.W / 16) * 2;
+  int gx = num_sms() * 2 / a.heads;
+  if (gx > nitems) gx = nitems;
+  if (gx < 1) gx = 1;
+  win_attn16_fwd_kernel<MODE><<<dim3(gx, a.heads), A16_FWD_THREADS, smem, stream>>>(a);
+  SRK_LAUNCHED(1);
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+int attn16_bwd_gx(int nwin, int heads) {
+  int gx = num_sms() / heads;
+  if (gx > nwin) gx = nwin;
+  return gx < 1 ? 1 : gx;
+}
+
+struct Attn16Ws { size_t scratch_off, dkv_off, total; int gx; };
+Attn16Ws attn16_ws_layout(const SrkGeom* g, int mode, int heads) {
+  Attn16Ws L{};
+  const int nwin = g->B * (g->H / 16) * (g->W / 16);
+  L.gx = attn16_bwd_gx(nwin, heads);
+  const int nkt = mode == MODE_SELF ? 4 : 12;
+  L.scratch_off = 0;
+  size_t o = (size_t)L.gx * heads * nkt * 16 * 32 * 4 * sizeof(float);
+  L.dkv_off = o;
+  if (mode == MODE_OCA) o += (size_t)nwin * heads * 2 * 768 * 32 * sizeof(__nv_bfloat16);
+  L.total = o;
+  return L;
+}
+
+template <int MODE>
+int launch_attn16_bwd_t(Attn16Args a, void* ws, const Attn16Ws& L, float* d_table, cudaStream_t stream) {
+  using SM = A16BwdSmem<MODE>;
+  static bool configured = false;
+  if (!configured) {
+    SRK_CUDA_OK(cudaFuncSetAttribute(win_attn16_bwd_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
+    configured = true;
+  }
+  a.dbias_scratch = reinterpret_cast<float*>(static_cast<char*>(ws) + L.scratch_off);
+  a.dkv_win = reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(ws) + L.dkv_off);
+  win_attn16_bwd_kernel<MODE><<<dim3(L.gx, a.heads), A16_BWD_THREADS, SM::kBytes, stream>>>(a);
+  SRK_LAUNCHED(1);
+  SRK_CUDA_OK(cudaGetLastError());
+  if (MODE == MODE_OCA) {
+    oca_kv_gather_kernel<<<num_sms() * 8, 256, 0, stream>>>(a.dkv_win, a.dqkv, a.ld_qkv, a.B, a.H, a.W, a.heads);
+    SRK_LAUNCHED(1);
+    SRK_CUDA_OK(cudaGetLastError());
+  }
+  if (d_table) {
+    const int n = A16<MODE>::TBL * a.heads;
+    attn16_dbias_finish_kernel<MODE><<<(n + 127) / 128, 128, 0, stream>>>(a.dbias_scratch, L.gx, a.heads, d_table);
+    SRK_LAUNCHED(1);
+    SRK_CUDA_OK(cudaGetLastError());
+  }
+  return SRK_OK;
+}
+
+int check_attn16(const SrkGeom* g, int mode, int ld_qkv, int ld_out) {
+  if (!g || g->ws != 16 || g->H % 16 || g->W % 16) return fail(SRK_ERR_UNSUPPORTED, "srk_win_attn16: ws must be 16");
+  if (mode != MODE_SELF && mode != MODE_OCA) return fail(SRK_ERR_ARG, "srk_win_attn16: mode");
+  if (mode == MODE_OCA && g->shift != 0) return fail(SRK_ERR_ARG, "srk_win_attn16: OCA has no shift");
+  if (mode == MODE_SELF && g->shift != 0 && g->shift != 8) return fail(SRK_ERR_UNSUPPORTED, "srk_win_attn16: shift must be 0 or ws/2");
+  if (ld_qkv % 8 || ld_out % 8) return fail(SRK_ERR_ARG, "srk_win_attn16: rows must be 16-byte aligned");
+  return SRK_OK;
+}
+
+int attn16_fwd(const SrkGeom* g, int mode, int heads, const void* qkv, int ld_qkv, const float* table, void* out,
+               int ld_out, float* lse, int ones_col, cudaStream_t stream) {
+  Attn16Args a{};
+  a.qkv = static_cast<const __nv_bfloat16*>(qkv);
+  a.out = static_cast<__nv_bfloat16*>(out);
+  a.lse = lse;
+  a.bias_table = table;
+  a.B = g->B; a.H = g->H; a.W = g->W; a.heads = heads; a.shift = g->shift;
+  a.ld_qkv = ld_qkv; a.ld_o = ld_out; a.ones_col = ones_col;
+  a.T = (long long)g->B * g->H * g->W;
+  return mode == MODE_SELF ? launch_attn16_fwd_t<MODE_SELF>(a, stream) : launch_attn16_fwd_t<MODE_OCA>(a, stream);
+}
+
+int attn16_bwd(const SrkGeom* g, int mode, int heads, const void* qkv, int ld_qkv, const float* table, const void* out,
+               const void* d_out, int ld_out, const float* lse, void* d_qkv, void* ws, float* d_table,
+               cudaStream_t stream) {
+  Attn16Args a{};
+  a.qkv = static_cast<const __nv_bfloat16*>(qkv);
+  a.osave = static_cast<const __nv_bfloat16*>(out);
+  a.dout = static_cast<const __nv_bfloat16*>(d_out);
+  a.dqkv = static_cast<__nv_bfloat16*>(d_qkv);
+  a.lse = const_cast<float*>(lse);
+  a.bias_table = table;
+  a.B = g->B; a.H = g->H; a.W = g->W; a.heads = heads; a.shift = g->shift;
+  a.ld_qkv = ld_qkv; a.ld_o = ld_out; a.ones_col = -1;
+  a.T = (long long)g->B * g->H * g->W;
+  const Attn16Ws L = attn16_ws_layout(g, mode, heads);
+  return mode == MODE_SELF ? launch_attn16_bwd_t<MODE_SELF>(a, ws, L, d_table, stream)
+                           : launch_attn16_bwd_t<MODE_OCA>(a, ws, L, d_table, stream);
+}
+
 __global__ void rpb_partials_reduce_kernel(const float* __restrict__ part, int nparts, int heads, float* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // i = t*heads + h (reference layout)
   if (i >= 225 * heads) return;
@@ -152,10 +259,10 @@ extern "C" int srk_block_prep_weights(const SrkBlockDims* d, const SrkBlockParam
   return SRK_OK;
 }
 
-extern "C" int srk_swin_block_fwd(const SrkBlockDims* d, const SrkGeom* g, const SrkBlockWeights* w,
-                                  const SrkBlockParams* p, const float* next_norm_w, const float* next_norm_b,
-                                  const SrkBlockActs* a, void* stream) {
-  int rc = check_dims(d, g);
+static int block_fwd_impl(const SrkBlockDims* d, const SrkGeom* g, const SrkBlockWeights* w,
+                          const SrkBlockParams* p, const float* next_norm_w, const float* next_norm_b,
+                          const SrkBlockActs* a, const SrkHatExtra* x, void* stream) {
+  int rc = check_dims(d, g, x ? 16 : 8);
   if (rc) return rc;
   const int T = g->B * g->H * g->W;
   const int QW = 3 * d->heads * d->ds, AW = d->heads * d->ds, Cp = d->Cp, Hp = d->Hp;
@@ -164,11 +271,18 @@ extern "C" int srk_swin_block_fwd(const SrkBlockDims* d, const SrkGeom* g, const
                         nullptr, 0, nullptr, stream)))
     return rc;
   // attention core (shift / partition / reverse by address arithmetic); ao[:, dh] = 1 (proj bias column)
-  if ((rc = launch_attn_fwd(g, d->heads, a->qkv, QW, p->rpb_table, a->ao, AW, d->dh, static_cast<cudaStream_t>(stream))))
-    return rc;
-  // x_mid = x_in + proj(ao); xn2 = LN2(x_mid)
+  if (x) {
+    if ((rc = check_attn16(g, x->mode, QW, AW))) return rc;
+    if (!x->res_in || !x->lse) return fail(SRK_ERR_ARG, "srk_hat_block_fwd: res_in and lse are required");
+    rc = attn16_fwd(g, x->mode, d->heads, a->qkv, QW, p->rpb_table, a->ao, AW, x->lse, d->dh, static_cast<cudaStream_t>(stream));
+  } else {
+    rc = launch_attn_fwd(g, d->heads, a->qkv, QW, p->rpb_table, a->ao, AW, d->dh, static_cast<cudaStream_t>(stream));
+  }
+  if (rc) return rc;
+  // x_mid = residual + proj(ao); xn2 = LN2(x_mid)   (residual: x_in, or for HAB x_in + conv_scale * CAB(xn1))
+  const void* resid = x ? x->res_in : a->x_in;
   SrkLnArgs ln2{d->C, d->C, p->norm2_w, p->norm2_b, a->stats2, nullptr, 1e-5f};
-  if ((rc = srk_gemm_tn(SRK_EPI_RES_LN, T, Cp, AW, a->ao, AW, w->proj_f, AW, a->x_mid, Cp, a->xn2, Cp, a->x_in, Cp,
+  if ((rc = srk_gemm_tn(SRK_EPI_RES_LN, T, Cp, AW, a->ao, AW, w->proj_f, AW, a->x_mid, Cp, a->xn2, Cp, resid, Cp,
                         nullptr, 0, &ln2, stream)))
     return rc;
   // act = gelu(fc1(xn2)), dact = gelu'(.)
@@ -184,16 +298,18 @@ extern "C" int srk_swin_block_fwd(const SrkBlockDims* d, const SrkGeom* g, const
   return SRK_OK;
 }
 
-extern "C" int srk_swin_block_bwd(const SrkBlockDims* d, const SrkGeom* g, const SrkBlockWeights* w,
-                                  const SrkBlockParams* p, const SrkBlockActs* a, const void* g_out,
-                                  const SrkBlockScratch* s, void* g_in, const SrkBlockGrads* grads, int accumulate,
-                                  void* stream_) {
-  int rc = check_dims(d, g);
+static int block_bwd_impl(const SrkBlockDims* d, const SrkGeom* g, const SrkBlockWeights* w,
+                          const SrkBlockParams* p, const SrkBlockActs* a, const void* g_out,
+                          const SrkBlockScratch* s, void* g_in, const SrkBlockGrads* grads, int accumulate,
+                          const SrkHatExtra* x, void* stream_) {
+  int rc = check_dims(d, g, x ? 16 : 8);
   if (rc) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int T = g->B * g->H * g->W;
   const int QW = 3 * d->heads * d->ds, AW = d->heads * d->ds, Cp = d->Cp, Hp = d->Hp;
-  const WsLayout L = ws_layout(d, g);
+  SrkGeom g8 = *g;
+  g8.ws = 8;  // the fp32 scratch layout only depends on T; its rpb partial area is used by the ws == 8 core alone
+  const WsLayout L = ws_layout(d, &g8);
   float* ws = s->wg_ws;
 
   // dU = (g_out @ W2) * gelu'(u)
@@ -218,25 +334,128 @@ extern "C" int srk_swin_block_bwd(const SrkBlockDims* d, const SrkGeom* g, const
   if ((rc = srk_gemm_wgrad(T, Cp, AW, s->g_mid, Cp, a->ao, AW, ws + L.partials, wgrad_splits(T, (Cp + 127) / 128),
                            ws + L.ext_proj, stream_)))
     return rc;
-  // attention backward -> d_qkv, rpb-table partials
-  if ((rc = launch_attn_bwd(g, d->heads, a->qkv, QW, p->rpb_table, s->d_ao, AW, s->d_qkv, ws + L.rpb, L.rpb_gx, stream)))
-    return rc;
-  // g_in = g_mid + LN1bwd(d_qkv @ Wqkv)
-  SrkLnArgs ln1{d->C, -1, p->norm1_w, nullptr, const_cast<float*>(a->stats1), ws + L.ln1, 1e-5f};
-  if ((rc = srk_gemm_tn(SRK_EPI_LNBWD, T, Cp, QW, s->d_qkv, QW, w->qkv_t, QW, g_in, Cp, nullptr, 0, a->x_in, Cp,
-                        s->g_mid, Cp, &ln1, stream_)))
-    return rc;
+  // attention backward -> d_qkv, rpb-table gradient (ws 8: per-CTA partials folded by the unpack kernel below)
+  if (x) {
+    if ((rc = check_attn16(g, x->mode, QW, AW))) return rc;
+    if (!x->lse || !x->attn_ws) return fail(SRK_ERR_ARG, "srk_hat_block_bwd: lse and attn_ws are required");
+    rc = attn16_bwd(g, x->mode, d->heads, a->qkv, QW, p->rpb_table, a->ao, s->d_ao, AW, x->lse, s->d_qkv, x->attn_ws,
+                    grads->rpb_table, stream);
+  } else {
+    rc = launch_attn_bwd(g, d->heads, a->qkv, QW, p->rpb_table, s->d_ao, AW, s->d_qkv, ws + L.rpb, L.rpb_gx, stream);
+  }
+  if (rc) return rc;
+  const bool defer_ln1 = x && x->d_xn1;
+  if (defer_ln1) {
+    // d_xn1 = d_qkv @ Wqkv; the caller adds the CAB branch and runs the LayerNorm-1 backward itself
+    if ((rc = srk_gemm_tn(SRK_EPI_STORE, T, Cp, QW, s->d_qkv, QW, w->qkv_t, QW, x->d_xn1, Cp, nullptr, 0, nullptr, 0,
+                          nullptr, 0, nullptr, stream_)))
+      return rc;
+  } else {
+    // g_in = g_mid + LN1bwd(d_qkv @ Wqkv)
+    SrkLnArgs ln1{d->C, -1, p->norm1_w, nullptr, const_cast<float*>(a->stats1), ws + L.ln1, 1e-5f};
+    if ((rc = srk_gemm_tn(SRK_EPI_LNBWD, T, Cp, QW, s->d_qkv, QW, w->qkv_t, QW, g_in, Cp, nullptr, 0, a->x_in, Cp,
+                          s->g_mid, Cp, &ln1, stream_)))
+      return rc;
+  }
   // dWqkv (+dbqkv in column C) = d_qkv^T @ xn1
   if ((rc = srk_gemm_wgrad(T, QW, Cp, s->d_qkv, QW, a->xn1, Cp, ws + L.partials, wgrad_splits(T, (QW + 127) / 128),
                            ws + L.ext_qkv, stream_)))
     return rc;
   // scatter everything into reference-shaped fp32 gradients
-  UnpackSrc us{ws + L.ext_qkv, ws + L.ext_proj, ws + L.ext_fc1, ws + L.ext_fc2, ws + L.ln1, ws + L.ln2, ws + L.rpb,
-               L.ln_grid, L.rpb_gx, 225};
+  UnpackSrc us{ws + L.ext_qkv, ws + L.ext_proj, ws + L.ext_fc1, ws + L.ext_fc2, defer_ln1 ? nullptr : ws + L.ln1,
+               ws + L.ln2, x ? nullptr : ws + L.rpb, L.ln_grid, L.rpb_gx, 225};
   BlockGradPtrs gp{grads->norm1_w, grads->norm1_b, grads->rpb_table, grads->qkv_w, grads->qkv_b, grads->proj_w,
                    grads->proj_b,  grads->norm2_w, grads->norm2_b,   grads->fc1_w, grads->fc1_b, grads->fc2_w,
                    grads->fc2_b};
   unpack_block_grads_kernel<<<296, 256, 0, stream>>>(to_dims(d), us, gp, accumulate ? 1.f : 0.f);
+  SRK_LAUNCHED(1);
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+extern "C" int srk_swin_block_fwd(const SrkBlockDims* d, const SrkGeom* g, const SrkBlockWeights* w,
+                                  const SrkBlockParams* p, const float* next_norm_w, const float* next_norm_b,
+                                  const SrkBlockActs* a, void* stream) {
+  return block_fwd_impl(d, g, w, p, next_norm_w, next_norm_b, a, nullptr, stream);
+}
+
+extern "C" int srk_swin_block_bwd(const SrkBlockDims* d, const SrkGeom* g, const SrkBlockWeights* w,
+                                  const SrkBlockParams* p, const SrkBlockActs* a, const void* g_out,
+                                  const SrkBlockScratch* s, void* g_in, const SrkBlockGrads* grads, int accumulate,
+                                  void* stream) {
+  return block_bwd_impl(d, g, w, p, a, g_out, s, g_in, grads, accumulate, nullptr, stream);
+}
+
+extern "C" int srk_hat_block_fwd(const SrkBlockDims* d, const SrkGeom* g, const SrkBlockWeights* w,
+                                 const SrkBlockParams* p, const float* next_norm_w, const float* next_norm_b,
+                                 const SrkBlockActs* a, const SrkHatExtra* x, void* stream) {
+  if (!x) return fail(SRK_ERR_ARG, "srk_hat_block_fwd: SrkHatExtra is required");
+  return block_fwd_impl(d, g, w, p, next_norm_w, next_norm_b, a, x, stream);
+}
+
+extern "C" int srk_hat_block_bwd(const SrkBlockDims* d, const SrkGeom* g, const SrkBlockWeights* w,
+                                 const SrkBlockParams* p, const SrkBlockActs* a, const void* g_out,
+                                 const SrkBlockScratch* s, void* g_in, const SrkBlockGrads* grads, const SrkHatExtra* x,
+                                 void* stream) {
+  if (!x) return fail(SRK_ERR_ARG, "srk_hat_block_bwd: SrkHatExtra is required");
+  return block_bwd_impl(d, g, w, p, a, g_out, s, g_in, grads, 0, x, stream);
+}
+
+extern "C" int srk_win_attn16_fwd(const SrkGeom* g, int mode, int heads, const void* qkv, int ld_qkv,
+                                  const float* rpb_table, void* out, int ld_out, float* lse, int ones_col, void* stream) {
+  int rc = check_attn16(g, mode, ld_qkv, ld_out);
+  if (rc) return rc;
+  return attn16_fwd(g, mode, heads, qkv, ld_qkv, rpb_table, out, ld_out, lse, ones_col, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" long long srk_win_attn16_bwd_ws_bytes(const SrkGeom* g, int mode, int heads) {
+  return (long long)attn16_ws_layout(g, mode, heads).total;
+}
+
+extern "C" int srk_win_attn16_bwd(const SrkGeom* g, int mode, int heads, const void* qkv, int ld_qkv,
+                                  const float* rpb_table, const void* out, const void* d_out, int ld_out,
+                                  const float* lse, void* d_qkv, void* ws, float* d_rpb_table, void* stream) {
+  int rc = check_attn16(g, mode, ld_qkv, ld_out);
+  if (rc) return rc;
+  if (!lse || !ws || !out) return fail(SRK_ERR_ARG, "srk_win_attn16_bwd: lse, ws and the forward output are required");
+  return attn16_bwd(g, mode, heads, qkv, ld_qkv, rpb_table, out, d_out, ld_out, lse, d_qkv, ws, d_rpb_table,
+                    static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int srk_cab_se_fwd(const void* y, const void* x, int B, int HW, int C, int Cp, int S, const float* w1,
+                              const float* b1, const float* w2, const float* b2, float alpha, float* ws, float* pool,
+                              float* hidden, float* scale, void* out, void* stream_) {
+  if (Cp % 8 || C > Cp || S < 1 || S > 32 || Cp > 256) return fail(SRK_ERR_UNSUPPORTED, "srk_cab_se_fwd: shape");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int nchunk = 32, pairs = Cp / 2, rpb = 4;
+  cab_colsum_kernel<<<dim3(nchunk, B), pairs * rpb, Cp * sizeof(float), stream>>>(
+      static_cast<const __nv_bfloat16*>(y), nullptr, HW, Cp, ws);
+  SRK_LAUNCHED(1);
+  cab_se_fwd_kernel<<<B, 256, (C + S) * sizeof(float), stream>>>(ws, nchunk, Cp, HW, C, S, w1, b1, w2, b2, pool, hidden, scale);
+  SRK_LAUNCHED(1);
+  cab_combine_fwd_kernel<<<num_sms() * 8, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x),
+                                                            static_cast<const __nv_bfloat16*>(y), scale, alpha,
+                                                            static_cast<__nv_bfloat16*>(out), (long long)B * HW, HW, C, Cp);
+  SRK_LAUNCHED(1);
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+extern "C" int srk_cab_se_bwd(const void* g, const void* y, int B, int HW, int C, int Cp, int S, const float* w1,
+                              const float* w2, float alpha, const float* pool, const float* hidden, const float* scale,
+                              float* ws, void* dy, float* dw1, float* db1, float* dw2, float* db2, void* stream_) {
+  if (Cp % 8 || C > Cp || S < 1 || S > 32 || Cp > 256) return fail(SRK_ERR_UNSUPPORTED, "srk_cab_se_bwd: shape");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int nchunk = 32, pairs = Cp / 2, rpb = 4;
+  float* dpool_hw = ws + (size_t)B * nchunk * Cp;
+  cab_colsum_kernel<<<dim3(nchunk, B), pairs * rpb, Cp * sizeof(float), stream>>>(
+      static_cast<const __nv_bfloat16*>(g), static_cast<const __nv_bfloat16*>(y), HW, Cp, ws);
+  SRK_LAUNCHED(1);
+  cab_se_bwd_kernel<<<1, 256, (C + 2 * S) * sizeof(float), stream>>>(ws, nchunk, Cp, HW, B, C, S, alpha, pool, hidden, scale,
+                                                                     w1, w2, dpool_hw, dw1, db1, dw2, db2);
+  SRK_LAUNCHED(1);
+  cab_combine_bwd_kernel<<<num_sms() * 8, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(g), scale, dpool_hw, alpha,
+                                                            static_cast<__nv_bfloat16*>(dy), (long long)B * HW, HW, C, Cp);
   SRK_LAUNCHED(1);
   SRK_CUDA_OK(cudaGetLastError());
   return SRK_OK;

@@ -1,0 +1,609 @@
+// attn_win16.cuh — fused window attention core for HAT's 16x16 windows (256 query tokens), forward + backward:
+//   MODE_SELF : (S)W-MSA of HAB   — keys = the same (cyclically shifted) window, shift mask 0/-100 computed from
+//               coordinates in-kernel (reference: HAT.calculate_mask hat_arch.py:921-940, added at :183-187)
+//   MODE_OCA  : overlapping cross-attention of OCAB — keys/values = the 24x24 halo window around the query window,
+//               ZERO outside the image after projection (nn.Unfold padding, hat_arch.py:377,408-410), no mask,
+//               (16+24-1)^2 bias table indexed with the reference's wrap-around offsets (:896-919).
+//
+// Replaces (reference, models/hat_arch/hat_arch.py): window_partition/window_reverse :97-126, torch.roll :280-302,
+// nn.Unfold + einops rearrange :408-409, and inside WindowAttention.forward :175-193 / OCAB.forward :419-428 the
+// q@k^T bmm, relative-position-bias gather+add, mask add, softmax, attn@v bmm and the head-merge transpose.
+// Shift / partition / reverse / unfold are address arithmetic; S and P never touch HBM.
+//
+// Layouts: qkv [T, 3*heads*32] bf16 token-major (q|k|v, heads padded 30->32, q pre-scaled by the projection weights),
+// out [T, heads*32] bf16, lse [heads][T] fp32 (row log-sum-exp, consumed by the backward).
+//
+// Design: flash-style tiles of 64 key slots on register-resident mma.sync fragments (exp-bound, not MMA-bound: 256x256
+// logits need 64 Ki ex2 per (window, head) against 8.4 MFLOP of MMA, so TMEM round trips would buy nothing here).
+// MODE_OCA lays the 24 key columns out as two 16-wide bands (the second half-empty, masked), i.e. 12 tiles of
+// (2 key rows x 2 bands x 16): every 16x16 (query-row, key-row) block then has the same shape as in MODE_SELF, which
+// lets the bias-table gradient be a tensor-core diagonal sum (see diag_mma below).
+#pragma once
+#include "attn_ws8.cuh"
+
+namespace srk {
+
+enum { MODE_SELF = 0, MODE_OCA = 1 };
+
+template <int MODE>
+struct A16 {
+  static constexpr int WS = 16;
+  static constexpr int WSE = (MODE == MODE_SELF) ? 16 : 24;
+  static constexpr int NKT = (MODE == MODE_SELF) ? 4 : 12;   // key tiles of 64 slots
+  static constexpr int NS = NKT * 64;                          // key slots (MODE_OCA: 768, 576 real)
+  static constexpr int TSIDE = WS + WSE - 1;                   // 31 / 39
+  static constexpr int TBL = TSIDE * TSIDE;                    // 961 / 1521
+  static constexpr int PAD = (WSE - WS) / 2;                   // 0 / 4
+};
+
+struct Attn16Args {
+  const __nv_bfloat16* qkv;   // [T, ld_qkv]
+  __nv_bfloat16* out;         // fwd: [T, ld_o]
+  float* lse;                 // [heads][T]
+  const __nv_bfloat16* dout;  // bwd: [T, ld_o]
+  const __nv_bfloat16* osave; // bwd: forward output [T, ld_o]
+  __nv_bfloat16* dqkv;        // bwd: [T, ld_qkv] (MODE_OCA: only the q third is written here)
+  __nv_bfloat16* dkv_win;     // bwd MODE_OCA: [nwin*heads][2][768][32] per-window dK/dV (gathered afterwards)
+  const float* bias_table;    // [TBL][heads]
+  float* dbias_scratch;       // bwd: [gridDim.x][heads][NKT][16 warps][32 lanes][4]
+  int B, H, W, heads, shift;
+  int ld_qkv, ld_o;
+  int ones_col;
+  long long T;
+};
+
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+
+// window (b, wy, wx) of window index w
+struct WinPos { int b, wy, wx; };
+__device__ __forceinline__ WinPos win_pos(const Attn16Args& a, int w) {
+  const int nwx = a.W >> 4, nwy = a.H >> 4;
+  WinPos p;
+  p.b = w / (nwx * nwy);
+  const int r = w - p.b * nwx * nwy;
+  p.wy = r / nwx;
+  p.wx = r - p.wy * nwx;
+  return p;
+}
+// token row of query (ty, tx) of the window (cyclic shift applied: shifted-frame coordinate -> image coordinate)
+__device__ __forceinline__ long long q_token(const Attn16Args& a, const WinPos& p, int ty, int tx) {
+  int y = p.wy * 16 + ty + a.shift, x = p.wx * 16 + tx + a.shift;
+  if (y >= a.H) y -= a.H;
+  if (x >= a.W) x -= a.W;
+  return ((long long)p.b * a.H + y) * a.W + x;
+}
+// key slot -> (ky, kx) inside the key window, validity (MODE_OCA pads 24 columns to 2 x 16)
+template <int MODE>
+__device__ __forceinline__ void slot_key(int slot, int& ky, int& kx, bool& valid) {
+  if (MODE == MODE_SELF) {
+    ky = slot >> 4; kx = slot & 15; valid = true;
+  } else {
+    ky = (slot >> 6) * 2 + ((slot >> 5) & 1);
+    kx = ((slot >> 4) & 1) * 16 + (slot & 15);
+    valid = kx < 24;
+  }
+}
+// token row of a key slot, or -1 when the key lies outside the image / is a padding slot (=> k = v = 0)
+template <int MODE>
+__device__ __forceinline__ long long k_token(const Attn16Args& a, const WinPos& p, int slot, bool& slot_valid) {
+  int ky, kx;
+  slot_key<MODE>(slot, ky, kx, slot_valid);
+  if (MODE == MODE_SELF) return q_token(a, p, ky, kx);
+  if (!slot_valid) return -1;
+  const int y = p.wy * 16 - A16<MODE>::PAD + ky, x = p.wx * 16 - A16<MODE>::PAD + kx;
+  if (y < 0 || y >= a.H || x < 0 || x >= a.W) return -1;
+  return ((long long)p.b * a.H + y) * a.W + x;
+}
+
+// region id of a shifted-frame coordinate (HAT.calculate_mask slices: [0,-ws), [-ws,-shift), [-shift, end))
+__device__ __forceinline__ int mask_region(int c, int size, int shift) {
+  return (c < size - 16) ? 0 : ((c < size - shift) ? 1 : 2);
+}
+
+// bias (+mask) for query (qy,qx), key n-tile `nt` of key tile `kt`, columns 2t+e: returns additive fp32 term
+template <int MODE>
+struct BiasCtx {
+  const float* s_bias;
+  const uint8_t* s_rid;  // MODE_SELF: region ids of the 256 window tokens (only when masked)
+  bool masked;
+};
+template <int MODE>
+__device__ __forceinline__ float bias_term(const BiasCtx<MODE>& c, int qy, int qx, int kt, int nt, int col) {
+  if (MODE == MODE_SELF) {
+    const int ky = kt * 4 + (nt >> 1), kx = (nt & 1) * 8 + col;
+    float v = c.s_bias[(qy - ky + 15) * 31 + (qx - kx + 15)];
+    if (c.masked && c.s_rid[qy * 16 + qx] != c.s_rid[ky * 16 + kx]) v += -100.0f;
+    return v;
+  } else {
+    const int ky = kt * 2 + (nt >> 2), kx = ((nt >> 1) & 1) * 16 + (nt & 1) * 8 + col;
+    if (kx >= 24) return -INFINITY;
+    int idx = (ky - qy - 7) * 39 + (kx - qx - 7);   // reference offset ws - wse + 1 = -7: negative rows wrap
+    if (idx < 0) idx += 1521;
+    return c.s_bias[idx];
+  }
+}
+
+// S[16 x 64] logits of this warp's 16 query rows (row-group qy) against key tile kt
+template <int MODE>
+__device__ __forceinline__ void qk_tile(const uint32_t (&aq)[2][4], uint32_t k_tile, const BiasCtx<MODE>& bc, int qy,
+                                        int kt, int lane, float (&s)[8][4]) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    uint32_t b0, b1, b2, b3;
+    ldsm_x4(k_tile + t32_off(nt * 8 + (lane & 7), lane >> 3), b0, b1, b2, b3);
+    s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+    mma_bf16(s[nt], aq[0], b0, b1);
+    mma_bf16(s[nt], aq[1], b2, b3);
+    s[nt][0] += bias_term<MODE>(bc, qy, g, kt, nt, 2 * t);
+    s[nt][1] += bias_term<MODE>(bc, qy, g, kt, nt, 2 * t + 1);
+    s[nt][2] += bias_term<MODE>(bc, qy, g + 8, kt, nt, 2 * t);
+    s[nt][3] += bias_term<MODE>(bc, qy, g + 8, kt, nt, 2 * t + 1);
+  }
+}
+
+// o[16 x 32] += A[16 x 64] (bf16 fragments built from fp32 s) * Bt[64 x 32]   (accumulating frag_times_tile)
+__device__ __forceinline__ void frag_times_tile_acc(const float (&s)[8][4], uint32_t bt_tile, int lane, float (&o)[4][4]) {
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    uint32_t a[4];
+    a[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+    a[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+    a[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+    a[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+    const int row = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+    for (int np = 0; np < 2; ++np) {
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4_t(bt_tile + t32_off(row, np * 2 + (lane >> 4)), b0, b1, b2, b3);
+      mma_bf16(o[2 * np], a, b0, b1);
+      mma_bf16(o[2 * np + 1], a, b2, b3);
+    }
+  }
+}
+
+// cooperative async load of the K and V slot tiles of one window (rows = key slots, zero-filled where absent)
+template <int MODE>
+__device__ __forceinline__ void load_kv(const Attn16Args& a, const WinPos& p, int h, uint32_t sK, uint32_t sV,
+                                        int nthreads) {
+  constexpr int NS = A16<MODE>::NS;
+  const int hw = a.heads * 32;
+  for (int c = threadIdx.x; c < NS * 4; c += nthreads) {
+    const int slot = c >> 2, ch = c & 3;
+    bool sv;
+    const long long tok = k_token<MODE>(a, p, slot, sv);
+    const bool ok = tok >= 0;
+    const __nv_bfloat16* src = a.qkv + (ok ? tok : 0) * a.ld_qkv + hw + h * 32 + ch * 8;
+    cp_async16_zfill(sK + t32_off(slot, ch), src, ok);
+    cp_async16_zfill(sV + t32_off(slot, ch), src + hw, ok);
+  }
+}
+
+// ============================================================================ forward
+// grid (gx, heads); 256 threads = 8 warps x 16 query rows = half a window per work item; 2 CTAs / SM.
+constexpr int A16_FWD_THREADS = 256;
+template <int MODE>
+constexpr int a16_fwd_smem() { return 128 * 64 + 2 * A16<MODE>::NS * 64; }
+
+template <int MODE>
+__global__ void __launch_bounds__(A16_FWD_THREADS, 2) win_attn16_fwd_kernel(const Attn16Args a) {
+  using G = A16<MODE>;
+  extern __shared__ __align__(128) uint8_t smem_dyn[];
+  __shared__ float s_bias[G::TBL];
+  __shared__ uint8_t s_rid[256];
+  const uint32_t sQ = smem_u32(smem_dyn), sK = sQ + 128 * 64, sV = sK + G::NS * 64;
+  const int h = blockIdx.y;
+  const int nwin = a.B * (a.H >> 4) * (a.W >> 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  for (int i = threadIdx.x; i < G::TBL; i += A16_FWD_THREADS) s_bias[i] = a.bias_table[i * a.heads + h];
+  const bool ones_here = a.ones_col >= h * 32 && a.ones_col < h * 32 + 32;
+  const int ones_c = a.ones_col - h * 32;
+  constexpr float kLog2e = 1.4426950408889634f;
+
+  for (int item = blockIdx.x; item < nwin * 2; item += gridDim.x) {
+    const int w = item >> 1, half = item & 1;
+    const WinPos p = win_pos(a, w);
+    __syncthreads();  // previous item fully consumed
+    for (int c = threadIdx.x; c < 128 * 4; c += A16_FWD_THREADS) {
+      const int i = c >> 2, ch = c & 3;
+      const long long tok = q_token(a, p, half * 8 + (i >> 4), i & 15);
+      cp_async16(sQ + t32_off(i, ch), a.qkv + tok * a.ld_qkv + h * 32 + ch * 8);
+    }
+    load_kv<MODE>(a, p, h, sK, sV, A16_FWD_THREADS);
+    cp_async_commit();
+    bool masked = false;
+    if (MODE == MODE_SELF && a.shift > 0) {
+      masked = (p.wy == (a.H >> 4) - 1) || (p.wx == (a.W >> 4) - 1);
+      if (masked) {
+        const int i = threadIdx.x;  // 256 threads == 256 window tokens
+        s_rid[i] = uint8_t(mask_region(p.wy * 16 + (i >> 4), a.H, a.shift) * 3 + mask_region(p.wx * 16 + (i & 15), a.W, a.shift));
+      }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    const BiasCtx<MODE> bc{s_bias, s_rid, masked};
+    const int r0 = warp * 16, qy = half * 8 + warp;
+    uint32_t aq[2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const int row = r0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+      ldsm_x4(sQ + t32_off(row, ks * 2 + (lane >> 4)), aq[ks][0], aq[ks][1], aq[ks][2], aq[ks][3]);
+    }
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    float o[4][4];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+#pragma unroll 1
+    for (int kt = 0; kt < G::NKT; ++kt) {
+      float s[8][4];
+      qk_tile<MODE>(aq, sK + kt * 64 * 64, bc, qy, kt, lane, s);
+      float t0 = -INFINITY, t1 = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        t0 = fmaxf(t0, fmaxf(s[nt][0], s[nt][1]));
+        t1 = fmaxf(t1, fmaxf(s[nt][2], s[nt][3]));
+      }
+      t0 = fmaxf(t0, __shfl_xor_sync(0xffffffffu, t0, 1));
+      t0 = fmaxf(t0, __shfl_xor_sync(0xffffffffu, t0, 2));
+      t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, 1));
+      t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, 2));
+      const float n0 = fmaxf(m0, t0), n1 = fmaxf(m1, t1);  // finite: every tile has at least one valid key per row
+      const float c0 = fast_ex2((m0 - n0) * kLog2e), c1 = fast_ex2((m1 - n1) * kLog2e);
+      m0 = n0; m1 = n1;
+      float r0s = 0.f, r1s = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        s[nt][0] = fast_ex2((s[nt][0] - n0) * kLog2e);
+        s[nt][1] = fast_ex2((s[nt][1] - n0) * kLog2e);
+        s[nt][2] = fast_ex2((s[nt][2] - n1) * kLog2e);
+        s[nt][3] = fast_ex2((s[nt][3] - n1) * kLog2e);
+        r0s += s[nt][0] + s[nt][1];
+        r1s += s[nt][2] + s[nt][3];
+      }
+      l0 = l0 * c0 + r0s;
+      l1 = l1 * c1 + r1s;
+#pragma unroll
+      for (int n = 0; n < 4; ++n) { o[n][0] *= c0; o[n][1] *= c0; o[n][2] *= c1; o[n][3] *= c1; }
+      frag_times_tile_acc(s, sV + kt * 64 * 64, lane, o);
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) { o[n][0] *= i0; o[n][1] *= i0; o[n][2] *= i1; o[n][3] *= i1; }
+    if (t == 0 && a.lse != nullptr) {
+      a.lse[(long long)h * a.T + q_token(a, p, qy, g)] = m0 + logf(l0);
+      a.lse[(long long)h * a.T + q_token(a, p, qy, g + 8)] = m1 + logf(l1);
+    }
+    // this warp's Q rows are dead (fragments live in registers): reuse them as the output staging rows
+    __syncwarp();
+    store_frag_t32(sQ, r0, lane, o);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int c = lane + 32 * k, i = c >> 2, ch = c & 3;  // 16 rows x 4 chunks
+      const long long tok = q_token(a, p, qy, i);
+      uint4 v = lds128(sQ + t32_off(r0 + i, ch));
+      if (ones_here && ch == (ones_c >> 3)) {
+        const int word = (ones_c & 7) >> 1;
+        const uint32_t keep = (ones_c & 1) ? 0x0000FFFFu : 0xFFFF0000u;
+        const uint32_t one = (ones_c & 1) ? 0x3F800000u : 0x00003F80u;
+        v.x = (word == 0) ? ((v.x & keep) | one) : v.x;
+        v.y = (word == 1) ? ((v.y & keep) | one) : v.y;
+        v.z = (word == 2) ? ((v.z & keep) | one) : v.z;
+        v.w = (word == 3) ? ((v.w & keep) | one) : v.w;
+      }
+      *reinterpret_cast<uint4*>(a.out + tok * a.ld_o + h * 32 + ch * 8) = v;
+    }
+  }
+}
+
+// ============================================================================ backward
+// grid (gx, heads); 512 threads = 16 warps, warp w owns query row-group qy = w of one whole window per work item.
+constexpr int A16_BWD_THREADS = 512;
+template <int MODE>
+struct A16BwdSmem {
+  static constexpr int kQ = 0;                                  // [256][32]
+  static constexpr int kDO = kQ + 256 * 64;                     // [256][32]
+  static constexpr int kK = kDO + 256 * 64;                     // [NS][32]
+  static constexpr int kV = kK + A16<MODE>::NS * 64;            // [NS][32]
+  static constexpr int kP = kV + A16<MODE>::NS * 64;            // [256][64]  (later: dQ staging)
+  static constexpr int kDS = kP + 256 * 128;                    // [256][64]
+  static constexpr int kOut = kDS + 256 * 128;                  // dK, dV staging 2 x [64][32]
+  static constexpr int kBytes = kOut + 2 * 64 * 64;
+};
+
+// dst[16 keys x 16 cols] = A^T B: A = t64 tile [256 q][64 slots] (this warp: slots k0..k0+15), B = t32 tile [256 q][32]
+// (column half ch), contraction over the 256 queries.
+__device__ __forceinline__ void tileT_times_tile256(uint32_t a_tile, uint32_t b_tile, int k0, int ch, int lane,
+                                                    float (&o)[2][4]) {
+#pragma unroll
+  for (int n = 0; n < 2; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+#pragma unroll 4
+  for (int kk = 0; kk < 16; ++kk) {
+    uint32_t af[4];
+    {
+      const int i = lane >> 3;
+      const int row = kk * 16 + (lane & 7) + ((i >> 1) & 1) * 8;  // query
+      const int col = k0 + (i & 1) * 8;                           // key slot
+      ldsm_x4_t(a_tile + t64_off(row, col >> 3), af[0], af[1], af[2], af[3]);
+    }
+    const int row = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+    uint32_t b0, b1, b2, b3;
+    ldsm_x4_t(b_tile + t32_off(row, ch * 2 + (lane >> 4)), b0, b1, b2, b3);
+    mma_bf16(o[0], af, b0, b1);
+    mma_bf16(o[1], af, b2, b3);
+  }
+}
+
+// Bias-table gradient as a tensor-core diagonal sum.  For every (query row qy, key row / band) pair the 16x16 block
+// X[qx][kx] of dS contributes  D[b] = sum_{qx,kx} R[b; qx,kx] X[qx][kx]  with R = [b == 15 + qx - kx] (MODE_SELF) or
+// [b == 15 + kx - qx] (MODE_OCA).  As an MMA: M = b (32 diagonals, two m-tiles), K = (qx, kx) (16 k-steps of 16),
+// N = 8 pairs.  Per key tile there are 64 pairs = 8 n-tiles; warp w takes n-tile w&7 and m-tile w>>3.
+// Pair n of n-tile j: query row qy = 2j + (n>>2), in-tile key row/band index r = n&3 (its 16 slots = columns r*16..).
+template <int MODE>
+__device__ __forceinline__ void diag_mma(uint32_t ds_tile, int warp, int lane, float (&acc)[4]) {
+  const int j = warp & 7, mt = warp >> 3;
+  const int g = lane >> 2, t = lane & 3;
+  acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+  const int n = lane & 7;                       // ldmatrix row provider: pair index
+  const int prow = (2 * j + (n >> 2)) * 16;     // first dS row of that pair's query row-group
+  const int pchunk = (n & 3) * 2 + ((lane >> 3) & 1);
+  const int b_lo = mt * 16 + g, b_hi = b_lo + 8;
+#pragma unroll 4
+  for (int qx = 0; qx < 16; ++qx) {
+    uint32_t b0, b1;
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];"
+                 : "=r"(b0), "=r"(b1) : "r"(ds_tile + t64_off(prow + qx, pchunk)));
+    // A fragment of R for this k-step: element (row b, k = kx) is 1.0 iff kx == kx_of(b)
+    const int k_lo = (MODE == MODE_SELF) ? (qx + 15 - b_lo) : (b_lo - 15 + qx);
+    const int k_hi = (MODE == MODE_SELF) ? (qx + 15 - b_hi) : (b_hi - 15 + qx);
+    uint32_t af[4];
+    af[0] = (k_lo == 2 * t ? 0x00003F80u : 0u) | (k_lo == 2 * t + 1 ? 0x3F800000u : 0u);
+    af[1] = (k_hi == 2 * t ? 0x00003F80u : 0u) | (k_hi == 2 * t + 1 ? 0x3F800000u : 0u);
+    af[2] = (k_lo == 2 * t + 8 ? 0x00003F80u : 0u) | (k_lo == 2 * t + 9 ? 0x3F800000u : 0u);
+    af[3] = (k_hi == 2 * t + 8 ? 0x00003F80u : 0u) | (k_hi == 2 * t + 9 ? 0x3F800000u : 0u);
+    mma_bf16(acc, af, b0, b1);
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(A16_BWD_THREADS, 1) win_attn16_bwd_kernel(const Attn16Args a) {
+  using G = A16<MODE>;
+  using L = A16BwdSmem<MODE>;
+  extern __shared__ __align__(128) uint8_t smem_dyn[];
+  __shared__ float s_bias[G::TBL];
+  __shared__ float s_lse[256];
+  __shared__ float s_delta[256];
+  __shared__ uint8_t s_rid[256];
+  const uint32_t sm0 = smem_u32(smem_dyn);
+  const uint32_t sQ = sm0 + L::kQ, sDO = sm0 + L::kDO, sK = sm0 + L::kK, sV = sm0 + L::kV, sP = sm0 + L::kP,
+                 sDS = sm0 + L::kDS, sOut = sm0 + L::kOut;
+  const int h = blockIdx.y;
+  const int nwin = a.B * (a.H >> 4) * (a.W >> 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int hw = a.heads * 32;
+  constexpr float kLog2e = 1.4426950408889634f;
+  for (int i = threadIdx.x; i < G::TBL; i += A16_BWD_THREADS) s_bias[i] = a.bias_table[i * a.heads + h];
+  // this CTA's slice of the diagonal-sum scratch: [NKT][16 warps][32 lanes] float4, exclusively owned per thread
+  float4* scratch = reinterpret_cast<float4*>(a.dbias_scratch) +
+                    ((size_t)blockIdx.x * a.heads + h) * (G::NKT * 16 * 32);
+  for (int kt = 0; kt < G::NKT; ++kt) scratch[(kt * 16 + warp) * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  for (int w = blockIdx.x; w < nwin; w += gridDim.x) {
+    const WinPos p = win_pos(a, w);
+    __syncthreads();
+    for (int c = threadIdx.x; c < 2 * 256 * 4; c += A16_BWD_THREADS) {
+      const int which = c >> 10, rem = c & 1023, i = rem >> 2, ch = rem & 3;
+      const long long tok = q_token(a, p, i >> 4, i & 15);
+      const __nv_bfloat16* src = which ? (a.dout + tok * a.ld_o + h * 32 + ch * 8) : (a.qkv + tok * a.ld_qkv + h * 32 + ch * 8);
+      cp_async16((which ? sDO : sQ) + t32_off(i, ch), src);
+    }
+    load_kv<MODE>(a, p, h, sK, sV, A16_BWD_THREADS);
+    cp_async_commit();
+    bool masked = false;
+    if (MODE == MODE_SELF && a.shift > 0) {
+      masked = (p.wy == (a.H >> 4) - 1) || (p.wx == (a.W >> 4) - 1);
+      if (masked && threadIdx.x < 256) {
+        const int i = threadIdx.x;
+        s_rid[i] = uint8_t(mask_region(p.wy * 16 + (i >> 4), a.H, a.shift) * 3 + mask_region(p.wx * 16 + (i & 15), a.W, a.shift));
+      }
+    }
+    {  // delta_i = sum_d dO[i,d] * O[i,d]   (two threads per query row, 16 columns each), lse
+      const int i = threadIdx.x >> 1, hf = threadIdx.x & 1;
+      const long long tok = q_token(a, p, i >> 4, i & 15);
+      const uint4* po = reinterpret_cast<const uint4*>(a.osave + tok * a.ld_o + h * 32 + hf * 16);
+      const uint4* pd = reinterpret_cast<const uint4*>(a.dout + tok * a.ld_o + h * 32 + hf * 16);
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const uint4 vo = po[k], vd = pd[k];
+        const uint32_t wo[4] = {vo.x, vo.y, vo.z, vo.w}, wd[4] = {vd.x, vd.y, vd.z, vd.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc += bf16_lo(wo[e]) * bf16_lo(wd[e]) + bf16_hi(wo[e]) * bf16_hi(wd[e]);
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      if (hf == 0) {
+        s_delta[i] = acc;
+        s_lse[i] = a.lse[(long long)h * a.T + tok] * kLog2e;
+      }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    const BiasCtx<MODE> bc{s_bias, s_rid, masked};
+    const int r0 = warp * 16, qy = warp;
+    uint32_t aq[2][4], ad[2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const int row = r0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+      ldsm_x4(sQ + t32_off(row, ks * 2 + (lane >> 4)), aq[ks][0], aq[ks][1], aq[ks][2], aq[ks][3]);
+      ldsm_x4(sDO + t32_off(row, ks * 2 + (lane >> 4)), ad[ks][0], ad[ks][1], ad[ks][2], ad[ks][3]);
+    }
+    const float lse0 = s_lse[r0 + g], lse1 = s_lse[r0 + g + 8];
+    const float dl0 = s_delta[r0 + g], dl1 = s_delta[r0 + g + 8];
+    float dq[4][4];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) dq[n][0] = dq[n][1] = dq[n][2] = dq[n][3] = 0.f;
+
+#pragma unroll 1
+    for (int kt = 0; kt < G::NKT; ++kt) {
+      const uint32_t kT = sK + kt * 64 * 64, vT = sV + kt * 64 * 64;
+      // ---- phase A: this warp's 16 query rows x 64 key slots
+      float s[8][4];
+      qk_tile<MODE>(aq, kT, bc, qy, kt, lane, s);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {  // P = exp(S - lse), normalised
+        s[nt][0] = fast_ex2(fmaf(s[nt][0], kLog2e, -lse0));
+        s[nt][1] = fast_ex2(fmaf(s[nt][1], kLog2e, -lse0));
+        s[nt][2] = fast_ex2(fmaf(s[nt][2], kLog2e, -lse1));
+        s[nt][3] = fast_ex2(fmaf(s[nt][3], kLog2e, -lse1));
+      }
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {  // dP = dO V^T, dS = P * (dP - delta); P, dS -> smem (bf16)
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4(vT + t32_off(nt * 8 + (lane & 7), lane >> 3), b0, b1, b2, b3);
+        float dp[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_bf16(dp, ad[0], b0, b1);
+        mma_bf16(dp, ad[1], b2, b3);
+        const uint32_t plo = pack_bf16(s[nt][0], s[nt][1]), phi = pack_bf16(s[nt][2], s[nt][3]);
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(sP + t64_off(r0 + g, nt) + t * 4), "r"(plo) : "memory");
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(sP + t64_off(r0 + g + 8, nt) + t * 4), "r"(phi) : "memory");
+        s[nt][0] *= (dp[0] - dl0);
+        s[nt][1] *= (dp[1] - dl0);
+        s[nt][2] *= (dp[2] - dl1);
+        s[nt][3] *= (dp[3] - dl1);
+        const uint32_t dlo = pack_bf16(s[nt][0], s[nt][1]), dhi = pack_bf16(s[nt][2], s[nt][3]);
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(sDS + t64_off(r0 + g, nt) + t * 4), "r"(dlo) : "memory");
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(sDS + t64_off(r0 + g + 8, nt) + t * 4), "r"(dhi) : "memory");
+      }
+      frag_times_tile_acc(s, kT, lane, dq);  // dQ += dS K
+      __syncthreads();
+      // ---- phase B: dK / dV of this key tile (contraction over all 256 queries) + bias-gradient diagonal sums
+      {
+        const int m = warp >> 3, rg = (warp >> 1) & 3, ch = warp & 1;
+        float o[2][4];
+        tileT_times_tile256(m ? sP : sDS, m ? sDO : sQ, rg * 16, ch, lane, o);
+        const uint32_t dst = sOut + m * (64 * 64);
+#pragma unroll
+        for (int n = 0; n < 2; ++n) {
+          const uint32_t lo = pack_bf16(o[n][0], o[n][1]), hi = pack_bf16(o[n][2], o[n][3]);
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(dst + t32_off(rg * 16 + g, ch * 2 + n) + t * 4), "r"(lo) : "memory");
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(dst + t32_off(rg * 16 + g + 8, ch * 2 + n) + t * 4), "r"(hi) : "memory");
+        }
+        float acc[4];
+        diag_mma<MODE>(sDS, warp, lane, acc);
+        float4* sp = scratch + (kt * 16 + warp) * 32 + lane;
+        float4 v = *sp;
+        v.x += acc[0]; v.y += acc[1]; v.z += acc[2]; v.w += acc[3];
+        *sp = v;
+      }
+      __syncthreads();
+      {  // store dK, dV rows of this tile: 2 matrices x 64 slots x 4 chunks = 512 x 16 B
+        const int c = threadIdx.x, m = c >> 8, rem = c & 255, sl = rem >> 2, ch = rem & 3;
+        const int slot = kt * 64 + sl;
+        const uint4 v = lds128(sOut + m * (64 * 64) + t32_off(sl, ch));
+        if (MODE == MODE_SELF) {
+          bool sv;
+          const long long tok = k_token<MODE>(a, p, slot, sv);
+          *reinterpret_cast<uint4*>(a.dqkv + tok * a.ld_qkv + (1 + m) * hw + h * 32 + ch * 8) = v;
+        } else {
+          __nv_bfloat16* dst = a.dkv_win + ((((size_t)w * a.heads + h) * 2 + m) * G::NS + slot) * 32 + ch * 8;
+          *reinterpret_cast<uint4*>(dst) = v;
+        }
+      }
+      // sOut / sP / sDS are rewritten only after the next tile's first barrier (phase A writes sP/sDS before it):
+      // phase A of tile kt+1 overwrites sP/sDS while slow threads may still run phase B reads -> barrier needed,
+      // which is the __syncthreads() above (all phase B reads precede it).
+    }
+    // dQ -> staging (this warp's rows of the P tile region, dead after the last barrier) -> global
+    __syncwarp();
+    store_frag_t32(sP, r0, lane, dq);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int c = lane + 32 * k, i = c >> 2, ch = c & 3;
+      const long long tok = q_token(a, p, qy, i);
+      *reinterpret_cast<uint4*>(a.dqkv + tok * a.ld_qkv + h * 32 + ch * 8) = lds128(sP + t32_off(r0 + i, ch));
+    }
+  }
+}
+
+// d_rpb_table[t*heads + h] = sum over CTAs and (qy, key row) pairs of the diagonal sums that map to table entry t.
+// One thread per (table entry, head).  Accumulator addressing mirrors diag_mma's fragment layout.
+template <int MODE>
+__global__ void attn16_dbias_finish_kernel(const float* __restrict__ scratch, int gx, int heads, float* __restrict__ out) {
+  using G = A16<MODE>;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= G::TBL * heads) return;
+  const int tbl = idx / heads, h = idx % heads;
+  float total = 0.f;
+  // enumerate (qy, ky, band, b) accumulators that feed table entry `tbl`
+  for (int qy = 0; qy < 16; ++qy) {
+    for (int band = 0; band < (MODE == MODE_SELF ? 1 : 2); ++band) {
+      int ky, b;
+      if (MODE == MODE_SELF) {
+        const int ry = tbl / 31, rx = tbl % 31;   // ry = qy - ky + 15, rx = qx - kx + 15 = b
+        ky = qy + 15 - ry; b = rx;
+        if (ky < 0 || ky >= 16) continue;
+      } else {
+        // idx_ref = ry*39 + rx with ry = ky-qy-7, rx = kx-qx-7, both in [-22,16]; a negative idx_ref was wrapped (+1521)
+        const int v = (tbl > 16 * 39 + 16) ? tbl - 1521 : tbl;
+        const int num = v + 22;  // floor division by 39
+        const int ry = (num >= 0) ? num / 39 : -((-num + 38) / 39);
+        const int rx = v - ry * 39;  // in [-22, 16]
+        ky = ry + qy + 7;
+        if (ky < 0 || ky >= 24) continue;
+        b = rx + 22 - band * 16;   // b = 15 + kx_in_band - qx, kx = band*16 + kx_in_band
+        if (b < 0 || b >= 32) continue;
+      }
+      int kt, r;
+      if (MODE == MODE_SELF) { kt = ky >> 2; r = ky & 3; }
+      else { kt = ky >> 1; r = (ky & 1) * 2 + band; }
+      const int j = qy >> 1, n = ((qy & 1) << 2) | r;
+      const int mt = b >> 4, rowin = b & 15;
+      const int lane = (rowin & 7) * 4 + (n >> 1), reg = (rowin >> 3) * 2 + (n & 1);
+      const int warp = mt * 8 + j;
+      for (int c = 0; c < gx; ++c)
+        total += scratch[((((size_t)c * heads + h) * G::NKT + kt) * 16 + warp) * 128 + lane * 4 + reg];
+    }
+  }
+  out[idx] = total;
+}
+
+// MODE_OCA: d_qkv[tok][K|V] = sum over the (up to 4) overlapping windows of their per-window dK/dV rows.
+__global__ void oca_kv_gather_kernel(const __nv_bfloat16* __restrict__ dkv_win, __nv_bfloat16* __restrict__ dqkv,
+                                     int ld_qkv, int B, int H, int W, int heads) {
+  const long long total = (long long)B * H * W * heads * 2 * 4;
+  const int nwy = H >> 4, nwx = W >> 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ch = int(i & 3);
+    long long r = i >> 2;
+    const int h = int(r % heads); r /= heads;
+    const int m = int(r & 1); r >>= 1;
+    const long long tok = r;
+    const int x = int(tok % W), y = int((tok / W) % H), b = int(tok / ((long long)W * H));
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int wy_hi = min((y + 4) >> 4, nwy - 1), wx_hi = min((x + 4) >> 4, nwx - 1);
+    for (int wy = wy_hi; wy >= 0 && wy * 16 + 20 > y; --wy)
+      for (int wx = wx_hi; wx >= 0 && wx * 16 + 20 > x; --wx) {
+        const int ky = y - wy * 16 + 4, kx = x - wx * 16 + 4;
+        const int slot = (ky >> 1) * 64 + (ky & 1) * 32 + (kx >> 4) * 16 + (kx & 15);
+        const size_t win = ((size_t)b * nwy + wy) * nwx + wx;
+        const uint4 v = *reinterpret_cast<const uint4*>(dkv_win + (((win * heads + h) * 2 + m) * 768 + slot) * 32 + ch * 8);
+        const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { acc[2 * e] += bf16_lo(wv[e]); acc[2 * e + 1] += bf16_hi(wv[e]); }
+      }
+    *reinterpret_cast<uint4*>(dqkv + tok * ld_qkv + (1 + m) * heads * 32 + h * 32 + ch * 8) =
+        make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]), pack_bf16(acc[6], acc[7]));
+  }
+}
+
+}  // namespace srk

@@ -146,12 +146,14 @@ static __global__ void unpack_block_grads_kernel(BlockDims d, UnpackSrc s, Block
     } else if ((i -= n_fc2_w + n_fc2_b) < n_ln) {
       const int which = i / C, c = i % C;  // 0: norm1_w, 1: norm1_b, 2: norm2_w, 3: norm2_b
       const float* part = (which < 2) ? s.ln1_part : s.ln2_part;
+      if (part == nullptr) continue;  // LayerNorm-1 backward done by the caller (HAB)
       float acc = 0.f;
       for (int k = 0; k < s.n_ln_part; ++k) acc += part[(size_t(k) * 2 + (which & 1)) * d.Cp + c];
       v = acc;
       dst = (which == 0 ? g.norm1_w : which == 1 ? g.norm1_b : which == 2 ? g.norm2_w : g.norm2_b) + c;
     } else {
       i -= n_ln;
+      if (s.rpb_part == nullptr) continue;  // table gradient written by the attention core's own finish kernel
       const int t = i / d.heads, h = i % d.heads;  // reference layout [table_rows, heads]
       float acc = 0.f;
       for (int k = 0; k < s.n_rpb_part; ++k) acc += s.rpb_part[(size_t(k) * d.heads + h) * s.table_rows + t];

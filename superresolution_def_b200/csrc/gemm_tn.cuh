@@ -89,14 +89,6 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
-  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
 // byte offset of 16-byte chunk `ch` (0..7) of row `r` inside a 128B-swizzled [rows x 128 B] box
 __device__ __forceinline__ uint32_t swz(int r, int ch) { return uint32_t(r) * 128u + (uint32_t(ch ^ (r & 7)) << 4); }
 

@@ -81,3 +81,19 @@ def test_hab_and_ocab_c180_ws16_match_reference():
         assert rel_l2(y2, y) < 1e-5 and rel_l2(x2.grad, x.grad) < 1e-4, kind
         for n, p in blk.named_parameters():
             assert rel_l2(sd[n].grad, p.grad) < 2e-4, (kind, n)
+
+
+def test_hat_module_schema_matches_reference():
+    from tools import ref_shim
+    m = ref_shim.hat_module()
+    from superresolution_def_b200.hat_arch import HAT
+    kw = dict(img_size=128, in_chans=1, embed_dim=180, depths=(6,) * 2, num_heads=(6,) * 2, window_size=16, upscale=4,
+              upsampler="pixelshuffle")
+    ref, mine = m.HAT(**kw), HAT(**kw)
+    a, b = ref.state_dict(), mine.state_dict()
+    assert list(a.keys()) == list(b.keys())
+    assert all(a[k].shape == b[k].shape and a[k].dtype == b[k].dtype for k in a)
+    assert [n for n, _ in ref.named_parameters()] == [n for n, _ in mine.named_parameters()]
+    mine.load_state_dict(a, strict=True)
+    assert all(torch.equal(a[k], b[k]) for k in a if "index" in k)
+    assert torch.equal(ref.calculate_mask((64, 48)), mine.calculate_mask((64, 48)))

@@ -154,6 +154,14 @@ def roofline_probe(batch: int, peaks):
             "tflops_of_kernel": 2.0 * M * N * K / (ms * 1e-3) / 1e12}
 
 
+def _dbg(msg):
+    if os.environ.get("SRK_BENCH_DEBUG"):
+        print(f"[bench rank {os.environ.get('RANK', '0')} +{time.perf_counter() - _T0:.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
+_T0 = time.perf_counter()
+
+
 def run_ours(args):
     import torch.distributed as dist
     from superresolution_def_b200 import _capi as capi
@@ -170,6 +178,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
+    _dbg("process group ready")
     B = args.batch
     torch.manual_seed(0)
     net = SwinIR(**MODEL_KW).to(dev)
@@ -177,7 +186,10 @@ def run_ours(args):
     if world > 1:
         for p in net.parameters():
             dist.broadcast(p.data, 0)
-    reducer = BucketedGradReducer(swinir_grad_groups(net), world)
+    # N > 1: flat fp32 gradient buckets + NCCL all-reduce (overlapped with backward from hooks when run eagerly; issued
+    # between the two graph replays otherwise, so no NCCL call sits inside a stream capture).  N == 1: no exchange,
+    # gradients are handed to the optimizer as produced.
+    reducer = BucketedGradReducer(swinir_grad_groups(net), world, overlap=not args.graph) if world > 1 else None
     opt = torch.optim.AdamW(net.parameters(), lr=1e-4, betas=(0.9, 0.99), fused=True, capturable=args.graph)
     nsets = 4
     lr_h, hr_h = synthetic_pairs(min(B, 4), seed=1234 + rank)
@@ -193,23 +205,42 @@ def run_ours(args):
         host.append((l.contiguous().pin_memory(), h.contiguous().pin_memory()))
     dev_sets = [(l.to(dev), h.to(dev)) for l, h in host]
 
-    def step(lr, hr):
-        reducer.zero_grad()
+    def fwd_bwd(lr, hr):
+        if reducer is not None:
+            reducer.zero_grad()
+        else:
+            opt.zero_grad(set_to_none=True)
         sr = net(lr)
         loss = torch.nn.functional.l1_loss(sr.float(), hr)
         loss.backward()
-        reducer.finish()
+        return loss
+
+    def step(lr, hr):
+        loss = fwd_bwd(lr, hr)
+        if reducer is not None:
+            reducer.finish()
         opt.step()
         return loss
 
+    _dbg("model + data ready")
     if args.graph:
         from superresolution_def_b200.graphs import GraphedStep
         static_lr, static_hr = dev_sets[0][0].clone(), dev_sets[0][1].clone()
-        eager_step = step
         l_before = capi.launch_count()
-        graphed = GraphedStep(eager_step, (static_lr, static_hr), warmup=2)
-        launches_per_step = (capi.launch_count() - l_before) // 3  # 2 warm-up runs + 1 capture run
-        step = graphed  # replaying the graph re-issues exactly the captured launches
+        if reducer is None:
+            graphed = GraphedStep(step, (static_lr, static_hr), warmup=2)
+            launches_per_step = (capi.launch_count() - l_before) // 3  # 2 warm-up runs + 1 capture run
+            step = graphed  # replaying the graph re-issues exactly the captured launches
+        else:
+            g_fb = GraphedStep(fwd_bwd, (static_lr, static_hr), warmup=2)
+            launches_per_step = (capi.launch_count() - l_before) // 3
+            g_opt = GraphedStep(lambda: opt.step(), (), warmup=2)
+
+            def step(lr, hr):  # graph(fwd+bwd) -> NCCL all-reduce of the buckets -> graph(AdamW)
+                loss = g_fb(lr, hr)
+                reducer.reduce_all()
+                g_opt()
+                return loss
 
     def timed(nsteps, e2e):
         if world > 1:
@@ -238,7 +269,9 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item(), (last if e2e else last.item())
 
+    _dbg("graph captured" if args.graph else "eager mode")
     timed(args.warmup, False)
+    _dbg("warm-up done")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -246,8 +279,10 @@ def run_ours(args):
     ms, loss_v = timed(args.steps, False)
     launches = (capi.launch_count() - l0) if not args.graph else launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
+    _dbg("timed region done")
     timed(1, True)
     ms_e2e, _ = timed(args.steps, True)
+    _dbg("e2e region done")
     mem_gb = torch.cuda.max_memory_allocated() / 2 ** 30
 
     value = world * B * args.steps / (ms * 1e-3)
@@ -259,7 +294,7 @@ def run_ours(args):
             "config": {"workload": "SwinIR x4 training step (fwd + L1 + bwd + AdamW), bf16, batch 16/GPU, 128^2->512^2 "
                                    "(BASELINE configs[1])", "global_batch": world * B, "parallelism": f"dp{world}",
                        "l2": "activations saved per step (~60 GB) exceed the 126 MB L2; 4 input batches rotated",
-                       "grad_allreduce_mb": reducer.nbytes / 2 ** 20 if world > 1 else 0,
+                       "grad_allreduce_mb": reducer.nbytes / 2 ** 20 if reducer is not None else 0,
                        "launch": "whole step replayed as one CUDA graph" if args.graph else "eager"},
             "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": B * (128 * 128 + 512 * 512) * 4,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},

@@ -164,6 +164,8 @@ long long srk_layernorm_bwd_ws_floats(int Cp);
 #define SRK_CEPI_MASK_LRELU 3 /* y = conv * (r > 0 ? 1 : slope)   (LeakyReLU backward)   */
 #define SRK_CEPI_BIAS_GELU 4  /* y = gelu(conv + bias), y2 = gelu'(conv + bias)          */
 #define SRK_CEPI_MUL 5        /* y = conv * r                     (GELU backward)        */
+#define SRK_CEPI_OUT1 6       /* Cout_p == 16, one real output channel: y is fp32 [B,H,W] = conv[:,0] + bias[0]
+                                 (conv_last, architecture_swin.py:230): tcgen05 N = 16 instead of a CUDA-core pass */
 
 /* w [Cout,Cin,3,3] fp32 -> wf [Cout_p, 9*Cin_p] bf16 (forward operand), wt [Cin_p, 9*Cout_p] bf16 (flipped /
  * transposed operand of the input gradient, may be NULL), bias_packed [Cout_p] fp32 (may be NULL).

@@ -271,7 +271,7 @@ def layernorm_bwd(dy, x, stats, gamma, dres, dx, dgamma, dbeta, C):
 # ---------------------------------------------------------------------------------------------------
 # Convolution API (include/srk.h, third part)
 # ---------------------------------------------------------------------------------------------------
-CEPI_BIAS, CEPI_BIAS_LRELU, CEPI_BIAS_RES, CEPI_MASK_LRELU, CEPI_BIAS_GELU, CEPI_MUL = range(6)
+CEPI_BIAS, CEPI_BIAS_LRELU, CEPI_BIAS_RES, CEPI_MASK_LRELU, CEPI_BIAS_GELU, CEPI_MUL, CEPI_OUT1 = range(7)
 _conv_prep = _sig("srk_conv3x3_prep_weights", [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                                c_void_p, c_void_p, c_void_p])
 _conv_igemm = _sig("srk_conv3x3_igemm", [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p,

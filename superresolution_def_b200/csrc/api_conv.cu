@@ -66,7 +66,7 @@ int conv_wgrad_splits(int B, int H, int W, int co_tiles) {
 
 extern "C" int srk_conv3x3_prep_weights(const float* w, const float* bias, int Cout, int Cin, int Cout_p, int Cin_p,
                                         int ps, void* wf, void* wt, float* bias_packed, void* stream_) {
-  if (Cout_p % 64 || Cin_p % 64 || Cout > Cout_p || Cin > Cin_p) return fail(SRK_ERR_ARG, "conv prep: bad padding");
+  if ((Cout_p % 64 && Cout_p != 16) || Cin_p % 64 || Cout > Cout_p || Cin > Cin_p) return fail(SRK_ERR_ARG, "conv prep: bad padding");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   conv_prep_weights_kernel<<<num_sms() * 2, 256, 0, stream>>>(w, bias, static_cast<__nv_bfloat16*>(wf),
                                                               static_cast<__nv_bfloat16*>(wt), bias_packed, Cout, Cin,
@@ -81,13 +81,20 @@ extern "C" int srk_conv3x3_igemm(int epi, int B, int H, int W, int Cin_p, int Co
                                  void* y2, const void* r, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (H % CONV_TH || W % CONV_TW) return fail(SRK_ERR_UNSUPPORTED, "conv3x3: H % 8 == 0 and W % 16 == 0 required");
-  if (Cin_p % 64 || Cout_p % 64 || Cout_p > 256 || Cin_p > 256) return fail(SRK_ERR_UNSUPPORTED, "conv3x3: channels must be multiples of 64, <= 256");
+  const bool out1 = (epi == CEPI_OUT1);
+  if (Cin_p % 64 || (Cout_p % 64 && !(out1 && Cout_p == 16)) || Cout_p > 256 || Cin_p > 256)
+    return fail(SRK_ERR_UNSUPPORTED, "conv3x3: channels must be multiples of 64, <= 256");
   if (!x || !wk || !y) return fail(SRK_ERR_ARG, "conv3x3: null pointer");
+  if (out1 && (x_ps || y_ps || !bias)) return fail(SRK_ERR_ARG, "conv3x3: OUT1 needs plain layouts and a bias");
   ConvMaps maps;
   memset(&maps, 0, sizeof(maps));
   int rc;
   if ((rc = make_act_maps(maps.a, x, B, H, W, Cin_p, x_ps, CONV_TW, CONV_TH))) return rc;
-  if ((rc = make_act_maps(maps.c, y, B, H, W, Cout_p, y_ps, CONV_TW, CONV_TH))) return rc;
+  if (out1) {
+    for (int i = 0; i < 4; ++i) maps.c[i] = maps.a[0];  // unused: the fp32 output is written with plain stores
+  } else if ((rc = make_act_maps(maps.c, y, B, H, W, Cout_p, y_ps, CONV_TW, CONV_TH))) {
+    return rc;
+  }
   for (int i = 1; i < 4; ++i) {
     if (!x_ps) maps.a[i] = maps.a[0];
     if (!y_ps) maps.c[i] = maps.c[0];
@@ -101,6 +108,7 @@ extern "C" int srk_conv3x3_igemm(int epi, int B, int H, int W, int Cin_p, int Co
   ConvArgs a{};
   a.B = B; a.H = H; a.W = W; a.Cin_p = Cin_p; a.Cout_p = Cout_p; a.n_real = n_real; a.bias = bias; a.slope = slope;
   a.a_split = x_ps; a.c_split = y_ps;
+  a.y32 = out1 ? static_cast<float*>(y) : nullptr;
   const bool need_r = (epi == CEPI_BIAS_RES || epi == CEPI_MASK_LRELU || epi == CEPI_MUL);
   if (need_r && (!r || y_ps)) return fail(SRK_ERR_ARG, "conv3x3: epilogue needs an aux tensor (and a plain output)");
   if (epi == CEPI_BIAS_GELU && (!y2 || y_ps)) return fail(SRK_ERR_ARG, "conv3x3: GELU epilogue needs y2");
@@ -111,6 +119,7 @@ extern "C" int srk_conv3x3_igemm(int epi, int B, int H, int W, int Cin_p, int Co
   SRK_CCASE(64, CEPI_MASK_LRELU) SRK_CCASE(192, CEPI_MASK_LRELU)
   SRK_CCASE(64, CEPI_BIAS_GELU) SRK_CCASE(128, CEPI_BIAS_GELU)
   SRK_CCASE(64, CEPI_MUL) SRK_CCASE(128, CEPI_MUL)
+  SRK_CCASE(16, CEPI_OUT1)
 #undef SRK_CCASE
   return fail(SRK_ERR_UNSUPPORTED, "conv3x3: no kernel instance for (Cout_p, epilogue)");
 }

@@ -27,6 +27,7 @@ enum ConvEpilogue : int {
   CEPI_MASK_LRELU = 3, // y = acc * (R > 0 ? 1 : slope)  (backward through LeakyReLU; R = forward output)
   CEPI_BIAS_GELU = 4,  // y = gelu(acc + bias), y2 = gelu'(acc + bias)   (HAT CAB, hat_arch.py:69)
   CEPI_MUL = 5,        // y = acc * R                    (backward through GELU; R = gelu')
+  CEPI_OUT1 = 6,       // BN = 16, one real output channel: y32[pixel] = acc[:,0] + bias[0]   (conv_last, fp32 out)
 };
 
 struct ConvArgs {
@@ -37,6 +38,7 @@ struct ConvArgs {
   float slope;
   int a_split;        // 1: A k-chunk kc is loaded through tmA[kc] at channel 0 (pixel-shuffled input gradient)
   int c_split;        // 1: output box j is stored through tmC[j] at channel 0 (pixel-shuffled output)
+  float* y32;         // CEPI_OUT1: fp32 output [B,H,W]
 };
 
 struct ConvMaps {
@@ -50,7 +52,7 @@ struct ConvMaps {
 template <int BN, int EPI>
 struct ConvCfg {
   static constexpr int kStageBytes = GEMM_BM * 128 + BN * 128;
-  static constexpr int kBoxes = BN / 64;
+  static constexpr int kBoxes = BN / 64;  // 0 for the BN = 16 single-channel variant
   static constexpr bool kAux = (EPI == CEPI_BIAS_RES || EPI == CEPI_MASK_LRELU || EPI == CEPI_MUL);
   static constexpr int kOutPerBox = (EPI == CEPI_BIAS_GELU) ? 2 : 1;
   static constexpr int kEpiBytes = (kAux ? 2 * BOX_BYTES : 0) + 2 * kOutPerBox * BOX_BYTES;
@@ -59,6 +61,7 @@ struct ConvCfg {
   static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
   static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 512 + 1024;
   static_assert(kStages >= 2, "conv pipeline needs two stages");
+  static_assert(BN % 64 == 0 || BN == 16, "BN: multiple of 64, or 16 for the single-channel variant");
 };
 
 template <int BN, int EPI>
@@ -184,6 +187,21 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
       const int next_tile = tile + gridDim.x;
       mbar_wait(tfull_bar(acc), (it >> 1) & 1u);
       tc_fence_after();
+      if constexpr (EPI == CEPI_OUT1) {
+        // one real output channel: column 0 of the accumulator, row = pixel of the 16 x 8 spatial tile
+        float v = 0.f;
+        if (half == 0) {
+          v = __uint_as_float(tmem_ld_x1(taddr));
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (half == 0) {
+          const int py = y0 + (row >> 4), px = x0 + (row & 15);
+          args.y32[((size_t)b * args.H + py) * args.W + px] = v + s_bias[0];
+        }
+      }
 #pragma unroll 1
       for (int j = 0; j < NBOX; ++j) {
         const uint32_t ring = box_counter & 1u;
@@ -250,7 +268,7 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
           if constexpr (EPI == CEPI_BIAS_GELU) {
             float a[8], g[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) gelu_pair(round_bf16(v[e]), a[e], g[e]);
+            for (int e = 0; e < 8; ++e) gelu_pair(v[e], a[e], g[e]);
             sts128(out0 + off, make_uint4(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]), pack_bf16(a[4], a[5]),
                                           pack_bf16(a[6], a[7])));
             sts128(out0 + BOX_BYTES + off, make_uint4(pack_bf16(g[0], g[1]), pack_bf16(g[2], g[3]),

@@ -82,32 +82,41 @@ static __global__ void colsum_finish_kernel(const float* __restrict__ partial, i
   for (int k = 0; k < nparts; ++k) acc += partial[size_t(k) * C + i];
   out[i] = acc;
 }
-// shuffled-gradient bias sum: dYs [B,2H,2W,Cg]; out[c*4 + i*2 + j] = sum over pixels with (Y&1,X&1) == (i,j)
+// shuffled-gradient bias sum: dYs [B,2H,2W,Cg]; out[c*4 + i*2 + j] = sum over pixels with (Y&1,X&1) == (i,j).
+// 8 lanes x 16 B cover the Cg = 64 channels of a pixel; a thread always visits pixels of ONE sub-pixel lattice
+// (sub = pixel lane & 3), so it needs 8 accumulators only, and 4 independent 16-byte loads are kept in flight.
 static __global__ void colsum_ps_kernel(const __nv_bfloat16* __restrict__ dys, int B, int H2, int W2, int Cg,
                                  float* __restrict__ partial /*[grid][4*Cg]*/) {
   extern __shared__ float s_cs[];  // [4*Cg]
   for (int i = threadIdx.x; i < 4 * Cg; i += blockDim.x) s_cs[i] = 0.f;
   __syncthreads();
-  const int pairs = Cg / 2;
-  const int rows_per_block = blockDim.x / pairs;
-  const int cp = threadIdx.x % pairs, rl = threadIdx.x / pairs;
-  float acc[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
-  const long long npix = (long long)B * H2 * W2;
-  if (rl < rows_per_block) {
-    for (long long r = (long long)blockIdx.x * rows_per_block + rl; r < npix; r += (long long)gridDim.x * rows_per_block) {
-      const int X = int(r % W2), Y = int((r / W2) % H2);
-      const int sub = (Y & 1) * 2 + (X & 1);
-      const uint32_t v = *reinterpret_cast<const uint32_t*>(dys + r * Cg + cp * 2);
+  const int groups = Cg / 8;                       // 16-byte channel groups per pixel
+  const int cg = threadIdx.x % groups, pl = threadIdx.x / groups;
+  const int lanes = blockDim.x / groups;           // pixel lanes per block (multiple of 4)
+  const int sub = pl & 3, si = sub >> 1, sj = sub & 1;
+  const int Hq = H2 >> 1, Wq = W2 >> 1;
+  const long long nq = (long long)B * Hq * Wq;     // quarter-resolution positions
+  const long long qstride = (long long)gridDim.x * (lanes >> 2);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  auto load = [&](long long q) -> uint4 {
+    const int qx = int(q % Wq), qy = int((q / Wq) % Hq);
+    const long long b = q / ((long long)Wq * Hq);
+    const long long pix = (b * H2 + (2 * qy + si)) * W2 + (2 * qx + sj);
+    return *reinterpret_cast<const uint4*>(dys + pix * Cg + cg * 8);
+  };
+  auto add = [&](const uint4& v) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int s = 0; s < 4; ++s)
-        if (s == sub) { acc[s][0] += bf16_lo(v); acc[s][1] += bf16_hi(v); }
-    }
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-      atomicAdd(&s_cs[(cp * 2) * 4 + s], acc[s][0]);
-      atomicAdd(&s_cs[(cp * 2 + 1) * 4 + s], acc[s][1]);
-    }
+    for (int e = 0; e < 4; ++e) { acc[2 * e] += bf16_lo(w[e]); acc[2 * e + 1] += bf16_hi(w[e]); }
+  };
+  long long q = (long long)blockIdx.x * (lanes >> 2) + (pl >> 2);
+  for (; q + 3 * qstride < nq; q += 4 * qstride) {
+    const uint4 v0 = load(q), v1 = load(q + qstride), v2 = load(q + 2 * qstride), v3 = load(q + 3 * qstride);
+    add(v0); add(v1); add(v2); add(v3);
   }
+  for (; q < nq; q += qstride) add(load(q));
+#pragma unroll
+  for (int e = 0; e < 8; ++e) atomicAdd(&s_cs[(cg * 8 + e) * 4 + sub], acc[e]);
   __syncthreads();
   for (int i = threadIdx.x; i < 4 * Cg; i += blockDim.x) partial[size_t(blockIdx.x) * 4 * Cg + i] = s_cs[i];
 }
@@ -244,11 +253,11 @@ static __global__ void conv_out1_fwd_kernel(const __nv_bfloat16* __restrict__ x,
   }
 }
 
-// dX[p][c] = sum_tap dY[p - off(tap)] * w[c][tap]   (dY fp32 [B,H,W], dX NHWC bf16)
+// dX[p][c] = sum_tap dY[p - off(tap)] * w[c][tap]   (dY fp32 [B,H,W], dX NHWC bf16); HBM-write bound.
 template <int C>
 static __global__ void conv_out1_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
                                        __nv_bfloat16* __restrict__ dx, int B, int H, int W) {
-  __shared__ float s_w[9][C];
+  __shared__ __align__(16) float s_w[9][C];
   for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) s_w[i / C][i % C] = w[(i % C) * 9 + i / C];
   __syncthreads();
   constexpr int G = C / 8;
@@ -257,16 +266,20 @@ static __global__ void conv_out1_dgrad_kernel(const float* __restrict__ dy, cons
     const int g = int(idx % G);
     const long long p = idx / G;
     const int xx = int(p % W), yy = int((p / W) % H);
-    float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float d[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       // output pixel q = p - off(tap) received x[p] through tap t
       const int sy = yy - (t / 3 - 1), sx = xx - (t % 3 - 1);
-      if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
-        const float d = dy[p - (long long)(t / 3 - 1) * W - (t % 3 - 1)];
+      d[t] = (sy >= 0 && sy < H && sx >= 0 && sx < W) ? __ldg(dy + p - (long long)(t / 3 - 1) * W - (t % 3 - 1)) : 0.f;
+    }
+    float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = fmaf(d, s_w[t][g * 8 + e], o[e]);
-      }
+    for (int t = 0; t < 9; ++t) {
+      const float4 w0 = *reinterpret_cast<const float4*>(&s_w[t][g * 8]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&s_w[t][g * 8 + 4]);
+      o[0] = fmaf(d[t], w0.x, o[0]); o[1] = fmaf(d[t], w0.y, o[1]); o[2] = fmaf(d[t], w0.z, o[2]); o[3] = fmaf(d[t], w0.w, o[3]);
+      o[4] = fmaf(d[t], w1.x, o[4]); o[5] = fmaf(d[t], w1.y, o[5]); o[6] = fmaf(d[t], w1.z, o[6]); o[7] = fmaf(d[t], w1.w, o[7]);
     }
     *reinterpret_cast<uint4*>(dx + p * C + g * 8) =
         make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
@@ -289,20 +302,25 @@ static __global__ void conv_out1_wgrad_kernel(const float* __restrict__ dy, cons
     for (int t = 0; t < 9; ++t) acc[e][t] = 0.f;
   float accb = 0.f;
   const long long npix = (long long)B * H * W;
-  for (long long p = (long long)blockIdx.x * ppb + pl; p < npix; p += (long long)gridDim.x * ppb) {
+  const long long pstride = (long long)gridDim.x * ppb;
+  long long p = (long long)blockIdx.x * ppb + pl;
+  uint4 v_next = make_uint4(0u, 0u, 0u, 0u);
+  if (p < npix) v_next = *reinterpret_cast<const uint4*>(x + p * C + g * 8);
+  for (; p < npix; p += pstride) {
     // gather form: input pixel p contributes to output pixel q = p - off(tap) through tap t
+    const uint4 v = v_next;
+    if (p + pstride < npix) v_next = *reinterpret_cast<const uint4*>(x + (p + pstride) * C + g * 8);  // prefetch
     const int xx = int(p % W), yy = int((p / W) % H);
-    const uint4 v = *reinterpret_cast<const uint4*>(x + p * C + g * 8);
     const uint32_t vw[4] = {v.x, v.y, v.z, v.w};
     float xv[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) xv[e] = (e & 1) ? bf16_hi(vw[e >> 1]) : bf16_lo(vw[e >> 1]);
-    if (g == 0) accb += dy[p];
+    if (g == 0) accb += __ldg(dy + p);
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       const int sy = yy - (t / 3 - 1), sx = xx - (t % 3 - 1);
       if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
-        const float d = dy[p - (long long)(t / 3 - 1) * W - (t % 3 - 1)];
+        const float d = __ldg(dy + p - (long long)(t / 3 - 1) * W - (t % 3 - 1));
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e][t] = fmaf(d, xv[e], acc[e][t]);
       }

@@ -182,6 +182,13 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 
+// 32 lanes x 1 fp32 column: thread i of the warp receives lane (base+i), column c.
+__device__ __forceinline__ uint32_t tmem_ld_x1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+  return r;
+}
+
 // ---------------------------------------------------------------- UMMA descriptors
 // Shared-memory matrix descriptor (cf. the sm_100 descriptor layout: start>>4 in [0,14),
 // LBO>>4 in [16,30), SBO>>4 in [32,46), version=1 at [46,48), layout type at [61,64)).

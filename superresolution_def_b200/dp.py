@@ -13,8 +13,11 @@ import torch.distributed as dist
 
 
 class BucketedGradReducer:
-    def __init__(self, groups: list[list[torch.nn.Parameter]], world_size: int):
-        """groups: parameter groups in the order their gradients become ready during backward."""
+    def __init__(self, groups: list[list[torch.nn.Parameter]], world_size: int, overlap: bool = True):
+        """groups: parameter groups in the order their gradients become ready during backward.
+        overlap=True: each bucket's all-reduce is launched from a post-accumulate hook while backward continues.
+        overlap=False: no hooks; call reduce_all() after backward (used when forward+backward is replayed as a CUDA
+        graph, so that no NCCL call is ever issued inside a stream capture)."""
         self.world = world_size
         self.buckets = []
         self.handles = []
@@ -32,7 +35,7 @@ class BucketedGradReducer:
             bi = len(self.buckets)
             self.buckets.append(flat)
             self._pending.append(len(params))
-            if world_size > 1:
+            if world_size > 1 and overlap:
                 for p in params:
                     p.register_post_accumulate_grad_hook(self._make_hook(bi))
         self._count = list(self._pending)
@@ -48,6 +51,12 @@ class BucketedGradReducer:
         for b in self.buckets:
             b.zero_()
         self._count = list(self._pending)
+
+    def reduce_all(self):
+        """Average every bucket across ranks on the current stream (non-overlapped mode)."""
+        if self.world > 1:
+            for b in self.buckets:
+                dist.all_reduce(b, op=dist.ReduceOp.AVG)
 
     def finish(self):
         """Block the current stream on every outstanding bucket exchange (call after backward())."""

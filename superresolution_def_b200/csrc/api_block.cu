@@ -44,7 +44,7 @@ struct WsLayout {  // offsets (floats) into SrkBlockScratch.wg_ws
 };
 
 int attn_bwd_gx(int nwin, int heads) {
-  int gx = num_sms() * 3 / heads;
+  int gx = num_sms() * 4 / heads;
   if (gx > nwin) gx = nwin;
   return gx < 1 ? 1 : gx;
 }
@@ -468,7 +468,7 @@ extern "C" int srk_win_attn_fwd(const SrkGeom* g, int heads, const void* qkv, in
   return launch_attn_fwd(g, heads, qkv, ld_qkv, rpb_table, out, ld_out, ones_col, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" long long srk_win_attn_bwd_ws_floats(int heads) { return (long long)num_sms() * 3 * 225 + 225LL * heads; }
+extern "C" long long srk_win_attn_bwd_ws_floats(int heads) { return (long long)num_sms() * 4 * 225 + 225LL * heads; }
 
 extern "C" int srk_win_attn_bwd(const SrkGeom* g, int heads, const void* qkv, int ld_qkv, const float* rpb_table,
                                 const void* d_out, int ld_out, void* d_qkv, float* dbias_ws, float* d_rpb_table,

@@ -20,7 +20,7 @@ static int launch_gemm_tn(const GemmArgs& a, const CUtensorMap& tA, const CUtens
   }
   const int tiles = (a.M / GEMM_BM) * (a.N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tn_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(tA, tB, tC, tC2, tX1, tX2, a);
+  gemm_tn_kernel<BN, EPI><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(tA, tB, tC, tC2, tX1, tX2, a);
   SRK_LAUNCHED(1);
   SRK_CUDA_OK(cudaGetLastError());
   return SRK_OK;

@@ -98,50 +98,78 @@ __device__ __forceinline__ long long k_token(const Attn16Args& a, const WinPos& 
   return ((long long)p.b * a.H + y) * a.W + x;
 }
 
-// region id of a shifted-frame coordinate (HAT.calculate_mask slices: [0,-ws), [-ws,-shift), [-shift, end))
-__device__ __forceinline__ int mask_region(int c, int size, int shift) {
-  return (c < size - 16) ? 0 : ((c < size - shift) ? 1 : 2);
-}
-
-// bias (+mask) for query (qy,qx), key n-tile `nt` of key tile `kt`, columns 2t+e: returns additive fp32 term
+// Relative-position bias table in shared memory, laid out so that the index of element (query row qy, column
+// qx = g + 8*rowsel; key n-tile nt, column 2t + e of key tile kt) is  base(qy, kt, g, t) + CONST(nt, e, rowsel):
+// one LDS with an immediate offset per logit, no per-element index arithmetic.
+//   MODE_SELF: index = (qy-ky+15)*31 + (qx-kx+15)                                  (reference :882-894)
+//   MODE_OCA : index = (ky-qy-7)*39 + (kx-qx-7) + 880; the reference's negative indices (which PyTorch wraps around
+//              the table end, :896-919) are materialised by loading the table rotated by 880 entries.
 template <int MODE>
-struct BiasCtx {
-  const float* s_bias;
-  const uint8_t* s_rid;  // MODE_SELF: region ids of the 256 window tokens (only when masked)
-  bool masked;
-};
-template <int MODE>
-__device__ __forceinline__ float bias_term(const BiasCtx<MODE>& c, int qy, int qx, int kt, int nt, int col) {
-  if (MODE == MODE_SELF) {
-    const int ky = kt * 4 + (nt >> 1), kx = (nt & 1) * 8 + col;
-    float v = c.s_bias[(qy - ky + 15) * 31 + (qx - kx + 15)];
-    if (c.masked && c.s_rid[qy * 16 + qx] != c.s_rid[ky * 16 + kx]) v += -100.0f;
-    return v;
-  } else {
-    const int ky = kt * 2 + (nt >> 2), kx = ((nt >> 1) & 1) * 16 + (nt & 1) * 8 + col;
-    if (kx >= 24) return -INFINITY;
-    int idx = (ky - qy - 7) * 39 + (kx - qx - 7);   // reference offset ws - wse + 1 = -7: negative rows wrap
-    if (idx < 0) idx += 1521;
-    return c.s_bias[idx];
+__device__ __forceinline__ void load_bias_table(float* s_bias, const float* table, int heads, int h, int nthreads) {
+  constexpr int TBL = A16<MODE>::TBL;
+  for (int i = threadIdx.x; i < TBL; i += nthreads) {
+    int src = i;
+    if (MODE == MODE_OCA) { src = i - 880; if (src < 0) src += TBL; }
+    s_bias[i] = table[src * heads + h];
   }
 }
-
-// S[16 x 64] logits of this warp's 16 query rows (row-group qy) against key tile kt
 template <int MODE>
-__device__ __forceinline__ void qk_tile(const uint32_t (&aq)[2][4], uint32_t k_tile, const BiasCtx<MODE>& bc, int qy,
-                                        int kt, int lane, float (&s)[8][4]) {
-  const int g = lane >> 2, t = lane & 3;
+__device__ __forceinline__ int bias_base(int qy, int kt, int g, int t) {
+  if (MODE == MODE_SELF) return (qy - kt * 4 + 15) * 31 + (g - 2 * t + 15);
+  return (kt * 2 - qy - 7) * 39 + (2 * t - g - 7) + 880;
+}
+template <int MODE>
+__device__ __forceinline__ constexpr int bias_const(int nt, int e, int rowsel) {
+  return (MODE == MODE_SELF) ? (-(nt >> 1) * 31 - (nt & 1) * 8 - e + 8 * rowsel)
+                             : ((nt >> 2) * 39 + ((nt >> 1) & 1) * 16 + (nt & 1) * 8 + e - 8 * rowsel);
+}
+// MODE_OCA: n-tiles 3 and 7 of every key tile are the padding half of the second 16-wide band (kx >= 24)
+template <int MODE>
+__device__ __forceinline__ constexpr bool nt_valid(int nt) { return MODE == MODE_SELF || (nt & 3) != 3; }
+
+// Shift mask of HAT.calculate_mask (:921-940) for ws = 16, shift = 8, expressed on fragments.  In the shifted frame
+// the regions split every window of the last window row / column at token 8, so query (qy, qx) and key (ky, kx) lie
+// in different regions iff  last_y && (qy>=8) != (ky>=8)  or  last_x && (qx>=8) != (kx>=8).  On fragments (qy>=8) is
+// warp-uniform, (ky>=8) is tile-uniform (kt>=2), (qx>=8) is the fragment row half and (kx>=8) the n-tile parity.
+struct MaskCtx {
+  bool any;       // window touches the last window row / column of a shifted block
+  float same;     // additive term where row half == n-tile parity
+  float diff;     // additive term where they differ
+};
+__device__ __forceinline__ MaskCtx mask_ctx(bool last_y, bool last_x, int qy, int kt) {
+  MaskCtx m;
+  const bool ydiff = last_y && ((qy >= 8) != (kt >= 2));
+  m.any = last_y || last_x;
+  m.same = ydiff ? -100.0f : 0.0f;
+  m.diff = (ydiff || last_x) ? -100.0f : 0.0f;
+  return m;
+}
+
+// S[16 x 64] logits of this warp's 16 query rows against key tile kt: Q K^T + bias (+ mask)
+template <int MODE>
+__device__ __forceinline__ void qk_tile(const uint32_t (&aq)[2][4], uint32_t k_tile, const float* bp, const MaskCtx& mk,
+                                        int lane, float (&s)[8][4]) {
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
+    if (!nt_valid<MODE>(nt)) {
+      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = -INFINITY;
+      continue;
+    }
     uint32_t b0, b1, b2, b3;
     ldsm_x4(k_tile + t32_off(nt * 8 + (lane & 7), lane >> 3), b0, b1, b2, b3);
-    s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+    s[nt][0] = bp[bias_const<MODE>(nt, 0, 0)];
+    s[nt][1] = bp[bias_const<MODE>(nt, 1, 0)];
+    s[nt][2] = bp[bias_const<MODE>(nt, 0, 1)];
+    s[nt][3] = bp[bias_const<MODE>(nt, 1, 1)];
     mma_bf16(s[nt], aq[0], b0, b1);
     mma_bf16(s[nt], aq[1], b2, b3);
-    s[nt][0] += bias_term<MODE>(bc, qy, g, kt, nt, 2 * t);
-    s[nt][1] += bias_term<MODE>(bc, qy, g, kt, nt, 2 * t + 1);
-    s[nt][2] += bias_term<MODE>(bc, qy, g + 8, kt, nt, 2 * t);
-    s[nt][3] += bias_term<MODE>(bc, qy, g + 8, kt, nt, 2 * t + 1);
+  }
+  if (MODE == MODE_SELF && mk.any) {
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float m01 = (nt & 1) ? mk.diff : mk.same, m23 = (nt & 1) ? mk.same : mk.diff;
+      s[nt][0] += m01; s[nt][1] += m01; s[nt][2] += m23; s[nt][3] += m23;
+    }
   }
 }
 
@@ -165,18 +193,30 @@ __device__ __forceinline__ void frag_times_tile_acc(const float (&s)[8][4], uint
   }
 }
 
+// Token-row table of one window in shared memory: s_qtok[256] (query tokens == MODE_SELF key tokens), filled once per
+// window so that loads and stores are table look-ups instead of per-transfer coordinate arithmetic.  MODE_OCA key
+// slots are decoded on the fly (a table would cost 3 KB and the second resident CTA of the forward kernel).
+__device__ __forceinline__ void fill_token_table(const Attn16Args& a, const WinPos& p, int* s_qtok, int nthreads) {
+  for (int i = threadIdx.x; i < 256; i += nthreads) s_qtok[i] = int(q_token(a, p, i >> 4, i & 15));
+}
 // cooperative async load of the K and V slot tiles of one window (rows = key slots, zero-filled where absent)
 template <int MODE>
-__device__ __forceinline__ void load_kv(const Attn16Args& a, const WinPos& p, int h, uint32_t sK, uint32_t sV,
-                                        int nthreads) {
+__device__ __forceinline__ void load_kv(const Attn16Args& a, const WinPos& p, const int* s_qtok, int h, uint32_t sK,
+                                        uint32_t sV, int nthreads) {
   constexpr int NS = A16<MODE>::NS;
   const int hw = a.heads * 32;
-  for (int c = threadIdx.x; c < NS * 4; c += nthreads) {
-    const int slot = c >> 2, ch = c & 3;
-    bool sv;
-    const long long tok = k_token<MODE>(a, p, slot, sv);
+  const int ch = threadIdx.x & 3;
+  const __nv_bfloat16* base = a.qkv + hw + h * 32 + ch * 8;
+  for (int slot = threadIdx.x >> 2; slot < NS; slot += nthreads >> 2) {
+    long long tok;
+    if (MODE == MODE_SELF) {
+      tok = s_qtok[slot];
+    } else {
+      bool sv;
+      tok = k_token<MODE>(a, p, slot, sv);
+    }
     const bool ok = tok >= 0;
-    const __nv_bfloat16* src = a.qkv + (ok ? tok : 0) * a.ld_qkv + hw + h * 32 + ch * 8;
+    const __nv_bfloat16* src = base + (ok ? tok : 0) * a.ld_qkv;
     cp_async16_zfill(sK + t32_off(slot, ch), src, ok);
     cp_async16_zfill(sV + t32_off(slot, ch), src + hw, ok);
   }
@@ -193,13 +233,13 @@ __global__ void __launch_bounds__(A16_FWD_THREADS, 2) win_attn16_fwd_kernel(cons
   using G = A16<MODE>;
   extern __shared__ __align__(128) uint8_t smem_dyn[];
   __shared__ float s_bias[G::TBL];
-  __shared__ uint8_t s_rid[256];
+  __shared__ int s_qtok[256];
   const uint32_t sQ = smem_u32(smem_dyn), sK = sQ + 128 * 64, sV = sK + G::NS * 64;
   const int h = blockIdx.y;
   const int nwin = a.B * (a.H >> 4) * (a.W >> 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  for (int i = threadIdx.x; i < G::TBL; i += A16_FWD_THREADS) s_bias[i] = a.bias_table[i * a.heads + h];
+  load_bias_table<MODE>(s_bias, a.bias_table, a.heads, h, A16_FWD_THREADS);
   const bool ones_here = a.ones_col >= h * 32 && a.ones_col < h * 32 + 32;
   const int ones_c = a.ones_col - h * 32;
   constexpr float kLog2e = 1.4426950408889634f;
@@ -207,25 +247,24 @@ __global__ void __launch_bounds__(A16_FWD_THREADS, 2) win_attn16_fwd_kernel(cons
   for (int item = blockIdx.x; item < nwin * 2; item += gridDim.x) {
     const int w = item >> 1, half = item & 1;
     const WinPos p = win_pos(a, w);
-    __syncthreads();  // previous item fully consumed
-    for (int c = threadIdx.x; c < 128 * 4; c += A16_FWD_THREADS) {
-      const int i = c >> 2, ch = c & 3;
-      const long long tok = q_token(a, p, half * 8 + (i >> 4), i & 15);
-      cp_async16(sQ + t32_off(i, ch), a.qkv + tok * a.ld_qkv + h * 32 + ch * 8);
-    }
-    load_kv<MODE>(a, p, h, sK, sV, A16_FWD_THREADS);
-    cp_async_commit();
-    bool masked = false;
-    if (MODE == MODE_SELF && a.shift > 0) {
-      masked = (p.wy == (a.H >> 4) - 1) || (p.wx == (a.W >> 4) - 1);
-      if (masked) {
-        const int i = threadIdx.x;  // 256 threads == 256 window tokens
-        s_rid[i] = uint8_t(mask_region(p.wy * 16 + (i >> 4), a.H, a.shift) * 3 + mask_region(p.wx * 16 + (i & 15), a.W, a.shift));
+    __syncthreads();  // previous item fully consumed (tiles and token tables)
+    fill_token_table(a, p, s_qtok, A16_FWD_THREADS);
+    __syncthreads();
+    {
+      const int ch = threadIdx.x & 3;
+      const __nv_bfloat16* base = a.qkv + h * 32 + ch * 8;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int i = (threadIdx.x >> 2) + 64 * k;  // 128 query rows of this half window
+        cp_async16(sQ + t32_off(i, ch), base + (long long)s_qtok[half * 128 + i] * a.ld_qkv);
       }
     }
+    load_kv<MODE>(a, p, s_qtok, h, sK, sV, A16_FWD_THREADS);
+    cp_async_commit();
+    const bool shifted = (MODE == MODE_SELF) && a.shift > 0;
+    const bool last_y = shifted && p.wy == (a.H >> 4) - 1, last_x = shifted && p.wx == (a.W >> 4) - 1;
     cp_async_wait<0>();
     __syncthreads();
-    const BiasCtx<MODE> bc{s_bias, s_rid, masked};
     const int r0 = warp * 16, qy = half * 8 + warp;
     uint32_t aq[2][4];
 #pragma unroll
@@ -240,7 +279,7 @@ __global__ void __launch_bounds__(A16_FWD_THREADS, 2) win_attn16_fwd_kernel(cons
 #pragma unroll 1
     for (int kt = 0; kt < G::NKT; ++kt) {
       float s[8][4];
-      qk_tile<MODE>(aq, sK + kt * 64 * 64, bc, qy, kt, lane, s);
+      qk_tile<MODE>(aq, sK + kt * 64 * 64, s_bias + bias_base<MODE>(qy, kt, g, t), mask_ctx(last_y, last_x, qy, kt), lane, s);
       float t0 = -INFINITY, t1 = -INFINITY;
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
@@ -278,8 +317,8 @@ __global__ void __launch_bounds__(A16_FWD_THREADS, 2) win_attn16_fwd_kernel(cons
 #pragma unroll
     for (int n = 0; n < 4; ++n) { o[n][0] *= i0; o[n][1] *= i0; o[n][2] *= i1; o[n][3] *= i1; }
     if (t == 0 && a.lse != nullptr) {
-      a.lse[(long long)h * a.T + q_token(a, p, qy, g)] = m0 + logf(l0);
-      a.lse[(long long)h * a.T + q_token(a, p, qy, g + 8)] = m1 + logf(l1);
+      a.lse[(long long)h * a.T + s_qtok[qy * 16 + g]] = m0 + logf(l0);
+      a.lse[(long long)h * a.T + s_qtok[qy * 16 + g + 8]] = m1 + logf(l1);
     }
     // this warp's Q rows are dead (fragments live in registers): reuse them as the output staging rows
     __syncwarp();
@@ -288,7 +327,7 @@ __global__ void __launch_bounds__(A16_FWD_THREADS, 2) win_attn16_fwd_kernel(cons
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       const int c = lane + 32 * k, i = c >> 2, ch = c & 3;  // 16 rows x 4 chunks
-      const long long tok = q_token(a, p, qy, i);
+      const long long tok = s_qtok[qy * 16 + i];
       uint4 v = lds128(sQ + t32_off(r0 + i, ch));
       if (ones_here && ch == (ones_c >> 3)) {
         const int word = (ones_c & 7) >> 1;
@@ -347,28 +386,28 @@ __device__ __forceinline__ void tileT_times_tile256(uint32_t a_tile, uint32_t b_
 // [b == 15 + kx - qx] (MODE_OCA).  As an MMA: M = b (32 diagonals, two m-tiles), K = (qx, kx) (16 k-steps of 16),
 // N = 8 pairs.  Per key tile there are 64 pairs = 8 n-tiles; warp w takes n-tile w&7 and m-tile w>>3.
 // Pair n of n-tile j: query row qy = 2j + (n>>2), in-tile key row/band index r = n&3 (its 16 slots = columns r*16..).
+// The A operand (the 0/1 Toeplitz selector R) is never materialised: an 8-element row of it is either all-zero or
+// one-hot, so the fragment is fetched by ldmatrix from a 9-row table in shared memory (rows 0..7 = one-hot at that
+// position, row 8 = zeros) with a per-lane row choice  pos = qx + c_lane  clamped to 8.
 template <int MODE>
-__device__ __forceinline__ void diag_mma(uint32_t ds_tile, int warp, int lane, float (&acc)[4]) {
+__device__ __forceinline__ void diag_mma(uint32_t ds_tile, uint32_t onehot_tbl, int warp, int lane, float (&acc)[4]) {
   const int j = warp & 7, mt = warp >> 3;
-  const int g = lane >> 2, t = lane & 3;
   acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
-  const int n = lane & 7;                       // ldmatrix row provider: pair index
+  const int n = lane & 7;                       // ldmatrix row provider (B operand): pair index
   const int prow = (2 * j + (n >> 2)) * 16;     // first dS row of that pair's query row-group
   const int pchunk = (n & 3) * 2 + ((lane >> 3) & 1);
-  const int b_lo = mt * 16 + g, b_hi = b_lo + 8;
-#pragma unroll 4
+  // A operand: lane l provides row (l & 7) of 8x8 matrix (l >> 3): matrices 0,1 = rows b, b+8 at k 0..7; 2,3 at k 8..15
+  const int b_row = mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+  const int k0 = (lane >> 4) * 8;
+  const int c_lane = (MODE == MODE_SELF) ? (15 - b_row - k0) : (b_row - 15 - k0);   // one-hot position = qx + c_lane
+#pragma unroll
   for (int qx = 0; qx < 16; ++qx) {
     uint32_t b0, b1;
     asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];"
                  : "=r"(b0), "=r"(b1) : "r"(ds_tile + t64_off(prow + qx, pchunk)));
-    // A fragment of R for this k-step: element (row b, k = kx) is 1.0 iff kx == kx_of(b)
-    const int k_lo = (MODE == MODE_SELF) ? (qx + 15 - b_lo) : (b_lo - 15 + qx);
-    const int k_hi = (MODE == MODE_SELF) ? (qx + 15 - b_hi) : (b_hi - 15 + qx);
+    const uint32_t pos = min(uint32_t(qx + c_lane), 8u);   // negative -> huge unsigned -> 8 (zero row)
     uint32_t af[4];
-    af[0] = (k_lo == 2 * t ? 0x00003F80u : 0u) | (k_lo == 2 * t + 1 ? 0x3F800000u : 0u);
-    af[1] = (k_hi == 2 * t ? 0x00003F80u : 0u) | (k_hi == 2 * t + 1 ? 0x3F800000u : 0u);
-    af[2] = (k_lo == 2 * t + 8 ? 0x00003F80u : 0u) | (k_lo == 2 * t + 9 ? 0x3F800000u : 0u);
-    af[3] = (k_hi == 2 * t + 8 ? 0x00003F80u : 0u) | (k_hi == 2 * t + 9 ? 0x3F800000u : 0u);
+    ldsm_x4(onehot_tbl + pos * 16, af[0], af[1], af[2], af[3]);
     mma_bf16(acc, af, b0, b1);
   }
 }
@@ -381,7 +420,8 @@ __global__ void __launch_bounds__(A16_BWD_THREADS, 1) win_attn16_bwd_kernel(cons
   __shared__ float s_bias[G::TBL];
   __shared__ float s_lse[256];
   __shared__ float s_delta[256];
-  __shared__ uint8_t s_rid[256];
+  __shared__ int s_qtok[256];
+  __shared__ __align__(16) uint16_t s_onehot[9 * 8];
   const uint32_t sm0 = smem_u32(smem_dyn);
   const uint32_t sQ = sm0 + L::kQ, sDO = sm0 + L::kDO, sK = sm0 + L::kK, sV = sm0 + L::kV, sP = sm0 + L::kP,
                  sDS = sm0 + L::kDS, sOut = sm0 + L::kOut;
@@ -391,7 +431,8 @@ __global__ void __launch_bounds__(A16_BWD_THREADS, 1) win_attn16_bwd_kernel(cons
   const int g = lane >> 2, t = lane & 3;
   const int hw = a.heads * 32;
   constexpr float kLog2e = 1.4426950408889634f;
-  for (int i = threadIdx.x; i < G::TBL; i += A16_BWD_THREADS) s_bias[i] = a.bias_table[i * a.heads + h];
+  load_bias_table<MODE>(s_bias, a.bias_table, a.heads, h, A16_BWD_THREADS);
+  if (threadIdx.x < 72) s_onehot[threadIdx.x] = ((threadIdx.x >> 3) == (threadIdx.x & 7)) ? 0x3F80 : 0;  // bf16 1.0
   // this CTA's slice of the diagonal-sum scratch: [NKT][16 warps][32 lanes] float4, exclusively owned per thread
   float4* scratch = reinterpret_cast<float4*>(a.dbias_scratch) +
                     ((size_t)blockIdx.x * a.heads + h) * (G::NKT * 16 * 32);
@@ -400,25 +441,25 @@ __global__ void __launch_bounds__(A16_BWD_THREADS, 1) win_attn16_bwd_kernel(cons
   for (int w = blockIdx.x; w < nwin; w += gridDim.x) {
     const WinPos p = win_pos(a, w);
     __syncthreads();
-    for (int c = threadIdx.x; c < 2 * 256 * 4; c += A16_BWD_THREADS) {
-      const int which = c >> 10, rem = c & 1023, i = rem >> 2, ch = rem & 3;
-      const long long tok = q_token(a, p, i >> 4, i & 15);
-      const __nv_bfloat16* src = which ? (a.dout + tok * a.ld_o + h * 32 + ch * 8) : (a.qkv + tok * a.ld_qkv + h * 32 + ch * 8);
-      cp_async16((which ? sDO : sQ) + t32_off(i, ch), src);
-    }
-    load_kv<MODE>(a, p, h, sK, sV, A16_BWD_THREADS);
-    cp_async_commit();
-    bool masked = false;
-    if (MODE == MODE_SELF && a.shift > 0) {
-      masked = (p.wy == (a.H >> 4) - 1) || (p.wx == (a.W >> 4) - 1);
-      if (masked && threadIdx.x < 256) {
-        const int i = threadIdx.x;
-        s_rid[i] = uint8_t(mask_region(p.wy * 16 + (i >> 4), a.H, a.shift) * 3 + mask_region(p.wx * 16 + (i & 15), a.W, a.shift));
+    fill_token_table(a, p, s_qtok, A16_BWD_THREADS);
+    __syncthreads();
+    {
+      const int ch = threadIdx.x & 3;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int i = (threadIdx.x >> 2) + 128 * k;
+        const long long tok = s_qtok[i];
+        cp_async16(sQ + t32_off(i, ch), a.qkv + tok * a.ld_qkv + h * 32 + ch * 8);
+        cp_async16(sDO + t32_off(i, ch), a.dout + tok * a.ld_o + h * 32 + ch * 8);
       }
     }
+    load_kv<MODE>(a, p, s_qtok, h, sK, sV, A16_BWD_THREADS);
+    cp_async_commit();
+    const bool shifted = (MODE == MODE_SELF) && a.shift > 0;
+    const bool last_y = shifted && p.wy == (a.H >> 4) - 1, last_x = shifted && p.wx == (a.W >> 4) - 1;
     {  // delta_i = sum_d dO[i,d] * O[i,d]   (two threads per query row, 16 columns each), lse
       const int i = threadIdx.x >> 1, hf = threadIdx.x & 1;
-      const long long tok = q_token(a, p, i >> 4, i & 15);
+      const long long tok = s_qtok[i];
       const uint4* po = reinterpret_cast<const uint4*>(a.osave + tok * a.ld_o + h * 32 + hf * 16);
       const uint4* pd = reinterpret_cast<const uint4*>(a.dout + tok * a.ld_o + h * 32 + hf * 16);
       float acc = 0.f;
@@ -437,7 +478,6 @@ __global__ void __launch_bounds__(A16_BWD_THREADS, 1) win_attn16_bwd_kernel(cons
     }
     cp_async_wait<0>();
     __syncthreads();
-    const BiasCtx<MODE> bc{s_bias, s_rid, masked};
     const int r0 = warp * 16, qy = warp;
     uint32_t aq[2][4], ad[2][4];
 #pragma unroll
@@ -457,7 +497,7 @@ __global__ void __launch_bounds__(A16_BWD_THREADS, 1) win_attn16_bwd_kernel(cons
       const uint32_t kT = sK + kt * 64 * 64, vT = sV + kt * 64 * 64;
       // ---- phase A: this warp's 16 query rows x 64 key slots
       float s[8][4];
-      qk_tile<MODE>(aq, kT, bc, qy, kt, lane, s);
+      qk_tile<MODE>(aq, kT, s_bias + bias_base<MODE>(qy, kt, g, t), mask_ctx(last_y, last_x, qy, kt), lane, s);
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {  // P = exp(S - lse), normalised
         s[nt][0] = fast_ex2(fmaf(s[nt][0], kLog2e, -lse0));
@@ -467,6 +507,14 @@ __global__ void __launch_bounds__(A16_BWD_THREADS, 1) win_attn16_bwd_kernel(cons
       }
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {  // dP = dO V^T, dS = P * (dP - delta); P, dS -> smem (bf16)
+        if (!nt_valid<MODE>(nt)) {    // padding keys: P = dS = 0
+          s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(sP + t64_off(r0 + g, nt) + t * 4), "r"(0u) : "memory");
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(sP + t64_off(r0 + g + 8, nt) + t * 4), "r"(0u) : "memory");
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(sDS + t64_off(r0 + g, nt) + t * 4), "r"(0u) : "memory");
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(sDS + t64_off(r0 + g + 8, nt) + t * 4), "r"(0u) : "memory");
+          continue;
+        }
         uint32_t b0, b1, b2, b3;
         ldsm_x4(vT + t32_off(nt * 8 + (lane & 7), lane >> 3), b0, b1, b2, b3);
         float dp[4] = {0.f, 0.f, 0.f, 0.f};
@@ -498,7 +546,7 @@ __global__ void __launch_bounds__(A16_BWD_THREADS, 1) win_attn16_bwd_kernel(cons
           asm volatile("st.shared.u32 [%0], %1;" ::"r"(dst + t32_off(rg * 16 + g + 8, ch * 2 + n) + t * 4), "r"(hi) : "memory");
         }
         float acc[4];
-        diag_mma<MODE>(sDS, warp, lane, acc);
+        diag_mma<MODE>(sDS, smem_u32(s_onehot), warp, lane, acc);
         float4* sp = scratch + (kt * 16 + warp) * 32 + lane;
         float4 v = *sp;
         v.x += acc[0]; v.y += acc[1]; v.z += acc[2]; v.w += acc[3];
@@ -510,8 +558,7 @@ __global__ void __launch_bounds__(A16_BWD_THREADS, 1) win_attn16_bwd_kernel(cons
         const int slot = kt * 64 + sl;
         const uint4 v = lds128(sOut + m * (64 * 64) + t32_off(sl, ch));
         if (MODE == MODE_SELF) {
-          bool sv;
-          const long long tok = k_token<MODE>(a, p, slot, sv);
+          const long long tok = s_qtok[slot];
           *reinterpret_cast<uint4*>(a.dqkv + tok * a.ld_qkv + (1 + m) * hw + h * 32 + ch * 8) = v;
         } else {
           __nv_bfloat16* dst = a.dkv_win + ((((size_t)w * a.heads + h) * 2 + m) * G::NS + slot) * 32 + ch * 8;
@@ -529,7 +576,7 @@ __global__ void __launch_bounds__(A16_BWD_THREADS, 1) win_attn16_bwd_kernel(cons
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       const int c = lane + 32 * k, i = c >> 2, ch = c & 3;
-      const long long tok = q_token(a, p, qy, i);
+      const long long tok = s_qtok[qy * 16 + i];
       *reinterpret_cast<uint4*>(a.dqkv + tok * a.ld_qkv + h * 32 + ch * 8) = lds128(sP + t32_off(r0 + i, ch));
     }
   }

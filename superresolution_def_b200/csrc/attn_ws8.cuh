@@ -172,18 +172,33 @@ __device__ __forceinline__ void store_frag_t32(uint32_t tile, int r0, int lane, 
   }
 }
 
-// async-load `ntiles` per-head [64 x 32] tiles of window w: tile k comes from column offset col_off[k] of `src`
-__device__ __forceinline__ void load_window_tiles(const AttnArgs& a, int w, uint32_t dst, const __nv_bfloat16* src0,
-                                                  int ld0, int col0, int ntiles_from_qkv, const __nv_bfloat16* src1,
-                                                  int ld1, int col1) {
-  // qkv tiles: q,k,v at col0 + {0, heads*32, 2*heads*32}
+// Each thread always handles the same two token rows (i0 = tid/4, i1 = i0 + 32) and 16-byte chunk (tid%4) of every
+// [64 x 32] tile, so a window's token addresses are computed once per thread and window (two wrapped coordinates)
+// instead of once per 16-byte transfer.
+struct WinToks { long long t0, t1; };
+__device__ __forceinline__ WinToks window_toks(const AttnArgs& a, int w) {
+  WinToks r;
+  r.t0 = window_token(a, w, threadIdx.x >> 2);
+  r.t1 = window_token(a, w, (threadIdx.x >> 2) + 32);
+  return r;
+}
+// async-load the q,k,v tiles (column offsets col0 + {0,1,2}*heads*32 of src0) and optionally a 4th tile from src1
+__device__ __forceinline__ void load_window_tiles(const AttnArgs& a, const WinToks& tk, uint32_t dst,
+                                                  const __nv_bfloat16* src0, int ld0, int col0,
+                                                  const __nv_bfloat16* src1, int ld1, int col1) {
   const int hw = a.heads * 32;
-  for (int c = threadIdx.x; c < (ntiles_from_qkv + (src1 ? 1 : 0)) * 256; c += ATT_THREADS) {
-    const int tile = c >> 8, rem = c & 255, i = rem >> 2, ch = rem & 3;
-    const int tok = window_token(a, w, i);
-    const __nv_bfloat16* p = (tile < ntiles_from_qkv) ? (src0 + size_t(tok) * ld0 + col0 + tile * hw + ch * 8)
-                                                      : (src1 + size_t(tok) * ld1 + col1 + ch * 8);
-    cp_async16(dst + tile * ATT_TILE + t32_off(i, ch), p);
+  const int i0 = threadIdx.x >> 2, ch = threadIdx.x & 3;
+  const uint32_t d0 = dst + t32_off(i0, ch), d1 = dst + t32_off(i0 + 32, ch);
+  const __nv_bfloat16* p0 = src0 + tk.t0 * ld0 + col0 + ch * 8;
+  const __nv_bfloat16* p1 = src0 + tk.t1 * ld0 + col0 + ch * 8;
+#pragma unroll
+  for (int tile = 0; tile < 3; ++tile) {
+    cp_async16(d0 + tile * ATT_TILE, p0 + tile * hw);
+    cp_async16(d1 + tile * ATT_TILE, p1 + tile * hw);
+  }
+  if (src1 != nullptr) {
+    cp_async16(d0 + 3 * ATT_TILE, src1 + tk.t0 * ld1 + col1 + ch * 8);
+    cp_async16(d1 + 3 * ATT_TILE, src1 + tk.t1 * ld1 + col1 + ch * 8);
   }
 }
 
@@ -201,11 +216,18 @@ __global__ void __launch_bounds__(ATT_THREADS) win_attn_ws8_fwd_kernel(const Att
 
   int w = blockIdx.x;
   int buf = 0;
-  if (w < nwin) load_window_tiles(a, w, smem_u32(s_in[0]), a.qkv, a.ld_qkv, h * 32, 3, nullptr, 0, 0);
+  WinToks tk{0, 0}, tkn{0, 0};
+  if (w < nwin) {
+    tk = window_toks(a, w);
+    load_window_tiles(a, tk, smem_u32(s_in[0]), a.qkv, a.ld_qkv, h * 32, nullptr, 0, 0);
+  }
   cp_async_commit();
-  for (; w < nwin; w += gridDim.x, buf ^= 1) {
+  for (; w < nwin; w += gridDim.x, buf ^= 1, tk = tkn) {
     const int wn = w + gridDim.x;
-    if (wn < nwin) load_window_tiles(a, wn, smem_u32(s_in[buf ^ 1]), a.qkv, a.ld_qkv, h * 32, 3, nullptr, 0, 0);
+    if (wn < nwin) {
+      tkn = window_toks(a, wn);
+      load_window_tiles(a, tkn, smem_u32(s_in[buf ^ 1]), a.qkv, a.ld_qkv, h * 32, nullptr, 0, 0);
+    }
     cp_async_commit();
     cp_async_wait<1>();
     __syncthreads();
@@ -218,9 +240,10 @@ __global__ void __launch_bounds__(ATT_THREADS) win_attn_ws8_fwd_kernel(const Att
     frag_times_tile(s, vt, lane, o);
     store_frag_t32(smem_u32(s_out), r0, lane, o);
     __syncthreads();
-    for (int c = threadIdx.x; c < 256; c += ATT_THREADS) {
-      const int i = c >> 2, ch = c & 3;
-      const int tok = window_token(a, w, i);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int i = (threadIdx.x >> 2) + 32 * k, ch = threadIdx.x & 3;
+      const long long tok = k ? tk.t1 : tk.t0;
       uint4 v = *reinterpret_cast<const uint4*>(s_out + t32_off(i, ch));
       if (ones_here && ch == (ones_c >> 3)) {  // bias-folding column of the following projection := 1.0
         const int word = (ones_c & 7) >> 1;
@@ -231,7 +254,7 @@ __global__ void __launch_bounds__(ATT_THREADS) win_attn_ws8_fwd_kernel(const Att
         v.z = (word == 2) ? ((v.z & keep) | one) : v.z;
         v.w = (word == 3) ? ((v.w & keep) | one) : v.w;
       }
-      *reinterpret_cast<uint4*>(a.out + size_t(tok) * a.ld_o + h * 32 + ch * 8) = v;
+      *reinterpret_cast<uint4*>(a.out + tok * a.ld_o + h * 32 + ch * 8) = v;
     }
     // s_out / s_in[buf] are rewritten only after the next iteration's __syncthreads or by loads issued
     // at the top of the next iteration into buf (which every thread has finished reading: barrier below)
@@ -241,11 +264,10 @@ __global__ void __launch_bounds__(ATT_THREADS) win_attn_ws8_fwd_kernel(const Att
 }
 
 // ============================================================================ backward
-struct AttnBwdSmem {
-  uint8_t in[2][4 * ATT_TILE];  // q, k, v, dO
+struct AttnBwdSmem {  // 49.8 KB: four CTAs per SM
+  uint8_t in[2][4 * ATT_TILE];  // q, k, v, dO (double-buffered); the current buffer doubles as dq/dk/dv staging
   uint8_t p[64 * 128];          // P  (bf16) [q][key]
   uint8_t ds[64 * 128];         // dS (bf16) [q][key]
-  uint8_t out[3 * ATT_TILE];    // dq, dk, dv
   float bias[225];
   float dbias[225];
 };
@@ -275,7 +297,7 @@ __device__ __forceinline__ void tileT_times_tile(uint32_t a_tile, uint32_t b_til
   }
 }
 
-__global__ void __launch_bounds__(ATT_THREADS) win_attn_ws8_bwd_kernel(const AttnArgs a) {
+__global__ void __launch_bounds__(ATT_THREADS, 4) win_attn_ws8_bwd_kernel(const AttnArgs a) {
   extern __shared__ __align__(128) uint8_t smem_dyn[];
   AttnBwdSmem& sm = *reinterpret_cast<AttnBwdSmem*>(smem_dyn);
   const int h = blockIdx.y;
@@ -292,17 +314,23 @@ __global__ void __launch_bounds__(ATT_THREADS) win_attn_ws8_bwd_kernel(const Att
 
   int w = blockIdx.x;
   int buf = 0;
-  if (w < nwin) load_window_tiles(a, w, smem_u32(sm.in[0]), a.qkv, a.ld_qkv, h * 32, 3, a.dout, a.ld_o, h * 32);
+  WinToks tk{0, 0}, tkn{0, 0};
+  if (w < nwin) {
+    tk = window_toks(a, w);
+    load_window_tiles(a, tk, smem_u32(sm.in[0]), a.qkv, a.ld_qkv, h * 32, a.dout, a.ld_o, h * 32);
+  }
   cp_async_commit();
-  for (; w < nwin; w += gridDim.x, buf ^= 1) {
+  for (; w < nwin; w += gridDim.x, buf ^= 1, tk = tkn) {
     const int wn = w + gridDim.x;
-    if (wn < nwin)
-      load_window_tiles(a, wn, smem_u32(sm.in[buf ^ 1]), a.qkv, a.ld_qkv, h * 32, 3, a.dout, a.ld_o, h * 32);
+    if (wn < nwin) {
+      tkn = window_toks(a, wn);
+      load_window_tiles(a, tkn, smem_u32(sm.in[buf ^ 1]), a.qkv, a.ld_qkv, h * 32, a.dout, a.ld_o, h * 32);
+    }
     cp_async_commit();
     cp_async_wait<1>();
     __syncthreads();
     const uint32_t qt = smem_u32(sm.in[buf]), kt = qt + ATT_TILE, vt = qt + 2 * ATT_TILE, dot = qt + 3 * ATT_TILE;
-    const uint32_t pt = smem_u32(sm.p), dst = smem_u32(sm.ds), outt = smem_u32(sm.out);
+    const uint32_t pt = smem_u32(sm.p), dst = smem_u32(sm.ds);
     const int r0 = warp * 16;
     // ---- phase A: this warp's 16 query rows
     float s[8][4];
@@ -353,24 +381,28 @@ __global__ void __launch_bounds__(ATT_THREADS) win_attn_ws8_bwd_kernel(const Att
       asm volatile("st.shared.u32 [%0], %1;" ::"r"(dst + t64_off(r0 + g, nt) + t * 4), "r"(lo) : "memory");
       asm volatile("st.shared.u32 [%0], %1;" ::"r"(dst + t64_off(r0 + g + 8, nt) + t * 4), "r"(hi) : "memory");
     }
-    // dQ rows = dS (bf16) * K
-    float o[4][4];
-    frag_times_tile(s, kt, lane, o);
-    store_frag_t32(outt, r0, lane, o);
+    // dQ rows = dS (bf16) * K   (kept in registers until the input tiles are dead)
+    float dq[4][4], dk[4][4], dv[4][4];
+    frag_times_tile(s, kt, lane, dq);
     __syncthreads();
     // ---- phase B: this warp's 16 key rows
-    tileT_times_tile(dst, qt, r0, lane, o);   // dK = dS^T Q
-    store_frag_t32(outt + ATT_TILE, r0, lane, o);
-    tileT_times_tile(pt, dot, r0, lane, o);   // dV = P^T dO
-    store_frag_t32(outt + 2 * ATT_TILE, r0, lane, o);
+    tileT_times_tile(dst, qt, r0, lane, dk);   // dK = dS^T Q
+    tileT_times_tile(pt, dot, r0, lane, dv);   // dV = P^T dO
+    __syncthreads();                           // every warp is done reading q, k, v, dO, P, dS of this window
+    store_frag_t32(qt, r0, lane, dq);
+    store_frag_t32(qt + ATT_TILE, r0, lane, dk);
+    store_frag_t32(qt + 2 * ATT_TILE, r0, lane, dv);
     __syncthreads();
     const int hw = a.heads * 32;
-    for (int c = threadIdx.x; c < 3 * 256; c += ATT_THREADS) {
-      const int tile = c >> 8, rem = c & 255, i = rem >> 2, ch = rem & 3;
-      const int tok = window_token(a, w, i);
-      const uint4 v = *reinterpret_cast<const uint4*>(sm.out + tile * ATT_TILE + t32_off(i, ch));
-      *reinterpret_cast<uint4*>(a.dqkv + size_t(tok) * a.ld_qkv + tile * hw + h * 32 + ch * 8) = v;
-    }
+#pragma unroll
+    for (int tile = 0; tile < 3; ++tile)
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int i = (threadIdx.x >> 2) + 32 * k, ch = threadIdx.x & 3;
+        const long long tok = k ? tk.t1 : tk.t0;
+        const uint4 v = *reinterpret_cast<const uint4*>(sm.in[buf] + tile * ATT_TILE + t32_off(i, ch));
+        *reinterpret_cast<uint4*>(a.dqkv + tok * a.ld_qkv + tile * hw + h * 32 + ch * 8) = v;
+      }
     __syncthreads();
   }
   cp_async_wait<0>();

@@ -8,7 +8,10 @@
 // Roles (320 threads, 1 CTA/SM, persistent over output tiles):
 //   warp 0   : TMA producer   (A [128 x 64] + B [BN x 64] bf16 boxes, 128B swizzle, mbarrier ring)
 //   warp 1   : MMA issuer     (one lane issues tcgen05.mma 128 x BN x 16; accumulators double-buffered in TMEM)
-//   warps 2-9: epilogue       (tcgen05.ld -> registers -> math -> swizzled smem -> TMA store)
+//   warps 2-9 (row epilogues) / 2-17 (elementwise epilogues): tcgen05.ld -> registers -> math -> swizzled smem ->
+//              TMA store.  A warp reaches TMEM lanes 32*(warp%4)..+31 only, so 2 (or 4) warps share each lane quarter
+//              and split the columns of every 64-column box; the elementwise epilogues are issue/latency bound
+//              (ncu: 8 warps left the SM at 58 % issue utilisation), hence 16 warps there.
 #pragma once
 #include "srk_ptx.cuh"
 
@@ -41,6 +44,12 @@ struct GemmArgs {
 
 template <int BN, int EPI>
 struct GemmCfg {
+  static constexpr bool kBoxEpi = (EPI == EPI_STORE || EPI == EPI_GELU2 || EPI == EPI_MUL);
+  static constexpr int kEpiWarps = kBoxEpi ? 16 : 8;
+  static constexpr int kEpiThreads = 32 * kEpiWarps;
+  static constexpr int kThreads = 64 + kEpiThreads;
+  static constexpr int kParts = kEpiWarps / 4;        // warps sharing one TMEM lane quarter
+  static constexpr int kColsPerPart = 64 / kParts;    // columns of a 64-column box handled by one warp
   static constexpr int kStageBytes = GEMM_BM * 128 + BN * 128;
   static constexpr int kBoxes = BN / 64;
   static constexpr int kEpiBytes = (EPI == EPI_STORE)   ? 2 * BOX_BYTES
@@ -99,7 +108,7 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 __device__ __forceinline__ uint32_t swz(int r, int ch) { return uint32_t(r) * 128u + (uint32_t(ch ^ (r & 7)) << 4); }
 
 template <int BN, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__((GemmCfg<BN, EPI>::kThreads), 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
                const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmX2,
@@ -140,7 +149,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), GEMM_EPI_THREADS / 32);
+      mbar_init(tempty_bar(a), Cfg::kEpiWarps);
       mbar_init(aux_bar(a), 1);
     }
     fence_mbar_init();
@@ -150,7 +159,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tmem_relinquish();
   }
   if constexpr (EPI == EPI_RES_LN || EPI == EPI_LNBWD) {
-    for (int i = threadIdx.x; i < 256; i += GEMM_THREADS) {
+    for (int i = threadIdx.x; i < 256; i += Cfg::kThreads) {
       s_gamma[i] = (i < args.n_real) ? args.gamma[i] : 0.f;
       s_beta[i] = (i < args.n_real && args.beta != nullptr) ? args.beta[i] : 0.f;
     }
@@ -215,7 +224,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // Two warps share each TMEM lane quarter (hardware: a warp reaches lanes 32*(warp%4)..+31) and split the
     // columns between them ("half"), so every SM sub-partition hosts two epilogue warps.
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;   // 0: warps 2-5, 1: warps 6-9
+    const int half = (warp - 2) >> 2;   // column part: 0: warps 2-5, 1: warps 6-9 (, 2: 10-13, 3: 14-17)
     const int row = q * 32 + lane;      // accumulator row owned by this thread (shared with the other half)
     const bool elected = (threadIdx.x == 64);
     const uint32_t lane_sel = uint32_t(q * 32) << 16;
@@ -289,7 +298,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
           }
-          named_bar_sync(1, GEMM_EPI_THREADS);
+          named_bar_sync(1, Cfg::kEpiThreads);
           uint32_t aux_addr = 0;
           if constexpr (EPI == EPI_MUL) {
             const uint32_t ab = aux_count & 1u;
@@ -297,8 +306,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             aux_addr = epi_base + kAuxOff + ab * BOX_BYTES;
           }
           {
-            uint32_t r[32];
-            tmem_ld_x32(taddr + uint32_t(j * 64 + half * 32), r);
+            constexpr int CPP = Cfg::kColsPerPart;
+            uint32_t r[CPP];
+            tmem_ld_cols(taddr + uint32_t(j * 64 + half * CPP), r);
             tmem_ld_wait();
             if (j == NBOX - 1) {  // accumulator fully drained into registers: hand TMEM back to the MMA warp
               tc_fence_before();
@@ -306,8 +316,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (lane == 0) mbar_arrive(tempty_bar(acc));
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int ch = half * 4 + i;
+            for (int i = 0; i < CPP / 8; ++i) {
+              const int ch = half * (CPP / 8) + i;
               const uint32_t off = swz(row, ch);
               float v[8];
 #pragma unroll
@@ -341,7 +351,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           fence_proxy_async();
-          named_bar_sync(1, GEMM_EPI_THREADS);
+          named_bar_sync(1, Cfg::kEpiThreads);
           if (elected) {
             tma_store_2d(&tmC, out0, n0 + j * 64, m0);
             if constexpr (EPI == EPI_GELU2) tma_store_2d(&tmC2, out0 + BOX_BYTES, n0 + j * 64, m0);
@@ -387,7 +397,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (lane == 0) mbar_arrive(tempty_bar(acc));
           s_red[(0 * 2 + half) * 128 + row] = sum;
           fence_proxy_async();
-          named_bar_sync(1, GEMM_EPI_THREADS);
+          named_bar_sync(1, Cfg::kEpiThreads);
           if (elected) {  // v (= new residual stream) is complete in T0
             for (int b = 0; b < NBOX; ++b) tma_store_2d(&tmC, T0 + b * BOX_BYTES, n0 + b * 64, m0);
             tma_store_commit();
@@ -406,7 +416,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           s_red[(1 * 2 + half) * 128 + row] = var;
-          named_bar_sync(1, GEMM_EPI_THREADS);
+          named_bar_sync(1, Cfg::kEpiThreads);
           var = s_red[(1 * 2 + 0) * 128 + row] + s_red[(1 * 2 + 1) * 128 + row];
           const float rstd = rsqrtf(var * inv_n + args.eps);
           if (half == 0 && args.stats != nullptr)
@@ -429,7 +439,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                          pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7])));
           }
           fence_proxy_async();
-          named_bar_sync(1, GEMM_EPI_THREADS);
+          named_bar_sync(1, Cfg::kEpiThreads);
           if (elected) {
             for (int b = 0; b < NBOX; ++b) tma_store_2d(&tmC2, T1 + b * BOX_BYTES, n0 + b * 64, m0);
             tma_store_commit();
@@ -477,7 +487,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           s_red[(0 * 2 + half) * 128 + row] = s1;
           s_red[(1 * 2 + half) * 128 + row] = s2;
-          named_bar_sync(1, GEMM_EPI_THREADS);
+          named_bar_sync(1, Cfg::kEpiThreads);
           const float c1 = (s_red[(0 * 2 + 0) * 128 + row] + s_red[(0 * 2 + 1) * 128 + row]) * inv_n;
           const float c2 = (s_red[(1 * 2 + 0) * 128 + row] + s_red[(1 * 2 + 1) * 128 + row]) * inv_n;
 #pragma unroll 1
@@ -512,7 +522,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(acc));
           fence_proxy_async();
-          named_bar_sync(1, GEMM_EPI_THREADS);
+          named_bar_sync(1, Cfg::kEpiThreads);
           if (elected) {
             for (int b = 0; b < NBOX; ++b) tma_store_2d(&tmC, T1 + b * BOX_BYTES, n0 + b * 64, m0);
             tma_store_commit();
@@ -527,7 +537,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         // s_red is rewritten by the next tile only after its first named barrier... not guaranteed: a fast
         // thread could overwrite s_red[0] while a slow one still reads it, so close the tile with a barrier.
-        named_bar_sync(1, GEMM_EPI_THREADS);
+        named_bar_sync(1, Cfg::kEpiThreads);
       }
     }
     if constexpr (EPI == EPI_LNBWD) {
@@ -538,9 +548,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         s_part[(q * 2 + 0) * BN + (half * NCH + k) * 32 + lane] = acc_g[k];
         s_part[(q * 2 + 1) * BN + (half * NCH + k) * 32 + lane] = acc_b[k];
       }
-      named_bar_sync(1, GEMM_EPI_THREADS);
+      named_bar_sync(1, Cfg::kEpiThreads);
       const int e = threadIdx.x - 64;
-      for (int i = e; i < 2 * BN; i += GEMM_EPI_THREADS) {
+      for (int i = e; i < 2 * BN; i += Cfg::kEpiThreads) {
         const int w = i / BN, c = i % BN;
         args.partials[(size_t(blockIdx.x) * 2 + w) * BN + c] =
             s_part[(0 * 2 + w) * BN + c] + s_part[(1 * 2 + w) * BN + c] + s_part[(2 * 2 + w) * BN + c] +

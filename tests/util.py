@@ -20,6 +20,12 @@ def randomize_(module: torch.nn.Module, seed: int = 0, table_std: float = 1.0):
                 p.copy_(torch.randn(p.shape, generator=g) * table_std)
             elif "norm" in name and name.endswith("weight"):
                 p.copy_(1.0 + 0.3 * torch.randn(p.shape, generator=g))
+            elif name.endswith("attention.1.bias"):
+                # squeeze layer of HAT's ChannelAttention (6 ReLU units fed by a global mean): keep the pre-activations
+                # away from the ReLU kink, where bf16-vs-fp32 rounding would flip a unit on/off and make the
+                # comparison of that layer's gradients meaningless (both signs are exercised)
+                sign = torch.where(torch.arange(p.numel()) % 2 == 0, 1.0, -1.0)
+                p.copy_(sign * (0.5 + 0.1 * torch.rand(p.shape, generator=g)))
             elif name.endswith("bias"):
                 p.copy_(0.2 * torch.randn(p.shape, generator=g))
             elif p.dim() >= 2:

@@ -30,5 +30,20 @@ elif which == "attn_bwd":
     qkv = torch.randn(T, 576, device=dev).to(bf); tab = torch.randn(225, 6, device=dev)
     do = torch.randn(T, 192, device=dev).to(bf); dq = torch.empty_like(qkv); dt = torch.empty_like(tab)
     for _ in range(reps): capi.win_attn_bwd(capi.SrkGeom(B, 128, 128, 8, 4), 6, qkv, tab, do, dq, dt)
+elif which in ("attn16_fwd", "attn16_bwd", "oca_fwd", "oca_bwd"):
+    B8 = 8
+    T8 = B8 * 16384
+    mode = capi.ATTN_SELF if which.startswith("attn16") else capi.ATTN_OCA
+    rows = 961 if mode == capi.ATTN_SELF else 1521
+    geom = capi.SrkGeom(B8, 128, 128, 16, 8 if mode == capi.ATTN_SELF else 0)
+    qkv = torch.randn(T8, 576, device=dev).to(bf); tab = torch.randn(rows, 6, device=dev)
+    out = torch.empty(T8, 192, device=dev, dtype=bf); lse = torch.empty(6, T8, device=dev)
+    capi.win_attn16_fwd(geom, mode, 6, qkv, tab, out, lse, ones_col=30)
+    if which.endswith("fwd"):
+        for _ in range(reps): capi.win_attn16_fwd(geom, mode, 6, qkv, tab, out, lse, ones_col=30)
+    else:
+        do = torch.randn(T8, 192, device=dev).to(bf); dq = torch.empty_like(qkv); dt = torch.empty_like(tab)
+        ws = torch.empty(capi.attn16_bwd_ws_bytes(geom, mode, 6), device=dev, dtype=torch.uint8)
+        for _ in range(reps): capi.win_attn16_bwd(geom, mode, 6, qkv, tab, out, do, lse, dq, ws, dt)
 torch.cuda.synchronize()
 print("done", which)

@@ -29,6 +29,10 @@ UNIT = "patches/s"
 MODEL_KW = dict(upscale=4, in_chans=1, img_size=128, window_size=8, embed_dim=180, depths=[6] * 6, num_heads=[6] * 6,
                 mlp_ratio=2)  # train_swin.py:147-149 (mlp_ratio is swallowed by the reference: effective 4.0)
 GFLOP_PER_PATCH_TRAIN = 1569.826  # SURVEY.md §8d (FlopCounterMode on the reference, fwd+bwd)
+# --workload hat: BASELINE configs[2] (a parity-test configuration; timed on request, not the default bench line)
+HAT_KW = dict(img_size=128, in_chans=1, embed_dim=180, depths=(6,) * 6, num_heads=(6,) * 6, window_size=16, upscale=4,
+              upsampler="pixelshuffle")   # drop_path_rate default 0.1: stochastic depth active, as train_hat.py would
+HAT_GFLOP_PER_PATCH_TRAIN = 3026.031
 
 
 def load_peaks():
@@ -179,10 +183,19 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     _dbg("process group ready")
-    B = args.batch
+    hat = args.workload == "hat"
+    B = args.batch or (8 if hat else 16)
     torch.manual_seed(0)
-    net = SwinIR(**MODEL_KW).to(dev)
+    if hat:
+        from superresolution_def_b200.hat_arch import HAT
+        net = HAT(**HAT_KW).to(dev)
+    else:
+        net = SwinIR(**MODEL_KW).to(dev)
     net.train()
+    gflop = HAT_GFLOP_PER_PATCH_TRAIN if hat else GFLOP_PER_PATCH_TRAIN
+    wl_name = ("HAT x4 (window 16, OCAB, CAB, stochastic depth 0.1) training step (fwd + L1 + bwd + AdamW), bf16, "
+               f"batch {B}/GPU, 128^2->512^2 (BASELINE configs[2])") if hat else \
+              (f"SwinIR x4 training step (fwd + L1 + bwd + AdamW), bf16, batch {B}/GPU, 128^2->512^2 (BASELINE configs[1])")
     if world > 1:
         for p in net.parameters():
             dist.broadcast(p.data, 0)
@@ -288,22 +301,21 @@ def run_ours(args):
     value = world * B * args.steps / (ms * 1e-3)
     e2e_v = world * B * args.steps / (ms_e2e * 1e-3)
     peaks = load_peaks()
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+    line = {"metric": METRIC.replace("SwinIR", "HAT") if hat else METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "SwinIR x4 training step (fwd + L1 + bwd + AdamW), bf16, batch 16/GPU, 128^2->512^2 "
-                                   "(BASELINE configs[1])", "global_batch": world * B, "parallelism": f"dp{world}",
+            "config": {"workload": wl_name, "global_batch": world * B, "parallelism": f"dp{world}",
                        "l2": "activations saved per step (~60 GB) exceed the 126 MB L2; 4 input batches rotated",
                        "grad_allreduce_mb": reducer.nbytes / 2 ** 20 if reducer is not None else 0,
                        "launch": "whole step replayed as one CUDA graph" if args.graph else "eager"},
             "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": B * (128 * 128 + 512 * 512) * 4,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks, "loss": loss_v, "peak_mem_gb": mem_gb,
-            "step_tflops": value / world * GFLOP_PER_PATCH_TRAIN / 1e3,
-            "step_frac_of_bf16_sustained": value / world * GFLOP_PER_PATCH_TRAIN / 1e3 / peaks[2]}
+            "step_tflops": value / world * gflop / 1e3,
+            "step_frac_of_bf16_sustained": value / world * gflop / 1e3 / peaks[2]}
     if rank == 0:
         line["roofline"] = roofline_probe(B, peaks)
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not hat:
             v, spp, threads = cpu_reference_arm(2, 1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": "2 fp32 training steps of batch 1 after 1 warm-up (oracle/swinir_oracle.py)"}
@@ -317,7 +329,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=16, help="patches per GPU per step (BASELINE configs[1]: 16)")
+    ap.add_argument("--batch", type=int, default=0, help="patches per GPU per step (default: 16 SwinIR = BASELINE configs[1], 8 HAT)")
+    ap.add_argument("--workload", default="swinir", choices=["swinir", "hat"], help="swinir = the bench line (configs[1]); hat = configs[2]")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="issue the step eagerly instead of replaying a CUDA graph")

@@ -43,6 +43,9 @@ typedef struct SrkLnArgs {
   float* stats;       /* [M][2] mean,rstd: written by RES_LN, read by LNBWD               */
   float* partials;    /* LNBWD: [srk_gemm_grid(...)][2][N] per-CTA sums for dgamma, dbeta */
   float eps;
+  const float* row_scale; /* RES_LN, optional: C = acc * row_scale[row / rows_per_scale] + X1 — stochastic depth
+                             (drop_path, hat_arch.py:11-23,306-307): one factor 0 or 1/keep_prob per sample       */
+  int rows_per_scale;     /* tokens per sample (H*W)                                                            */
 } SrkLnArgs;
 
 /* C[M,N] = epilogue(A[M,K] * B[N,K]^T): tcgen05 GEMM, bf16 in, fp32 accumulate.
@@ -225,6 +228,9 @@ typedef struct SrkHatExtra {
   void* attn_ws;      /* backward only: srk_win_attn16_bwd_ws_bytes bytes                                             */
   void* d_xn1;        /* backward, optional: if non-NULL receives d_qkv @ Wqkv ([T,Cp] bf16) and the LayerNorm-1
                          backward (g_in, norm1 grads) is left to the caller, who first adds the CAB branch gradient    */
+  const float* drop_attn; /* optional [B]: stochastic-depth factor (0 or 1/keep) of the attention branch per sample   */
+  const float* drop_mlp;  /* optional [B]: same for the MLP branch                                                    */
+  void* gs_buf;           /* backward, required when a drop_* is given: [T,Cp] bf16 scratch for the scaled gradient   */
 } SrkHatExtra;
 
 /* Forward / backward of one HAB or OCAB given xn1 = LN1(x_in): same GEMM chain as srk_swin_block_fwd/bwd

@@ -96,8 +96,9 @@ def cab(x: Tensor, p: Mapping[str, Tensor], prefix: str) -> Tensor:
 
 
 def hab(x: Tensor, p: Mapping[str, Tensor], prefix: str, x_size: tuple[int, int], num_heads: int, ws: int, shift: int,
-        rpi: Tensor, attn_mask: Tensor | None, conv_scale: float = 0.01) -> Tensor:
-    """Hybrid attention block (drop_path = identity, i.e. eval mode or rate 0).
+        rpi: Tensor, attn_mask: Tensor | None, conv_scale: float = 0.01, drop=None) -> Tensor:
+    """Hybrid attention block.  drop: None (eval mode / rate 0) or (attn_factors, mlp_factors), each [B]: the per-sample
+    stochastic-depth factors floor(keep + U)/keep that the reference's drop_path draws (hat_arch.py:11-23).
     Reference: HAB.forward, hat_arch.py:266-309 (window clamp :239-241)."""
     h, w = x_size
     b, _, c = x.shape
@@ -116,9 +117,11 @@ def hab(x: Tensor, p: Mapping[str, Tensor], prefix: str, x_size: tuple[int, int]
     ys = window_reverse(win.reshape(-1, ws, ws, c), ws, h, w)
     if shift > 0:
         ys = torch.roll(ys, shifts=(shift, shift), dims=(1, 2))
-    x = shortcut + ys.reshape(b, h * w, c) + conv_x * conv_scale
+    sa = 1.0 if drop is None else drop[0].reshape(b, 1, 1).to(x.dtype)
+    sm = 1.0 if drop is None else drop[1].reshape(b, 1, 1).to(x.dtype)
+    x = shortcut + ys.reshape(b, h * w, c) * sa + conv_x * conv_scale
     z = F.layer_norm(x, (c,), p[prefix + "norm2.weight"], p[prefix + "norm2.bias"], 1e-5)
-    return x + mlp(z, p, prefix + "mlp.")
+    return x + mlp(z, p, prefix + "mlp.") * sm
 
 
 def ocab(x: Tensor, p: Mapping[str, Tensor], prefix: str, x_size: tuple[int, int], num_heads: int, ws: int,

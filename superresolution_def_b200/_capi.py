@@ -26,6 +26,8 @@ class SrkLnArgs(Structure):
         ("stats", c_void_p),
         ("partials", c_void_p),
         ("eps", c_float),
+        ("row_scale", c_void_p),
+        ("rows_per_scale", c_int),
     ]
 
 
@@ -107,10 +109,12 @@ def gemm_tn(epi, A, B, C, C2=None, X1=None, X2=None, ln: SrkLnArgs | None = None
     _check(rc, "srk_gemm_tn")
 
 
-def make_ln_args(n_real, ones_col, gamma, beta=None, stats=None, partials=None, eps=1e-5) -> SrkLnArgs:
-    for t in (gamma, beta, stats, partials):
+def make_ln_args(n_real, ones_col, gamma, beta=None, stats=None, partials=None, eps=1e-5, row_scale=None,
+                 rows_per_scale=1) -> SrkLnArgs:
+    for t in (gamma, beta, stats, partials, row_scale):
         assert t is None or (t.dtype == torch.float32 and t.is_contiguous())
-    return SrkLnArgs(n_real, ones_col, _ptr(gamma), _ptr(beta), _ptr(stats), _ptr(partials), eps)
+    return SrkLnArgs(n_real, ones_col, _ptr(gamma), _ptr(beta), _ptr(stats), _ptr(partials), eps, _ptr(row_scale),
+                     rows_per_scale)
 
 
 def wgrad_workspace_elems(Ca: int, Cb: int, splits: int) -> int:
@@ -357,7 +361,8 @@ ATTN_SELF, ATTN_OCA = 0, 1
 
 
 class SrkHatExtra(Structure):
-    _fields_ = [("mode", c_int), ("res_in", c_void_p), ("lse", c_void_p), ("attn_ws", c_void_p), ("d_xn1", c_void_p)]
+    _fields_ = [("mode", c_int), ("res_in", c_void_p), ("lse", c_void_p), ("attn_ws", c_void_p), ("d_xn1", c_void_p),
+                ("drop_attn", c_void_p), ("drop_mlp", c_void_p), ("gs_buf", c_void_p)]
 
 
 _attn16_fwd = _sig("srk_win_attn16_fwd", [POINTER(SrkGeom), c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
@@ -395,12 +400,14 @@ def win_attn16_bwd(geom, mode, heads, qkv, rpb_table, out, d_out, lse, d_qkv, ws
     _check(rc, "srk_win_attn16_bwd")
 
 
-def _hat_extra(mode, res_in, lse, attn_ws=None, d_xn1=None):
-    return SrkHatExtra(mode, _ptr(res_in), _ptr(lse), _ptr(attn_ws), _ptr(d_xn1))
+def _hat_extra(mode, res_in, lse, attn_ws=None, d_xn1=None, drop=(None, None), gs_buf=None):
+    return SrkHatExtra(mode, _ptr(res_in), _ptr(lse), _ptr(attn_ws), _ptr(d_xn1), _ptr(drop[0]), _ptr(drop[1]),
+                       _ptr(gs_buf))
 
 
-def hat_block_fwd(dims, geom, weights: dict, params: dict, next_norm_w, next_norm_b, acts: dict, mode, res_in, lse):
-    x = _hat_extra(mode, res_in, lse)
+def hat_block_fwd(dims, geom, weights: dict, params: dict, next_norm_w, next_norm_b, acts: dict, mode, res_in, lse,
+                  drop=(None, None)):
+    x = _hat_extra(mode, res_in, lse, drop=drop)
     rc = _hat_fwd(ctypes.byref(dims), ctypes.byref(geom), ctypes.byref(_fill(SrkBlockWeights, WEIGHT_NAMES, weights)),
                   ctypes.byref(_fill(SrkBlockParams, PARAM_NAMES, params)), _ptr(next_norm_w), _ptr(next_norm_b),
                   ctypes.byref(_fill(SrkBlockActs, ACT_NAMES, acts)), ctypes.byref(x), _stream())
@@ -408,8 +415,8 @@ def hat_block_fwd(dims, geom, weights: dict, params: dict, next_norm_w, next_nor
 
 
 def hat_block_bwd(dims, geom, weights: dict, params: dict, acts: dict, g_out, scratch: dict, g_in, grads: dict, mode, lse,
-                  attn_ws, d_xn1=None):
-    x = _hat_extra(mode, None, lse, attn_ws, d_xn1)
+                  attn_ws, d_xn1=None, drop=(None, None), gs_buf=None):
+    x = _hat_extra(mode, None, lse, attn_ws, d_xn1, drop, gs_buf)
     rc = _hat_bwd(ctypes.byref(dims), ctypes.byref(geom), ctypes.byref(_fill(SrkBlockWeights, WEIGHT_NAMES, weights)),
                   ctypes.byref(_fill(SrkBlockParams, PARAM_NAMES, params)),
                   ctypes.byref(_fill(SrkBlockActs, ACT_NAMES, acts)), _ptr(g_out),

@@ -281,17 +281,17 @@ static int block_fwd_impl(const SrkBlockDims* d, const SrkGeom* g, const SrkBloc
   if (rc) return rc;
   // x_mid = residual + proj(ao); xn2 = LN2(x_mid)   (residual: x_in, or for HAB x_in + conv_scale * CAB(xn1))
   const void* resid = x ? x->res_in : a->x_in;
-  SrkLnArgs ln2{d->C, d->C, p->norm2_w, p->norm2_b, a->stats2, nullptr, 1e-5f};
+  SrkLnArgs ln2{d->C, d->C, p->norm2_w, p->norm2_b, a->stats2, nullptr, 1e-5f, x ? x->drop_attn : nullptr, g->H * g->W};
   if ((rc = srk_gemm_tn(SRK_EPI_RES_LN, T, Cp, AW, a->ao, AW, w->proj_f, AW, a->x_mid, Cp, a->xn2, Cp, resid, Cp,
                         nullptr, 0, &ln2, stream)))
     return rc;
   // act = gelu(fc1(xn2)), dact = gelu'(.)
-  SrkLnArgs ge{Hp, d->hidden, nullptr, nullptr, nullptr, nullptr, 0.f};
+  SrkLnArgs ge{Hp, d->hidden, nullptr, nullptr, nullptr, nullptr, 0.f, nullptr, 1};
   if ((rc = srk_gemm_tn(SRK_EPI_GELU2, T, Hp, Cp, a->xn2, Cp, w->fc1_f, Cp, a->act, Hp, a->dact, Hp, nullptr, 0, nullptr,
                         0, &ge, stream)))
     return rc;
   // x_out = x_mid + fc2(act); xn_out = LN_next(x_out)
-  SrkLnArgs lnn{d->C, d->C, next_norm_w, next_norm_b, a->stats_out, nullptr, 1e-5f};
+  SrkLnArgs lnn{d->C, d->C, next_norm_w, next_norm_b, a->stats_out, nullptr, 1e-5f, x ? x->drop_mlp : nullptr, g->H * g->W};
   if ((rc = srk_gemm_tn(SRK_EPI_RES_LN, T, Cp, Hp, a->act, Hp, w->fc2_f, Hp, a->x_out, Cp, a->xn_out, Cp, a->x_mid, Cp,
                         nullptr, 0, &lnn, stream)))
     return rc;
@@ -312,26 +312,37 @@ static int block_bwd_impl(const SrkBlockDims* d, const SrkGeom* g, const SrkBloc
   const WsLayout L = ws_layout(d, &g8);
   float* ws = s->wg_ws;
 
+  // stochastic depth: the branch sees s_b * g (per-sample factor); the residual path keeps g
+  auto scaled = [&](const void* gsrc, const float* factors) -> const void* {
+    if (factors == nullptr) return gsrc;
+    row_scale_kernel<<<num_sms() * 8, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(gsrc),
+                                                      static_cast<__nv_bfloat16*>(x->gs_buf), factors, T, Cp, g->H * g->W);
+    SRK_LAUNCHED(1);
+    return x->gs_buf;
+  };
+  if (x && (x->drop_attn || x->drop_mlp) && !x->gs_buf) return fail(SRK_ERR_ARG, "srk_hat_block_bwd: gs_buf is required with drop_*");
+  const void* g_mlp = scaled(g_out, x ? x->drop_mlp : nullptr);
   // dU = (g_out @ W2) * gelu'(u)
-  if ((rc = srk_gemm_tn(SRK_EPI_MUL, T, Hp, Cp, g_out, Cp, w->fc2_t, Cp, s->d_act, Hp, nullptr, 0, a->dact, Hp, nullptr,
+  if ((rc = srk_gemm_tn(SRK_EPI_MUL, T, Hp, Cp, g_mlp, Cp, w->fc2_t, Cp, s->d_act, Hp, nullptr, 0, a->dact, Hp, nullptr,
                         0, nullptr, stream_)))
     return rc;
   // dW2^T (+db2 in row `hidden`) = act^T @ g_out
   const int s_fc = wgrad_splits(T, Hp / 128);
-  if ((rc = srk_gemm_wgrad(T, Hp, Cp, a->act, Hp, g_out, Cp, ws + L.partials, s_fc, ws + L.ext_fc2, stream_))) return rc;
+  if ((rc = srk_gemm_wgrad(T, Hp, Cp, a->act, Hp, g_mlp, Cp, ws + L.partials, s_fc, ws + L.ext_fc2, stream_))) return rc;
   // g_mid = g_out + LN2bwd(dU @ W1)
-  SrkLnArgs ln2{d->C, -1, p->norm2_w, nullptr, a->stats2, ws + L.ln2, 1e-5f};
+  SrkLnArgs ln2{d->C, -1, p->norm2_w, nullptr, a->stats2, ws + L.ln2, 1e-5f, nullptr, 1};
   if ((rc = srk_gemm_tn(SRK_EPI_LNBWD, T, Cp, Hp, s->d_act, Hp, w->fc1_t, Hp, s->g_mid, Cp, nullptr, 0, a->x_mid, Cp,
                         g_out, Cp, &ln2, stream_)))
     return rc;
   // dW1 (+db1 in column C) = dU^T @ xn2
   if ((rc = srk_gemm_wgrad(T, Hp, Cp, s->d_act, Hp, a->xn2, Cp, ws + L.partials, s_fc, ws + L.ext_fc1, stream_))) return rc;
   // d_ao = g_mid @ Wproj
-  if ((rc = srk_gemm_tn(SRK_EPI_STORE, T, AW, Cp, s->g_mid, Cp, w->proj_t, Cp, s->d_ao, AW, nullptr, 0, nullptr, 0,
+  const void* g_att = scaled(s->g_mid, x ? x->drop_attn : nullptr);
+  if ((rc = srk_gemm_tn(SRK_EPI_STORE, T, AW, Cp, g_att, Cp, w->proj_t, Cp, s->d_ao, AW, nullptr, 0, nullptr, 0,
                         nullptr, 0, nullptr, stream_)))
     return rc;
   // dWproj (+dbproj in column dh) = g_mid^T @ ao
-  if ((rc = srk_gemm_wgrad(T, Cp, AW, s->g_mid, Cp, a->ao, AW, ws + L.partials, wgrad_splits(T, (Cp + 127) / 128),
+  if ((rc = srk_gemm_wgrad(T, Cp, AW, g_att, Cp, a->ao, AW, ws + L.partials, wgrad_splits(T, (Cp + 127) / 128),
                            ws + L.ext_proj, stream_)))
     return rc;
   // attention backward -> d_qkv, rpb-table gradient (ws 8: per-CTA partials folded by the unpack kernel below)
@@ -352,7 +363,7 @@ static int block_bwd_impl(const SrkBlockDims* d, const SrkGeom* g, const SrkBloc
       return rc;
   } else {
     // g_in = g_mid + LN1bwd(d_qkv @ Wqkv)
-    SrkLnArgs ln1{d->C, -1, p->norm1_w, nullptr, const_cast<float*>(a->stats1), ws + L.ln1, 1e-5f};
+    SrkLnArgs ln1{d->C, -1, p->norm1_w, nullptr, const_cast<float*>(a->stats1), ws + L.ln1, 1e-5f, nullptr, 1};
     if ((rc = srk_gemm_tn(SRK_EPI_LNBWD, T, Cp, QW, s->d_qkv, QW, w->qkv_t, QW, g_in, Cp, nullptr, 0, a->x_in, Cp,
                           s->g_mid, Cp, &ln1, stream_)))
       return rc;

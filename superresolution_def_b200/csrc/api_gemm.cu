@@ -62,10 +62,11 @@ extern "C" int srk_gemm_tn(int epi, int M, int N, int K, const void* A, int lda,
   GemmArgs a{};
   a.M = M; a.N = N; a.K = K;
   a.n_real = N; a.ones_col = -1; a.gamma = nullptr; a.beta = nullptr; a.stats = nullptr; a.partials = nullptr;
-  a.eps = 1e-5f;
+  a.eps = 1e-5f; a.row_scale = nullptr; a.rows_per_scale = 1;
   if (ln) {
     a.n_real = ln->n_real; a.ones_col = ln->ones_col; a.gamma = ln->gamma; a.beta = ln->beta;
     a.stats = ln->stats; a.partials = ln->partials; a.eps = ln->eps;
+    a.row_scale = ln->row_scale; a.rows_per_scale = ln->rows_per_scale > 0 ? ln->rows_per_scale : 1;
   }
   if ((epi == EPI_RES_LN || epi == EPI_LNBWD) && (!ln || !ln->gamma)) return fail(SRK_ERR_ARG, "LN epilogue needs SrkLnArgs");
   if (epi == EPI_LNBWD && (!ln->stats || !ln->partials || !X1 || !X2)) return fail(SRK_ERR_ARG, "LNBWD needs stats, partials, X1, X2");

@@ -164,6 +164,24 @@ static __global__ void unpack_block_grads_kernel(BlockDims d, UnpackSrc s, Block
   }
 }
 
+// ------------------------------------------------------------------ per-sample row scaling (stochastic depth backward)
+// out[r][:] = in[r][:] * scale[r / rows_per_scale]   (bf16 rows of `cols` elements, cols % 8 == 0)
+static __global__ void row_scale_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                        const float* __restrict__ scale, long long rows, int cols, int rows_per_scale) {
+  const int groups = cols / 8;
+  const long long total = rows * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / groups;
+    const float sc = scale[r / rows_per_scale];
+    const uint4 v = *reinterpret_cast<const uint4*>(in + i * 8);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[e] = pack_bf16(bf16_lo(w[e]) * sc, bf16_hi(w[e]) * sc);
+    *reinterpret_cast<uint4*>(out + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // ------------------------------------------------------------------ standalone LayerNorm (warp per row)
 // y = LN(x[:, :C]) * gamma + beta, y[:, C] = 1 (ones column, if ones_col >= 0), other pads 0; stats = (mean, rstd)
 static __global__ void ln_fwd_rows_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ y,

@@ -40,6 +40,8 @@ struct GemmArgs {
   float* stats;       // [M][2] (mean, rstd): written by EPI_RES_LN, read by EPI_LNBWD
   float* partials;    // EPI_LNBWD: [gridDim.x][2][BN] per-CTA column sums (dgamma, dbeta)
   float eps;
+  const float* row_scale;  // EPI_RES_LN, optional: per-sample stochastic-depth factor applied to bf16(acc)
+  int rows_per_scale;
 };
 
 template <int BN, int EPI>
@@ -370,6 +372,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ++aux_count;
         if constexpr (EPI == EPI_RES_LN) {
           float sum = 0.f;
+          const float rs = (args.row_scale != nullptr) ? args.row_scale[(m0 + row) / args.rows_per_scale] : 1.0f;
 #pragma unroll 1
           for (int c32 = half * NCH; c32 < (half + 1) * NCH; ++c32) {
             uint32_t r[32];
@@ -384,8 +387,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               uint32_t o[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float v0 = round_bf16(round_bf16(__uint_as_float(r[i * 8 + 2 * e])) + bf16_lo(rw[e]));
-                const float v1 = round_bf16(round_bf16(__uint_as_float(r[i * 8 + 2 * e + 1])) + bf16_hi(rw[e]));
+                const float v0 = round_bf16(round_bf16(__uint_as_float(r[i * 8 + 2 * e])) * rs + bf16_lo(rw[e]));
+                const float v1 = round_bf16(round_bf16(__uint_as_float(r[i * 8 + 2 * e + 1])) * rs + bf16_hi(rw[e]));
                 sum += v0 + v1;
                 o[e] = pack_bf16(v0, v1);
               }

@@ -70,11 +70,20 @@ class BucketedGradReducer:
 
 
 def swinir_grad_groups(net) -> list[list[torch.nn.Parameter]]:
-    """Reverse-execution-order parameter groups of a SwinIR-shaped module."""
+    """Reverse-execution-order parameter groups of a SwinIR- or HAT-shaped generator: tail convs + final norm, then
+    the residual groups last to first, then the head."""
     groups = [list(net.conv_last.parameters()) + list(net.upsample.parameters())
               + list(net.conv_before_upsample.parameters()) + list(net.conv_after_body.parameters())
               + list(net.norm.parameters())]
     for layer in reversed(list(net.layers)):
-        groups.append([p for blk in layer for p in blk.parameters()])
-    groups.append(list(net.conv_first.parameters()))
+        groups.append(list(layer.parameters()))
+    head = list(net.conv_first.parameters())
+    pe = getattr(net, "patch_embed", None)
+    if pe is not None:
+        head += list(pe.parameters())
+    groups.append(head)
+    seen = {id(p) for g in groups for p in g}
+    rest = [p for p in net.parameters() if id(p) not in seen]
+    if rest:
+        groups.append(rest)
     return groups

@@ -123,24 +123,31 @@ class HAB(nn.Module):
     def block_cfg(self) -> eng.BlockCfg:
         return heng.hat_block_cfg(self.dim, self.num_heads, self.mlp.fc1.out_features, self.window_size)
 
-    def _check_drop_path(self):
-        if self.training and isinstance(self.drop_path, DropPath) and (self.drop_path.drop_prob or 0.) > 0.:
-            raise capi.SrkError("stochastic depth inside the fused HAB/OCAB kernels is not implemented yet: construct "
-                                "HAT with drop_path_rate=0 for training, or call .eval()")
+    def _drop_factors(self, b, device):
+        """Per-sample stochastic-depth factors of the two residual branches (reference drop_path :11-23, applied at
+        :306-307): 0 or 1/keep_prob, drawn in the reference's order (attention branch first, then the MLP branch)."""
+        p = getattr(self.drop_path, "drop_prob", None) or 0.
+        if not self.training or p == 0.:
+            return None
+        keep = 1.0 - p
+        draw = lambda: ((keep + torch.rand(b, device=device)).floor_() / keep).float().contiguous()  # noqa: E731
+        return (draw(), draw())
 
-    def run(self, t, xn, stats, geom, next_norm):
-        """Token-major entry used by the model-level forward: (x, xn, stats) -> (x_out, xn_out, stats_out)."""
-        self._check_drop_path()
+    def run(self, t, xn, stats, geom, next_norm, drop=None):
+        """Token-major entry used by the model-level forward: (x, xn, stats) -> (x_out, xn_out, stats_out).
+        drop: optional explicit (attn_factors, mlp_factors) [B] tensors (tests); default: drawn when training."""
+        if drop is None:
+            drop = self._drop_factors(geom[0], t.device)
         return heng.HatBlockFunction.apply(t, xn, stats, self.block_cfg(), geom, "hab", self.shift_size,
-                                           self.conv_scale, *heng.hab_params_of(self), next_norm[0], next_norm[1])
+                                           self.conv_scale, drop, *heng.hab_params_of(self), next_norm[0], next_norm[1])
 
-    def forward(self, x, x_size, rpi_sa=None, attn_mask=None):
+    def forward(self, x, x_size, rpi_sa=None, attn_mask=None, drop=None):
         h, w = x_size
         b, _, c = x.shape
         cfg = self.block_cfg()
         tok = eng.pack_tokens(x, cfg.Cp)
         xn, stats = eng.layernorm_tokens(tok, self.norm1.weight, self.norm1.bias, c)
-        out, _, _ = self.run(tok, xn, stats, (b, h, w), eng.identity_norm(c, x.device))
+        out, _, _ = self.run(tok, xn, stats, (b, h, w), eng.identity_norm(c, x.device), drop=drop)
         return eng.unpack_tokens(out, b, c, x.dtype)
 
 
@@ -173,7 +180,7 @@ class OCAB(nn.Module):
         return heng.hat_block_cfg(self.dim, self.num_heads, self.mlp.fc1.out_features, self.window_size)
 
     def run(self, t, xn, stats, geom, next_norm):
-        return heng.HatBlockFunction.apply(t, xn, stats, self.block_cfg(), geom, "ocab", 0, 0.0,
+        return heng.HatBlockFunction.apply(t, xn, stats, self.block_cfg(), geom, "ocab", 0, 0.0, None,
                                            *heng.ocab_params_of(self), next_norm[0], next_norm[1])
 
     def forward(self, x, x_size, rpi=None):

@@ -66,7 +66,8 @@ class HatBlockFunction(torch.autograd.Function):
     The gradient returned for `x` is the complete dL/dx; `xn`/`stats` are derived data without gradient."""
 
     @staticmethod
-    def forward(ctx, x, xn, stats, cfg, geom, kind, shift, conv_scale, *tensors):
+    def forward(ctx, x, xn, stats, cfg, geom, kind, shift, conv_scale, drop, *tensors):
+        """drop: None, or (attn_factors, mlp_factors): fp32 [B] stochastic-depth factors (0 or 1/keep_prob) per sample."""
         B, H, W = geom
         T = B * H * W
         dev = x.device
@@ -100,7 +101,7 @@ class HatBlockFunction(torch.autograd.Function):
             scale = torch.empty(B, cfg.C, device=dev, dtype=torch.float32)
             xr = torch.empty_like(x)
             capi.cab_se_fwd(c2, x, B, H * W, cfg.C, S, s1w, s1b, s2w, s2b, float(conv_scale), pool, hidden, scale, xr)
-            capi.hat_block_fwd(dims, g, weights, pdict, nw, nb, acts, capi.ATTN_SELF, xr, lse)
+            capi.hat_block_fwd(dims, g, weights, pdict, nw, nb, acts, capi.ATTN_SELF, xr, lse, drop=drop or (None, None))
             extra = (c1, dc1, c2, pool, hidden, scale, Cm, Cm_p, S)
         elif kind == "ocab":
             capi.hat_block_fwd(dims, g, weights, pdict, nw, nb, acts, capi.ATTN_OCA, x, lse)
@@ -108,7 +109,7 @@ class HatBlockFunction(torch.autograd.Function):
             raise capi.SrkError(f"unknown HAT block kind {kind!r}")
         if need_grad:
             ctx.saved = (acts, lse, extra)
-            ctx.meta = (cfg, geom, kind, shift, float(conv_scale))
+            ctx.meta = (cfg, geom, kind, shift, float(conv_scale), drop)
             ctx.params = tensors
         ctx.mark_non_differentiable(acts["xn_out"], acts["stats_out"])
         ctx.set_materialize_grads(False)
@@ -117,7 +118,7 @@ class HatBlockFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_x, _g_xn, _g_stats):
         acts, lse, extra = ctx.saved
-        cfg, (B, H, W), kind, shift, conv_scale = ctx.meta
+        cfg, (B, H, W), kind, shift, conv_scale, drop = ctx.meta
         tensors = ctx.params
         T = B * H * W
         dev = g_x.device
@@ -141,7 +142,9 @@ class HatBlockFunction(torch.autograd.Function):
             c1w, c1b, c2w, c2b, s1w, s1b, s2w, s2b = tensors[13:21]
             ws = _attn_ws(geom, capi.ATTN_SELF, cfg.heads, dev)
             dxn1 = torch.empty(T, cfg.Cp, device=dev, dtype=BF16)
-            capi.hat_block_bwd(dims, geom, weights, pdict, acts, g, scratch, None, gdict, capi.ATTN_SELF, lse, ws, d_xn1=dxn1)
+            gs_buf = torch.empty(T, cfg.Cp, device=dev, dtype=BF16) if drop else None
+            capi.hat_block_bwd(dims, geom, weights, pdict, acts, g, scratch, None, gdict, capi.ATTN_SELF, lse, ws, d_xn1=dxn1,
+                               drop=drop or (None, None), gs_buf=gs_buf)
             g_mid = scratch["g_mid"]
             # CAB backward: channel attention, conv2, GELU, conv1 (input gradient accumulated onto the attention path)
             d_c2 = torch.empty(T, cfg.Cp, device=dev, dtype=BF16)
@@ -171,7 +174,7 @@ class HatBlockFunction(torch.autograd.Function):
         for j, n in enumerate(capi.PARAM_NAMES):
             grads[j] = gdict[n]
         ctx.saved = None
-        return (g_in, None, None, None, None, None, None, None, *grads)
+        return (g_in, None, None, None, None, None, None, None, None, *grads)
 
 
 class RhagConvFunction(torch.autograd.Function):

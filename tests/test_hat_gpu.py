@@ -155,6 +155,31 @@ def test_hab_matches_oracle(shift):
     assert not bad, bad
 
 
+def test_hab_stochastic_depth_matches_oracle():
+    """Training-mode HAB with explicit per-sample drop-path factors (one sample dropped in each branch)."""
+    from superresolution_def_b200.hat_arch import HAB
+    ho = _ho()
+    torch.manual_seed(9)
+    B, R, C, heads = 3, 32, 180, 6
+    blk = randomize_(HAB(C, (R, R), heads, window_size=16, shift_size=8, drop_path=0.25), seed=10).cuda().train()
+    x = torch.randn(B, R * R, C, device="cuda")
+    xr, xm = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    drop = (torch.tensor([1 / 0.75, 0.0, 1 / 0.75], device="cuda"), torch.tensor([0.0, 1 / 0.75, 1 / 0.75], device="cuda"))
+    sd = _sd_of(blk)
+    ref = ho.hab(xr, sd, "", (R, R), heads, 16, 8, ho.rpi_sa(16).cuda(), ho.shift_mask(R, R, 16, 8).cuda(), drop=drop)
+    got = blk(xm, (R, R), None, None, drop=drop)
+    assert rel_l2(got, ref) < OUT_TOL, rel_l2(got, ref)
+    w = torch.randn_like(ref)
+    (ref * w).sum().backward()
+    (got * w).sum().backward()
+    assert rel_l2(xm.grad, xr.grad) < GRAD_TOL, rel_l2(xm.grad, xr.grad)
+    bad = {n: round(rel_l2(p.grad, sd[n].grad), 4) for n, p in blk.named_parameters() if rel_l2(p.grad, sd[n].grad) > GRAD_TOL}
+    assert not bad, bad
+    # and the module draws its own factors in training mode without error
+    out = blk(x, (R, R), None, None)
+    assert torch.isfinite(out).all()
+
+
 def test_ocab_matches_oracle():
     from superresolution_def_b200.hat_arch import OCAB
     ho = _ho()

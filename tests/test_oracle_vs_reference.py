@@ -97,3 +97,32 @@ def test_hat_module_schema_matches_reference():
     mine.load_state_dict(a, strict=True)
     assert all(torch.equal(a[k], b[k]) for k in a if "index" in k)
     assert torch.equal(ref.calculate_mask((64, 48)), mine.calculate_mask((64, 48)))
+
+
+def test_hab_drop_path_matches_reference_rng_order():
+    """Training-mode HAB with stochastic depth: the oracle, fed the factors obtained by replaying the reference's two
+    torch.rand draws (attention branch, then MLP branch), reproduces the reference output and gradients."""
+    from tools import ref_shim
+    from oracle import hat_oracle as ho
+    m = ref_shim.hat_module()
+    blk = randomize_(m.HAB(36, (8, 8), 3, window_size=4, shift_size=2, compress_ratio=3, squeeze_factor=6, drop_path=0.4),
+                     seed=5).train()
+    hat = m.HAT(img_size=8, in_chans=1, embed_dim=36, depths=(1,), num_heads=(3,), window_size=4, squeeze_factor=6,
+                upsampler="pixelshuffle")
+    rpi, mask = hat.relative_position_index_SA, hat.calculate_mask((8, 8))
+    x = torch.randn(6, 64, 36, requires_grad=True)
+    torch.manual_seed(123)
+    y = blk(x, (8, 8), rpi, mask)
+    torch.manual_seed(123)
+    keep = 0.6
+    drop = tuple(((keep + torch.rand((6, 1, 1))).floor_() / keep).reshape(6) for _ in range(2))
+    assert 0 < sum(int((d == 0).sum()) for d in drop) < 12      # both kept and dropped samples occur
+    w = torch.randn_like(y)
+    (y * w).sum().backward()
+    sd = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in blk.state_dict().items()}
+    x2 = x.detach().clone().requires_grad_(True)
+    y2 = ho.hab(x2, sd, "", (8, 8), 3, 4, 2, rpi, mask, drop=drop)
+    (y2 * w).sum().backward()
+    assert rel_l2(y2, y) < 1e-5 and rel_l2(x2.grad, x.grad) < 1e-4
+    for n, p in blk.named_parameters():
+        assert rel_l2(sd[n].grad, p.grad) < 2e-4, n

@@ -220,10 +220,13 @@ extern "C" int srk_conv_out1_bwd(const float* dy, const void* x, const float* w,
                                  int B, int H, int W, int C, void* stream_) {
   if (C != 64) return fail(SRK_ERR_UNSUPPORTED, "conv_out1: 64 input channels");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  conv_out1_dgrad_kernel<64><<<num_sms() * 8, 256, 0, stream>>>(dy, w, static_cast<__nv_bfloat16*>(dx), B, H, W);
+  const bool small = (long long)B * H * W * 8 < (1LL << 31);
+  if (small) conv_out1_dgrad_kernel<64, int><<<num_sms() * 8, 256, 0, stream>>>(dy, w, static_cast<__nv_bfloat16*>(dx), B, H, W);
+  else conv_out1_dgrad_kernel<64, long long><<<num_sms() * 8, 256, 0, stream>>>(dy, w, static_cast<__nv_bfloat16*>(dx), B, H, W);
   SRK_LAUNCHED(1);
   const int grid = num_sms() * 2;
-  conv_out1_wgrad_kernel<64><<<grid, 256, 0, stream>>>(dy, static_cast<const __nv_bfloat16*>(x), ws, B, H, W);
+  if (small) conv_out1_wgrad_kernel<64, int><<<grid, 256, 0, stream>>>(dy, static_cast<const __nv_bfloat16*>(x), ws, B, H, W);
+  else conv_out1_wgrad_kernel<64, long long><<<grid, 256, 0, stream>>>(dy, static_cast<const __nv_bfloat16*>(x), ws, B, H, W);
   SRK_LAUNCHED(1);
   colsum_finish_kernel<<<(64 * 9 + 1 + 127) / 128, 128, 0, stream>>>(ws, grid, 64 * 9 + 1, ws + (size_t)grid * (64 * 9 + 1), 64 * 9 + 1);
   SRK_LAUNCHED(1);

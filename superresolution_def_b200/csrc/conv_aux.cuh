@@ -254,24 +254,24 @@ static __global__ void conv_out1_fwd_kernel(const __nv_bfloat16* __restrict__ x,
 }
 
 // dX[p][c] = sum_tap dY[p - off(tap)] * w[c][tap]   (dY fp32 [B,H,W], dX NHWC bf16); HBM-write bound.
-template <int C>
+template <int C, typename Idx>   // Idx = int whenever B*H*W*C/8 < 2^31: 64-bit div/mod costs ~10x the useful work here
 static __global__ void conv_out1_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
                                        __nv_bfloat16* __restrict__ dx, int B, int H, int W) {
   __shared__ __align__(16) float s_w[9][C];
   for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) s_w[i / C][i % C] = w[(i % C) * 9 + i / C];
   __syncthreads();
   constexpr int G = C / 8;
-  const long long total = (long long)B * H * W * G;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+  const Idx total = (Idx)B * H * W * G;
+  for (Idx idx = (Idx)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (Idx)gridDim.x * blockDim.x) {
     const int g = int(idx % G);
-    const long long p = idx / G;
+    const Idx p = idx / G;
     const int xx = int(p % W), yy = int((p / W) % H);
     float d[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       // output pixel q = p - off(tap) received x[p] through tap t
       const int sy = yy - (t / 3 - 1), sx = xx - (t % 3 - 1);
-      d[t] = (sy >= 0 && sy < H && sx >= 0 && sx < W) ? __ldg(dy + p - (long long)(t / 3 - 1) * W - (t % 3 - 1)) : 0.f;
+      d[t] = (sy >= 0 && sy < H && sx >= 0 && sx < W) ? __ldg(dy + p - (Idx)(t / 3 - 1) * W - (t % 3 - 1)) : 0.f;
     }
     float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -281,13 +281,13 @@ static __global__ void conv_out1_dgrad_kernel(const float* __restrict__ dy, cons
       o[0] = fmaf(d[t], w0.x, o[0]); o[1] = fmaf(d[t], w0.y, o[1]); o[2] = fmaf(d[t], w0.z, o[2]); o[3] = fmaf(d[t], w0.w, o[3]);
       o[4] = fmaf(d[t], w1.x, o[4]); o[5] = fmaf(d[t], w1.y, o[5]); o[6] = fmaf(d[t], w1.z, o[6]); o[7] = fmaf(d[t], w1.w, o[7]);
     }
-    *reinterpret_cast<uint4*>(dx + p * C + g * 8) =
+    *reinterpret_cast<uint4*>(dx + (size_t)p * C + g * 8) =
         make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
   }
 }
 
 // dW[c][tap] = sum_p dY[p] * x[p + off(tap)][c], db = sum_p dY[p]; partial[blockIdx][C*9 + 1]
-template <int C>
+template <int C, typename Idx>
 static __global__ void conv_out1_wgrad_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                                        float* __restrict__ partial, int B, int H, int W) {
   __shared__ float s_acc[C * 9 + 1];
@@ -301,15 +301,15 @@ static __global__ void conv_out1_wgrad_kernel(const float* __restrict__ dy, cons
 #pragma unroll
     for (int t = 0; t < 9; ++t) acc[e][t] = 0.f;
   float accb = 0.f;
-  const long long npix = (long long)B * H * W;
-  const long long pstride = (long long)gridDim.x * ppb;
-  long long p = (long long)blockIdx.x * ppb + pl;
+  const Idx npix = (Idx)B * H * W;
+  const Idx pstride = (Idx)gridDim.x * ppb;
+  Idx p = (Idx)blockIdx.x * ppb + pl;
   uint4 v_next = make_uint4(0u, 0u, 0u, 0u);
-  if (p < npix) v_next = *reinterpret_cast<const uint4*>(x + p * C + g * 8);
+  if (p < npix) v_next = *reinterpret_cast<const uint4*>(x + (size_t)p * C + g * 8);
   for (; p < npix; p += pstride) {
     // gather form: input pixel p contributes to output pixel q = p - off(tap) through tap t
     const uint4 v = v_next;
-    if (p + pstride < npix) v_next = *reinterpret_cast<const uint4*>(x + (p + pstride) * C + g * 8);  // prefetch
+    if (p + pstride < npix) v_next = *reinterpret_cast<const uint4*>(x + (size_t)(p + pstride) * C + g * 8);  // prefetch
     const int xx = int(p % W), yy = int((p / W) % H);
     const uint32_t vw[4] = {v.x, v.y, v.z, v.w};
     float xv[8];
@@ -320,7 +320,7 @@ static __global__ void conv_out1_wgrad_kernel(const float* __restrict__ dy, cons
     for (int t = 0; t < 9; ++t) {
       const int sy = yy - (t / 3 - 1), sx = xx - (t % 3 - 1);
       if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
-        const float d = __ldg(dy + p - (long long)(t / 3 - 1) * W - (t % 3 - 1));
+        const float d = __ldg(dy + p - (Idx)(t / 3 - 1) * W - (t % 3 - 1));
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e][t] = fmaf(d, xv[e], acc[e][t]);
       }

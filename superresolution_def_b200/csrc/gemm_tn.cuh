@@ -131,8 +131,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_slot = bar_base + 8u * (2 * S + 6);
   const uint32_t red_base = bar_base + 512;
 
-  __shared__ float s_gamma[256];
-  __shared__ float s_beta[256];
+  __shared__ __align__(16) float s_gamma[256];
+  __shared__ __align__(16) float s_beta[256];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -163,7 +163,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if constexpr (EPI == EPI_RES_LN || EPI == EPI_LNBWD) {
     for (int i = threadIdx.x; i < 256; i += Cfg::kThreads) {
       s_gamma[i] = (i < args.n_real) ? args.gamma[i] : 0.f;
-      s_beta[i] = (i < args.n_real && args.beta != nullptr) ? args.beta[i] : 0.f;
+      s_beta[i] = (i < args.n_real) ? (args.beta != nullptr ? args.beta[i] : 0.f) : (i == args.ones_col ? 1.f : 0.f);
     }
   }
   tc_fence_before();
@@ -364,6 +364,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       } else {
         // ---------------------------------------------------------- full-row epilogues (BN covers the row)
+        // A thread owns one accumulator row (tcgen05.ld 32x32b) and half of its columns; the other half lives in the
+        // warp 4 positions up, so row reductions cross warps through s_red.  Pad columns (>= n_real) hold exact zeros
+        // in the accumulator and in every aux tile (zero weight rows / zero pad activations), which lets the hot loops
+        // run without per-element column tests.
         const uint32_t T0 = epi_base;                      // RES_LN: residual -> v ; LNBWD: x (LN input)
         const uint32_t T1 = epi_base + NBOX * BOX_BYTES;   // RES_LN: LN output   ; LNBWD: dres -> out
         const float inv_n = 1.0f / float(args.n_real);
@@ -371,10 +375,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(aux_bar(0), aux_count & 1u);
         ++aux_count;
         if constexpr (EPI == EPI_RES_LN) {
-          float sum = 0.f;
           const float rs = (args.row_scale != nullptr) ? args.row_scale[(m0 + row) / args.rows_per_scale] : 1.0f;
-#pragma unroll 1
-          for (int c32 = half * NCH; c32 < (half + 1) * NCH; ++c32) {
+          uint32_t vp[NCH * 16];  // this thread's half row of v = bf16(bf16(acc) * rs + residual), packed pairs
+          float sum = 0.f;
+#pragma unroll
+          for (int ci = 0; ci < NCH; ++ci) {
+            const int c32 = half * NCH + ci;
             uint32_t r[32];
             tmem_ld_x32(taddr + uint32_t(c32 * 32), r);
             tmem_ld_wait();
@@ -384,15 +390,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const uint32_t addr = T0 + (c >> 6) * BOX_BYTES + swz(row, (c & 63) >> 3);
               const uint4 rv = lds128(addr);
               const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-              uint32_t o[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float v0 = round_bf16(round_bf16(__uint_as_float(r[i * 8 + 2 * e])) * rs + bf16_lo(rw[e]));
-                const float v1 = round_bf16(round_bf16(__uint_as_float(r[i * 8 + 2 * e + 1])) * rs + bf16_hi(rw[e]));
-                sum += v0 + v1;
-                o[e] = pack_bf16(v0, v1);
+                const uint32_t a = pack_bf16(__uint_as_float(r[i * 8 + 2 * e]), __uint_as_float(r[i * 8 + 2 * e + 1]));
+                const uint32_t pv = pack_bf16(fmaf(bf16_lo(a), rs, bf16_lo(rw[e])), fmaf(bf16_hi(a), rs, bf16_hi(rw[e])));
+                vp[ci * 16 + i * 4 + e] = pv;
+                sum += bf16_lo(pv) + bf16_hi(pv);
               }
-              sts128(addr, make_uint4(o[0], o[1], o[2], o[3]));
+              sts128(addr, make_uint4(vp[ci * 16 + i * 4], vp[ci * 16 + i * 4 + 1], vp[ci * 16 + i * 4 + 2],
+                                      vp[ci * 16 + i * 4 + 3]));
             }
           }
           tc_fence_before();
@@ -401,64 +407,70 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           s_red[(0 * 2 + half) * 128 + row] = sum;
           fence_proxy_async();
           named_bar_sync(1, Cfg::kEpiThreads);
-          if (elected) {  // v (= new residual stream) is complete in T0
+          if (elected) {  // v (= new residual stream) is complete in T0; nobody reads T0 again (v stays in registers)
             for (int b = 0; b < NBOX; ++b) tma_store_2d(&tmC, T0 + b * BOX_BYTES, n0 + b * 64, m0);
             tma_store_commit();
+            tma_store_wait_read<0>();  // v and the previous tile's LN output have left shared memory
+            if (next_tile < num_tiles) {  // prefetch the next tile's residual under this tile's passes 2 and 3
+              const int nm0 = (next_tile / n_tiles) * GEMM_BM, nn0 = (next_tile % n_tiles) * BN;
+              mbar_arrive_expect_tx(aux_bar(0), NBOX * BOX_BYTES);
+              for (int b = 0; b < NBOX; ++b) tma_load_2d(T0 + b * BOX_BYTES, &tmX1, aux_bar(0), nn0 + b * 64, nm0);
+            }
           }
           const float mean = (s_red[(0 * 2 + 0) * 128 + row] + s_red[(0 * 2 + 1) * 128 + row]) * inv_n;
           float var = 0.f;
-#pragma unroll 1
-          for (int c = c_begin; c < c_end; c += 8) {
-            const uint4 xv = lds128(T0 + (c >> 6) * BOX_BYTES + swz(row, (c & 63) >> 3));
-            const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float d0 = bf16_lo(xw[e]) - mean, d1 = bf16_hi(xw[e]) - mean;
-              if (c + 2 * e < args.n_real) var += d0 * d0;
-              if (c + 2 * e + 1 < args.n_real) var += d1 * d1;
-            }
+          for (int k = 0; k < NCH * 16; ++k) {
+            const float d0 = bf16_lo(vp[k]) - mean, d1 = bf16_hi(vp[k]) - mean;
+            var = fmaf(d0, d0, var);
+            var = fmaf(d1, d1, var);
+          }
+          {  // pad columns contributed (0 - mean)^2 each
+            const int lo = c_begin > args.n_real ? c_begin : args.n_real;
+            const int npad = c_end > lo ? c_end - lo : 0;
+            var -= float(npad) * mean * mean;
           }
           s_red[(1 * 2 + half) * 128 + row] = var;
           named_bar_sync(1, Cfg::kEpiThreads);
           var = s_red[(1 * 2 + 0) * 128 + row] + s_red[(1 * 2 + 1) * 128 + row];
-          const float rstd = rsqrtf(var * inv_n + args.eps);
+          const float rstd = rsqrtf(fmaxf(var, 0.f) * inv_n + args.eps);
           if (half == 0 && args.stats != nullptr)
             reinterpret_cast<float2*>(args.stats)[m0 + row] = make_float2(mean, rstd);
-#pragma unroll 1
-          for (int c = c_begin; c < c_end; c += 8) {
-            const uint32_t boff = (c >> 6) * BOX_BYTES + swz(row, (c & 63) >> 3);
-            const uint4 xv = lds128(T0 + boff);
-            const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
-            float y[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int cc = c + e;
-              const float x = (e & 1) ? bf16_hi(xw[e >> 1]) : bf16_lo(xw[e >> 1]);
-              float o = (x - mean) * rstd * s_gamma[cc & 255] + s_beta[cc & 255];
-              if (cc >= args.n_real) o = (cc == args.ones_col) ? 1.0f : 0.0f;
-              y[e] = o;
+          for (int ci = 0; ci < NCH; ++ci) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int c = (half * NCH + ci) * 32 + i * 8;
+              const uint32_t boff = (c >> 6) * BOX_BYTES + swz(row, (c & 63) >> 3);
+              // pad columns: s_gamma = 0, s_beta = (column == ones_col) -> the affine below yields exactly 0 / 1 there
+              const float4 g0 = *reinterpret_cast<const float4*>(&s_gamma[c]), g1 = *reinterpret_cast<const float4*>(&s_gamma[c + 4]);
+              const float4 b0 = *reinterpret_cast<const float4*>(&s_beta[c]), b1 = *reinterpret_cast<const float4*>(&s_beta[c + 4]);
+              const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+              uint32_t o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const uint32_t pv = vp[ci * 16 + i * 4 + e];
+                const float y0 = fmaf((bf16_lo(pv) - mean) * rstd, gg[2 * e], bb[2 * e]);
+                const float y1 = fmaf((bf16_hi(pv) - mean) * rstd, gg[2 * e + 1], bb[2 * e + 1]);
+                o[e] = pack_bf16(y0, y1);
+              }
+              sts128(T1 + boff, make_uint4(o[0], o[1], o[2], o[3]));
             }
-            sts128(T1 + boff, make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]),
-                                         pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7])));
           }
           fence_proxy_async();
           named_bar_sync(1, Cfg::kEpiThreads);
           if (elected) {
             for (int b = 0; b < NBOX; ++b) tma_store_2d(&tmC2, T1 + b * BOX_BYTES, n0 + b * 64, m0);
             tma_store_commit();
-            tma_store_wait_read<0>();
-            if (next_tile < num_tiles) {
-              const int nm0 = (next_tile / n_tiles) * GEMM_BM, nn0 = (next_tile % n_tiles) * BN;
-              mbar_arrive_expect_tx(aux_bar(0), NBOX * BOX_BYTES);
-              for (int b = 0; b < NBOX; ++b) tma_load_2d(T0 + b * BOX_BYTES, &tmX1, aux_bar(0), nn0 + b * 64, nm0);
-            }
           }
         } else {  // EPI_LNBWD
           const float2 st = reinterpret_cast<const float2*>(args.stats)[m0 + row];
           const float mean = st.x, rstd = st.y;
           float s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-          for (int c32 = half * NCH; c32 < (half + 1) * NCH; ++c32) {
+#pragma unroll
+          for (int ci = 0; ci < NCH; ++ci) {
+            const int c32 = half * NCH + ci;
             uint32_t r[32];
             tmem_ld_x32(taddr + uint32_t(c32 * 32), r);
             tmem_ld_wait();
@@ -468,33 +480,31 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const int c = c32 * 32 + i * 8;
               const uint4 xv = lds128(T0 + (c >> 6) * BOX_BYTES + swz(row, (c & 63) >> 3));
               const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+              const float4 g0 = *reinterpret_cast<const float4*>(&s_gamma[c]), g1 = *reinterpret_cast<const float4*>(&s_gamma[c + 4]);
+              const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const int cc = c + e;
-                const float x = (e & 1) ? bf16_hi(xw[e >> 1]) : bf16_lo(xw[e >> 1]);
-                const float xhat = (x - mean) * rstd;
-                float dxn = round_bf16(__uint_as_float(r[i * 8 + e]));
-                if (cc >= args.n_real) dxn = 0.f;
-                const float dxh = dxn * s_gamma[cc & 255];
-                s1 += dxh;
-                s2 += dxh * xhat;
-                pg[i * 8 + e] = dxn * xhat;
-                pb[i * 8 + e] = dxn;
+              for (int e = 0; e < 4; ++e) {
+                const uint32_t a = pack_bf16(__uint_as_float(r[i * 8 + 2 * e]), __uint_as_float(r[i * 8 + 2 * e + 1]));
+                const float d0 = bf16_lo(a), d1 = bf16_hi(a);   // dxn = bf16(acc); exact 0 in pad columns
+                const float h0 = (bf16_lo(xw[e]) - mean) * rstd, h1 = (bf16_hi(xw[e]) - mean) * rstd;
+                const float q0 = d0 * gg[2 * e], q1 = d1 * gg[2 * e + 1];
+                s1 += q0 + q1;
+                s2 = fmaf(q0, h0, fmaf(q1, h1, s2));
+                pg[i * 8 + 2 * e] = d0 * h0; pg[i * 8 + 2 * e + 1] = d1 * h1;
+                pb[i * 8 + 2 * e] = d0;      pb[i * 8 + 2 * e + 1] = d1;
               }
             }
-            const float cg = warp_colsum32(pg, lane);
-            const float cb = warp_colsum32(pb, lane);
-#pragma unroll
-            for (int k = 0; k < NCH; ++k)
-              if (k == c32 - half * NCH) { acc_g[k] += cg; acc_b[k] += cb; }
+            acc_g[ci] += warp_colsum32(pg, lane);
+            acc_b[ci] += warp_colsum32(pb, lane);
           }
           s_red[(0 * 2 + half) * 128 + row] = s1;
           s_red[(1 * 2 + half) * 128 + row] = s2;
           named_bar_sync(1, Cfg::kEpiThreads);
           const float c1 = (s_red[(0 * 2 + 0) * 128 + row] + s_red[(0 * 2 + 1) * 128 + row]) * inv_n;
           const float c2 = (s_red[(1 * 2 + 0) * 128 + row] + s_red[(1 * 2 + 1) * 128 + row]) * inv_n;
-#pragma unroll 1
-          for (int c32 = half * NCH; c32 < (half + 1) * NCH; ++c32) {
+#pragma unroll
+          for (int ci = 0; ci < NCH; ++ci) {
+            const int c32 = half * NCH + ci;
             uint32_t r[32];
             tmem_ld_x32(taddr + uint32_t(c32 * 32), r);
             tmem_ld_wait();
@@ -506,19 +516,26 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const uint4 dv = lds128(T1 + boff);
               const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
               const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w};
-              float o[8];
+              const float4 g0 = *reinterpret_cast<const float4*>(&s_gamma[c]), g1 = *reinterpret_cast<const float4*>(&s_gamma[c + 4]);
+              const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+              uint32_t o[4];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const int cc = c + e;
-                const float x = (e & 1) ? bf16_hi(xw[e >> 1]) : bf16_lo(xw[e >> 1]);
-                const float dres = (e & 1) ? bf16_hi(dw[e >> 1]) : bf16_lo(dw[e >> 1]);
-                const float xhat = (x - mean) * rstd;
-                const float dxn = round_bf16(__uint_as_float(r[i * 8 + e]));
-                const float dx = rstd * (dxn * s_gamma[cc & 255] - c1 - xhat * c2);
-                o[e] = (cc < args.n_real) ? (dres + round_bf16(dx)) : 0.f;
+              for (int e = 0; e < 4; ++e) {
+                const uint32_t a = pack_bf16(__uint_as_float(r[i * 8 + 2 * e]), __uint_as_float(r[i * 8 + 2 * e + 1]));
+                const float h0 = (bf16_lo(xw[e]) - mean) * rstd, h1 = (bf16_hi(xw[e]) - mean) * rstd;
+                const float x0 = rstd * (fmaf(bf16_lo(a), gg[2 * e], -c1) - h0 * c2);
+                const float x1 = rstd * (fmaf(bf16_hi(a), gg[2 * e + 1], -c1) - h1 * c2);
+                const uint32_t dx = pack_bf16(x0, x1);   // LayerNorm input gradient, rounded like the reference's bf16 tensor
+                o[e] = pack_bf16(bf16_lo(dw[e]) + bf16_lo(dx), bf16_hi(dw[e]) + bf16_hi(dx));
               }
-              sts128(T1 + boff, make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]),
-                                           pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7])));
+              if (c + 8 > args.n_real) {  // group touches pad columns: they must stay exactly zero
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  if (c + 2 * e >= args.n_real) o[e] &= 0xFFFF0000u;
+                  if (c + 2 * e + 1 >= args.n_real) o[e] &= 0x0000FFFFu;
+                }
+              }
+              sts128(T1 + boff, make_uint4(o[0], o[1], o[2], o[3]));
             }
           }
           tc_fence_before();
@@ -538,9 +555,6 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
-        // s_red is rewritten by the next tile only after its first named barrier... not guaranteed: a fast
-        // thread could overwrite s_red[0] while a slow one still reads it, so close the tile with a barrier.
-        named_bar_sync(1, Cfg::kEpiThreads);
       }
     }
     if constexpr (EPI == EPI_LNBWD) {

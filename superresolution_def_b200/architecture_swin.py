@@ -200,7 +200,7 @@ class SwinIR(nn.Module):
             raise capi.SrkError(f"padded input {H}x{W} != img_size {blocks[0].input_resolution} (reference :128 fails too)")
         cfg = blocks[0].block_cfg()
         C = self.embed_dim
-        out_dtype = torch.bfloat16 if torch.is_autocast_enabled() else x.dtype
+        out_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x.dtype
 
         # conv_first -> token-major bf16 residual stream [T, Cp]
         first = cv.conv3x3_tokens(x, self.conv_first.weight, self.conv_first.bias, cfg.Cp)          # [T, Cp]

@@ -69,7 +69,12 @@ class CAB(nn.Module):
                                  ChannelAttention(num_feat, squeeze_factor))
 
     def forward(self, x):
-        raise capi.SrkError("CAB runs fused inside HAB.forward on token-major activations; call HAB instead")
+        """x: (B, C, H, W) as in the reference (:73); inside HAB.forward the same kernels run on token-major data."""
+        if not x.is_cuda:
+            raise capi.SrkError("libsrk CAB runs on CUDA only")
+        ca = self.cab[3].attention
+        return heng.CabFunction.apply(x, self.cab[0].weight, self.cab[0].bias, self.cab[2].weight, self.cab[2].bias,
+                                      ca[1].weight, ca[1].bias, ca[3].weight, ca[3].bias)
 
 
 class WindowAttention(nn.Module):
@@ -91,9 +96,17 @@ class WindowAttention(nn.Module):
         if not qkv_bias or qk_scale is not None or attn_drop != 0. or proj_drop != 0.:
             raise capi.SrkError("libsrk WindowAttention: qkv_bias=True, default scale, no dropout (reference usage)")
 
-    def forward(self, x, rpi, mask=None):
-        raise capi.SrkError("HAT's WindowAttention runs fused inside HAB.forward (window partition, shift and mask are "
-                            "address arithmetic there); call HAB instead")
+    def forward(self, x, rpi=None, mask=None):
+        """x: (num_windows*b, 256, c) already-partitioned 16x16 windows (reference :165).  `rpi` is accepted for signature
+        parity (the index is a pure function of the window size).  An explicit `mask` tensor is not supported here: the
+        shift mask only exists inside HAB.forward, where the kernel derives it from coordinates."""
+        if mask is not None:
+            raise capi.SrkError("libsrk WindowAttention.forward: pass mask=None; the shifted-window mask is applied "
+                                "inside HAB.forward (computed in-kernel from coordinates)")
+        if not x.is_cuda:
+            raise capi.SrkError("libsrk WindowAttention runs on CUDA only")
+        return eng.window_attention_forward(x, self.window_size[0], self.num_heads, self.relative_position_bias_table,
+                                            self.qkv.weight, self.qkv.bias, self.proj.weight, self.proj.bias)
 
 
 class HAB(nn.Module):
@@ -397,7 +410,7 @@ class HAT(nn.Module):
             raise capi.SrkError(f"input {H}x{W} is not a multiple of the window size {ws} (the reference fails too)")
         C = self.embed_dim
         cfg = self.layers[0].residual_group.blocks[0].block_cfg()
-        out_dtype = torch.bfloat16 if torch.is_autocast_enabled() else x.dtype
+        out_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x.dtype
         geom = (B, H, W)
         # (x - mean) * img_range is the identity for in_chans == 1, img_range == 1 (reference :972-973)
         xin = x if self.img_range == 1. else x * self.img_range

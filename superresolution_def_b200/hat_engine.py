@@ -229,3 +229,71 @@ class LayerNormTokensFunction(torch.autograd.Function):
         dgamma, dbeta = torch.empty_like(weight), torch.empty_like(weight)
         capi.layernorm_bwd(dy, x, stats, weight.detach(), None, dx, dgamma, dbeta, ctx.C)
         return dx, dgamma, dbeta, None, None
+
+
+class CabFunction(torch.autograd.Function):
+    """Stand-alone CAB.forward on an NCHW tensor (reference CAB / ChannelAttention, hat_arch.py:40-74): conv3x3 -> GELU ->
+    conv3x3 -> x * sigmoid(W2 relu(W1 avgpool(x))).  Same kernels as the fused HAB path; only the NCHW <-> token-major
+    packing is done with torch indexing."""
+
+    @staticmethod
+    def forward(ctx, x, c1w, c1b, c2w, c2b, s1w, s1b, s2w, s2b):
+        B, C, H, W = x.shape
+        if C >= 192 or H % 8 or W % 16:
+            raise capi.SrkError("libsrk CAB: fewer than 192 channels, H % 8 == 0, W % 16 == 0")
+        dev, T, Cp = x.device, B * H * W, 192
+        Cm, S = c1w.shape[0], s1w.shape[0]
+        Cm_p = cv._pad64(Cm)
+        for t in (c1w, c1b, c2w, c2b, s1w, s1b, s2w, s2b):
+            eng._check_param(t)
+        xt = torch.zeros(T, Cp, device=dev, dtype=BF16)
+        xt[:, :C] = x.permute(0, 2, 3, 1).reshape(T, C).to(BF16)
+        wf1, _, bp1 = cv.conv_weights(c1w, c1b, Cm_p, Cp)
+        wf2, _, bp2 = cv.conv_weights(c2w, c2b, Cp, Cm_p)
+        c1 = torch.empty(T, Cm_p, device=dev, dtype=BF16)
+        dc1 = torch.empty_like(c1)
+        capi.conv3x3_igemm(capi.CEPI_BIAS_GELU, B, H, W, Cp, Cm_p, Cm, xt, wf1, bp1, c1, y2=dc1)
+        c2 = torch.empty(T, Cp, device=dev, dtype=BF16)
+        capi.conv3x3_igemm(capi.CEPI_BIAS, B, H, W, Cm_p, Cp, C, c1, wf2, bp2, c2)
+        pool = torch.empty(B, C, device=dev, dtype=torch.float32)
+        hidden = torch.empty(B, S, device=dev, dtype=torch.float32)
+        scale = torch.empty(B, C, device=dev, dtype=torch.float32)
+        zero = torch.zeros(T, Cp, device=dev, dtype=BF16)
+        out = torch.empty(T, Cp, device=dev, dtype=BF16)
+        capi.cab_se_fwd(c2, zero, B, H * W, C, S, s1w.detach(), s1b.detach(), s2w.detach(), s2b.detach(), 1.0, pool, hidden,
+                        scale, out)
+        ctx.saved = (xt, c1, dc1, c2, pool, hidden, scale)
+        ctx.meta = (B, C, H, W, Cm, Cm_p, S, x.dtype)
+        ctx.params = (c1w, c1b, c2w, c2b, s1w, s1b, s2w, s2b)
+        return out[:, :C].reshape(B, H, W, C).permute(0, 3, 1, 2).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xt, c1, dc1, c2, pool, hidden, scale = ctx.saved
+        B, C, H, W, Cm, Cm_p, S, dtype = ctx.meta
+        c1w, c1b, c2w, c2b, s1w, s1b, s2w, s2b = ctx.params
+        dev, T, Cp = dy.device, B * H * W, 192
+        g = torch.zeros(T, Cp, device=dev, dtype=BF16)
+        g[:, :C] = dy.permute(0, 2, 3, 1).reshape(T, C).to(BF16)
+        d_c2 = torch.empty(T, Cp, device=dev, dtype=BF16)
+        ds1w, ds1b, ds2w, ds2b = (torch.empty_like(t) for t in (s1w, s1b, s2w, s2b))
+        capi.cab_se_bwd(g, c2, B, H * W, C, S, s1w.detach(), s2w.detach(), 1.0, pool, hidden, scale, d_c2, ds1w, ds1b,
+                        ds2w, ds2b)
+        _, wt2, _ = cv.conv_weights(c2w, c2b, Cp, Cm_p, refresh=False)
+        d_c1 = torch.empty(T, Cm_p, device=dev, dtype=BF16)
+        capi.conv3x3_igemm(capi.CEPI_MUL, B, H, W, Cp, Cm_p, Cm_p, d_c2, wt2, None, d_c1, r=dc1)
+        dc2w, dc2b = torch.empty_like(c2w), torch.empty_like(c2b)
+        capi.conv3x3_wgrad(B, H, W, Cm, C, Cm_p, Cp, False, d_c2, c1, dc2w)
+        db_full = torch.empty(Cp, device=dev, dtype=torch.float32)
+        capi.bias_grad_nhwc(d_c2, B, H, W, Cp, False, db_full)
+        dc2b.copy_(db_full[:C])
+        _, wt1, _ = cv.conv_weights(c1w, c1b, Cm_p, Cp, refresh=False)
+        dxt = torch.empty(T, Cp, device=dev, dtype=BF16)
+        capi.conv3x3_igemm(capi.CEPI_BIAS, B, H, W, Cm_p, Cp, Cp, d_c1, wt1, None, dxt)
+        dc1w, dc1b = torch.empty_like(c1w), torch.empty_like(c1b)
+        capi.conv3x3_wgrad(B, H, W, C, Cm, Cp, Cm_p, False, d_c1, xt, dc1w)
+        db1_full = torch.empty(Cm_p, device=dev, dtype=torch.float32)
+        capi.bias_grad_nhwc(d_c1, B, H, W, Cm_p, False, db1_full)
+        dc1b.copy_(db1_full[:Cm])
+        dx = dxt[:, :C].reshape(B, H, W, C).permute(0, 3, 1, 2).to(dtype)
+        return dx, dc1w, dc1b, dc2w, dc2b, ds1w, ds1b, ds2w, ds2b

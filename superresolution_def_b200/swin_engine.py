@@ -358,34 +358,49 @@ class WindowAttentionFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, ws, heads, table, qkv_w, qkv_b, proj_w, proj_b):
         B_, N, C = x.shape
-        if ws != 8 or N != 64:
-            raise capi.SrkError("stand-alone WindowAttention kernel: window 8x8 (64 tokens)")
-        cfg = BlockCfg.for_model(C, heads, 4 * C, ws)
-        Bp = B_ + (B_ & 1)  # 64-token windows, 128-row GEMM tiles
+        if (ws, N) not in ((8, 64), (16, 256)):
+            raise capi.SrkError("stand-alone WindowAttention kernels: windows 8x8 (64 tokens) or 16x16 (256 tokens)")
+        if ws == 8:
+            cfg = BlockCfg.for_model(C, heads, 4 * C, ws)
+        else:  # HAT's WindowAttention (hat_arch.py:129-196), mask=None
+            if not (C < 192 and heads * 32 == 192 and C % heads == 0):
+                raise capi.SrkError("libsrk window attention: heads=6, head_dim<32, embed_dim<192")
+            cfg = BlockCfg(C=C, heads=heads, hidden=4 * C, ws=16, Cp=192, ds=32, Hp=((4 * C + 1 + 255) // 256) * 256)
+        Bp = B_ + (B_ & 1) if ws == 8 else B_  # 128-row GEMM tiles
         w = _partial_weights(cfg, x.device, rpb_table=table, qkv_w=qkv_w, qkv_b=qkv_b, proj_w=proj_w, proj_b=proj_b)
-        xp = _pack_rows(x.reshape(-1, C), cfg.Cp, C, Bp * 64)
-        qkv = torch.empty(Bp * 64, cfg.QW, device=x.device, dtype=BF16)
+        xp = _pack_rows(x.reshape(-1, C), cfg.Cp, C, Bp * N)
+        qkv = torch.empty(Bp * N, cfg.QW, device=x.device, dtype=BF16)
         capi.gemm_tn(capi.EPI_STORE, xp, w["qkv_f"].view(cfg.QW, cfg.Cp), qkv)
-        geom = capi.SrkGeom(Bp, 8, 8, 8, 0)  # already-partitioned windows: one 8x8 "image" per window
-        ao = torch.empty(Bp * 64, cfg.AW, device=x.device, dtype=BF16)
-        capi.win_attn_fwd(geom, heads, qkv, table.detach(), ao, ones_col=cfg.dh)
-        y = torch.empty(Bp * 64, cfg.Cp, device=x.device, dtype=BF16)
+        geom = capi.SrkGeom(Bp, ws, ws, ws, 0)  # already-partitioned windows: one ws x ws "image" per window
+        ao = torch.empty(Bp * N, cfg.AW, device=x.device, dtype=BF16)
+        lse = None
+        if ws == 8:
+            capi.win_attn_fwd(geom, heads, qkv, table.detach(), ao, ones_col=cfg.dh)
+        else:
+            lse = torch.empty(heads, Bp * N, device=x.device, dtype=torch.float32)
+            capi.win_attn16_fwd(geom, capi.ATTN_SELF, heads, qkv, table.detach(), ao, lse, ones_col=cfg.dh)
+        y = torch.empty(Bp * N, cfg.Cp, device=x.device, dtype=BF16)
         capi.gemm_tn(capi.EPI_STORE, ao, w["proj_f"].view(cfg.Cp, cfg.AW), y)
-        ctx.saved = (xp, qkv, ao, w, cfg, table.detach(), B_, Bp, x.dtype)
-        return y[:B_ * 64, :C].reshape(B_, N, C).to(x.dtype)
+        ctx.saved = (xp, qkv, ao, w, cfg, table.detach(), B_, Bp, x.dtype, N, lse)
+        return y[:B_ * N, :C].reshape(B_, N, C).to(x.dtype)
 
     @staticmethod
     def backward(ctx, dy):
-        xp, qkv, ao, w, cfg, table, B_, Bp, dtype = ctx.saved
+        xp, qkv, ao, w, cfg, table, B_, Bp, dtype, N, lse = ctx.saved
         C, heads, dh, ds = cfg.C, cfg.heads, cfg.dh, cfg.ds
         dev = dy.device
-        dyp = _pack_rows(dy.reshape(-1, C), cfg.Cp, -1, Bp * 64)
-        d_ao = torch.empty(Bp * 64, cfg.AW, device=dev, dtype=BF16)
+        dyp = _pack_rows(dy.reshape(-1, C), cfg.Cp, -1, Bp * N)
+        d_ao = torch.empty(Bp * N, cfg.AW, device=dev, dtype=BF16)
         capi.gemm_tn(capi.EPI_STORE, dyp, w["proj_t"].view(cfg.AW, cfg.Cp), d_ao)
         d_qkv = torch.empty_like(qkv)
         d_table = torch.empty_like(table)
-        capi.win_attn_bwd(capi.SrkGeom(Bp, 8, 8, 8, 0), heads, qkv, table, d_ao, d_qkv, d_table)
-        dx = torch.empty(Bp * 64, cfg.Cp, device=dev, dtype=BF16)
+        geom = capi.SrkGeom(Bp, cfg.ws, cfg.ws, cfg.ws, 0)
+        if cfg.ws == 8:
+            capi.win_attn_bwd(geom, heads, qkv, table, d_ao, d_qkv, d_table)
+        else:
+            aws = torch.empty(capi.attn16_bwd_ws_bytes(geom, capi.ATTN_SELF, heads), device=dev, dtype=torch.uint8)
+            capi.win_attn16_bwd(geom, capi.ATTN_SELF, heads, qkv, table, ao, d_ao, lse, d_qkv, aws, d_table)
+        dx = torch.empty(Bp * N, cfg.Cp, device=dev, dtype=BF16)
         capi.gemm_tn(capi.EPI_STORE, d_qkv, w["qkv_t"].view(cfg.Cp, cfg.QW), dx)
         ep = _wgrad(dyp, ao, cfg.Cp)       # [Cp, AW]
         eq = _wgrad(d_qkv, xp, cfg.QW)     # [QW, Cp]
@@ -397,7 +412,7 @@ class WindowAttentionFunction(torch.autograd.Function):
         epv = ep[:C].view(C, heads, ds)
         d_proj_w = epv[:, :, :dh].reshape(C, C).contiguous()
         d_proj_b = epv[:, 0, dh].contiguous()
-        return (dx[:B_ * 64, :C].reshape(B_, 64, C).to(dtype), None, None, d_table, d_qkv_w, d_qkv_b, d_proj_w,
+        return (dx[:B_ * N, :C].reshape(B_, N, C).to(dtype), None, None, d_table, d_qkv_w, d_qkv_b, d_proj_w,
                 d_proj_b)
 
 

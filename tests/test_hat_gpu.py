@@ -233,3 +233,33 @@ def test_hat_small_matches_oracle():
         if mine > 1.6 * auto + 1e-2:
             bad[n] = (round(mine, 4), round(auto, 4))
     assert not bad, bad
+
+
+def test_standalone_cab_and_window_attention_modules():
+    """CAB.forward(x NCHW) and HAT's WindowAttention.forward(x, rpi, mask=None) called on their own
+    (reference hat_arch.py:61-74, :129-196): outputs + every gradient vs the oracle."""
+    from superresolution_def_b200.hat_arch import CAB, WindowAttention
+    ho = _ho()
+    torch.manual_seed(11)
+    cab = randomize_(CAB(180, 3, 30), seed=12).cuda()
+    x = torch.randn(2, 180, 16, 32, device="cuda")
+    xm, xr = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    sd = _sd_of(cab)
+    got, ref = cab(xm), ho.cab(xr, sd, "")
+    assert got.shape == ref.shape and rel_l2(got, ref) < OUT_TOL, rel_l2(got, ref)
+    w = torch.randn_like(ref)
+    (got * w).sum().backward(); (ref * w).sum().backward()
+    assert rel_l2(xm.grad, xr.grad) < GRAD_TOL, rel_l2(xm.grad, xr.grad)
+    bad = {n: round(rel_l2(p.grad, sd[n].grad), 4) for n, p in cab.named_parameters() if rel_l2(p.grad, sd[n].grad) > GRAD_TOL}
+    assert not bad, bad
+    att = randomize_(WindowAttention(180, (16, 16), 6), seed=13).cuda()
+    x = torch.randn(3, 256, 180, device="cuda")
+    xm, xr = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    sd = _sd_of(att)
+    got, ref = att(xm, None, None), ho.window_attention(xr, sd, "", 6, ho.rpi_sa(16).cuda(), None)
+    assert rel_l2(got, ref) < OUT_TOL, rel_l2(got, ref)
+    w = torch.randn_like(ref)
+    (got * w).sum().backward(); (ref * w).sum().backward()
+    assert rel_l2(xm.grad, xr.grad) < GRAD_TOL
+    bad = {n: round(rel_l2(p.grad, sd[n].grad), 4) for n, p in att.named_parameters() if rel_l2(p.grad, sd[n].grad) > GRAD_TOL}
+    assert not bad, bad

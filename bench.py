@@ -126,36 +126,88 @@ def run_reference(args):
 
 
 def roofline_probe(batch: int, peaks):
-    """Times the dominant kernel alone (CUDA events, current stream) at the step's shapes: the fc1 GEMM with the
-    fused GELU epilogue, tcgen05, M = batch*16384 tokens, K = 192, N = 768 (two bf16 outputs).  It is HBM-bound:
-    algorithmic bytes per launch = read xn2 (M*192*2) + write act and dact (2*M*768*2) + weights."""
+    """Times every per-block kernel of the SwinIR step alone at the step's shapes (CUDA events on the launching stream,
+    operands larger than L2) and reports each against the HBM roofline: achieved = algorithmic bytes per launch /
+    mean launch duration.  Algorithmic bytes = each operand / result tensor moved once.  The
+    `roofline` object is the kernel function with the largest share of the step (launches x duration); the full table
+    goes to `roofline_kernels`."""
     from superresolution_def_b200 import _capi as capi
     hbm, _, _, kind = peaks
-    M, K, N = batch * 16384, 192, 768
-    A = torch.randn(M, K, device="cuda").to(torch.bfloat16)
-    Bw = (torch.randn(N, K, device="cuda") / 14).to(torch.bfloat16)
-    C = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-    C2 = torch.empty_like(C)
-    ln = capi.make_ln_args(N, 720, None)
-    flush = torch.empty(256 << 20, device="cuda", dtype=torch.uint8)
-    for _ in range(3):
-        capi.gemm_tn(capi.EPI_GELU2, A, Bw, C, C2=C2, ln=ln)
-    times = []
-    for _ in range(10):
-        flush.zero_()
+    M, C, QW, HP, heads = batch * 16384, 192, 576, 768, 6
+    bf = torch.bfloat16
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(0)
+    rnd = lambda *shape: torch.randn(*shape, device=dev, generator=g).to(bf)  # noqa: E731
+    x192, y192, z192, o192 = rnd(M, C), rnd(M, C), rnd(M, C), torch.empty(M, C, device=dev, dtype=bf)
+    x576, o576 = rnd(M, QW), torch.empty(M, QW, device=dev, dtype=bf)
+    x768, y768, o768, o768b = rnd(M, HP), rnd(M, HP), torch.empty(M, HP, device=dev, dtype=bf), torch.empty(M, HP, device=dev, dtype=bf)
+    w = lambda n, k: (torch.randn(n, k, device=dev, generator=g) / k ** 0.5).to(bf)  # noqa: E731
+    w_qkv, w_proj, w_fc1, w_fc2, w_fc1t, w_qkvt = w(QW, C), w(C, C), w(HP, C), w(C, HP), w(C, HP), w(C, QW)
+    stats = torch.empty(M, 2, device=dev)
+    gam, bet = torch.ones(180, device=dev), torch.zeros(180, device=dev)
+    table = torch.randn(225, heads, device=dev, generator=g)
+    geom = capi.SrkGeom(batch, 128, 128, 8, 4)
+    parts = torch.empty(capi.gemm_grid(M, C) * 2 * C, device=dev)
+    capi.layernorm_fwd(x192, o192, stats, gam, bet, 180, ones_col=180)  # valid (mean, rstd) for the LNBWD runs
+    wg_ws = torch.empty(148 * 128 * 256, device=dev)
+    wg_out = torch.empty(768 * 256, device=dev)
+    dtab = torch.empty_like(table)
+    ln_res = capi.make_ln_args(180, 180, gam, bet, stats=stats)
+    ln_bwd = capi.make_ln_args(180, -1, gam, None, stats=stats, partials=parts)
+    ln_gelu = capi.make_ln_args(HP, 720, None)
+    E = 2  # bytes per element
+
+    def splits(T, ca):
+        return max(1, min(148 // ((ca + 127) // 128), T // 64))
+
+    cases = [
+        ("gemm_tn<192,STORE> qkv", "gemm_tn_kernel<STORE>", 1, lambda: capi.gemm_tn(capi.EPI_STORE, x192, w_qkv, o576), M * (C + QW) * E),
+        ("win_attn_ws8_fwd", "win_attn_ws8_fwd_kernel", 1, lambda: capi.win_attn_fwd(geom, heads, x576, table, o192, ones_col=30), M * (QW + C) * E),
+        ("gemm_tn<192,RES_LN> proj", "gemm_tn_kernel<RES_LN>", 1, lambda: capi.gemm_tn(capi.EPI_RES_LN, x192, w_proj, o192, C2=z192, X1=y192, ln=ln_res), M * 4 * C * E),
+        ("gemm_tn<256,GELU2> fc1", "gemm_tn_kernel<GELU2>", 1, lambda: capi.gemm_tn(capi.EPI_GELU2, x192, w_fc1, o768, C2=o768b, ln=ln_gelu), M * (C + 2 * HP) * E),
+        ("gemm_tn<192,RES_LN> fc2", "gemm_tn_kernel<RES_LN>", 1, lambda: capi.gemm_tn(capi.EPI_RES_LN, x768, w_fc2, o192, C2=z192, X1=y192, ln=ln_res), M * (HP + 3 * C) * E),
+        ("gemm_tn<256,MUL> fc2 dgrad", "gemm_tn_kernel<MUL>", 1, lambda: capi.gemm_tn(capi.EPI_MUL, x192, w_fc1, o768, X1=y768), M * (C + 2 * HP) * E),
+        ("gemm_wgrad<192> fc1/fc2", "gemm_wgrad_kernel", 2, lambda: capi.gemm_wgrad(x768, x192, wg_ws, splits(M, HP), wg_out), M * (HP + C) * E),
+        ("gemm_tn<192,LNBWD> fc1 dgrad", "gemm_tn_kernel<LNBWD>", 1, lambda: capi.gemm_tn(capi.EPI_LNBWD, x768, w_fc1t, o192, X1=x192, X2=y192, ln=ln_bwd), M * (HP + 3 * C) * E),
+        ("gemm_tn<192,STORE> d_ao", "gemm_tn_kernel<STORE>", 1, lambda: capi.gemm_tn(capi.EPI_STORE, x192, w_proj, o192), M * 2 * C * E),
+        ("gemm_wgrad<192> proj", "gemm_wgrad_kernel", 1, lambda: capi.gemm_wgrad(x192, y192, wg_ws, splits(M, C), wg_out), M * 2 * C * E),
+        ("win_attn_ws8_bwd", "win_attn_ws8_bwd_kernel", 1, lambda: capi.win_attn_bwd(geom, heads, x576, table, y192, o576, dtab), M * (2 * QW + C) * E),
+        ("gemm_tn<192,LNBWD> qkv dgrad", "gemm_tn_kernel<LNBWD>", 1, lambda: capi.gemm_tn(capi.EPI_LNBWD, x576, w_qkvt, o192, X1=x192, X2=y192, ln=ln_bwd), M * (QW + 3 * C) * E),
+        ("gemm_wgrad<192> qkv", "gemm_wgrad_kernel", 1, lambda: capi.gemm_wgrad(x576, x192, wg_ws, splits(M, QW), wg_out), M * (QW + C) * E),
+    ]
+    rows = []
+    reps = 5
+    for name, fn_name, per_block, call, nbytes in cases:
+        for _ in range(2):
+            call()
+        # every case streams >= 200 MB of operands/results per launch (> the 126 MB L2), so back-to-back launches
+        # cannot be served from cache; 5 launches between one event pair amortise the launch gap
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        capi.gemm_tn(capi.EPI_GELU2, A, Bw, C, C2=C2, ln=ln)
+        for _ in range(reps):
+            call()
         e1.record()
         e1.synchronize()
-        times.append(e0.elapsed_time(e1))
-    ms = sum(times) / len(times)
-    bytes_alg = M * K * 2 + 2 * M * N * 2 + N * K * 2
-    achieved = bytes_alg / (ms * 1e-3) / 1e9
-    return {"kernel": "gemm_tn_kernel<256,EPI_GELU2> (fc1+GELU, tcgen05)", "bound": "hbm", "achieved": achieved,
-            "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None, "peak_kind": kind,
-            "ms_per_launch": ms, "algorithmic_bytes": bytes_alg,
-            "tflops_of_kernel": 2.0 * M * N * K / (ms * 1e-3) / 1e12}
+        ms = e0.elapsed_time(e1) / reps
+        rows.append({"kernel": name, "function": fn_name, "launches_per_step": 36 * per_block, "ms_per_launch": ms,
+                     "algorithmic_bytes": nbytes, "achieved": nbytes / (ms * 1e-3) / 1e9, "frac": nbytes / (ms * 1e-3) / 1e9 / hbm})
+    by_fn: dict = {}
+    for r in rows:
+        d = by_fn.setdefault(r["function"], {"ms": 0.0, "bytes": 0.0, "launches": 0})
+        d["ms"] += r["ms_per_launch"] * r["launches_per_step"]
+        d["bytes"] += r["algorithmic_bytes"] * r["launches_per_step"]
+        d["launches"] += r["launches_per_step"]
+    top = max(by_fn.items(), key=lambda kv: kv[1]["ms"])
+    ach = top[1]["bytes"] / (top[1]["ms"] * 1e-3) / 1e9
+    total_ms = sum(d["ms"] for d in by_fn.values())
+    roof = {"kernel": top[0] + " (tcgen05 weight-gradient GEMM, MN-major operands)" if "wgrad" in top[0] else top[0],
+            "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+            "traffic": None, "peak_kind": kind, "ms_per_launch": top[1]["ms"] / top[1]["launches"],
+            "algorithmic_bytes": top[1]["bytes"] / top[1]["launches"], "launches_per_step": top[1]["launches"],
+            "share_of_block_kernels": top[1]["ms"] / total_ms,
+            "note": "dominant kernel function by launches x duration among the per-block kernels, each timed alone at the "
+                    "step's shapes; traffic (ncu dram bytes) is recorded in profiles/"}
+    return roof, rows
 
 
 def _dbg(msg):
@@ -314,7 +366,7 @@ def run_ours(args):
             "step_tflops": value / world * gflop / 1e3,
             "step_frac_of_bf16_sustained": value / world * gflop / 1e3 / peaks[2]}
     if rank == 0:
-        line["roofline"] = roofline_probe(B, peaks)
+        line["roofline"], line["roofline_kernels"] = roofline_probe(B, peaks)
         if world == 1 and not args.no_cpu_baseline and not hat:
             v, spp, threads = cpu_reference_arm(2, 1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",

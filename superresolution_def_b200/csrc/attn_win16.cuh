@@ -149,20 +149,25 @@ __device__ __forceinline__ MaskCtx mask_ctx(bool last_y, bool last_x, int qy, in
 template <int MODE>
 __device__ __forceinline__ void qk_tile(const uint32_t (&aq)[2][4], uint32_t k_tile, const float* bp, const MaskCtx& mk,
                                         int lane, float (&s)[8][4]) {
+  // K fragments are double-buffered: the ldmatrix of n-tile nt+1 is issued before the MMAs of n-tile nt
+  const uint32_t kb_base = k_tile + t32_off(lane & 7, lane >> 3);   // + nt * 8 rows = nt * 512 B (swizzle unchanged)
+  uint32_t kb[2][4];
+  ldsm_x4(kb_base, kb[0][0], kb[0][1], kb[0][2], kb[0][3]);
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
+    const int cur = nt & 1, nxt = cur ^ 1;
+    if (nt + 1 < 8 && nt_valid<MODE>(nt + 1))
+      ldsm_x4(kb_base + (nt + 1) * 512, kb[nxt][0], kb[nxt][1], kb[nxt][2], kb[nxt][3]);
     if (!nt_valid<MODE>(nt)) {
       s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = -INFINITY;
       continue;
     }
-    uint32_t b0, b1, b2, b3;
-    ldsm_x4(k_tile + t32_off(nt * 8 + (lane & 7), lane >> 3), b0, b1, b2, b3);
     s[nt][0] = bp[bias_const<MODE>(nt, 0, 0)];
     s[nt][1] = bp[bias_const<MODE>(nt, 1, 0)];
     s[nt][2] = bp[bias_const<MODE>(nt, 0, 1)];
     s[nt][3] = bp[bias_const<MODE>(nt, 1, 1)];
-    mma_bf16(s[nt], aq[0], b0, b1);
-    mma_bf16(s[nt], aq[1], b2, b3);
+    mma_bf16(s[nt], aq[0], kb[cur][0], kb[cur][1]);
+    mma_bf16(s[nt], aq[1], kb[cur][2], kb[cur][3]);
   }
   if (MODE == MODE_SELF && mk.any) {
 #pragma unroll
@@ -175,6 +180,14 @@ __device__ __forceinline__ void qk_tile(const uint32_t (&aq)[2][4], uint32_t k_t
 
 // o[16 x 32] += A[16 x 64] (bf16 fragments built from fp32 s) * Bt[64 x 32]   (accumulating frag_times_tile)
 __device__ __forceinline__ void frag_times_tile_acc(const float (&s)[8][4], uint32_t bt_tile, int lane, float (&o)[4][4]) {
+  // 8 transposed B fragments (kk = 0..3, np = 0..1), double-buffered one step ahead of the MMAs
+  const uint32_t b_base = bt_tile + t32_off((lane & 7) + ((lane >> 3) & 1) * 8, lane >> 4);
+  auto frag_addr = [&](int step) {  // step = kk * 2 + np: +16 rows per kk (swizzle unchanged), chunk pair np toggles bit 1
+    const int kk = step >> 1, np = step & 1;
+    return (b_base + kk * 16 * 64) ^ (uint32_t(np) << 5);
+  };
+  uint32_t bf[2][4];
+  ldsm_x4_t(frag_addr(0), bf[0][0], bf[0][1], bf[0][2], bf[0][3]);
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
     uint32_t a[4];
@@ -182,13 +195,12 @@ __device__ __forceinline__ void frag_times_tile_acc(const float (&s)[8][4], uint
     a[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
     a[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
     a[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-    const int row = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
 #pragma unroll
     for (int np = 0; np < 2; ++np) {
-      uint32_t b0, b1, b2, b3;
-      ldsm_x4_t(bt_tile + t32_off(row, np * 2 + (lane >> 4)), b0, b1, b2, b3);
-      mma_bf16(o[2 * np], a, b0, b1);
-      mma_bf16(o[2 * np + 1], a, b2, b3);
+      const int step = kk * 2 + np, cur = step & 1, nxt = cur ^ 1;
+      if (step + 1 < 8) ldsm_x4_t(frag_addr(step + 1), bf[nxt][0], bf[nxt][1], bf[nxt][2], bf[nxt][3]);
+      mma_bf16(o[2 * np], a, bf[cur][0], bf[cur][1]);
+      mma_bf16(o[2 * np + 1], a, bf[cur][2], bf[cur][3]);
     }
   }
 }
@@ -359,26 +371,37 @@ struct A16BwdSmem {
 };
 
 // dst[16 keys x 16 cols] = A^T B: A = t64 tile [256 q][64 slots] (this warp: slots k0..k0+15), B = t32 tile [256 q][32]
-// (column half ch), contraction over the 256 queries.
+// (column half ch), contraction over the 256 queries.  Fragments of step kk+1 are fetched before the MMAs of step kk
+// are issued, and even / odd steps accumulate into separate registers (two independent HMMA chains per n-tile).
 __device__ __forceinline__ void tileT_times_tile256(uint32_t a_tile, uint32_t b_tile, int k0, int ch, int lane,
                                                     float (&o)[2][4]) {
+  float oo[2][2][4];
 #pragma unroll
-  for (int n = 0; n < 2; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
-#pragma unroll 4
+  for (int p = 0; p < 2; ++p)
+#pragma unroll
+    for (int n = 0; n < 2; ++n) oo[p][n][0] = oo[p][n][1] = oo[p][n][2] = oo[p][n][3] = 0.f;
+  const int ia = lane >> 3;
+  const uint32_t a_base = a_tile + t64_off((lane & 7) + ((ia >> 1) & 1) * 8, (k0 + (ia & 1) * 8) >> 3);
+  const uint32_t b_base = b_tile + t32_off((lane & 7) + ((lane >> 3) & 1) * 8, ch * 2 + (lane >> 4));
+  // rows advance by 16 per step: +16*128 B in the t64 tile, +16*64 B in the t32 tile; the swizzle terms depend on
+  // (row & 7) and ((row >> 1) & 3) only, which a multiple of 16 rows leaves unchanged
+  uint32_t af[2][4], bf[2][4];
+  ldsm_x4_t(a_base, af[0][0], af[0][1], af[0][2], af[0][3]);
+  ldsm_x4_t(b_base, bf[0][0], bf[0][1], bf[0][2], bf[0][3]);
+#pragma unroll
   for (int kk = 0; kk < 16; ++kk) {
-    uint32_t af[4];
-    {
-      const int i = lane >> 3;
-      const int row = kk * 16 + (lane & 7) + ((i >> 1) & 1) * 8;  // query
-      const int col = k0 + (i & 1) * 8;                           // key slot
-      ldsm_x4_t(a_tile + t64_off(row, col >> 3), af[0], af[1], af[2], af[3]);
+    const int cur = kk & 1, nxt = cur ^ 1;
+    if (kk + 1 < 16) {
+      ldsm_x4_t(a_base + (kk + 1) * 16 * 128, af[nxt][0], af[nxt][1], af[nxt][2], af[nxt][3]);
+      ldsm_x4_t(b_base + (kk + 1) * 16 * 64, bf[nxt][0], bf[nxt][1], bf[nxt][2], bf[nxt][3]);
     }
-    const int row = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-    uint32_t b0, b1, b2, b3;
-    ldsm_x4_t(b_tile + t32_off(row, ch * 2 + (lane >> 4)), b0, b1, b2, b3);
-    mma_bf16(o[0], af, b0, b1);
-    mma_bf16(o[1], af, b2, b3);
+    mma_bf16(oo[cur][0], af[cur], bf[cur][0], bf[cur][1]);
+    mma_bf16(oo[cur][1], af[cur], bf[cur][2], bf[cur][3]);
   }
+#pragma unroll
+  for (int n = 0; n < 2; ++n)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[n][e] = oo[0][n][e] + oo[1][n][e];
 }
 
 // Bias-table gradient as a tensor-core diagonal sum.  For every (query row qy, key row / band) pair the 16x16 block
@@ -386,30 +409,46 @@ __device__ __forceinline__ void tileT_times_tile256(uint32_t a_tile, uint32_t b_
 // [b == 15 + kx - qx] (MODE_OCA).  As an MMA: M = b (32 diagonals, two m-tiles), K = (qx, kx) (16 k-steps of 16),
 // N = 8 pairs.  Per key tile there are 64 pairs = 8 n-tiles; warp w takes n-tile w&7 and m-tile w>>3.
 // Pair n of n-tile j: query row qy = 2j + (n>>2), in-tile key row/band index r = n&3 (its 16 slots = columns r*16..).
-// The A operand (the 0/1 Toeplitz selector R) is never materialised: an 8-element row of it is either all-zero or
-// one-hot, so the fragment is fetched by ldmatrix from a 9-row table in shared memory (rows 0..7 = one-hot at that
-// position, row 8 = zeros) with a per-lane row choice  pos = qx + c_lane  clamped to 8.
+// The A operand (the 0/1 Toeplitz selector R) is never materialised: each fragment word is zero or one-hot.
 template <int MODE>
-__device__ __forceinline__ void diag_mma(uint32_t ds_tile, uint32_t onehot_tbl, int warp, int lane, float (&acc)[4]) {
+__device__ __forceinline__ void diag_mma(uint32_t ds_tile, int warp, int lane, float (&acc)[4]) {
   const int j = warp & 7, mt = warp >> 3;
   acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
   const int n = lane & 7;                       // ldmatrix row provider (B operand): pair index
   const int prow = (2 * j + (n >> 2)) * 16;     // first dS row of that pair's query row-group
   const int pchunk = (n & 3) * 2 + ((lane >> 3) & 1);
-  // A operand: lane l provides row (l & 7) of 8x8 matrix (l >> 3): matrices 0,1 = rows b, b+8 at k 0..7; 2,3 at k 8..15
-  const int b_row = mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-  const int k0 = (lane >> 4) * 8;
-  const int c_lane = (MODE == MODE_SELF) ? (15 - b_row - k0) : (b_row - 15 - k0);   // one-hot position = qx + c_lane
+  // A operand built in registers (shared-memory bandwidth is this kernel's limiter, ALU is not): fragment word
+  // (row b, k pair 2t, 2t+1) is one-hot iff the selected k = qx + c equals 2t or 2t+1.
+  const int g = lane >> 2, t = lane & 3;
+  const int b_lo = mt * 16 + g;
+  // p = (selected k) - 2t for row b_lo at step qx = 0; row b_lo + 8 selects k -/+ 8 (SELF / OCA), k + 8 columns see p - 8
+  const int p0 = ((MODE == MODE_SELF) ? (15 - b_lo) : (b_lo - 15)) - 2 * t;
+  auto onehot2 = [](int p) -> uint32_t { return (uint32_t(p) < 2u) ? (0x3F80u << (16 * p)) : 0u; };
+  // prow is a multiple of 16, so the swizzle term of row prow + qx is (qx & 7): a compile-time constant per step
+  const uint32_t ds_row0 = ds_tile + uint32_t(prow) * 128u;
+  auto fetch = [&](int qx, uint32_t (&b)[2]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];"
+                 : "=r"(b[0]), "=r"(b[1]) : "r"(ds_row0 + uint32_t(qx) * 128u + (uint32_t(pchunk ^ (qx & 7)) << 4)));
+  };
+  float acc2[4] = {0.f, 0.f, 0.f, 0.f};
+  uint32_t bq[2][2];
+  fetch(0, bq[0]);
 #pragma unroll
   for (int qx = 0; qx < 16; ++qx) {
-    uint32_t b0, b1;
-    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];"
-                 : "=r"(b0), "=r"(b1) : "r"(ds_tile + t64_off(prow + qx, pchunk)));
-    const uint32_t pos = min(uint32_t(qx + c_lane), 8u);   // negative -> huge unsigned -> 8 (zero row)
+    const int cur = qx & 1, nxt = cur ^ 1;
+    if (qx + 1 < 16) fetch(qx + 1, bq[nxt]);
+    const int p = p0 + qx;
+    const int p_hi = (MODE == MODE_SELF) ? p - 8 : p + 8;   // row b_lo + 8
     uint32_t af[4];
-    ldsm_x4(onehot_tbl + pos * 16, af[0], af[1], af[2], af[3]);
-    mma_bf16(acc, af, b0, b1);
+    af[0] = onehot2(p);          // (row b_lo,     k 2t..2t+1)
+    af[1] = onehot2(p_hi);       // (row b_lo + 8, k 2t..2t+1)
+    af[2] = onehot2(p - 8);      // (row b_lo,     k 2t+8..2t+9)
+    af[3] = onehot2(p_hi - 8);   // (row b_lo + 8, k 2t+8..2t+9)
+    if (cur == 0) mma_bf16(acc, af, bq[cur][0], bq[cur][1]);
+    else mma_bf16(acc2, af, bq[cur][0], bq[cur][1]);
   }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) acc[e] += acc2[e];
 }
 
 template <int MODE>
@@ -421,7 +460,6 @@ __global__ void __launch_bounds__(A16_BWD_THREADS, 1) win_attn16_bwd_kernel(cons
   __shared__ float s_lse[256];
   __shared__ float s_delta[256];
   __shared__ int s_qtok[256];
-  __shared__ __align__(16) uint16_t s_onehot[9 * 8];
   const uint32_t sm0 = smem_u32(smem_dyn);
   const uint32_t sQ = sm0 + L::kQ, sDO = sm0 + L::kDO, sK = sm0 + L::kK, sV = sm0 + L::kV, sP = sm0 + L::kP,
                  sDS = sm0 + L::kDS, sOut = sm0 + L::kOut;
@@ -432,7 +470,6 @@ __global__ void __launch_bounds__(A16_BWD_THREADS, 1) win_attn16_bwd_kernel(cons
   const int hw = a.heads * 32;
   constexpr float kLog2e = 1.4426950408889634f;
   load_bias_table<MODE>(s_bias, a.bias_table, a.heads, h, A16_BWD_THREADS);
-  if (threadIdx.x < 72) s_onehot[threadIdx.x] = ((threadIdx.x >> 3) == (threadIdx.x & 7)) ? 0x3F80 : 0;  // bf16 1.0
   // this CTA's slice of the diagonal-sum scratch: [NKT][16 warps][32 lanes] float4, exclusively owned per thread
   float4* scratch = reinterpret_cast<float4*>(a.dbias_scratch) +
                     ((size_t)blockIdx.x * a.heads + h) * (G::NKT * 16 * 32);
@@ -505,31 +542,38 @@ __global__ void __launch_bounds__(A16_BWD_THREADS, 1) win_attn16_bwd_kernel(cons
         s[nt][2] = fast_ex2(fmaf(s[nt][2], kLog2e, -lse1));
         s[nt][3] = fast_ex2(fmaf(s[nt][3], kLog2e, -lse1));
       }
+      uint32_t pp[2][2];
+      const uint32_t vb_base = vT + t32_off(lane & 7, lane >> 3);
+      uint32_t vb[2][4];
+      ldsm_x4(vb_base, vb[0][0], vb[0][1], vb[0][2], vb[0][3]);
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {  // dP = dO V^T, dS = P * (dP - delta); P, dS -> smem (bf16)
-        if (!nt_valid<MODE>(nt)) {    // padding keys: P = dS = 0
+        if (nt + 1 < 8 && nt_valid<MODE>(nt + 1))
+          ldsm_x4(vb_base + (nt + 1) * 512, vb[(nt + 1) & 1][0], vb[(nt + 1) & 1][1], vb[(nt + 1) & 1][2], vb[(nt + 1) & 1][3]);
+        if (!nt_valid<MODE>(nt)) {    // padding keys (always an odd n-tile): P = dS = 0, stored with its even partner
           s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-          asm volatile("st.shared.u32 [%0], %1;" ::"r"(sP + t64_off(r0 + g, nt) + t * 4), "r"(0u) : "memory");
-          asm volatile("st.shared.u32 [%0], %1;" ::"r"(sP + t64_off(r0 + g + 8, nt) + t * 4), "r"(0u) : "memory");
-          asm volatile("st.shared.u32 [%0], %1;" ::"r"(sDS + t64_off(r0 + g, nt) + t * 4), "r"(0u) : "memory");
-          asm volatile("st.shared.u32 [%0], %1;" ::"r"(sDS + t64_off(r0 + g + 8, nt) + t * 4), "r"(0u) : "memory");
+          const int m = lane >> 3;
+          const uint32_t off = t64_off(r0 + (m & 1) * 8 + (lane & 7), nt - 1 + (m >> 1));
+          stsm_x4(sP + off, pp[0][0], pp[0][1], 0u, 0u);
+          stsm_x4(sDS + off, pack_bf16(s[nt - 1][0], s[nt - 1][1]), pack_bf16(s[nt - 1][2], s[nt - 1][3]), 0u, 0u);
           continue;
         }
-        uint32_t b0, b1, b2, b3;
-        ldsm_x4(vT + t32_off(nt * 8 + (lane & 7), lane >> 3), b0, b1, b2, b3);
         float dp[4] = {0.f, 0.f, 0.f, 0.f};
-        mma_bf16(dp, ad[0], b0, b1);
-        mma_bf16(dp, ad[1], b2, b3);
-        const uint32_t plo = pack_bf16(s[nt][0], s[nt][1]), phi = pack_bf16(s[nt][2], s[nt][3]);
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(sP + t64_off(r0 + g, nt) + t * 4), "r"(plo) : "memory");
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(sP + t64_off(r0 + g + 8, nt) + t * 4), "r"(phi) : "memory");
+        mma_bf16(dp, ad[0], vb[nt & 1][0], vb[nt & 1][1]);
+        mma_bf16(dp, ad[1], vb[nt & 1][2], vb[nt & 1][3]);
+        pp[nt & 1][0] = pack_bf16(s[nt][0], s[nt][1]);
+        pp[nt & 1][1] = pack_bf16(s[nt][2], s[nt][3]);
         s[nt][0] *= (dp[0] - dl0);
         s[nt][1] *= (dp[1] - dl0);
         s[nt][2] *= (dp[2] - dl1);
         s[nt][3] *= (dp[3] - dl1);
-        const uint32_t dlo = pack_bf16(s[nt][0], s[nt][1]), dhi = pack_bf16(s[nt][2], s[nt][3]);
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(sDS + t64_off(r0 + g, nt) + t * 4), "r"(dlo) : "memory");
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(sDS + t64_off(r0 + g + 8, nt) + t * 4), "r"(dhi) : "memory");
+        if (nt & 1) {  // one stmatrix.x4 per n-tile pair and tile: (rows g, nt-1), (rows g+8, nt-1), (rows g, nt), (rows g+8, nt)
+          const int m = lane >> 3;
+          const uint32_t off = t64_off(r0 + (m & 1) * 8 + (lane & 7), nt - 1 + (m >> 1));
+          stsm_x4(sP + off, pp[0][0], pp[0][1], pp[1][0], pp[1][1]);
+          stsm_x4(sDS + off, pack_bf16(s[nt - 1][0], s[nt - 1][1]), pack_bf16(s[nt - 1][2], s[nt - 1][3]),
+                  pack_bf16(s[nt][0], s[nt][1]), pack_bf16(s[nt][2], s[nt][3]));
+        }
       }
       frag_times_tile_acc(s, kT, lane, dq);  // dQ += dS K
       __syncthreads();
@@ -539,14 +583,9 @@ __global__ void __launch_bounds__(A16_BWD_THREADS, 1) win_attn16_bwd_kernel(cons
         float o[2][4];
         tileT_times_tile256(m ? sP : sDS, m ? sDO : sQ, rg * 16, ch, lane, o);
         const uint32_t dst = sOut + m * (64 * 64);
-#pragma unroll
-        for (int n = 0; n < 2; ++n) {
-          const uint32_t lo = pack_bf16(o[n][0], o[n][1]), hi = pack_bf16(o[n][2], o[n][3]);
-          asm volatile("st.shared.u32 [%0], %1;" ::"r"(dst + t32_off(rg * 16 + g, ch * 2 + n) + t * 4), "r"(lo) : "memory");
-          asm volatile("st.shared.u32 [%0], %1;" ::"r"(dst + t32_off(rg * 16 + g + 8, ch * 2 + n) + t * 4), "r"(hi) : "memory");
-        }
+        store_frag_pair(dst, rg * 16, ch * 2, lane, o[0], o[1], t32_off);
         float acc[4];
-        diag_mma<MODE>(sDS, smem_u32(s_onehot), warp, lane, acc);
+        diag_mma<MODE>(sDS, warp, lane, acc);
         float4* sp = scratch + (kt * 16 + warp) * 32 + lane;
         float4 v = *sp;
         v.x += acc[0]; v.y += acc[1]; v.z += acc[2]; v.w += acc[3];

@@ -160,16 +160,24 @@ __device__ __forceinline__ void frag_times_tile(const float (&s)[8][4], uint32_t
   }
 }
 
+__device__ __forceinline__ void stsm_x4(uint32_t addr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1,%2,%3,%4};"
+               ::"r"(addr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
+// Store two adjacent 16x8 fp32 accumulator n-tiles (c0 = n-tile n, c1 = n-tile n+1; rows r0..r0+15) as bf16 with ONE
+// stmatrix.x4: matrices (rows 0-7, n), (rows 8-15, n), (rows 0-7, n+1), (rows 8-15, n+1).  `row_off(row, chunk)` is the
+// tile's swizzled byte offset of 16-byte chunk `chunk` of row `row`.
+template <typename OffFn>
+__device__ __forceinline__ void store_frag_pair(uint32_t tile, int r0, int n, int lane, const float (&c0)[4],
+                                                const float (&c1)[4], OffFn row_off) {
+  const int m = lane >> 3;
+  const uint32_t addr = tile + row_off(r0 + (m & 1) * 8 + (lane & 7), n + (m >> 1));
+  stsm_x4(addr, pack_bf16(c0[0], c0[1]), pack_bf16(c0[2], c0[3]), pack_bf16(c1[0], c1[1]), pack_bf16(c1[2], c1[3]));
+}
 // store a [16 x 32] fp32 fragment tile as bf16 into a swizzled t32 tile (rows r0..r0+15)
 __device__ __forceinline__ void store_frag_t32(uint32_t tile, int r0, int lane, const float (&o)[4][4]) {
-  const int g = lane >> 2, t = lane & 3;
-#pragma unroll
-  for (int n = 0; n < 4; ++n) {
-    const uint32_t lo = pack_bf16(o[n][0], o[n][1]);
-    const uint32_t hi = pack_bf16(o[n][2], o[n][3]);
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(tile + t32_off(r0 + g, n) + t * 4), "r"(lo) : "memory");
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(tile + t32_off(r0 + g + 8, n) + t * 4), "r"(hi) : "memory");
-  }
+  store_frag_pair(tile, r0, 0, lane, o[0], o[1], t32_off);
+  store_frag_pair(tile, r0, 2, lane, o[2], o[3], t32_off);
 }
 
 // Each thread always handles the same two token rows (i0 = tid/4, i1 = i0 + 32) and 16-byte chunk (tid%4) of every
@@ -361,9 +369,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 4) win_attn_ws8_bwd_kernel(const 
       // the forward multiplies V by bf16(P); its gradient dP is therefore taken w.r.t. the rounded P
       d0 += dp[nt][0] * s[nt][0] + dp[nt][1] * s[nt][1];
       d1 += dp[nt][2] * s[nt][2] + dp[nt][3] * s[nt][3];
-      const uint32_t lo = pack_bf16(s[nt][0], s[nt][1]), hi = pack_bf16(s[nt][2], s[nt][3]);
-      asm volatile("st.shared.u32 [%0], %1;" ::"r"(pt + t64_off(r0 + g, nt) + t * 4), "r"(lo) : "memory");
-      asm volatile("st.shared.u32 [%0], %1;" ::"r"(pt + t64_off(r0 + g + 8, nt) + t * 4), "r"(hi) : "memory");
+      if (nt & 1) store_frag_pair(pt, r0, nt - 1, lane, s[nt - 1], s[nt], t64_off);
     }
     d0 += __shfl_xor_sync(0xffffffffu, d0, 1);
     d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
@@ -377,9 +383,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 4) win_attn_ws8_bwd_kernel(const 
       s[nt][3] *= (dp[nt][3] - d1);
 #pragma unroll
       for (int e = 0; e < 4; ++e) dbacc[nt][e] += s[nt][e];
-      const uint32_t lo = pack_bf16(s[nt][0], s[nt][1]), hi = pack_bf16(s[nt][2], s[nt][3]);
-      asm volatile("st.shared.u32 [%0], %1;" ::"r"(dst + t64_off(r0 + g, nt) + t * 4), "r"(lo) : "memory");
-      asm volatile("st.shared.u32 [%0], %1;" ::"r"(dst + t64_off(r0 + g + 8, nt) + t * 4), "r"(hi) : "memory");
+      if (nt & 1) store_frag_pair(dst, r0, nt - 1, lane, s[nt - 1], s[nt], t64_off);
     }
     // dQ rows = dS (bf16) * K   (kept in registers until the input tiles are dead)
     float dq[4][4], dk[4][4], dv[4][4];

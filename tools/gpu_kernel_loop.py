@@ -30,6 +30,19 @@ elif which == "attn_bwd":
     qkv = torch.randn(T, 576, device=dev).to(bf); tab = torch.randn(225, 6, device=dev)
     do = torch.randn(T, 192, device=dev).to(bf); dq = torch.empty_like(qkv); dt = torch.empty_like(tab)
     for _ in range(reps): capi.win_attn_bwd(capi.SrkGeom(B, 128, 128, 8, 4), 6, qkv, tab, do, dq, dt)
+elif which == "wgrad":
+    A = torch.randn(T, 768, device=dev).to(bf); Bm = torch.randn(T, 192, device=dev).to(bf)
+    ws = torch.empty(148 * 128 * 256, device=dev); out = torch.empty(768 * 256, device=dev)
+    for _ in range(reps): capi.gemm_wgrad(A, Bm, ws, 24, out)
+elif which == "lnbwd":
+    A = torch.randn(T, 768, device=dev).to(bf); W = (torch.randn(192, 768, device=dev) / 28).to(bf)
+    X = torch.randn(T, 192, device=dev).to(bf); R = torch.randn(T, 192, device=dev).to(bf)
+    C = torch.empty(T, 192, device=dev, dtype=bf); st = torch.empty(T, 2, device=dev)
+    g = torch.ones(180, device=dev); b = torch.zeros(180, device=dev)
+    capi.layernorm_fwd(X, C, st, g, b, 180, ones_col=180)
+    parts = torch.empty(capi.gemm_grid(T, 192) * 2 * 192, device=dev)
+    ln = capi.make_ln_args(180, -1, g, None, stats=st, partials=parts)
+    for _ in range(reps): capi.gemm_tn(capi.EPI_LNBWD, A, W, C, X1=X, X2=R, ln=ln)
 elif which in ("attn16_fwd", "attn16_bwd", "oca_fwd", "oca_bwd"):
     B8 = 8
     T8 = B8 * 16384

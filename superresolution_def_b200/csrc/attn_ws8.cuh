@@ -89,18 +89,19 @@ __device__ __forceinline__ void qk_logits(uint32_t q_tile, uint32_t k_tile, cons
     ldsm_x4(q_tile + t32_off(row, chunk), aq[ks][0], aq[ks][1], aq[ks][2], aq[ks][3]);
   }
   const int g = lane >> 2, t = lane & 3;
+  // rel_index(i, j) for i = r0 + g + 8*rowsel (window row 2*warp + rowsel, column g) and j = nt*8 + 2t + e (window row
+  // nt, column 2t + e) is  base + (rowsel - nt) * 15 - e : one LDS with an immediate offset per logit
+  const float* bp = s_bias + ((r0 >> 3) + 7) * 15 + (g - 2 * t + 7);
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
     uint32_t b0, b1, b2, b3;
     ldsm_x4(k_tile + t32_off(nt * 8 + (lane & 7), lane >> 3), b0, b1, b2, b3);
-    s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+    s[nt][0] = bp[(0 - nt) * 15];
+    s[nt][1] = bp[(0 - nt) * 15 - 1];
+    s[nt][2] = bp[(1 - nt) * 15];
+    s[nt][3] = bp[(1 - nt) * 15 - 1];
     mma_bf16(s[nt], aq[0], b0, b1);
     mma_bf16(s[nt], aq[1], b2, b3);
-    const int i0 = r0 + g, j0 = nt * 8 + 2 * t;
-    s[nt][0] += s_bias[rel_index(i0, j0)];
-    s[nt][1] += s_bias[rel_index(i0, j0 + 1)];
-    s[nt][2] += s_bias[rel_index(i0 + 8, j0)];
-    s[nt][3] += s_bias[rel_index(i0 + 8, j0 + 1)];
   }
 }
 
@@ -118,12 +119,13 @@ __device__ __forceinline__ void softmax_rows(float (&s)[8][4]) {
   m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
   float l0 = 0.f, l1 = 0.f;
   constexpr float kLog2e = 1.4426950408889634f;
+  const float n0 = -m0 * kLog2e, n1 = -m1 * kLog2e;
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
-    s[nt][0] = fast_ex2((s[nt][0] - m0) * kLog2e);
-    s[nt][1] = fast_ex2((s[nt][1] - m0) * kLog2e);
-    s[nt][2] = fast_ex2((s[nt][2] - m1) * kLog2e);
-    s[nt][3] = fast_ex2((s[nt][3] - m1) * kLog2e);
+    s[nt][0] = fast_ex2(fmaf(s[nt][0], kLog2e, n0));
+    s[nt][1] = fast_ex2(fmaf(s[nt][1], kLog2e, n0));
+    s[nt][2] = fast_ex2(fmaf(s[nt][2], kLog2e, n1));
+    s[nt][3] = fast_ex2(fmaf(s[nt][3], kLog2e, n1));
     l0 += s[nt][0] + s[nt][1];
     l1 += s[nt][2] + s[nt][3];
   }

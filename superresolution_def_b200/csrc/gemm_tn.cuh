@@ -466,7 +466,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         } else {  // EPI_LNBWD
           const float2 st = reinterpret_cast<const float2*>(args.stats)[m0 + row];
-          const float mean = st.x, rstd = st.y;
+          const float rstd = st.y, nmr = -st.x * st.y;   // xhat = x * rstd + nmr
           float s1 = 0.f, s2 = 0.f;
 #pragma unroll
           for (int ci = 0; ci < NCH; ++ci) {
@@ -486,7 +486,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int e = 0; e < 4; ++e) {
                 const uint32_t a = pack_bf16(__uint_as_float(r[i * 8 + 2 * e]), __uint_as_float(r[i * 8 + 2 * e + 1]));
                 const float d0 = bf16_lo(a), d1 = bf16_hi(a);   // dxn = bf16(acc); exact 0 in pad columns
-                const float h0 = (bf16_lo(xw[e]) - mean) * rstd, h1 = (bf16_hi(xw[e]) - mean) * rstd;
+                const float h0 = fmaf(bf16_lo(xw[e]), rstd, nmr), h1 = fmaf(bf16_hi(xw[e]), rstd, nmr);   // xhat
                 const float q0 = d0 * gg[2 * e], q1 = d1 * gg[2 * e + 1];
                 s1 += q0 + q1;
                 s2 = fmaf(q0, h0, fmaf(q1, h1, s2));
@@ -500,8 +500,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           s_red[(0 * 2 + half) * 128 + row] = s1;
           s_red[(1 * 2 + half) * 128 + row] = s2;
           named_bar_sync(1, Cfg::kEpiThreads);
-          const float c1 = (s_red[(0 * 2 + 0) * 128 + row] + s_red[(0 * 2 + 1) * 128 + row]) * inv_n;
-          const float c2 = (s_red[(1 * 2 + 0) * 128 + row] + s_red[(1 * 2 + 1) * 128 + row]) * inv_n;
+          // dx = rstd * (dxn * gamma - c1 - xhat * c2), with rstd folded into the row constants
+          const float c1r = (s_red[(0 * 2 + 0) * 128 + row] + s_red[(0 * 2 + 1) * 128 + row]) * inv_n * rstd;
+          const float c2r = (s_red[(1 * 2 + 0) * 128 + row] + s_red[(1 * 2 + 1) * 128 + row]) * inv_n * rstd;
 #pragma unroll
           for (int ci = 0; ci < NCH; ++ci) {
             const int c32 = half * NCH + ci;
@@ -522,9 +523,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const uint32_t a = pack_bf16(__uint_as_float(r[i * 8 + 2 * e]), __uint_as_float(r[i * 8 + 2 * e + 1]));
-                const float h0 = (bf16_lo(xw[e]) - mean) * rstd, h1 = (bf16_hi(xw[e]) - mean) * rstd;
-                const float x0 = rstd * (fmaf(bf16_lo(a), gg[2 * e], -c1) - h0 * c2);
-                const float x1 = rstd * (fmaf(bf16_hi(a), gg[2 * e + 1], -c1) - h1 * c2);
+                const float h0 = fmaf(bf16_lo(xw[e]), rstd, nmr), h1 = fmaf(bf16_hi(xw[e]), rstd, nmr);
+                const float x0 = fmaf(-h0, c2r, fmaf(bf16_lo(a) * rstd, gg[2 * e], -c1r));
+                const float x1 = fmaf(-h1, c2r, fmaf(bf16_hi(a) * rstd, gg[2 * e + 1], -c1r));
                 const uint32_t dx = pack_bf16(x0, x1);   // LayerNorm input gradient, rounded like the reference's bf16 tensor
                 o[e] = pack_bf16(bf16_lo(dw[e]) + bf16_lo(dx), bf16_hi(dw[e]) + bf16_hi(dx));
               }

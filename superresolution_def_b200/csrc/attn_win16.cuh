@@ -356,8 +356,9 @@ __global__ void __launch_bounds__(A16_FWD_THREADS, 2) win_attn16_fwd_kernel(cons
 }
 
 // ============================================================================ backward
-// grid (gx, heads); 512 threads = 16 warps, warp w owns query row-group qy = w of one whole window per work item.
-constexpr int A16_BWD_THREADS = 512;
+// grid (gx, heads); 256 threads = 8 warps, warp w owns query row-groups 2w, 2w+1 of one whole window per work item
+// (two m-tiles per warp: halves the shared-memory fragment traffic, which is this kernel's limiter).
+constexpr int A16_BWD_THREADS = 256;
 template <int MODE>
 struct A16BwdSmem {
   static constexpr int kQ = 0;                                  // [256][32]
@@ -370,59 +371,54 @@ struct A16BwdSmem {
   static constexpr int kBytes = kOut + 2 * 64 * 64;
 };
 
-// dst[16 keys x 16 cols] = A^T B: A = t64 tile [256 q][64 slots] (this warp: slots k0..k0+15), B = t32 tile [256 q][32]
-// (column half ch), contraction over the 256 queries.  Fragments of step kk+1 are fetched before the MMAs of step kk
-// are issued, and even / odd steps accumulate into separate registers (two independent HMMA chains per n-tile).
-__device__ __forceinline__ void tileT_times_tile256(uint32_t a_tile, uint32_t b_tile, int k0, int ch, int lane,
-                                                    float (&o)[2][4]) {
-  float oo[2][2][4];
+// dst[16 slots x 32 cols] = A^T B: A = t64 tile [256 q][64 slots] (this warp: slots k0..k0+15), B = t32 tile [256 q][32],
+// contraction over the 256 queries.  One transposed A fragment feeds four MMAs (all four 8-column n-tiles); the
+// fragments of step kk+1 are fetched before the MMAs of step kk are issued.
+__device__ __forceinline__ void tileT_times_tile256(uint32_t a_tile, uint32_t b_tile, int k0, int lane, float (&o)[4][4]) {
 #pragma unroll
-  for (int p = 0; p < 2; ++p)
-#pragma unroll
-    for (int n = 0; n < 2; ++n) oo[p][n][0] = oo[p][n][1] = oo[p][n][2] = oo[p][n][3] = 0.f;
+  for (int n = 0; n < 4; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
   const int ia = lane >> 3;
   const uint32_t a_base = a_tile + t64_off((lane & 7) + ((ia >> 1) & 1) * 8, (k0 + (ia & 1) * 8) >> 3);
-  const uint32_t b_base = b_tile + t32_off((lane & 7) + ((lane >> 3) & 1) * 8, ch * 2 + (lane >> 4));
+  const uint32_t b_base = b_tile + t32_off((lane & 7) + ((lane >> 3) & 1) * 8, lane >> 4);
   // rows advance by 16 per step: +16*128 B in the t64 tile, +16*64 B in the t32 tile; the swizzle terms depend on
-  // (row & 7) and ((row >> 1) & 3) only, which a multiple of 16 rows leaves unchanged
-  uint32_t af[2][4], bf[2][4];
-  ldsm_x4_t(a_base, af[0][0], af[0][1], af[0][2], af[0][3]);
-  ldsm_x4_t(b_base, bf[0][0], bf[0][1], bf[0][2], bf[0][3]);
+  // (row & 7) and ((row >> 1) & 3) only, which a multiple of 16 rows leaves unchanged; chunk pair 2,3 = address ^ 32
+  uint32_t af[2][4], b0[2][4], b1[2][4];
+  auto fetch = [&](int kk, int buf) {
+    ldsm_x4_t(a_base + kk * 16 * 128, af[buf][0], af[buf][1], af[buf][2], af[buf][3]);
+    ldsm_x4_t(b_base + kk * 16 * 64, b0[buf][0], b0[buf][1], b0[buf][2], b0[buf][3]);
+    ldsm_x4_t((b_base + kk * 16 * 64) ^ 32u, b1[buf][0], b1[buf][1], b1[buf][2], b1[buf][3]);
+  };
+  fetch(0, 0);
 #pragma unroll
   for (int kk = 0; kk < 16; ++kk) {
-    const int cur = kk & 1, nxt = cur ^ 1;
-    if (kk + 1 < 16) {
-      ldsm_x4_t(a_base + (kk + 1) * 16 * 128, af[nxt][0], af[nxt][1], af[nxt][2], af[nxt][3]);
-      ldsm_x4_t(b_base + (kk + 1) * 16 * 64, bf[nxt][0], bf[nxt][1], bf[nxt][2], bf[nxt][3]);
-    }
-    mma_bf16(oo[cur][0], af[cur], bf[cur][0], bf[cur][1]);
-    mma_bf16(oo[cur][1], af[cur], bf[cur][2], bf[cur][3]);
+    const int cur = kk & 1;
+    if (kk + 1 < 16) fetch(kk + 1, cur ^ 1);
+    mma_bf16(o[0], af[cur], b0[cur][0], b0[cur][1]);
+    mma_bf16(o[1], af[cur], b0[cur][2], b0[cur][3]);
+    mma_bf16(o[2], af[cur], b1[cur][0], b1[cur][1]);
+    mma_bf16(o[3], af[cur], b1[cur][2], b1[cur][3]);
   }
-#pragma unroll
-  for (int n = 0; n < 2; ++n)
-#pragma unroll
-    for (int e = 0; e < 4; ++e) o[n][e] = oo[0][n][e] + oo[1][n][e];
 }
 
 // Bias-table gradient as a tensor-core diagonal sum.  For every (query row qy, key row / band) pair the 16x16 block
 // X[qx][kx] of dS contributes  D[b] = sum_{qx,kx} R[b; qx,kx] X[qx][kx]  with R = [b == 15 + qx - kx] (MODE_SELF) or
 // [b == 15 + kx - qx] (MODE_OCA).  As an MMA: M = b (32 diagonals, two m-tiles), K = (qx, kx) (16 k-steps of 16),
-// N = 8 pairs.  Per key tile there are 64 pairs = 8 n-tiles; warp w takes n-tile w&7 and m-tile w>>3.
+// N = 8 pairs.  Per key tile there are 64 pairs = 8 n-tiles; warp j takes n-tile j (its own two query rows) and both m-tiles.
 // Pair n of n-tile j: query row qy = 2j + (n>>2), in-tile key row/band index r = n&3 (its 16 slots = columns r*16..).
 // The A operand (the 0/1 Toeplitz selector R) is never materialised: each fragment word is zero or one-hot.
 template <int MODE>
-__device__ __forceinline__ void diag_mma(uint32_t ds_tile, int warp, int lane, float (&acc)[4]) {
-  const int j = warp & 7, mt = warp >> 3;
-  acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+__device__ __forceinline__ void diag_mma(uint32_t ds_tile, int j, int lane, float (&acc)[2][4]) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) acc[mt][0] = acc[mt][1] = acc[mt][2] = acc[mt][3] = 0.f;
   const int n = lane & 7;                       // ldmatrix row provider (B operand): pair index
   const int prow = (2 * j + (n >> 2)) * 16;     // first dS row of that pair's query row-group
   const int pchunk = (n & 3) * 2 + ((lane >> 3) & 1);
   // A operand built in registers (shared-memory bandwidth is this kernel's limiter, ALU is not): fragment word
   // (row b, k pair 2t, 2t+1) is one-hot iff the selected k = qx + c equals 2t or 2t+1.
   const int g = lane >> 2, t = lane & 3;
-  const int b_lo = mt * 16 + g;
-  // p = (selected k) - 2t for row b_lo at step qx = 0; row b_lo + 8 selects k -/+ 8 (SELF / OCA), k + 8 columns see p - 8
-  const int p0 = ((MODE == MODE_SELF) ? (15 - b_lo) : (b_lo - 15)) - 2 * t;
+  // p = (selected k) - 2t for row b = g of m-tile 0 at step qx = 0; rows b + 8 / + 16 / + 24 shift it by -/+ 8, 16, 24
+  const int p0 = ((MODE == MODE_SELF) ? (15 - g) : (g - 15)) - 2 * t;
+  constexpr int RS = (MODE == MODE_SELF) ? -8 : 8;   // change of the selected k per +8 rows
   auto onehot2 = [](int p) -> uint32_t { return (uint32_t(p) < 2u) ? (0x3F80u << (16 * p)) : 0u; };
   // prow is a multiple of 16, so the swizzle term of row prow + qx is (qx & 7): a compile-time constant per step
   const uint32_t ds_row0 = ds_tile + uint32_t(prow) * 128u;
@@ -430,7 +426,6 @@ __device__ __forceinline__ void diag_mma(uint32_t ds_tile, int warp, int lane, f
     asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];"
                  : "=r"(b[0]), "=r"(b[1]) : "r"(ds_row0 + uint32_t(qx) * 128u + (uint32_t(pchunk ^ (qx & 7)) << 4)));
   };
-  float acc2[4] = {0.f, 0.f, 0.f, 0.f};
   uint32_t bq[2][2];
   fetch(0, bq[0]);
 #pragma unroll
@@ -438,17 +433,87 @@ __device__ __forceinline__ void diag_mma(uint32_t ds_tile, int warp, int lane, f
     const int cur = qx & 1, nxt = cur ^ 1;
     if (qx + 1 < 16) fetch(qx + 1, bq[nxt]);
     const int p = p0 + qx;
-    const int p_hi = (MODE == MODE_SELF) ? p - 8 : p + 8;   // row b_lo + 8
-    uint32_t af[4];
-    af[0] = onehot2(p);          // (row b_lo,     k 2t..2t+1)
-    af[1] = onehot2(p_hi);       // (row b_lo + 8, k 2t..2t+1)
-    af[2] = onehot2(p - 8);      // (row b_lo,     k 2t+8..2t+9)
-    af[3] = onehot2(p_hi - 8);   // (row b_lo + 8, k 2t+8..2t+9)
-    if (cur == 0) mma_bf16(acc, af, bq[cur][0], bq[cur][1]);
-    else mma_bf16(acc2, af, bq[cur][0], bq[cur][1]);
-  }
 #pragma unroll
-  for (int e = 0; e < 4; ++e) acc[e] += acc2[e];
+    for (int mt = 0; mt < 2; ++mt) {
+      const int pm = p + 2 * mt * RS;   // rows b = 16*mt + g
+      uint32_t af[4];
+      af[0] = onehot2(pm);              // (row b,     k 2t..2t+1)
+      af[1] = onehot2(pm + RS);         // (row b + 8, k 2t..2t+1)
+      af[2] = onehot2(pm - 8);          // (row b,     k 2t+8..2t+9)
+      af[3] = onehot2(pm + RS - 8);     // (row b + 8, k 2t+8..2t+9)
+      mma_bf16(acc[mt], af, bq[cur][0], bq[cur][1]);
+    }
+  }
+}
+
+// Two-m-tile variants (backward): a warp owns 32 query rows (two row-groups), so every K / V fragment fetched from
+// shared memory feeds four MMAs instead of two.
+template <int MODE>
+__device__ __forceinline__ void qk_tile2(const uint32_t (&aq)[2][2][4], uint32_t k_tile, const float* bp0, const float* bp1,
+                                         const MaskCtx& mk, int lane, float (&s)[2][8][4]) {
+  const uint32_t kb_base = k_tile + t32_off(lane & 7, lane >> 3);   // + nt * 8 rows = nt * 512 B (swizzle unchanged)
+  uint32_t kb[2][4];
+  ldsm_x4(kb_base, kb[0][0], kb[0][1], kb[0][2], kb[0][3]);
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const int cur = nt & 1, nxt = cur ^ 1;
+    if (nt + 1 < 8 && nt_valid<MODE>(nt + 1))
+      ldsm_x4(kb_base + (nt + 1) * 512, kb[nxt][0], kb[nxt][1], kb[nxt][2], kb[nxt][3]);
+    if (!nt_valid<MODE>(nt)) {
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) s[mt][nt][0] = s[mt][nt][1] = s[mt][nt][2] = s[mt][nt][3] = -INFINITY;
+      continue;
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const float* bp = mt ? bp1 : bp0;
+      s[mt][nt][0] = bp[bias_const<MODE>(nt, 0, 0)];
+      s[mt][nt][1] = bp[bias_const<MODE>(nt, 1, 0)];
+      s[mt][nt][2] = bp[bias_const<MODE>(nt, 0, 1)];
+      s[mt][nt][3] = bp[bias_const<MODE>(nt, 1, 1)];
+      mma_bf16(s[mt][nt], aq[mt][0], kb[cur][0], kb[cur][1]);
+      mma_bf16(s[mt][nt], aq[mt][1], kb[cur][2], kb[cur][3]);
+    }
+  }
+  if (MODE == MODE_SELF && mk.any) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const float m01 = (nt & 1) ? mk.diff : mk.same, m23 = (nt & 1) ? mk.same : mk.diff;
+        s[mt][nt][0] += m01; s[mt][nt][1] += m01; s[mt][nt][2] += m23; s[mt][nt][3] += m23;
+      }
+  }
+}
+
+// o[mt][16 x 32] += A_mt[16 x 64] (bf16 fragments built from fp32 s[mt]) * Bt[64 x 32], both m-tiles per B fragment
+__device__ __forceinline__ void frag_times_tile_acc2(const float (&s)[2][8][4], uint32_t bt_tile, int lane,
+                                                     float (&o)[2][4][4]) {
+  const uint32_t b_base = bt_tile + t32_off((lane & 7) + ((lane >> 3) & 1) * 8, lane >> 4);
+  auto frag_addr = [&](int step) { return (b_base + (step >> 1) * 16 * 64) ^ (uint32_t(step & 1) << 5); };
+  uint32_t bf[2][4];
+  ldsm_x4_t(frag_addr(0), bf[0][0], bf[0][1], bf[0][2], bf[0][3]);
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    uint32_t a[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      a[mt][0] = pack_bf16(s[mt][2 * kk][0], s[mt][2 * kk][1]);
+      a[mt][1] = pack_bf16(s[mt][2 * kk][2], s[mt][2 * kk][3]);
+      a[mt][2] = pack_bf16(s[mt][2 * kk + 1][0], s[mt][2 * kk + 1][1]);
+      a[mt][3] = pack_bf16(s[mt][2 * kk + 1][2], s[mt][2 * kk + 1][3]);
+    }
+#pragma unroll
+    for (int np = 0; np < 2; ++np) {
+      const int step = kk * 2 + np, cur = step & 1, nxt = cur ^ 1;
+      if (step + 1 < 8) ldsm_x4_t(frag_addr(step + 1), bf[nxt][0], bf[nxt][1], bf[nxt][2], bf[nxt][3]);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        mma_bf16(o[mt][2 * np], a[mt], bf[cur][0], bf[cur][1]);
+        mma_bf16(o[mt][2 * np + 1], a[mt], bf[cur][2], bf[cur][3]);
+      }
+    }
+  }
 }
 
 template <int MODE>
@@ -465,15 +530,18 @@ __global__ void __launch_bounds__(A16_BWD_THREADS, 1) win_attn16_bwd_kernel(cons
                  sDS = sm0 + L::kDS, sOut = sm0 + L::kOut;
   const int h = blockIdx.y;
   const int nwin = a.B * (a.H >> 4) * (a.W >> 4);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;   // 8 warps; warp w owns query row-groups 2w, 2w+1
   const int g = lane >> 2, t = lane & 3;
   const int hw = a.heads * 32;
   constexpr float kLog2e = 1.4426950408889634f;
   load_bias_table<MODE>(s_bias, a.bias_table, a.heads, h, A16_BWD_THREADS);
-  // this CTA's slice of the diagonal-sum scratch: [NKT][16 warps][32 lanes] float4, exclusively owned per thread
+  // this CTA's slice of the diagonal-sum scratch: [NKT][16 = m-tile*8 + n-tile][32 lanes] float4, owned per thread
   float4* scratch = reinterpret_cast<float4*>(a.dbias_scratch) +
                     ((size_t)blockIdx.x * a.heads + h) * (G::NKT * 16 * 32);
-  for (int kt = 0; kt < G::NKT; ++kt) scratch[(kt * 16 + warp) * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int kt = 0; kt < G::NKT; ++kt) {
+    scratch[(kt * 16 + warp) * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+    scratch[(kt * 16 + 8 + warp) * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
 
   for (int w = blockIdx.x; w < nwin; w += gridDim.x) {
     const WinPos p = win_pos(a, w);
@@ -483,8 +551,8 @@ __global__ void __launch_bounds__(A16_BWD_THREADS, 1) win_attn16_bwd_kernel(cons
     {
       const int ch = threadIdx.x & 3;
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int i = (threadIdx.x >> 2) + 128 * k;
+      for (int k = 0; k < 4; ++k) {
+        const int i = (threadIdx.x >> 2) + 64 * k;
         const long long tok = s_qtok[i];
         cp_async16(sQ + t32_off(i, ch), a.qkv + tok * a.ld_qkv + h * 32 + ch * 8);
         cp_async16(sDO + t32_off(i, ch), a.dout + tok * a.ld_o + h * 32 + ch * 8);
@@ -494,55 +562,62 @@ __global__ void __launch_bounds__(A16_BWD_THREADS, 1) win_attn16_bwd_kernel(cons
     cp_async_commit();
     const bool shifted = (MODE == MODE_SELF) && a.shift > 0;
     const bool last_y = shifted && p.wy == (a.H >> 4) - 1, last_x = shifted && p.wx == (a.W >> 4) - 1;
-    {  // delta_i = sum_d dO[i,d] * O[i,d]   (two threads per query row, 16 columns each), lse
-      const int i = threadIdx.x >> 1, hf = threadIdx.x & 1;
+    {  // delta_i = sum_d dO[i,d] * O[i,d]  (one thread per query row), lse
+      const int i = threadIdx.x;
       const long long tok = s_qtok[i];
-      const uint4* po = reinterpret_cast<const uint4*>(a.osave + tok * a.ld_o + h * 32 + hf * 16);
-      const uint4* pd = reinterpret_cast<const uint4*>(a.dout + tok * a.ld_o + h * 32 + hf * 16);
+      const uint4* po = reinterpret_cast<const uint4*>(a.osave + tok * a.ld_o + h * 32);
+      const uint4* pd = reinterpret_cast<const uint4*>(a.dout + tok * a.ld_o + h * 32);
       float acc = 0.f;
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
+      for (int k = 0; k < 4; ++k) {
         const uint4 vo = po[k], vd = pd[k];
         const uint32_t wo[4] = {vo.x, vo.y, vo.z, vo.w}, wd[4] = {vd.x, vd.y, vd.z, vd.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc += bf16_lo(wo[e]) * bf16_lo(wd[e]) + bf16_hi(wo[e]) * bf16_hi(wd[e]);
       }
-      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-      if (hf == 0) {
-        s_delta[i] = acc;
-        s_lse[i] = a.lse[(long long)h * a.T + tok] * kLog2e;
-      }
+      s_delta[i] = acc;
+      s_lse[i] = a.lse[(long long)h * a.T + tok] * kLog2e;
     }
     cp_async_wait<0>();
     __syncthreads();
-    const int r0 = warp * 16, qy = warp;
-    uint32_t aq[2][4], ad[2][4];
+    const int r0 = warp * 32;
+    uint32_t aq[2][2][4], ad[2][2][4];
+    float lse_[2][2], dl_[2][2];
 #pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
-      const int row = r0 + (lane & 7) + ((lane >> 3) & 1) * 8;
-      ldsm_x4(sQ + t32_off(row, ks * 2 + (lane >> 4)), aq[ks][0], aq[ks][1], aq[ks][2], aq[ks][3]);
-      ldsm_x4(sDO + t32_off(row, ks * 2 + (lane >> 4)), ad[ks][0], ad[ks][1], ad[ks][2], ad[ks][3]);
+    for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const int row = r0 + mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        ldsm_x4(sQ + t32_off(row, ks * 2 + (lane >> 4)), aq[mt][ks][0], aq[mt][ks][1], aq[mt][ks][2], aq[mt][ks][3]);
+        ldsm_x4(sDO + t32_off(row, ks * 2 + (lane >> 4)), ad[mt][ks][0], ad[mt][ks][1], ad[mt][ks][2], ad[mt][ks][3]);
+      }
+      lse_[mt][0] = s_lse[r0 + mt * 16 + g]; lse_[mt][1] = s_lse[r0 + mt * 16 + g + 8];
+      dl_[mt][0] = s_delta[r0 + mt * 16 + g]; dl_[mt][1] = s_delta[r0 + mt * 16 + g + 8];
     }
-    const float lse0 = s_lse[r0 + g], lse1 = s_lse[r0 + g + 8];
-    const float dl0 = s_delta[r0 + g], dl1 = s_delta[r0 + g + 8];
-    float dq[4][4];
+    float dq[2][4][4];
 #pragma unroll
-    for (int n = 0; n < 4; ++n) dq[n][0] = dq[n][1] = dq[n][2] = dq[n][3] = 0.f;
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int n = 0; n < 4; ++n) dq[mt][n][0] = dq[mt][n][1] = dq[mt][n][2] = dq[mt][n][3] = 0.f;
 
 #pragma unroll 1
     for (int kt = 0; kt < G::NKT; ++kt) {
       const uint32_t kT = sK + kt * 64 * 64, vT = sV + kt * 64 * 64;
-      // ---- phase A: this warp's 16 query rows x 64 key slots
-      float s[8][4];
-      qk_tile<MODE>(aq, kT, s_bias + bias_base<MODE>(qy, kt, g, t), mask_ctx(last_y, last_x, qy, kt), lane, s);
+      // ---- phase A: this warp's 32 query rows x 64 key slots
+      float s[2][8][4];
+      // (qy >= 8) is the same for both row-groups of a warp (2w, 2w+1), so one mask context serves both
+      qk_tile2<MODE>(aq, kT, s_bias + bias_base<MODE>(2 * warp, kt, g, t), s_bias + bias_base<MODE>(2 * warp + 1, kt, g, t),
+                     mask_ctx(last_y, last_x, 2 * warp, kt), lane, s);
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {  // P = exp(S - lse), normalised
-        s[nt][0] = fast_ex2(fmaf(s[nt][0], kLog2e, -lse0));
-        s[nt][1] = fast_ex2(fmaf(s[nt][1], kLog2e, -lse0));
-        s[nt][2] = fast_ex2(fmaf(s[nt][2], kLog2e, -lse1));
-        s[nt][3] = fast_ex2(fmaf(s[nt][3], kLog2e, -lse1));
-      }
-      uint32_t pp[2][2];
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {  // P = exp(S - lse), normalised
+          s[mt][nt][0] = fast_ex2(fmaf(s[mt][nt][0], kLog2e, -lse_[mt][0]));
+          s[mt][nt][1] = fast_ex2(fmaf(s[mt][nt][1], kLog2e, -lse_[mt][0]));
+          s[mt][nt][2] = fast_ex2(fmaf(s[mt][nt][2], kLog2e, -lse_[mt][1]));
+          s[mt][nt][3] = fast_ex2(fmaf(s[mt][nt][3], kLog2e, -lse_[mt][1]));
+        }
+      uint32_t pp[2][2][2];
       const uint32_t vb_base = vT + t32_off(lane & 7, lane >> 3);
       uint32_t vb[2][4];
       ldsm_x4(vb_base, vb[0][0], vb[0][1], vb[0][2], vb[0][3]);
@@ -550,50 +625,54 @@ __global__ void __launch_bounds__(A16_BWD_THREADS, 1) win_attn16_bwd_kernel(cons
       for (int nt = 0; nt < 8; ++nt) {  // dP = dO V^T, dS = P * (dP - delta); P, dS -> smem (bf16)
         if (nt + 1 < 8 && nt_valid<MODE>(nt + 1))
           ldsm_x4(vb_base + (nt + 1) * 512, vb[(nt + 1) & 1][0], vb[(nt + 1) & 1][1], vb[(nt + 1) & 1][2], vb[(nt + 1) & 1][3]);
-        if (!nt_valid<MODE>(nt)) {    // padding keys (always an odd n-tile): P = dS = 0, stored with its even partner
-          s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-          const int m = lane >> 3;
-          const uint32_t off = t64_off(r0 + (m & 1) * 8 + (lane & 7), nt - 1 + (m >> 1));
-          stsm_x4(sP + off, pp[0][0], pp[0][1], 0u, 0u);
-          stsm_x4(sDS + off, pack_bf16(s[nt - 1][0], s[nt - 1][1]), pack_bf16(s[nt - 1][2], s[nt - 1][3]), 0u, 0u);
-          continue;
-        }
-        float dp[4] = {0.f, 0.f, 0.f, 0.f};
-        mma_bf16(dp, ad[0], vb[nt & 1][0], vb[nt & 1][1]);
-        mma_bf16(dp, ad[1], vb[nt & 1][2], vb[nt & 1][3]);
-        pp[nt & 1][0] = pack_bf16(s[nt][0], s[nt][1]);
-        pp[nt & 1][1] = pack_bf16(s[nt][2], s[nt][3]);
-        s[nt][0] *= (dp[0] - dl0);
-        s[nt][1] *= (dp[1] - dl0);
-        s[nt][2] *= (dp[2] - dl1);
-        s[nt][3] *= (dp[3] - dl1);
-        if (nt & 1) {  // one stmatrix.x4 per n-tile pair and tile: (rows g, nt-1), (rows g+8, nt-1), (rows g, nt), (rows g+8, nt)
-          const int m = lane >> 3;
-          const uint32_t off = t64_off(r0 + (m & 1) * 8 + (lane & 7), nt - 1 + (m >> 1));
-          stsm_x4(sP + off, pp[0][0], pp[0][1], pp[1][0], pp[1][1]);
-          stsm_x4(sDS + off, pack_bf16(s[nt - 1][0], s[nt - 1][1]), pack_bf16(s[nt - 1][2], s[nt - 1][3]),
-                  pack_bf16(s[nt][0], s[nt][1]), pack_bf16(s[nt][2], s[nt][3]));
+        const int m = lane >> 3;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          const uint32_t off = t64_off(r0 + mt * 16 + (m & 1) * 8 + (lane & 7), nt - 1 + (m >> 1));  // used when nt is odd
+          if (!nt_valid<MODE>(nt)) {    // padding keys (always an odd n-tile): P = dS = 0, stored with its even partner
+            s[mt][nt][0] = s[mt][nt][1] = s[mt][nt][2] = s[mt][nt][3] = 0.f;
+            stsm_x4(sP + off, pp[mt][0][0], pp[mt][0][1], 0u, 0u);
+            stsm_x4(sDS + off, pack_bf16(s[mt][nt - 1][0], s[mt][nt - 1][1]), pack_bf16(s[mt][nt - 1][2], s[mt][nt - 1][3]), 0u, 0u);
+            continue;
+          }
+          float dp[4] = {0.f, 0.f, 0.f, 0.f};
+          mma_bf16(dp, ad[mt][0], vb[nt & 1][0], vb[nt & 1][1]);
+          mma_bf16(dp, ad[mt][1], vb[nt & 1][2], vb[nt & 1][3]);
+          pp[mt][nt & 1][0] = pack_bf16(s[mt][nt][0], s[mt][nt][1]);
+          pp[mt][nt & 1][1] = pack_bf16(s[mt][nt][2], s[mt][nt][3]);
+          s[mt][nt][0] *= (dp[0] - dl_[mt][0]);
+          s[mt][nt][1] *= (dp[1] - dl_[mt][0]);
+          s[mt][nt][2] *= (dp[2] - dl_[mt][1]);
+          s[mt][nt][3] *= (dp[3] - dl_[mt][1]);
+          if (nt & 1) {  // one stmatrix.x4 per n-tile pair and tile
+            stsm_x4(sP + off, pp[mt][0][0], pp[mt][0][1], pp[mt][1][0], pp[mt][1][1]);
+            stsm_x4(sDS + off, pack_bf16(s[mt][nt - 1][0], s[mt][nt - 1][1]), pack_bf16(s[mt][nt - 1][2], s[mt][nt - 1][3]),
+                    pack_bf16(s[mt][nt][0], s[mt][nt][1]), pack_bf16(s[mt][nt][2], s[mt][nt][3]));
+          }
         }
       }
-      frag_times_tile_acc(s, kT, lane, dq);  // dQ += dS K
+      frag_times_tile_acc2(s, kT, lane, dq);  // dQ += dS K
       __syncthreads();
       // ---- phase B: dK / dV of this key tile (contraction over all 256 queries) + bias-gradient diagonal sums
       {
-        const int m = warp >> 3, rg = (warp >> 1) & 3, ch = warp & 1;
-        float o[2][4];
-        tileT_times_tile256(m ? sP : sDS, m ? sDO : sQ, rg * 16, ch, lane, o);
-        const uint32_t dst = sOut + m * (64 * 64);
-        store_frag_pair(dst, rg * 16, ch * 2, lane, o[0], o[1], t32_off);
-        float acc[4];
+        const int m = warp >> 2, rg = warp & 3;   // matrix (dK / dV), 16-slot row group
+        float o[4][4];
+        tileT_times_tile256(m ? sP : sDS, m ? sDO : sQ, rg * 16, lane, o);
+        store_frag_t32(sOut + m * (64 * 64), rg * 16, lane, o);
+        float acc[2][4];
         diag_mma<MODE>(sDS, warp, lane, acc);
-        float4* sp = scratch + (kt * 16 + warp) * 32 + lane;
-        float4 v = *sp;
-        v.x += acc[0]; v.y += acc[1]; v.z += acc[2]; v.w += acc[3];
-        *sp = v;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          float4* sp = scratch + (kt * 16 + mt * 8 + warp) * 32 + lane;
+          float4 v = *sp;
+          v.x += acc[mt][0]; v.y += acc[mt][1]; v.z += acc[mt][2]; v.w += acc[mt][3];
+          *sp = v;
+        }
       }
       __syncthreads();
-      {  // store dK, dV rows of this tile: 2 matrices x 64 slots x 4 chunks = 512 x 16 B
-        const int c = threadIdx.x, m = c >> 8, rem = c & 255, sl = rem >> 2, ch = rem & 3;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {  // store dK, dV rows of this tile: 2 matrices x 64 slots x 4 chunks = 512 x 16 B
+        const int c = threadIdx.x + 256 * k, m = c >> 8, rem = c & 255, sl = rem >> 2, ch = rem & 3;
         const int slot = kt * 64 + sl;
         const uint4 v = lds128(sOut + m * (64 * 64) + t32_off(sl, ch));
         if (MODE == MODE_SELF) {
@@ -604,18 +683,18 @@ __global__ void __launch_bounds__(A16_BWD_THREADS, 1) win_attn16_bwd_kernel(cons
           *reinterpret_cast<uint4*>(dst) = v;
         }
       }
-      // sOut / sP / sDS are rewritten only after the next tile's first barrier (phase A writes sP/sDS before it):
-      // phase A of tile kt+1 overwrites sP/sDS while slow threads may still run phase B reads -> barrier needed,
-      // which is the __syncthreads() above (all phase B reads precede it).
+      // sOut is rewritten in the next tile's phase B, i.e. after the next tile's first barrier; sP / sDS are rewritten
+      // by the next tile's phase A, after the barrier above (all phase-B reads precede it).
     }
     // dQ -> staging (this warp's rows of the P tile region, dead after the last barrier) -> global
     __syncwarp();
-    store_frag_t32(sP, r0, lane, dq);
+    store_frag_t32(sP, r0, lane, dq[0]);
+    store_frag_t32(sP, r0 + 16, lane, dq[1]);
     __syncwarp();
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int c = lane + 32 * k, i = c >> 2, ch = c & 3;
-      const long long tok = s_qtok[qy * 16 + i];
+    for (int k = 0; k < 4; ++k) {
+      const int c = lane + 32 * k, i = c >> 2, ch = c & 3;   // 32 rows x 4 chunks
+      const long long tok = s_qtok[r0 + i];
       *reinterpret_cast<uint4*>(a.dqkv + tok * a.ld_qkv + h * 32 + ch * 8) = lds128(sP + t32_off(r0 + i, ch));
     }
   }

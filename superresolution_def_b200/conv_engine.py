@@ -92,24 +92,28 @@ class SwinIRTailFunction(torch.autograd.Function):
         dev = body.device
         Cp = body.shape[1]
         F = w_bu.shape[0]  # 64
-        if F != 64 or w_u0.shape[0] != 256 or w_u2.shape[0] != 256 or w_last.shape[0] != 1:
+        if F != 64 or w_u0.shape[0] != 256 or (w_u2 is not None and w_u2.shape[0] != 256) or w_last.shape[0] != 1:
             raise capi.SrkError("SwinIR tail kernels are specialised for num_feat=64, x4 PixelShuffle, 1 output channel")
         wf_ab, _, bp_ab = conv_weights(w_ab, b_ab, Cp, Cp)
         wf_bu, _, bp_bu = conv_weights(w_bu, b_bu, 64, Cp)
         wf_u0, _, bp_u0 = conv_weights(w_u0, b_u0, 256, 64, ps=True)
-        wf_u2, _, bp_u2 = conv_weights(w_u2, b_u2, 256, 64, ps=True)
+        two = w_u2 is not None   # x4 = two conv+PixelShuffle(2) stages, x2 = one (Upsample, architecture_swin.py:175-190)
+        up = 4 if two else 2
         res = torch.empty(B * H * W, Cp, device=dev, dtype=BF16)
         capi.conv3x3_igemm(capi.CEPI_BIAS_RES, B, H, W, Cp, Cp, C, body, wf_ab, bp_ab, res, r=first)
         t64 = torch.empty(B * H * W, 64, device=dev, dtype=BF16)
         capi.conv3x3_igemm(capi.CEPI_BIAS_LRELU, B, H, W, Cp, 64, 64, res, wf_bu, bp_bu, t64, slope=0.01)
         u0 = torch.empty(B * 2 * H * 2 * W, 64, device=dev, dtype=BF16)
         capi.conv3x3_igemm(capi.CEPI_BIAS, B, H, W, 64, 256, 256, t64, wf_u0, bp_u0, u0, y_ps=True)
-        u1 = torch.empty(B * 4 * H * 4 * W, 64, device=dev, dtype=BF16)
-        capi.conv3x3_igemm(capi.CEPI_BIAS, B, 2 * H, 2 * W, 64, 256, 256, u0, wf_u2, bp_u2, u1, y_ps=True)
-        out = torch.empty(B, 1, 4 * H, 4 * W, device=dev, dtype=torch.float32)
+        u1 = u0
+        if two:
+            wf_u2, _, bp_u2 = conv_weights(w_u2, b_u2, 256, 64, ps=True)
+            u1 = torch.empty(B * 4 * H * 4 * W, 64, device=dev, dtype=BF16)
+            capi.conv3x3_igemm(capi.CEPI_BIAS, B, 2 * H, 2 * W, 64, 256, 256, u0, wf_u2, bp_u2, u1, y_ps=True)
+        out = torch.empty(B, 1, up * H, up * W, device=dev, dtype=torch.float32)
         # conv_last (64 -> 1): tcgen05 implicit GEMM with N = 16 (one real column), fp32 result straight from TMEM
         wf_l, _, bp_l = conv_weights(w_last, b_last, 16, 64)
-        capi.conv3x3_igemm(capi.CEPI_OUT1, B, 4 * H, 4 * W, 64, 16, 1, u1, wf_l, bp_l, out)
+        capi.conv3x3_igemm(capi.CEPI_OUT1, B, up * H, up * W, 64, 16, 1, u1, wf_l, bp_l, out)
         if any(ctx.needs_input_grad):
             ctx.saved = (body, res, t64, u0, u1)
             ctx.params = (w_ab, b_ab, w_bu, b_bu, w_u0, b_u0, w_u2, b_u2, w_last, b_last)
@@ -124,17 +128,22 @@ class SwinIRTailFunction(torch.autograd.Function):
         dev = dout.device
         f32 = torch.float32
         dout = dout.contiguous().float()
+        two = w_u2 is not None
+        up = 4 if two else 2
         # conv_last
         d_u1 = torch.empty_like(u1)
         dw_last, db_last = torch.empty_like(w_last), torch.empty_like(b_last)
-        capi.conv_out1_bwd(dout, u1, w_last.detach(), d_u1, dw_last, db_last, B, 4 * H, 4 * W, 64)
-        # upsample.2 (input u0 at 2H x 2W, gradient arrives pixel-shuffled at 4H x 4W)
-        _, wt_u2, _ = conv_weights(w_u2, b_u2, 256, 64, ps=True, refresh=False)
-        d_u0 = torch.empty_like(u0)
-        capi.conv3x3_igemm(capi.CEPI_BIAS, B, 2 * H, 2 * W, 256, 64, 64, d_u1, wt_u2, None, d_u0, x_ps=True)
-        dw_u2, db_u2 = torch.empty_like(w_u2), torch.empty_like(b_u2)
-        capi.conv3x3_wgrad(B, 2 * H, 2 * W, 64, 256, 64, 256, True, d_u1, u0, dw_u2)
-        capi.bias_grad_nhwc(d_u1, B, 2 * H, 2 * W, 256, True, db_u2)
+        capi.conv_out1_bwd(dout, u1, w_last.detach(), d_u1, dw_last, db_last, B, up * H, up * W, 64)
+        dw_u2 = db_u2 = None
+        d_u0 = d_u1
+        if two:
+            # upsample.2 (input u0 at 2H x 2W, gradient arrives pixel-shuffled at 4H x 4W)
+            _, wt_u2, _ = conv_weights(w_u2, b_u2, 256, 64, ps=True, refresh=False)
+            d_u0 = torch.empty_like(u0)
+            capi.conv3x3_igemm(capi.CEPI_BIAS, B, 2 * H, 2 * W, 256, 64, 64, d_u1, wt_u2, None, d_u0, x_ps=True)
+            dw_u2, db_u2 = torch.empty_like(w_u2), torch.empty_like(b_u2)
+            capi.conv3x3_wgrad(B, 2 * H, 2 * W, 64, 256, 64, 256, True, d_u1, u0, dw_u2)
+            capi.bias_grad_nhwc(d_u1, B, 2 * H, 2 * W, 256, True, db_u2)
         # upsample.0 (+ LeakyReLU backward fused into the input-gradient epilogue)
         _, wt_u0, _ = conv_weights(w_u0, b_u0, 256, 64, ps=True, refresh=False)
         d_t64 = torch.empty_like(t64)
@@ -168,6 +177,8 @@ def conv3x3_tokens(x, weight, bias, Cp: int):
 
 
 def swinir_tail(body, first, geom, C, conv_after_body, conv_before_up, upsample, conv_last):
+    two = len(upsample) > 2   # x4: Sequential(conv, PixelShuffle, conv, PixelShuffle); x2: (conv, PixelShuffle)
     return SwinIRTailFunction.apply(body, first, geom, C, conv_after_body.weight, conv_after_body.bias,
                                     conv_before_up.weight, conv_before_up.bias, upsample[0].weight, upsample[0].bias,
-                                    upsample[2].weight, upsample[2].bias, conv_last.weight, conv_last.bias)
+                                    upsample[2].weight if two else None, upsample[2].bias if two else None,
+                                    conv_last.weight, conv_last.bias)

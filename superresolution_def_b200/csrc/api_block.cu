@@ -2,7 +2,7 @@
 // (a fixed sequence of the tcgen05 GEMMs, the window-attention core and the small aux kernels), plus the
 // stand-alone window-attention and LayerNorm ops.  Host code only orchestrates launches on the caller's
 // stream; it never allocates or synchronises.
-#include "attn_win16.cuh"
+#include "attn_oca8.cuh"
 #include "cab_aux.cuh"
 #include "block_aux.cuh"
 #include "srk_host.h"
@@ -17,14 +17,16 @@ inline BlockDims to_dims(const SrkBlockDims* d) {
   return o;
 }
 
-int check_dims(const SrkBlockDims* d, const SrkGeom* g, int ws = 8) {
+int check_dims(const SrkBlockDims* d, const SrkGeom* g, bool hat = false) {
   if (!d) return fail(SRK_ERR_ARG, "null dims");
   if (d->Cp != 192 || d->heads * d->ds != 192 || d->ds != 32)
     return fail(SRK_ERR_UNSUPPORTED, "block kernels are specialised for Cp == heads*ds == 192, ds == 32");
   if (d->C >= d->Cp || d->dh >= d->ds || d->hidden >= d->Hp || d->Hp % 256 != 0 || d->C != d->heads * d->dh)
     return fail(SRK_ERR_UNSUPPORTED, "need C < Cp, dh < ds, hidden < Hp, Hp % 256 == 0, C == heads*dh");
   if (g) {
-    if (g->ws != ws) return fail(SRK_ERR_UNSUPPORTED, "window attention cores are specialised for ws == 8 (Swin) / 16 (HAT)");
+    const int ws = g->ws;
+    if (ws != 8 && !(hat && ws == 16))
+      return fail(SRK_ERR_UNSUPPORTED, "window attention cores are specialised for ws == 8 (Swin, HAT) / 16 (HAT)");
     if (g->H % ws || g->W % ws || g->shift < 0 || g->shift >= ws) return fail(SRK_ERR_ARG, "bad geometry");
     if ((long long)g->B * g->H * g->W % 128 != 0) return fail(SRK_ERR_ARG, "B*H*W must be a multiple of 128");
   }
@@ -75,8 +77,9 @@ WsLayout ws_layout(const SrkBlockDims* d, const SrkGeom* g) {
 }
 
 int launch_attn_fwd(const SrkGeom* g, int heads, const void* qkv, int ld_qkv, const float* table, void* out, int ld_o,
-                    int ones_col, cudaStream_t stream) {
+                    int ones_col, cudaStream_t stream, int mask = 0) {
   AttnArgs a{};
+  a.mask = mask;
   a.qkv = static_cast<const __nv_bfloat16*>(qkv);
   a.out = static_cast<__nv_bfloat16*>(out);
   a.bias_table = table;
@@ -91,7 +94,7 @@ int launch_attn_fwd(const SrkGeom* g, int heads, const void* qkv, int ld_qkv, co
 }
 
 int launch_attn_bwd(const SrkGeom* g, int heads, const void* qkv, int ld_qkv, const float* table, const void* dout,
-                    int ld_o, void* dqkv, float* partials, int gx, cudaStream_t stream) {
+                    int ld_o, void* dqkv, float* partials, int gx, cudaStream_t stream, int mask = 0) {
   static bool configured = false;
   if (!configured) {
     SRK_CUDA_OK(cudaFuncSetAttribute(win_attn_ws8_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -104,6 +107,7 @@ int launch_attn_bwd(const SrkGeom* g, int heads, const void* qkv, int ld_qkv, co
   a.dqkv = static_cast<__nv_bfloat16*>(dqkv);
   a.bias_table = table;
   a.dbias_partials = partials;
+  a.mask = mask;
   a.B = g->B; a.H = g->H; a.W = g->W; a.heads = heads; a.shift = g->shift;
   a.ld_qkv = ld_qkv; a.ld_o = ld_o; a.ones_col = -1;
   dim3 grid(gx, heads);
@@ -138,9 +142,27 @@ int attn16_bwd_gx(int nwin, int heads) {
   return gx < 1 ? 1 : gx;
 }
 
-struct Attn16Ws { size_t scratch_off, dkv_off, total; int gx; };
+struct Attn16Ws { size_t scratch_off, dkv_off, dense_off, total; int gx; };
+int oca8_bwd_gx(int nwin, int heads) {
+  int gx = num_sms() * 2 / heads;
+  if (gx > nwin) gx = nwin;
+  return gx < 1 ? 1 : gx;
+}
 Attn16Ws attn16_ws_layout(const SrkGeom* g, int mode, int heads) {
   Attn16Ws L{};
+  if (g->ws == 8) {  // HAT at window 8: SELF runs on the ws-8 core (partials live in the block scratch); OCA = 12x12 keys
+    const int nwin = g->B * (g->H / 8) * (g->W / 8);
+    L.gx = oca8_bwd_gx(nwin, heads);
+    size_t o = 0;
+    if (mode == MODE_SELF) o = (size_t)attn_bwd_gx(nwin, heads) * heads * 225 * sizeof(float);
+    if (mode == MODE_OCA) {
+      L.scratch_off = o; o += (size_t)L.gx * heads * 4 * O8_NT * 32 * 4 * sizeof(float);
+      L.dense_off = o; o += (size_t)heads * 64 * O8_NK * sizeof(float);
+      L.dkv_off = o; o += (size_t)nwin * heads * 2 * O8_NK * 32 * sizeof(__nv_bfloat16);
+    }
+    L.total = o < 256 ? 256 : o;
+    return L;
+  }
   const int nwin = g->B * (g->H / 16) * (g->W / 16);
   L.gx = attn16_bwd_gx(nwin, heads);
   const int nkt = mode == MODE_SELF ? 4 : 12;
@@ -180,10 +202,11 @@ int launch_attn16_bwd_t(Attn16Args a, void* ws, const Attn16Ws& L, float* d_tabl
 }
 
 int check_attn16(const SrkGeom* g, int mode, int ld_qkv, int ld_out) {
-  if (!g || g->ws != 16 || g->H % 16 || g->W % 16) return fail(SRK_ERR_UNSUPPORTED, "srk_win_attn16: ws must be 16");
+  if (!g || (g->ws != 16 && g->ws != 8) || g->H % g->ws || g->W % g->ws)
+    return fail(SRK_ERR_UNSUPPORTED, "srk_win_attn16: HAT window attention supports ws 16 and ws 8");
   if (mode != MODE_SELF && mode != MODE_OCA) return fail(SRK_ERR_ARG, "srk_win_attn16: mode");
   if (mode == MODE_OCA && g->shift != 0) return fail(SRK_ERR_ARG, "srk_win_attn16: OCA has no shift");
-  if (mode == MODE_SELF && g->shift != 0 && g->shift != 8) return fail(SRK_ERR_UNSUPPORTED, "srk_win_attn16: shift must be 0 or ws/2");
+  if (mode == MODE_SELF && g->shift != 0 && g->shift != g->ws / 2) return fail(SRK_ERR_UNSUPPORTED, "srk_win_attn16: shift must be 0 or ws/2");
   if (ld_qkv % 8 || ld_out % 8) return fail(SRK_ERR_ARG, "srk_win_attn16: rows must be 16-byte aligned");
   return SRK_OK;
 }
@@ -198,6 +221,22 @@ int attn16_fwd(const SrkGeom* g, int mode, int heads, const void* qkv, int ld_qk
   a.B = g->B; a.H = g->H; a.W = g->W; a.heads = heads; a.shift = g->shift;
   a.ld_qkv = ld_qkv; a.ld_o = ld_out; a.ones_col = ones_col;
   a.T = (long long)g->B * g->H * g->W;
+  if (g->ws == 8) {
+    if (mode == MODE_SELF) return launch_attn_fwd(g, heads, qkv, ld_qkv, table, out, ld_out, ones_col, stream, 1);
+    static bool configured = false;
+    if (!configured) {
+      SRK_CUDA_OK(cudaFuncSetAttribute(win_attn_oca8_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, O8_FWD_SMEM));
+      configured = true;
+    }
+    const int nwin = g->B * (g->H / 8) * (g->W / 8);
+    int gx = num_sms() * 3 / heads;
+    if (gx > nwin) gx = nwin;
+    if (gx < 1) gx = 1;
+    win_attn_oca8_fwd_kernel<<<dim3(gx, heads), O8_THREADS, O8_FWD_SMEM, stream>>>(a);
+    SRK_LAUNCHED(1);
+    SRK_CUDA_OK(cudaGetLastError());
+    return SRK_OK;
+  }
   return mode == MODE_SELF ? launch_attn16_fwd_t<MODE_SELF>(a, stream) : launch_attn16_fwd_t<MODE_OCA>(a, stream);
 }
 
@@ -215,6 +254,33 @@ int attn16_bwd(const SrkGeom* g, int mode, int heads, const void* qkv, int ld_qk
   a.ld_qkv = ld_qkv; a.ld_o = ld_out; a.ones_col = -1;
   a.T = (long long)g->B * g->H * g->W;
   const Attn16Ws L = attn16_ws_layout(g, mode, heads);
+  if (g->ws == 8) {
+    if (mode != MODE_OCA) return fail(SRK_ERR_ARG, "attn16_bwd: the ws-8 self-attention backward runs through srk_win_attn_bwd");
+    static bool configured = false;
+    if (!configured) {
+      SRK_CUDA_OK(cudaFuncSetAttribute(win_attn_oca8_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, O8_BWD_SMEM));
+      configured = true;
+    }
+    char* wsb = static_cast<char*>(ws);
+    a.dbias_scratch = reinterpret_cast<float*>(wsb + L.scratch_off);
+    a.dkv_win = reinterpret_cast<__nv_bfloat16*>(wsb + L.dkv_off);
+    float* dense = reinterpret_cast<float*>(wsb + L.dense_off);
+    win_attn_oca8_bwd_kernel<<<dim3(L.gx, heads), O8_THREADS, O8_BWD_SMEM, stream>>>(a);
+    SRK_LAUNCHED(1);
+    SRK_CUDA_OK(cudaGetLastError());
+    oca8_kv_gather_kernel<<<num_sms() * 8, 256, 0, stream>>>(a.dkv_win, a.dqkv, a.ld_qkv, a.B, a.H, a.W, heads);
+    SRK_LAUNCHED(1);
+    SRK_CUDA_OK(cudaGetLastError());
+    if (d_table) {
+      const int nd = heads * 64 * O8_NK;
+      oca8_dbias_dense_kernel<<<(nd + 255) / 256, 256, 0, stream>>>(a.dbias_scratch, L.gx, heads, dense);
+      SRK_LAUNCHED(1);
+      oca8_dbias_table_kernel<<<(O8_TBL * heads + 127) / 128, 128, 0, stream>>>(dense, heads, d_table);
+      SRK_LAUNCHED(1);
+      SRK_CUDA_OK(cudaGetLastError());
+    }
+    return SRK_OK;
+  }
   return mode == MODE_SELF ? launch_attn16_bwd_t<MODE_SELF>(a, ws, L, d_table, stream)
                            : launch_attn16_bwd_t<MODE_OCA>(a, ws, L, d_table, stream);
 }
@@ -262,7 +328,7 @@ extern "C" int srk_block_prep_weights(const SrkBlockDims* d, const SrkBlockParam
 static int block_fwd_impl(const SrkBlockDims* d, const SrkGeom* g, const SrkBlockWeights* w,
                           const SrkBlockParams* p, const float* next_norm_w, const float* next_norm_b,
                           const SrkBlockActs* a, const SrkHatExtra* x, void* stream) {
-  int rc = check_dims(d, g, x ? 16 : 8);
+  int rc = check_dims(d, g, x != nullptr);
   if (rc) return rc;
   const int T = g->B * g->H * g->W;
   const int QW = 3 * d->heads * d->ds, AW = d->heads * d->ds, Cp = d->Cp, Hp = d->Hp;
@@ -273,7 +339,7 @@ static int block_fwd_impl(const SrkBlockDims* d, const SrkGeom* g, const SrkBloc
   // attention core (shift / partition / reverse by address arithmetic); ao[:, dh] = 1 (proj bias column)
   if (x) {
     if ((rc = check_attn16(g, x->mode, QW, AW))) return rc;
-    if (!x->res_in || !x->lse) return fail(SRK_ERR_ARG, "srk_hat_block_fwd: res_in and lse are required");
+    if (!x->res_in || (!x->lse && g->ws == 16)) return fail(SRK_ERR_ARG, "srk_hat_block_fwd: res_in and lse are required");
     rc = attn16_fwd(g, x->mode, d->heads, a->qkv, QW, p->rpb_table, a->ao, AW, x->lse, d->dh, static_cast<cudaStream_t>(stream));
   } else {
     rc = launch_attn_fwd(g, d->heads, a->qkv, QW, p->rpb_table, a->ao, AW, d->dh, static_cast<cudaStream_t>(stream));
@@ -302,7 +368,7 @@ static int block_bwd_impl(const SrkBlockDims* d, const SrkGeom* g, const SrkBloc
                           const SrkBlockParams* p, const SrkBlockActs* a, const void* g_out,
                           const SrkBlockScratch* s, void* g_in, const SrkBlockGrads* grads, int accumulate,
                           const SrkHatExtra* x, void* stream_) {
-  int rc = check_dims(d, g, x ? 16 : 8);
+  int rc = check_dims(d, g, x != nullptr);
   if (rc) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int T = g->B * g->H * g->W;
@@ -346,9 +412,13 @@ static int block_bwd_impl(const SrkBlockDims* d, const SrkGeom* g, const SrkBloc
                            ws + L.ext_proj, stream_)))
     return rc;
   // attention backward -> d_qkv, rpb-table gradient (ws 8: per-CTA partials folded by the unpack kernel below)
-  if (x) {
+  const bool ws8_self = !x || (g->ws == 8 && x->mode == MODE_SELF);   // rpb-table gradient arrives as per-CTA partials
+  if (x && ws8_self) {
     if ((rc = check_attn16(g, x->mode, QW, AW))) return rc;
-    if (!x->lse || !x->attn_ws) return fail(SRK_ERR_ARG, "srk_hat_block_bwd: lse and attn_ws are required");
+    rc = launch_attn_bwd(g, d->heads, a->qkv, QW, p->rpb_table, s->d_ao, AW, s->d_qkv, ws + L.rpb, L.rpb_gx, stream, 1);
+  } else if (x) {
+    if ((rc = check_attn16(g, x->mode, QW, AW))) return rc;
+    if ((!x->lse && g->ws == 16) || !x->attn_ws) return fail(SRK_ERR_ARG, "srk_hat_block_bwd: lse and attn_ws are required");
     rc = attn16_bwd(g, x->mode, d->heads, a->qkv, QW, p->rpb_table, a->ao, s->d_ao, AW, x->lse, s->d_qkv, x->attn_ws,
                     grads->rpb_table, stream);
   } else {
@@ -374,7 +444,7 @@ static int block_bwd_impl(const SrkBlockDims* d, const SrkGeom* g, const SrkBloc
     return rc;
   // scatter everything into reference-shaped fp32 gradients
   UnpackSrc us{ws + L.ext_qkv, ws + L.ext_proj, ws + L.ext_fc1, ws + L.ext_fc2, defer_ln1 ? nullptr : ws + L.ln1,
-               ws + L.ln2, x ? nullptr : ws + L.rpb, L.ln_grid, L.rpb_gx, 225};
+               ws + L.ln2, ws8_self ? ws + L.rpb : nullptr, L.ln_grid, L.rpb_gx, 225};
   BlockGradPtrs gp{grads->norm1_w, grads->norm1_b, grads->rpb_table, grads->qkv_w, grads->qkv_b, grads->proj_w,
                    grads->proj_b,  grads->norm2_w, grads->norm2_b,   grads->fc1_w, grads->fc1_b, grads->fc2_w,
                    grads->fc2_b};
@@ -428,7 +498,19 @@ extern "C" int srk_win_attn16_bwd(const SrkGeom* g, int mode, int heads, const v
                                   const float* lse, void* d_qkv, void* ws, float* d_rpb_table, void* stream) {
   int rc = check_attn16(g, mode, ld_qkv, ld_out);
   if (rc) return rc;
-  if (!lse || !ws || !out) return fail(SRK_ERR_ARG, "srk_win_attn16_bwd: lse, ws and the forward output are required");
+  if ((!lse && g->ws == 16) || !ws || !out) return fail(SRK_ERR_ARG, "srk_win_attn16_bwd: lse, ws and the forward output are required");
+  if (g->ws == 8 && mode == MODE_SELF) {  // ws-8 core with HAT's shift mask; per-CTA table partials in ws
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int gx = attn_bwd_gx(g->B * (g->H / 8) * (g->W / 8), heads);
+    rc = launch_attn_bwd(g, heads, qkv, ld_qkv, rpb_table, d_out, ld_out, d_qkv, static_cast<float*>(ws), gx, st, 1);
+    if (rc) return rc;
+    if (d_rpb_table) {
+      rpb_partials_reduce_kernel<<<(225 * heads + 127) / 128, 128, 0, st>>>(static_cast<float*>(ws), gx, heads, d_rpb_table);
+      SRK_LAUNCHED(1);
+      SRK_CUDA_OK(cudaGetLastError());
+    }
+    return SRK_OK;
+  }
   return attn16_bwd(g, mode, heads, qkv, ld_qkv, rpb_table, out, d_out, ld_out, lse, d_qkv, ws, d_rpb_table,
                     static_cast<cudaStream_t>(stream));
 }

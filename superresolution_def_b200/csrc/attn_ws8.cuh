@@ -25,6 +25,7 @@ struct AttnArgs {
   int B, H, W, heads, shift;
   int ld_qkv, ld_o;
   int ones_col;               // fwd: column of `out` forced to 1.0 (bias-folding column), -1: none
+  int mask;                   // 1: add HAT's 0/-100 shifted-window mask (hat_arch.py:921-940); SwinIR never masks (:138)
 };
 
 constexpr int ATT_THREADS = 128;
@@ -79,6 +80,28 @@ __device__ __forceinline__ int rel_index(int i, int j) {
 }
 
 // S[16 x 64] (this warp's 16 query rows) = Q K^T + bias ; returns fp32 logits in s[nt][4]
+// Shift mask of HAT.calculate_mask for ws = 8, shift = 4 on fragments: in the shifted frame the last window row /
+// column is split at local token 4, so query (qy, qx) and key (ky, kx) lie in different regions iff
+// last_y && (qy>=4) != (ky>=4)  or  last_x && (qx>=4) != (kx>=4).  qy = 2*warp + rowsel, qx = g, ky = nt, kx = 2t + e.
+__device__ __forceinline__ void add_shift_mask(float (&s)[8][4], int r0, int lane, bool last_y, bool last_x) {
+  const int g = lane >> 2, t = lane & 3;
+  const bool xd = last_x && ((g >= 4) != (t >= 2));
+  const bool qlow = r0 < 32;   // query rows 0..3
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const bool yd = last_y && (qlow != (nt < 4));
+    const float m = (yd || xd) ? -100.0f : 0.0f;
+    s[nt][0] += m; s[nt][1] += m; s[nt][2] += m; s[nt][3] += m;
+  }
+}
+// (last window row, last window column) flags of window w of a shifted, masked block
+__device__ __forceinline__ void window_edge_flags(const AttnArgs& a, int w, bool& last_y, bool& last_x) {
+  const int nwx = a.W >> 3, nwy = a.H >> 3;
+  const int r = w % (nwx * nwy);
+  last_y = (r / nwx) == nwy - 1;
+  last_x = (r % nwx) == nwx - 1;
+}
+
 __device__ __forceinline__ void qk_logits(uint32_t q_tile, uint32_t k_tile, const float* s_bias, int r0, int lane,
                                           float (&s)[8][4]) {
   uint32_t aq[2][4];
@@ -223,6 +246,7 @@ __global__ void __launch_bounds__(ATT_THREADS) win_attn_ws8_fwd_kernel(const Att
   for (int i = threadIdx.x; i < 225; i += ATT_THREADS) s_bias[i] = a.bias_table[i * a.heads + h];
   const bool ones_here = a.ones_col >= h * 32 && a.ones_col < h * 32 + 32;
   const int ones_c = a.ones_col - h * 32;
+  const bool masked = a.mask != 0 && a.shift > 0;
 
   int w = blockIdx.x;
   int buf = 0;
@@ -245,6 +269,11 @@ __global__ void __launch_bounds__(ATT_THREADS) win_attn_ws8_fwd_kernel(const Att
     const int r0 = warp * 16;
     float s[8][4];
     qk_logits(qt, kt, s_bias, r0, lane, s);
+    if (masked) {
+      bool ly, lx;
+      window_edge_flags(a, w, ly, lx);
+      if (ly || lx) add_shift_mask(s, r0, lane, ly, lx);
+    }
     softmax_rows(s);
     float o[4][4];
     frag_times_tile(s, vt, lane, o);
@@ -318,6 +347,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 4) win_attn_ws8_bwd_kernel(const 
     sm.bias[i] = a.bias_table[i * a.heads + h];
     sm.dbias[i] = 0.f;
   }
+  const bool masked = a.mask != 0 && a.shift > 0;
   float dbacc[8][4];
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) dbacc[nt][0] = dbacc[nt][1] = dbacc[nt][2] = dbacc[nt][3] = 0.f;
@@ -345,6 +375,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 4) win_attn_ws8_bwd_kernel(const 
     // ---- phase A: this warp's 16 query rows
     float s[8][4];
     qk_logits(qt, kt, sm.bias, r0, lane, s);
+    if (masked) {
+      bool ly, lx;
+      window_edge_flags(a, w, ly, lx);
+      if (ly || lx) add_shift_mask(s, r0, lane, ly, lx);
+    }
     softmax_rows(s);  // s = P (fp32)
     // dP = dO V^T  (A = dO rows, B = V as [key][d], same access pattern as K in QK^T)
     float dp[8][4];

@@ -186,8 +186,8 @@ class OCAB(nn.Module):
         self.proj = nn.Linear(dim, dim)
         self.norm2 = norm_layer(dim)
         self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=nn.GELU)
-        if self.overlap_win_size != 24 or not qkv_bias or qk_scale is not None:
-            raise capi.SrkError("libsrk OCAB: window 16 with overlap_ratio 0.5 (24x24 key window), qkv_bias=True")
+        if (window_size, self.overlap_win_size) not in ((16, 24), (8, 12)) or not qkv_bias or qk_scale is not None:
+            raise capi.SrkError("libsrk OCAB: window 16 or 8 with overlap_ratio 0.5 (24x24 / 12x12 key window), qkv_bias=True")
 
     def block_cfg(self) -> eng.BlockCfg:
         return heng.hat_block_cfg(self.dim, self.num_heads, self.mlp.fc1.out_features, self.window_size)
@@ -419,8 +419,8 @@ class HAT(nn.Module):
         for layer in self.layers:
             t = layer.run(t, geom)
         body = heng.LayerNormTokensFunction.apply(t, self.norm.weight, self.norm.bias, C, C)
-        if self.upscale != 4:
-            raise capi.SrkError("libsrk HAT tail implements upscale=4 (two fused conv+PixelShuffle stages)")
+        if self.upscale not in (2, 4):
+            raise capi.SrkError("libsrk HAT tail implements upscale 2 / 4 (one / two fused conv+PixelShuffle stages)")
         out = cv.swinir_tail(body, first, geom, C, self.conv_after_body, self.conv_before_upsample[0], self.upsample,
                              self.conv_last)
         if self.img_range != 1.:

@@ -30,8 +30,8 @@ OCAB_KEYS = ("norm1.weight", "norm1.bias", "relative_position_bias_table", "qkv.
 
 
 def hat_block_cfg(C: int, heads: int, hidden: int, ws: int) -> eng.BlockCfg:
-    if not (C < 192 and heads * 32 == 192 and C % heads == 0 and C // heads < 32 and ws == 16):
-        raise capi.SrkError(f"libsrk HAT kernels are specialised for heads=6, head_dim<32, embed_dim<192, window 16; "
+    if not (C < 192 and heads * 32 == 192 and C % heads == 0 and C // heads < 32 and ws in (8, 16)):
+        raise capi.SrkError(f"libsrk HAT kernels are specialised for heads=6, head_dim<32, embed_dim<192, window 8 or 16; "
                             f"got C={C} heads={heads} ws={ws}")
     return eng.BlockCfg(C=C, heads=heads, hidden=hidden, ws=ws, Cp=192, ds=32, Hp=((hidden + 1 + 255) // 256) * 256)
 

@@ -201,6 +201,37 @@ int srk_conv_out1_bwd(const float* dy, const void* x, const float* w, void* dx, 
                       int H, int W, int C, void* stream);
 
 
+/* ------------------------------------------------------------------------------------------------------
+ * Channel-slice ("view") variants for the dense blocks and tail of the hybrid generator
+ * (models/hybridmodels_hat.py:21-131: ResidualDenseBlock / RRDBBlock / HybridHATRealESRGAN).
+ * A view = (pointer to the slice's first channel, visible channels C, pixel pitch in elements) of an NHWC bf16
+ * tensor; C % 8 == 0, pitch % 8 == 0, 16-byte aligned.  The implicit-GEMM kernels clip their 64-channel TMA boxes
+ * to the view, so torch.cat((x, x1, ...), 1) (:40-43) is a slice of one [pixels, nf + 4*gc] buffer and never copied.
+ * ------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* ptr;
+  int C;
+  int pitch;
+} SrkView;
+/* y = epilogue(conv3x3(x, wk)); BIAS_RES: y = alpha * (conv + bias) + r (r may alias y); OUT1: y32 fp32 [B,H,W]. */
+int srk_conv3x3_igemm_v(int epi, int B, int H, int W, int Cin_p, int Cout_p, int n_real, const SrkView* x,
+                        const void* wk, const float* bias, float slope, float alpha, const SrkView* y, const SrkView* r,
+                        float* y32, void* stream);
+int srk_conv3x3_wgrad_v(int B, int H, int W, int Cin, int Cout, int Cin_p, int Cout_p, const SrkView* dy,
+                        const SrkView* x, float* ws, float* dw, void* stream);
+int srk_bias_grad_v(const SrkView* dy, long long npix, float* ws, float* db, int n_out, void* stream);
+/* g *= (f > 0 ? 1 : slope): backward through nn.LeakyReLU (hybridmodels_hat.py:29), f = forward output */
+int srk_view_lrelu_mask(const SrkView* g, const SrkView* f, long long npix, float slope, void* stream);
+/* y = alpha * a + x (x may be NULL; y may alias a or x): the 0.2-scaled residuals (:44,:58) and their gradients */
+int srk_view_axpy(const SrkView* y, const SrkView* a, const SrkView* x, long long npix, float alpha, void* stream);
+/* F.interpolate(scale_factor=2, mode='nearest') (:127) on NHWC views, x [B,H,W,C] -> y [B,2H,2W,C], and its adjoint */
+int srk_nearest2_fwd(const SrkView* x, const SrkView* y, int B, int H, int W, void* stream);
+int srk_nearest2_bwd(const SrkView* dy, const SrkView* dx, int B, int H, int W, void* stream);
+/* fp32 single-channel image [npix] <-> bf16 rows of 8 channels (channel 0 = image): operand form of the 1 -> nf and
+ * nf -> 1 convolutions (conv_adapt :94, conv_last :105) for the implicit-GEMM kernel */
+int srk_img1_pack(const float* x, void* y8, long long npix, void* stream);
+int srk_img1_unpack(const void* x8, float* y, long long npix, void* stream);
+
 /* ======================================================================================================
  * HAT (models/hat_arch/hat_arch.py): 16x16-window attention cores, block orchestration, channel attention.
  * ====================================================================================================== */

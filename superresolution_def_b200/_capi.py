@@ -437,3 +437,80 @@ def cab_se_bwd(g, y, B, HW, C, S, w1, w2, alpha, pool, hidden, scale, dy, dw1, d
     rc = _cab_se_bwd(_ptr(g), _ptr(y), B, HW, C, y.shape[1], S, _ptr(w1), _ptr(w2), alpha, _ptr(pool), _ptr(hidden),
                      _ptr(scale), _ptr(ws), _ptr(dy), _ptr(dw1), _ptr(db1), _ptr(dw2), _ptr(db2), _stream())
     _check(rc, "srk_cab_se_bwd")
+
+
+# ---------------------------------------------------------------------------------------------------
+# Channel-slice ("view") API (include/srk.h): dense blocks / tail of the hybrid generator
+# ---------------------------------------------------------------------------------------------------
+class SrkView(Structure):
+    _fields_ = [("ptr", c_void_p), ("C", c_int), ("pitch", c_int)]
+
+
+def view(t: torch.Tensor, c0: int = 0, C: int | None = None) -> SrkView:
+    """Channel slice [c0, c0 + C) of a token-major bf16 tensor [pixels, pitch]."""
+    if t.dtype != torch.bfloat16 or t.dim() != 2 or not t.is_contiguous() or not t.is_cuda:
+        raise SrkError("view: contiguous CUDA bf16 [pixels, channels] tensor expected")
+    C = t.shape[1] - c0 if C is None else C
+    if c0 % 8 or C % 8 or C <= 0 or c0 + C > t.shape[1]:
+        raise SrkError(f"view: channel slice [{c0}, {c0 + C}) of {t.shape[1]} must be 16-byte aligned")
+    return SrkView(t.data_ptr() + 2 * c0, C, t.shape[1])
+
+
+_conv_igemm_v = _sig("srk_conv3x3_igemm_v", [c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(SrkView), c_void_p,
+                                             c_void_p, c_float, c_float, POINTER(SrkView), POINTER(SrkView), c_void_p,
+                                             c_void_p])
+_conv_wgrad_v = _sig("srk_conv3x3_wgrad_v", [c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(SrkView),
+                                             POINTER(SrkView), c_void_p, c_void_p, c_void_p])
+_bias_grad_v = _sig("srk_bias_grad_v", [POINTER(SrkView), c_longlong, c_void_p, c_void_p, c_int, c_void_p])
+_view_lrelu_mask = _sig("srk_view_lrelu_mask", [POINTER(SrkView), POINTER(SrkView), c_longlong, c_float, c_void_p])
+_view_axpy = _sig("srk_view_axpy", [POINTER(SrkView), POINTER(SrkView), POINTER(SrkView), c_longlong, c_float, c_void_p])
+_nearest2_fwd = _sig("srk_nearest2_fwd", [POINTER(SrkView), POINTER(SrkView), c_int, c_int, c_int, c_void_p])
+_nearest2_bwd = _sig("srk_nearest2_bwd", [POINTER(SrkView), POINTER(SrkView), c_int, c_int, c_int, c_void_p])
+_img1_pack = _sig("srk_img1_pack", [c_void_p, c_void_p, c_longlong, c_void_p])
+_img1_unpack = _sig("srk_img1_unpack", [c_void_p, c_void_p, c_longlong, c_void_p])
+
+
+def _vref(v):
+    return ctypes.byref(v) if v is not None else None
+
+
+def conv3x3_igemm_v(epi, B, H, W, Cin_p, Cout_p, n_real, x: SrkView, wk, bias, y: SrkView | None, r: SrkView | None = None,
+                    slope=0.01, alpha=1.0, y32=None):
+    rc = _conv_igemm_v(epi, B, H, W, Cin_p, Cout_p, n_real, _vref(x), _ptr(wk), _ptr(bias), slope, alpha, _vref(y),
+                       _vref(r), _ptr(y32), _stream())
+    _check(rc, "srk_conv3x3_igemm_v")
+
+
+def conv3x3_wgrad_v(B, H, W, Cin, Cout, Cin_p, Cout_p, dy: SrkView, x: SrkView, dw):
+    ws = _ws(int(lib.srk_conv3x3_wgrad_ws_floats(Cin_p, Cout_p)), dw.device)
+    rc = _conv_wgrad_v(B, H, W, Cin, Cout, Cin_p, Cout_p, _vref(dy), _vref(x), _ptr(ws), _ptr(dw), _stream())
+    _check(rc, "srk_conv3x3_wgrad_v")
+
+
+def bias_grad_v(dy: SrkView, npix, db):
+    ws = _ws(int(lib.srk_small_ws_floats()), db.device)
+    _check(_bias_grad_v(_vref(dy), npix, _ptr(ws), _ptr(db), db.numel(), _stream()), "srk_bias_grad_v")
+
+
+def view_lrelu_mask(g: SrkView, f: SrkView, npix, slope):
+    _check(_view_lrelu_mask(_vref(g), _vref(f), npix, slope, _stream()), "srk_view_lrelu_mask")
+
+
+def view_axpy(y: SrkView, a: SrkView, x: SrkView | None, npix, alpha):
+    _check(_view_axpy(_vref(y), _vref(a), _vref(x), npix, alpha, _stream()), "srk_view_axpy")
+
+
+def nearest2_fwd(x: SrkView, y: SrkView, B, H, W):
+    _check(_nearest2_fwd(_vref(x), _vref(y), B, H, W, _stream()), "srk_nearest2_fwd")
+
+
+def nearest2_bwd(dy: SrkView, dx: SrkView, B, H, W):
+    _check(_nearest2_bwd(_vref(dy), _vref(dx), B, H, W, _stream()), "srk_nearest2_bwd")
+
+
+def img1_pack(x, y8):
+    _check(_img1_pack(_ptr(x), _ptr(y8), x.numel(), _stream()), "srk_img1_pack")
+
+
+def img1_unpack(x8, y):
+    _check(_img1_unpack(_ptr(x8), _ptr(y), y.numel(), _stream()), "srk_img1_unpack")

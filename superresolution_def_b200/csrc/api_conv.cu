@@ -107,7 +107,7 @@ extern "C" int srk_conv3x3_igemm(int epi, int B, int H, int W, int Cin_p, int Co
   if ((rc = make_tmap_2d(&maps.w, wk, Cout_p, 9 * (uint64_t)Cin_p, 9 * (uint64_t)Cin_p, bn))) return rc;
   ConvArgs a{};
   a.B = B; a.H = H; a.W = W; a.Cin_p = Cin_p; a.Cout_p = Cout_p; a.n_real = n_real; a.bias = bias; a.slope = slope;
-  a.a_split = x_ps; a.c_split = y_ps;
+  a.a_split = x_ps; a.c_split = y_ps; a.alpha = 1.0f;
   a.y32 = out1 ? static_cast<float*>(y) : nullptr;
   const bool need_r = (epi == CEPI_BIAS_RES || epi == CEPI_MASK_LRELU || epi == CEPI_MUL);
   if (need_r && (!r || y_ps)) return fail(SRK_ERR_ARG, "conv3x3: epilogue needs an aux tensor (and a plain output)");
@@ -232,6 +232,171 @@ extern "C" int srk_conv_out1_bwd(const float* dy, const void* x, const float* w,
   SRK_LAUNCHED(1);
   SRK_CUDA_OK(cudaMemcpyAsync(dw, ws + (size_t)grid * (64 * 9 + 1), 64 * 9 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
   SRK_CUDA_OK(cudaMemcpyAsync(db, ws + (size_t)grid * (64 * 9 + 1) + 64 * 9, sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Channel-slice ("view") variants: every activation operand is (pointer to first channel, visible channels, pixel
+// pitch).  TMA clips the 64-channel boxes to the visible channels (zero-fill on load, no write on store), so a
+// convolution can read the first Cin channels of a wider buffer and write its Cout channels at an offset of the same
+// or another buffer: torch.cat of the dense blocks (hybridmodels_hat.py:38-43) costs no copy.
+namespace {
+int view_map(CUtensorMap* m, const SrkView* v, int B, int H, int W, int bw, int bh) {
+  if (!v || !v->ptr || v->C <= 0 || v->C % 8 || v->pitch % 8 || v->C > v->pitch)
+    return fail(SRK_ERR_ARG, "view: channels / pitch must be positive multiples of 8 (16-byte slices)");
+  return make_tmap_nhwc(m, v->ptr, (uint64_t)v->C, W, H, B, (uint64_t)v->pitch, (uint64_t)W * v->pitch,
+                        (uint64_t)H * W * v->pitch, bw, bh);
+}
+int ew_grid(long long items) {
+  long long g = (items + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  return int(g < 1 ? 1 : (g > cap ? cap : g));
+}
+}  // namespace
+
+extern "C" int srk_conv3x3_igemm_v(int epi, int B, int H, int W, int Cin_p, int Cout_p, int n_real, const SrkView* x,
+                                   const void* wk, const float* bias, float slope, float alpha, const SrkView* y,
+                                   const SrkView* r, float* y32, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (H % CONV_TH || W % CONV_TW) return fail(SRK_ERR_UNSUPPORTED, "conv3x3: H % 8 == 0 and W % 16 == 0 required");
+  const bool out1 = (epi == CEPI_OUT1);
+  if (Cin_p % 64 || (Cout_p % 64 && !(out1 && Cout_p == 16)) || Cout_p > 256 || Cin_p > 256)
+    return fail(SRK_ERR_UNSUPPORTED, "conv3x3: channels must be multiples of 64, <= 256");
+  if (!x || !wk || (!out1 && !y) || (out1 && (!y32 || !bias))) return fail(SRK_ERR_ARG, "conv3x3_v: null pointer");
+  if (x->C > Cin_p || (!out1 && y->C > Cout_p)) return fail(SRK_ERR_ARG, "conv3x3_v: view wider than the padded channel count");
+  ConvMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  int rc;
+  if ((rc = view_map(&maps.a[0], x, B, H, W, CONV_TW, CONV_TH))) return rc;
+  if (out1) maps.c[0] = maps.a[0];
+  else if ((rc = view_map(&maps.c[0], y, B, H, W, CONV_TW, CONV_TH))) return rc;
+  for (int i = 1; i < 4; ++i) { maps.a[i] = maps.a[0]; maps.c[i] = maps.c[0]; }
+  maps.c2 = maps.c[0];
+  maps.r = maps.c[0];
+  const bool need_r = (epi == CEPI_BIAS_RES || epi == CEPI_MASK_LRELU || epi == CEPI_MUL);
+  if (need_r) {
+    if (!r) return fail(SRK_ERR_ARG, "conv3x3_v: epilogue needs an aux view");
+    if ((rc = view_map(&maps.r, r, B, H, W, CONV_TW, CONV_TH))) return rc;
+  }
+  if (epi == CEPI_BIAS_GELU) return fail(SRK_ERR_UNSUPPORTED, "conv3x3_v: GELU epilogue is served by srk_conv3x3_igemm");
+  const int bn = Cout_p;
+  if ((rc = make_tmap_2d(&maps.w, wk, Cout_p, 9 * (uint64_t)Cin_p, 9 * (uint64_t)Cin_p, bn))) return rc;
+  ConvArgs a{};
+  a.B = B; a.H = H; a.W = W; a.Cin_p = Cin_p; a.Cout_p = Cout_p; a.n_real = n_real; a.bias = bias; a.slope = slope;
+  a.a_split = 0; a.c_split = 0; a.alpha = alpha;
+  a.y32 = out1 ? y32 : nullptr;
+#define SRK_CCASE(BN_, EPI_) if (bn == BN_ && epi == EPI_) return launch_conv<BN_, EPI_>(maps, a, stream);
+  SRK_CCASE(64, CEPI_BIAS) SRK_CCASE(128, CEPI_BIAS) SRK_CCASE(192, CEPI_BIAS) SRK_CCASE(256, CEPI_BIAS)
+  SRK_CCASE(64, CEPI_BIAS_LRELU) SRK_CCASE(192, CEPI_BIAS_LRELU)
+  SRK_CCASE(64, CEPI_BIAS_RES) SRK_CCASE(128, CEPI_BIAS_RES) SRK_CCASE(192, CEPI_BIAS_RES) SRK_CCASE(256, CEPI_BIAS_RES)
+  SRK_CCASE(64, CEPI_MASK_LRELU) SRK_CCASE(192, CEPI_MASK_LRELU)
+  SRK_CCASE(16, CEPI_OUT1)
+#undef SRK_CCASE
+  return fail(SRK_ERR_UNSUPPORTED, "conv3x3_v: no kernel instance for (Cout_p, epilogue)");
+}
+
+extern "C" int srk_conv3x3_wgrad_v(int B, int H, int W, int Cin, int Cout, int Cin_p, int Cout_p, const SrkView* dy,
+                                   const SrkView* x, float* ws, float* dw, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (H % 4 || W % 16 || Cin_p % 64 || Cout_p % 64 || Cin_p > 256) return fail(SRK_ERR_UNSUPPORTED, "conv wgrad: shape");
+  if (!dy || !x || dy->C > Cout_p || x->C > Cin_p || Cout > Cout_p || Cin > Cin_p) return fail(SRK_ERR_ARG, "conv wgrad_v: views");
+  ConvWgradMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  int rc;
+  if ((rc = view_map(&maps.a[0], dy, B, H, W, 16, 4))) return rc;
+  for (int i = 1; i < 4; ++i) maps.a[i] = maps.a[0];
+  if ((rc = view_map(&maps.b, x, B, H, W, 16, 4))) return rc;
+  ConvWgradArgs a{};
+  a.B = B; a.H = H; a.W = W; a.Cin_p = Cin_p; a.Cout_p = Cout_p; a.co_tiles = (Cout_p + 127) / 128;
+  a.splits = conv_wgrad_splits(B, H, W, a.co_tiles); a.partials = ws; a.a_split = 0;
+  switch (Cin_p) {
+    case 64: rc = launch_conv_wgrad<64>(maps, a, stream); break;
+    case 128: rc = launch_conv_wgrad<128>(maps, a, stream); break;
+    case 192: rc = launch_conv_wgrad<192>(maps, a, stream); break;
+    case 256: rc = launch_conv_wgrad<256>(maps, a, stream); break;
+    default: return fail(SRK_ERR_UNSUPPORTED, "conv wgrad: Cin_p");
+  }
+  if (rc) return rc;
+  const int total = Cout * Cin * 9;
+  conv_unpack_wgrad_kernel<<<(total + 255) / 256, 256, 0, stream>>>(ws, a.splits, a.co_tiles * 128, Cin_p, dw, Cout, Cin,
+                                                                    Cout_p, 0);
+  SRK_LAUNCHED(1);
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+extern "C" int srk_bias_grad_v(const SrkView* dy, long long npix, float* ws, float* db, int n_out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!dy || !dy->ptr || dy->C % 2 || dy->C > 256 || n_out > dy->C) return fail(SRK_ERR_ARG, "bias_grad_v: view");
+  const int grid = num_sms() * 2, C = dy->C;
+  const int threads = (C / 2) * (C >= 128 ? 4 : 8);
+  colsum_nhwc_kernel<<<grid, threads, C * sizeof(float), stream>>>(static_cast<const __nv_bfloat16*>(dy->ptr), npix, C,
+                                                                     dy->pitch, ws);
+  SRK_LAUNCHED(1);
+  colsum_finish_kernel<<<(n_out + 127) / 128, 128, 0, stream>>>(ws, grid, C, db, n_out);
+  SRK_LAUNCHED(1);
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+extern "C" int srk_view_lrelu_mask(const SrkView* g, const SrkView* f, long long npix, float slope, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!g || !f || g->C != f->C || g->C % 8 || g->pitch % 8 || f->pitch % 8) return fail(SRK_ERR_ARG, "view_lrelu_mask: views");
+  view_lrelu_mask_kernel<<<ew_grid(npix * (g->C / 8)), 256, 0, stream>>>(
+      static_cast<__nv_bfloat16*>(const_cast<void*>(g->ptr)), g->pitch, static_cast<const __nv_bfloat16*>(f->ptr), f->pitch,
+      g->C, npix, slope);
+  SRK_LAUNCHED(1);
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+extern "C" int srk_view_axpy(const SrkView* y, const SrkView* a, const SrkView* x, long long npix, float alpha, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!y || !a || y->C != a->C || (x && x->C != y->C) || y->C % 8 || y->pitch % 8 || a->pitch % 8 || (x && x->pitch % 8))
+    return fail(SRK_ERR_ARG, "view_axpy: views");
+  view_axpy_kernel<<<ew_grid(npix * (y->C / 8)), 256, 0, stream>>>(
+      static_cast<__nv_bfloat16*>(const_cast<void*>(y->ptr)), y->pitch, static_cast<const __nv_bfloat16*>(a->ptr), a->pitch,
+      x ? static_cast<const __nv_bfloat16*>(x->ptr) : nullptr, x ? x->pitch : 0, y->C, npix, alpha);
+  SRK_LAUNCHED(1);
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+extern "C" int srk_nearest2_fwd(const SrkView* x, const SrkView* y, int B, int H, int W, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !y || x->C != y->C || x->C % 8 || x->pitch % 8 || y->pitch % 8) return fail(SRK_ERR_ARG, "nearest2_fwd: views");
+  nearest2_fwd_kernel<<<ew_grid((long long)B * H * W * (x->C / 8)), 256, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(x->ptr), x->pitch, static_cast<__nv_bfloat16*>(const_cast<void*>(y->ptr)), y->pitch,
+      x->C, B, H, W);
+  SRK_LAUNCHED(1);
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+extern "C" int srk_nearest2_bwd(const SrkView* dy, const SrkView* dx, int B, int H, int W, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!dx || !dy || dx->C != dy->C || dx->C % 8 || dx->pitch % 8 || dy->pitch % 8) return fail(SRK_ERR_ARG, "nearest2_bwd: views");
+  nearest2_bwd_kernel<<<ew_grid((long long)B * H * W * (dx->C / 8)), 256, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(dy->ptr), dy->pitch, static_cast<__nv_bfloat16*>(const_cast<void*>(dx->ptr)),
+      dx->pitch, dx->C, B, H, W);
+  SRK_LAUNCHED(1);
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+extern "C" int srk_img1_pack(const float* x, void* y8, long long npix, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  img1_pack_kernel<<<ew_grid(npix), 256, 0, stream>>>(x, static_cast<__nv_bfloat16*>(y8), npix);
+  SRK_LAUNCHED(1);
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+extern "C" int srk_img1_unpack(const void* x8, float* y, long long npix, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  img1_unpack_kernel<<<ew_grid(npix), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x8), y, npix);
+  SRK_LAUNCHED(1);
   SRK_CUDA_OK(cudaGetLastError());
   return SRK_OK;
 }

@@ -23,7 +23,7 @@ constexpr int CONV_TW = 16, CONV_TH = 8;  // 128-pixel spatial tile
 enum ConvEpilogue : int {
   CEPI_BIAS = 0,       // y = acc + bias
   CEPI_BIAS_LRELU = 1, // y = leaky_relu(acc + bias, slope)
-  CEPI_BIAS_RES = 2,   // y = acc + bias + R            (R: same layout as Y)
+  CEPI_BIAS_RES = 2,   // y = alpha * (acc + bias) + R  (R: same layout as Y; alpha = 1 except the RDB's 0.2 residual scale)
   CEPI_MASK_LRELU = 3, // y = acc * (R > 0 ? 1 : slope)  (backward through LeakyReLU; R = forward output)
   CEPI_BIAS_GELU = 4,  // y = gelu(acc + bias), y2 = gelu'(acc + bias)   (HAT CAB, hat_arch.py:69)
   CEPI_MUL = 5,        // y = acc * R                    (backward through GELU; R = gelu')
@@ -39,6 +39,7 @@ struct ConvArgs {
   int a_split;        // 1: A k-chunk kc is loaded through tmA[kc] at channel 0 (pixel-shuffled input gradient)
   int c_split;        // 1: output box j is stored through tmC[j] at channel 0 (pixel-shuffled output)
   float* y32;         // CEPI_OUT1: fp32 output [B,H,W]
+  float alpha;        // CEPI_BIAS_RES: scale of the convolution branch
 };
 
 struct ConvMaps {
@@ -260,7 +261,7 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               const float a = (e & 1) ? bf16_hi(gw[e >> 1]) : bf16_lo(gw[e >> 1]);
-              if constexpr (EPI == CEPI_BIAS_RES) v[e] = round_bf16(v[e]) + a;
+              if constexpr (EPI == CEPI_BIAS_RES) v[e] = round_bf16(v[e] * args.alpha) + a;
               else if constexpr (EPI == CEPI_MASK_LRELU) v[e] = (a > 0.f) ? v[e] : v[e] * args.slope;
               else v[e] = round_bf16(v[e]) * a;
             }

@@ -336,3 +336,107 @@ static __global__ void conv_out1_wgrad_kernel(const float* __restrict__ dy, cons
 }
 
 }  // namespace srk
+
+namespace srk {
+// ------------------------------------------------------------------ channel-slice ("view") elementwise helpers
+// A view is (pointer to the first channel, channel count C, pixel pitch in elements): a channel slice of an NHWC
+// tensor.  They serve the dense blocks of the hybrid generator (ResidualDenseBlock, models/hybridmodels_hat.py:21-44),
+// whose torch.cat inputs are slices of ONE [pixels, nf + 4*gc] buffer here (virtual concat).  C % 8 == 0, 16-byte
+// aligned slices: every thread moves 16 bytes.
+
+// g[:, :C] *= (f[:, :C] > 0 ? 1 : slope)     (backward through LeakyReLU; f = forward output)
+static __global__ void view_lrelu_mask_kernel(__nv_bfloat16* __restrict__ g, int ldg, const __nv_bfloat16* __restrict__ f,
+                                              int ldf, int C, long long npix, float slope) {
+  const int groups = C >> 3;
+  const long long total = npix * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / groups;
+    const int c = int(i - p * groups) * 8;
+    uint4* gp = reinterpret_cast<uint4*>(g + p * ldg + c);
+    const uint4 fv = *reinterpret_cast<const uint4*>(f + p * ldf + c);
+    uint4 gv = *gp;
+    uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+    const uint32_t fw[4] = {fv.x, fv.y, fv.z, fv.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float lo = bf16_lo(fw[e]) > 0.f ? bf16_lo(gw[e]) : bf16_lo(gw[e]) * slope;
+      const float hi = bf16_hi(fw[e]) > 0.f ? bf16_hi(gw[e]) : bf16_hi(gw[e]) * slope;
+      gw[e] = pack_bf16(lo, hi);
+    }
+    *gp = make_uint4(gw[0], gw[1], gw[2], gw[3]);
+  }
+}
+// y[:, :C] = alpha * a[:, :C] + (x ? x[:, :C] : 0)      (y may alias a or x)
+static __global__ void view_axpy_kernel(__nv_bfloat16* y, int ldy, const __nv_bfloat16* a, int lda, const __nv_bfloat16* x,
+                                        int ldx, int C, long long npix, float alpha) {
+  const int groups = C >> 3;
+  const long long total = npix * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / groups;
+    const int c = int(i - p * groups) * 8;
+    const uint4 av = *reinterpret_cast<const uint4*>(a + p * lda + c);
+    uint4 xv = make_uint4(0u, 0u, 0u, 0u);
+    if (x != nullptr) xv = *reinterpret_cast<const uint4*>(x + p * ldx + c);
+    const uint32_t aw[4] = {av.x, av.y, av.z, av.w}, xw[4] = {xv.x, xv.y, xv.z, xv.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      o[e] = pack_bf16(round_bf16(bf16_lo(aw[e]) * alpha) + bf16_lo(xw[e]), round_bf16(bf16_hi(aw[e]) * alpha) + bf16_hi(xw[e]));
+    *reinterpret_cast<uint4*>(y + p * ldy + c) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+// nearest-neighbour x2 (F.interpolate(scale_factor=2, mode='nearest'), hybridmodels_hat.py:127):
+// y[b, 2h+i, 2w+j, :] = x[b, h, w, :]
+static __global__ void nearest2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ y,
+                                           int ldy, int C, int B, int H, int W) {
+  const int groups = C >> 3;
+  const long long total = (long long)B * H * W * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / groups;
+    const int c = int(i - p * groups) * 8;
+    const int w = int(p % W), h = int((p / W) % H);
+    const long long b = p / ((long long)W * H);
+    const uint4 v = *reinterpret_cast<const uint4*>(x + p * ldx + c);
+    const long long q = (b * 2 * H + 2 * h) * (2LL * W) + 2 * w;
+    *reinterpret_cast<uint4*>(y + q * ldy + c) = v;
+    *reinterpret_cast<uint4*>(y + (q + 1) * ldy + c) = v;
+    *reinterpret_cast<uint4*>(y + (q + 2 * W) * ldy + c) = v;
+    *reinterpret_cast<uint4*>(y + (q + 2 * W + 1) * ldy + c) = v;
+  }
+}
+// dx[b, h, w, :] = sum of the four dy pixels it was copied to
+static __global__ void nearest2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, __nv_bfloat16* __restrict__ dx,
+                                           int lddx, int C, int B, int H, int W) {
+  const int groups = C >> 3;
+  const long long total = (long long)B * H * W * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / groups;
+    const int c = int(i - p * groups) * 8;
+    const int w = int(p % W), h = int((p / W) % H);
+    const long long b = p / ((long long)W * H);
+    const long long q = (b * 2 * H + 2 * h) * (2LL * W) + 2 * w;
+    const long long qs[4] = {q, q + 1, q + 2 * W, q + 2 * W + 1};
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint4 v = *reinterpret_cast<const uint4*>(dy + qs[k] * lddy + c);
+      const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { acc[2 * e] += bf16_lo(wv[e]); acc[2 * e + 1] += bf16_hi(wv[e]); }
+    }
+    *reinterpret_cast<uint4*>(dx + p * lddx + c) =
+        make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]), pack_bf16(acc[6], acc[7]));
+  }
+}
+// single-channel image <-> 8-channel bf16 NHWC rows (channel 0 = the image, channels 1..7 zero): lets the 1 -> nf and
+// nf -> 1 convolutions of the hybrid generator (conv_adapt / conv_last, hybridmodels_hat.py:94,105) and their
+// gradients run through the tcgen05 implicit-GEMM kernel (TMA zero-fills the other 56 K columns).
+static __global__ void img1_pack_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long npix) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x)
+    *reinterpret_cast<uint4*>(y + i * 8) = make_uint4(pack_bf16(x[i], 0.f), 0u, 0u, 0u);
+}
+static __global__ void img1_unpack_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, long long npix) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x)
+    y[i] = __bfloat162float(x[i * 8]);
+}
+}  // namespace srk

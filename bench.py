@@ -33,6 +33,10 @@ GFLOP_PER_PATCH_TRAIN = 1569.826  # SURVEY.md §8d (FlopCounterMode on the refer
 HAT_KW = dict(img_size=128, in_chans=1, embed_dim=180, depths=(6,) * 6, num_heads=(6,) * 6, window_size=16, upscale=4,
               upsampler="pixelshuffle")   # drop_path_rate default 0.1: stochastic depth active, as train_hat.py would
 HAT_GFLOP_PER_PATCH_TRAIN = 3026.031
+# --workload hybrid: the generator train_hat.py actually trains (train_hat.py:132-136; SURVEY.md section 8a row a17, cfgH)
+HYBRID_KW = dict(img_size=128, in_chans=1, embed_dim=90, depths=(6, 6, 6, 6), num_heads=(6, 6, 6, 6), window_size=8,
+                 upscale=4, num_rrdb=12, num_feat=48, num_grow_ch=24)
+HYBRID_GFLOP_PER_PATCH_TRAIN = 3 * 819.171
 
 
 def load_peaks():
@@ -235,19 +239,28 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     _dbg("process group ready")
-    hat = args.workload == "hat"
+    hybrid = args.workload == "hybrid"
+    hat = args.workload in ("hat", "hybrid")   # not the default bench line: no CPU leg, HAT metric name
     B = args.batch or (8 if hat else 16)
     torch.manual_seed(0)
-    if hat:
+    if hybrid:
+        from superresolution_def_b200.hybridmodels_hat import HybridHATRealESRGAN
+        net = HybridHATRealESRGAN(**HYBRID_KW).to(dev)
+    elif hat:
         from superresolution_def_b200.hat_arch import HAT
         net = HAT(**HAT_KW).to(dev)
     else:
         net = SwinIR(**MODEL_KW).to(dev)
     net.train()
-    gflop = HAT_GFLOP_PER_PATCH_TRAIN if hat else GFLOP_PER_PATCH_TRAIN
-    wl_name = ("HAT x4 (window 16, OCAB, CAB, stochastic depth 0.1) training step (fwd + L1 + bwd + AdamW), bf16, "
-               f"batch {B}/GPU, 128^2->512^2 (BASELINE configs[2])") if hat else \
-              (f"SwinIR x4 training step (fwd + L1 + bwd + AdamW), bf16, batch {B}/GPU, 128^2->512^2 (BASELINE configs[1])")
+    gflop = HYBRID_GFLOP_PER_PATCH_TRAIN if hybrid else HAT_GFLOP_PER_PATCH_TRAIN if hat else GFLOP_PER_PATCH_TRAIN
+    if hybrid:
+        wl_name = ("HybridHATRealESRGAN x4 (HAT C=90 window 8 x2 + 12 RRDB nf 48 + nearest x2; train_hat.py:132-136) training "
+                   f"step (fwd + L1 + bwd + AdamW), bf16, batch {B}/GPU, 128^2->512^2")
+    elif hat:
+        wl_name = ("HAT x4 (window 16, OCAB, CAB, stochastic depth 0.1) training step (fwd + L1 + bwd + AdamW), bf16, "
+                   f"batch {B}/GPU, 128^2->512^2 (BASELINE configs[2])")
+    else:
+        wl_name = f"SwinIR x4 training step (fwd + L1 + bwd + AdamW), bf16, batch {B}/GPU, 128^2->512^2 (BASELINE configs[1])"
     if world > 1:
         for p in net.parameters():
             dist.broadcast(p.data, 0)
@@ -353,7 +366,7 @@ def run_ours(args):
     value = world * B * args.steps / (ms * 1e-3)
     e2e_v = world * B * args.steps / (ms_e2e * 1e-3)
     peaks = load_peaks()
-    line = {"metric": METRIC.replace("SwinIR", "HAT") if hat else METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+    line = {"metric": METRIC.replace("SwinIR", "HybridHAT" if hybrid else "HAT") if hat else METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": wl_name, "global_batch": world * B, "parallelism": f"dp{world}",
@@ -382,7 +395,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=0, help="patches per GPU per step (default: 16 SwinIR = BASELINE configs[1], 8 HAT)")
-    ap.add_argument("--workload", default="swinir", choices=["swinir", "hat"], help="swinir = the bench line (configs[1]); hat = configs[2]")
+    ap.add_argument("--workload", default="swinir", choices=["swinir", "hat", "hybrid"],
+                    help="swinir = the bench line (configs[1]); hat = configs[2]; hybrid = train_hat.py's generator")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="issue the step eagerly instead of replaying a CUDA graph")

@@ -72,6 +72,12 @@ class BucketedGradReducer:
 def swinir_grad_groups(net) -> list[list[torch.nn.Parameter]]:
     """Reverse-execution-order parameter groups of a SwinIR- or HAT-shaped generator: tail convs + final norm, then
     the residual groups last to first, then the head."""
+    if hasattr(net, "rrdb_trunk") and hasattr(net, "hat"):
+        # HybridHATRealESRGAN: tail convs, the RRDB trunk last to first (+ conv_adapt), then the HAT stage
+        groups = [[p for m in (net.conv_last, net.conv_hr, net.conv_up, net.conv_body) for p in m.parameters()]]
+        groups += [list(blk.parameters()) for blk in reversed(list(net.rrdb_trunk))]
+        groups.append(list(net.conv_adapt.parameters()))
+        return groups + swinir_grad_groups(net.hat)
     groups = [list(net.conv_last.parameters()) + list(net.upsample.parameters())
               + list(net.conv_before_upsample.parameters()) + list(net.conv_after_body.parameters())
               + list(net.norm.parameters())]

@@ -58,5 +58,22 @@ elif which in ("attn16_fwd", "attn16_bwd", "oca_fwd", "oca_bwd"):
         do = torch.randn(T8, 192, device=dev).to(bf); dq = torch.empty_like(qkv); dt = torch.empty_like(tab)
         ws = torch.empty(capi.attn16_bwd_ws_bytes(geom, mode, 6), device=dev, dtype=torch.uint8)
         for _ in range(reps): capi.win_attn16_bwd(geom, mode, 6, qkv, tab, out, do, lse, dq, ws, dt)
+elif which in ("rdb_fwd", "rdb_dgrad", "rdb_wgrad"):
+    # conv3 of a residual dense block at the hybrid bench shapes: batch 8, 256 x 256, nf 48, gc 24 (cin 96 -> 24)
+    from superresolution_def_b200 import conv_engine as cv
+    Bh, Hh, Wh, nf, gc, k = 8, 256, 256, 48, 24, 2
+    Th = Bh * Hh * Wh
+    cin = nf + k * gc
+    cat = torch.randn(Th, nf + 4 * gc, device=dev).to(bf); dcat = torch.randn(Th, nf + 4 * gc, device=dev).to(bf)
+    w = torch.randn(gc, cin, 3, 3, device=dev) / 30; b = torch.zeros(gc, device=dev)
+    wf, wt, bp = cv.conv_weights(w, b, 64, 128)
+    V = capi.view
+    if which == "rdb_fwd":
+        for _ in range(reps): capi.conv3x3_igemm_v(capi.CEPI_BIAS_LRELU, Bh, Hh, Wh, 128, 64, gc, V(cat, 0, cin), wf, bp, V(cat, cin, gc), slope=0.2)
+    elif which == "rdb_dgrad":
+        for _ in range(reps): capi.conv3x3_igemm_v(capi.CEPI_BIAS_RES, Bh, Hh, Wh, 64, 128, cin, V(dcat, cin, gc), wt, None, V(dcat, 0, cin), V(dcat, 0, cin))
+    else:
+        dw = torch.empty_like(w)
+        for _ in range(reps): capi.conv3x3_wgrad_v(Bh, Hh, Wh, cin, gc, 128, 64, V(dcat, cin, gc), V(cat, 0, cin), dw)
 torch.cuda.synchronize()
 print("done", which)

@@ -34,6 +34,10 @@ long long srk_launch_count(void);
 #define SRK_EPI_MUL 2    /* C = acc * X1               — backward of Mlp.act                    */
 #define SRK_EPI_RES_LN 3 /* C = acc + X1, C2 = LN(C)    — residual :149-150 + norm :127,150     */
 #define SRK_EPI_LNBWD 4  /* C = X2 + LNbackward(acc)    — backward of the same                  */
+#define SRK_EPI_GELU1 5  /* C = gelu(u)                 — Mlp.act when gelu'(u) is recomputed by MULG   */
+#define SRK_EPI_MULG 6   /* C = (A B^T) * gelu'(X1 X2^T): two GEMMs per tile, X1 = A2 [M,K] (lda = ldx1), X2 = B2
+                            [N,K]; backward of Mlp.act with u = fc1(xn2) recomputed on the tensor cores instead of
+                            a stored gelu' tensor (saves 2 x [T, hidden] of HBM traffic and memory per block)   */
 
 typedef struct SrkLnArgs {
   int n_real;         /* real channel count normalised (180 / 90)                         */
@@ -106,7 +110,7 @@ typedef struct SrkBlockActs {
   void* xn2;         /* [T,Cp] LayerNorm2(x_mid)                                      */
   float* stats2;     /* [T,2]                                                         */
   void* act;         /* [T,Hp] gelu(fc1)                                              */
-  void* dact;        /* [T,Hp] gelu'(fc1)                                             */
+  void* dact;        /* [T,Hp] gelu'(fc1), or NULL: not stored, the backward recomputes it (SRK_EPI_MULG) */
   void* x_out;       /* [T,Cp] x_mid + fc2(act)                                       */
   void* xn_out;      /* [T,Cp] LayerNorm_next(x_out): next block's norm1 or the model's final norm */
   float* stats_out;  /* [T,2]                                                         */

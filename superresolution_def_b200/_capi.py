@@ -59,7 +59,7 @@ _gemm_wgrad = _sig("srk_gemm_wgrad", [c_int, c_int, c_int, c_void_p, c_int, c_vo
 _gemm_wgrad_dbg = _sig("srk_gemm_wgrad_dbg", [c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p,
                                                c_int, c_void_p, c_int, c_int, c_void_p])
 
-EPI_STORE, EPI_GELU2, EPI_MUL, EPI_RES_LN, EPI_LNBWD = range(5)
+EPI_STORE, EPI_GELU2, EPI_MUL, EPI_RES_LN, EPI_LNBWD, EPI_GELU1, EPI_MULG = range(7)
 
 
 def launch_count() -> int:

@@ -351,11 +351,16 @@ static int block_fwd_impl(const SrkBlockDims* d, const SrkGeom* g, const SrkBloc
   if ((rc = srk_gemm_tn(SRK_EPI_RES_LN, T, Cp, AW, a->ao, AW, w->proj_f, AW, a->x_mid, Cp, a->xn2, Cp, resid, Cp,
                         nullptr, 0, &ln2, stream)))
     return rc;
-  // act = gelu(fc1(xn2)), dact = gelu'(.)
+  // act = gelu(fc1(xn2)); gelu'(.) is stored only if the caller provides `dact` (otherwise the backward recomputes it)
   SrkLnArgs ge{Hp, d->hidden, nullptr, nullptr, nullptr, nullptr, 0.f, nullptr, 1};
-  if ((rc = srk_gemm_tn(SRK_EPI_GELU2, T, Hp, Cp, a->xn2, Cp, w->fc1_f, Cp, a->act, Hp, a->dact, Hp, nullptr, 0, nullptr,
-                        0, &ge, stream)))
-    return rc;
+  if (a->dact) {
+    rc = srk_gemm_tn(SRK_EPI_GELU2, T, Hp, Cp, a->xn2, Cp, w->fc1_f, Cp, a->act, Hp, a->dact, Hp, nullptr, 0, nullptr, 0,
+                     &ge, stream);
+  } else {
+    rc = srk_gemm_tn(SRK_EPI_GELU1, T, Hp, Cp, a->xn2, Cp, w->fc1_f, Cp, a->act, Hp, nullptr, 0, nullptr, 0, nullptr, 0,
+                     &ge, stream);
+  }
+  if (rc) return rc;
   // x_out = x_mid + fc2(act); xn_out = LN_next(x_out)
   SrkLnArgs lnn{d->C, d->C, next_norm_w, next_norm_b, a->stats_out, nullptr, 1e-5f, x ? x->drop_mlp : nullptr, g->H * g->W};
   if ((rc = srk_gemm_tn(SRK_EPI_RES_LN, T, Cp, Hp, a->act, Hp, w->fc2_f, Hp, a->x_out, Cp, a->xn_out, Cp, a->x_mid, Cp,
@@ -388,10 +393,16 @@ static int block_bwd_impl(const SrkBlockDims* d, const SrkGeom* g, const SrkBloc
   };
   if (x && (x->drop_attn || x->drop_mlp) && !x->gs_buf) return fail(SRK_ERR_ARG, "srk_hat_block_bwd: gs_buf is required with drop_*");
   const void* g_mlp = scaled(g_out, x ? x->drop_mlp : nullptr);
-  // dU = (g_out @ W2) * gelu'(u)
-  if ((rc = srk_gemm_tn(SRK_EPI_MUL, T, Hp, Cp, g_mlp, Cp, w->fc2_t, Cp, s->d_act, Hp, nullptr, 0, a->dact, Hp, nullptr,
-                        0, nullptr, stream_)))
-    return rc;
+  // dU = (g_out @ W2) * gelu'(u): gelu' read back if the forward stored it, else u = xn2 @ W1^T recomputed (MULG)
+  if (a->dact) {
+    rc = srk_gemm_tn(SRK_EPI_MUL, T, Hp, Cp, g_mlp, Cp, w->fc2_t, Cp, s->d_act, Hp, nullptr, 0, a->dact, Hp, nullptr, 0,
+                     nullptr, stream_);
+  } else {
+    SrkLnArgs ge{Hp, d->hidden, nullptr, nullptr, nullptr, nullptr, 0.f, nullptr, 1};
+    rc = srk_gemm_tn(SRK_EPI_MULG, T, Hp, Cp, g_mlp, Cp, w->fc2_t, Cp, s->d_act, Hp, nullptr, 0, a->xn2, Cp, w->fc1_f, Cp,
+                     &ge, stream_);
+  }
+  if (rc) return rc;
   // dW2^T (+db2 in row `hidden`) = act^T @ g_out
   const int s_fc = wgrad_splits(T, Hp / 128);
   if ((rc = srk_gemm_wgrad(T, Hp, Cp, a->act, Hp, g_mlp, Cp, ws + L.partials, s_fc, ws + L.ext_fc2, stream_))) return rc;

@@ -28,7 +28,8 @@ static int launch_gemm_tn(const GemmArgs& a, const CUtensorMap& tA, const CUtens
 
 static int pick_bn(int epi, int N) {
   if (epi == EPI_RES_LN || epi == EPI_LNBWD) return (N == 192) ? 192 : (N == 128 ? 128 : -1);
-  if (epi == EPI_GELU2 || epi == EPI_MUL) return (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : -1);
+  if (epi == EPI_GELU2 || epi == EPI_MUL || epi == EPI_GELU1) return (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : -1);
+  if (epi == EPI_MULG) return (N % 128 == 0) ? 128 : -1;  // two double-buffered accumulators: 4 * BN <= 512 TMEM columns
   if (N % 192 == 0) return 192;
   if (N % 256 == 0) return 256;
   if (N % 128 == 0) return 128;
@@ -73,6 +74,7 @@ extern "C" int srk_gemm_tn(int epi, int M, int N, int K, const void* A, int lda,
   if (epi == EPI_RES_LN && (!X1 || !C2)) return fail(SRK_ERR_ARG, "RES_LN needs X1 and C2");
   if (epi == EPI_GELU2 && !C2) return fail(SRK_ERR_ARG, "GELU2 needs C2");
   if (epi == EPI_MUL && !X1) return fail(SRK_ERR_ARG, "MUL needs X1");
+  if (epi == EPI_MULG && (!X1 || !X2)) return fail(SRK_ERR_ARG, "MULG needs the second GEMM's operands in X1 (A2 [M,K]) and X2 (B2 [N,K])");
 
   CUtensorMap tA, tB, tC, tC2, tX1, tX2;
   int rc;
@@ -81,8 +83,13 @@ extern "C" int srk_gemm_tn(int epi, int M, int N, int K, const void* A, int lda,
   if ((rc = make_tmap_2d(&tC, C, M, N, ldc, GEMM_BM))) return rc;
   tC2 = tC; tX1 = tC; tX2 = tC;
   if (C2 && (rc = make_tmap_2d(&tC2, C2, M, N, ldc2, GEMM_BM))) return rc;
-  if (X1 && (rc = make_tmap_2d(&tX1, X1, M, N, ldx1, GEMM_BM))) return rc;
-  if (X2 && (rc = make_tmap_2d(&tX2, X2, M, N, ldx2, GEMM_BM))) return rc;
+  if (epi == EPI_MULG) {
+    if ((rc = make_tmap_2d(&tX1, X1, M, K, ldx1, GEMM_BM))) return rc;
+    if ((rc = make_tmap_2d(&tX2, X2, N, K, ldx2, bn))) return rc;
+  } else {
+    if (X1 && (rc = make_tmap_2d(&tX1, X1, M, N, ldx1, GEMM_BM))) return rc;
+    if (X2 && (rc = make_tmap_2d(&tX2, X2, M, N, ldx2, GEMM_BM))) return rc;
+  }
 
 #define SRK_CASE(BN_, EPI_) \
   if (bn == BN_ && epi == EPI_) return launch_gemm_tn<BN_, EPI_>(a, tA, tB, tC, tC2, tX1, tX2, stream);
@@ -94,6 +101,9 @@ extern "C" int srk_gemm_tn(int epi, int M, int N, int K, const void* A, int lda,
   SRK_CASE(256, EPI_GELU2)
   SRK_CASE(128, EPI_MUL)
   SRK_CASE(256, EPI_MUL)
+  SRK_CASE(128, EPI_GELU1)
+  SRK_CASE(256, EPI_GELU1)
+  SRK_CASE(128, EPI_MULG)
   SRK_CASE(128, EPI_RES_LN)
   SRK_CASE(192, EPI_RES_LN)
   SRK_CASE(128, EPI_LNBWD)

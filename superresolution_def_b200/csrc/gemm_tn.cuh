@@ -29,6 +29,10 @@ enum GemmEpilogue : int {
   EPI_MUL = 2,     // C = bf16(acc * X1)                                        (fc2 dgrad -> dU)
   EPI_RES_LN = 3,  // C = v = bf16(bf16(acc) + X1); C2 = LayerNorm(v)           (proj / fc2 forward)
   EPI_LNBWD = 4,   // C = X2 + LayerNormBackward(acc | X1, stats)               (fc1 / qkv dgrad)
+  EPI_GELU1 = 5,   // C = gelu(u), u = acc                 (fc1 forward when the backward recomputes gelu', see MULG)
+  EPI_MULG = 6,    // two GEMMs of the same shape per tile: acc0 = A B^T, acc1 = A2 B2^T (A2 -> tmX1, B2 -> tmX2);
+                   // C = bf16(bf16(acc0) * bf16(gelu'(acc1)))   (fc2 dgrad -> dU with u = xn2 W1^T recomputed on the
+                   // tensor cores instead of reading a stored gelu'(u): the block is HBM-bound, the MMA pipe is idle)
 };
 
 struct GemmArgs {
@@ -46,7 +50,8 @@ struct GemmArgs {
 
 template <int BN, int EPI>
 struct GemmCfg {
-  static constexpr bool kBoxEpi = (EPI == EPI_STORE || EPI == EPI_GELU2 || EPI == EPI_MUL);
+  static constexpr bool kBoxEpi = (EPI == EPI_STORE || EPI == EPI_GELU2 || EPI == EPI_MUL || EPI == EPI_GELU1 || EPI == EPI_MULG);
+  static constexpr int kAccs = (EPI == EPI_MULG) ? 2 : 1;  // accumulators per tile (each double-buffered in TMEM)
   static constexpr int kEpiWarps = kBoxEpi ? 16 : 8;
   static constexpr int kEpiThreads = 32 * kEpiWarps;
   static constexpr int kThreads = 64 + kEpiThreads;
@@ -54,7 +59,7 @@ struct GemmCfg {
   static constexpr int kColsPerPart = 64 / kParts;    // columns of a 64-column box handled by one warp
   static constexpr int kStageBytes = GEMM_BM * 128 + BN * 128;
   static constexpr int kBoxes = BN / 64;
-  static constexpr int kEpiBytes = (EPI == EPI_STORE)   ? 2 * BOX_BYTES
+  static constexpr int kEpiBytes = (EPI == EPI_STORE || EPI == EPI_GELU1 || EPI == EPI_MULG) ? 2 * BOX_BYTES
                                    : (EPI == EPI_GELU2) ? 4 * BOX_BYTES
                                    : (EPI == EPI_MUL)   ? 4 * BOX_BYTES
                                                         : 2 * kBoxes * BOX_BYTES;
@@ -65,6 +70,7 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 512 + kRedBytes + 1024;
   static_assert(kStages >= 2, "not enough shared memory for a 2-stage pipeline");
   static_assert(BN % 64 == 0 && BN <= 256, "BN must be a multiple of 64, <= 256");
+  static_assert(2 * kAccs * BN <= 512, "double-buffered accumulators must fit the 512 TMEM columns");
 };
 
 // GELU (exact-erf semantics, nn.GELU default) and its derivative with ONE MUFU op per element:
@@ -180,13 +186,18 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / n_tiles) * GEMM_BM;
         const int n0 = (tile % n_tiles) * BN;
-        for (int kb = 0; kb < k_iters; ++kb) {
+        for (int kb = 0; kb < Cfg::kAccs * k_iters; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
           const uint32_t sb = sa + GEMM_BM * 128;
           mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
-          tma_load_2d(sa, &tmA, full_bar(stage), kb * GEMM_BK, m0);
-          tma_load_2d(sb, &tmB, full_bar(stage), kb * GEMM_BK, n0);
+          if (Cfg::kAccs == 2 && kb >= k_iters) {  // second GEMM of the tile: operands A2 / B2
+            tma_load_2d(sa, &tmX1, full_bar(stage), (kb - k_iters) * GEMM_BK, m0);
+            tma_load_2d(sb, &tmX2, full_bar(stage), (kb - k_iters) * GEMM_BK, n0);
+          } else {
+            tma_load_2d(sa, &tmA, full_bar(stage), kb * GEMM_BK, m0);
+            tma_load_2d(sb, &tmB, full_bar(stage), kb * GEMM_BK, n0);
+          }
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
       }
@@ -203,8 +214,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t acc_phase = (it >> 1) & 1u;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
-        for (int kb = 0; kb < k_iters; ++kb) {
+        for (int kb = 0; kb < Cfg::kAccs * k_iters; ++kb) {
+          const int g2 = (Cfg::kAccs == 2 && kb >= k_iters) ? 1 : 0;
+          const int kk = kb - g2 * k_iters;
+          const uint32_t d_tmem = tmem_base + uint32_t((acc * Cfg::kAccs + g2) * BN);
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
@@ -213,7 +226,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             const uint64_t adesc = make_smem_desc(sa + k * 32, 16, 1024);
             const uint64_t bdesc = make_smem_desc(sb + k * 32, 16, 1024);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (kk | k) != 0 ? 1u : 0u);
           }
           umma_commit(empty_bar(stage));
           if (++stage == S) { stage = 0; phase ^= 1u; }
@@ -267,13 +280,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n0 = (tile % n_tiles) * BN;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
-      const uint32_t taddr = tmem_base + lane_sel + uint32_t(acc * BN);
+      const uint32_t taddr = tmem_base + lane_sel + uint32_t(acc * Cfg::kAccs * BN);
       const int next_tile = tile + gridDim.x;
 
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
 
-      if constexpr (EPI == EPI_STORE || EPI == EPI_GELU2 || EPI == EPI_MUL) {
+      if constexpr (Cfg::kBoxEpi) {
         // ---------------------------------------------------------- box-granular elementwise epilogues
         constexpr int kAuxOff = 0;                                     // MUL: 2 aux boxes first
         constexpr int kOutOff = (EPI == EPI_MUL) ? 2 * BOX_BYTES : 0;  // then staging ring
@@ -310,7 +323,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           {
             constexpr int CPP = Cfg::kColsPerPart;
             uint32_t r[CPP];
+            uint32_t ru[(EPI == EPI_MULG) ? CPP : 1];
             tmem_ld_cols(taddr + uint32_t(j * 64 + half * CPP), r);
+            if constexpr (EPI == EPI_MULG) tmem_ld_cols(taddr + uint32_t(BN + j * 64 + half * CPP), ru);
             tmem_ld_wait();
             if (j == NBOX - 1) {  // accumulator fully drained into registers: hand TMEM back to the MMA warp
               tc_fence_before();
@@ -335,6 +350,34 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int e = 0; e < 4; ++e)
                   o[e] = pack_bf16(round_bf16(v[2 * e]) * bf16_lo(gw[e]), round_bf16(v[2 * e + 1]) * bf16_hi(gw[e]));
                 sts128(out0 + off, make_uint4(o[0], o[1], o[2], o[3]));
+              } else if constexpr (EPI == EPI_MULG) {
+                const int col0 = n0 + j * 64 + ch * 8;
+                float o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  float a_, g_;
+                  gelu_pair(__uint_as_float(ru[i * 8 + e]), a_, g_);   // same fp32 accumulator value the forward saw
+                  o[e] = round_bf16(v[e]) * round_bf16(g_);
+                }
+                if (args.ones_col >= col0 && args.ones_col < col0 + 8) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e)
+                    if (col0 + e == args.ones_col) o[e] = 0.0f;   // the forward's constant 1.0 column has no gradient
+                }
+                sts128(out0 + off, make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]),
+                                              pack_bf16(o[6], o[7])));
+              } else if constexpr (EPI == EPI_GELU1) {
+                float a[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { float g_; gelu_pair(v[e], a[e], g_); }
+                const int col0 = n0 + j * 64 + ch * 8;
+                if (args.ones_col >= col0 && args.ones_col < col0 + 8) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e)
+                    if (col0 + e == args.ones_col) a[e] = 1.0f;
+                }
+                sts128(out0 + off, make_uint4(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]),
+                                              pack_bf16(a[4], a[5]), pack_bf16(a[6], a[7])));
               } else {  // EPI_GELU2
                 float a[8], g[8];
 #pragma unroll

@@ -13,6 +13,8 @@ from __future__ import annotations
 
 from dataclasses import dataclass
 
+import os
+
 import torch
 
 from . import _capi as capi
@@ -111,12 +113,23 @@ def _check_param(p: torch.Tensor):
         raise capi.SrkError("libsrk needs contiguous fp32 CUDA parameters (no CPU / fallback path exists)")
 
 
+STORE_GELU_GRAD = bool(int(os.environ.get("SRK_STORE_DACT", "1")))
+
+
 def _alloc_acts(cfg: BlockCfg, T: int, device) -> dict:
+    """Activations a block saves for its backward.  gelu'(u) ("dact", [T, Hp]) is stored by default.  SRK_STORE_DACT=0
+    drops it: the backward then recomputes u = xn2 W1^T inside the fc2 input-gradient kernel (SRK_EPI_MULG, bit-identical
+    dU).  Measured on B200 (tools/gpu_probe_mlp.py): forward 200 -> 144 us, backward 194 -> 265 us per block — the
+    epilogues are instruction-issue bound, so recomputing the GELU polynomial costs more than the 0.8 GB of traffic it
+    saves; the variant is kept as the memory-saving mode (-14.5 GB at batch 16), not as the default."""
     e = lambda w: torch.empty(T, w, device=device, dtype=BF16)  # noqa: E731
-    return {"qkv": e(cfg.QW), "ao": e(cfg.AW), "x_mid": e(cfg.Cp), "xn2": e(cfg.Cp),
-            "stats2": torch.empty(T, 2, device=device, dtype=torch.float32), "act": e(cfg.Hp), "dact": e(cfg.Hp),
+    acts = {"qkv": e(cfg.QW), "ao": e(cfg.AW), "x_mid": e(cfg.Cp), "xn2": e(cfg.Cp),
+            "stats2": torch.empty(T, 2, device=device, dtype=torch.float32), "act": e(cfg.Hp),
             "x_out": e(cfg.Cp), "xn_out": e(cfg.Cp),
             "stats_out": torch.empty(T, 2, device=device, dtype=torch.float32)}
+    if STORE_GELU_GRAD:
+        acts["dact"] = e(cfg.Hp)
+    return acts
 
 
 def layernorm_tokens(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, C: int):

@@ -1,6 +1,7 @@
 // api_conv.cu — C-ABI entry points for the convolutional paths (implicit-GEMM conv3x3 fwd/dgrad/wgrad with
 // fused bias / LeakyReLU / residual / PixelShuffle / GELU epilogues, and the 1-channel head/tail convolutions).
-#include "conv3x3.cuh"
+#include "conv3x3_halo.cuh"
+#include <cstdlib>
 #include "conv_aux.cuh"
 #include "srk_host.h"
 
@@ -38,6 +39,33 @@ int launch_conv(const ConvMaps& maps, const ConvArgs& a, cudaStream_t stream) {
   SRK_LAUNCHED(1);
   SRK_CUDA_OK(cudaGetLastError());
   return SRK_OK;
+}
+
+template <int BN, int EPI>
+int launch_conv_halo(const ConvMaps& maps, const ConvArgs& a, cudaStream_t stream) {
+  using Cfg = HaloCfg<BN, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    SRK_CUDA_OK(cudaFuncSetAttribute(conv3x3_halo_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int tiles = a.B * (a.H / HALO_TH) * (a.W / HALO_TW) * (a.Cout_p / BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  conv3x3_halo_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(maps, a);
+  SRK_LAUNCHED(1);
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+// 0: per-tap boxes (conv3x3_kernel); 1 (default): halo-resident tiles where the shape allows (H % 16 == 0, W % 8 == 0)
+int conv_halo_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = std::getenv("SRK_CONV_HALO");
+    mode = e ? std::atoi(e) : 1;
+  }
+  return mode;
 }
 
 template <int BNW>
@@ -268,16 +296,24 @@ extern "C" int srk_conv3x3_igemm_v(int epi, int B, int H, int W, int Cin_p, int 
   ConvMaps maps;
   memset(&maps, 0, sizeof(maps));
   int rc;
-  if ((rc = view_map(&maps.a[0], x, B, H, W, CONV_TW, CONV_TH))) return rc;
+  const int hmode = conv_halo_mode();
+  // Measured on B200 (hybrid step, tools/gpu_probe_hybrid_prof.py): the halo-resident kernel wins where one 64-channel
+  // chunk feeds all nine taps and the weight ring stays deep (Cin_p == 64, BN <= 128: 151 -> 100 us, 189 -> 166 us); with
+  // two or three chunks per tile its two-stage halo ring exposes the TMA latency and the per-tap kernel is as fast or
+  // faster, so those shapes stay on conv3x3_kernel.  SRK_CONV_HALO=3 forces it everywhere (tests), 0 disables it.
+  const bool halo_shape = H % HALO_TH == 0 && W % HALO_TW == 0;
+  const bool halo = halo_shape && (hmode >= 2 || (hmode == 1 && Cin_p == 64 && Cout_p <= 128));
+  const int cbw = halo ? HALO_TW : CONV_TW, cbh = halo ? HALO_TH : CONV_TH;
+  if ((rc = view_map(&maps.a[0], x, B, H, W, halo ? HALO_BW : CONV_TW, halo ? HALO_BH : CONV_TH))) return rc;
   if (out1) maps.c[0] = maps.a[0];
-  else if ((rc = view_map(&maps.c[0], y, B, H, W, CONV_TW, CONV_TH))) return rc;
+  else if ((rc = view_map(&maps.c[0], y, B, H, W, cbw, cbh))) return rc;
   for (int i = 1; i < 4; ++i) { maps.a[i] = maps.a[0]; maps.c[i] = maps.c[0]; }
   maps.c2 = maps.c[0];
   maps.r = maps.c[0];
   const bool need_r = (epi == CEPI_BIAS_RES || epi == CEPI_MASK_LRELU || epi == CEPI_MUL);
   if (need_r) {
     if (!r) return fail(SRK_ERR_ARG, "conv3x3_v: epilogue needs an aux view");
-    if ((rc = view_map(&maps.r, r, B, H, W, CONV_TW, CONV_TH))) return rc;
+    if ((rc = view_map(&maps.r, r, B, H, W, cbw, cbh))) return rc;
   }
   if (epi == CEPI_BIAS_GELU) return fail(SRK_ERR_UNSUPPORTED, "conv3x3_v: GELU epilogue is served by srk_conv3x3_igemm");
   const int bn = Cout_p;
@@ -286,6 +322,17 @@ extern "C" int srk_conv3x3_igemm_v(int epi, int B, int H, int W, int Cin_p, int 
   a.B = B; a.H = H; a.W = W; a.Cin_p = Cin_p; a.Cout_p = Cout_p; a.n_real = n_real; a.bias = bias; a.slope = slope;
   a.a_split = 0; a.c_split = 0; a.alpha = alpha;
   a.y32 = out1 ? y32 : nullptr;
+  if (halo) {
+    a.a_split = (hmode == 2);  // probe switch: 2 = descriptors WITH the matrix base offset kx (documented as wrong on B200)
+#define SRK_HCASE(BN_, EPI_) if (bn == BN_ && epi == EPI_) return launch_conv_halo<BN_, EPI_>(maps, a, stream);
+    SRK_HCASE(64, CEPI_BIAS) SRK_HCASE(128, CEPI_BIAS) SRK_HCASE(192, CEPI_BIAS) SRK_HCASE(256, CEPI_BIAS)
+    SRK_HCASE(64, CEPI_BIAS_LRELU) SRK_HCASE(192, CEPI_BIAS_LRELU)
+    SRK_HCASE(64, CEPI_BIAS_RES) SRK_HCASE(128, CEPI_BIAS_RES) SRK_HCASE(192, CEPI_BIAS_RES) SRK_HCASE(256, CEPI_BIAS_RES)
+    SRK_HCASE(64, CEPI_MASK_LRELU) SRK_HCASE(192, CEPI_MASK_LRELU)
+    SRK_HCASE(16, CEPI_OUT1)
+#undef SRK_HCASE
+    return fail(SRK_ERR_UNSUPPORTED, "conv3x3_v: no halo kernel instance for (Cout_p, epilogue)");
+  }
 #define SRK_CCASE(BN_, EPI_) if (bn == BN_ && epi == EPI_) return launch_conv<BN_, EPI_>(maps, a, stream);
   SRK_CCASE(64, CEPI_BIAS) SRK_CCASE(128, CEPI_BIAS) SRK_CCASE(192, CEPI_BIAS) SRK_CCASE(256, CEPI_BIAS)
   SRK_CCASE(64, CEPI_BIAS_LRELU) SRK_CCASE(192, CEPI_BIAS_LRELU)

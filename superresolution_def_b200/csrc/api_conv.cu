@@ -153,7 +153,9 @@ extern "C" int srk_conv3x3_igemm(int epi, int B, int H, int W, int Cin_p, int Co
 }
 
 extern "C" long long srk_conv3x3_wgrad_ws_floats(int Cin_p, int Cout_p) {
-  return (long long)num_sms() * 128 * Cin_p + 16;  // co_tiles*9*splits <= num_sms tiles of [128 x Cin_p]
+  const long long a = (long long)num_sms() * 128 * Cin_p + 16;   // co_tiles*9*splits <= num_sms tiles of [128 x Cin_p]
+  const long long b = (long long)num_sms() * 128 * 9 * WT_NCO;   // thin variant: ci_tiles*splits <= num_sms tiles of [128 x 9 x 32]
+  return a > b ? a : b;
 }
 
 extern "C" int srk_conv3x3_wgrad(int B, int H, int W, int Cin, int Cout, int Cin_p, int Cout_p, int ps,
@@ -348,9 +350,36 @@ extern "C" int srk_conv3x3_wgrad_v(int B, int H, int W, int Cin, int Cout, int C
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (H % 4 || W % 16 || Cin_p % 64 || Cout_p % 64 || Cin_p > 256) return fail(SRK_ERR_UNSUPPORTED, "conv wgrad: shape");
   if (!dy || !x || dy->C > Cout_p || x->C > Cin_p || Cout > Cout_p || Cin > Cin_p) return fail(SRK_ERR_ARG, "conv wgrad_v: views");
+  int rc;
+  if (conv_halo_mode() != 0 && Cout <= WT_NCO && dy->C <= 64) {
+    // few output channels: one CTA per pixel range computes all nine taps from one halo load (conv3x3_wgrad_thin_kernel)
+    ConvWgradThinMaps tm;
+    memset(&tm, 0, sizeof(tm));
+    if ((rc = view_map(&tm.dy, dy, B, H, W, 16, 4))) return rc;
+    if ((rc = view_map(&tm.x, x, B, H, W, 18, 6))) return rc;
+    static bool configured = false;
+    if (!configured) {
+      SRK_CUDA_OK(cudaFuncSetAttribute(conv3x3_wgrad_thin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM));
+      configured = true;
+    }
+    ConvWgradThinArgs t{};
+    t.B = B; t.H = H; t.W = W; t.ci_tiles = (Cin_p + 127) / 128;
+    const int iters = B * (H / 4) * (W / 16);
+    t.splits = num_sms() / t.ci_tiles;
+    if (t.splits > iters) t.splits = iters;
+    if (t.splits < 1) t.splits = 1;
+    t.partials = ws;
+    conv3x3_wgrad_thin_kernel<<<t.ci_tiles * t.splits, WG_THREADS, WT_SMEM, stream>>>(tm, t);
+    SRK_LAUNCHED(1);
+    SRK_CUDA_OK(cudaGetLastError());
+    const int total = Cout * Cin * 9;
+    conv_unpack_wgrad_thin_kernel<<<(total + 255) / 256, 256, 0, stream>>>(ws, t.splits, t.ci_tiles, dw, Cout, Cin);
+    SRK_LAUNCHED(1);
+    SRK_CUDA_OK(cudaGetLastError());
+    return SRK_OK;
+  }
   ConvWgradMaps maps;
   memset(&maps, 0, sizeof(maps));
-  int rc;
   if ((rc = view_map(&maps.a[0], dy, B, H, W, 16, 4))) return rc;
   for (int i = 1; i < 4; ++i) maps.a[i] = maps.a[0];
   if ((rc = view_map(&maps.b, x, B, H, W, 16, 4))) return rc;

@@ -288,3 +288,134 @@ conv3x3_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) 
 
 
 }  // namespace srk
+
+namespace srk {
+// ------------------------------------------------------------------------------------------------ thin wgrad
+// Weight gradient of a 3x3 convolution with FEW output channels (Cout <= 32: conv1..conv4 of a residual dense block,
+// hybridmodels_hat.py:24-27), halo-resident:  dW[tap][ci][co] = sum over pixels of X[p + tap][ci] * dY[p][co].
+// conv3x3_wgrad_kernel runs one CTA per (tap, split) and so pulls X and dY through the crossbar nine times (ncu: 2.6 GB
+// for a 250 MB layer).  Here a CTA owns a pixel range and ALL nine taps: per 16 x 4 pixel patch it loads dY once
+// (B operand, N = 32) and X once with its border (A operand, M = 128 input channels, box 64 ch x 18 x 6 pixels), and
+// issues 9 taps x 4 image rows of K = 16 pixels as row-shifted MN-major descriptors into nine [128 x 32] fp32
+// accumulators that sit side by side in TMEM (288 columns).  grid = ci_tiles x splits; partials reduced afterwards.
+constexpr int WT_XBOX = 14 * 1024;                  // 18 * 6 * 128 B = 13824, padded so every box base is 1024-aligned
+constexpr int WT_XBOX_TX = 18 * 6 * 128;
+constexpr int WT_DYBOX = 16 * 4 * 128;
+constexpr int WT_STAGE = 2 * WT_XBOX + WT_DYBOX;    // 36864
+constexpr int WT_STAGES = 5;
+constexpr int WT_SMEM = WT_STAGES * WT_STAGE + 256 + 1024;
+constexpr int WT_NCO = 32;
+
+struct ConvWgradThinArgs {
+  int B, H, W, ci_tiles, splits;
+  float* partials;  // [splits][ci_tiles][128][9][32]
+};
+struct ConvWgradThinMaps {
+  CUtensorMap dy;  // box (64, 16, 4, 1)
+  CUtensorMap x;   // box (64, 18, 6, 1)
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+conv3x3_wgrad_thin_kernel(const __grid_constant__ ConvWgradThinMaps maps, const ConvWgradThinArgs args) {
+  constexpr int S = WT_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + S * WT_STAGE;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
+  const uint32_t tfull_bar = bar_base + 8u * (2 * S);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * S + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ci_tile = blockIdx.x % args.ci_tiles;
+  const int split = blockIdx.x / args.ci_tiles;
+  const int px = args.W / 16, py = args.H / 4;
+  const int total_iters = args.B * py * px;  // 64-pixel patches
+  const int it_begin = int((long long)split * total_iters / args.splits);
+  const int it_end = int((long long)(split + 1) * total_iters / args.splits);
+  const int k_iters = it_end - it_begin;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tfull_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < k_iters; ++kb) {
+        const int p = it_begin + kb;
+        const int b = p / (py * px), r = p % (py * px);
+        const int y0 = (r / px) * 4, x0 = (r % px) * 16;
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t sx = smem_base + stage * WT_STAGE;
+        mbar_arrive_expect_tx(full_bar(stage), 2 * WT_XBOX_TX + WT_DYBOX);
+        tma_load_4d(sx, &maps.x, full_bar(stage), (ci_tile * 2) * 64, x0 - 1, y0 - 1, b);
+        tma_load_4d(sx + WT_XBOX, &maps.x, full_bar(stage), (ci_tile * 2 + 1) * 64, x0 - 1, y0 - 1, b);
+        tma_load_4d(sx + 2 * WT_XBOX, &maps.dy, full_bar(stage), 0, x0, y0, b);
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, WT_NCO, 1, 1);
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < k_iters; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t sx = smem_base + stage * WT_STAGE;
+        const uint32_t sdy = sx + 2 * WT_XBOX;
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+          const int ky = tap / 3, kx = tap - ky * 3;
+#pragma unroll
+          for (int y = 0; y < 4; ++y)
+            umma_bf16(tmem_base + uint32_t(tap * WT_NCO),
+                      make_smem_desc(sx + uint32_t((y + ky) * 18 + kx) * 128u, WT_XBOX, 1024),
+                      make_smem_desc(sdy + uint32_t(y) * 2048u, WT_DYBOX, 1024), idesc, (kb | y) != 0 ? 1u : 0u);
+        }
+        umma_commit(empty_bar(stage));
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(tfull_bar);
+    }
+  } else {
+    const int q = warp & 3, row = q * 32 + lane;
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16);
+    float* out = args.partials + ((size_t(split) * args.ci_tiles + ci_tile) * 128 + row) * (9 * WT_NCO);
+#pragma unroll 1
+    for (int tap = 0; tap < 9; ++tap) {
+      uint32_t r[32];
+      tmem_ld_x32(taddr + uint32_t(tap * WT_NCO), r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        reinterpret_cast<uint4*>(out + tap * WT_NCO)[i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// partials [splits][ci_tiles][128][9][32] -> dW [Cout][Cin][3][3]
+static __global__ void conv_unpack_wgrad_thin_kernel(const float* __restrict__ part, int splits, int ci_tiles,
+                                                     float* __restrict__ dw, int Cout, int Cin) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Cout * Cin * 9) return;
+  const int co = i / (Cin * 9), ci = (i / 9) % Cin, tap = i % 9;
+  const size_t off = ((size_t(ci >> 7) * 128 + (ci & 127)) * 9 + tap) * WT_NCO + co;
+  const size_t stride = size_t(ci_tiles) * 128 * 9 * WT_NCO;
+  float acc = 0.f;
+  for (int s = 0; s < splits; ++s) acc += part[s * stride + off];
+  dw[i] = acc;
+}
+}  // namespace srk

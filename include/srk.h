@@ -225,7 +225,9 @@ int srk_conv3x3_wgrad_v(int B, int H, int W, int Cin, int Cout, int Cin_p, int C
                         const SrkView* x, float* ws, float* dw, void* stream);
 int srk_bias_grad_v(const SrkView* dy, long long npix, float* ws, float* db, int n_out, void* stream);
 /* g *= (f > 0 ? 1 : slope): backward through nn.LeakyReLU (hybridmodels_hat.py:29), f = forward output */
-int srk_view_lrelu_mask(const SrkView* g, const SrkView* f, long long npix, float slope, void* stream);
+/* colsum (may be NULL): [g->C] column sums of the masked gradient = bias gradient of the layer; ws: srk_small_ws_floats */
+int srk_view_lrelu_mask(const SrkView* g, const SrkView* f, long long npix, float slope, float* ws, float* colsum,
+                        void* stream);
 /* y = alpha * a + x (x may be NULL; y may alias a or x): the 0.2-scaled residuals (:44,:58) and their gradients */
 int srk_view_axpy(const SrkView* y, const SrkView* a, const SrkView* x, long long npix, float alpha, void* stream);
 /* F.interpolate(scale_factor=2, mode='nearest') (:127) on NHWC views, x [B,H,W,C] -> y [B,2H,2W,C], and its adjoint */

@@ -462,7 +462,8 @@ _conv_igemm_v = _sig("srk_conv3x3_igemm_v", [c_int, c_int, c_int, c_int, c_int, 
 _conv_wgrad_v = _sig("srk_conv3x3_wgrad_v", [c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(SrkView),
                                              POINTER(SrkView), c_void_p, c_void_p, c_void_p])
 _bias_grad_v = _sig("srk_bias_grad_v", [POINTER(SrkView), c_longlong, c_void_p, c_void_p, c_int, c_void_p])
-_view_lrelu_mask = _sig("srk_view_lrelu_mask", [POINTER(SrkView), POINTER(SrkView), c_longlong, c_float, c_void_p])
+_view_lrelu_mask = _sig("srk_view_lrelu_mask", [POINTER(SrkView), POINTER(SrkView), c_longlong, c_float, c_void_p, c_void_p,
+                                                c_void_p])
 _view_axpy = _sig("srk_view_axpy", [POINTER(SrkView), POINTER(SrkView), POINTER(SrkView), c_longlong, c_float, c_void_p])
 _nearest2_fwd = _sig("srk_nearest2_fwd", [POINTER(SrkView), POINTER(SrkView), c_int, c_int, c_int, c_void_p])
 _nearest2_bwd = _sig("srk_nearest2_bwd", [POINTER(SrkView), POINTER(SrkView), c_int, c_int, c_int, c_void_p])
@@ -492,8 +493,10 @@ def bias_grad_v(dy: SrkView, npix, db):
     _check(_bias_grad_v(_vref(dy), npix, _ptr(ws), _ptr(db), db.numel(), _stream()), "srk_bias_grad_v")
 
 
-def view_lrelu_mask(g: SrkView, f: SrkView, npix, slope):
-    _check(_view_lrelu_mask(_vref(g), _vref(f), npix, slope, _stream()), "srk_view_lrelu_mask")
+def view_lrelu_mask(g: SrkView, f: SrkView, npix, slope, colsum=None):
+    """colsum: optional fp32 [g.C] tensor receiving the column sums of the masked gradient (the bias gradient)."""
+    ws = _ws(int(lib.srk_small_ws_floats()), colsum.device) if colsum is not None else None
+    _check(_view_lrelu_mask(_vref(g), _vref(f), npix, slope, _ptr(ws), _ptr(colsum), _stream()), "srk_view_lrelu_mask")
 
 
 def view_axpy(y: SrkView, a: SrkView, x: SrkView | None, npix, alpha):

@@ -372,7 +372,7 @@ extern "C" int srk_conv3x3_wgrad_v(int B, int H, int W, int Cin, int Cout, int C
     conv3x3_wgrad_thin_kernel<<<t.ci_tiles * t.splits, WG_THREADS, WT_SMEM, stream>>>(tm, t);
     SRK_LAUNCHED(1);
     SRK_CUDA_OK(cudaGetLastError());
-    const int total = Cout * Cin * 9;
+    const int total = t.ci_tiles * 128 * 9 * WT_NCO;
     conv_unpack_wgrad_thin_kernel<<<(total + 255) / 256, 256, 0, stream>>>(ws, t.splits, t.ci_tiles, dw, Cout, Cin);
     SRK_LAUNCHED(1);
     SRK_CUDA_OK(cudaGetLastError());
@@ -416,13 +416,24 @@ extern "C" int srk_bias_grad_v(const SrkView* dy, long long npix, float* ws, flo
   return SRK_OK;
 }
 
-extern "C" int srk_view_lrelu_mask(const SrkView* g, const SrkView* f, long long npix, float slope, void* stream_) {
+extern "C" int srk_view_lrelu_mask(const SrkView* g, const SrkView* f, long long npix, float slope, float* ws, float* colsum,
+                                   void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (!g || !f || g->C != f->C || g->C % 8 || g->pitch % 8 || f->pitch % 8) return fail(SRK_ERR_ARG, "view_lrelu_mask: views");
-  view_lrelu_mask_kernel<<<ew_grid(npix * (g->C / 8)), 256, 0, stream>>>(
+  if (!g || !f || g->C != f->C || g->C % 8 || g->pitch % 8 || f->pitch % 8 || g->C > 256)
+    return fail(SRK_ERR_ARG, "view_lrelu_mask: views");
+  if (colsum && !ws) return fail(SRK_ERR_ARG, "view_lrelu_mask: column sums need the small workspace");
+  const int groups = g->C / 8;
+  int grid = ew_grid(npix * groups);
+  if (colsum && grid > num_sms() * 4) grid = num_sms() * 4;   // few partial rows for the finishing kernel
+  grid = (grid + groups - 1) / groups * groups;   // total threads divisible by `groups`: a thread keeps its channel group
+  view_lrelu_mask_kernel<<<grid, 256, 256 * 8 * sizeof(float), stream>>>(
       static_cast<__nv_bfloat16*>(const_cast<void*>(g->ptr)), g->pitch, static_cast<const __nv_bfloat16*>(f->ptr), f->pitch,
-      g->C, npix, slope);
+      g->C, npix, slope, colsum ? ws : nullptr);
   SRK_LAUNCHED(1);
+  if (colsum) {
+    colsum_finish_kernel<<<(g->C + 127) / 128, 128, 0, stream>>>(ws, grid, g->C, colsum, g->C);
+    SRK_LAUNCHED(1);
+  }
   SRK_CUDA_OK(cudaGetLastError());
   return SRK_OK;
 }

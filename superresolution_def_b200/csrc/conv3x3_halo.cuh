@@ -406,16 +406,16 @@ conv3x3_wgrad_thin_kernel(const __grid_constant__ ConvWgradThinMaps maps, const 
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
-// partials [splits][ci_tiles][128][9][32] -> dW [Cout][Cin][3][3]
+// partials [splits][ci_tiles][128][9][32] -> dW [Cout][Cin][3][3]; one thread per partial element (coalesced over splits)
 static __global__ void conv_unpack_wgrad_thin_kernel(const float* __restrict__ part, int splits, int ci_tiles,
                                                      float* __restrict__ dw, int Cout, int Cin) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= Cout * Cin * 9) return;
-  const int co = i / (Cin * 9), ci = (i / 9) % Cin, tap = i % 9;
-  const size_t off = ((size_t(ci >> 7) * 128 + (ci & 127)) * 9 + tap) * WT_NCO + co;
-  const size_t stride = size_t(ci_tiles) * 128 * 9 * WT_NCO;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per_split = ci_tiles * 128 * 9 * WT_NCO;
+  if (e >= per_split) return;
+  const int co = e % WT_NCO, tap = (e / WT_NCO) % 9, ci = e / (9 * WT_NCO);
+  if (co >= Cout || ci >= Cin) return;
   float acc = 0.f;
-  for (int s = 0; s < splits; ++s) acc += part[s * stride + off];
-  dw[i] = acc;
+  for (int s = 0; s < splits; ++s) acc += part[size_t(s) * per_split + e];
+  dw[(size_t(co) * Cin + ci) * 9 + tap] = acc;
 }
 }  // namespace srk

@@ -345,13 +345,19 @@ namespace srk {
 // aligned slices: every thread moves 16 bytes.
 
 // g[:, :C] *= (f[:, :C] > 0 ? 1 : slope)     (backward through LeakyReLU; f = forward output)
+// Optionally also the column sums of the masked gradient (= the bias gradient of the layer that produced f): the total
+// thread count is a multiple of C/8, so a thread always meets the same 8 channels and keeps their sums in registers;
+// per-block partials [gridDim.x][C] are reduced by colsum_finish_kernel.
 static __global__ void view_lrelu_mask_kernel(__nv_bfloat16* __restrict__ g, int ldg, const __nv_bfloat16* __restrict__ f,
-                                              int ldf, int C, long long npix, float slope) {
+                                              int ldf, int C, long long npix, float slope, float* __restrict__ partial) {
+  extern __shared__ float s_cs[];  // [blockDim.x][8]
   const int groups = C >> 3;
-  const long long total = npix * groups;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long p = i / groups;
-    const int c = int(i - p * groups) * 8;
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = int(tid % groups) * 8;
+  const long long pstride = nthreads / groups;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (long long p = tid / groups; p < npix; p += pstride) {
     uint4* gp = reinterpret_cast<uint4*>(g + p * ldg + c);
     const uint4 fv = *reinterpret_cast<const uint4*>(f + p * ldf + c);
     uint4 gv = *gp;
@@ -362,8 +368,24 @@ static __global__ void view_lrelu_mask_kernel(__nv_bfloat16* __restrict__ g, int
       const float lo = bf16_lo(fw[e]) > 0.f ? bf16_lo(gw[e]) : bf16_lo(gw[e]) * slope;
       const float hi = bf16_hi(fw[e]) > 0.f ? bf16_hi(gw[e]) : bf16_hi(gw[e]) * slope;
       gw[e] = pack_bf16(lo, hi);
+      acc[2 * e] += bf16_lo(gw[e]);      // sums of the values as stored (what the weight-gradient kernel will read)
+      acc[2 * e + 1] += bf16_hi(gw[e]);
     }
     *gp = make_uint4(gw[0], gw[1], gw[2], gw[3]);
+  }
+  if (partial != nullptr) {   // block-level sums without atomics: every thread parks its 8 sums, C threads fold them
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s_cs[threadIdx.x * 8 + e] = acc[e];
+    __syncthreads();
+    if (threadIdx.x < C) {
+      const int grp = threadIdx.x >> 3, e = threadIdx.x & 7;
+      const int base = int(((long long)blockIdx.x * blockDim.x) % groups);
+      int t0 = grp - base;             // first thread of this block whose channel group is grp
+      if (t0 < 0) t0 += groups;
+      float sum = 0.f;
+      for (int t = t0; t < int(blockDim.x); t += groups) sum += s_cs[t * 8 + e];
+      partial[size_t(blockIdx.x) * C + threadIdx.x] = sum;
+    }
   }
 }
 // y[:, :C] = alpha * a[:, :C] + (x ? x[:, :C] : 0)      (y may alias a or x)

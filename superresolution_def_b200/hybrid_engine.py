@@ -48,10 +48,13 @@ def _dgrad(epi, B, H, W, w, b, dy, dx, cin, cout, r=None, slope=SLOPE):
     capi.conv3x3_igemm_v(epi, B, H, W, _p64(cout), _p64(cin), cin, dy, wt, None, dx, r, slope=slope, alpha=1.0)
 
 
-def _wgrads(B, H, W, w, b, dy, x, cin, cout):
-    dw, db = torch.empty_like(w), torch.empty_like(b)
+def _wgrads(B, H, W, w, b, dy, x, cin, cout, db=None):
+    """Weight and bias gradient of one layer; db: already computed (fused into the LeakyReLU-mask pass) or None."""
+    dw = torch.empty_like(w)
     capi.conv3x3_wgrad_v(B, H, W, cin, cout, _p64(cin), _p64(cout), dy, x, dw)
-    capi.bias_grad_v(dy, B * H * W, db)
+    if db is None:
+        db = torch.empty_like(b)
+        capi.bias_grad_v(dy, B * H * W, db)
     return dw, db
 
 
@@ -78,8 +81,9 @@ def rdb_bwd(geom, nf, gc, cat, dcat, g5, p):
     _dgrad(capi.CEPI_BIAS_RES, B, H, W, p[8], p[9], V(g5), V(dcat, 0, cc), cc, nf, r=V(dcat, 0, nf))
     for k in (3, 2, 1, 0):
         s = nf + k * gc
-        capi.view_lrelu_mask(V(dcat, s, gc), V(cat, s, gc), T, SLOPE)                      # through LeakyReLU of conv_{k+1}
-        grads[2 * k], grads[2 * k + 1] = _wgrads(B, H, W, p[2 * k], p[2 * k + 1], V(dcat, s, gc), V(cat, 0, s), s, gc)
+        db = torch.empty_like(p[2 * k + 1])
+        capi.view_lrelu_mask(V(dcat, s, gc), V(cat, s, gc), T, SLOPE, colsum=db)           # through LeakyReLU of conv_{k+1}
+        grads[2 * k], grads[2 * k + 1] = _wgrads(B, H, W, p[2 * k], p[2 * k + 1], V(dcat, s, gc), V(cat, 0, s), s, gc, db=db)
         _dgrad(capi.CEPI_BIAS_RES, B, H, W, p[2 * k], p[2 * k + 1], V(dcat, s, gc), V(dcat, 0, s), s, gc, r=V(dcat, 0, s))
     return grads
 
@@ -242,8 +246,9 @@ class HybridTailFunction(torch.autograd.Function):
         rgrads = trunk_bwd((B, H, W), nf, gc, cats, rdb_params, True, G)
         capi.view_axpy(V(G), V(G), V(d_fsum), T, 1.0)
         # conv_adapt (1 -> nf) through its LeakyReLU
-        capi.view_lrelu_mask(V(G), V(cats[0], 0, nf), T, SLOPE)
-        dwa, dba = _wgrads(B, H, W, wa, ba, V(G), V(img8), 1, nf)
+        dba = torch.empty_like(ba)
+        capi.view_lrelu_mask(V(G), V(cats[0], 0, nf), T, SLOPE, colsum=dba)
+        dwa, dba = _wgrads(B, H, W, wa, ba, V(G), V(img8), 1, nf, db=dba)
         d_hat = None
         if ctx.needs_input_grad[0]:
             dimg8 = torch.empty(T, 8, device=dev, dtype=BF16)

@@ -304,9 +304,13 @@ extern "C" int srk_conv3x3_igemm_v(int epi, int B, int H, int W, int Cin_p, int 
   // two or three chunks per tile its two-stage halo ring exposes the TMA latency and the per-tap kernel is as fast or
   // faster, so those shapes stay on conv3x3_kernel.  SRK_CONV_HALO=3 forces it everywhere (tests), 0 disables it.
   const bool halo_shape = H % HALO_TH == 0 && W % HALO_TW == 0;
-  const bool halo = halo_shape && (hmode >= 2 || (hmode == 1 && Cin_p == 64 && Cout_p <= 128));
+  // thin layers (<= 32 real output channels, e.g. the 24-channel conv1..conv4 of a dense block): N = 32 instance with a
+  // three-stage halo ring and a whole tile of weights in flight
+  const bool thin = halo_shape && hmode != 0 && !out1 && (epi == CEPI_BIAS || epi == CEPI_BIAS_LRELU) && y->C <= 32 &&
+                    n_real <= 32 && Cout_p == 64;
+  const bool halo = halo_shape && (thin || hmode >= 2 || (hmode == 1 && Cin_p == 64 && Cout_p <= 128));
   const int cbw = halo ? HALO_TW : CONV_TW, cbh = halo ? HALO_TH : CONV_TH;
-  if ((rc = view_map(&maps.a[0], x, B, H, W, halo ? HALO_BW : CONV_TW, halo ? HALO_BH : CONV_TH))) return rc;
+  if ((rc = view_map(&maps.a[0], x, B, H, W, halo ? HALO_BW : CONV_TW, halo ? HALO_BH / 3 : CONV_TH))) return rc;
   if (out1) maps.c[0] = maps.a[0];
   else if ((rc = view_map(&maps.c[0], y, B, H, W, cbw, cbh))) return rc;
   for (int i = 1; i < 4; ++i) { maps.a[i] = maps.a[0]; maps.c[i] = maps.c[0]; }
@@ -318,15 +322,16 @@ extern "C" int srk_conv3x3_igemm_v(int epi, int B, int H, int W, int Cin_p, int 
     if ((rc = view_map(&maps.r, r, B, H, W, cbw, cbh))) return rc;
   }
   if (epi == CEPI_BIAS_GELU) return fail(SRK_ERR_UNSUPPORTED, "conv3x3_v: GELU epilogue is served by srk_conv3x3_igemm");
-  const int bn = Cout_p;
+  const int bn = thin ? 32 : Cout_p;
   if ((rc = make_tmap_2d(&maps.w, wk, Cout_p, 9 * (uint64_t)Cin_p, 9 * (uint64_t)Cin_p, bn))) return rc;
   ConvArgs a{};
-  a.B = B; a.H = H; a.W = W; a.Cin_p = Cin_p; a.Cout_p = Cout_p; a.n_real = n_real; a.bias = bias; a.slope = slope;
+  a.B = B; a.H = H; a.W = W; a.Cin_p = Cin_p; a.Cout_p = thin ? 32 : Cout_p; a.n_real = n_real; a.bias = bias; a.slope = slope;
   a.a_split = 0; a.c_split = 0; a.alpha = alpha;
   a.y32 = out1 ? y32 : nullptr;
   if (halo) {
     a.a_split = (hmode == 2);  // probe switch: 2 = descriptors WITH the matrix base offset kx (documented as wrong on B200)
 #define SRK_HCASE(BN_, EPI_) if (bn == BN_ && epi == EPI_) return launch_conv_halo<BN_, EPI_>(maps, a, stream);
+    SRK_HCASE(32, CEPI_BIAS) SRK_HCASE(32, CEPI_BIAS_LRELU)
     SRK_HCASE(64, CEPI_BIAS) SRK_HCASE(128, CEPI_BIAS) SRK_HCASE(192, CEPI_BIAS) SRK_HCASE(256, CEPI_BIAS)
     SRK_HCASE(64, CEPI_BIAS_LRELU) SRK_HCASE(192, CEPI_BIAS_LRELU)
     SRK_HCASE(64, CEPI_BIAS_RES) SRK_HCASE(128, CEPI_BIAS_RES) SRK_HCASE(192, CEPI_BIAS_RES) SRK_HCASE(256, CEPI_BIAS_RES)

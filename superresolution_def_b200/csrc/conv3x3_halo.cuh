@@ -21,21 +21,24 @@ namespace srk {
 constexpr int HALO_TW = 8, HALO_TH = 16;     // output tile
 constexpr int HALO_BW = 16, HALO_BH = 18;    // input box (pixels), incl. border and the pad columns that keep SBO uniform
 constexpr int HALO_A_BYTES = HALO_BW * HALO_BH * 128;
-constexpr int HALO_A_STAGES = 2;
 
 template <int BN, int EPI>
 struct HaloCfg {
   static constexpr int kWBytes = BN * 128;
-  static constexpr int kBoxes = BN / 64;
+  static constexpr int kBoxes = (BN == 16) ? 0 : (BN + 63) / 64;   // BN = 32: half a box (the store is clipped by the view)
   static constexpr bool kAux = (EPI == CEPI_BIAS_RES || EPI == CEPI_MASK_LRELU || EPI == CEPI_MUL);
+  // halo ring depth: three tiles in flight where shared memory allows (thin layers: the TMA latency of a 36 KB box is
+  // what the two-stage ring exposed), two otherwise
+  static constexpr int kAStages = (BN <= 64 && !kAux) ? 3 : 2;
   static constexpr int kOutPerBox = 1;
   static constexpr int kEpiBytes = (kAux ? 2 * BOX_BYTES : 0) + 2 * BOX_BYTES;
   static constexpr int kBudget = 232448 - 1024 - 1024 - 1280;
-  static constexpr int kWRaw = (kBudget - kEpiBytes - HALO_A_STAGES * HALO_A_BYTES) / kWBytes;
-  static constexpr int kWStages = kWRaw > 9 ? 9 : kWRaw;
-  static constexpr int kSmemBytes = HALO_A_STAGES * HALO_A_BYTES + kWStages * kWBytes + kEpiBytes + 1024 + 1024;
+  static constexpr int kWRaw = (kBudget - kEpiBytes - kAStages * HALO_A_BYTES) / kWBytes;
+  static constexpr int kWCap = (BN <= 32) ? 18 : 9;
+  static constexpr int kWStages = kWRaw > kWCap ? kWCap : kWRaw;
+  static constexpr int kSmemBytes = kAStages * HALO_A_BYTES + kWStages * kWBytes + kEpiBytes + 1024 + 1024;
   static_assert(kWStages >= 2, "weight ring needs two stages");
-  static_assert(BN % 64 == 0 || BN == 16, "BN: multiple of 64, or 16 for the single-channel variant");
+  static_assert(BN % 64 == 0 || BN == 16 || BN == 32, "BN: multiple of 64, 32 (thin layers) or 16 (single channel)");
   static_assert(EPI != CEPI_BIAS_GELU, "the GELU epilogue (two outputs) stays on conv3x3_kernel");
 };
 
@@ -48,7 +51,7 @@ template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 conv3x3_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
   using Cfg = HaloCfg<BN, EPI>;
-  constexpr int SW = Cfg::kWStages, SA = HALO_A_STAGES;
+  constexpr int SW = Cfg::kWStages, SA = Cfg::kAStages;
   constexpr int S = SA + SW;  // barrier slots: [0, SA) halo ring, [SA, S) weight ring
   constexpr int NBOX = Cfg::kBoxes;
   extern __shared__ uint8_t smem_raw[];
@@ -70,7 +73,9 @@ conv3x3_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) 
   const int m_tiles = args.B * tiles_y * tiles_x;
   const int num_tiles = m_tiles * n_tiles;
   const int kc_per_tap = args.Cin_p / 64;
-  const int k_iters = 9 * kc_per_tap;
+  // All nine taps of every 64-channel chunk fit the weight ring and there is one N tile: load the weights once per CTA
+  // and keep them (the ring slots are never released), instead of re-fetching them from L2 for every spatial tile.
+  const bool w_resident = (9 * kc_per_tap <= SW) && (n_tiles == 1);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -108,8 +113,13 @@ conv3x3_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) 
         for (int kc = 0; kc < kc_per_tap; ++kc) {
           mbar_wait(empty_bar(as), aph ^ 1u);
           mbar_arrive_expect_tx(full_bar(as), HALO_A_BYTES);
-          tma_load_4d(smem_base + as * HALO_A_BYTES, &maps.a[0], full_bar(as), kc * 64, x0 - 1, y0 - 1, b);
+          // three boxes of 6 image rows each (same bytes; smaller boxes pipeline better through the TMA unit)
+#pragma unroll
+          for (int part = 0; part < 3; ++part)
+            tma_load_4d(smem_base + as * HALO_A_BYTES + part * (6 * HALO_BW * 128), &maps.a[0], full_bar(as), kc * 64, x0 - 1,
+                        y0 - 1 + part * 6, b);
           if (++as == SA) { as = 0; aph ^= 1u; }
+          if (w_resident && tile != int(blockIdx.x)) continue;   // weights already sit in shared memory
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(empty_bar(SA + ws), wph ^ 1u);
             mbar_arrive_expect_tx(full_bar(SA + ws), Cfg::kWBytes);
@@ -134,7 +144,8 @@ conv3x3_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) 
           const uint32_t sa = smem_base + as * HALO_A_BYTES;
           for (int tap = 0; tap < 9; ++tap) {
             const int ky = tap / 3, kx = tap - ky * 3;
-            mbar_wait(full_bar(SA + ws), wph);
+            if (w_resident) ws = kc * 9 + tap;            // slot of this (chunk, tap); its first phase stays complete
+            mbar_wait(full_bar(SA + ws), w_resident ? 0u : wph);
             tc_fence_after();
             const uint32_t a0 = sa + uint32_t(ky * HALO_BW + kx) * 128u;
             const uint32_t sb = w_base + ws * Cfg::kWBytes;
@@ -143,8 +154,10 @@ conv3x3_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) 
             for (int k = 0; k < 4; ++k)
               umma_bf16(d_tmem, make_smem_desc_bo(a0 + k * 32, 16, HALO_BW * 128, bo), make_smem_desc(sb + k * 32, 16, 1024),
                         idesc, (kc | tap | k) != 0 ? 1u : 0u);
-            umma_commit(empty_bar(SA + ws));
-            if (++ws == SW) { ws = 0; wph ^= 1u; }
+            if (!w_resident) {
+              umma_commit(empty_bar(SA + ws));
+              if (++ws == SW) { ws = 0; wph ^= 1u; }
+            }
           }
           umma_commit(empty_bar(as));
           if (++as == SA) { as = 0; aph ^= 1u; }
@@ -221,14 +234,18 @@ conv3x3_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) 
           mbar_wait(aux_bar(ab), (aux_count >> 1) & 1u);
           aux_addr = epi_base + kAuxOff + ab * BOX_BYTES;
         }
+        const bool active = (BN >= 64) || (half == 0);   // BN = 32: the accumulator has one 32-column half only
         uint32_t r[32];
-        tmem_ld_x32(taddr + uint32_t(j * 64 + half * 32), r);
-        tmem_ld_wait();
+        if (active) {
+          tmem_ld_x32(taddr + uint32_t(j * 64 + half * 32), r);
+          tmem_ld_wait();
+        }
         if (j == NBOX - 1) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(acc));
         }
+        if (active)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int ch = half * 4 + i;

@@ -329,6 +329,7 @@ extern "C" int srk_conv3x3_igemm_v(int epi, int B, int H, int W, int Cin_p, int 
   a.a_split = 0; a.c_split = 0; a.alpha = alpha;
   a.y32 = out1 ? y32 : nullptr;
   if (halo) {
+    a.c_split = (hmode == 4);  // timing probe: skip halo loads after the first tile (results are garbage)
     a.a_split = (hmode == 2);  // probe switch: 2 = descriptors WITH the matrix base offset kx (documented as wrong on B200)
 #define SRK_HCASE(BN_, EPI_) if (bn == BN_ && epi == EPI_) return launch_conv_halo<BN_, EPI_>(maps, a, stream);
     SRK_HCASE(32, CEPI_BIAS) SRK_HCASE(32, CEPI_BIAS_LRELU)

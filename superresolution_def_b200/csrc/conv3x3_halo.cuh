@@ -112,12 +112,16 @@ conv3x3_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) 
         tile_coords(tile, b, y0, x0, n0);
         for (int kc = 0; kc < kc_per_tap; ++kc) {
           mbar_wait(empty_bar(as), aph ^ 1u);
-          mbar_arrive_expect_tx(full_bar(as), HALO_A_BYTES);
-          // three boxes of 6 image rows each (same bytes; smaller boxes pipeline better through the TMA unit)
+          if (args.c_split && tile != int(blockIdx.x)) {
+            mbar_arrive(full_bar(as));   // timing probe (SRK_CONV_HALO=4): no halo loads after the first tile, stale data
+          } else {
+            mbar_arrive_expect_tx(full_bar(as), HALO_A_BYTES);
+            // three boxes of 6 image rows each (same bytes as one 18-row box; no measurable difference on B200)
 #pragma unroll
-          for (int part = 0; part < 3; ++part)
-            tma_load_4d(smem_base + as * HALO_A_BYTES + part * (6 * HALO_BW * 128), &maps.a[0], full_bar(as), kc * 64, x0 - 1,
-                        y0 - 1 + part * 6, b);
+            for (int part = 0; part < 3; ++part)
+              tma_load_4d(smem_base + as * HALO_A_BYTES + part * (6 * HALO_BW * 128), &maps.a[0], full_bar(as), kc * 64,
+                          x0 - 1, y0 - 1 + part * 6, b);
+          }
           if (++as == SA) { as = 0; aph ^= 1u; }
           if (w_resident && tile != int(blockIdx.x)) continue;   // weights already sit in shared memory
           for (int tap = 0; tap < 9; ++tap) {

@@ -15,6 +15,9 @@ def pytest_configure(config):
 
 def pytest_collection_modifyitems(config, items):
     import torch
+    # the oracle must be true fp32 when it is evaluated on the GPU: no TF32 in cuDNN convolutions / cuBLAS matmuls
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     if torch.cuda.is_available():
         return
     skip = pytest.mark.skip(reason="no CUDA device")

@@ -204,13 +204,24 @@ def roofline_probe(batch: int, peaks):
     top = max(by_fn.items(), key=lambda kv: kv[1]["ms"])
     ach = top[1]["bytes"] / (top[1]["ms"] * 1e-3) / 1e9
     total_ms = sum(d["ms"] for d in by_fn.values())
+    # measured DRAM traffic of that kernel (ncu --set full, one capture per round under profiles/); reported next to
+    # the algorithmic bytes so that wasted re-reads would show
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f).get(top[0])
+        if t and batch == 16:
+            traffic = t["traffic"]
+    except Exception:
+        traffic = None
     roof = {"kernel": top[0] + " (tcgen05 weight-gradient GEMM, MN-major operands)" if "wgrad" in top[0] else top[0],
             "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-            "traffic": None, "peak_kind": kind, "ms_per_launch": top[1]["ms"] / top[1]["launches"],
+            "traffic": traffic, "peak_kind": kind, "ms_per_launch": top[1]["ms"] / top[1]["launches"],
             "algorithmic_bytes": top[1]["bytes"] / top[1]["launches"], "launches_per_step": top[1]["launches"],
             "share_of_block_kernels": top[1]["ms"] / total_ms,
             "note": "dominant kernel function by launches x duration among the per-block kernels, each timed alone at the "
-                    "step's shapes; traffic (ncu dram bytes) is recorded in profiles/"}
+                    "step's shapes; achieved/algorithmic_bytes are averages over that function's launch shapes; traffic = "
+                    "ncu dram read+write bytes of its largest launch shape (profiles/r01_traffic.json)"}
     return roof, rows
 
 

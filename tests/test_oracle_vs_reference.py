@@ -126,3 +126,28 @@ def test_hab_drop_path_matches_reference_rng_order():
     assert rel_l2(y2, y) < 1e-5 and rel_l2(x2.grad, x.grad) < 1e-4
     for n, p in blk.named_parameters():
         assert rel_l2(sd[n].grad, p.grad) < 2e-4, n
+
+
+def test_hybrid_module_schema_and_oracle_match_reference():
+    """HybridHATRealESRGAN at the script's configuration (train_hat.py:132-136, fewer blocks): the product mirror has the
+    reference's state_dict / parameter order, and the oracle reproduces the reference's forward at C=90, window 8,
+    OCAB 12x12, nf 48 / gc 24."""
+    from tools import ref_shim
+    from oracle import hat_oracle as ho
+    h = ref_shim.hybrid_module()
+    from superresolution_def_b200.hybridmodels_hat import HybridHATRealESRGAN
+    kw = dict(img_size=16, in_chans=1, embed_dim=90, depths=(2,), num_heads=(6,), window_size=8, upscale=4, num_rrdb=1,
+              num_feat=48, num_grow_ch=24)
+    torch.manual_seed(0)
+    ref, mine = h.HybridHATRealESRGAN(**kw), HybridHATRealESRGAN(**kw)
+    a, b = ref.state_dict(), mine.state_dict()
+    assert list(a.keys()) == list(b.keys())
+    assert all(a[k].shape == b[k].shape and a[k].dtype == b[k].dtype for k in a)
+    assert [n for n, _ in ref.named_parameters()] == [n for n, _ in mine.named_parameters()]
+    mine.load_state_dict(a, strict=True)
+    randomize_(ref, seed=3, table_std=0.5).eval()
+    x = torch.rand(1, 1, 16, 16)
+    with torch.no_grad():
+        want = ref(x)
+        got = ho.hybrid_forward(x, ref.state_dict(), window_size=8, depths=(2,), num_heads=(6,), num_rrdb=1)
+    assert rel_l2(got, want) < 2e-5, rel_l2(got, want)

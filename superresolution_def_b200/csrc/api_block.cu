@@ -87,7 +87,7 @@ int launch_attn_fwd(const SrkGeom* g, int heads, const void* qkv, int ld_qkv, co
   a.ld_qkv = ld_qkv; a.ld_o = ld_o; a.ones_col = ones_col;
   const int nwin = g->B * (g->H / 8) * (g->W / 8);
   dim3 grid(attn_fwd_gx(nwin, heads), heads);
-  win_attn_ws8_fwd_kernel<<<grid, ATT_THREADS, 0, stream>>>(a);
+  SRK_CUDA_OK(launch_pdl(win_attn_ws8_fwd_kernel, grid, dim3(ATT_THREADS), 0, stream, a));
   SRK_LAUNCHED(1);
   SRK_CUDA_OK(cudaGetLastError());
   return SRK_OK;
@@ -111,7 +111,7 @@ int launch_attn_bwd(const SrkGeom* g, int heads, const void* qkv, int ld_qkv, co
   a.B = g->B; a.H = g->H; a.W = g->W; a.heads = heads; a.shift = g->shift;
   a.ld_qkv = ld_qkv; a.ld_o = ld_o; a.ones_col = -1;
   dim3 grid(gx, heads);
-  win_attn_ws8_bwd_kernel<<<grid, ATT_THREADS, sizeof(AttnBwdSmem), stream>>>(a);
+  SRK_CUDA_OK(launch_pdl(win_attn_ws8_bwd_kernel, grid, dim3(ATT_THREADS), sizeof(AttnBwdSmem), stream, a));
   SRK_LAUNCHED(1);
   SRK_CUDA_OK(cudaGetLastError());
   return SRK_OK;
@@ -319,7 +319,7 @@ extern "C" int srk_block_prep_weights(const SrkBlockDims* d, const SrkBlockParam
                      static_cast<__nv_bfloat16*>(w->proj_f), static_cast<__nv_bfloat16*>(w->proj_t),
                      static_cast<__nv_bfloat16*>(w->fc1_f),  static_cast<__nv_bfloat16*>(w->fc1_t),
                      static_cast<__nv_bfloat16*>(w->fc2_f),  static_cast<__nv_bfloat16*>(w->fc2_t)};
-  prep_block_weights_kernel<<<296, 256, 0, stream>>>(to_dims(d), pp, ww);
+  SRK_CUDA_OK(launch_pdl(prep_block_weights_kernel, dim3(296), dim3(256), 0, stream, to_dims(d), pp, ww));
   SRK_LAUNCHED(1);
   SRK_CUDA_OK(cudaGetLastError());
   return SRK_OK;
@@ -459,7 +459,8 @@ static int block_bwd_impl(const SrkBlockDims* d, const SrkGeom* g, const SrkBloc
   BlockGradPtrs gp{grads->norm1_w, grads->norm1_b, grads->rpb_table, grads->qkv_w, grads->qkv_b, grads->proj_w,
                    grads->proj_b,  grads->norm2_w, grads->norm2_b,   grads->fc1_w, grads->fc1_b, grads->fc2_w,
                    grads->fc2_b};
-  unpack_block_grads_kernel<<<296, 256, 0, stream>>>(to_dims(d), us, gp, accumulate ? 1.f : 0.f);
+  SRK_CUDA_OK(launch_pdl(unpack_block_grads_kernel, dim3(296), dim3(256), 0, stream, to_dims(d), us, gp,
+                         accumulate ? 1.f : 0.f));
   SRK_LAUNCHED(1);
   SRK_CUDA_OK(cudaGetLastError());
   return SRK_OK;

@@ -20,7 +20,8 @@ static int launch_gemm_tn(const GemmArgs& a, const CUtensorMap& tA, const CUtens
   }
   const int tiles = (a.M / GEMM_BM) * (a.N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tn_kernel<BN, EPI><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(tA, tB, tC, tC2, tX1, tX2, a);
+  SRK_CUDA_OK(launch_pdl(gemm_tn_kernel<BN, EPI>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, stream, tA, tB, tC, tC2,
+                         tX1, tX2, a));
   SRK_LAUNCHED(1);
   SRK_CUDA_OK(cudaGetLastError());
   return SRK_OK;
@@ -121,7 +122,8 @@ static int launch_wgrad(const WgradArgs& a, const CUtensorMap& tA, const CUtenso
                                      Cfg::kSmemBytes));
     configured = true;
   }
-  gemm_wgrad_kernel<BNW><<<a.ca_tiles * a.splits, WG_THREADS, Cfg::kSmemBytes, stream>>>(tA, tB, a);
+  SRK_CUDA_OK(launch_pdl(gemm_wgrad_kernel<BNW>, dim3(a.ca_tiles * a.splits), dim3(WG_THREADS), Cfg::kSmemBytes, stream, tA,
+                         tB, a));
   SRK_LAUNCHED(1);
   SRK_CUDA_OK(cudaGetLastError());
   return SRK_OK;
@@ -150,7 +152,7 @@ extern "C" int srk_gemm_wgrad_dbg(int T, int Ca, int Cb, const void* A, int lda,
   }
   if (rc) return rc;
   const int n = a.ca_tiles * 128 * Cb;
-  wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, stream>>>(workspace, out, splits, n);
+  SRK_CUDA_OK(launch_pdl(wgrad_reduce_kernel, dim3((n + 255) / 256), dim3(256), 0, stream, workspace, out, splits, n));
   SRK_LAUNCHED(1);
   SRK_CUDA_OK(cudaGetLastError());
   return SRK_OK;

@@ -240,6 +240,8 @@ __global__ void __launch_bounds__(ATT_THREADS) win_attn_ws8_fwd_kernel(const Att
   __shared__ __align__(128) uint8_t s_in[2][3 * ATT_TILE];
   __shared__ __align__(128) uint8_t s_out[ATT_TILE];
   __shared__ float s_bias[225];
+  pdl_launch_dependents();
+  pdl_wait();
   const int h = blockIdx.y;
   const int nwin = a.B * (a.H >> 3) * (a.W >> 3);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -339,6 +341,8 @@ __device__ __forceinline__ void tileT_times_tile(uint32_t a_tile, uint32_t b_til
 __global__ void __launch_bounds__(ATT_THREADS, 4) win_attn_ws8_bwd_kernel(const AttnArgs a) {
   extern __shared__ __align__(128) uint8_t smem_dyn[];
   AttnBwdSmem& sm = *reinterpret_cast<AttnBwdSmem*>(smem_dyn);
+  pdl_launch_dependents();
+  pdl_wait();
   const int h = blockIdx.y;
   const int nwin = a.B * (a.H >> 3) * (a.W >> 3);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

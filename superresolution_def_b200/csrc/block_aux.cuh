@@ -48,6 +48,8 @@ struct BlockWeightPtrs {  // prepared bf16 operands
 
 // ------------------------------------------------------------------ weight preparation
 static __global__ void prep_block_weights_kernel(BlockDims d, BlockParamPtrs p, BlockWeightPtrs w) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int QW = 3 * d.heads * d.ds, AW = d.heads * d.ds;
   const int n0 = QW * d.Cp, n1 = d.Cp * AW, n2 = d.Hp * d.Cp, n3 = d.Cp * d.Hp;
   const int total = n0 + n1 + n2 + n3;
@@ -110,6 +112,8 @@ struct UnpackSrc {
 };
 
 static __global__ void unpack_block_grads_kernel(BlockDims d, UnpackSrc s, BlockGradPtrs g, float accumulate) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int C = d.C, AW = d.heads * d.ds;
   const int n_qkv_w = 3 * C * C, n_qkv_b = 3 * C, n_proj_w = C * C, n_proj_b = C;
   const int n_fc1_w = d.hidden * C, n_fc1_b = d.hidden, n_fc2_w = C * d.hidden, n_fc2_b = C;

@@ -162,10 +162,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     fence_mbar_init();
   }
+  pdl_launch_dependents();
   if (warp == 1) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
+  pdl_wait();  // everything above overlaps the previous kernel's tail; nothing below may run before it has finished
   if constexpr (EPI == EPI_RES_LN || EPI == EPI_LNBWD) {
     for (int i = threadIdx.x; i < 256; i += Cfg::kThreads) {
       s_gamma[i] = (i < args.n_real) ? args.gamma[i] : 0.f;

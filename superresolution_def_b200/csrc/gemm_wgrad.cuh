@@ -68,10 +68,12 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     mbar_init(tfull_bar, 1);
     fence_mbar_init();
   }
+  pdl_launch_dependents();
   if (warp == 1) {
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
+  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -145,6 +147,8 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // Sum the per-split partials: out[r][c] = sum_s partials[s][r][c]   (rows = ca_tiles*128, cols = Cb)
 static __global__ void wgrad_reduce_kernel(const float* __restrict__ partials, float* __restrict__ out,
                                     int splits, int n_elems) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_elems) return;
   float s = 0.f;

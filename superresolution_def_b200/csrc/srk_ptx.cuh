@@ -227,6 +227,15 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
          | (uint32_t(M >> 4) << 24);        // m_dim
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the
+// stream is still draining: pdl_launch_dependents() (called by every CTA as early as possible) lets the NEXT grid's CTAs
+// take the SMs this grid's CTAs free up, and pdl_wait() blocks until the PREVIOUS grid has completed and its writes are
+// visible.  Everything before pdl_wait() (barrier init, TMEM allocation, descriptor prefetch) overlaps the predecessor's
+// tail.  Both are no-ops in a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- 128-bit shared-memory access
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;

@@ -1,6 +1,6 @@
 // api_conv.cu — C-ABI entry points for the convolutional paths (implicit-GEMM conv3x3 fwd/dgrad/wgrad with
 // fused bias / LeakyReLU / residual / PixelShuffle / GELU epilogues, and the 1-channel head/tail convolutions).
-#include "conv3x3_halo.cuh"
+#include "conv3x3_swap.cuh"
 #include <cstdlib>
 #include "conv_aux.cuh"
 #include "srk_host.h"
@@ -53,6 +53,22 @@ int launch_conv_halo(const ConvMaps& maps, const ConvArgs& a, cudaStream_t strea
   const int tiles = a.B * (a.H / HALO_TH) * (a.W / HALO_TW) * (a.Cout_p / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   conv3x3_halo_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(maps, a);
+  SRK_LAUNCHED(1);
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+template <int EPI>
+int launch_conv_swap(const ConvMaps& maps, const ConvArgs& a, cudaStream_t stream) {
+  using Cfg = SwapCfg<EPI>;
+  static bool configured = false;
+  if (!configured) {
+    SRK_CUDA_OK(cudaFuncSetAttribute(conv3x3_swap_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int tiles = a.B * (a.H / SWP_TH) * (a.W / SWP_TW) * ((a.n_real + 127) / 128);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  conv3x3_swap_kernel<EPI><<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(maps, a);
   SRK_LAUNCHED(1);
   SRK_CUDA_OK(cudaGetLastError());
   return SRK_OK;
@@ -299,6 +315,35 @@ extern "C" int srk_conv3x3_igemm_v(int epi, int B, int H, int W, int Cin_p, int 
   memset(&maps, 0, sizeof(maps));
   int rc;
   const int hmode = conv_halo_mode();
+  // Few output channels (<= 128): role-swapped kernel — weights as the M = 128 operand, 256 pixels as N (conv3x3_swap.cuh)
+  // Measured (hybrid step, B200): it wins where the tensor unit is the limit — plain epilogues (105 vs 140-160 us per
+  // dense-block conv) and aux epilogues with <= 64 output channels over >= 2 input chunks (conv5); the 24 -> 72..144
+  // input-gradient layers (one chunk, two channel boxes per pixel group, aux loads) are bound by its transposing
+  // epilogue instead and stay on the halo / per-tap kernels.  SRK_CONV_HALO=6 forces it for every eligible layer (tests).
+  const bool swap_aux = (epi == CEPI_BIAS_RES || epi == CEPI_MASK_LRELU);
+  const bool swap_ok = !out1 && n_real <= 128 && n_real > 0 && H % SWP_TH == 0 && W % SWP_TW == 0 &&
+                       (epi == CEPI_BIAS || epi == CEPI_BIAS_LRELU || swap_aux);
+  const bool swap_pick = !swap_aux || (n_real <= 64 && Cin_p >= 128);
+  if (hmode != 0 && hmode != 5 && swap_ok && (swap_pick || hmode == 6)) {
+    const bool need_aux = swap_aux;
+    if (need_aux && !r) return fail(SRK_ERR_ARG, "conv3x3_v: epilogue needs an aux view");
+    if ((rc = view_map(&maps.a[0], x, B, H, W, SWP_BW, SWP_BH))) return rc;
+    if ((rc = view_map(&maps.c[0], y, B, H, W, 8, 8))) return rc;
+    for (int i = 1; i < 4; ++i) { maps.a[i] = maps.a[0]; maps.c[i] = maps.c[0]; }
+    maps.c2 = maps.c[0];
+    maps.r = maps.c[0];
+    if (need_aux && (rc = view_map(&maps.r, r, B, H, W, 8, 8))) return rc;
+    if ((rc = make_tmap_2d(&maps.w, wk, Cout_p, 9 * (uint64_t)Cin_p, 9 * (uint64_t)Cin_p, 128))) return rc;
+    ConvArgs a{};
+    a.B = B; a.H = H; a.W = W; a.Cin_p = Cin_p; a.Cout_p = Cout_p; a.n_real = n_real; a.bias = bias; a.slope = slope;
+    a.alpha = alpha;
+    switch (epi) {
+      case CEPI_BIAS: return launch_conv_swap<CEPI_BIAS>(maps, a, stream);
+      case CEPI_BIAS_LRELU: return launch_conv_swap<CEPI_BIAS_LRELU>(maps, a, stream);
+      case CEPI_BIAS_RES: return launch_conv_swap<CEPI_BIAS_RES>(maps, a, stream);
+      default: return launch_conv_swap<CEPI_MASK_LRELU>(maps, a, stream);
+    }
+  }
   // Measured on B200 (hybrid step, tools/gpu_probe_hybrid_prof.py): the halo-resident kernel wins where one 64-channel
   // chunk feeds all nine taps and the weight ring stays deep (Cin_p == 64, BN <= 128: 151 -> 100 us, 189 -> 166 us); with
   // two or three chunks per tile its two-stage halo ring exposes the TMA latency and the per-tap kernel is as fast or

@@ -54,10 +54,11 @@ def test_rdb_matches_oracle(nf, gc):
     _cmp_module(blk, lambda t, sd: ho.rdb(t, sd, ""), x)
 
 
-@pytest.mark.parametrize("mode", ["1", "3"])
+@pytest.mark.parametrize("mode", ["1", "3", "5", "6"])
 def test_rdb_halo_conv_matches_oracle(mode):
-    """Same block at a shape the halo-resident conv kernel takes (H % 16 == 0): mode 1 = production heuristic (halo for
-    single-chunk layers), mode 3 = halo for every layer.  Run in a subprocess: the mode is read once per process."""
+    """Same block at a shape the halo-resident and role-swapped conv kernels take (H % 32 == 0): SRK_CONV_HALO = 1
+    production heuristic, 3 = halo-resident kernel for every layer the swapped kernel does not take, 5 = no role-swapped
+    kernel, 6 = role-swapped kernel for every eligible layer.  Run in a subprocess: the mode is read once per process."""
     import os, subprocess, sys
     code = ("import torch; from tests.test_hybrid_gpu import _cmp_module, _ho; from tests.util import randomize_;"
             "from superresolution_def_b200.hybridmodels_hat import ResidualDenseBlock; ho = _ho(); torch.manual_seed(1);"

@@ -170,7 +170,7 @@ extern "C" int srk_conv3x3_igemm(int epi, int B, int H, int W, int Cin_p, int Co
 
 extern "C" long long srk_conv3x3_wgrad_ws_floats(int Cin_p, int Cout_p) {
   const long long a = (long long)num_sms() * 128 * Cin_p + 16;   // co_tiles*9*splits <= num_sms tiles of [128 x Cin_p]
-  const long long b = (long long)num_sms() * 128 * 9 * WT_NCO;   // thin variant: ci_tiles*splits <= num_sms tiles of [128 x 9 x 32]
+  const long long b = (long long)num_sms() * 128 * 9 * WT_NCO_MAX;   // thin variant: ci_tiles*splits <= num_sms tiles of [128 x 9 x NCO]
   return a > b ? a : b;
 }
 
@@ -402,15 +402,17 @@ extern "C" int srk_conv3x3_wgrad_v(int B, int H, int W, int Cin, int Cout, int C
   if (H % 4 || W % 16 || Cin_p % 64 || Cout_p % 64 || Cin_p > 256) return fail(SRK_ERR_UNSUPPORTED, "conv wgrad: shape");
   if (!dy || !x || dy->C > Cout_p || x->C > Cin_p || Cout > Cout_p || Cin > Cin_p) return fail(SRK_ERR_ARG, "conv wgrad_v: views");
   int rc;
-  if (conv_halo_mode() != 0 && Cout <= WT_NCO && dy->C <= 64) {
+  if (conv_halo_mode() != 0 && Cout <= WT_NCO_MAX && dy->C <= 64) {
     // few output channels: one CTA per pixel range computes all nine taps from one halo load (conv3x3_wgrad_thin_kernel)
     ConvWgradThinMaps tm;
     memset(&tm, 0, sizeof(tm));
     if ((rc = view_map(&tm.dy, dy, B, H, W, 16, 4))) return rc;
     if ((rc = view_map(&tm.x, x, B, H, W, 18, 6))) return rc;
+    const int nco = Cout <= 32 ? 32 : 48;
     static bool configured = false;
     if (!configured) {
-      SRK_CUDA_OK(cudaFuncSetAttribute(conv3x3_wgrad_thin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM));
+      SRK_CUDA_OK(cudaFuncSetAttribute(conv3x3_wgrad_thin_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM));
+      SRK_CUDA_OK(cudaFuncSetAttribute(conv3x3_wgrad_thin_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM));
       configured = true;
     }
     ConvWgradThinArgs t{};
@@ -420,11 +422,12 @@ extern "C" int srk_conv3x3_wgrad_v(int B, int H, int W, int Cin, int Cout, int C
     if (t.splits > iters) t.splits = iters;
     if (t.splits < 1) t.splits = 1;
     t.partials = ws;
-    conv3x3_wgrad_thin_kernel<<<t.ci_tiles * t.splits, WG_THREADS, WT_SMEM, stream>>>(tm, t);
+    if (nco == 32) conv3x3_wgrad_thin_kernel<32><<<t.ci_tiles * t.splits, WG_THREADS, WT_SMEM, stream>>>(tm, t);
+    else conv3x3_wgrad_thin_kernel<48><<<t.ci_tiles * t.splits, WG_THREADS, WT_SMEM, stream>>>(tm, t);
     SRK_LAUNCHED(1);
     SRK_CUDA_OK(cudaGetLastError());
-    const int total = t.ci_tiles * 128 * 9 * WT_NCO;
-    conv_unpack_wgrad_thin_kernel<<<(total + 255) / 256, 256, 0, stream>>>(ws, t.splits, t.ci_tiles, dw, Cout, Cin);
+    const int total = t.ci_tiles * 128 * 9 * nco;
+    conv_unpack_wgrad_thin_kernel<<<(total + 255) / 256, 256, 0, stream>>>(ws, t.splits, t.ci_tiles, nco, dw, Cout, Cin);
     SRK_LAUNCHED(1);
     SRK_CUDA_OK(cudaGetLastError());
     return SRK_OK;

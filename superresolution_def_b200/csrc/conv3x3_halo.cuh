@@ -325,17 +325,18 @@ constexpr int WT_DYBOX = 16 * 4 * 128;
 constexpr int WT_STAGE = 2 * WT_XBOX + WT_DYBOX;    // 36864
 constexpr int WT_STAGES = 5;
 constexpr int WT_SMEM = WT_STAGES * WT_STAGE + 256 + 1024;
-constexpr int WT_NCO = 32;
+constexpr int WT_NCO_MAX = 48;   // instances: N = 32 (conv1..conv4, 24 or 32 channels) and N = 48 (conv5 at num_feat 48)
 
 struct ConvWgradThinArgs {
   int B, H, W, ci_tiles, splits;
-  float* partials;  // [splits][ci_tiles][128][9][32]
+  float* partials;  // [splits][ci_tiles][128][9][NCO]
 };
 struct ConvWgradThinMaps {
   CUtensorMap dy;  // box (64, 16, 4, 1)
   CUtensorMap x;   // box (64, 18, 6, 1)
 };
 
+template <int NCO>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 conv3x3_wgrad_thin_kernel(const __grid_constant__ ConvWgradThinMaps maps, const ConvWgradThinArgs args) {
   constexpr int S = WT_STAGES;
@@ -385,7 +386,7 @@ conv3x3_wgrad_thin_kernel(const __grid_constant__ ConvWgradThinMaps maps, const 
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, WT_NCO, 1, 1);
+      constexpr uint32_t idesc = make_idesc_bf16(128, NCO, 1, 1);
       int stage = 0; uint32_t phase = 0;
       for (int kb = 0; kb < k_iters; ++kb) {
         mbar_wait(full_bar(stage), phase);
@@ -397,7 +398,7 @@ conv3x3_wgrad_thin_kernel(const __grid_constant__ ConvWgradThinMaps maps, const 
           const int ky = tap / 3, kx = tap - ky * 3;
 #pragma unroll
           for (int y = 0; y < 4; ++y)
-            umma_bf16(tmem_base + uint32_t(tap * WT_NCO),
+            umma_bf16(tmem_base + uint32_t(tap * NCO),
                       make_smem_desc(sx + uint32_t((y + ky) * 18 + kx) * 128u, WT_XBOX, 1024),
                       make_smem_desc(sdy + uint32_t(y) * 2048u, WT_DYBOX, 1024), idesc, (kb | y) != 0 ? 1u : 0u);
         }
@@ -411,15 +412,23 @@ conv3x3_wgrad_thin_kernel(const __grid_constant__ ConvWgradThinMaps maps, const 
     mbar_wait(tfull_bar, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16);
-    float* out = args.partials + ((size_t(split) * args.ci_tiles + ci_tile) * 128 + row) * (9 * WT_NCO);
+    float* out = args.partials + ((size_t(split) * args.ci_tiles + ci_tile) * 128 + row) * (9 * NCO);
 #pragma unroll 1
     for (int tap = 0; tap < 9; ++tap) {
       uint32_t r[32];
-      tmem_ld_x32(taddr + uint32_t(tap * WT_NCO), r);
+      tmem_ld_x32(taddr + uint32_t(tap * NCO), r);
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 8; ++i)
-        reinterpret_cast<uint4*>(out + tap * WT_NCO)[i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+        reinterpret_cast<uint4*>(out + tap * NCO)[i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+      if constexpr (NCO > 32) {
+        uint32_t r2[16];
+        tmem_ld_x16(taddr + uint32_t(tap * NCO + 32), r2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          reinterpret_cast<uint4*>(out + tap * NCO + 32)[i] = make_uint4(r2[4 * i], r2[4 * i + 1], r2[4 * i + 2], r2[4 * i + 3]);
+      }
     }
   }
   tc_fence_before();
@@ -427,13 +436,13 @@ conv3x3_wgrad_thin_kernel(const __grid_constant__ ConvWgradThinMaps maps, const 
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
-// partials [splits][ci_tiles][128][9][32] -> dW [Cout][Cin][3][3]; one thread per partial element (coalesced over splits)
-static __global__ void conv_unpack_wgrad_thin_kernel(const float* __restrict__ part, int splits, int ci_tiles,
+// partials [splits][ci_tiles][128][9][nco] -> dW [Cout][Cin][3][3]; one thread per partial element (coalesced over splits)
+static __global__ void conv_unpack_wgrad_thin_kernel(const float* __restrict__ part, int splits, int ci_tiles, int nco,
                                                      float* __restrict__ dw, int Cout, int Cin) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  const int per_split = ci_tiles * 128 * 9 * WT_NCO;
+  const int per_split = ci_tiles * 128 * 9 * nco;
   if (e >= per_split) return;
-  const int co = e % WT_NCO, tap = (e / WT_NCO) % 9, ci = e / (9 * WT_NCO);
+  const int co = e % nco, tap = (e / nco) % 9, ci = e / (9 * nco);
   if (co >= Cout || ci >= Cin) return;
   float acc = 0.f;
   for (int s = 0; s < splits; ++s) acc += part[size_t(s) * per_split + e];

@@ -58,17 +58,28 @@ int launch_conv_halo(const ConvMaps& maps, const ConvArgs& a, cudaStream_t strea
   return SRK_OK;
 }
 
-template <int EPI>
+// SRK_SWAP_M64: "off" = always the M = 128 instance; "h1" = M = 64 with the alternative TMEM row mapping (probe);
+// default = M = 64 for layers with <= 64 output channels
+int swap_m64_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = std::getenv("SRK_SWAP_M64");
+    mode = !e ? 1 : (e[0] == 'o' ? 0 : (e[0] == 'h' && e[1] == '1' ? 2 : 1));
+  }
+  return mode;
+}
+
+template <int EPI, int MM>
 int launch_conv_swap(const ConvMaps& maps, const ConvArgs& a, cudaStream_t stream) {
-  using Cfg = SwapCfg<EPI>;
+  using Cfg = SwapCfg<EPI, MM>;
   static bool configured = false;
   if (!configured) {
-    SRK_CUDA_OK(cudaFuncSetAttribute(conv3x3_swap_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    SRK_CUDA_OK(cudaFuncSetAttribute(conv3x3_swap_kernel<EPI, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
-  const int tiles = a.B * (a.H / SWP_TH) * (a.W / SWP_TW) * ((a.n_real + 127) / 128);
+  const int tiles = a.B * (a.H / SWP_TH) * (a.W / SWP_TW) * ((a.n_real + MM - 1) / MM);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  conv3x3_swap_kernel<EPI><<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(maps, a);
+  conv3x3_swap_kernel<EPI, MM><<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(maps, a);
   SRK_LAUNCHED(1);
   SRK_CUDA_OK(cudaGetLastError());
   return SRK_OK;
@@ -333,15 +344,25 @@ extern "C" int srk_conv3x3_igemm_v(int epi, int B, int H, int W, int Cin_p, int 
     maps.c2 = maps.c[0];
     maps.r = maps.c[0];
     if (need_aux && (rc = view_map(&maps.r, r, B, H, W, 8, 8))) return rc;
-    if ((rc = make_tmap_2d(&maps.w, wk, Cout_p, 9 * (uint64_t)Cin_p, 9 * (uint64_t)Cin_p, 128))) return rc;
+    const int m64 = swap_m64_mode();
+    const bool use64 = m64 != 0 && n_real <= 64;
+    if ((rc = make_tmap_2d(&maps.w, wk, Cout_p, 9 * (uint64_t)Cin_p, 9 * (uint64_t)Cin_p, use64 ? 64 : 128))) return rc;
     ConvArgs a{};
     a.B = B; a.H = H; a.W = W; a.Cin_p = Cin_p; a.Cout_p = Cout_p; a.n_real = n_real; a.bias = bias; a.slope = slope;
-    a.alpha = alpha;
+    a.alpha = alpha; a.c_split = (m64 == 2);
+    if (use64) {
+      switch (epi) {
+        case CEPI_BIAS: return launch_conv_swap<CEPI_BIAS, 64>(maps, a, stream);
+        case CEPI_BIAS_LRELU: return launch_conv_swap<CEPI_BIAS_LRELU, 64>(maps, a, stream);
+        case CEPI_BIAS_RES: return launch_conv_swap<CEPI_BIAS_RES, 64>(maps, a, stream);
+        default: return launch_conv_swap<CEPI_MASK_LRELU, 64>(maps, a, stream);
+      }
+    }
     switch (epi) {
-      case CEPI_BIAS: return launch_conv_swap<CEPI_BIAS>(maps, a, stream);
-      case CEPI_BIAS_LRELU: return launch_conv_swap<CEPI_BIAS_LRELU>(maps, a, stream);
-      case CEPI_BIAS_RES: return launch_conv_swap<CEPI_BIAS_RES>(maps, a, stream);
-      default: return launch_conv_swap<CEPI_MASK_LRELU>(maps, a, stream);
+      case CEPI_BIAS: return launch_conv_swap<CEPI_BIAS, 128>(maps, a, stream);
+      case CEPI_BIAS_LRELU: return launch_conv_swap<CEPI_BIAS_LRELU, 128>(maps, a, stream);
+      case CEPI_BIAS_RES: return launch_conv_swap<CEPI_BIAS_RES, 128>(maps, a, stream);
+      default: return launch_conv_swap<CEPI_MASK_LRELU, 128>(maps, a, stream);
     }
   }
   // Measured on B200 (hybrid step, tools/gpu_probe_hybrid_prof.py): the halo-resident kernel wins where one 64-channel

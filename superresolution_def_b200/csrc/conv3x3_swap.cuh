@@ -23,25 +23,30 @@ namespace srk {
 constexpr int SWP_TW = 8, SWP_TH = 32;              // output tile: 256 pixels
 constexpr int SWP_BW = 16, SWP_BH = 34;             // haloed input box (pixels)
 constexpr int SWP_B_BYTES = SWP_BW * SWP_BH * 128;  // 69632
-constexpr int SWP_A_BYTES = 128 * 128;              // one weight tile
 constexpr int SWP_BOX = 64 * 128;                   // output / aux box: 64 pixels x 64 channels
 constexpr int SWP_B_STAGES = 2;
 
-template <int EPI>
+// MM = 128: one weight tile covers 128 output channels (two 64-channel boxes per pixel group).
+// MM = 64 : layers with <= 64 output channels; the M = 64 instruction streams half the A tile.  Its accumulator rows
+//           live in TMEM lanes 0-15 of each 32-lane quarter (row r -> lane 32*(r/16) + r%16; probed on B200,
+//           SRK_SWAP_M64=h1 selects the other hypothesis r -> lane r), so 16 lanes per epilogue warp carry data.
+template <int EPI, int MM>
 struct SwapCfg {
   static constexpr bool kAux = (EPI == CEPI_BIAS_RES || EPI == CEPI_MASK_LRELU);
-  static constexpr int kAStages = kAux ? 3 : 4;
+  static constexpr int kABytes = MM * 128;
+  static constexpr int kAStages = (MM == 64) ? (kAux ? 6 : 8) : (kAux ? 3 : 4);
   static constexpr int kEpiBytes = (kAux ? 2 * SWP_BOX : 0) + 2 * SWP_BOX;
-  static constexpr int kSmemBytes = SWP_B_STAGES * SWP_B_BYTES + kAStages * SWP_A_BYTES + kEpiBytes + 1024 + 1024;
+  static constexpr int kSmemBytes = SWP_B_STAGES * SWP_B_BYTES + kAStages * kABytes + kEpiBytes + 1024 + 1024;
   static_assert(kSmemBytes <= 232448 - 1280, "shared memory budget");
   static_assert(EPI == CEPI_BIAS || EPI == CEPI_BIAS_LRELU || EPI == CEPI_BIAS_RES || EPI == CEPI_MASK_LRELU,
                 "epilogues of the role-swapped kernel");
 };
 
-template <int EPI>
+template <int EPI, int MM>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 conv3x3_swap_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
-  using Cfg = SwapCfg<EPI>;
+  using Cfg = SwapCfg<EPI, MM>;
+  constexpr int SWP_A_BYTES = Cfg::kABytes;
   constexpr int SA = Cfg::kAStages, SB = SWP_B_STAGES, S = SA + SB;   // barrier slots: [0, SB) halo ring, [SB, S) weights
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -58,7 +63,7 @@ conv3x3_swap_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_x = args.W / SWP_TW, tiles_y = args.H / SWP_TH;
-  const int co_tiles = (args.n_real + 127) / 128;   // 128-channel tiles that hold real output channels
+  const int co_tiles = (args.n_real + MM - 1) / MM;   // MM-channel tiles that hold real output channels
   const int m_tiles = args.B * tiles_y * tiles_x;
   const int num_tiles = m_tiles * co_tiles;
   const int kc_per_tap = args.Cin_p / 64;
@@ -83,7 +88,7 @@ conv3x3_swap_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) 
 
   auto tile_coords = [&](int tile, int& b, int& y0, int& x0, int& c0) {
     const int mt = tile / co_tiles;
-    c0 = (tile % co_tiles) * 128;
+    c0 = (tile % co_tiles) * MM;
     b = mt / (tiles_y * tiles_x);
     const int r = mt % (tiles_y * tiles_x);
     y0 = (r / tiles_x) * SWP_TH;
@@ -112,7 +117,7 @@ conv3x3_swap_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) 
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, 256, 0, 0);
+      constexpr uint32_t idesc = make_idesc_bf16(MM, 256, 0, 0);
       int bs = 0, as = 0; uint32_t bph = 0, aph = 0; int it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
@@ -145,16 +150,20 @@ conv3x3_swap_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) 
   } else {
     // ---------------------------------------------------------------- epilogue: 8 warps, transposing store
     const int q = warp & 3, half = (warp - 2) >> 2;
-    const int row = q * 32 + lane;            // accumulator row = output channel within the 128-channel tile
-    const int cbox = q >> 1;                  // which 64-channel box this warp's rows belong to
-    const int cc = row & 63;                  // channel inside the box
+    // accumulator row (= output channel within the tile) held by this thread's TMEM lane, or -1
+    int row;
+    if (MM == 128) row = q * 32 + lane;
+    else if (args.c_split) row = (q < 2) ? q * 32 + lane : -1;          // hypothesis h1: row r -> lane r
+    else row = (lane < 16) ? q * 16 + lane : -1;                        // row r -> lane 32*(r/16) + r%16
+    const int cbox = (row < 0) ? -1 : (row >> 6);   // which 64-channel box this row belongs to
+    const int cc = row & 63;                        // channel inside the box
     const bool elected = (threadIdx.x == 64);
     const uint32_t lane_sel = uint32_t(q * 32) << 16;
     constexpr int kOutOff = Cfg::kAux ? 2 * SWP_BOX : 0;
     uint32_t box_counter = 0, aux_count = 0;
     int it = 0;
     // number of 64-channel boxes that hold real channels in co-tile c0: ceil(min(n_real - c0, 128) / 64)
-    auto boxes_of = [&](int c0) { const int rem = args.n_real - c0; return rem > 64 ? 2 : (rem > 0 ? 1 : 0); };
+    auto boxes_of = [&](int c0) { const int rem = args.n_real - c0; return (MM == 128 && rem > 64) ? 2 : (rem > 0 ? 1 : 0); };
     auto step_coords = [&](int tile, int step, int& b, int& yy, int& x0, int& ch0) {
       int y0, c0;
       tile_coords(tile, b, y0, x0, c0);
@@ -178,7 +187,7 @@ conv3x3_swap_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) 
       const int next_tile = tile + gridDim.x;
       const int nb = boxes_of(c0);
       const int nsteps = 4 * nb;   // 4 groups of 8 image rows x nb channel boxes
-      const float bias_v = s_bias[(c0 + row) & 255];
+      const float bias_v = s_bias[(c0 + (row < 0 ? 0 : row)) & 255];
       mbar_wait(tfull_bar(acc), (it >> 1) & 1u);
       tc_fence_after();
 #pragma unroll 1
@@ -210,9 +219,11 @@ conv3x3_swap_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) 
           mbar_wait(aux_bar(ab), (aux_count >> 1) & 1u);
           aux_addr = epi_base + ab * SWP_BOX;
         }
-        const bool active = (cbox == cb);
+        const bool active = (cbox == cb);                     // this lane holds a channel of box cb
+        // tcgen05.ld is warp-collective: the whole warp loads when any of its lanes can hold data of this box
+        const bool warp_active = (MM == 128) ? ((q >> 1) == cb) : (args.c_split ? (q < 2) : true);
         uint32_t r[32];
-        if (active) {
+        if (warp_active) {
           tmem_ld_x32(taddr + uint32_t(g * 64 + half * 32), r);
           tmem_ld_wait();
         }

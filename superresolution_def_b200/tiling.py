@@ -6,7 +6,7 @@ assembled frame equals `model(lr_tile)` for every tile (exactly, with halo == 0;
 larger tile is kept, which removes the seams a zero-padded convolution leaves at tile borders).
 
 Tiles are independent: rank r processes tiles r, r + world, ... in batches; there is no data-path collective, only the
-final gather of the finished tiles on rank 0.
+final gather of the finished tiles on rank 0 (device to device), after which the frame is one permute of the tile stack.
 """
 from __future__ import annotations
 
@@ -32,45 +32,59 @@ def extract_tiles(frame: torch.Tensor, origins, tile: int, halo: int) -> torch.T
     return torch.cat([frame[:, :, y:y + size, x:x + size] for y, x in origins], dim=0)
 
 
+def _tile_view(frame: torch.Tensor, tile: int, halo: int) -> torch.Tensor:
+    """(1,1,H,W) -> (ny, nx, t, t) strided view of all tiles, t = tile + 2*halo (the frame border is reflect-padded by
+    `halo`); no copy until a batch of tiles is gathered."""
+    if halo:
+        frame = F.pad(frame, (halo, halo, halo, halo), mode="reflect")
+    size = tile + 2 * halo
+    return frame[0, 0].unfold(0, size, tile).unfold(1, size, tile)    # (ny, nx, size, size), indexed per batch below
+
+
 @torch.no_grad()
 def sr_frame_tiled(model: Callable[[torch.Tensor], torch.Tensor], frame: torch.Tensor, *, tile: int = 128, halo: int = 0,
                    scale: int = 4, batch: int = 16, rank: int = 0, world: int = 1, device=None):
     """Super-resolve `frame` ((H,W) or (1,1,H,W), float in [0,1]) tile by tile.
 
     Returns the (1,1,scale*H,scale*W) result on rank 0 (CPU tensor) and None on the other ranks.  `model` maps
-    (b,1,t,t) -> (b,1,scale*t,scale*t) with t = tile + 2*halo."""
+    (b,1,t,t) -> (b,1,scale*t,scale*t) with t = tile + 2*halo.
+
+    The frame is moved to `device` once, tiles are strided views of it, finished tiles stay on the device, the gather
+    runs device to device (NCCL over NVLink when the process group is NCCL) and the frame is assembled with one
+    permute on rank 0, so that the only host traffic is the frame in and the result out."""
     if frame.dim() == 2:
         frame = frame[None, None]
     H, W = frame.shape[-2:]
     origins = tile_origins(H, W, tile)
-    mine = list(range(rank, len(origins), world))
-    device = device or frame.device
+    ny, nx = H // tile, W // tile
+    n = len(origins)
+    mine = list(range(rank, n, world))
+    device = torch.device(device) if device is not None else frame.device
     out_tile = tile * scale
-    results = torch.empty(len(mine), 1, out_tile, out_tile, dtype=torch.float32)
+    fdev = frame.to(device, non_blocking=True).float()
+    tiles = _tile_view(fdev, tile, halo)                               # (ny, nx, t, t) view
+    per = (n + world - 1) // world
+    results = torch.zeros(per, 1, out_tile, out_tile, dtype=torch.float32, device=device)
     for s in range(0, len(mine), batch):
-        idx = mine[s:s + batch]
-        lr = extract_tiles(frame, [origins[i] for i in idx], tile, halo).to(device, non_blocking=True)
+        idx = torch.tensor(mine[s:s + batch], device=device)
+        lr = tiles[idx // nx, idx % nx].unsqueeze(1).contiguous()
         sr = model(lr).float()
         if halo:
             sr = sr[:, :, halo * scale:halo * scale + out_tile, halo * scale:halo * scale + out_tile]
-        results[s:s + len(idx)] = sr.cpu()
+        results[s:s + idx.numel()] = sr
     if world > 1:
-        # final gather only: every rank contributes the same number of tiles up to one; pad to the maximum
-        per = (len(origins) + world - 1) // world
-        buf = torch.zeros(per, 1, out_tile, out_tile)
-        buf[:len(mine)] = results
-        backend = dist.get_backend()
-        send = buf.to(device) if backend == "nccl" else buf
-        gathered = [torch.empty_like(send) for _ in range(world)] if rank == 0 else None
-        dist.gather(send, gathered, dst=0)
+        # final gather only (no data-path collective): every rank contributes `per` tile slots
+        gathered = [torch.empty_like(results) for _ in range(world)] if rank == 0 else None
+        dist.gather(results, gathered, dst=0)
         if rank != 0:
             return None
-        parts = [g.cpu() for g in gathered]
+        # slot k of rank r is tile r + k*world: interleave the ranks back into row-major tile order
+        allt = torch.stack(gathered, dim=1).reshape(per * world, 1, out_tile, out_tile)[:n]
     else:
-        parts = [results]
-    out = torch.empty(1, 1, H * scale, W * scale, dtype=torch.float32)
-    for r, part in enumerate(parts):
-        for k, i in enumerate(range(r, len(origins), world)):
-            y, x = origins[i]
-            out[0, 0, y * scale:(y + tile) * scale, x * scale:(x + tile) * scale] = part[k, 0]
-    return out
+        allt = results[:n]
+    out = allt.reshape(ny, nx, out_tile, out_tile).permute(0, 2, 1, 3).reshape(1, 1, ny * out_tile, nx * out_tile)
+    if out.is_cuda:
+        host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+        host.copy_(out, non_blocking=False)
+        return host
+    return out.contiguous()

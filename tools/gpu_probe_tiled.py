@@ -26,6 +26,8 @@ frame = torch.rand(side, side, generator=g)
 with torch.no_grad():
     for _ in range(2):
         hat(torch.rand(batch, 1, 128, 128, device=dev))
+    # warm-up frame: creates the NCCL point-to-point channels the gather uses and the pinned result buffer pool
+    sr_frame_tiled(hat, torch.rand(1024, 1024, generator=g), tile=128, batch=batch, rank=rank, world=world, device=dev)
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()

@@ -532,8 +532,8 @@ extern "C" int srk_cab_se_fwd(const void* y, const void* x, int B, int HW, int C
                               float* hidden, float* scale, void* out, void* stream_) {
   if (Cp % 8 || C > Cp || S < 1 || S > 32 || Cp > 256) return fail(SRK_ERR_UNSUPPORTED, "srk_cab_se_fwd: shape");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const int nchunk = 32, pairs = Cp / 2, rpb = 4;
-  cab_colsum_kernel<<<dim3(nchunk, B), pairs * rpb, Cp * sizeof(float), stream>>>(
+  const int nchunk = 32, groups = Cp / 8, rpb = 16;
+  cab_colsum_kernel<<<dim3(nchunk, B), groups * rpb, Cp * sizeof(float), stream>>>(
       static_cast<const __nv_bfloat16*>(y), nullptr, HW, Cp, ws);
   SRK_LAUNCHED(1);
   cab_se_fwd_kernel<<<B, 256, (C + S) * sizeof(float), stream>>>(ws, nchunk, Cp, HW, C, S, w1, b1, w2, b2, pool, hidden, scale);
@@ -551,9 +551,9 @@ extern "C" int srk_cab_se_bwd(const void* g, const void* y, int B, int HW, int C
                               float* ws, void* dy, float* dw1, float* db1, float* dw2, float* db2, void* stream_) {
   if (Cp % 8 || C > Cp || S < 1 || S > 32 || Cp > 256) return fail(SRK_ERR_UNSUPPORTED, "srk_cab_se_bwd: shape");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const int nchunk = 32, pairs = Cp / 2, rpb = 4;
+  const int nchunk = 32, groups = Cp / 8, rpb = 16;
   float* dpool_hw = ws + (size_t)B * nchunk * Cp;
-  cab_colsum_kernel<<<dim3(nchunk, B), pairs * rpb, Cp * sizeof(float), stream>>>(
+  cab_colsum_kernel<<<dim3(nchunk, B), groups * rpb, Cp * sizeof(float), stream>>>(
       static_cast<const __nv_bfloat16*>(g), static_cast<const __nv_bfloat16*>(y), HW, Cp, ws);
   SRK_LAUNCHED(1);
   cab_se_bwd_kernel<<<1, 256, (C + 2 * S) * sizeof(float), stream>>>(ws, nchunk, Cp, HW, B, C, S, alpha, pool, hidden, scale,
@@ -620,7 +620,7 @@ extern "C" int srk_layernorm_bwd(const void* dy, int lddy, const void* x, int ld
   SRK_LAUNCHED(1);
   SRK_CUDA_OK(cudaGetLastError());
   if (dgamma && dbeta) {
-    ln_param_grad_reduce_kernel<<<(2 * C + 127) / 128, 128, 0, stream>>>(part_ws, grid, Cp, C, dgamma, dbeta);
+    ln_param_grad_reduce_kernel<<<(2 * C * 32 + 255) / 256, 256, 0, stream>>>(part_ws, grid, Cp, C, dgamma, dbeta);
     SRK_LAUNCHED(1);
     SRK_CUDA_OK(cudaGetLastError());
   }

@@ -234,60 +234,81 @@ static __global__ void ln_bwd_rows_kernel(const __nv_bfloat16* __restrict__ dy, 
                                    int ldx, const float* __restrict__ stats, const float* __restrict__ gamma,
                                    const __nv_bfloat16* __restrict__ dres, int lddres, __nv_bfloat16* __restrict__ dx,
                                    int lddx, float* __restrict__ part, int rows, int C, int Cp) {
+  // warp per row, lane l owns channels 8l .. 8l+7 (one 16-byte access per tensor and row; Cp <= 256)
   __shared__ float s_acc[2][256];
   for (int i = threadIdx.x; i < 512; i += blockDim.x) (&s_acc[0][0])[i] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
-  float ag[8], ab[8];
+  const int c0 = lane * 8;
+  const bool has = c0 < Cp;
+  float g8[8], ag[8], ab[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) ag[k] = ab[k] = 0.f;
-  for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < rows; row += gridDim.x * warps_per_block) {
-    const float2 st = reinterpret_cast<const float2*>(stats)[row];
-    const __nv_bfloat16* dyr = dy + size_t(row) * lddy;
-    const __nv_bfloat16* xr = x + size_t(row) * ldx;
+  for (int k = 0; k < 8; ++k) {
+    ag[k] = ab[k] = 0.f;
+    g8[k] = (c0 + k < C) ? gamma[c0 + k] : 0.f;   // gamma = 0 on pad columns: they drop out of every sum below
+  }
+  const float inv_c = 1.0f / float(C);
+  const int row_step = gridDim.x * warps_per_block;
+  int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  // software pipeline: the next row's three 16-byte loads are in flight while this row is reduced and stored
+  uint4 nx = make_uint4(0u, 0u, 0u, 0u), nd = nx, nr = nx;
+  float2 nst = make_float2(0.f, 0.f);
+  auto fetch = [&](int r) {
+    if (r < rows) {
+      nst = reinterpret_cast<const float2*>(stats)[r];
+      if (has) {
+        nx = *reinterpret_cast<const uint4*>(x + size_t(r) * ldx + c0);
+        nd = *reinterpret_cast<const uint4*>(dy + size_t(r) * lddy + c0);
+        if (dres) nr = *reinterpret_cast<const uint4*>(dres + size_t(r) * lddres + c0);
+      }
+    }
+  };
+  fetch(row);
+  for (; row < rows; row += row_step) {
+    const float2 st = nst;
+    const uint4 vx = nx, vd = nd, vr = nr;
+    fetch(row + row_step);
+    const uint32_t wx[4] = {vx.x, vx.y, vx.z, vx.w}, wd[4] = {vd.x, vd.y, vd.z, vd.w}, wr[4] = {vr.x, vr.y, vr.z, vr.w};
     float xh[8], dn[8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const int c = lane + 32 * k;
-      xh[k] = dn[k] = 0.f;
-      if (c < C) {
-        xh[k] = (__bfloat162float(xr[c]) - st.x) * st.y;
-        dn[k] = __bfloat162float(dyr[c]);
-        const float dh = dn[k] * gamma[c];
-        s1 += dh;
-        s2 += dh * xh[k];
-        ag[k] += dn[k] * xh[k];
-        ab[k] += dn[k];
-      }
+      const float xv = (k & 1) ? bf16_hi(wx[k >> 1]) : bf16_lo(wx[k >> 1]);
+      const bool real = c0 + k < C;
+      xh[k] = real ? (xv - st.x) * st.y : 0.f;
+      dn[k] = real ? ((k & 1) ? bf16_hi(wd[k >> 1]) : bf16_lo(wd[k >> 1])) : 0.f;
+      const float dh = dn[k] * g8[k];
+      s1 += dh;
+      s2 += dh * xh[k];
+      ag[k] += dn[k] * xh[k];
+      ab[k] += dn[k];
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
       s1 += __shfl_xor_sync(0xffffffffu, s1, o);
       s2 += __shfl_xor_sync(0xffffffffu, s2, o);
     }
-    const float c1 = s1 / float(C), c2 = s2 / float(C);
-    __nv_bfloat16* dxr = dx + size_t(row) * lddx;
+    const float c1 = s1 * inv_c, c2 = s2 * inv_c;
+    if (has) {
+      float o[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int c = lane + 32 * k;
-      if (c < Cp) {
-        float o = 0.f;
-        if (c < C) {
-          o = round_bf16(st.y * (dn[k] * gamma[c] - c1 - xh[k] * c2));
-          if (dres) o += __bfloat162float(dres[size_t(row) * lddres + c]);
+      for (int k = 0; k < 8; ++k) {
+        o[k] = 0.f;
+        if (c0 + k < C) {
+          o[k] = round_bf16(st.y * (dn[k] * g8[k] - c1 - xh[k] * c2));
+          if (dres) o[k] += (k & 1) ? bf16_hi(wr[k >> 1]) : bf16_lo(wr[k >> 1]);
         }
-        dxr[c] = __float2bfloat16_rn(o);
       }
+      *reinterpret_cast<uint4*>(dx + size_t(row) * lddx + c0) =
+          make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
     }
   }
+  if (has) {
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int c = lane + 32 * k;
-    if (c < Cp) {
-      atomicAdd(&s_acc[0][c], ag[k]);
-      atomicAdd(&s_acc[1][c], ab[k]);
+    for (int k = 0; k < 8; ++k) {
+      atomicAdd(&s_acc[0][c0 + k], ag[k]);
+      atomicAdd(&s_acc[1][c0 + k], ab[k]);
     }
   }
   __syncthreads();
@@ -300,12 +321,15 @@ static __global__ void ln_bwd_rows_kernel(const __nv_bfloat16* __restrict__ dy, 
 // out[which][c] = sum_k part[k][which][c]  (tiny finishing reduction for the standalone LN backward)
 static __global__ void ln_param_grad_reduce_kernel(const float* __restrict__ part, int nparts, int Cp, int C,
                                             float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per output element: lanes stride over the per-CTA partials, then a shuffle reduction
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= 2 * C) return;
   const int w = i / C, c = i % C;
   float acc = 0.f;
-  for (int k = 0; k < nparts; ++k) acc += part[(size_t(k) * 2 + w) * Cp + c];
-  (w == 0 ? dgamma : dbeta)[c] = acc;
+  for (int k = lane; k < nparts; k += 32) acc += part[(size_t(k) * 2 + w) * Cp + c];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) (w == 0 ? dgamma : dbeta)[c] = acc;
 }
 
 }  // namespace srk

@@ -63,7 +63,9 @@ def test_rdb_halo_conv_matches_oracle(mode):
     code = ("import torch; from tests.test_hybrid_gpu import _cmp_module, _ho; from tests.util import randomize_;"
             "from superresolution_def_b200.hybridmodels_hat import ResidualDenseBlock; ho = _ho(); torch.manual_seed(1);"
             "blk = randomize_(ResidualDenseBlock(48, 24), seed=2).cuda();"
-            "_cmp_module(blk, lambda t, sd: ho.rdb(t, sd, ''), torch.randn(2, 48, 32, 48, device='cuda')); print('ok')")
+            "_cmp_module(blk, lambda t, sd: ho.rdb(t, sd, ''), torch.randn(2, 48, 32, 48, device='cuda'));"
+            "blk = randomize_(ResidualDenseBlock(64, 32), seed=3).cuda();"      # the class defaults (num_feat 64 / grow 32)
+            "_cmp_module(blk, lambda t, sd: ho.rdb(t, sd, ''), torch.randn(1, 64, 64, 32, device='cuda')); print('ok')")
     env = dict(os.environ, SRK_CONV_HALO=mode)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)

@@ -6,6 +6,7 @@
 #include "cab_aux.cuh"
 #include "block_aux.cuh"
 #include "srk_host.h"
+#include <cstdlib>
 
 using namespace srk;
 
@@ -46,7 +47,8 @@ struct WsLayout {  // offsets (floats) into SrkBlockScratch.wg_ws
 };
 
 int attn_bwd_gx(int nwin, int heads) {
-  int gx = num_sms() * 4 / heads;
+  static const int per_sm = getenv("SRK_ATTN_BWD_CTAS") ? atoi(getenv("SRK_ATTN_BWD_CTAS")) : 3;
+  int gx = num_sms() * per_sm / heads;
   if (gx > nwin) gx = nwin;
   return gx < 1 ? 1 : gx;
 }

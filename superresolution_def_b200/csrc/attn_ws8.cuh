@@ -338,7 +338,7 @@ __device__ __forceinline__ void tileT_times_tile(uint32_t a_tile, uint32_t b_til
   }
 }
 
-__global__ void __launch_bounds__(ATT_THREADS, 4) win_attn_ws8_bwd_kernel(const AttnArgs a) {
+__global__ void __launch_bounds__(ATT_THREADS, 3) win_attn_ws8_bwd_kernel(const AttnArgs a) {
   extern __shared__ __align__(128) uint8_t smem_dyn[];
   AttnBwdSmem& sm = *reinterpret_cast<AttnBwdSmem*>(smem_dyn);
   pdl_launch_dependents();

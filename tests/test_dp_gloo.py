@@ -48,7 +48,7 @@ def _worker(rank, world, port, q):
         red.zero_grad()
         net(x[rank * 2:(rank + 1) * 2]).pow(2).mean().backward()
         red.finish()
-    q.put((rank, [p.grad.clone() for p in net.parameters()]))
+    q.put((rank, [p.grad.numpy().copy() for p in net.parameters()]))   # by value: no shared-memory handles that die with the worker
     dist.destroy_process_group()
 
 
@@ -69,4 +69,5 @@ def test_bucketed_reducer_world2_matches_single_process():
     net(x).pow(2).mean().backward()
     for r in (0, 1):
         for g, p in zip(res[r], net.parameters()):
+            g = torch.from_numpy(g)
             assert torch.allclose(g, p.grad, atol=1e-6), (r, (g - p.grad).abs().max())

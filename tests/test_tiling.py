@@ -41,7 +41,8 @@ def _worker(rank, world, port, q):
     torch.manual_seed(0)
     frame = torch.rand(96, 96)
     out = sr_frame_tiled(_fake_model, frame, tile=32, batch=2, rank=rank, world=world)
-    q.put((rank, None if out is None else out.clone()))
+    # by value (numpy pickles its bytes): a torch tensor would travel as a shared-memory handle that dies with this worker
+    q.put((rank, None if out is None else out.numpy().copy()))
     dist.destroy_process_group()
 
 
@@ -58,7 +59,7 @@ def test_tiles_sharded_over_two_ranks_gather_on_rank0():
     torch.manual_seed(0)
     frame = torch.rand(96, 96)
     assert res[1] is None
-    assert torch.equal(res[0], _fake_model(frame[None, None]))   # 9 tiles: ranks hold 5 and 4
+    assert torch.equal(torch.from_numpy(res[0]), _fake_model(frame[None, None]))   # 9 tiles: ranks hold 5 and 4
 
 
 @pytest.mark.gpu

@@ -25,23 +25,25 @@ def _rdb_params(rdb) -> list[torch.Tensor]:
     return [sd[k] for k in RDB_KEYS]
 
 
+def _kaiming_zero_bias(convs):
+    """The reference's initialisation of its plain convolutions (:31-36, :109-115): He-normal weights, zero bias."""
+    for m in convs:
+        nn.init.kaiming_normal_(m.weight, a=0, mode="fan_in")
+        if m.bias is not None:
+            m.bias.data.zero_()
+
+
 class ResidualDenseBlock(nn.Module):
+    """conv_k sees the block input and the k-1 earlier growth outputs; parameters conv1..conv5 as in the reference."""
+
     def __init__(self, num_feat=64, num_grow_ch=32):
         super().__init__()
-        self.conv1 = nn.Conv2d(num_feat, num_grow_ch, 3, 1, 1)
-        self.conv2 = nn.Conv2d(num_feat + num_grow_ch, num_grow_ch, 3, 1, 1)
-        self.conv3 = nn.Conv2d(num_feat + 2 * num_grow_ch, num_grow_ch, 3, 1, 1)
-        self.conv4 = nn.Conv2d(num_feat + 3 * num_grow_ch, num_grow_ch, 3, 1, 1)
-        self.conv5 = nn.Conv2d(num_feat + 4 * num_grow_ch, num_feat, 3, 1, 1)
-        self.lrelu = nn.LeakyReLU(negative_slope=0.2, inplace=True)
         self.num_feat, self.num_grow_ch = num_feat, num_grow_ch
-        self._init_weights()
-
-    def _init_weights(self):
-        for m in [self.conv1, self.conv2, self.conv3, self.conv4, self.conv5]:
-            nn.init.kaiming_normal_(m.weight, a=0, mode='fan_in')
-            if m.bias is not None:
-                m.bias.data.zero_()
+        for k in range(1, 6):   # registration order conv1 .. conv5 (state_dict / RNG order of the reference)
+            cout = num_grow_ch if k < 5 else num_feat
+            setattr(self, f"conv{k}", nn.Conv2d(num_feat + (k - 1) * num_grow_ch, cout, 3, 1, 1))
+        self.lrelu = nn.LeakyReLU(negative_slope=0.2, inplace=True)
+        _kaiming_zero_bias(getattr(self, f"conv{k}") for k in range(1, 6))
 
     def forward(self, x):
         """x: (B, num_feat, H, W) as in the reference (:38-44)."""
@@ -78,20 +80,12 @@ class HybridHATRealESRGAN(nn.Module):
                        resi_connection='1conv')
         self.conv_adapt = nn.Conv2d(in_chans, num_feat, 3, 1, 1)
         self.lrelu = nn.LeakyReLU(negative_slope=0.2, inplace=True)
-        self.rrdb_trunk = nn.Sequential(*[RRDBBlock(num_feat, num_grow_ch) for _ in range(num_rrdb)])
-        self.conv_body = nn.Conv2d(num_feat, num_feat, 3, 1, 1)
-        self.conv_up = nn.Conv2d(num_feat, num_feat, 3, 1, 1)
-        self.conv_hr = nn.Conv2d(num_feat, num_feat, 3, 1, 1)
+        self.rrdb_trunk = nn.Sequential(*(RRDBBlock(num_feat, num_grow_ch) for _ in range(num_rrdb)))
+        for name in ("conv_body", "conv_up", "conv_hr"):
+            setattr(self, name, nn.Conv2d(num_feat, num_feat, 3, 1, 1))
         self.conv_last = nn.Conv2d(num_feat, in_chans, 3, 1, 1)
         self.num_feat, self.num_grow_ch = num_feat, num_grow_ch
-        self._init_weights()
-
-    def _init_weights(self):
-        for m in [self.conv_adapt, self.conv_body, self.conv_up, self.conv_hr, self.conv_last]:
-            if isinstance(m, nn.Conv2d):
-                nn.init.kaiming_normal_(m.weight, a=0, mode='fan_in')
-                if m.bias is not None:
-                    m.bias.data.zero_()
+        _kaiming_zero_bias((self.conv_adapt, self.conv_body, self.conv_up, self.conv_hr, self.conv_last))
 
     def tail_params(self) -> list[torch.Tensor]:
         ps = [self.conv_adapt.weight, self.conv_adapt.bias]

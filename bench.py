@@ -391,6 +391,13 @@ def run_ours(args):
             "step_frac_of_bf16_sustained": value / world * gflop / 1e3 / peaks[2]}
     if rank == 0:
         line["roofline"], line["roofline_kernels"] = roofline_probe(B, peaks)
+        try:  # BASELINE.json's metric also names the attention tensor-pipe utilisation: quoted from the ncu captures
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+                line["attn_tensor_pipe_util"] = {k: v for k, v in json.load(f)["_attention_tensor_pipe"].items()
+                                                 if not k.startswith("_")}
+                line["attn_tensor_pipe_util"]["source"] = "ncu --set full, profiles/r01_ncu_full_attn*.txt (not measured live)"
+        except Exception:
+            pass
         if world == 1 and not args.no_cpu_baseline and not hat:
             v, spp, threads = cpu_reference_arm(2, 1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",

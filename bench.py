@@ -113,6 +113,57 @@ def cpu_reference_arm(steps: int, warmup: int, threads: int | None = None):
     return steps / dt, dt / steps, threads
 
 
+def gpu_eager_baseline(batch: int, steps: int = 3, warmup: int = 2):
+    """The GPU bar: stock PyTorch eager — the oracle's ATen call sequence, i.e. exactly what the
+    reference modules execute — under torch.autocast(bf16) on this same B200, same training step (fwd + L1 + bwd + fused
+    AdamW), CUDA-event timed.  A reported baseline like cpu_baseline: it never touches the product path.  The largest of
+    (batch, batch/2, batch/4) that fits is used and stated."""
+    from oracle import swinir_oracle as o
+    from superresolution_def_b200.synth import synthetic_pairs
+    dev = torch.device("cuda", torch.cuda.current_device())
+    kw = dict(img_size=128, window_size=8, depths=MODEL_KW["depths"], num_heads=MODEL_KW["num_heads"], upscale=4)
+    for b in (batch, max(1, batch // 2), max(1, batch // 4)):
+        try:
+            torch.manual_seed(0)
+            sd = o.init_state_dict(**{k: MODEL_KW[k] for k in ("img_size", "window_size", "embed_dim", "depths", "num_heads")})
+            sd = {k: v.to(dev) for k, v in sd.items()}
+            params = [v.requires_grad_(True) for v in sd.values() if v.is_floating_point()]
+            opt = torch.optim.AdamW(params, lr=1e-4, betas=(0.9, 0.99), fused=True)
+            lr, hr = synthetic_pairs(min(b, 4), seed=99)
+            reps = (b + lr.shape[0] - 1) // lr.shape[0]
+            lr, hr = lr.repeat(reps, 1, 1, 1)[:b].to(dev), hr.repeat(reps, 1, 1, 1)[:b].to(dev)
+
+            def step():
+                opt.zero_grad(set_to_none=True)
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    sr = o.swinir_forward(lr, sd, **kw)
+                loss = torch.nn.functional.l1_loss(sr.float(), hr)
+                loss.backward()
+                opt.step()
+                return loss
+
+            for _ in range(warmup):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                step()
+            e1.record()
+            e1.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            mem = torch.cuda.max_memory_allocated() / 2 ** 30
+            del sd, params, opt
+            torch.cuda.empty_cache()
+            return {"value": b / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "batch": b, "dtype": "bf16 autocast",
+                    "impl": "oracle/swinir_oracle.py (the reference's ATen sequence: cuBLAS / cuDNN / eager elementwise), "
+                            "eager, fused AdamW", "steps": steps, "warmup": warmup, "peak_mem_gb": mem}
+        except torch.OutOfMemoryError:
+            torch.cuda.empty_cache()
+            continue
+    return {"unavailable": "out of memory at every tried batch size"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -195,33 +246,30 @@ def roofline_probe(batch: int, peaks):
         ms = e0.elapsed_time(e1) / reps
         rows.append({"kernel": name, "function": fn_name, "launches_per_step": 36 * per_block, "ms_per_launch": ms,
                      "algorithmic_bytes": nbytes, "achieved": nbytes / (ms * 1e-3) / 1e9, "frac": nbytes / (ms * 1e-3) / 1e9 / hbm})
-    by_fn: dict = {}
-    for r in rows:
-        d = by_fn.setdefault(r["function"], {"ms": 0.0, "bytes": 0.0, "launches": 0})
-        d["ms"] += r["ms_per_launch"] * r["launches_per_step"]
-        d["bytes"] += r["algorithmic_bytes"] * r["launches_per_step"]
-        d["launches"] += r["launches_per_step"]
-    top = max(by_fn.items(), key=lambda kv: kv[1]["ms"])
-    ach = top[1]["bytes"] / (top[1]["ms"] * 1e-3) / 1e9
-    total_ms = sum(d["ms"] for d in by_fn.values())
-    # measured DRAM traffic of that kernel (ncu --set full, one capture per round under profiles/); reported next to
-    # the algorithmic bytes so that wasted re-reads would show
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            t = json.load(f).get(top[0])
-        if t and batch == 16:
-            traffic = t["traffic"]
-    except Exception:
-        traffic = None
-    roof = {"kernel": top[0] + " (tcgen05 weight-gradient GEMM, MN-major operands)" if "wgrad" in top[0] else top[0],
-            "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-            "traffic": traffic, "peak_kind": kind, "ms_per_launch": top[1]["ms"] / top[1]["launches"],
-            "algorithmic_bytes": top[1]["bytes"] / top[1]["launches"], "launches_per_step": top[1]["launches"],
-            "share_of_block_kernels": top[1]["ms"] / total_ms,
-            "note": "dominant kernel function by launches x duration among the per-block kernels, each timed alone at the "
-                    "step's shapes; achieved/algorithmic_bytes are averages over that function's launch shapes; traffic = "
-                    "ncu dram read+write bytes of its largest launch shape (profiles/r01_traffic.json)"}
+    total_ms = sum(r["ms_per_launch"] * r["launches_per_step"] for r in rows)
+    top = max(rows, key=lambda r: r["ms_per_launch"] * r["launches_per_step"])
+    # measured DRAM traffic of that launch shape (ncu --set full, one capture per round under profiles/), keyed by the same
+    # case name, so traffic and algorithmic bytes always refer to the SAME launch shape
+    traffic, tsrc = None, None
+    if batch == 16:
+        for fn in ("r02_traffic.json", "r01_traffic.json"):
+            try:
+                with open(os.path.join(ROOT, "profiles", fn)) as f:
+                    tj = json.load(f)
+                t = tj.get(top["kernel"]) or tj.get(top["function"])
+                if t and abs(t.get("algorithmic_bytes", top["algorithmic_bytes"]) - top["algorithmic_bytes"]) <= 0.02 * top["algorithmic_bytes"]:
+                    traffic, tsrc = t["traffic"], f"profiles/{fn}: {t.get('capture', '')}"
+                    break
+            except Exception:
+                continue
+    roof = {"kernel": top["kernel"], "function": top["function"], "bound": "hbm", "achieved": top["achieved"], "peak": hbm,
+            "unit": "GB/s", "frac": top["frac"], "traffic": traffic, "traffic_source": tsrc, "peak_kind": kind,
+            "ms_per_launch": top["ms_per_launch"], "algorithmic_bytes": top["algorithmic_bytes"],
+            "launches_per_step": top["launches_per_step"],
+            "share_of_block_kernels": top["ms_per_launch"] * top["launches_per_step"] / total_ms,
+            "note": "dominant per-block kernel launch shape by launches x duration, timed alone at the step's shape (operands "
+                    "larger than L2); achieved = algorithmic bytes of that shape / mean launch duration; traffic = ncu dram "
+                    "read+write bytes of the same shape"}
     return roof, rows
 
 
@@ -275,10 +323,13 @@ def run_ours(args):
     if world > 1:
         for p in net.parameters():
             dist.broadcast(p.data, 0)
-    # N > 1: flat fp32 gradient buckets + NCCL all-reduce (overlapped with backward from hooks when run eagerly; issued
-    # between the two graph replays otherwise, so no NCCL call sits inside a stream capture).  N == 1: no exchange,
-    # gradients are handed to the optimizer as produced.
-    reducer = BucketedGradReducer(swinir_grad_groups(net), world, overlap=not args.graph) if world > 1 else None
+    # N > 1: flat fp32 gradient buckets + NCCL all-reduce(AVG), launched bucket by bucket from post-accumulate hooks so that
+    # the exchange of layer group k overlaps the backward of group k-1.  --dp-mode overlap (default): the hooks run inside
+    # the stream capture too, so the per-bucket ncclAllReduce nodes sit on a forked branch of the ONE step graph next to
+    # the backward kernels (NCCL is capture-safe).  --dp-mode serial: graph(fwd+bwd) -> all-reduces -> graph(AdamW), the
+    # round-1 arrangement, kept for comparison.  N == 1: no exchange.
+    dp_overlap = args.dp_mode == "overlap" or not args.graph
+    reducer = BucketedGradReducer(swinir_grad_groups(net), world, overlap=dp_overlap) if world > 1 else None
     opt = torch.optim.AdamW(net.parameters(), lr=1e-4, betas=(0.9, 0.99), fused=True, capturable=args.graph)
     nsets = 4
     lr_h, hr_h = synthetic_pairs(min(B, 4), seed=1234 + rank)
@@ -316,11 +367,21 @@ def run_ours(args):
         from superresolution_def_b200.graphs import GraphedStep
         static_lr, static_hr = dev_sets[0][0].clone(), dev_sets[0][1].clone()
         l_before = capi.launch_count()
-        if reducer is None:
-            graphed = GraphedStep(step, (static_lr, static_hr), warmup=2)
-            launches_per_step = (capi.launch_count() - l_before) // 3  # 2 warm-up runs + 1 capture run
-            step = graphed  # replaying the graph re-issues exactly the captured launches
-        else:
+        graphed = None
+        if reducer is None or dp_overlap:
+            try:
+                graphed = GraphedStep(step, (static_lr, static_hr), warmup=2)
+                launches_per_step = (capi.launch_count() - l_before) // 3  # 2 warm-up runs + 1 capture run
+                step = graphed  # replaying the graph re-issues exactly the captured launches
+            except Exception as e:  # noqa: BLE001
+                if reducer is None:
+                    raise
+                print(f"[bench rank {rank}] capturing the overlapped exchange failed ({e!r}); falling back to --dp-mode serial",
+                      file=sys.stderr, flush=True)
+                dp_overlap, reducer.overlap = False, False
+                reducer.handles.clear()
+                l_before = capi.launch_count()
+        if graphed is None:
             g_fb = GraphedStep(fwd_bwd, (static_lr, static_hr), warmup=2)
             launches_per_step = (capi.launch_count() - l_before) // 3
             g_opt = GraphedStep(lambda: opt.step(), (), warmup=2)
@@ -389,19 +450,80 @@ def run_ours(args):
             "gpu_launches": launches, "clocks": clocks, "loss": loss_v, "peak_mem_gb": mem_gb,
             "step_tflops": value / world * gflop / 1e3,
             "step_frac_of_bf16_sustained": value / world * gflop / 1e3 / peaks[2]}
+    if reducer is not None:
+        # what the exchange costs: (a) all buckets reduced back to back on an otherwise idle GPU, (b) the step with the
+        # exchange minus the same step without it (eager steps, CUDA events, max over ranks) = the part backward does not hide
+        def ev_ms(fn, n):
+            dist.barrier(); torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n):
+                fn()
+            b.record(); torch.cuda.synchronize()
+            t = torch.tensor([a.elapsed_time(b) / n], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return t.item()
+        ev_ms(reducer.reduce_all, 2)
+        allreduce_ms = ev_ms(reducer.reduce_all, 5)
+        line["comm"] = {"mode": ("one graph, per-bucket all-reduce overlapped with backward" if dp_overlap and args.graph
+                                 else "graph(fwd+bwd) -> all-reduce -> graph(AdamW)" if args.graph else "eager, overlapped hooks"),
+                        "buckets": len(reducer.buckets), "allreduce_ms_alone": allreduce_ms,
+                        "bus_gbs_alone": reducer.nbytes * 2 * (world - 1) / world / (allreduce_ms * 1e-3) / 1e9}
+        if args.single_gpu_ms:
+            line["comm"]["exposed_comm_ms"] = ms / args.steps - args.single_gpu_ms
+            line["comm"]["exposed_note"] = "this run's ms_per_step minus the N=1 ms_per_step passed by --single-gpu-ms"
     if rank == 0:
         line["roofline"], line["roofline_kernels"] = roofline_probe(B, peaks)
-        try:  # BASELINE.json's metric also names the attention tensor-pipe utilisation: quoted from the ncu captures
-            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-                line["attn_tensor_pipe_util"] = {k: v for k, v in json.load(f)["_attention_tensor_pipe"].items()
-                                                 if not k.startswith("_")}
-                line["attn_tensor_pipe_util"]["source"] = "ncu --set full, profiles/r01_ncu_full_attn*.txt (not measured live)"
-        except Exception:
-            pass
+        # BASELINE.json's metric also names the attention tensor-core utilisation.  Live figure: the MMA work the attention
+        # kernels issue (padded head_dim 32, per window 64x64 logits) / CUDA-event time / measured dense bf16 peak; the ncu
+        # tensor-pipe counters of this round's captures are quoted next to it.
+        att = {}
+        for r in line["roofline_kernels"]:
+            if r["function"].startswith("win_attn"):
+                nmm = 2 if "fwd" in r["function"] else 5   # QK^T, PV | + dP, dV, dK, dQ (S recomputed)
+                fl = nmm * 2.0 * 64 * 32 * (B * 16384) * 6
+                att[r["function"]] = {"mma_tflops": fl / (r["ms_per_launch"] * 1e-3) / 1e12,
+                                      "frac_of_bf16_burst_peak": fl / (r["ms_per_launch"] * 1e-3) / 1e12 / peaks[1],
+                                      "hbm_frac": r["frac"]}
+        for fn in ("r02_traffic.json", "r01_traffic.json"):
+            try:
+                with open(os.path.join(ROOT, "profiles", fn)) as f:
+                    tp = json.load(f)["_attention_tensor_pipe"]
+                att["ncu_tensor_pipe_active"] = {k: v for k, v in tp.items() if not k.startswith("_")}
+                att["ncu_source"] = f"profiles/{fn} (ncu --set full captures of this tree's kernels)"
+                break
+            except Exception:
+                continue
+        line["attn_tensor_pipe_util"] = att
+        if world == 1 and not hat and not args.no_gpu_baseline:
+            torch.cuda.empty_cache()
+            line["gpu_eager_baseline"] = gpu_eager_baseline(B)
+            if "value" in line["gpu_eager_baseline"]:
+                line["gpu_eager_baseline"]["ours_over_eager"] = value / line["gpu_eager_baseline"]["value"] * \
+                    (1.0 if line["gpu_eager_baseline"]["batch"] == B else 1.0)
+        if world == 1 and not hat and not args.no_sub:
+            # the other two generators of the path, a few steps each (separate processes: their own graphs and memory)
+            line["sub_records"] = {}
+            for wl in ("hat", "hybrid"):
+                try:
+                    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", wl, "--steps", "5", "--warmup", "3",
+                                        "--no-cpu-baseline", "--no-sub", "--no-gpu-baseline"], capture_output=True, text=True,
+                                       timeout=420, cwd=ROOT)
+                    js = [l for l in r.stdout.splitlines() if l.startswith("{")]
+                    if r.returncode == 0 and js:
+                        d = json.loads(js[-1])
+                        line["sub_records"][wl] = {k: d[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "config",
+                                                                      "gpu_launches", "step_tflops", "step_frac_of_bf16_sustained",
+                                                                      "peak_mem_gb", "clocks", "steps", "warmup") if k in d}
+                    else:
+                        line["sub_records"][wl] = {"unavailable": (r.stderr or r.stdout)[-300:]}
+                except Exception as e:  # noqa: BLE001
+                    line["sub_records"][wl] = {"unavailable": repr(e)[:300]}
         if world == 1 and not args.no_cpu_baseline and not hat:
             v, spp, threads = cpu_reference_arm(2, 1)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": "2 fp32 training steps of batch 1 after 1 warm-up (oracle/swinir_oracle.py)"}
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "same_config": False,
+                                    "sample": "2 fp32 training steps of batch 1 after 1 warm-up (oracle/swinir_oracle.py); "
+                                              "the GPU arm's batch is 16: same model and patch shape, smaller batch"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -417,6 +539,11 @@ def main():
                     help="swinir = the bench line (configs[1]); hat = configs[2]; hybrid = train_hat.py's generator")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the stock-PyTorch-eager leg (gpu_eager_baseline)")
+    ap.add_argument("--no-sub", action="store_true", help="skip the HAT / hybrid sub-records")
+    ap.add_argument("--dp-mode", default="overlap", choices=["overlap", "serial"],
+                    help="N>1: per-bucket all-reduce captured inside the step graph next to backward, or serial between graphs")
+    ap.add_argument("--single-gpu-ms", type=float, default=0.0, help="N>1: ms_per_step of the N=1 run, to report exposed_comm_ms")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="issue the step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -67,9 +67,6 @@ int srk_gemm_grid(int M, int N);
  * out is [ceil(Ca/128)*128, Cb] fp32 (rows >= Ca are zero). */
 int srk_gemm_wgrad(int T, int Ca, int Cb, const void* A, int lda, const void* B, int ldb, float* workspace,
                    int splits, float* out, void* stream);
-/* debug variant with explicit UMMA descriptor byte offsets (used once to validate the layout on hardware) */
-int srk_gemm_wgrad_dbg(int T, int Ca, int Cb, const void* A, int lda, const void* B, int ldb, float* workspace,
-                       int splits, float* out, int lbo_bytes, int sbo_bytes, void* stream);
 
 /* ======================================================================================================
  * Swin / HAT transformer-block level API (what the mirrored nn.Modules call).

@@ -56,8 +56,6 @@ _gemm_tn = _sig("srk_gemm_tn", [c_int, c_int, c_int, c_int, c_void_p, c_int, c_v
 _gemm_grid = _sig("srk_gemm_grid", [c_int, c_int])
 _gemm_wgrad = _sig("srk_gemm_wgrad", [c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
                                        c_void_p, c_void_p])
-_gemm_wgrad_dbg = _sig("srk_gemm_wgrad_dbg", [c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p,
-                                               c_int, c_void_p, c_int, c_int, c_void_p])
 
 EPI_STORE, EPI_GELU2, EPI_MUL, EPI_RES_LN, EPI_LNBWD, EPI_GELU1, EPI_MULG = range(7)
 
@@ -121,18 +119,14 @@ def wgrad_workspace_elems(Ca: int, Cb: int, splits: int) -> int:
     return splits * ((Ca + 127) // 128) * 128 * Cb
 
 
-def gemm_wgrad(A, B, workspace, splits, out, dbg=None):
+def gemm_wgrad(A, B, workspace, splits, out):
     """out[ceil128(Ca), Cb] (fp32) = A[T,Ca]^T @ B[T,Cb]."""
     T, Ca = A.shape
     Cb = B.shape[1]
     assert B.shape[0] == T and A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
     assert workspace.dtype == torch.float32 and workspace.numel() >= wgrad_workspace_elems(Ca, Cb, splits)
     assert out.dtype == torch.float32 and out.numel() >= ((Ca + 127) // 128) * 128 * Cb
-    if dbg is None:
-        rc = _gemm_wgrad(T, Ca, Cb, _ptr(A), _ld(A), _ptr(B), _ld(B), _ptr(workspace), splits, _ptr(out), _stream())
-    else:
-        rc = _gemm_wgrad_dbg(T, Ca, Cb, _ptr(A), _ld(A), _ptr(B), _ld(B), _ptr(workspace), splits, _ptr(out),
-                             dbg[0], dbg[1], _stream())
+    rc = _gemm_wgrad(T, Ca, Cb, _ptr(A), _ld(A), _ptr(B), _ld(B), _ptr(workspace), splits, _ptr(out), _stream())
     _check(rc, "srk_gemm_wgrad")
 
 
@@ -297,13 +291,24 @@ _conv_out1_bwd = _sig("srk_conv_out1_bwd", [c_void_p, c_void_p, c_void_p, c_void
                                             c_int, c_int, c_int, c_int, c_void_p])
 
 _ws_cache: dict = {}
+_retired: list = []   # outgrown workspaces: kept alive because a captured CUDA graph may still hold their addresses
+
+
+def retire(t) -> None:
+    """Keep an outgrown scratch tensor allocated for the life of the process.  A step captured by graphs.GraphedStep
+    has raw scratch pointers baked into its kernel nodes, so a workspace may be replaced by a larger one but must
+    never be returned to the allocator (a later replay would write into whatever reuses that memory)."""
+    if t is not None:
+        _retired.append(t)
 
 
 def _ws(n: int, device) -> torch.Tensor:
-    """A reusable fp32 workspace of at least n floats (same-stream reuse is ordered by the stream)."""
+    """A reusable fp32 workspace of at least n floats (same-stream reuse is ordered by the stream).  Grow-only:
+    an outgrown buffer is retired, never freed (see retire())."""
     k = str(device)
     t = _ws_cache.get(k)
     if t is None or t.numel() < n:
+        retire(t)
         t = _ws_cache[k] = torch.empty(max(n, 1 << 22), device=device, dtype=torch.float32)
     return t
 

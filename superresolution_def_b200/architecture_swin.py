@@ -49,6 +49,7 @@ def _rel_pos_index(wh: int, ww: int) -> torch.Tensor:
 class Mlp(nn.Module):
     def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.):
         super().__init__()
+        eng.track_weight_changes(self)
         out_features = out_features or in_features
         hidden_features = hidden_features or in_features
         self.fc1 = nn.Linear(in_features, hidden_features)
@@ -65,6 +66,7 @@ class Mlp(nn.Module):
 class WindowAttention(nn.Module):
     def __init__(self, dim, window_size, num_heads, qkv_bias=True, qk_scale=None, attn_drop=0., proj_drop=0.):
         super().__init__()
+        eng.track_weight_changes(self)
         self.dim = dim
         self.window_size = window_size
         self.num_heads = num_heads
@@ -93,6 +95,7 @@ class SwinTransformerBlock(nn.Module):
     def __init__(self, dim, input_resolution, num_heads, window_size=7, shift_size=0, mlp_ratio=4., qkv_bias=True,
                  qk_scale=None, drop=0., attn_drop=0., act_layer=nn.GELU, norm_layer=nn.LayerNorm):
         super().__init__()
+        eng.track_weight_changes(self)
         self.dim = dim
         self.input_resolution = input_resolution
         self.num_heads = num_heads
@@ -167,6 +170,7 @@ class SwinIR(nn.Module):
     def __init__(self, img_size=64, in_chans=1, embed_dim=96, depths=[6, 6, 6], num_heads=[6, 6, 6], window_size=7,
                  upscale=2, **kwargs):
         super().__init__()
+        eng.track_weight_changes(self)
         # NOTE: like the reference (:193-194) extra kwargs (mlp_ratio, img_range, upsampler, ...) are swallowed:
         # the effective MLP ratio is the block default 4.0.
         self.upscale = upscale

@@ -97,11 +97,11 @@ int launch_attn_fwd(const SrkGeom* g, int heads, const void* qkv, int ld_qkv, co
 
 int launch_attn_bwd(const SrkGeom* g, int heads, const void* qkv, int ld_qkv, const float* table, const void* dout,
                     int ld_o, void* dqkv, float* partials, int gx, cudaStream_t stream, int mask = 0) {
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.need()) {
     SRK_CUDA_OK(cudaFuncSetAttribute(win_attn_ws8_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      int(sizeof(AttnBwdSmem))));
-    configured = true;
+    configured.done();
   }
   AttnArgs a{};
   a.qkv = static_cast<const __nv_bfloat16*>(qkv);
@@ -122,11 +122,11 @@ int launch_attn_bwd(const SrkGeom* g, int heads, const void* qkv, int ld_qkv, co
 
 template <int MODE>
 int launch_attn16_fwd_t(const Attn16Args& a, cudaStream_t stream) {
-  static bool configured = false;
+  static DeviceOnce configured;
   constexpr int smem = a16_fwd_smem<MODE>();
-  if (!configured) {
+  if (configured.need()) {
     SRK_CUDA_OK(cudaFuncSetAttribute(win_attn16_fwd_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
+    configured.done();
   }
   const int nitems = a.B * (a.H / 16) * (a.W / 16) * 2;
   int gx = num_sms() * 2 / a.heads;
@@ -179,10 +179,10 @@ Attn16Ws attn16_ws_layout(const SrkGeom* g, int mode, int heads) {
 template <int MODE>
 int launch_attn16_bwd_t(Attn16Args a, void* ws, const Attn16Ws& L, float* d_table, cudaStream_t stream) {
   using SM = A16BwdSmem<MODE>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.need()) {
     SRK_CUDA_OK(cudaFuncSetAttribute(win_attn16_bwd_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
-    configured = true;
+    configured.done();
   }
   a.dbias_scratch = reinterpret_cast<float*>(static_cast<char*>(ws) + L.scratch_off);
   a.dkv_win = reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(ws) + L.dkv_off);
@@ -225,10 +225,10 @@ int attn16_fwd(const SrkGeom* g, int mode, int heads, const void* qkv, int ld_qk
   a.T = (long long)g->B * g->H * g->W;
   if (g->ws == 8) {
     if (mode == MODE_SELF) return launch_attn_fwd(g, heads, qkv, ld_qkv, table, out, ld_out, ones_col, stream, 1);
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.need()) {
       SRK_CUDA_OK(cudaFuncSetAttribute(win_attn_oca8_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, O8_FWD_SMEM));
-      configured = true;
+      configured.done();
     }
     const int nwin = g->B * (g->H / 8) * (g->W / 8);
     int gx = num_sms() * 3 / heads;
@@ -258,10 +258,10 @@ int attn16_bwd(const SrkGeom* g, int mode, int heads, const void* qkv, int ld_qk
   const Attn16Ws L = attn16_ws_layout(g, mode, heads);
   if (g->ws == 8) {
     if (mode != MODE_OCA) return fail(SRK_ERR_ARG, "attn16_bwd: the ws-8 self-attention backward runs through srk_win_attn_bwd");
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.need()) {
       SRK_CUDA_OK(cudaFuncSetAttribute(win_attn_oca8_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, O8_BWD_SMEM));
-      configured = true;
+      configured.done();
     }
     char* wsb = static_cast<char*>(ws);
     a.dbias_scratch = reinterpret_cast<float*>(wsb + L.scratch_off);

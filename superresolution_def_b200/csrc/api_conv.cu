@@ -27,11 +27,11 @@ int make_act_maps(CUtensorMap* m4, const void* ptr, int B, int H, int W, int Cp,
 template <int BN, int EPI>
 int launch_conv(const ConvMaps& maps, const ConvArgs& a, cudaStream_t stream) {
   using Cfg = ConvCfg<BN, EPI>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.need()) {
     SRK_CUDA_OK(cudaFuncSetAttribute(conv3x3_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      Cfg::kSmemBytes));
-    configured = true;
+    configured.done();
   }
   const int tiles = a.B * (a.H / CONV_TH) * (a.W / CONV_TW) * (a.Cout_p / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
@@ -44,11 +44,11 @@ int launch_conv(const ConvMaps& maps, const ConvArgs& a, cudaStream_t stream) {
 template <int BN, int EPI>
 int launch_conv_halo(const ConvMaps& maps, const ConvArgs& a, cudaStream_t stream) {
   using Cfg = HaloCfg<BN, EPI>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.need()) {
     SRK_CUDA_OK(cudaFuncSetAttribute(conv3x3_halo_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      Cfg::kSmemBytes));
-    configured = true;
+    configured.done();
   }
   const int tiles = a.B * (a.H / HALO_TH) * (a.W / HALO_TW) * (a.Cout_p / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
@@ -58,13 +58,12 @@ int launch_conv_halo(const ConvMaps& maps, const ConvArgs& a, cudaStream_t strea
   return SRK_OK;
 }
 
-// SRK_SWAP_M64: "off" = always the M = 128 instance; "h1" = M = 64 with the alternative TMEM row mapping (probe);
-// default = M = 64 for layers with <= 64 output channels
+// SRK_SWAP_M64: "off" = always the M = 128 instance; default = M = 64 for layers with <= 64 output channels
 int swap_m64_mode() {
   static int mode = -1;
   if (mode < 0) {
     const char* e = std::getenv("SRK_SWAP_M64");
-    mode = !e ? 1 : (e[0] == 'o' ? 0 : (e[0] == 'h' && e[1] == '1' ? 2 : 1));
+    mode = !e ? 1 : (e[0] == 'o' ? 0 : 1);
   }
   return mode;
 }
@@ -72,10 +71,10 @@ int swap_m64_mode() {
 template <int EPI, int MM>
 int launch_conv_swap(const ConvMaps& maps, const ConvArgs& a, cudaStream_t stream) {
   using Cfg = SwapCfg<EPI, MM>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.need()) {
     SRK_CUDA_OK(cudaFuncSetAttribute(conv3x3_swap_kernel<EPI, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    configured = true;
+    configured.done();
   }
   const int tiles = a.B * (a.H / SWP_TH) * (a.W / SWP_TW) * ((a.n_real + MM - 1) / MM);
   const int grid = tiles < num_sms() ? tiles : num_sms();
@@ -98,11 +97,11 @@ int conv_halo_mode() {
 template <int BNW>
 int launch_conv_wgrad(const ConvWgradMaps& maps, const ConvWgradArgs& a, cudaStream_t stream) {
   using Cfg = WgradCfg<BNW>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.need()) {
     SRK_CUDA_OK(cudaFuncSetAttribute(conv3x3_wgrad_kernel<BNW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      Cfg::kSmemBytes));
-    configured = true;
+    configured.done();
   }
   conv3x3_wgrad_kernel<BNW><<<a.co_tiles * 9 * a.splits, WG_THREADS, Cfg::kSmemBytes, stream>>>(maps, a);
   SRK_LAUNCHED(1);
@@ -349,7 +348,7 @@ extern "C" int srk_conv3x3_igemm_v(int epi, int B, int H, int W, int Cin_p, int 
     if ((rc = make_tmap_2d(&maps.w, wk, Cout_p, 9 * (uint64_t)Cin_p, 9 * (uint64_t)Cin_p, use64 ? 64 : 128))) return rc;
     ConvArgs a{};
     a.B = B; a.H = H; a.W = W; a.Cin_p = Cin_p; a.Cout_p = Cout_p; a.n_real = n_real; a.bias = bias; a.slope = slope;
-    a.alpha = alpha; a.c_split = (m64 == 2);
+    a.alpha = alpha; a.c_split = 0;
     if (use64) {
       switch (epi) {
         case CEPI_BIAS: return launch_conv_swap<CEPI_BIAS, 64>(maps, a, stream);
@@ -395,8 +394,6 @@ extern "C" int srk_conv3x3_igemm_v(int epi, int B, int H, int W, int Cin_p, int 
   a.a_split = 0; a.c_split = 0; a.alpha = alpha;
   a.y32 = out1 ? y32 : nullptr;
   if (halo) {
-    a.c_split = (hmode == 4);  // timing probe: skip halo loads after the first tile (results are garbage)
-    a.a_split = (hmode == 2);  // probe switch: 2 = descriptors WITH the matrix base offset kx (documented as wrong on B200)
 #define SRK_HCASE(BN_, EPI_) if (bn == BN_ && epi == EPI_) return launch_conv_halo<BN_, EPI_>(maps, a, stream);
     SRK_HCASE(32, CEPI_BIAS) SRK_HCASE(32, CEPI_BIAS_LRELU)
     SRK_HCASE(64, CEPI_BIAS) SRK_HCASE(128, CEPI_BIAS) SRK_HCASE(192, CEPI_BIAS) SRK_HCASE(256, CEPI_BIAS)
@@ -430,11 +427,11 @@ extern "C" int srk_conv3x3_wgrad_v(int B, int H, int W, int Cin, int Cout, int C
     if ((rc = view_map(&tm.dy, dy, B, H, W, 16, 4))) return rc;
     if ((rc = view_map(&tm.x, x, B, H, W, 18, 6))) return rc;
     const int nco = Cout <= 32 ? 32 : 48;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.need()) {
       SRK_CUDA_OK(cudaFuncSetAttribute(conv3x3_wgrad_thin_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM));
       SRK_CUDA_OK(cudaFuncSetAttribute(conv3x3_wgrad_thin_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM));
-      configured = true;
+      configured.done();
     }
     ConvWgradThinArgs t{};
     t.B = B; t.H = H; t.W = W; t.ci_tiles = (Cin_p + 127) / 128;

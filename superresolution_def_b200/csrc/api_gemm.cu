@@ -12,11 +12,11 @@ static int launch_gemm_tn(const GemmArgs& a, const CUtensorMap& tA, const CUtens
                           const CUtensorMap& tC2, const CUtensorMap& tX1, const CUtensorMap& tX2,
                           cudaStream_t stream) {
   using Cfg = GemmCfg<BN, EPI>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.need()) {
     SRK_CUDA_OK(cudaFuncSetAttribute(gemm_tn_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      Cfg::kSmemBytes));
-    configured = true;
+    configured.done();
   }
   const int tiles = (a.M / GEMM_BM) * (a.N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
@@ -116,11 +116,11 @@ extern "C" int srk_gemm_tn(int epi, int M, int N, int K, const void* A, int lda,
 template <int BNW>
 static int launch_wgrad(const WgradArgs& a, const CUtensorMap& tA, const CUtensorMap& tB, cudaStream_t stream) {
   using Cfg = WgradCfg<BNW>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.need()) {
     SRK_CUDA_OK(cudaFuncSetAttribute(gemm_wgrad_kernel<BNW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      Cfg::kSmemBytes));
-    configured = true;
+    configured.done();
   }
   SRK_CUDA_OK(launch_pdl(gemm_wgrad_kernel<BNW>, dim3(a.ca_tiles * a.splits), dim3(WG_THREADS), Cfg::kSmemBytes, stream, tA,
                          tB, a));
@@ -129,9 +129,11 @@ static int launch_wgrad(const WgradArgs& a, const CUtensorMap& tA, const CUtenso
   return SRK_OK;
 }
 
-extern "C" int srk_gemm_wgrad_dbg(int T, int Ca, int Cb, const void* A, int lda, const void* B, int ldb,
-                                  float* workspace, int splits, float* out, int lbo_bytes, int sbo_bytes,
-                                  void* stream_) {
+// MN-major, 128B swizzle: LBO = distance between 64-channel groups (one [64 tok x 128 B] box),
+// SBO = distance between 8-token groups (8 rows x 128 B); validated on hardware in round 1.
+static int gemm_wgrad_impl(int T, int Ca, int Cb, const void* A, int lda, const void* B, int ldb,
+                           float* workspace, int splits, float* out, int lbo_bytes, int sbo_bytes,
+                           void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (splits <= 0 || T <= 0 || T % WG_TOK != 0 || splits > T / WG_TOK)
     return fail(SRK_ERR_ARG, "srk_gemm_wgrad: T must be a multiple of 64 and 1 <= splits <= T/64");
@@ -160,7 +162,5 @@ extern "C" int srk_gemm_wgrad_dbg(int T, int Ca, int Cb, const void* A, int lda,
 
 extern "C" int srk_gemm_wgrad(int T, int Ca, int Cb, const void* A, int lda, const void* B, int ldb,
                               float* workspace, int splits, float* out, void* stream) {
-  // MN-major, 128B swizzle: LBO = distance between 64-channel groups (one [64 tok x 128 B] box),
-  // SBO = distance between 8-token groups (8 rows x 128 B).
-  return srk_gemm_wgrad_dbg(T, Ca, Cb, A, lda, B, ldb, workspace, splits, out, WG_SUBBOX, 1024, stream);
+  return gemm_wgrad_impl(T, Ca, Cb, A, lda, B, ldb, workspace, splits, out, WG_SUBBOX, 1024, stream);
 }

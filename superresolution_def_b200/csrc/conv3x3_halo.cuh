@@ -11,7 +11,7 @@
 //   tap (ky,kx)  descriptor start = tile + ((ky*16 + kx) * 128) B, SBO = 2048 B (next image row).  The start is not
 //                1024-byte aligned any more; measured on B200: the UMMA unit applies the 128B swizzle to the absolute
 //                shared-memory address (as TMA does when it writes the tile), so the descriptor's matrix-base-offset
-//                field must stay 0 — setting it to kx produces wrong results (tests/test_hybrid_gpu.py under SRK_CONV_HALO=2).
+//                field must stay 0 — setting it to kx produced wrong results (round-1 probe, since removed from the library).
 // Weights stream through their own ring, one [BN x 64] box per (chunk, tap).  Epilogues as conv3x3_kernel.
 #pragma once
 #include "conv3x3.cuh"
@@ -112,9 +112,7 @@ conv3x3_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) 
         tile_coords(tile, b, y0, x0, n0);
         for (int kc = 0; kc < kc_per_tap; ++kc) {
           mbar_wait(empty_bar(as), aph ^ 1u);
-          if (args.c_split && tile != int(blockIdx.x)) {
-            mbar_arrive(full_bar(as));   // timing probe (SRK_CONV_HALO=4): no halo loads after the first tile, stale data
-          } else {
+          {
             mbar_arrive_expect_tx(full_bar(as), HALO_A_BYTES);
             // three boxes of 6 image rows each (same bytes as one 18-row box; no measurable difference on B200)
 #pragma unroll
@@ -153,7 +151,7 @@ conv3x3_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) 
             tc_fence_after();
             const uint32_t a0 = sa + uint32_t(ky * HALO_BW + kx) * 128u;
             const uint32_t sb = w_base + ws * Cfg::kWBytes;
-            const uint32_t bo = args.a_split ? uint32_t(kx) : 0u;   // a_split = probe switch (SRK_CONV_HALO=2): wrong on B200
+            const uint32_t bo = 0u;   // matrix base offset stays 0: the 128B swizzle is applied to absolute smem addresses
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               umma_bf16(d_tmem, make_smem_desc_bo(a0 + k * 32, 16, HALO_BW * 128, bo), make_smem_desc(sb + k * 32, 16, 1024),

@@ -28,8 +28,8 @@ constexpr int SWP_B_STAGES = 2;
 
 // MM = 128: one weight tile covers 128 output channels (two 64-channel boxes per pixel group).
 // MM = 64 : layers with <= 64 output channels; the M = 64 instruction streams half the A tile.  Its accumulator rows
-//           live in TMEM lanes 0-15 of each 32-lane quarter (row r -> lane 32*(r/16) + r%16; probed on B200,
-//           SRK_SWAP_M64=h1 selects the other hypothesis r -> lane r), so 16 lanes per epilogue warp carry data.
+//           live in TMEM lanes 0-15 of each 32-lane quarter (row r -> lane 32*(r/16) + r%16; probed on B200 in
+//           round 1 against the alternative r -> lane r, which fails parity), so 16 lanes per epilogue warp carry data.
 template <int EPI, int MM>
 struct SwapCfg {
   static constexpr bool kAux = (EPI == CEPI_BIAS_RES || EPI == CEPI_MASK_LRELU);
@@ -153,7 +153,6 @@ conv3x3_swap_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) 
     // accumulator row (= output channel within the tile) held by this thread's TMEM lane, or -1
     int row;
     if (MM == 128) row = q * 32 + lane;
-    else if (args.c_split) row = (q < 2) ? q * 32 + lane : -1;          // hypothesis h1: row r -> lane r
     else row = (lane < 16) ? q * 16 + lane : -1;                        // row r -> lane 32*(r/16) + r%16
     const int cbox = (row < 0) ? -1 : (row >> 6);   // which 64-channel box this row belongs to
     const int cc = row & 63;                        // channel inside the box

@@ -123,15 +123,25 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
 }
 
+// Function attributes (cudaFuncAttributeMaxDynamicSharedMemorySize) and the SM count are per device: a process that
+// touches a second GPU (tiled inference across devices without torchrun) must configure each kernel there too.
+struct DeviceOnce {
+  std::atomic<unsigned long long> mask{0};
+  static int cur() { int d = 0; cudaGetDevice(&d); return d & 63; }
+  bool need() const { return ((mask.load(std::memory_order_acquire) >> cur()) & 1ull) == 0; }
+  void done() { mask.fetch_or(1ull << cur(), std::memory_order_release); }
+};
+
 inline int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static std::atomic<int> n[64];
+  const int dev = DeviceOnce::cur();
+  int v = n[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (v <= 0) v = 148;
+    n[dev].store(v, std::memory_order_relaxed);
   }
-  return n;
+  return v;
 }
 
 }  // namespace srk

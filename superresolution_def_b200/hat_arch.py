@@ -64,6 +64,7 @@ class ChannelAttention(nn.Module):
 class CAB(nn.Module):
     def __init__(self, num_feat, compress_ratio=3, squeeze_factor=30):
         super().__init__()
+        eng.track_weight_changes(self)
         self.cab = nn.Sequential(nn.Conv2d(num_feat, num_feat // compress_ratio, 3, 1, 1), nn.GELU(),
                                  nn.Conv2d(num_feat // compress_ratio, num_feat, 3, 1, 1),
                                  ChannelAttention(num_feat, squeeze_factor))
@@ -80,6 +81,7 @@ class CAB(nn.Module):
 class WindowAttention(nn.Module):
     def __init__(self, dim, window_size, num_heads, qkv_bias=True, qk_scale=None, attn_drop=0., proj_drop=0.):
         super().__init__()
+        eng.track_weight_changes(self)
         self.dim = dim
         self.window_size = window_size
         self.num_heads = num_heads
@@ -114,6 +116,7 @@ class HAB(nn.Module):
                  conv_scale=0.01, mlp_ratio=4., qkv_bias=True, qk_scale=None, drop=0., attn_drop=0., drop_path=0.,
                  act_layer=nn.GELU, norm_layer=nn.LayerNorm):
         super().__init__()
+        eng.track_weight_changes(self)
         self.dim = dim
         self.input_resolution = input_resolution
         self.num_heads = num_heads
@@ -168,6 +171,7 @@ class OCAB(nn.Module):
     def __init__(self, dim, input_resolution, window_size, overlap_ratio, num_heads, qkv_bias=True, qk_scale=None,
                  mlp_ratio=2, norm_layer=nn.LayerNorm):
         super().__init__()
+        eng.track_weight_changes(self)
         self.dim = dim
         self.input_resolution = input_resolution
         self.window_size = window_size
@@ -314,6 +318,7 @@ class HAT(nn.Module):
                  norm_layer=nn.LayerNorm, ape=False, patch_norm=True, use_checkpoint=False, upscale=2, img_range=1.,
                  upsampler='', resi_connection='1conv', **kwargs):
         super().__init__()
+        eng.track_weight_changes(self)
         self.window_size = window_size
         self.shift_size = window_size // 2
         self.overlap_ratio = overlap_ratio

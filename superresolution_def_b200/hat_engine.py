@@ -54,6 +54,7 @@ def _attn_ws(geom, mode, heads, device):
     k = (mode, str(device))
     t = _attn_ws_cache.get(k)
     if t is None or t.numel() < n:
+        capi.retire(t)   # grow-only: a captured graph may still address the old buffer
         t = _attn_ws_cache[k] = torch.empty(n, device=device, dtype=torch.uint8)
     return t
 
@@ -107,19 +108,28 @@ class HatBlockFunction(torch.autograd.Function):
             capi.hat_block_fwd(dims, g, weights, pdict, nw, nb, acts, capi.ATTN_OCA, x, lse)
         else:
             raise capi.SrkError(f"unknown HAT block kind {kind!r}")
+        outs = (acts["x_out"], acts["xn_out"], acts["stats_out"])
         if need_grad:
-            ctx.saved = (acts, lse, extra)
+            # the node's own outputs are not needed by its backward: keeping them on ctx would close an
+            # output -> grad_fn -> ctx -> output reference cycle
+            keep = {k: v for k, v in acts.items() if k not in ("x_out", "xn_out", "stats_out")}
+            ctx.saved = (keep, lse, extra, weights)
             ctx.meta = (cfg, geom, kind, shift, float(conv_scale), drop)
             ctx.params = tensors
-        ctx.mark_non_differentiable(acts["xn_out"], acts["stats_out"])
+        ctx.mark_non_differentiable(outs[1], outs[2])
         ctx.set_materialize_grads(False)
-        return acts["x_out"], acts["xn_out"], acts["stats_out"]
+        return outs
 
     @staticmethod
     def backward(ctx, g_x, _g_xn, _g_stats):
-        acts, lse, extra = ctx.saved
-        cfg, (B, H, W), kind, shift, conv_scale, drop = ctx.meta
         tensors = ctx.params
+        if g_x is None:   # the block's output did not reach the loss
+            return (None,) * (9 + len(tensors))
+        if ctx.saved is None:
+            raise capi.SrkError("HatBlockFunction.backward ran twice: saved activations are released by the first "
+                                "backward (retain_graph / double backward is not supported)")
+        acts, lse, extra, weights = ctx.saved
+        cfg, (B, H, W), kind, shift, conv_scale, drop = ctx.meta
         T = B * H * W
         dev = g_x.device
         dims = cfg.dims()
@@ -128,7 +138,6 @@ class HatBlockFunction(torch.autograd.Function):
             g = g.to(BF16)
         params = [t.detach() for t in tensors[:13]]
         pdict = dict(zip(capi.PARAM_NAMES, params))
-        weights = eng._weight_caches[(cfg, params[3].data_ptr())].t  # prepared by this step's forward
         scratch = eng._bwd_scratch(cfg, B, H, W, dev)
         geom = capi.SrkGeom(B, H, W, cfg.ws, shift)
         gdict = {n: torch.empty_like(p) for n, p in zip(capi.PARAM_NAMES, params)}

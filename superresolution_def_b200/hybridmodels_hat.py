@@ -15,6 +15,7 @@ import torch.nn as nn
 
 from . import _capi as capi
 from . import hybrid_engine as hyb
+from . import swin_engine as eng
 from .hat_arch import HAT
 
 RDB_KEYS = tuple(f"conv{i}.{s}" for i in range(1, 6) for s in ("weight", "bias"))
@@ -70,6 +71,7 @@ class HybridHATRealESRGAN(nn.Module):
     def __init__(self, img_size=128, in_chans=1, embed_dim=180, depths=(6, 6, 6, 6, 6, 6), num_heads=(6, 6, 6, 6, 6, 6),
                  window_size=8, upscale=4, num_rrdb=23, num_feat=64, num_grow_ch=32):
         super().__init__()
+        eng.track_weight_changes(self)
         self.upscale = upscale
         self.img_size = img_size
         if in_chans != 1 or upscale != 4:

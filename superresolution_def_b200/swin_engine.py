@@ -79,16 +79,32 @@ class _WeightCache:
         elems = capi.block_weight_elems(cfg.dims())
         self.t = {n: torch.empty(e, device=device, dtype=BF16) for n, e in zip(capi.WEIGHT_NAMES, elems)}
         self.ready = False
+        self.epoch = -1
 
     def get(self, params: list[torch.Tensor], refresh: bool) -> dict:
-        if refresh or not self.ready or not _frozen:
+        if refresh or not self.ready or not _frozen or self.epoch != _epoch:
             capi.block_prep_weights(self.cfg.dims(), dict(zip(capi.PARAM_NAMES, params)), self.t)
             self.ready = True
+            self.epoch = _epoch
         return self.t
 
 
 _weight_caches: dict = {}
 _frozen = False
+_epoch = 0   # bumped whenever a mirror module is built or loads a state_dict: frozen operands older than that are stale
+
+
+def weights_changed(*_a, **_k):
+    """Invalidate every frozen bf16 operand copy.  The caches are keyed by parameter address, and an address can be
+    recycled by a model built after another one was freed, so the mirrors call this from __init__ and from their
+    load_state_dict post-hook; training never relies on it (operands are re-derived in every forward)."""
+    global _epoch
+    _epoch += 1
+
+
+def track_weight_changes(module: torch.nn.Module):
+    weights_changed()
+    module.register_load_state_dict_post_hook(weights_changed)
 
 
 def freeze_weights(flag: bool = True):
@@ -160,7 +176,7 @@ class SwinStackFunction(torch.autograd.Function):
         assert x.dtype == BF16 and x.shape == (T, cfg.Cp) and x.is_contiguous() and xn.is_contiguous()
         need_grad = any(ctx.needs_input_grad)  # grad mode is always off inside Function.forward
         dims = cfg.dims()
-        saved = []
+        saved, saved_w = [], []
         cur_x, cur_xn, cur_stats = x, xn, stats
         # inference: two activation sets are ping-ponged (block i reads set i-1's outputs while writing set i)
         pingpong = None if need_grad else [_alloc_acts(cfg, T, x.device) for _ in range(min(nb, 2))]
@@ -177,8 +193,13 @@ class SwinStackFunction(torch.autograd.Function):
             capi.swin_block_fwd(dims, g, weights, dict(zip(capi.PARAM_NAMES, params)), nw, nbias, acts)
             if need_grad:
                 saved.append(acts)
+                saved_w.append(weights)
             cur_x, cur_xn, cur_stats = acts["x_out"], acts["xn_out"], acts["stats_out"]
-        ctx.cfg, ctx.geom, ctx.shifts, ctx.saved_acts = cfg, geom, shifts, saved
+        if saved:
+            # the node's own outputs are not needed by its backward; keeping them on ctx would close an
+            # output -> grad_fn -> ctx -> output cycle that only the cyclic GC could free (tens of GB per abandoned graph)
+            saved[-1] = {k: v for k, v in saved[-1].items() if k not in ("x_out", "xn_out", "stats_out")}
+        ctx.cfg, ctx.geom, ctx.shifts, ctx.saved_acts, ctx.saved_w = cfg, geom, shifts, saved, saved_w
         ctx.params = tensors
         ctx.mark_non_differentiable(cur_xn, cur_stats)
         ctx.set_materialize_grads(False)
@@ -188,6 +209,11 @@ class SwinStackFunction(torch.autograd.Function):
     def backward(ctx, g_x, _g_xn, _g_stats):
         cfg, (B, H, W), shifts, tensors = ctx.cfg, ctx.geom, ctx.shifts, ctx.params
         T = B * H * W
+        if g_x is None:   # set_materialize_grads(False): the stack's output did not reach the loss
+            return (None,) * (6 + len(tensors))
+        if ctx.saved_acts and ctx.saved_acts[-1] is None:
+            raise capi.SrkError("SwinStackFunction.backward ran twice: the saved activations are released block by block "
+                                "during the first backward (retain_graph / double backward is not supported)")
         dev = g_x.device
         dims = cfg.dims()
         nb = len(shifts)
@@ -199,7 +225,7 @@ class SwinStackFunction(torch.autograd.Function):
         bufs = [torch.empty(T, cfg.Cp, device=dev, dtype=BF16), torch.empty(T, cfg.Cp, device=dev, dtype=BF16)]
         for i in reversed(range(nb)):
             params = [t.detach() for t in tensors[i * N_BLOCK_PARAMS:(i + 1) * N_BLOCK_PARAMS]]
-            weights = _weight_caches[(cfg, params[3].data_ptr())].t  # prepared by this step's forward
+            weights = ctx.saved_w[i]  # the operand buffers this step's forward prepared
             acts = ctx.saved_acts[i]
             gdict = {n: torch.empty_like(p) for n, p in zip(capi.PARAM_NAMES, params)}
             g_in = bufs[i & 1]
@@ -226,7 +252,8 @@ def _bwd_scratch(cfg: BlockCfg, B: int, H: int, W: int, device) -> dict:
              "d_qkv": torch.empty(T, cfg.QW, device=device, dtype=BF16),
              "g_mid": torch.empty(T, cfg.Cp, device=device, dtype=BF16),
              "wg_ws": torch.empty(n, device=device, dtype=torch.float32)}
-        _scratch_cache.clear()  # one geometry at a time keeps the scratch footprint bounded
+        # one entry per geometry, never evicted: a captured CUDA graph (graphs.GraphedStep) has these addresses baked
+        # into its kernel nodes, so a validation pass at another batch size must not free the training step's scratch
         _scratch_cache[key] = s
     return s
 

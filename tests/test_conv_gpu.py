@@ -1,13 +1,14 @@
 """-m gpu parity tests of the convolutional head/tail kernels against plain torch fp32 on the same (bf16-rounded)
-inputs.  Tolerances: outputs rel-L2 <= 1e-2, gradients rel-L2 <= 8e-2.  The gradient figure is dominated by LeakyReLU sign
-flips: a pre-activation within bf16 rounding distance of zero (~0.2 % of them) gets slope 0.01 instead of 1 on one side of
-the comparison, i.e. a relative error of ~1 on that element => sqrt(0.002) ~ 4.5 % rel-L2 upstream of conv_before_upsample;
-layers after the LeakyReLU agree to <= 5e-3 (asserted separately)."""
+inputs.  Tolerances: outputs rel-L2 <= 1e-2; every gradient tensor within 1.6x (+5e-3) of the error the same ATen sequence
+makes under bf16 autocast (the reference's training arithmetic), rel-L2 and max-abs.  Gradients upstream of
+conv_before_upsample are dominated by LeakyReLU sign flips (a pre-activation within bf16 rounding distance of zero gets slope
+0.01 instead of 1 on one side of the comparison) — the autocast run has the same flips, which is why it is the yardstick
+rather than a blanket bound; layers after the LeakyReLU agree to <= 1e-2 (asserted separately)."""
 import pytest
 import torch
 import torch.nn.functional as F
 
-from tests.util import rel_l2
+from tests.util import rel_l2, max_abs
 
 pytestmark = pytest.mark.gpu
 
@@ -36,23 +37,45 @@ def test_tail_matches_torch(B, H, W):
 
     def nchw(t):
         return t.float()[:, :C].reshape(B, H, W, C).permute(0, 3, 1, 2)
-    br, fr = body.float().clone().requires_grad_(True), first.float().clone().requires_grad_(True)
-    x = F.conv2d(nchw(br), ref[0], ref[1], padding=1) + nchw(fr)
-    x = F.leaky_relu(F.conv2d(x, ref[2], ref[3], padding=1), 0.01)
-    x = F.pixel_shuffle(F.conv2d(x, ref[4], ref[5], padding=1), 2)
-    x = F.pixel_shuffle(F.conv2d(x, ref[6], ref[7], padding=1), 2)
-    ro = F.conv2d(x, ref[8], ref[9], padding=1)
+
+    w = None
+
+    def run_ref(autocast):
+        """The reference's ATen sequence (architecture_swin.py:249-255) in fp32, or under the bf16 autocast the scripts
+        train with: the latter's distance to fp32 calibrates the per-tensor bound (LeakyReLU sign flips included)."""
+        nonlocal w
+        ps = [t.detach().clone().requires_grad_(True) for t in ws]
+        br, fr = body.float().clone().requires_grad_(True), first.float().clone().requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            x = F.conv2d(nchw(br), ps[0], ps[1], padding=1) + nchw(fr)
+            x = F.leaky_relu(F.conv2d(x, ps[2], ps[3], padding=1), 0.01)
+            x = F.pixel_shuffle(F.conv2d(x, ps[4], ps[5], padding=1), 2)
+            x = F.pixel_shuffle(F.conv2d(x, ps[6], ps[7], padding=1), 2)
+            ro = F.conv2d(x, ps[8], ps[9], padding=1)
+        if w is None:
+            w = torch.randn_like(ro.float())
+        (ro.float() * w).sum().backward()
+        g = {i: p.grad for i, p in enumerate(ps)}
+        g["body"], g["first"] = br.grad[:, :C], fr.grad[:, :C]
+        return ro.float().detach(), g
+
+    ro, g32 = run_ref(False)
+    r16, g16 = run_ref(True)
     assert out.shape == ro.shape
-    assert rel_l2(out, ro) < 1e-2, rel_l2(out, ro)
-    w = torch.randn_like(ro)
+    assert rel_l2(out, ro) < 1e-2 and rel_l2(out, ro) < 1.6 * rel_l2(r16, ro) + 2e-3, (rel_l2(out, ro), rel_l2(r16, ro))
+    assert max_abs(out, ro) < 3 * max_abs(r16, ro) + 1e-3 * ro.abs().max().item(), (max_abs(out, ro), max_abs(r16, ro))
     (out * w).sum().backward()
-    (ro * w).sum().backward()
-    errs = {i: rel_l2(a.grad, b.grad) for i, (a, b) in enumerate(zip(mine, ref))}
-    errs["body"] = rel_l2(bm.grad[:, :C], br.grad[:, :C])
-    errs["first"] = rel_l2(fm.grad[:, :C], fr.grad[:, :C])
-    print({k: round(v, 4) for k, v in errs.items()})
-    assert all(v < 8e-2 for v in errs.values()), str({k: round(v, 4) for k, v in errs.items()})
-    assert all(errs[i] < 1e-2 for i in range(4, 10)), str({k: round(v, 4) for k, v in errs.items()})
+    gm = {i: a.grad for i, a in enumerate(mine)}
+    gm["body"], gm["first"] = bm.grad[:, :C], fm.grad[:, :C]
+    errs = {k: (rel_l2(gm[k], g32[k]), rel_l2(g16[k], g32[k])) for k in gm}
+    print({k: (round(a, 4), round(b, 4)) for k, (a, b) in errs.items()})
+    # per tensor: within 1.6x (+5e-3) of what the reference's own bf16-autocast arithmetic delivers for that tensor
+    bad = {k: v for k, v in errs.items() if v[0] > 1.6 * v[1] + 5e-3}
+    assert not bad, str(bad)
+    for k in gm:
+        scale = g32[k].abs().max().item()
+        assert max_abs(gm[k], g32[k]) < 3 * max_abs(g16[k], g32[k]) + 2e-2 * scale, (k, max_abs(gm[k], g32[k]), scale)
+    assert all(errs[i][0] < 1e-2 for i in range(4, 10)), str(errs)
     assert bm.grad[:, C:].abs().max() == 0 and fm.grad[:, C:].abs().max() == 0
 
 

@@ -46,8 +46,14 @@ def _check_forward(net, oracle_fn, lr, hr, what):
         got = net(lr)
     assert got.shape == ref.shape == hr.shape
     e, e16 = rel_l2(got, ref), rel_l2(r16, ref)
-    msg = f"{what}: rel-L2 {e:.4f} (oracle under bf16 autocast {e16:.4f}), max-abs {max_abs(got, ref):.4f}"
+    ma, ma16 = max_abs(got, ref), max_abs(r16, ref)
+    msg = (f"{what}: rel-L2 {e:.4f} (oracle under bf16 autocast {e16:.4f}), max-abs {ma:.4f} (autocast oracle {ma16:.4f}) "
+           f"on outputs of scale {ref.abs().max().item():.3f}")
     assert e < 3e-2 and e < 2 * e16 + 5e-3, msg
+    # max-abs (north_star's second tolerance): the worst single pixel is a tail statistic of ~1.3e5 outputs, so it is
+    # bounded against the same statistic of the reference's own bf16-autocast arithmetic (x3) and, absolutely, against
+    # 10 % of the output range
+    assert ma < 3 * ma16 + 5e-3 and ma < 0.1 * max(1.0, ref.abs().max().item()), msg
     dp = abs(_psnr(got, hr) - _psnr(ref, hr))
     assert dp < 0.1, f"{msg}; PSNR delta {dp:.3f} dB"
     print(msg, f"PSNR delta {dp:.4f} dB")
@@ -115,3 +121,76 @@ def test_swinir_full_train_step_batch_linearity():
     assert rel_l2(cat(g_all), cat(half)) < 2e-2, rel_l2(cat(g_all), cat(half))
     worst = max(rel_l2(x, y) for x, y in zip(g_all, half) if y.norm() > 1e-6)
     assert worst < 6e-2, worst
+
+
+def _grad_parity(net, oracle_fn, lr, hr, what, per_tensor=1.6, slack=2e-2):
+    """Every parameter gradient of the full-size model against the fp32 oracle on the same device.  Per tensor the error
+    is bounded relative to the error of the oracle itself under bf16 autocast (the reference's training arithmetic):
+    rel-L2(ours) <= per_tensor * rel-L2(autocast oracle) + slack, and max-abs(ours) <= 3 * max-abs(autocast) + 2 % of the
+    gradient tensor's own largest entry.  Returns the worst cases for the log."""
+    def run_oracle(autocast):
+        sd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in net.state_dict().items()}
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            out = oracle_fn(lr, sd)
+        torch.nn.functional.l1_loss(out.float(), hr).backward()
+        return out.detach(), {k: v.grad for k, v in sd.items() if v.grad is not None}
+
+    ref, g32 = run_oracle(False)
+    r16, g16 = run_oracle(True)
+    net.zero_grad(set_to_none=True)
+    got = net(lr)
+    torch.nn.functional.l1_loss(got.float(), hr).backward()
+    e, e16 = rel_l2(got, ref), rel_l2(r16, ref)
+    assert e < 3e-2 and e < 2 * e16 + 5e-3, (what, e, e16)
+    bad, worst_rel, worst_abs = {}, (0.0, ""), (0.0, "")
+    cat_m, cat_r, cat_a = [], [], []
+    for n, p in net.named_parameters():
+        r = g32[n]
+        mine, auto = rel_l2(p.grad, r), rel_l2(g16[n], r)
+        ma, ma16, scale = max_abs(p.grad, r), max_abs(g16[n], r), r.abs().max().item()
+        cat_m.append(p.grad.flatten().float()); cat_r.append(r.flatten().float()); cat_a.append(g16[n].flatten().float())
+        worst_rel = max(worst_rel, (mine, f"{n} (autocast {auto:.4f})"))
+        worst_abs = max(worst_abs, (ma / (scale + 1e-12), f"{n} max-abs {ma:.3e} of scale {scale:.3e}"))
+        if mine > per_tensor * auto + slack or ma > 3 * ma16 + 2e-2 * scale + 1e-9:
+            bad[n] = dict(rel=round(mine, 4), rel_autocast=round(auto, 4), max_abs=ma, max_abs_autocast=ma16, scale=scale)
+    tot, tot16 = rel_l2(torch.cat(cat_m), torch.cat(cat_r)), rel_l2(torch.cat(cat_a), torch.cat(cat_r))
+    print(f"{what}: gradient rel-L2 over all parameters {tot:.4f} (autocast oracle {tot16:.4f}); worst tensor {worst_rel[0]:.4f} "
+          f"{worst_rel[1]}; worst max-abs/scale {worst_abs[0]:.4f} {worst_abs[1]}; output rel-L2 {e:.4f} ({e16:.4f})")
+    assert not bad, (what, bad)
+    assert tot < 1.6 * tot16 + 1e-2, (what, tot, tot16)
+
+
+def test_swinir_full_gradients_vs_oracle():
+    """BASELINE configs[1] at the script configuration (36 blocks, embed_dim 180), batch 2 of 128^2 -> 512^2, L1 loss:
+    all 437 parameter gradients against the fp32 oracle (not only the self-consistency identity below)."""
+    from oracle import swinir_oracle as o
+    from superresolution_def_b200.architecture_swin import SwinIR
+    torch.manual_seed(0)
+    kw = dict(img_size=128, window_size=8, depths=[6] * 6, num_heads=[6] * 6)
+    net = _tables(SwinIR(upscale=4, in_chans=1, embed_dim=180, mlp_ratio=2, **kw)).cuda().train()
+    lr, hr = _pairs(2)
+    _grad_parity(net, lambda x, sd: o.swinir_forward(x, sd, upscale=4, **kw), lr, hr, "SwinIR x4 full, B=2")
+
+
+def test_hat_full_gradients_vs_oracle():
+    """BASELINE configs[2] (window 16, OCAB, CAB, 6 x 6 HAB), batch 1, eval mode so that stochastic depth is off on both
+    sides: every parameter gradient against the fp32 oracle."""
+    from oracle import hat_oracle as ho
+    from superresolution_def_b200.hat_arch import HAT
+    torch.manual_seed(0)
+    kw = dict(window_size=16, depths=(6,) * 6, num_heads=(6,) * 6)
+    net = _tables(HAT(img_size=128, in_chans=1, embed_dim=180, upscale=4, upsampler="pixelshuffle", **kw)).cuda().eval()
+    lr, hr = _pairs(1)
+    _grad_parity(net, lambda x, sd: ho.hat_forward(x, sd, upscale=4, **kw), lr, hr, "HAT x4 full, B=1")
+
+
+def test_hybrid_full_gradients_vs_oracle():
+    """The generator train_hat.py:132-136 trains, batch 1: every parameter gradient against the fp32 oracle."""
+    from oracle import hat_oracle as ho
+    from superresolution_def_b200.hybridmodels_hat import HybridHATRealESRGAN
+    torch.manual_seed(0)
+    kw = dict(window_size=8, depths=(6,) * 4, num_heads=(6,) * 4)
+    net = _tables(HybridHATRealESRGAN(img_size=128, in_chans=1, embed_dim=90, upscale=4, num_rrdb=12, num_feat=48,
+                                      num_grow_ch=24, **kw)).cuda().eval()
+    lr, hr = _pairs(1)
+    _grad_parity(net, lambda x, sd: ho.hybrid_forward(x, sd, num_rrdb=12, **kw), lr, hr, "HybridHAT x4 full, B=1")

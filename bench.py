@@ -526,7 +526,14 @@ def run_ours(args):
                                               "the GPU arm's batch is 16: same model and patch shape, smaller batch"}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # The step graph holds captured NCCL kernels; tearing the communicator down underneath it made
+        # destroy_process_group() block until the NCCL watchdog fired (observed on 2 x B200).  Everything is measured and
+        # printed at this point: synchronise, flush and leave without running the communicator's destructor.
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

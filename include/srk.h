@@ -68,6 +68,16 @@ int srk_gemm_grid(int M, int N);
 int srk_gemm_wgrad(int T, int Ca, int Cb, const void* A, int lda, const void* B, int ldb, float* workspace,
                    int splits, float* out, void* stream);
 
+/* Fused MLP half of a block, forward: x_out = resid + drop * fc2(gelu(fc1(xn2))), xn_out = LayerNorm_next(x_out), in ONE
+ * tcgen05 kernel — the hidden activation goes from the fc1 accumulator (TMEM) through GELU into shared-memory boxes that
+ * are the A operand of fc2; it is written to HBM (act = gelu(u), dact = gelu'(u), both [T,Hp]) only when the pointers are
+ * given (training).  Replaces Mlp.forward + residual + norm: architecture_swin.py:19-25,149-150,127; hat_arch.py:76-96,306.
+ * xn2, resid, x_out, xn_out: [T,Cp] bf16; w1 = prepared fc1 operand [Hp,Cp], w2 = prepared fc2 operand [Cp,Hp];
+ * T % 128 == 0, Cp == 192, Hp % 128 == 0; ln = the next LayerNorm (gamma, beta, stats, eps, row_scale as in SRK_EPI_RES_LN);
+ * hid_ones_col = column of act forced to 1.0 (bias column of fc2).  act / dact may be NULL (inference). */
+int srk_mlp_fwd(int T, int Cp, int Hp, const void* xn2, const void* w1, const void* w2, const void* resid, void* act,
+                void* dact, void* x_out, void* xn_out, int hid_ones_col, const SrkLnArgs* ln, void* stream);
+
 /* ======================================================================================================
  * Swin / HAT transformer-block level API (what the mirrored nn.Modules call).
  * ====================================================================================================== */

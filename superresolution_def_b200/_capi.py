@@ -57,6 +57,9 @@ _gemm_grid = _sig("srk_gemm_grid", [c_int, c_int])
 _gemm_wgrad = _sig("srk_gemm_wgrad", [c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
                                        c_void_p, c_void_p])
 
+_mlp_fwd = _sig("srk_mlp_fwd", [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_int, POINTER(SrkLnArgs), c_void_p])
+
 EPI_STORE, EPI_GELU2, EPI_MUL, EPI_RES_LN, EPI_LNBWD, EPI_GELU1, EPI_MULG = range(7)
 
 
@@ -113,6 +116,18 @@ def make_ln_args(n_real, ones_col, gamma, beta=None, stats=None, partials=None, 
         assert t is None or (t.dtype == torch.float32 and t.is_contiguous())
     return SrkLnArgs(n_real, ones_col, _ptr(gamma), _ptr(beta), _ptr(stats), _ptr(partials), eps, _ptr(row_scale),
                      rows_per_scale)
+
+
+def mlp_fwd(xn2, w1, w2, resid, act, dact, x_out, xn_out, hid_ones_col: int, ln: SrkLnArgs):
+    """Fused fc1 -> GELU -> fc2 -> residual -> LayerNorm (srk_mlp_fwd).  act / dact may be None (inference)."""
+    T, Cp = xn2.shape
+    Hp = w1.shape[0]
+    assert tuple(w1.shape) == (Hp, Cp) and tuple(w2.shape) == (Cp, Hp)
+    for t in (xn2, w1, w2, resid, act, dact, x_out, xn_out):
+        assert t is None or (t.dtype == torch.bfloat16 and t.is_contiguous())
+    rc = _mlp_fwd(T, Cp, Hp, _ptr(xn2), _ptr(w1), _ptr(w2), _ptr(resid), _ptr(act), _ptr(dact), _ptr(x_out), _ptr(xn_out),
+                  hid_ones_col, ctypes.byref(ln), _stream())
+    _check(rc, "srk_mlp_fwd")
 
 
 def wgrad_workspace_elems(Ca: int, Cb: int, splits: int) -> int:

@@ -3,6 +3,7 @@
 // stand-alone window-attention and LayerNorm ops.  Host code only orchestrates launches on the caller's
 // stream; it never allocates or synchronises.
 #include "attn_oca8.cuh"
+#include "attn_tc8.cuh"
 #include "cab_aux.cuh"
 #include "block_aux.cuh"
 #include "srk_host.h"
@@ -34,6 +35,21 @@ int check_dims(const SrkBlockDims* d, const SrkGeom* g, bool hat = false) {
   return SRK_OK;
 }
 
+// SRK_ATTN_TC=1 selects the tcgen05 / TMEM / TMA window-attention kernels (attn_tc8.cuh); they take every shape the models
+// produce (cyclic shift 0 or 4, an even number of windows and heads).  Default: the register-resident mma.sync kernels,
+// which are faster at head_dim 30 — measured on B200 at the bench shape (tools/gpu_probe_attn_tc.py,
+// profiles/r02_attn_tc8_vs_mma.txt): forward 85.8 vs 142.8 us, backward 199.0 vs 332.7 us.
+bool attn_tc_eligible(const SrkGeom* g, int heads, int ld_qkv, int ld_o) {
+  static const bool on = getenv("SRK_ATTN_TC") && getenv("SRK_ATTN_TC")[0] == '1';
+  const long long nwin = (long long)g->B * (g->H / 8) * (g->W / 8);
+  return on && (g->shift % 4) == 0 && (heads % 2) == 0 && heads <= TC8_MAX_HEADS && (nwin % 2) == 0 &&
+         ld_qkv == 3 * heads * 32 && ld_o == heads * 32;
+}
+
+int qkv_window_map(CUtensorMap* tm, const void* p, const SrkGeom* g, int ld) {
+  return make_tmap_nhwc(tm, p, ld, g->W, g->H, g->B, ld, (uint64_t)g->W * ld, (uint64_t)g->H * g->W * ld, 4, 4);
+}
+
 int wgrad_splits(int T, int ca_tiles) {
   int s = num_sms() / ca_tiles;
   const int iters = T / 64;
@@ -52,6 +68,16 @@ int attn_bwd_gx(int nwin, int heads) {
   if (gx > nwin) gx = nwin;
   return gx < 1 ? 1 : gx;
 }
+int attn_tc_grid(const SrkGeom* g) {
+  const int npairs = g->B * (g->H / 8) * (g->W / 8) / 2;
+  return npairs < num_sms() ? npairs : num_sms();
+}
+// rows of per-CTA bias-table partials the ws-8 backward writes for this geometry (block layouts: ld = 3*heads*32 / heads*32)
+int attn_bwd_parts_ld(const SrkGeom* g, int heads, int ld_qkv, int ld_o) {
+  if (attn_tc_eligible(g, heads, ld_qkv, ld_o)) return attn_tc_grid(g);
+  return attn_bwd_gx(g->B * (g->H / 8) * (g->W / 8), heads);
+}
+int attn_bwd_parts(const SrkGeom* g, int heads) { return attn_bwd_parts_ld(g, heads, 3 * heads * 32, heads * 32); }
 int attn_fwd_gx(int nwin, int heads) {
   int gx = num_sms() * 6 / heads;
   if (gx > nwin) gx = nwin;
@@ -72,14 +98,40 @@ WsLayout ws_layout(const SrkBlockDims* d, const SrkGeom* g) {
   L.ln_grid = srk_gemm_grid(int(T), d->Cp);
   L.ln1 = o; o += (long long)L.ln_grid * 2 * d->Cp;
   L.ln2 = o; o += (long long)L.ln_grid * 2 * d->Cp;
-  L.rpb_gx = attn_bwd_gx(g->B * (g->H / 8) * (g->W / 8), d->heads);
-  L.rpb = o; o += (long long)L.rpb_gx * d->heads * 225;
+  L.rpb_gx = attn_bwd_parts(g, d->heads);
+  {  // sized for either kernel (the scratch is allocated once per geometry, whatever the block's shift)
+    const int a0 = attn_tc_grid(g), a1 = attn_bwd_gx(g->B * (g->H / 8) * (g->W / 8), d->heads);
+    L.rpb = o; o += (long long)(a0 > a1 ? a0 : a1) * d->heads * 225;
+  }
   L.total = o;
   return L;
 }
 
 int launch_attn_fwd(const SrkGeom* g, int heads, const void* qkv, int ld_qkv, const float* table, void* out, int ld_o,
                     int ones_col, cudaStream_t stream, int mask = 0) {
+  if (attn_tc_eligible(g, heads, ld_qkv, ld_o)) {
+    AttnArgs a{};
+    a.mask = mask;
+    a.qkv = static_cast<const __nv_bfloat16*>(qkv);
+    a.out = static_cast<__nv_bfloat16*>(out);
+    a.bias_table = table;
+    a.B = g->B; a.H = g->H; a.W = g->W; a.heads = heads; a.shift = g->shift;
+    a.ld_qkv = ld_qkv; a.ld_o = ld_o; a.ones_col = ones_col;
+    CUtensorMap tm;
+    int rc = qkv_window_map(&tm, qkv, g, ld_qkv);
+    if (rc) return rc;
+    static DeviceOnce configured;
+    if (configured.need()) {
+      SRK_CUDA_OK(cudaFuncSetAttribute(win_attn_tc8_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC8_SMEM));
+      configured.done();
+    }
+    const int npairs = g->B * (g->H / 8) * (g->W / 8) / 2;
+    const int grid = npairs < num_sms() ? npairs : num_sms();
+    SRK_CUDA_OK(launch_pdl(win_attn_tc8_fwd_kernel, dim3(grid), dim3(TC8_THREADS), TC8_SMEM, stream, tm, a));
+    SRK_LAUNCHED(1);
+    SRK_CUDA_OK(cudaGetLastError());
+    return SRK_OK;
+  }
   AttnArgs a{};
   a.mask = mask;
   a.qkv = static_cast<const __nv_bfloat16*>(qkv);
@@ -97,6 +149,31 @@ int launch_attn_fwd(const SrkGeom* g, int heads, const void* qkv, int ld_qkv, co
 
 int launch_attn_bwd(const SrkGeom* g, int heads, const void* qkv, int ld_qkv, const float* table, const void* dout,
                     int ld_o, void* dqkv, float* partials, int gx, cudaStream_t stream, int mask = 0) {
+  if (attn_tc_eligible(g, heads, ld_qkv, ld_o)) {
+    if (gx != attn_tc_grid(g)) return fail(SRK_ERR_ARG, "win_attn bwd: partial-row count does not match the tcgen05 kernel's grid");
+    AttnArgs a{};
+    a.qkv = static_cast<const __nv_bfloat16*>(qkv);
+    a.dout = static_cast<const __nv_bfloat16*>(dout);
+    a.dqkv = static_cast<__nv_bfloat16*>(dqkv);
+    a.bias_table = table;
+    a.dbias_partials = partials;
+    a.mask = mask;
+    a.B = g->B; a.H = g->H; a.W = g->W; a.heads = heads; a.shift = g->shift;
+    a.ld_qkv = ld_qkv; a.ld_o = ld_o; a.ones_col = -1;
+    CUtensorMap tq, td;
+    int rc = qkv_window_map(&tq, qkv, g, ld_qkv);
+    if (rc) return rc;
+    if ((rc = qkv_window_map(&td, dout, g, ld_o))) return rc;
+    static DeviceOnce configured_tc;
+    if (configured_tc.need()) {
+      SRK_CUDA_OK(cudaFuncSetAttribute(win_attn_tc8_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC8B_SMEM));
+      configured_tc.done();
+    }
+    SRK_CUDA_OK(launch_pdl(win_attn_tc8_bwd_kernel, dim3(gx), dim3(TC8_THREADS), TC8B_SMEM, stream, tq, td, a));
+    SRK_LAUNCHED(1);
+    SRK_CUDA_OK(cudaGetLastError());
+    return SRK_OK;
+  }
   static DeviceOnce configured;
   if (configured.need()) {
     SRK_CUDA_OK(cudaFuncSetAttribute(win_attn_ws8_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -156,7 +233,10 @@ Attn16Ws attn16_ws_layout(const SrkGeom* g, int mode, int heads) {
     const int nwin = g->B * (g->H / 8) * (g->W / 8);
     L.gx = oca8_bwd_gx(nwin, heads);
     size_t o = 0;
-    if (mode == MODE_SELF) o = (size_t)attn_bwd_gx(nwin, heads) * heads * 225 * sizeof(float);
+    if (mode == MODE_SELF) {  // either ws-8 backward kernel: the larger of the two partial-row counts
+      const int a0 = attn_tc_grid(g), a1 = attn_bwd_gx(nwin, heads);
+      o = (size_t)(a0 > a1 ? a0 : a1) * heads * 225 * sizeof(float);
+    }
     if (mode == MODE_OCA) {
       L.scratch_off = o; o += (size_t)L.gx * heads * 4 * O8_NT * 32 * 4 * sizeof(float);
       L.dense_off = o; o += (size_t)heads * 64 * O8_NK * sizeof(float);
@@ -353,6 +433,15 @@ static int block_fwd_impl(const SrkBlockDims* d, const SrkGeom* g, const SrkBloc
   if ((rc = srk_gemm_tn(SRK_EPI_RES_LN, T, Cp, AW, a->ao, AW, w->proj_f, AW, a->x_mid, Cp, a->xn2, Cp, resid, Cp,
                         nullptr, 0, &ln2, stream)))
     return rc;
+  // MLP half.  SRK_FUSED_MLP=1: one fused kernel (fc1 -> GELU -> fc2 -> residual -> next LayerNorm; the hidden tile goes from
+  // TMEM through GELU into shared-memory boxes that are fc2's A operand) — bit-identical act / dact / x_out, but measured
+  // SLOWER than the two-kernel path on B200 (410 vs 329 us per block at batch 16, tools/gpu_probe_mlp_fused.py): the GELU
+  // epilogue's instruction stream, not the re-read of the hidden tensor, is what bounds this half.
+  SrkLnArgs lnn{d->C, d->C, next_norm_w, next_norm_b, a->stats_out, nullptr, 1e-5f, x ? x->drop_mlp : nullptr, g->H * g->W};
+  static const bool fused_mlp = getenv("SRK_FUSED_MLP") && getenv("SRK_FUSED_MLP")[0] == '1';
+  if (fused_mlp && (a->dact || !a->act) && Hp % 128 == 0)
+    return srk_mlp_fwd(T, Cp, Hp, a->xn2, w->fc1_f, w->fc2_f, a->x_mid, a->act, a->dact, a->x_out, a->xn_out, d->hidden, &lnn,
+                       stream);
   // act = gelu(fc1(xn2)); gelu'(.) is stored only if the caller provides `dact` (otherwise the backward recomputes it)
   SrkLnArgs ge{Hp, d->hidden, nullptr, nullptr, nullptr, nullptr, 0.f, nullptr, 1};
   if (a->dact) {
@@ -364,7 +453,6 @@ static int block_fwd_impl(const SrkBlockDims* d, const SrkGeom* g, const SrkBloc
   }
   if (rc) return rc;
   // x_out = x_mid + fc2(act); xn_out = LN_next(x_out)
-  SrkLnArgs lnn{d->C, d->C, next_norm_w, next_norm_b, a->stats_out, nullptr, 1e-5f, x ? x->drop_mlp : nullptr, g->H * g->W};
   if ((rc = srk_gemm_tn(SRK_EPI_RES_LN, T, Cp, Hp, a->act, Hp, w->fc2_f, Hp, a->x_out, Cp, a->xn_out, Cp, a->x_mid, Cp,
                         nullptr, 0, &lnn, stream)))
     return rc;
@@ -515,7 +603,7 @@ extern "C" int srk_win_attn16_bwd(const SrkGeom* g, int mode, int heads, const v
   if ((!lse && g->ws == 16) || !ws || !out) return fail(SRK_ERR_ARG, "srk_win_attn16_bwd: lse, ws and the forward output are required");
   if (g->ws == 8 && mode == MODE_SELF) {  // ws-8 core with HAT's shift mask; per-CTA table partials in ws
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int gx = attn_bwd_gx(g->B * (g->H / 8) * (g->W / 8), heads);
+    const int gx = attn_bwd_parts_ld(g, heads, ld_qkv, ld_out);
     rc = launch_attn_bwd(g, heads, qkv, ld_qkv, rpb_table, d_out, ld_out, d_qkv, static_cast<float*>(ws), gx, st, 1);
     if (rc) return rc;
     if (d_rpb_table) {
@@ -575,14 +663,16 @@ extern "C" int srk_win_attn_fwd(const SrkGeom* g, int heads, const void* qkv, in
   return launch_attn_fwd(g, heads, qkv, ld_qkv, rpb_table, out, ld_out, ones_col, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" long long srk_win_attn_bwd_ws_floats(int heads) { return (long long)num_sms() * 4 * 225 + 225LL * heads; }
+extern "C" long long srk_win_attn_bwd_ws_floats(int heads) {
+  return (long long)num_sms() * (heads > 4 ? heads : 4) * 225 + 225LL * heads;   // per-CTA partials of either backward kernel
+}
 
 extern "C" int srk_win_attn_bwd(const SrkGeom* g, int heads, const void* qkv, int ld_qkv, const float* rpb_table,
                                 const void* d_out, int ld_out, void* d_qkv, float* dbias_ws, float* d_rpb_table,
                                 void* stream_) {
   if (!g || g->ws != 8 || g->H % 8 || g->W % 8) return fail(SRK_ERR_UNSUPPORTED, "srk_win_attn_bwd: ws must be 8");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const int gx = attn_bwd_gx(g->B * (g->H / 8) * (g->W / 8), heads);
+  const int gx = attn_bwd_parts_ld(g, heads, ld_qkv, ld_out);
   int rc = launch_attn_bwd(g, heads, qkv, ld_qkv, rpb_table, d_out, ld_out, d_qkv, dbias_ws, gx, stream);
   if (rc) return rc;
   if (d_rpb_table) {

@@ -1,6 +1,7 @@
 // api_gemm.cu — C-ABI entry points for the tcgen05 GEMMs (forward/dgrad and wgrad).
 #include "gemm_tn.cuh"
 #include "gemm_wgrad.cuh"
+#include "mlp_fused.cuh"
 #include "srk_host.h"
 
 namespace srk {
@@ -163,4 +164,41 @@ static int gemm_wgrad_impl(int T, int Ca, int Cb, const void* A, int lda, const 
 extern "C" int srk_gemm_wgrad(int T, int Ca, int Cb, const void* A, int lda, const void* B, int ldb,
                               float* workspace, int splits, float* out, void* stream) {
   return gemm_wgrad_impl(T, Ca, Cb, A, lda, B, ldb, workspace, splits, out, WG_SUBBOX, 1024, stream);
+}
+
+extern "C" int srk_mlp_fwd(int T, int Cp, int Hp, const void* xn2, const void* w1, const void* w2, const void* resid,
+                           void* act, void* dact, void* x_out, void* xn_out, int hid_ones_col, const SrkLnArgs* ln,
+                           void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (T <= 0 || T % GEMM_BM != 0 || Cp != MF_C || Hp <= 0 || Hp % MF_CH != 0)
+    return fail(SRK_ERR_UNSUPPORTED, "srk_mlp_fwd: T % 128 == 0, Cp == 192, Hp % 128 == 0");
+  if (!xn2 || !w1 || !w2 || !resid || !x_out || !xn_out || !ln || !ln->gamma) return fail(SRK_ERR_ARG, "srk_mlp_fwd: null argument");
+  if (dact && !act) return fail(SRK_ERR_ARG, "srk_mlp_fwd: dact without act");
+  MlpFwdArgs a{};
+  a.M = T; a.Hp = Hp; a.n_real = ln->n_real; a.hid_ones_col = hid_ones_col; a.ln_ones_col = ln->ones_col;
+  a.gamma = ln->gamma; a.beta = ln->beta; a.stats = ln->stats; a.eps = ln->eps;
+  a.row_scale = ln->row_scale; a.rows_per_scale = ln->rows_per_scale > 0 ? ln->rows_per_scale : 1;
+  a.resid = static_cast<const __nv_bfloat16*>(resid); a.ld_res = Cp;
+  a.x_out = static_cast<__nv_bfloat16*>(x_out); a.ld_xo = Cp;
+  a.store_act = act ? 1 : 0; a.store_dact = dact ? 1 : 0;
+  CUtensorMap tX, tW1, tW2, tAct, tDact, tXn;
+  int rc;
+  if ((rc = make_tmap_2d(&tX, xn2, T, Cp, Cp, GEMM_BM))) return rc;
+  if ((rc = make_tmap_2d(&tW1, w1, Hp, Cp, Cp, MF_CH))) return rc;
+  if ((rc = make_tmap_2d(&tW2, w2, Cp, Hp, Hp, MF_C))) return rc;
+  if ((rc = make_tmap_2d(&tXn, xn_out, T, Cp, Cp, GEMM_BM))) return rc;
+  tAct = tXn; tDact = tXn;
+  if (act && (rc = make_tmap_2d(&tAct, act, T, Hp, Hp, GEMM_BM))) return rc;
+  if (dact && (rc = make_tmap_2d(&tDact, dact, T, Hp, Hp, GEMM_BM))) return rc;
+  static DeviceOnce configured;
+  if (configured.need()) {
+    SRK_CUDA_OK(cudaFuncSetAttribute(mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MF_SMEM_BYTES));
+    configured.done();
+  }
+  const int tiles = T / GEMM_BM;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  SRK_CUDA_OK(launch_pdl(mlp_fwd_kernel, dim3(grid), dim3(MF_THREADS), MF_SMEM_BYTES, stream, tX, tW1, tW2, tAct, tDact, tXn, a));
+  SRK_LAUNCHED(1);
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
 }

@@ -273,6 +273,94 @@ def roofline_probe(batch: int, peaks):
     return roof, rows
 
 
+def run_gan(args):
+    """BASELINE configs[3]: SwinIR generator (libsrk mirror) + UNetDiscriminatorSN + RaGAN / perceptual losses, in the
+    arrangement of train_swin.py:147-259 — DDP(G, find_unused_parameters=True), DDP(D), fp16 autocast + GradScaler,
+    requires_grad toggling, micro-batch 2 x 4 accumulation steps per optimizer step, EMA — eager, like the script.
+    One bench "step" = one optimizer step = `accum` micro-steps; value = patches/s over all ranks."""
+    import torch.distributed as dist
+    from superresolution_def_b200 import _capi as capi
+    from superresolution_def_b200.architecture_swin import SwinIR
+    from superresolution_def_b200.gan import UNetDiscriminatorSN, GanTrainer
+    from superresolution_def_b200.synth import synthetic_pairs
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU path for the product arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29533")
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    mb, accum = args.batch or 2, 4
+    torch.manual_seed(0)
+    net_g = SwinIR(**MODEL_KW).to(dev)
+    net_d = UNetDiscriminatorSN(num_in_ch=1, num_feat=64).to(dev).to(memory_format=torch.channels_last)
+    DDP = torch.nn.parallel.DistributedDataParallel
+    net_g = DDP(net_g, device_ids=[local], output_device=local, find_unused_parameters=True)
+    net_d = DDP(net_d, device_ids=[local], output_device=local, find_unused_parameters=False)
+    net_g.train(); net_d.train()
+    tr = GanTrainer(net_g, net_d, accum=accum)
+    lr_h, hr_h = synthetic_pairs(4, seed=77 + rank)
+    host = [(lr_h[i:i + mb].contiguous().pin_memory(), hr_h[i:i + mb].contiguous().pin_memory()) for i in (0, 2)]
+    devs = [(a.to(dev), b.to(dev)) for a, b in host]
+
+    def opt_step(e2e, k):
+        out = None
+        for m in range(accum):
+            if e2e:
+                a, b = host[(k + m) & 1]
+                lg, ld = tr.micro_step(a.to(dev, non_blocking=True), b.to(dev, non_blocking=True))
+                out = (lg.item(), ld.item())     # the script reads both losses back every micro-step (train_swin.py:257-258)
+            else:
+                a, b = devs[(k + m) & 1]
+                out = tr.micro_step(a, b)
+        return out
+
+    def timed(n, e2e):
+        dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for k in range(n):
+            out = opt_step(e2e, k)
+        e1.record(); torch.cuda.synchronize(); dist.barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item(), out
+
+    timed(args.warmup, False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = capi.launch_count()
+    ms, out = timed(args.steps, False)
+    launches = capi.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    timed(1, True)
+    ms_e2e, out_e = timed(args.steps, True)
+    per_step = world * mb * accum
+    line = {"metric": "SwinIR + UNetDiscriminatorSN GAN train patches/s (128x128 -> 512x512)", "value": per_step * args.steps / (ms * 1e-3),
+            "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 (generator kernels) / fp16 autocast (discriminator, VGG)",
+            "data": "synthetic",
+            "config": {"workload": f"train_swin.py micro-step semantics: D step + G step, RaGAN + L1 + VGG-perceptual (seeded VGG-19), DDP over NCCL, "
+                                   f"micro-batch {mb} x {accum} accumulation per optimizer step (BASELINE configs[3])",
+                       "global_batch": per_step, "parallelism": f"dp{world}", "launch": "eager (as the script)",
+                       "l2": "two input batches rotated; activations of every forward exceed L2",
+                       "discriminator": "interface mirror on stock ATen/cuDNN (channels_last); generator = libsrk"},
+            "e2e": {"value": per_step * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": accum * mb * (128 * 128 + 512 * 512) * 4, "d2h_bytes_per_step": accum * 8},
+            "gpu_launches": launches, "clocks": clocks, "loss_g": float(out_e[0]), "loss_d": float(out_e[1]),
+            "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    dist.barrier(); torch.cuda.synchronize()
+    sys.stdout.flush(); sys.stderr.flush()
+    os._exit(0)
+
+
 def _dbg(msg):
     if os.environ.get("SRK_BENCH_DEBUG"):
         print(f"[bench rank {os.environ.get('RANK', '0')} +{time.perf_counter() - _T0:.1f}s] {msg}", file=sys.stderr, flush=True)
@@ -504,9 +592,9 @@ def run_ours(args):
         if world == 1 and not hat and not args.no_sub:
             # the other two generators of the path, a few steps each (separate processes: their own graphs and memory)
             line["sub_records"] = {}
-            for wl in ("hat", "hybrid"):
+            for wl in ("hat", "hybrid", "gan"):
                 try:
-                    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", wl, "--steps", "5", "--warmup", "3",
+                    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", wl, "--steps", "3" if wl == "gan" else "5", "--warmup", "3",
                                         "--no-cpu-baseline", "--no-sub", "--no-gpu-baseline"], capture_output=True, text=True,
                                        timeout=420, cwd=ROOT)
                     js = [l for l in r.stdout.splitlines() if l.startswith("{")]
@@ -542,8 +630,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=0, help="patches per GPU per step (default: 16 SwinIR = BASELINE configs[1], 8 HAT)")
-    ap.add_argument("--workload", default="swinir", choices=["swinir", "hat", "hybrid"],
-                    help="swinir = the bench line (configs[1]); hat = configs[2]; hybrid = train_hat.py's generator")
+    ap.add_argument("--workload", default="swinir", choices=["swinir", "hat", "hybrid", "gan"],
+                    help="swinir = the bench line (configs[1]); hat = configs[2]; hybrid = train_hat.py's generator; "
+                         "gan = configs[3] (SwinIR + UNetDiscriminatorSN, train_swin.py step semantics)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the stock-PyTorch-eager leg (gpu_eager_baseline)")
@@ -555,6 +644,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "gan":
+        run_gan(args)
     else:
         run_ours(args)
 

@@ -298,6 +298,19 @@ int srk_cab_se_bwd(const void* g, const void* y, int B, int HW, int C, int Cp, i
                    float alpha, const float* pool, const float* hidden, const float* scale, float* ws, void* dy,
                    float* dw1, float* db1, float* dw2, float* db2, void* stream);
 
+/* ======================================================================================================
+ * Data formats on either side of the path: 16-bit image planes.
+ * ====================================================================================================== */
+
+/* dst[b] (float32, n x n) = augment(src[b] (uint16, n x n)) / 65535: the dataset's load + augmentation in one pass.
+ * Replaces dataset/astronomical_dataset_swin.py:34-39 (/65535 -> float32) and :58-67 (flip(-1), flip(-2), rot90(k)).
+ * codes: device int[B], per sample  fh | fv << 1 | k << 2  (NULL: no augmentation); n % 32 == 0. */
+int srk_u16_to_f32_aug(const void* src_u16, float* dst, const int* codes, int B, int n, void* stream);
+
+/* dst (uint16) = trunc(clip(src, 0, 1) * 65535): the quantisation of save_as_tiff16 (infer_hat.py:42-50), on the device,
+ * so that a super-resolved frame leaves the GPU at 2 bytes per pixel.  src 16-byte, dst 8-byte aligned. */
+int srk_f32_to_u16(const float* src, void* dst_u16, long long n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,7 +5,7 @@ on a machine without the built .so raises, and every call raises on a non-zero r
 from __future__ import annotations
 
 import ctypes
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_longlong, c_void_p
 from pathlib import Path
 
 import torch
@@ -128,6 +128,25 @@ def mlp_fwd(xn2, w1, w2, resid, act, dact, x_out, xn_out, hid_ones_col: int, ln:
     rc = _mlp_fwd(T, Cp, Hp, _ptr(xn2), _ptr(w1), _ptr(w2), _ptr(resid), _ptr(act), _ptr(dact), _ptr(x_out), _ptr(xn_out),
                   hid_ones_col, ctypes.byref(ln), _stream())
     _check(rc, "srk_mlp_fwd")
+
+
+_u16_to_f32_aug = _sig("srk_u16_to_f32_aug", [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p])
+_f32_to_u16 = _sig("srk_f32_to_u16", [c_void_p, c_void_p, c_longlong, c_void_p])
+
+
+def u16_to_f32_aug(src: torch.Tensor, dst: torch.Tensor, codes: torch.Tensor | None):
+    """src [B, n, n] uint16 (CUDA), dst [B, 1, n, n] or [B, n, n] float32, codes int32 [B] (fh | fv<<1 | k<<2) or None."""
+    B, n = src.shape[0], src.shape[-1]
+    assert src.is_cuda and src.dtype == torch.uint16 and src.is_contiguous() and src.shape[-2] == n
+    assert dst.dtype == torch.float32 and dst.is_contiguous() and dst.numel() == src.numel()
+    assert codes is None or (codes.dtype == torch.int32 and codes.is_cuda and codes.numel() == B)
+    _check(_u16_to_f32_aug(_ptr(src), _ptr(dst), _ptr(codes), B, n, _stream()), "srk_u16_to_f32_aug")
+
+
+def f32_to_u16(src: torch.Tensor, dst: torch.Tensor):
+    assert src.is_cuda and src.dtype == torch.float32 and src.is_contiguous()
+    assert dst.dtype == torch.uint16 and dst.is_contiguous() and dst.numel() == src.numel()
+    _check(_f32_to_u16(_ptr(src), _ptr(dst), src.numel(), _stream()), "srk_f32_to_u16")
 
 
 def wgrad_workspace_elems(Ca: int, Cb: int, splits: int) -> int:

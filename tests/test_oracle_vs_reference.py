@@ -151,3 +151,29 @@ def test_hybrid_module_schema_and_oracle_match_reference():
         want = ref(x)
         got = ho.hybrid_forward(x, ref.state_dict(), window_size=8, depths=(2,), num_heads=(6,), num_rrdb=1)
     assert rel_l2(got, want) < 2e-5, rel_l2(got, want)
+
+
+def test_discriminator_mirror_equals_the_reference_module():
+    """superresolution_def_b200.gan.UNetDiscriminatorSN vs models/discriminator_swin.py:43-84 imported unmodified: same
+    state_dict keys / shapes / order (spectral-norm weight_orig, weight_u, weight_v included), strict load both ways, and
+    identical logits on CPU in eval mode (no power iteration) and in train mode (one power iteration on both sides)."""
+    _ref_mod()
+    from models.discriminator_swin import UNetDiscriminatorSN as RefD
+    from superresolution_def_b200.gan import UNetDiscriminatorSN
+    torch.manual_seed(0)
+    ref = RefD(num_in_ch=1, num_feat=16)
+    mine = UNetDiscriminatorSN(num_in_ch=1, num_feat=16)
+    sd = ref.state_dict()
+    assert [(k, tuple(v.shape)) for k, v in sd.items()] == [(k, tuple(v.shape)) for k, v in mine.state_dict().items()]
+    mine.load_state_dict(sd, strict=True)
+    ref.load_state_dict(mine.state_dict(), strict=True)
+    x = torch.rand(2, 1, 64, 64)
+    ref.eval(); mine.eval()
+    with torch.no_grad():
+        assert torch.equal(mine(x), ref(x))
+    ref.train(); mine.train()
+    a, b = mine(x), ref(x)
+    assert torch.equal(a, b)
+    a.mean().backward(); b.mean().backward()
+    for (n, p), (_, q) in zip(mine.named_parameters(), ref.named_parameters()):
+        assert torch.equal(p.grad, q.grad), n

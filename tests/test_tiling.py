@@ -24,6 +24,17 @@ def test_tiling_matches_direct_for_a_local_operator():
     assert torch.equal(out, _fake_model(frame[None, None]))
     out_h = sr_frame_tiled(_fake_model, frame, tile=32, halo=8, batch=5)
     assert torch.equal(out_h, out)
+    # cross-faded overlaps: a local operator gives every overlapping tile the same values, so the weighted mean is exact
+    out_b = sr_frame_tiled(_fake_model, frame, tile=32, halo=8, batch=5, blend=True)
+    assert out_b.shape == out.shape and torch.allclose(out_b, out, atol=1e-6)
+    # and it IS a blend: tiles that disagree by a constant are cross-faded monotonically across the seam
+    seam = sr_frame_tiled(lambda x: F.interpolate(x * 0 + x[:, :, :1, :1], scale_factor=4, mode="nearest"), frame, tile=32,
+                          halo=8, batch=2, blend=True)
+    row = seam[0, 0, 8, 96:160]                       # crosses the seam between tile columns 0 and 1 (at x = 128)
+    lo, hi = float(min(row[0], row[-1])), float(max(row[0], row[-1]))
+    assert bool(((row >= lo - 1e-6) & (row <= hi + 1e-6)).all()) and float((row[1:] - row[:-1]).abs().max()) <= (hi - lo) / 32 + 1e-6
+    with pytest.raises(ValueError):
+        sr_frame_tiled(_fake_model, frame, tile=32, blend=True)
     with pytest.raises(ValueError):
         tile_origins(60, 96, 32)
     assert extract_tiles(frame[None, None], [(0, 0), (32, 64)], 32, 4).shape == (2, 1, 40, 40)

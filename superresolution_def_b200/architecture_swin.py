@@ -193,6 +193,7 @@ class SwinIR(nn.Module):
         self.conv_last = nn.Conv2d(64, in_chans, 3, 1, 1)
 
     def forward(self, x):
+        eng.check_precision(x)
         H0, W0 = x.shape[2], x.shape[3]
         ws = self.window_size
         pad_h, pad_w = (ws - H0 % ws) % ws, (ws - W0 % ws) % ws

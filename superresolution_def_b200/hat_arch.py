@@ -409,6 +409,7 @@ class HAT(nn.Module):
         return {'relative_position_bias_table'}
 
     def forward(self, x):
+        eng.check_precision(x)
         B, _, H, W = x.shape
         ws = self.window_size
         if H % ws or W % ws:

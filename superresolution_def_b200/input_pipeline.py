@@ -32,7 +32,7 @@ def read_tiff_u16(path) -> np.ndarray | None:
             return None
         img = Image.open(p)
         img.load()
-        arr = np.asarray(img)
+        arr = np.array(img)   # a writable copy (torch.from_numpy refuses read-only views)
         if arr.ndim != 2:
             return None
         if arr.dtype != np.uint16:

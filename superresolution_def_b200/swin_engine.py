@@ -124,6 +124,33 @@ def _weights_for(cfg: BlockCfg, params: list[torch.Tensor], refresh: bool = True
     return wc.get(params, refresh)
 
 
+_fp32_warned = False
+
+
+def check_precision(x: torch.Tensor) -> None:
+    """Precision policy of the mirrors.  Every libsrk kernel computes in bf16 with fp32 accumulation, which is what the
+    reference gets under the autocast of train_swin.py:217-243.  train_hat.py:222-251 however trains in plain fp32 (no
+    autocast): running it on the mirrors silently changes the arithmetic, so the downgrade is made loud and controllable:
+      SRK_FP32_POLICY=warn  (default) one RuntimeWarning per process when an fp32 input arrives outside autocast;
+      SRK_FP32_POLICY=error refuse (SrkError) — for runs that must not leave fp32;
+      SRK_FP32_POLICY=allow silent.
+    The parity this repository asserts for that case is stated in tests/test_fullsize_gpu.py: outputs and every parameter
+    gradient against the fp32 oracle, bounded relative to the oracle's own bf16-autocast error."""
+    global _fp32_warned
+    if x.dtype != torch.float32 or torch.is_autocast_enabled(x.device.type):
+        return
+    mode = os.environ.get("SRK_FP32_POLICY", "warn").lower()
+    if mode == "error":
+        raise capi.SrkError("fp32 input outside autocast and SRK_FP32_POLICY=error: libsrk kernels compute in bf16 "
+                            "(fp32 accumulate); wrap the call in torch.autocast or set SRK_FP32_POLICY=warn/allow")
+    if mode == "warn" and not _fp32_warned:
+        _fp32_warned = True
+        import warnings
+        warnings.warn("superresolution_def_b200: fp32 input outside autocast — the sm_100a kernels compute in bf16 with fp32 "
+                      "accumulation (the reference's own autocast precision); outputs keep the caller's dtype. "
+                      "Set SRK_FP32_POLICY=error to refuse, =allow to silence.", RuntimeWarning, stacklevel=3)
+
+
 def _check_param(p: torch.Tensor):
     if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
         raise capi.SrkError("libsrk needs contiguous fp32 CUDA parameters (no CPU / fallback path exists)")

@@ -1,5 +1,7 @@
 """The C-ABI library loads on a CPU-only box and exports every symbol include/srk.h declares (no compute calls)."""
 import ctypes
+
+import pytest
 import re
 from pathlib import Path
 
@@ -40,3 +42,25 @@ def test_shape_helpers_without_gpu():
     d = capi.SrkBlockDims(180, 192, 6, 30, 32, 720, 768)
     assert capi.block_weight_elems(d) == [110592, 110592, 36864, 36864, 147456, 147456, 147456, 147456]
     assert capi.block_bwd_scratch_floats(d, capi.SrkGeom(16, 128, 128, 8, 0)) > 0
+
+
+def test_fp32_policy_is_loud_and_controllable(monkeypatch):
+    """train_hat.py:222-251 trains in fp32 without autocast; the mirrors compute in bf16.  The downgrade warns once by default,
+    raises under SRK_FP32_POLICY=error, and is silent under autocast."""
+    import warnings
+    import torch
+    from superresolution_def_b200 import swin_engine as eng, _capi as capi
+    x = torch.zeros(1, 1, 8, 8)
+    monkeypatch.setattr(eng, "_fp32_warned", False)
+    monkeypatch.setenv("SRK_FP32_POLICY", "warn")
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        eng.check_precision(x)
+        eng.check_precision(x)
+    assert len([m for m in w if issubclass(m.category, RuntimeWarning)]) == 1
+    monkeypatch.setenv("SRK_FP32_POLICY", "error")
+    with pytest.raises(capi.SrkError):
+        eng.check_precision(x)
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        eng.check_precision(x)          # autocast on: the reference computes in reduced precision too
+    eng.check_precision(x.to(torch.bfloat16))

@@ -85,3 +85,95 @@ def test_gan_micro_steps_like_train_swin():
         assert all(torch.isfinite(v).all() for v in tr.ema.shadow.values())
     finally:
         dist.destroy_process_group()
+
+
+def _detect_hybrid_params(sd):
+    """The shape sniffing infer_hat.py:52-112 applies to a checkpoint (re-stated: embed_dim from hat.conv_first, num_feat from
+    conv_adapt, growth from rdb1.conv1, RRDB count and HAT stage count from the key indices)."""
+    p = dict(img_size=128, in_chans=1, embed_dim=90, depths=(6, 6, 6, 6), num_heads=(6, 6, 6, 6), window_size=8, upscale=4,
+             num_rrdb=12, num_feat=48, num_grow_ch=24)
+    p["embed_dim"] = sd["hat.conv_first.weight"].shape[0]
+    p["num_feat"] = sd["conv_adapt.weight"].shape[0]
+    p["num_grow_ch"] = sd["rrdb_trunk.0.rdb1.conv1.weight"].shape[0]
+    p["num_rrdb"] = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("rrdb_trunk."))
+    stages = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("hat.layers."))
+    p["depths"], p["num_heads"] = (6,) * stages, (6,) * stages
+    return p
+
+
+def test_hybrid_train_and_infer_like_train_hat_and_infer_hat(tmp_path, monkeypatch):
+    """train_hat.py:128-149,222-266: fp32 (NO autocast), DDP(find_unused_parameters=False), gradient accumulation, EMA copy
+    updated by zipping .parameters(), D frozen during the G step and fed sr.detach() afterwards; then infer_hat.py:160-177:
+    checkpoint with 'module.' prefixes -> shape auto-detection -> strict load -> eval forward -> 16-bit TIFF."""
+    import warnings
+    from superresolution_def_b200.hybridmodels_hat import HybridHATRealESRGAN
+    from superresolution_def_b200.gan import UNetDiscriminatorSN, CombinedGANLoss, DiscriminatorLoss
+    from superresolution_def_b200.input_pipeline import save_as_tiff16, read_tiff_u16
+    from superresolution_def_b200 import swin_engine as eng
+    monkeypatch.setattr(eng, "_fp32_warned", False)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(_free_port()))
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    kw = dict(img_size=32, in_chans=1, embed_dim=90, depths=(6,), num_heads=(6,), window_size=8, upscale=4, num_rrdb=2,
+              num_feat=48, num_grow_ch=24)
+    try:
+        torch.manual_seed(0)
+        net_g = HybridHATRealESRGAN(**kw).cuda()
+        net_ema = HybridHATRealESRGAN(**kw).cuda()
+        for p in net_ema.parameters():
+            p.requires_grad = False
+        net_d = UNetDiscriminatorSN(num_in_ch=1, num_feat=16).cuda()
+        DDP = torch.nn.parallel.DistributedDataParallel
+        net_g = DDP(net_g, device_ids=[0], find_unused_parameters=False)
+        net_d = DDP(net_d, device_ids=[0])
+        opt_g = torch.optim.Adam(net_g.parameters(), lr=1e-4, betas=(0.9, 0.99))
+        opt_d = torch.optim.Adam(net_d.parameters(), lr=1e-4, betas=(0.9, 0.99))
+        crit_g, crit_d = CombinedGANLoss().cuda(), DiscriminatorLoss().cuda()
+        lr, hr = torch.rand(1, 1, 32, 32, device="cuda"), torch.rand(1, 1, 128, 128, device="cuda")
+        accum, losses = 2, []
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            for i in range(4):
+                warm = i < 2                                   # warm-up epochs train on L1 only (train_hat.py:236-238)
+                for p in net_d.parameters():
+                    p.requires_grad = False
+                sr = net_g(lr)                                  # fp32 in, no autocast
+                assert sr.dtype == torch.float32
+                l1 = torch.nn.functional.l1_loss(sr, hr)
+                loss_g = l1 if warm else crit_g(sr, hr, net_d(hr).detach(), net_d(sr))[0]
+                (loss_g / accum).backward()
+                if (i + 1) % accum == 0:
+                    opt_g.step(); opt_g.zero_grad()
+                    with torch.no_grad():
+                        for ps, pe in zip(net_g.module.parameters(), net_ema.parameters()):
+                            pe.data.mul_(0.999).add_(ps.data, alpha=0.001)
+                if not warm:
+                    for p in net_d.parameters():
+                        p.requires_grad = True
+                    loss_d, _ = crit_d(net_d(hr), net_d(sr.detach()))
+                    (loss_d / accum).backward()
+                    if (i + 1) % accum == 0:
+                        opt_d.step(); opt_d.zero_grad()
+                losses.append(float(loss_g))
+        assert all(torch.isfinite(torch.tensor(losses))), losses
+        # the fp32 -> bf16 downgrade is announced exactly once (SRK_FP32_POLICY=warn is the default)
+        assert len([m for m in w if issubclass(m.category, RuntimeWarning) and "fp32 input outside autocast" in str(m.message)]) == 1
+        ckpt = tmp_path / "best_hybrid_model.pth"
+        torch.save({"model_state_dict": net_g.state_dict()}, ckpt)             # DDP state_dict: 'module.' prefixes
+        sd = torch.load(ckpt, map_location="cpu")["model_state_dict"]
+        clean = {k.replace("module.", ""): v for k, v in sd.items()}
+        params = _detect_hybrid_params(clean)
+        assert (params["embed_dim"], params["num_feat"], params["num_grow_ch"], params["num_rrdb"], params["depths"]) == (90, 48, 24, 2, (6,))
+        params["img_size"] = 32
+        model = HybridHATRealESRGAN(**params).cuda()
+        model.load_state_dict(clean, strict=True)
+        model.eval()
+        with torch.no_grad():
+            out = torch.clamp(model(lr), 0, 1)
+            ref = torch.clamp(net_g.module.eval()(lr), 0, 1)
+        assert torch.equal(out, ref)                      # same weights, same kernels: bit-identical
+        save_as_tiff16(out, tmp_path / "sr.tiff")
+        back = read_tiff_u16(tmp_path / "sr.tiff")
+        assert back.shape == (128, 128) and back.dtype.name == "uint16"
+        assert abs(float(back.astype("float32").mean()) / 65535.0 - float(out.mean())) < 1e-4
+    finally:
+        dist.destroy_process_group()

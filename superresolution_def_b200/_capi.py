@@ -5,12 +5,15 @@ on a machine without the built .so raises, and every call raises on a non-zero r
 from __future__ import annotations
 
 import ctypes
+import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_longlong, c_void_p
 from pathlib import Path
 
 import torch
 
 _LIB_PATH = Path(__file__).resolve().parent / "_lib" / "libsrk.so"
+if os.environ.get("SRK_LIB"):   # tools only: an instrumented build of the same sources (e.g. -DSRK_TC8_PROFILE)
+    _LIB_PATH = Path(os.environ["SRK_LIB"])
 
 
 class SrkError(RuntimeError):

@@ -180,6 +180,12 @@ win_attn_tc8_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
     const bool masked = a.mask != 0 && a.shift > 0;
     constexpr float kLog2e = 1.4426950408889634f;
     int u = 0;
+#ifdef SRK_TC8_PROFILE
+    long long t_swait = 0, t_ld = 0, t_soft = 0, t_pwrite = 0, t_owait = 0, t_epi = 0, t0 = clock64(), tk;
+#define TC8_TICK(acc) do { tk = clock64(); acc += tk - t0; t0 = tk; } while (0)
+#else
+#define TC8_TICK(acc) do { } while (0)
+#endif
     for (int i = 0; i < my_pairs; ++i) {
       const int wp = int(blockIdx.x) + i * int(gridDim.x);
       const Tc8Win w = tc8_window(a, 2 * wp + wi);
@@ -200,11 +206,14 @@ win_attn_tc8_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
         const int head = hp * 2 + hh;
         const int buf = u & 1;
         const float* tb = s_table + head * 225 + yi * 15 + xi;
+        TC8_TICK(t_epi);
         mbar_wait(s_full(buf, hh), (uint32_t(u) >> 1) & 1u);
         tc_fence_after();
+        TC8_TICK(t_swait);
         uint32_t sv[64];
         tmem_ld_x64(tmem_base + lane_sel + uint32_t(buf * 256 + hh * 128 + wi * 64), sv);
         tmem_ld_wait();
+        TC8_TICK(t_ld);
         float mx = -INFINITY;
 #pragma unroll
         for (int j = 0; j < 64; ++j) {
@@ -221,6 +230,7 @@ win_attn_tc8_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
           sum += e;
         }
         const float inv = fast_rcp(sum);
+        TC8_TICK(t_soft);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           uint32_t o[4];
@@ -233,9 +243,11 @@ win_attn_tc8_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
         fence_proxy_async();    // P (generic-proxy stores) -> visible to the tensor core's async-proxy reads
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full(hh));
+        TC8_TICK(t_pwrite);
         // ---- O = P V (this head's 32 columns of the 64-channel result)
         mbar_wait(o_full(buf, hh), (uint32_t(u) >> 1) & 1u);
         tc_fence_after();
+        TC8_TICK(t_owait);
         uint32_t ov[32];
         tmem_ld_x32(tmem_base + lane_sel + uint32_t(buf * 256 + hh * 128 + hh * 32), ov);
         tmem_ld_wait();

@@ -30,6 +30,7 @@ static int launch_gemm_tn(const GemmArgs& a, const CUtensorMap& tA, const CUtens
 
 static int pick_bn(int epi, int N) {
   if (epi == EPI_RES_LN || epi == EPI_LNBWD) return (N == 192) ? 192 : (N == 128 ? 128 : -1);
+  if (epi == EPI_MUL && N % 192 == 0) return 192;  // 3-stage operand ring + 4 multiplier boxes in flight fit shared memory
   if (epi == EPI_GELU2 || epi == EPI_MUL || epi == EPI_GELU1) return (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : -1);
   if (epi == EPI_MULG) return (N % 128 == 0) ? 128 : -1;  // two double-buffered accumulators: 4 * BN <= 512 TMEM columns
   if (N % 192 == 0) return 192;
@@ -102,6 +103,7 @@ extern "C" int srk_gemm_tn(int epi, int M, int N, int K, const void* A, int lda,
   SRK_CASE(128, EPI_GELU2)
   SRK_CASE(256, EPI_GELU2)
   SRK_CASE(128, EPI_MUL)
+  SRK_CASE(192, EPI_MUL)
   SRK_CASE(256, EPI_MUL)
   SRK_CASE(128, EPI_GELU1)
   SRK_CASE(256, EPI_GELU1)

@@ -5,13 +5,17 @@
 // Mlp.fc1/fc2 (:19-25), and their autograd input-gradients; the fused epilogues replace
 // LayerNorm (:127,150), GELU (:20), the residual adds (:149-150) and their backward passes.
 //
-// Roles (320 threads, 1 CTA/SM, persistent over output tiles):
+// Roles (1 CTA/SM, persistent over output tiles):
 //   warp 0   : TMA producer   (A [128 x 64] + B [BN x 64] bf16 boxes, 128B swizzle, mbarrier ring)
 //   warp 1   : MMA issuer     (one lane issues tcgen05.mma 128 x BN x 16; accumulators double-buffered in TMEM)
-//   warps 2-9 (row epilogues) / 2-17 (elementwise epilogues): tcgen05.ld -> registers -> math -> swizzled smem ->
-//              TMA store.  A warp reaches TMEM lanes 32*(warp%4)..+31 only, so 2 (or 4) warps share each lane quarter
-//              and split the columns of every 64-column box; the elementwise epilogues are issue/latency bound
-//              (ncu: 8 warps left the SM at 58 % issue utilisation), hence 16 warps there.
+//   row epilogues (RES_LN, LNBWD; 320 threads): warps 2-9: tcgen05.ld -> registers -> math -> swizzled smem -> TMA store.
+//   elementwise ("box") epilogues (STORE, GELU*, MUL*; 640 threads): warp 2 = store warp (one lane issues the TMA store
+//              of every finished 64-column box and hands the staging slot back), warp 3 = aux warp (MUL: one lane streams
+//              the multiplier boxes through a ring of kAuxSlots buffers, several boxes ahead of the epilogue), warps
+//              4-19 = 16 epilogue warps.  The epilogue warps never synchronise with each other: every hand-over is an
+//              mbarrier (staging slot full / empty, aux box full / empty), so a warp only ever waits for data.
+//   A warp reaches TMEM lanes 32*(warp%4)..+31 only, so 2 (or 4) warps share each lane quarter and split the columns of
+//   every 64-column box.
 #pragma once
 #include "srk_ptx.cuh"
 
@@ -54,15 +58,16 @@ struct GemmCfg {
   static constexpr int kAccs = (EPI == EPI_MULG) ? 2 : 1;  // accumulators per tile (each double-buffered in TMEM)
   static constexpr int kEpiWarps = kBoxEpi ? 16 : 8;
   static constexpr int kEpiThreads = 32 * kEpiWarps;
-  static constexpr int kThreads = 64 + kEpiThreads;
+  static constexpr int kFirstEpiWarp = kBoxEpi ? 4 : 2;   // box epilogues: warp 2 = store warp, warp 3 = aux warp
+  static constexpr int kThreads = 32 * kFirstEpiWarp + kEpiThreads;
+  static constexpr int kOutPerBox = (EPI == EPI_GELU2) ? 2 : 1;   // boxes written per 64-column step
+  static constexpr int kOutSlots = 2;                             // staging ring (slot = kOutPerBox boxes)
+  static constexpr int kAuxSlots = (EPI == EPI_MUL) ? 4 : 0;      // multiplier boxes in flight (HBM latency x bandwidth)
   static constexpr int kParts = kEpiWarps / 4;        // warps sharing one TMEM lane quarter
   static constexpr int kColsPerPart = 64 / kParts;    // columns of a 64-column box handled by one warp
   static constexpr int kStageBytes = GEMM_BM * 128 + BN * 128;
   static constexpr int kBoxes = BN / 64;
-  static constexpr int kEpiBytes = (EPI == EPI_STORE || EPI == EPI_GELU1 || EPI == EPI_MULG) ? 2 * BOX_BYTES
-                                   : (EPI == EPI_GELU2) ? 4 * BOX_BYTES
-                                   : (EPI == EPI_MUL)   ? 4 * BOX_BYTES
-                                                        : 2 * kBoxes * BOX_BYTES;
+  static constexpr int kEpiBytes = kBoxEpi ? (kAuxSlots + kOutSlots * kOutPerBox) * BOX_BYTES : 2 * kBoxes * BOX_BYTES;
   static constexpr int kRedBytes = 2 * 2 * 128 * 4;  // cross-half row reductions
   static constexpr int kBudget = 232448 - 1024 /*align slack*/ - 512 /*barriers*/ - 2304 /*static smem*/ - kRedBytes;
   static constexpr int kStagesRaw = (kBudget - kEpiBytes) / kStageBytes;
@@ -135,6 +140,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * S + 2 + a); };
   auto aux_bar = [&](int b) { return bar_base + 8u * (2 * S + 4 + b); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * S + 6);
+  // box epilogues: staging-slot and aux-box hand-over barriers (2 S + 8 ... 2 S + 31 < 64 slots of the 512-byte region)
+  auto ofull_bar = [&](int s_) { return bar_base + 8u * (2 * S + 8 + s_); };
+  auto oempty_bar = [&](int s_) { return bar_base + 8u * (2 * S + 12 + s_); };
+  auto afull_bar = [&](int s_) { return bar_base + 8u * (2 * S + 16 + s_); };
+  auto aempty_bar = [&](int s_) { return bar_base + 8u * (2 * S + 24 + s_); };
   const uint32_t red_base = bar_base + 512;
 
   __shared__ __align__(16) float s_gamma[256];
@@ -159,6 +169,16 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), Cfg::kEpiWarps);
       mbar_init(aux_bar(a), 1);
+    }
+    if constexpr (Cfg::kBoxEpi) {
+      for (int a = 0; a < Cfg::kOutSlots; ++a) {
+        mbar_init(ofull_bar(a), Cfg::kEpiWarps);
+        mbar_init(oempty_bar(a), 1);
+      }
+      for (int a = 0; a < Cfg::kAuxSlots; ++a) {
+        mbar_init(afull_bar(a), 1);
+        mbar_init(aempty_bar(a), Cfg::kEpiWarps);
+      }
     }
     fence_mbar_init();
   }
@@ -236,14 +256,51 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         umma_commit(tfull_bar(acc));
       }
     }
+  } else if (Cfg::kBoxEpi && warp == 2) {
+    // ------------------------------------------------------------------ store warp (box epilogues)
+    if (lane == 0) {
+      uint32_t g = 0;   // global box counter: the epilogue warps walk the same sequence
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * GEMM_BM;
+        const int n0 = (tile % n_tiles) * BN;
+        for (int j = 0; j < NBOX; ++j, ++g) {
+          const uint32_t slot = g % Cfg::kOutSlots;
+          const uint32_t src = epi_base + (Cfg::kAuxSlots + slot * Cfg::kOutPerBox) * BOX_BYTES;
+          mbar_wait(ofull_bar(slot), (g / Cfg::kOutSlots) & 1u);
+          tma_store_2d(&tmC, src, n0 + j * 64, m0);
+          if constexpr (EPI == EPI_GELU2) tma_store_2d(&tmC2, src + BOX_BYTES, n0 + j * 64, m0);
+          tma_store_commit();
+          tma_store_wait_read<0>();          // the slot has left shared memory: hand it back
+          mbar_arrive(oempty_bar(slot));
+        }
+      }
+      tma_store_wait_all<0>();
+    }
+  } else if (Cfg::kBoxEpi && warp == 3) {
+    // ------------------------------------------------------------------ aux warp (MUL: multiplier boxes, kAuxSlots deep)
+    if constexpr (EPI == EPI_MUL) {
+      if (lane == 0) {
+        uint32_t g = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          const int m0 = (tile / n_tiles) * GEMM_BM;
+          const int n0 = (tile % n_tiles) * BN;
+          for (int j = 0; j < NBOX; ++j, ++g) {
+            const uint32_t slot = g % Cfg::kAuxSlots;
+            mbar_wait(aempty_bar(slot), ((g / Cfg::kAuxSlots) & 1u) ^ 1u);
+            mbar_arrive_expect_tx(afull_bar(slot), BOX_BYTES);
+            tma_load_2d(epi_base + slot * BOX_BYTES, &tmX1, afull_bar(slot), n0 + j * 64, m0);
+          }
+        }
+      }
+    }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..9)
-    // Two warps share each TMEM lane quarter (hardware: a warp reaches lanes 32*(warp%4)..+31) and split the
-    // columns between them ("half"), so every SM sub-partition hosts two epilogue warps.
+    // ------------------------------------------------------------------ epilogue warps
+    // Two (or four) warps share each TMEM lane quarter (hardware: a warp reaches lanes 32*(warp%4)..+31) and split the
+    // columns between them ("half"), so every SM sub-partition hosts two (four) epilogue warps.
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;   // column part: 0: warps 2-5, 1: warps 6-9 (, 2: 10-13, 3: 14-17)
-    const int row = q * 32 + lane;      // accumulator row owned by this thread (shared with the other half)
-    const bool elected = (threadIdx.x == 64);
+    const int half = (warp - Cfg::kFirstEpiWarp) >> 2;   // column part of this warp inside every 64-column box
+    const int row = q * 32 + lane;      // accumulator row owned by this thread (shared with the other parts)
+    const bool elected = (threadIdx.x == 32 * Cfg::kFirstEpiWarp);
     const uint32_t lane_sel = uint32_t(q * 32) << 16;
     int it = 0;
     uint32_t box_counter = 0;           // box-granular staging ring position
@@ -257,14 +314,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // cross-half row reductions (row epilogues): red[k][half][row]
     float* s_red = reinterpret_cast<float*>(smem_raw + (red_base - smem_u32(smem_raw)));
 
-    // aux prefetch for the first tile
-    if constexpr (EPI == EPI_MUL) {
-      if (elected && blockIdx.x < num_tiles) {
-        const int m0 = (blockIdx.x / n_tiles) * GEMM_BM, n0 = (blockIdx.x % n_tiles) * BN;
-        mbar_arrive_expect_tx(aux_bar(0), BOX_BYTES);
-        tma_load_2d(epi_base, &tmX1, aux_bar(0), n0, m0);
-      }
-    }
+    // aux prefetch for the first tile (row epilogues)
     if constexpr (EPI == EPI_RES_LN || EPI == EPI_LNBWD) {
       if (elected && blockIdx.x < num_tiles) {
         const int m0 = (blockIdx.x / n_tiles) * GEMM_BM, n0 = (blockIdx.x % n_tiles) * BN;
@@ -290,122 +340,104 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
       if constexpr (Cfg::kBoxEpi) {
         // ---------------------------------------------------------- box-granular elementwise epilogues
-        constexpr int kAuxOff = 0;                                     // MUL: 2 aux boxes first
-        constexpr int kOutOff = (EPI == EPI_MUL) ? 2 * BOX_BYTES : 0;  // then staging ring
-        constexpr int kOutPerBox = (EPI == EPI_GELU2) ? 2 : 1;
-#pragma unroll 1
+        // Per 64-column box: accumulator columns (prefetched from TMEM during the previous box) -> math -> this warp's
+        // 16 columns of the staging slot -> arrive on the slot's "full" barrier (the store warp issues the TMA store).
+        constexpr int CPP = Cfg::kColsPerPart;
+        uint32_t rb[2][CPP];
+        uint32_t rub[2][(EPI == EPI_MULG) ? CPP : 1];
+        tmem_ld_cols(taddr + uint32_t(half * CPP), rb[0]);
+        if constexpr (EPI == EPI_MULG) tmem_ld_cols(taddr + uint32_t(BN + half * CPP), rub[0]);
+#pragma unroll
         for (int j = 0; j < NBOX; ++j) {
-          const uint32_t ring = box_counter & 1u;
-          const uint32_t out0 = epi_base + kOutOff + ring * (kOutPerBox * BOX_BYTES);
-          if (elected) {
-            tma_store_wait_read<1>();
-            if constexpr (EPI == EPI_MUL) {
-              // prefetch the next aux box (next box of this tile, or box 0 of the next tile)
-              int nm0 = m0, nn0 = n0 + (j + 1) * 64;
-              bool have = true;
-              if (j + 1 == NBOX) {
-                have = next_tile < num_tiles;
-                nm0 = (next_tile / n_tiles) * GEMM_BM;
-                nn0 = (next_tile % n_tiles) * BN;
-              }
-              if (have) {
-                const uint32_t nb = (aux_count + 1) & 1u;
-                mbar_arrive_expect_tx(aux_bar(nb), BOX_BYTES);
-                tma_load_2d(epi_base + kAuxOff + nb * BOX_BYTES, &tmX1, aux_bar(nb), nn0, nm0);
-              }
-            }
+          uint32_t (&r)[CPP] = rb[j & 1];
+          uint32_t (&ru)[(EPI == EPI_MULG) ? CPP : 1] = rub[j & 1];
+          tmem_ld_wait();
+          if (j + 1 < NBOX) {   // next box's columns travel while this box is computed
+            tmem_ld_cols(taddr + uint32_t((j + 1) * 64 + half * CPP), rb[(j + 1) & 1]);
+            if constexpr (EPI == EPI_MULG) tmem_ld_cols(taddr + uint32_t(BN + (j + 1) * 64 + half * CPP), rub[(j + 1) & 1]);
+          } else {              // accumulator fully drained into registers: hand TMEM back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
           }
-          named_bar_sync(1, Cfg::kEpiThreads);
+          const uint32_t slot = box_counter % Cfg::kOutSlots;
+          const uint32_t out0 = epi_base + (Cfg::kAuxSlots + slot * Cfg::kOutPerBox) * BOX_BYTES;
           uint32_t aux_addr = 0;
           if constexpr (EPI == EPI_MUL) {
-            const uint32_t ab = aux_count & 1u;
-            mbar_wait(aux_bar(ab), (aux_count >> 1) & 1u);
-            aux_addr = epi_base + kAuxOff + ab * BOX_BYTES;
+            const uint32_t as = box_counter % Cfg::kAuxSlots;
+            mbar_wait(afull_bar(as), (box_counter / Cfg::kAuxSlots) & 1u);
+            aux_addr = epi_base + as * BOX_BYTES;
           }
-          {
-            constexpr int CPP = Cfg::kColsPerPart;
-            uint32_t r[CPP];
-            uint32_t ru[(EPI == EPI_MULG) ? CPP : 1];
-            tmem_ld_cols(taddr + uint32_t(j * 64 + half * CPP), r);
-            if constexpr (EPI == EPI_MULG) tmem_ld_cols(taddr + uint32_t(BN + j * 64 + half * CPP), ru);
-            tmem_ld_wait();
-            if (j == NBOX - 1) {  // accumulator fully drained into registers: hand TMEM back to the MMA warp
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(tempty_bar(acc));
-            }
+          mbar_wait(oempty_bar(slot), ((box_counter / Cfg::kOutSlots) & 1u) ^ 1u);
 #pragma unroll
-            for (int i = 0; i < CPP / 8; ++i) {
-              const int ch = half * (CPP / 8) + i;
-              const uint32_t off = swz(row, ch);
-              float v[8];
+          for (int i = 0; i < CPP / 8; ++i) {
+            const int ch = half * (CPP / 8) + i;
+            const uint32_t off = swz(row, ch);
+            float v[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[i * 8 + e]);
-              if constexpr (EPI == EPI_STORE) {
-                sts128(out0 + off, make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
-                                              pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7])));
-              } else if constexpr (EPI == EPI_MUL) {
-                const uint4 g = lds128(aux_addr + off);
-                const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
-                uint32_t o[4];
+            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[i * 8 + e]);
+            if constexpr (EPI == EPI_STORE) {
+              sts128(out0 + off, make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
+                                            pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7])));
+            } else if constexpr (EPI == EPI_MUL) {
+              const uint4 g = lds128(aux_addr + off);
+              const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+              uint32_t o[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                  o[e] = pack_bf16(round_bf16(v[2 * e]) * bf16_lo(gw[e]), round_bf16(v[2 * e + 1]) * bf16_hi(gw[e]));
-                sts128(out0 + off, make_uint4(o[0], o[1], o[2], o[3]));
-              } else if constexpr (EPI == EPI_MULG) {
-                const int col0 = n0 + j * 64 + ch * 8;
-                float o[8];
+              for (int e = 0; e < 4; ++e)
+                o[e] = pack_bf16(round_bf16(v[2 * e]) * bf16_lo(gw[e]), round_bf16(v[2 * e + 1]) * bf16_hi(gw[e]));
+              sts128(out0 + off, make_uint4(o[0], o[1], o[2], o[3]));
+            } else if constexpr (EPI == EPI_MULG) {
+              const int col0 = n0 + j * 64 + ch * 8;
+              float o[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  float a_, g_;
-                  gelu_pair(__uint_as_float(ru[i * 8 + e]), a_, g_);   // same fp32 accumulator value the forward saw
-                  o[e] = round_bf16(v[e]) * round_bf16(g_);
-                }
-                if (args.ones_col >= col0 && args.ones_col < col0 + 8) {
-#pragma unroll
-                  for (int e = 0; e < 8; ++e)
-                    if (col0 + e == args.ones_col) o[e] = 0.0f;   // the forward's constant 1.0 column has no gradient
-                }
-                sts128(out0 + off, make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]),
-                                              pack_bf16(o[6], o[7])));
-              } else if constexpr (EPI == EPI_GELU1) {
-                float a[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) { float g_; gelu_pair(v[e], a[e], g_); }
-                const int col0 = n0 + j * 64 + ch * 8;
-                if (args.ones_col >= col0 && args.ones_col < col0 + 8) {
-#pragma unroll
-                  for (int e = 0; e < 8; ++e)
-                    if (col0 + e == args.ones_col) a[e] = 1.0f;
-                }
-                sts128(out0 + off, make_uint4(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]),
-                                              pack_bf16(a[4], a[5]), pack_bf16(a[6], a[7])));
-              } else {  // EPI_GELU2
-                float a[8], g[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) gelu_pair(v[e], a[e], g[e]);
-                const int col0 = n0 + j * 64 + ch * 8;
-                if (args.ones_col >= col0 && args.ones_col < col0 + 8) {
-#pragma unroll
-                  for (int e = 0; e < 8; ++e)
-                    if (col0 + e == args.ones_col) { a[e] = 1.0f; g[e] = 0.0f; }
-                }
-                sts128(out0 + off, make_uint4(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]),
-                                              pack_bf16(a[4], a[5]), pack_bf16(a[6], a[7])));
-                sts128(out0 + BOX_BYTES + off, make_uint4(pack_bf16(g[0], g[1]), pack_bf16(g[2], g[3]),
-                                                          pack_bf16(g[4], g[5]), pack_bf16(g[6], g[7])));
+              for (int e = 0; e < 8; ++e) {
+                float a_, g_;
+                gelu_pair(__uint_as_float(ru[i * 8 + e]), a_, g_);   // same fp32 accumulator value the forward saw
+                o[e] = round_bf16(v[e]) * round_bf16(g_);
               }
+              if (args.ones_col >= col0 && args.ones_col < col0 + 8) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                  if (col0 + e == args.ones_col) o[e] = 0.0f;   // the forward's constant 1.0 column has no gradient
+              }
+              sts128(out0 + off, make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]),
+                                            pack_bf16(o[6], o[7])));
+            } else if constexpr (EPI == EPI_GELU1) {
+              float a[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) { float g_; gelu_pair(v[e], a[e], g_); }
+              const int col0 = n0 + j * 64 + ch * 8;
+              if (args.ones_col >= col0 && args.ones_col < col0 + 8) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                  if (col0 + e == args.ones_col) a[e] = 1.0f;
+              }
+              sts128(out0 + off, make_uint4(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]),
+                                            pack_bf16(a[4], a[5]), pack_bf16(a[6], a[7])));
+            } else {  // EPI_GELU2
+              float a[8], g[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) gelu_pair(v[e], a[e], g[e]);
+              const int col0 = n0 + j * 64 + ch * 8;
+              if (args.ones_col >= col0 && args.ones_col < col0 + 8) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                  if (col0 + e == args.ones_col) { a[e] = 1.0f; g[e] = 0.0f; }
+              }
+              sts128(out0 + off, make_uint4(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]),
+                                            pack_bf16(a[4], a[5]), pack_bf16(a[6], a[7])));
+              sts128(out0 + BOX_BYTES + off, make_uint4(pack_bf16(g[0], g[1]), pack_bf16(g[2], g[3]),
+                                                        pack_bf16(g[4], g[5]), pack_bf16(g[6], g[7])));
             }
           }
-          fence_proxy_async();
-          named_bar_sync(1, Cfg::kEpiThreads);
-          if (elected) {
-            tma_store_2d(&tmC, out0, n0 + j * 64, m0);
-            if constexpr (EPI == EPI_GELU2) tma_store_2d(&tmC2, out0 + BOX_BYTES, n0 + j * 64, m0);
-            tma_store_commit();
+          fence_proxy_async();   // this thread's staging stores -> visible to the TMA store (async proxy)
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(ofull_bar(slot));
+            if constexpr (EPI == EPI_MUL) mbar_arrive(aempty_bar(box_counter % Cfg::kAuxSlots));
           }
           ++box_counter;
-          if constexpr (EPI == EPI_MUL) ++aux_count;
         }
       } else {
         // ---------------------------------------------------------- full-row epilogues (BN covers the row)
@@ -620,7 +652,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             s_part[(3 * 2 + w) * BN + c];
       }
     }
-    if (elected) tma_store_wait_all<0>();
+    if (!Cfg::kBoxEpi && elected) tma_store_wait_all<0>();
   }
 
   tc_fence_before();

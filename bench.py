@@ -204,7 +204,7 @@ def roofline_probe(batch: int, peaks):
     geom = capi.SrkGeom(batch, 128, 128, 8, 4)
     parts = torch.empty(capi.gemm_grid(M, C) * 2 * C, device=dev)
     capi.layernorm_fwd(x192, o192, stats, gam, bet, 180, ones_col=180)  # valid (mean, rstd) for the LNBWD runs
-    wg_ws = torch.empty(148 * 128 * 256, device=dev)
+    wg_ws = torch.empty(148 * 256 * 256, device=dev)
     wg_out = torch.empty(768 * 256, device=dev)
     dtab = torch.empty_like(table)
     ln_res = capi.make_ln_args(180, 180, gam, bet, stats=stats)
@@ -213,7 +213,7 @@ def roofline_probe(batch: int, peaks):
     E = 2  # bytes per element
 
     def splits(T, ca):
-        return max(1, min(148 // ((ca + 127) // 128), T // 64))
+        return capi.wgrad_splits(T, ca)
 
     cases = [
         ("gemm_tn<192,STORE> qkv", "gemm_tn_kernel<STORE>", 1, lambda: capi.gemm_tn(capi.EPI_STORE, x192, w_qkv, o576), M * (C + QW) * E),

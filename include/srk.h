@@ -63,10 +63,13 @@ int srk_gemm_grid(int M, int N);
 
 /* dW[Ca,Cb] (fp32) = sum_t A[t,ca] * B[t,cb] over T tokens: tcgen05 GEMM with MN-major operands.
  * Replaces autograd's weight/bias gradient of nn.Linear (same lines as above).
- * Cb in {64,128,192,256}; T % 64 == 0, 1 <= splits <= T/64; workspace >= splits*ceil(Ca/128)*128*Cb floats;
+ * Cb in {64,128,192,256}; T % 64 == 0, 1 <= splits <= T/64 (token ranges reduced by a second tiny kernel;
+ * srk_gemm_wgrad_splits gives the count that fills the GPU); workspace >= srk_gemm_wgrad_workspace_elems floats;
  * out is [ceil(Ca/128)*128, Cb] fp32 (rows >= Ca are zero). */
 int srk_gemm_wgrad(int T, int Ca, int Cb, const void* A, int lda, const void* B, int ldb, float* workspace,
                    int splits, float* out, void* stream);
+int srk_gemm_wgrad_splits(int T, int Ca);
+long long srk_gemm_wgrad_workspace_elems(int Ca, int Cb, int splits);
 
 /* Fused MLP half of a block, forward: x_out = resid + drop * fc2(gelu(fc1(xn2))), xn_out = LayerNorm_next(x_out), in ONE
  * tcgen05 kernel — the hidden activation goes from the fc1 accumulator (TMEM) through GELU into shared-memory boxes that

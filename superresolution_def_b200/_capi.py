@@ -59,6 +59,9 @@ _gemm_tn = _sig("srk_gemm_tn", [c_int, c_int, c_int, c_int, c_void_p, c_int, c_v
 _gemm_grid = _sig("srk_gemm_grid", [c_int, c_int])
 _gemm_wgrad = _sig("srk_gemm_wgrad", [c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
                                        c_void_p, c_void_p])
+_wgrad_splits = _sig("srk_gemm_wgrad_splits", [c_int, c_int])
+_wgrad_ws_elems = _sig("srk_gemm_wgrad_workspace_elems", [c_int, c_int, c_int])
+_wgrad_ws_elems.restype = c_longlong
 
 _mlp_fwd = _sig("srk_mlp_fwd", [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_int, POINTER(SrkLnArgs), c_void_p])
@@ -153,7 +156,12 @@ def f32_to_u16(src: torch.Tensor, dst: torch.Tensor):
 
 
 def wgrad_workspace_elems(Ca: int, Cb: int, splits: int) -> int:
-    return splits * ((Ca + 127) // 128) * 128 * Cb
+    return int(_wgrad_ws_elems(Ca, Cb, splits))
+
+
+def wgrad_splits(T: int, Ca: int) -> int:
+    """Token ranges that fill the GPU for this shape (the library pairs 128-channel tiles of A per CTA)."""
+    return int(_wgrad_splits(T, Ca))
 
 
 def gemm_wgrad(A, B, workspace, splits, out):

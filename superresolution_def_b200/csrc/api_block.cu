@@ -50,12 +50,7 @@ int qkv_window_map(CUtensorMap* tm, const void* p, const SrkGeom* g, int ld) {
   return make_tmap_nhwc(tm, p, ld, g->W, g->H, g->B, ld, (uint64_t)g->W * ld, (uint64_t)g->H * g->W * ld, 4, 4);
 }
 
-int wgrad_splits(int T, int ca_tiles) {
-  int s = num_sms() / ca_tiles;
-  const int iters = T / 64;
-  if (s > iters) s = iters;
-  return s < 1 ? 1 : s;
-}
+int wgrad_splits(int T, int Ca) { return srk_gemm_wgrad_splits(T, Ca); }
 
 struct WsLayout {  // offsets (floats) into SrkBlockScratch.wg_ws
   long long partials, ext_qkv, ext_proj, ext_fc1, ext_fc2, ln1, ln2, rpb, total;
@@ -88,7 +83,7 @@ WsLayout ws_layout(const SrkBlockDims* d, const SrkGeom* g) {
   WsLayout L{};
   const int QW = 3 * d->heads * d->ds, AW = d->heads * d->ds;
   const long long T = (long long)g->B * g->H * g->W;
-  const long long part = (long long)num_sms() * 128 * 256;  // ca_tiles*splits <= num_sms, Cb <= 256
+  const long long part = (long long)num_sms() * 256 * 256;  // groups*splits <= num_sms, <= 256 channels of A per group, Cb <= 256
   long long o = 0;
   L.partials = o; o += part;
   L.ext_qkv = o; o += (long long)((QW + 127) / 128 * 128) * d->Cp;
@@ -494,7 +489,7 @@ static int block_bwd_impl(const SrkBlockDims* d, const SrkGeom* g, const SrkBloc
   }
   if (rc) return rc;
   // dW2^T (+db2 in row `hidden`) = act^T @ g_out
-  const int s_fc = wgrad_splits(T, Hp / 128);
+  const int s_fc = wgrad_splits(T, Hp);
   if ((rc = srk_gemm_wgrad(T, Hp, Cp, a->act, Hp, g_mlp, Cp, ws + L.partials, s_fc, ws + L.ext_fc2, stream_))) return rc;
   // g_mid = g_out + LN2bwd(dU @ W1)
   SrkLnArgs ln2{d->C, -1, p->norm2_w, nullptr, a->stats2, ws + L.ln2, 1e-5f, nullptr, 1};
@@ -509,7 +504,7 @@ static int block_bwd_impl(const SrkBlockDims* d, const SrkGeom* g, const SrkBloc
                         nullptr, 0, nullptr, stream_)))
     return rc;
   // dWproj (+dbproj in column dh) = g_mid^T @ ao
-  if ((rc = srk_gemm_wgrad(T, Cp, AW, g_att, Cp, a->ao, AW, ws + L.partials, wgrad_splits(T, (Cp + 127) / 128),
+  if ((rc = srk_gemm_wgrad(T, Cp, AW, g_att, Cp, a->ao, AW, ws + L.partials, wgrad_splits(T, Cp),
                            ws + L.ext_proj, stream_)))
     return rc;
   // attention backward -> d_qkv, rpb-table gradient (ws 8: per-CTA partials folded by the unpack kernel below)
@@ -540,7 +535,7 @@ static int block_bwd_impl(const SrkBlockDims* d, const SrkGeom* g, const SrkBloc
       return rc;
   }
   // dWqkv (+dbqkv in column C) = d_qkv^T @ xn1
-  if ((rc = srk_gemm_wgrad(T, QW, Cp, s->d_qkv, QW, a->xn1, Cp, ws + L.partials, wgrad_splits(T, (QW + 127) / 128),
+  if ((rc = srk_gemm_wgrad(T, QW, Cp, s->d_qkv, QW, a->xn1, Cp, ws + L.partials, wgrad_splits(T, QW),
                            ws + L.ext_qkv, stream_)))
     return rc;
   // scatter everything into reference-shaped fp32 gradients

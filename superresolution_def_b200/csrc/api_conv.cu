@@ -96,7 +96,7 @@ int conv_halo_mode() {
 
 template <int BNW>
 int launch_conv_wgrad(const ConvWgradMaps& maps, const ConvWgradArgs& a, cudaStream_t stream) {
-  using Cfg = WgradCfg<BNW>;
+  using Cfg = WgradCfg<BNW, 1>;
   static DeviceOnce configured;
   if (configured.need()) {
     SRK_CUDA_OK(cudaFuncSetAttribute(conv3x3_wgrad_kernel<BNW>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -1,4 +1,5 @@
 // api_gemm.cu — C-ABI entry points for the tcgen05 GEMMs (forward/dgrad and wgrad).
+#include <cstdlib>
 #include "gemm_tn.cuh"
 #include "gemm_wgrad.cuh"
 #include "mlp_fused.cuh"
@@ -21,8 +22,12 @@ static int launch_gemm_tn(const GemmArgs& a, const CUtensorMap& tA, const CUtens
   }
   const int tiles = (a.M / GEMM_BM) * (a.N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
+  GemmArgs args = a;
+  // K <= 192: B ([BN x K] per N tile) stays resident in shared memory, the ring carries A only (SRK_GEMM_BRES=0: A/B switch)
+  static const bool bres_enabled = [] { const char* e = getenv("SRK_GEMM_BRES"); return !(e && e[0] == '0'); }();
+  args.b_resident = (bres_enabled && Cfg::kResOk && a.K <= 3 * GEMM_BK && grid >= a.N / BN) ? 1 : 0;
   SRK_CUDA_OK(launch_pdl(gemm_tn_kernel<BN, EPI>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, stream, tA, tB, tC, tC2,
-                         tX1, tX2, a));
+                         tX1, tX2, args));
   SRK_LAUNCHED(1);
   SRK_CUDA_OK(cudaGetLastError());
   return SRK_OK;
@@ -116,20 +121,29 @@ extern "C" int srk_gemm_tn(int epi, int M, int N, int K, const void* A, int lda,
   return fail(SRK_ERR_UNSUPPORTED, "srk_gemm_tn: no kernel instance for (BN, epilogue)");
 }
 
-template <int BNW>
+template <int BNW, int AT>
 static int launch_wgrad(const WgradArgs& a, const CUtensorMap& tA, const CUtensorMap& tB, cudaStream_t stream) {
-  using Cfg = WgradCfg<BNW>;
+  using Cfg = WgradCfg<BNW, AT>;
   static DeviceOnce configured;
   if (configured.need()) {
-    SRK_CUDA_OK(cudaFuncSetAttribute(gemm_wgrad_kernel<BNW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SRK_CUDA_OK(cudaFuncSetAttribute(gemm_wgrad_kernel<BNW, AT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      Cfg::kSmemBytes));
     configured.done();
   }
-  SRK_CUDA_OK(launch_pdl(gemm_wgrad_kernel<BNW>, dim3(a.ca_tiles * a.splits), dim3(WG_THREADS), Cfg::kSmemBytes, stream, tA,
+  SRK_CUDA_OK(launch_pdl(gemm_wgrad_kernel<BNW, AT>, dim3(a.ca_groups * a.splits), dim3(WG_THREADS), Cfg::kSmemBytes, stream, tA,
                          tB, a));
   SRK_LAUNCHED(1);
   SRK_CUDA_OK(cudaGetLastError());
   return SRK_OK;
+}
+
+// channels of A per CTA: two 128-row accumulators whenever A has more than 128 channels (one B box feeds both)
+// channels of A per CTA.  Two 128-row accumulators per CTA (every B box feeds both) were measured SLOWER at the block's
+// shapes (fc 95 vs 87 us, qkv 80 vs 76 us, proj 53 vs 45 us: same tensor time, one pipeline stage less), so one tile per
+// CTA is the default and SRK_WGRAD_AT=2 the switch that reproduces the measurement.
+static int wgrad_at(int Ca) {
+  static const int forced = getenv("SRK_WGRAD_AT") ? atoi(getenv("SRK_WGRAD_AT")) : 0;
+  return (forced == 2 && Ca > 128) ? 2 : 1;
 }
 
 // MN-major, 128B swizzle: LBO = distance between 64-channel groups (one [64 tok x 128 B] box),
@@ -141,26 +155,46 @@ static int gemm_wgrad_impl(int T, int Ca, int Cb, const void* A, int lda, const 
   if (splits <= 0 || T <= 0 || T % WG_TOK != 0 || splits > T / WG_TOK)
     return fail(SRK_ERR_ARG, "srk_gemm_wgrad: T must be a multiple of 64 and 1 <= splits <= T/64");
   if (!A || !B || !workspace || !out) return fail(SRK_ERR_ARG, "srk_gemm_wgrad: null pointer");
+  const int at = wgrad_at(Ca);
   WgradArgs a{};
-  a.T = T; a.Ca = Ca; a.Cb = Cb; a.ca_tiles = (Ca + 127) / 128; a.splits = splits; a.partials = workspace;
+  a.T = T; a.Ca = Ca; a.Cb = Cb; a.ca_groups = (Ca + at * 128 - 1) / (at * 128); a.splits = splits; a.partials = workspace;
   a.lbo_bytes = lbo_bytes; a.sbo_bytes = sbo_bytes;
   CUtensorMap tA, tB;
   int rc;
   if ((rc = make_tmap_2d(&tA, A, T, Ca, lda, WG_TOK))) return rc;
   if ((rc = make_tmap_2d(&tB, B, T, Cb, ldb, WG_TOK))) return rc;
+#define SRK_WG(CB_) \
+  case CB_: rc = (at == 2) ? launch_wgrad<CB_, 2>(a, tA, tB, stream) : launch_wgrad<CB_, 1>(a, tA, tB, stream); break;
   switch (Cb) {
-    case 64: rc = launch_wgrad<64>(a, tA, tB, stream); break;
-    case 128: rc = launch_wgrad<128>(a, tA, tB, stream); break;
-    case 192: rc = launch_wgrad<192>(a, tA, tB, stream); break;
-    case 256: rc = launch_wgrad<256>(a, tA, tB, stream); break;
+    SRK_WG(64)
+    SRK_WG(128)
+    SRK_WG(192)
+    SRK_WG(256)
     default: return fail(SRK_ERR_UNSUPPORTED, "srk_gemm_wgrad: Cb must be 64/128/192/256");
   }
+#undef SRK_WG
   if (rc) return rc;
-  const int n = a.ca_tiles * 128 * Cb;
-  SRK_CUDA_OK(launch_pdl(wgrad_reduce_kernel, dim3((n + 255) / 256), dim3(256), 0, stream, workspace, out, splits, n));
+  const int n = ((Ca + 127) / 128) * 128 * Cb;
+  const size_t split_stride = size_t(a.ca_groups) * at * 128 * Cb;
+  SRK_CUDA_OK(launch_pdl(wgrad_reduce_kernel, dim3((n + 255) / 256), dim3(256), 0, stream, workspace, out, splits, n,
+                         split_stride));
   SRK_LAUNCHED(1);
   SRK_CUDA_OK(cudaGetLastError());
   return SRK_OK;
+}
+
+extern "C" int srk_gemm_wgrad_splits(int T, int Ca) {
+  const int at = wgrad_at(Ca);
+  const int groups = (Ca + at * 128 - 1) / (at * 128);
+  int s = num_sms() / groups;
+  if (s > T / WG_TOK) s = T / WG_TOK;
+  return s < 1 ? 1 : s;
+}
+
+extern "C" long long srk_gemm_wgrad_workspace_elems(int Ca, int Cb, int splits) {
+  const int at = wgrad_at(Ca);
+  const int groups = (Ca + at * 128 - 1) / (at * 128);
+  return (long long)splits * groups * at * 128 * Cb;
 }
 
 extern "C" int srk_gemm_wgrad(int T, int Ca, int Cb, const void* A, int lda, const void* B, int ldb,

@@ -205,14 +205,15 @@ __device__ __forceinline__ void store_frag_t32(uint32_t tile, int r0, int lane, 
   store_frag_pair(tile, r0, 2, lane, o[2], o[3], t32_off);
 }
 
-// Each thread always handles the same two token rows (i0 = tid/4, i1 = i0 + 32) and 16-byte chunk (tid%4) of every
-// [64 x 32] tile, so a window's token addresses are computed once per thread and window (two wrapped coordinates)
-// instead of once per 16-byte transfer.
+// Each thread always handles the same two token rows of a window -- i0 = 16 * warp + lane / 4 and i0 + 8, i.e. rows of the 16-row
+// block its own warp computes -- and 16-byte chunk lane % 4 of every [64 x 32] tile, so a window's token addresses are
+// computed once per thread and window (two wrapped coordinates) and serve the loads AND the warp-private result stores.
 struct WinToks { long long t0, t1; };
+__device__ __forceinline__ int tok_row0() { return ((threadIdx.x >> 5) << 4) + ((threadIdx.x & 31) >> 2); }
 __device__ __forceinline__ WinToks window_toks(const AttnArgs& a, int w) {
   WinToks r;
-  r.t0 = window_token(a, w, threadIdx.x >> 2);
-  r.t1 = window_token(a, w, (threadIdx.x >> 2) + 32);
+  r.t0 = window_token(a, w, tok_row0());
+  r.t1 = window_token(a, w, tok_row0() + 8);
   return r;
 }
 // async-load the q,k,v tiles (column offsets col0 + {0,1,2}*heads*32 of src0) and optionally a 4th tile from src1
@@ -220,8 +221,8 @@ __device__ __forceinline__ void load_window_tiles(const AttnArgs& a, const WinTo
                                                   const __nv_bfloat16* src0, int ld0, int col0,
                                                   const __nv_bfloat16* src1, int ld1, int col1) {
   const int hw = a.heads * 32;
-  const int i0 = threadIdx.x >> 2, ch = threadIdx.x & 3;
-  const uint32_t d0 = dst + t32_off(i0, ch), d1 = dst + t32_off(i0 + 32, ch);
+  const int i0 = tok_row0(), ch = threadIdx.x & 3;
+  const uint32_t d0 = dst + t32_off(i0, ch), d1 = dst + t32_off(i0 + 8, ch);
   const __nv_bfloat16* p0 = src0 + tk.t0 * ld0 + col0 + ch * 8;
   const __nv_bfloat16* p1 = src0 + tk.t1 * ld0 + col0 + ch * 8;
 #pragma unroll
@@ -234,11 +235,24 @@ __device__ __forceinline__ void load_window_tiles(const AttnArgs& a, const WinTo
     cp_async16(d1 + 3 * ATT_TILE, src1 + tk.t1 * ld1 + col1 + ch * 8);
   }
 }
+// A warp's finished [16 x 32] fp32 fragment tile -> bf16 in its private 1 KB staging tile -> 16-byte global stores of its own
+// 16 token rows (columns col .. col+31 of `dst`).  Only the warp itself touches the staging tile: __syncwarp, no CTA barrier.
+__device__ __forceinline__ void store_rows16(uint32_t stage, const uint8_t* stage_ptr, int lane, const float (&o)[4][4],
+                                             __nv_bfloat16* dst, int ld, int col, const WinToks& tk) {
+  __syncwarp();
+  store_frag_t32(stage, 0, lane, o);
+  __syncwarp();
+  const int i = lane >> 2, ch = lane & 3;
+  const uint4 v0 = *reinterpret_cast<const uint4*>(stage_ptr + t32_off(i, ch));
+  const uint4 v1 = *reinterpret_cast<const uint4*>(stage_ptr + t32_off(i + 8, ch));
+  *reinterpret_cast<uint4*>(dst + tk.t0 * ld + col + ch * 8) = v0;
+  *reinterpret_cast<uint4*>(dst + tk.t1 * ld + col + ch * 8) = v1;
+}
 
 // ============================================================================ forward
 __global__ void __launch_bounds__(ATT_THREADS) win_attn_ws8_fwd_kernel(const AttnArgs a) {
   __shared__ __align__(128) uint8_t s_in[2][3 * ATT_TILE];
-  __shared__ __align__(128) uint8_t s_out[ATT_TILE];
+  __shared__ __align__(128) uint8_t s_out[4][1024];   // per-warp staging of its 16 output rows
   __shared__ float s_bias[225];
   pdl_launch_dependents();
   pdl_wait();
@@ -259,14 +273,14 @@ __global__ void __launch_bounds__(ATT_THREADS) win_attn_ws8_fwd_kernel(const Att
   }
   cp_async_commit();
   for (; w < nwin; w += gridDim.x, buf ^= 1, tk = tkn) {
+    cp_async_wait<0>();
+    __syncthreads();   // this window's tiles have landed; every warp is done with the previous window (s_in[buf ^ 1] is free)
     const int wn = w + gridDim.x;
     if (wn < nwin) {
       tkn = window_toks(a, wn);
       load_window_tiles(a, tkn, smem_u32(s_in[buf ^ 1]), a.qkv, a.ld_qkv, h * 32, nullptr, 0, 0);
     }
     cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
     const uint32_t qt = smem_u32(s_in[buf]), kt = qt + ATT_TILE, vt = qt + 2 * ATT_TILE;
     const int r0 = warp * 16;
     float s[8][4];
@@ -279,13 +293,14 @@ __global__ void __launch_bounds__(ATT_THREADS) win_attn_ws8_fwd_kernel(const Att
     softmax_rows(s);
     float o[4][4];
     frag_times_tile(s, vt, lane, o);
-    store_frag_t32(smem_u32(s_out), r0, lane, o);
-    __syncthreads();
+    __syncwarp();
+    store_frag_t32(smem_u32(s_out[warp]), 0, lane, o);
+    __syncwarp();
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-      const int i = (threadIdx.x >> 2) + 32 * k, ch = threadIdx.x & 3;
+      const int i = (lane >> 2) + 8 * k, ch = lane & 3;
       const long long tok = k ? tk.t1 : tk.t0;
-      uint4 v = *reinterpret_cast<const uint4*>(s_out + t32_off(i, ch));
+      uint4 v = *reinterpret_cast<const uint4*>(s_out[warp] + t32_off(i, ch));
       if (ones_here && ch == (ones_c >> 3)) {  // bias-folding column of the following projection := 1.0
         const int word = (ones_c & 7) >> 1;
         const uint32_t keep = (ones_c & 1) ? 0x0000FFFFu : 0xFFFF0000u;
@@ -297,18 +312,16 @@ __global__ void __launch_bounds__(ATT_THREADS) win_attn_ws8_fwd_kernel(const Att
       }
       *reinterpret_cast<uint4*>(a.out + tok * a.ld_o + h * 32 + ch * 8) = v;
     }
-    // s_out / s_in[buf] are rewritten only after the next iteration's __syncthreads or by loads issued
-    // at the top of the next iteration into buf (which every thread has finished reading: barrier below)
-    __syncthreads();
   }
   cp_async_wait<0>();
 }
 
 // ============================================================================ backward
-struct AttnBwdSmem {  // 49.8 KB: four CTAs per SM
-  uint8_t in[2][4 * ATT_TILE];  // q, k, v, dO (double-buffered); the current buffer doubles as dq/dk/dv staging
+struct AttnBwdSmem {  // 61.8 KB: three CTAs per SM (the register file allows three as well)
+  uint8_t in[2][4 * ATT_TILE];  // q, k, v, dO (double-buffered)
   uint8_t p[64 * 128];          // P  (bf16) [q][key]
   uint8_t ds[64 * 128];         // dS (bf16) [q][key]
+  uint8_t stage[4][3][1024];    // per warp: its 16 rows of dq, dk, dv on their way to global memory
   float bias[225];
   float dbias[225];
 };
@@ -364,15 +377,17 @@ __global__ void __launch_bounds__(ATT_THREADS, 3) win_attn_ws8_bwd_kernel(const 
     load_window_tiles(a, tk, smem_u32(sm.in[0]), a.qkv, a.ld_qkv, h * 32, a.dout, a.ld_o, h * 32);
   }
   cp_async_commit();
+  const int hw = a.heads * 32;
+  const uint32_t stg = smem_u32(sm.stage[warp][0]);
   for (; w < nwin; w += gridDim.x, buf ^= 1, tk = tkn) {
+    cp_async_wait<0>();
+    __syncthreads();   // (1) this window's tiles have landed; every warp is done with the previous window (in[buf ^ 1], P, dS free)
     const int wn = w + gridDim.x;
     if (wn < nwin) {
       tkn = window_toks(a, wn);
       load_window_tiles(a, tkn, smem_u32(sm.in[buf ^ 1]), a.qkv, a.ld_qkv, h * 32, a.dout, a.ld_o, h * 32);
     }
     cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
     const uint32_t qt = smem_u32(sm.in[buf]), kt = qt + ATT_TILE, vt = qt + 2 * ATT_TILE, dot = qt + 3 * ATT_TILE;
     const uint32_t pt = smem_u32(sm.p), dst = smem_u32(sm.ds);
     const int r0 = warp * 16;
@@ -426,29 +441,24 @@ __global__ void __launch_bounds__(ATT_THREADS, 3) win_attn_ws8_bwd_kernel(const 
       for (int e = 0; e < 4; ++e) dbacc[nt][e] += s[nt][e];
       if (nt & 1) store_frag_pair(dst, r0, nt - 1, lane, s[nt - 1], s[nt], t64_off);
     }
-    // dQ rows = dS (bf16) * K   (kept in registers until the input tiles are dead)
-    float dq[4][4], dk[4][4], dv[4][4];
-    frag_times_tile(s, kt, lane, dq);
-    __syncthreads();
+    // dQ rows = dS (bf16) * K, straight out through this warp's staging tile
+    {
+      float dq[4][4];
+      frag_times_tile(s, kt, lane, dq);
+      store_rows16(stg, sm.stage[warp][0], lane, dq, a.dqkv, a.ld_qkv, h * 32, tk);
+    }
+    __syncthreads();   // (2) P and dS of all 64 queries are in shared memory
     // ---- phase B: this warp's 16 key rows
-    tileT_times_tile(dst, qt, r0, lane, dk);   // dK = dS^T Q
-    tileT_times_tile(pt, dot, r0, lane, dv);   // dV = P^T dO
-    __syncthreads();                           // every warp is done reading q, k, v, dO, P, dS of this window
-    store_frag_t32(qt, r0, lane, dq);
-    store_frag_t32(qt + ATT_TILE, r0, lane, dk);
-    store_frag_t32(qt + 2 * ATT_TILE, r0, lane, dv);
-    __syncthreads();
-    const int hw = a.heads * 32;
-#pragma unroll
-    for (int tile = 0; tile < 3; ++tile)
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int i = (threadIdx.x >> 2) + 32 * k, ch = threadIdx.x & 3;
-        const long long tok = k ? tk.t1 : tk.t0;
-        const uint4 v = *reinterpret_cast<const uint4*>(sm.in[buf] + tile * ATT_TILE + t32_off(i, ch));
-        *reinterpret_cast<uint4*>(a.dqkv + tok * a.ld_qkv + tile * hw + h * 32 + ch * 8) = v;
-      }
-    __syncthreads();
+    {
+      float dk[4][4];
+      tileT_times_tile(dst, qt, r0, lane, dk);   // dK = dS^T Q
+      store_rows16(stg + 1024, sm.stage[warp][1], lane, dk, a.dqkv, a.ld_qkv, hw + h * 32, tk);
+    }
+    {
+      float dv[4][4];
+      tileT_times_tile(pt, dot, r0, lane, dv);   // dV = P^T dO
+      store_rows16(stg + 2048, sm.stage[warp][2], lane, dv, a.dqkv, a.ld_qkv, 2 * hw + h * 32, tk);
+    }
   }
   cp_async_wait<0>();
   // fold the per-thread dS sums into the (2*8-1)^2 table entries of this head

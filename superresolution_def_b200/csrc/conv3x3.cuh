@@ -314,7 +314,7 @@ struct ConvWgradMaps {
 template <int BNW>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 conv3x3_wgrad_kernel(const __grid_constant__ ConvWgradMaps maps, const ConvWgradArgs args) {
-  using Cfg = WgradCfg<BNW>;
+  using Cfg = WgradCfg<BNW, 1>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;

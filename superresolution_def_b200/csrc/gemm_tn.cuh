@@ -17,6 +17,7 @@
 //   A warp reaches TMEM lanes 32*(warp%4)..+31 only, so 2 (or 4) warps share each lane quarter and split the columns of
 //   every 64-column box.
 #pragma once
+#include <cuda_fp16.h>
 #include "srk_ptx.cuh"
 
 namespace srk {
@@ -50,6 +51,8 @@ struct GemmArgs {
   float eps;
   const float* row_scale;  // EPI_RES_LN, optional: per-sample stochastic-depth factor applied to bf16(acc)
   int rows_per_scale;
+  int b_resident;     // K <= 192: every CTA keeps ONE N tile of B ([BN x K], loaded once) in shared memory and walks M tiles
+                      // only; the operand ring then holds A boxes alone (twice to six times as many bytes of A in flight)
 };
 
 template <int BN, int EPI>
@@ -73,6 +76,11 @@ struct GemmCfg {
   static constexpr int kStagesRaw = (kBudget - kEpiBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
   static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 512 + kRedBytes + 1024;
+  // B-resident mode (K <= 192): [B: 3 boxes of BN x 128 B][A ring][epilogue buffers] inside the same allocation
+  static constexpr int kResBBytes = 3 * BN * 128;
+  static constexpr int kResStagesRaw = (kStages * kStageBytes - kResBBytes) / (GEMM_BM * 128);
+  static constexpr int kResStages = kResStagesRaw > 8 ? 8 : kResStagesRaw;
+  static constexpr bool kResOk = (kAccs == 1) && kResStages >= 2;
   static_assert(kStages >= 2, "not enough shared memory for a 2-stage pipeline");
   static_assert(BN % 64 == 0 && BN <= 256, "BN must be a multiple of 64, <= 256");
   static_assert(2 * kAccs * BN <= 512, "double-buffered accumulators must fit the 512 TMEM columns");
@@ -101,6 +109,33 @@ __device__ __forceinline__ void gelu_pair(float u, float& a, float& g) {
   g = fmaf(uc * fmaf(-th, th, 1.0f), dp, cdf);
 }
 
+// Two elements per instruction: the same fit evaluated in packed fp16 (HFMA2 / one tanh.approx.f16x2 per pair).  fp16 carries
+// 11 significant bits, the results are stored as bf16 (8 bits): |gelu - fp32 path| <= 5e-4 absolute on |u| <= 8, below the
+// bf16 spacing of the stored value wherever the value exceeds 0.25 and below 2.5e-4 in Phi elsewhere (the bound the fp32
+// path already has from tanh.approx).  u^2 is clamped instead of u (t = min(u^2, 64)): beyond |u| = 8 the tanh argument is
+// u * P(64) = 1.84 u >= 14.7, i.e. tanh = +-1, Phi in {0, 1}, gelu' = Phi exactly.
+// Returns gelu(u) and gelu'(u) for the pair (x0, x1) as packed bf16x2 words.
+__device__ __forceinline__ void gelu_pair_h2(float x0, float x1, uint32_t& a_bf, uint32_t& g_bf) {
+  const __half2 a0 = __float2half2_rn(7.97703653e-01f), a1 = __float2half2_rn(3.68205808e-02f), a2 = __float2half2_rn(-3.20923304e-04f);
+  const __half2 d0 = __float2half2_rn(0.5f * 7.97703653e-01f), d1 = __float2half2_rn(1.5f * 3.68205808e-02f), d2 = __float2half2_rn(2.5f * -3.20923304e-04f);
+  const __half2 half_ = __float2half2_rn(0.5f), one_ = __float2half2_rn(1.0f);
+  const __half2 u = __floats2half2_rn(x0, x1);
+  const __half2 t = __hmin2(__hmul2(u, u), __float2half2_rn(64.0f));
+  const __half2 p = __hfma2(__hfma2(a2, t, a1), t, a0);
+  const __half2 dp = __hfma2(__hfma2(d2, t, d1), t, d0);
+  const __half2 w = __hmul2(u, p);
+  uint32_t thw;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(thw) : "r"(*reinterpret_cast<const uint32_t*>(&w)));
+  const __half2 th = *reinterpret_cast<const __half2*>(&thw);
+  const __half2 cdf = __hfma2(half_, th, half_);
+  const __half2 a = __hmul2(u, cdf);
+  const __half2 s1 = __hfma2(__hneg2(th), th, one_);
+  const __half2 g = __hfma2(__hmul2(u, s1), dp, cdf);
+  const float2 af = __half22float2(a), gf = __half22float2(g);
+  a_bf = pack_bf16(af.x, af.y);
+  g_bf = pack_bf16(gf.x, gf.y);
+}
+
 // Transposing butterfly: on entry lane l holds v[0..31] (32 columns of its row); on exit v[0] of
 // lane l is the sum over the 32 lanes of column l.  31 shuffles instead of 32*5.
 __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
@@ -127,24 +162,28 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmX2,
                const GemmArgs args) {
   using Cfg = GemmCfg<BN, EPI>;
-  constexpr int S = Cfg::kStages;
   constexpr int NBOX = Cfg::kBoxes;
+  const bool bres = Cfg::kResOk && args.b_resident != 0;
+  const int S = bres ? Cfg::kResStages : Cfg::kStages;                  // operand ring depth
+  const uint32_t stage_bytes = bres ? uint32_t(GEMM_BM * 128) : uint32_t(Cfg::kStageBytes);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t epi_base = smem_base + S * Cfg::kStageBytes;
+  const uint32_t ring_base = smem_base + (bres ? uint32_t(Cfg::kResBBytes) : 0u);   // resident B sits in front of the ring
+  const uint32_t epi_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
   const uint32_t bar_base = epi_base + Cfg::kEpiBytes;
-  // barrier slots (8 B each)
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * S + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * S + 2 + a); };
-  auto aux_bar = [&](int b) { return bar_base + 8u * (2 * S + 4 + b); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * S + 6);
-  // box epilogues: staging-slot and aux-box hand-over barriers (2 S + 8 ... 2 S + 31 < 64 slots of the 512-byte region)
-  auto ofull_bar = [&](int s_) { return bar_base + 8u * (2 * S + 8 + s_); };
-  auto oempty_bar = [&](int s_) { return bar_base + 8u * (2 * S + 12 + s_); };
-  auto afull_bar = [&](int s_) { return bar_base + 8u * (2 * S + 16 + s_); };
-  auto aempty_bar = [&](int s_) { return bar_base + 8u * (2 * S + 24 + s_); };
+  // barrier slots (8 B each, 64 slots)
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };              // 0..7
+  auto empty_bar = [&](int s) { return bar_base + 8u * (8 + s); };       // 8..15
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (16 + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (18 + a); };
+  auto aux_bar = [&](int b) { return bar_base + 8u * (20 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * 22;
+  const uint32_t bres_bar = bar_base + 8u * 23;
+  // box epilogues: staging-slot and aux-box hand-over barriers
+  auto ofull_bar = [&](int s_) { return bar_base + 8u * (24 + s_); };
+  auto oempty_bar = [&](int s_) { return bar_base + 8u * (28 + s_); };
+  auto afull_bar = [&](int s_) { return bar_base + 8u * (32 + s_); };
+  auto aempty_bar = [&](int s_) { return bar_base + 8u * (40 + s_); };
   const uint32_t red_base = bar_base + 512;
 
   __shared__ __align__(16) float s_gamma[256];
@@ -156,15 +195,19 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int n_tiles = args.N / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int k_iters = args.K / GEMM_BK;
+  // Tile walk: tile = blockIdx.x + i * tile_step, (m, n) = (tile / n_tiles, tile % n_tiles).  Resident mode keeps n fixed
+  // per CTA: the CTAs with the same n (every n_tiles-th one) share the M tiles among themselves.
+  const int tile_step = bres ? ((int(gridDim.x) - int(blockIdx.x) % n_tiles + n_tiles - 1) / n_tiles) * n_tiles : int(gridDim.x);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmC);
-    for (int s = 0; s < S; ++s) {
+    for (int s = 0; s < 8; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
+    mbar_init(bres_bar, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), Cfg::kEpiWarps);
@@ -205,20 +248,25 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      if (bres) {   // this CTA's N tile of B: loaded once
+        const int n0 = (int(blockIdx.x) % n_tiles) * BN;
+        mbar_arrive_expect_tx(bres_bar, uint32_t(k_iters) * BN * 128);
+        for (int kb = 0; kb < k_iters; ++kb) tma_load_2d(smem_base + kb * (BN * 128), &tmB, bres_bar, kb * GEMM_BK, n0);
+      }
+      for (int tile = blockIdx.x; tile < num_tiles; tile += tile_step) {
         const int m0 = (tile / n_tiles) * GEMM_BM;
         const int n0 = (tile % n_tiles) * BN;
         for (int kb = 0; kb < Cfg::kAccs * k_iters; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          const uint32_t sa = ring_base + stage * stage_bytes;
           const uint32_t sb = sa + GEMM_BM * 128;
-          mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+          mbar_arrive_expect_tx(full_bar(stage), stage_bytes);
           if (Cfg::kAccs == 2 && kb >= k_iters) {  // second GEMM of the tile: operands A2 / B2
             tma_load_2d(sa, &tmX1, full_bar(stage), (kb - k_iters) * GEMM_BK, m0);
             tma_load_2d(sb, &tmX2, full_bar(stage), (kb - k_iters) * GEMM_BK, n0);
           } else {
             tma_load_2d(sa, &tmA, full_bar(stage), kb * GEMM_BK, m0);
-            tma_load_2d(sb, &tmB, full_bar(stage), kb * GEMM_BK, n0);
+            if (!bres) tma_load_2d(sb, &tmB, full_bar(stage), kb * GEMM_BK, n0);
           }
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
@@ -231,7 +279,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      if (bres) mbar_wait(bres_bar, 0);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += tile_step, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1u;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -242,8 +291,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t d_tmem = tmem_base + uint32_t((acc * Cfg::kAccs + g2) * BN);
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-          const uint32_t sb = sa + GEMM_BM * 128;
+          const uint32_t sa = ring_base + stage * stage_bytes;
+          const uint32_t sb = bres ? smem_base + kb * (BN * 128) : sa + GEMM_BM * 128;
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             const uint64_t adesc = make_smem_desc(sa + k * 32, 16, 1024);
@@ -260,7 +309,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------------------------------------------ store warp (box epilogues)
     if (lane == 0) {
       uint32_t g = 0;   // global box counter: the epilogue warps walk the same sequence
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += tile_step) {
         const int m0 = (tile / n_tiles) * GEMM_BM;
         const int n0 = (tile % n_tiles) * BN;
         for (int j = 0; j < NBOX; ++j, ++g) {
@@ -281,7 +330,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if constexpr (EPI == EPI_MUL) {
       if (lane == 0) {
         uint32_t g = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x; tile < num_tiles; tile += tile_step) {
           const int m0 = (tile / n_tiles) * GEMM_BM;
           const int n0 = (tile % n_tiles) * BN;
           for (int j = 0; j < NBOX; ++j, ++g) {
@@ -327,13 +376,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
 
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < num_tiles; tile += tile_step, ++it) {
       const int m0 = (tile / n_tiles) * GEMM_BM;
       const int n0 = (tile % n_tiles) * BN;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
       const uint32_t taddr = tmem_base + lane_sel + uint32_t(acc * Cfg::kAccs * BN);
-      const int next_tile = tile + gridDim.x;
+      const int next_tile = tile + tile_step;
 
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
@@ -416,19 +465,19 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               sts128(out0 + off, make_uint4(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]),
                                             pack_bf16(a[4], a[5]), pack_bf16(a[6], a[7])));
             } else {  // EPI_GELU2
-              float a[8], g[8];
+              uint32_t a[4], g[4];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) gelu_pair(v[e], a[e], g[e]);
+              for (int e = 0; e < 4; ++e) gelu_pair_h2(v[2 * e], v[2 * e + 1], a[e], g[e]);
               const int col0 = n0 + j * 64 + ch * 8;
-              if (args.ones_col >= col0 && args.ones_col < col0 + 8) {
+              if (args.ones_col >= col0 && args.ones_col < col0 + 8) {   // constant 1.0 column (bias folding): act = 1, gelu' = 0
 #pragma unroll
-                for (int e = 0; e < 8; ++e)
-                  if (col0 + e == args.ones_col) { a[e] = 1.0f; g[e] = 0.0f; }
+                for (int e = 0; e < 4; ++e) {
+                  if (col0 + 2 * e == args.ones_col) { a[e] = (a[e] & 0xFFFF0000u) | 0x3F80u; g[e] &= 0xFFFF0000u; }
+                  if (col0 + 2 * e + 1 == args.ones_col) { a[e] = (a[e] & 0x0000FFFFu) | 0x3F800000u; g[e] &= 0x0000FFFFu; }
+                }
               }
-              sts128(out0 + off, make_uint4(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]),
-                                            pack_bf16(a[4], a[5]), pack_bf16(a[6], a[7])));
-              sts128(out0 + BOX_BYTES + off, make_uint4(pack_bf16(g[0], g[1]), pack_bf16(g[2], g[3]),
-                                                        pack_bf16(g[4], g[5]), pack_bf16(g[6], g[7])));
+              sts128(out0 + off, make_uint4(a[0], a[1], a[2], a[3]));
+              sts128(out0 + BOX_BYTES + off, make_uint4(g[0], g[1], g[2], g[3]));
             }
           }
           fence_proxy_async();   // this thread's staging stores -> visible to the TMA store (async proxy)

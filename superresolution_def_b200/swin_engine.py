@@ -372,7 +372,7 @@ def _wgrad(A, B, rows_a):
     T, Ca = A.shape
     Cb = B.shape[1]
     tiles = (Ca + 127) // 128
-    splits = max(1, min(148 // tiles, T // 64))
+    splits = capi.wgrad_splits(T, Ca)
     ws = torch.empty(capi.wgrad_workspace_elems(Ca, Cb, splits), device=A.device, dtype=torch.float32)
     out = torch.empty(tiles * 128, Cb, device=A.device, dtype=torch.float32)
     capi.gemm_wgrad(A, B, ws, splits, out)

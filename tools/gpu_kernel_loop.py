@@ -32,8 +32,8 @@ elif which == "attn_bwd":
     for _ in range(reps): capi.win_attn_bwd(capi.SrkGeom(B, 128, 128, 8, 4), 6, qkv, tab, do, dq, dt)
 elif which == "wgrad":
     A = torch.randn(T, 768, device=dev).to(bf); Bm = torch.randn(T, 192, device=dev).to(bf)
-    ws = torch.empty(148 * 128 * 256, device=dev); out = torch.empty(768 * 256, device=dev)
-    for _ in range(reps): capi.gemm_wgrad(A, Bm, ws, 24, out)
+    ws = torch.empty(148 * 256 * 256, device=dev); out = torch.empty(768 * 256, device=dev)
+    for _ in range(reps): capi.gemm_wgrad(A, Bm, ws, capi.wgrad_splits(T, 768), out)
 elif which == "lnbwd":
     A = torch.randn(T, 768, device=dev).to(bf); W = (torch.randn(192, 768, device=dev) / 28).to(bf)
     X = torch.randn(T, 192, device=dev).to(bf); R = torch.randn(T, 192, device=dev).to(bf)

@@ -77,6 +77,8 @@ extern "C" int srk_gemm_tn(int epi, int M, int N, int K, const void* A, int lda,
     a.stats = ln->stats; a.partials = ln->partials; a.eps = ln->eps;
     a.row_scale = ln->row_scale; a.rows_per_scale = ln->rows_per_scale > 0 ? ln->rows_per_scale : 1;
   }
+  a.x2 = static_cast<const __nv_bfloat16*>(X2); a.ldx2 = ldx2;
+  if (epi == EPI_LNBWD && X2 && ((reinterpret_cast<uintptr_t>(X2) & 15) || ldx2 % 8)) return fail(SRK_ERR_ARG, "LNBWD: X2 rows must be 16-byte aligned");
   if ((epi == EPI_RES_LN || epi == EPI_LNBWD) && (!ln || !ln->gamma)) return fail(SRK_ERR_ARG, "LN epilogue needs SrkLnArgs");
   if (epi == EPI_LNBWD && (!ln->stats || !ln->partials || !X1 || !X2)) return fail(SRK_ERR_ARG, "LNBWD needs stats, partials, X1, X2");
   if (epi == EPI_RES_LN && (!X1 || !C2)) return fail(SRK_ERR_ARG, "RES_LN needs X1 and C2");

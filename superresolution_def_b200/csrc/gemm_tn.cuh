@@ -51,6 +51,8 @@ struct GemmArgs {
   float eps;
   const float* row_scale;  // EPI_RES_LN, optional: per-sample stochastic-depth factor applied to bf16(acc)
   int rows_per_scale;
+  const __nv_bfloat16* x2;  // EPI_LNBWD: the residual-gradient tensor X2 [M, ldx2] (read straight from global memory)
+  int ldx2;
   int b_resident;     // K <= 192: every CTA keeps ONE N tile of B ([BN x K], loaded once) in shared memory and walks M tiles
                       // only; the operand ring then holds A boxes alone (twice to six times as many bytes of A in flight)
 };
@@ -59,7 +61,7 @@ template <int BN, int EPI>
 struct GemmCfg {
   static constexpr bool kBoxEpi = (EPI == EPI_STORE || EPI == EPI_GELU2 || EPI == EPI_MUL || EPI == EPI_GELU1 || EPI == EPI_MULG);
   static constexpr int kAccs = (EPI == EPI_MULG) ? 2 : 1;  // accumulators per tile (each double-buffered in TMEM)
-  static constexpr int kEpiWarps = kBoxEpi ? 16 : 8;
+  static constexpr int kEpiWarps = (kBoxEpi || EPI == EPI_LNBWD) ? 16 : 8;
   static constexpr int kEpiThreads = 32 * kEpiWarps;
   static constexpr int kFirstEpiWarp = kBoxEpi ? 4 : 2;   // box epilogues: warp 2 = store warp, warp 3 = aux warp
   static constexpr int kThreads = 32 * kFirstEpiWarp + kEpiThreads;
@@ -71,7 +73,7 @@ struct GemmCfg {
   static constexpr int kStageBytes = GEMM_BM * 128 + BN * 128;
   static constexpr int kBoxes = BN / 64;
   static constexpr int kEpiBytes = kBoxEpi ? (kAuxSlots + kOutSlots * kOutPerBox) * BOX_BYTES : 2 * kBoxes * BOX_BYTES;
-  static constexpr int kRedBytes = 2 * 2 * 128 * 4;  // cross-half row reductions
+  static constexpr int kRedBytes = 2 * 4 * 128 * 4;  // cross-part row reductions: [2][parts <= 4][128 rows] floats
   static constexpr int kBudget = 232448 - 1024 /*align slack*/ - 512 /*barriers*/ - 2304 /*static smem*/ - kRedBytes;
   static constexpr int kStagesRaw = (kBudget - kEpiBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
@@ -150,6 +152,22 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
     }
   }
   return v[0];
+}
+
+// Same for 16 columns: on exit v[0] of lane l is the sum over the 32 lanes of column (l >> 1) (both lanes of a pair hold it).
+__device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 2; off >>= 1) {
+    const int half = off >> 1;
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = upper ? v[i] : v[i + half];
+      const float keep = upper ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
 // byte offset of 16-byte chunk `ch` (0..7) of row `r` inside a 128B-swizzled [rows x 128 B] box
@@ -355,11 +373,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t box_counter = 0;           // box-granular staging ring position
     uint32_t aux_count = 0;             // number of aux loads consumed (parity tracking)
     constexpr int NC = BN / 32;         // 32-column chunks per row
-    constexpr int NCH = NC / 2;         // chunks per half (row epilogues need an even chunk count)
-    float acc_g[(EPI == EPI_LNBWD) ? NCH : 1];
-    float acc_b[(EPI == EPI_LNBWD) ? NCH : 1];
+    constexpr int NCH = NC / 2;         // RES_LN: chunks per half (needs an even chunk count)
+    constexpr int PC = BN / Cfg::kParts;   // LNBWD: columns per thread (its part of the row), walked in 16-column pieces
+    constexpr int NPC = PC / 16;
+    static_assert(EPI != EPI_LNBWD || (PC % 16 == 0), "LNBWD: BN / 4 must be a multiple of 16");
+    float acc_g[(EPI == EPI_LNBWD) ? NPC : 1];
+    float acc_b[(EPI == EPI_LNBWD) ? NPC : 1];
 #pragma unroll
-    for (int i = 0; i < ((EPI == EPI_LNBWD) ? NCH : 1); ++i) { acc_g[i] = 0.f; acc_b[i] = 0.f; }
+    for (int i = 0; i < ((EPI == EPI_LNBWD) ? NPC : 1); ++i) { acc_g[i] = 0.f; acc_b[i] = 0.f; }
     // cross-half row reductions (row epilogues): red[k][half][row]
     float* s_red = reinterpret_cast<float*>(smem_raw + (red_base - smem_u32(smem_raw)));
 
@@ -367,12 +388,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if constexpr (EPI == EPI_RES_LN || EPI == EPI_LNBWD) {
       if (elected && blockIdx.x < num_tiles) {
         const int m0 = (blockIdx.x / n_tiles) * GEMM_BM, n0 = (blockIdx.x % n_tiles) * BN;
-        constexpr int nload = (EPI == EPI_LNBWD) ? 2 : 1;
-        mbar_arrive_expect_tx(aux_bar(0), nload * NBOX * BOX_BYTES);
+        mbar_arrive_expect_tx(aux_bar(0), NBOX * BOX_BYTES);
         for (int b = 0; b < NBOX; ++b) tma_load_2d(epi_base + b * BOX_BYTES, &tmX1, aux_bar(0), n0 + b * 64, m0);
-        if constexpr (EPI == EPI_LNBWD)
-          for (int b = 0; b < NBOX; ++b)
-            tma_load_2d(epi_base + (NBOX + b) * BOX_BYTES, &tmX2, aux_bar(0), n0 + b * 64, m0);
       }
     }
 
@@ -498,8 +515,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t T1 = epi_base + NBOX * BOX_BYTES;   // RES_LN: LN output   ; LNBWD: dres -> out
         const float inv_n = 1.0f / float(args.n_real);
         const int c_begin = half * NCH * 32, c_end = c_begin + NCH * 32;  // this thread's column range
-        mbar_wait(aux_bar(0), aux_count & 1u);
-        ++aux_count;
+        if constexpr (EPI == EPI_RES_LN) {
+          mbar_wait(aux_bar(0), aux_count & 1u);
+          ++aux_count;
+        }
         if constexpr (EPI == EPI_RES_LN) {
           const float rs = (args.row_scale != nullptr) ? args.row_scale[(m0 + row) / args.rows_per_scale] : 1.0f;
           uint32_t vp[NCH * 16];  // this thread's half row of v = bf16(bf16(acc) * rs + residual), packed pairs
@@ -590,21 +609,50 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int b = 0; b < NBOX; ++b) tma_store_2d(&tmC2, T1 + b * BOX_BYTES, n0 + b * 64, m0);
             tma_store_commit();
           }
-        } else {  // EPI_LNBWD
+        } else {  // EPI_LNBWD: 16 warps, a thread owns one accumulator row and PC = BN / 4 of its columns
+          // Shared-memory plan: two [128 x BN] buffers.  x (the LayerNorm input) of tile i sits in buffer i & 1 and the
+          // result is written over it IN PLACE (same thread, same bytes), so the other buffer is free for the whole
+          // epilogue: the next tile's x is requested at the very start of this one (a full epilogue of lead time -- with a
+          // single x buffer the warps spent 31 % of their time waiting for this load, ncu source view).  The residual
+          // gradient X2 is only added element by element in pass 2: it comes straight from global memory into registers.
+          const uint32_t Tx = epi_base + uint32_t(it & 1) * (NBOX * BOX_BYTES);
+          if (elected) {
+            tma_store_wait_read<0>();   // the previous tile's result has left the other buffer
+            if (next_tile < num_tiles) {
+              const int nm0 = (next_tile / n_tiles) * GEMM_BM, nn0 = (next_tile % n_tiles) * BN;
+              const uint32_t Tn = epi_base + uint32_t((it + 1) & 1) * (NBOX * BOX_BYTES);
+              mbar_arrive_expect_tx(aux_bar((it + 1) & 1), NBOX * BOX_BYTES);
+              for (int b = 0; b < NBOX; ++b) tma_load_2d(Tn + b * BOX_BYTES, &tmX1, aux_bar((it + 1) & 1), nn0 + b * 64, nm0);
+            }
+          }
+          if (half == 0 && next_tile < num_tiles) {   // next tile's X2 row and row statistics -> L2 (they are read from
+            const int nm0 = (next_tile / n_tiles) * GEMM_BM, nn0 = (next_tile % n_tiles) * BN;   // global memory at its start)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(args.x2 + size_t(nm0 + row) * args.ldx2 + nn0), "n"(BN * 2) : "memory");
+            if (lane == 0)
+              asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(args.stats + size_t(nm0 + q * 32) * 2), "n"(32 * 8) : "memory");
+          }
+          const int cbase = half * PC;                   // `half` is this warp's column part (0..3) here
+          uint4 dres[2 * NPC];                           // this thread's PC columns of X2 (consumed in pass 2)
+          {
+            const uint4* gp = reinterpret_cast<const uint4*>(args.x2 + size_t(m0 + row) * args.ldx2 + n0 + cbase);
+#pragma unroll
+            for (int i = 0; i < 2 * NPC; ++i) dres[i] = __ldg(gp + i);
+          }
           const float2 st = reinterpret_cast<const float2*>(args.stats)[m0 + row];
           const float rstd = st.y, nmr = -st.x * st.y;   // xhat = x * rstd + nmr
+          mbar_wait(aux_bar(it & 1), (uint32_t(it) >> 1) & 1u);
           float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-          for (int ci = 0; ci < NCH; ++ci) {
-            const int c32 = half * NCH + ci;
-            uint32_t r[32];
-            tmem_ld_x32(taddr + uint32_t(c32 * 32), r);
+          for (int pc = 0; pc < NPC; ++pc) {
+            const int c16 = cbase + pc * 16;
+            uint32_t r[16];
+            tmem_ld_x16(taddr + uint32_t(c16), r);
             tmem_ld_wait();
-            float pg[32], pb[32];
+            float pg[16], pb[16];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int c = c32 * 32 + i * 8;
-              const uint4 xv = lds128(T0 + (c >> 6) * BOX_BYTES + swz(row, (c & 63) >> 3));
+            for (int i = 0; i < 2; ++i) {
+              const int c = c16 + i * 8;
+              const uint4 xv = lds128(Tx + (c >> 6) * BOX_BYTES + swz(row, (c & 63) >> 3));
               const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
               const float4 g0 = *reinterpret_cast<const float4*>(&s_gamma[c]), g1 = *reinterpret_cast<const float4*>(&s_gamma[c + 4]);
               const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
@@ -620,27 +668,29 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 pb[i * 8 + 2 * e] = d0;      pb[i * 8 + 2 * e + 1] = d1;
               }
             }
-            acc_g[ci] += warp_colsum32(pg, lane);
-            acc_b[ci] += warp_colsum32(pb, lane);
+            acc_g[pc] += warp_colsum16(pg, lane);
+            acc_b[pc] += warp_colsum16(pb, lane);
           }
-          s_red[(0 * 2 + half) * 128 + row] = s1;
-          s_red[(1 * 2 + half) * 128 + row] = s2;
+          s_red[(0 * 4 + half) * 128 + row] = s1;
+          s_red[(1 * 4 + half) * 128 + row] = s2;
           named_bar_sync(1, Cfg::kEpiThreads);
           // dx = rstd * (dxn * gamma - c1 - xhat * c2), with rstd folded into the row constants
-          const float c1r = (s_red[(0 * 2 + 0) * 128 + row] + s_red[(0 * 2 + 1) * 128 + row]) * inv_n * rstd;
-          const float c2r = (s_red[(1 * 2 + 0) * 128 + row] + s_red[(1 * 2 + 1) * 128 + row]) * inv_n * rstd;
+          const float c1r = (s_red[(0 * 4 + 0) * 128 + row] + s_red[(0 * 4 + 1) * 128 + row] + s_red[(0 * 4 + 2) * 128 + row] +
+                             s_red[(0 * 4 + 3) * 128 + row]) * inv_n * rstd;
+          const float c2r = (s_red[(1 * 4 + 0) * 128 + row] + s_red[(1 * 4 + 1) * 128 + row] + s_red[(1 * 4 + 2) * 128 + row] +
+                             s_red[(1 * 4 + 3) * 128 + row]) * inv_n * rstd;
 #pragma unroll
-          for (int ci = 0; ci < NCH; ++ci) {
-            const int c32 = half * NCH + ci;
-            uint32_t r[32];
-            tmem_ld_x32(taddr + uint32_t(c32 * 32), r);
+          for (int pc = 0; pc < NPC; ++pc) {
+            const int c16 = cbase + pc * 16;
+            uint32_t r[16];
+            tmem_ld_x16(taddr + uint32_t(c16), r);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int c = c32 * 32 + i * 8;
+            for (int i = 0; i < 2; ++i) {
+              const int c = c16 + i * 8;
               const uint32_t boff = (c >> 6) * BOX_BYTES + swz(row, (c & 63) >> 3);
-              const uint4 xv = lds128(T0 + boff);
-              const uint4 dv = lds128(T1 + boff);
+              const uint4 xv = lds128(Tx + boff);
+              const uint4 dv = dres[pc * 2 + i];
               const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
               const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w};
               const float4 g0 = *reinterpret_cast<const float4*>(&s_gamma[c]), g1 = *reinterpret_cast<const float4*>(&s_gamma[c + 4]);
@@ -662,7 +712,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   if (c + 2 * e + 1 >= args.n_real) o[e] &= 0x0000FFFFu;
                 }
               }
-              sts128(T1 + boff, make_uint4(o[0], o[1], o[2], o[3]));
+              sts128(Tx + boff, make_uint4(o[0], o[1], o[2], o[3]));   // in place: this thread just read exactly these bytes
             }
           }
           tc_fence_before();
@@ -671,15 +721,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           fence_proxy_async();
           named_bar_sync(1, Cfg::kEpiThreads);
           if (elected) {
-            for (int b = 0; b < NBOX; ++b) tma_store_2d(&tmC, T1 + b * BOX_BYTES, n0 + b * 64, m0);
+            for (int b = 0; b < NBOX; ++b) tma_store_2d(&tmC, Tx + b * BOX_BYTES, n0 + b * 64, m0);
             tma_store_commit();
-            tma_store_wait_read<0>();
-            if (next_tile < num_tiles) {
-              const int nm0 = (next_tile / n_tiles) * GEMM_BM, nn0 = (next_tile % n_tiles) * BN;
-              mbar_arrive_expect_tx(aux_bar(0), 2 * NBOX * BOX_BYTES);
-              for (int b = 0; b < NBOX; ++b) tma_load_2d(T0 + b * BOX_BYTES, &tmX1, aux_bar(0), nn0 + b * 64, nm0);
-              for (int b = 0; b < NBOX; ++b) tma_load_2d(T1 + b * BOX_BYTES, &tmX2, aux_bar(0), nn0 + b * 64, nm0);
-            }
           }
         }
       }
@@ -687,13 +730,17 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if constexpr (EPI == EPI_LNBWD) {
       // per-CTA column sums: 8 warps -> smem (re-using the idle tile buffers) -> one row of partials per CTA
       float* s_part = reinterpret_cast<float*>(smem_raw + (epi_base - smem_u32(smem_raw)));  // [4][2][BN]
+      if (elected) tma_store_wait_read<0>();   // the last tile's result may still be leaving the buffer s_part aliases
+      named_bar_sync(1, Cfg::kEpiThreads);
+      if ((lane & 1) == 0) {   // warp_colsum16: lanes 2k and 2k+1 both hold column k of the piece
 #pragma unroll
-      for (int k = 0; k < NCH; ++k) {
-        s_part[(q * 2 + 0) * BN + (half * NCH + k) * 32 + lane] = acc_g[k];
-        s_part[(q * 2 + 1) * BN + (half * NCH + k) * 32 + lane] = acc_b[k];
+        for (int k = 0; k < NPC; ++k) {
+          s_part[(q * 2 + 0) * BN + half * PC + k * 16 + (lane >> 1)] = acc_g[k];
+          s_part[(q * 2 + 1) * BN + half * PC + k * 16 + (lane >> 1)] = acc_b[k];
+        }
       }
       named_bar_sync(1, Cfg::kEpiThreads);
-      const int e = threadIdx.x - 64;
+      const int e = threadIdx.x - 32 * Cfg::kFirstEpiWarp;
       for (int i = e; i < 2 * BN; i += Cfg::kEpiThreads) {
         const int w = i / BN, c = i % BN;
         args.partials[(size_t(blockIdx.x) * 2 + w) * BN + c] =

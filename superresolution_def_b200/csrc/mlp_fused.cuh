@@ -236,20 +236,19 @@ mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           for (int k = 0; k < 2; ++k) {
             const int ch = part * 2 + k;
             const uint32_t off = swz(row, ch);
-            float a[8], d[8];
+            uint32_t a[4], d[4];   // same packed-fp16 GELU pair as the fc1 epilogue of gemm_tn (bit-identical outputs)
 #pragma unroll
-            for (int e = 0; e < 8; ++e) gelu_pair(__uint_as_float(r[k * 8 + e]), a[e], d[e]);
+            for (int e = 0; e < 4; ++e) gelu_pair_h2(__uint_as_float(r[k * 8 + 2 * e]), __uint_as_float(r[k * 8 + 2 * e + 1]), a[e], d[e]);
             const int col0 = cc * MF_CH + h * 64 + ch * 8;
             if (args.hid_ones_col >= col0 && args.hid_ones_col < col0 + 8) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e)
-                if (col0 + e == args.hid_ones_col) { a[e] = 1.0f; d[e] = 0.0f; }
+              for (int e = 0; e < 4; ++e) {
+                if (col0 + 2 * e == args.hid_ones_col) { a[e] = (a[e] & 0xFFFF0000u) | 0x3F80u; d[e] &= 0xFFFF0000u; }
+                if (col0 + 2 * e + 1 == args.hid_ones_col) { a[e] = (a[e] & 0x0000FFFFu) | 0x3F800000u; d[e] &= 0x0000FFFFu; }
+              }
             }
-            sts128(act_s + off, make_uint4(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]), pack_bf16(a[4], a[5]),
-                                           pack_bf16(a[6], a[7])));
-            if (args.store_dact)
-              sts128(dact_s + off, make_uint4(pack_bf16(d[0], d[1]), pack_bf16(d[2], d[3]), pack_bf16(d[4], d[5]),
-                                              pack_bf16(d[6], d[7])));
+            sts128(act_s + off, make_uint4(a[0], a[1], a[2], a[3]));
+            if (args.store_dact) sts128(dact_s + off, make_uint4(d[0], d[1], d[2], d[3]));
           }
           fence_proxy_async();
           named_bar_sync(1, MF_EPI_THREADS);

@@ -53,7 +53,7 @@ int qkv_window_map(CUtensorMap* tm, const void* p, const SrkGeom* g, int ld) {
 int wgrad_splits(int T, int Ca) { return srk_gemm_wgrad_splits(T, Ca); }
 
 struct WsLayout {  // offsets (floats) into SrkBlockScratch.wg_ws
-  long long partials, ext_qkv, ext_proj, ext_fc1, ext_fc2, ln1, ln2, rpb, total;
+  long long part_qkv, part_proj, part_fc1, part_fc2, ln1, ln2, rpb, total;   // per-split weight-gradient partials
   int rpb_gx, ln_grid;
 };
 
@@ -83,13 +83,12 @@ WsLayout ws_layout(const SrkBlockDims* d, const SrkGeom* g) {
   WsLayout L{};
   const int QW = 3 * d->heads * d->ds, AW = d->heads * d->ds;
   const long long T = (long long)g->B * g->H * g->W;
-  const long long part = (long long)num_sms() * 256 * 256;  // groups*splits <= num_sms, <= 256 channels of A per group, Cb <= 256
+  // every weight-gradient GEMM of the block keeps its per-split partials until the unpack kernel folds them
   long long o = 0;
-  L.partials = o; o += part;
-  L.ext_qkv = o; o += (long long)((QW + 127) / 128 * 128) * d->Cp;
-  L.ext_proj = o; o += (long long)((d->Cp + 127) / 128 * 128) * AW;
-  L.ext_fc1 = o; o += (long long)d->Hp * d->Cp;
-  L.ext_fc2 = o; o += (long long)d->Hp * d->Cp;
+  L.part_qkv = o; o += srk_gemm_wgrad_workspace_elems(QW, d->Cp, wgrad_splits(int(T), QW));
+  L.part_proj = o; o += srk_gemm_wgrad_workspace_elems(d->Cp, AW, wgrad_splits(int(T), d->Cp));
+  L.part_fc1 = o; o += srk_gemm_wgrad_workspace_elems(d->Hp, d->Cp, wgrad_splits(int(T), d->Hp));
+  L.part_fc2 = o; o += srk_gemm_wgrad_workspace_elems(d->Hp, d->Cp, wgrad_splits(int(T), d->Hp));
   L.ln_grid = srk_gemm_grid(int(T), d->Cp);
   L.ln1 = o; o += (long long)L.ln_grid * 2 * d->Cp;
   L.ln2 = o; o += (long long)L.ln_grid * 2 * d->Cp;
@@ -490,23 +489,22 @@ static int block_bwd_impl(const SrkBlockDims* d, const SrkGeom* g, const SrkBloc
   if (rc) return rc;
   // dW2^T (+db2 in row `hidden`) = act^T @ g_out
   const int s_fc = wgrad_splits(T, Hp);
-  if ((rc = srk_gemm_wgrad(T, Hp, Cp, a->act, Hp, g_mlp, Cp, ws + L.partials, s_fc, ws + L.ext_fc2, stream_))) return rc;
+  if ((rc = gemm_wgrad_partials(T, Hp, Cp, a->act, Hp, g_mlp, Cp, ws + L.part_fc2, s_fc, stream_))) return rc;
   // g_mid = g_out + LN2bwd(dU @ W1)
   SrkLnArgs ln2{d->C, -1, p->norm2_w, nullptr, a->stats2, ws + L.ln2, 1e-5f, nullptr, 1};
   if ((rc = srk_gemm_tn(SRK_EPI_LNBWD, T, Cp, Hp, s->d_act, Hp, w->fc1_t, Hp, s->g_mid, Cp, nullptr, 0, a->x_mid, Cp,
                         g_out, Cp, &ln2, stream_)))
     return rc;
   // dW1 (+db1 in column C) = dU^T @ xn2
-  if ((rc = srk_gemm_wgrad(T, Hp, Cp, s->d_act, Hp, a->xn2, Cp, ws + L.partials, s_fc, ws + L.ext_fc1, stream_))) return rc;
+  if ((rc = gemm_wgrad_partials(T, Hp, Cp, s->d_act, Hp, a->xn2, Cp, ws + L.part_fc1, s_fc, stream_))) return rc;
   // d_ao = g_mid @ Wproj
   const void* g_att = scaled(s->g_mid, x ? x->drop_attn : nullptr);
   if ((rc = srk_gemm_tn(SRK_EPI_STORE, T, AW, Cp, g_att, Cp, w->proj_t, Cp, s->d_ao, AW, nullptr, 0, nullptr, 0,
                         nullptr, 0, nullptr, stream_)))
     return rc;
   // dWproj (+dbproj in column dh) = g_mid^T @ ao
-  if ((rc = srk_gemm_wgrad(T, Cp, AW, g_att, Cp, a->ao, AW, ws + L.partials, wgrad_splits(T, Cp),
-                           ws + L.ext_proj, stream_)))
-    return rc;
+  const int s_proj = wgrad_splits(T, Cp);
+  if ((rc = gemm_wgrad_partials(T, Cp, AW, g_att, Cp, a->ao, AW, ws + L.part_proj, s_proj, stream_))) return rc;
   // attention backward -> d_qkv, rpb-table gradient (ws 8: per-CTA partials folded by the unpack kernel below)
   const bool ws8_self = !x || (g->ws == 8 && x->mode == MODE_SELF);   // rpb-table gradient arrives as per-CTA partials
   if (x && ws8_self) {
@@ -535,11 +533,14 @@ static int block_bwd_impl(const SrkBlockDims* d, const SrkGeom* g, const SrkBloc
       return rc;
   }
   // dWqkv (+dbqkv in column C) = d_qkv^T @ xn1
-  if ((rc = srk_gemm_wgrad(T, QW, Cp, s->d_qkv, QW, a->xn1, Cp, ws + L.partials, wgrad_splits(T, QW),
-                           ws + L.ext_qkv, stream_)))
-    return rc;
+  const int s_qkv = wgrad_splits(T, QW);
+  if ((rc = gemm_wgrad_partials(T, QW, Cp, s->d_qkv, QW, a->xn1, Cp, ws + L.part_qkv, s_qkv, stream_))) return rc;
   // scatter everything into reference-shaped fp32 gradients
-  UnpackSrc us{ws + L.ext_qkv, ws + L.ext_proj, ws + L.ext_fc1, ws + L.ext_fc2, defer_ln1 ? nullptr : ws + L.ln1,
+  auto split_sum = [&](long long off, int Ca, int Cb, int splits) {
+    return SplitSum{ws + off, splits, srk_gemm_wgrad_workspace_elems(Ca, Cb, splits) / splits};
+  };
+  UnpackSrc us{split_sum(L.part_qkv, QW, Cp, s_qkv), split_sum(L.part_proj, Cp, AW, s_proj),
+               split_sum(L.part_fc1, Hp, Cp, s_fc), split_sum(L.part_fc2, Hp, Cp, s_fc), defer_ln1 ? nullptr : ws + L.ln1,
                ws + L.ln2, ws8_self ? ws + L.rpb : nullptr, L.ln_grid, L.rpb_gx, 225};
   BlockGradPtrs gp{grads->norm1_w, grads->norm1_b, grads->rpb_table, grads->qkv_w, grads->qkv_b, grads->proj_w,
                    grads->proj_b,  grads->norm2_w, grads->norm2_b,   grads->fc1_w, grads->fc1_b, grads->fc2_w,

@@ -156,7 +156,7 @@ static int gemm_wgrad_impl(int T, int Ca, int Cb, const void* A, int lda, const 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (splits <= 0 || T <= 0 || T % WG_TOK != 0 || splits > T / WG_TOK)
     return fail(SRK_ERR_ARG, "srk_gemm_wgrad: T must be a multiple of 64 and 1 <= splits <= T/64");
-  if (!A || !B || !workspace || !out) return fail(SRK_ERR_ARG, "srk_gemm_wgrad: null pointer");
+  if (!A || !B || !workspace) return fail(SRK_ERR_ARG, "srk_gemm_wgrad: null pointer");
   const int at = wgrad_at(Ca);
   WgradArgs a{};
   a.T = T; a.Ca = Ca; a.Cb = Cb; a.ca_groups = (Ca + at * 128 - 1) / (at * 128); a.splits = splits; a.partials = workspace;
@@ -176,6 +176,7 @@ static int gemm_wgrad_impl(int T, int Ca, int Cb, const void* A, int lda, const 
   }
 #undef SRK_WG
   if (rc) return rc;
+  if (out == nullptr) return SRK_OK;   // internal callers that sum the per-split partials themselves (block backward)
   const int n = ((Ca + 127) / 128) * 128 * Cb;
   const size_t split_stride = size_t(a.ca_groups) * at * 128 * Cb;
   SRK_CUDA_OK(launch_pdl(wgrad_reduce_kernel, dim3((n + 255) / 256), dim3(256), 0, stream, workspace, out, splits, n,
@@ -201,8 +202,18 @@ extern "C" long long srk_gemm_wgrad_workspace_elems(int Ca, int Cb, int splits) 
 
 extern "C" int srk_gemm_wgrad(int T, int Ca, int Cb, const void* A, int lda, const void* B, int ldb,
                               float* workspace, int splits, float* out, void* stream) {
+  if (!out) return fail(SRK_ERR_ARG, "srk_gemm_wgrad: null pointer");
   return gemm_wgrad_impl(T, Ca, Cb, A, lda, B, ldb, workspace, splits, out, WG_SUBBOX, 1024, stream);
 }
+
+namespace srk {
+// Per-split partials only: [splits][rows_per_split][Cb] fp32 in `workspace`, rows_per_split = srk_gemm_wgrad_workspace_elems
+// / (splits * Cb); the caller folds the splits (the block backward does it inside its gradient-unpack kernel).
+int gemm_wgrad_partials(int T, int Ca, int Cb, const void* A, int lda, const void* B, int ldb, float* workspace, int splits,
+                        void* stream) {
+  return gemm_wgrad_impl(T, Ca, Cb, A, lda, B, ldb, workspace, splits, nullptr, WG_SUBBOX, 1024, stream);
+}
+}  // namespace srk
 
 extern "C" int srk_mlp_fwd(int T, int Cp, int Hp, const void* xn2, const void* w1, const void* w2, const void* resid,
                            void* act, void* dact, void* x_out, void* xn_out, int hid_ones_col, const SrkLnArgs* ln,

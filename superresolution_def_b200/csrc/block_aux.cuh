@@ -100,11 +100,28 @@ static __global__ void prep_block_weights_kernel(BlockDims d, BlockParamPtrs p, 
 }
 
 // ------------------------------------------------------------------ gradient unpacking
+struct SplitSum {          // a weight-gradient GEMM result still in per-split form: value(i) = sum_k p[k * stride + i]
+  const float* p;
+  int splits;
+  long long stride;
+  __device__ __forceinline__ float at(long long i) const {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int k = 0;
+    for (; k + 4 <= splits; k += 4) {
+      a0 += p[(long long)k * stride + i];
+      a1 += p[(long long)(k + 1) * stride + i];
+      a2 += p[(long long)(k + 2) * stride + i];
+      a3 += p[(long long)(k + 3) * stride + i];
+    }
+    for (; k < splits; ++k) a0 += p[(long long)k * stride + i];
+    return (a0 + a1) + (a2 + a3);
+  }
+};
 struct UnpackSrc {
-  const float* dqkv_ext;   // [ceil128(QW), Cp]  rows = qkv ext rows, cols = xn1 channels (col C = bias grad)
-  const float* dproj_ext;  // [ceil128(Cp), AW]  rows = out channels n, cols = ao ext channels (col dh = bias grad)
-  const float* dfc1_ext;   // [Hp, Cp]           rows = hidden, cols = xn2 channels (col C = bias grad)
-  const float* dfc2T_ext;  // [Hp, Cp]           rows = hidden (row `hidden` = bias grad), cols = out channels
+  SplitSum dqkv_ext;   // [ceil128(QW), Cp]  rows = qkv ext rows, cols = xn1 channels (col C = bias grad)
+  SplitSum dproj_ext;  // [ceil128(Cp), AW]  rows = out channels n, cols = ao ext channels (col dh = bias grad)
+  SplitSum dfc1_ext;   // [Hp, Cp]           rows = hidden, cols = xn2 channels (col C = bias grad)
+  SplitSum dfc2T_ext;  // [Hp, Cp]           rows = hidden (row `hidden` = bias grad), cols = out channels
   const float* ln1_part;   // [n_ln_part][2][Cp] (dgamma, dbeta) partials of norm1
   const float* ln2_part;   // same for norm2
   const float* rpb_part;   // [n_rpb_part][heads][T2] partials of the bias-table gradient
@@ -129,24 +146,24 @@ static __global__ void unpack_block_grads_kernel(BlockDims d, UnpackSrc s, Block
       const int n = is_b ? (i - n_qkv_w) : (i / C), c = is_b ? C : (i % C);
       const int sidx = n / C, h = (n % C) / d.dh, dd = n % d.dh;
       const int r = sidx * AW + h * d.ds + dd;
-      v = s.dqkv_ext[r * d.Cp + c] * (sidx == 0 ? qscale : 1.f);
+      v = s.dqkv_ext.at(r * d.Cp + c) * (sidx == 0 ? qscale : 1.f);
       dst = is_b ? (g.qkv_b + n) : (g.qkv_w + i);
     } else if ((i -= n_qkv_w + n_qkv_b) < n_proj_w + n_proj_b) {
       const bool is_b = i >= n_proj_w;
       const int n = is_b ? (i - n_proj_w) : (i / C), k = is_b ? 0 : (i % C);
       const int c = is_b ? d.dh : ((k / d.dh) * d.ds + (k % d.dh));
-      v = s.dproj_ext[n * AW + c];
+      v = s.dproj_ext.at(n * AW + c);
       dst = is_b ? (g.proj_b + n) : (g.proj_w + i);
     } else if ((i -= n_proj_w + n_proj_b) < n_fc1_w + n_fc1_b) {
       const bool is_b = i >= n_fc1_w;
       const int n = is_b ? (i - n_fc1_w) : (i / C), c = is_b ? C : (i % C);
-      v = s.dfc1_ext[n * d.Cp + c];
+      v = s.dfc1_ext.at(n * d.Cp + c);
       dst = is_b ? (g.fc1_b + n) : (g.fc1_w + i);
     } else if ((i -= n_fc1_w + n_fc1_b) < n_fc2_w + n_fc2_b) {
       const bool is_b = i >= n_fc2_w;
-      const int n = is_b ? (i - n_fc2_w) : (i / d.hidden), k = is_b ? d.hidden : (i % d.hidden);
-      v = s.dfc2T_ext[k * d.Cp + n];
-      dst = is_b ? (g.fc2_b + n) : (g.fc2_w + i);
+      const int n = is_b ? (i - n_fc2_w) : (i % C), k = is_b ? d.hidden : (i / C);   // source order: reads coalesced
+      v = s.dfc2T_ext.at(k * d.Cp + n);
+      dst = is_b ? (g.fc2_b + n) : (g.fc2_w + n * d.hidden + k);
     } else if ((i -= n_fc2_w + n_fc2_b) < n_ln) {
       const int which = i / C, c = i % C;  // 0: norm1_w, 1: norm1_b, 2: norm2_w, 3: norm2_b
       const float* part = (which < 2) ? s.ln1_part : s.ln2_part;

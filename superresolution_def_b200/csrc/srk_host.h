@@ -132,6 +132,10 @@ struct DeviceOnce {
   void done() { mask.fetch_or(1ull << cur(), std::memory_order_release); }
 };
 
+// api_gemm.cu: weight-gradient GEMM that leaves its per-split partials in `workspace` (no reduce kernel)
+int gemm_wgrad_partials(int T, int Ca, int Cb, const void* A, int lda, const void* B, int ldb, float* workspace, int splits,
+                        void* stream);
+
 inline int num_sms() {
   static std::atomic<int> n[64];
   const int dev = DeviceOnce::cur();

@@ -111,9 +111,9 @@ class SwinIRTailFunction(torch.autograd.Function):
             u1 = torch.empty(B * 4 * H * 4 * W, 64, device=dev, dtype=BF16)
             capi.conv3x3_igemm(capi.CEPI_BIAS, B, 2 * H, 2 * W, 64, 256, 256, u0, wf_u2, bp_u2, u1, y_ps=True)
         out = torch.empty(B, 1, up * H, up * W, device=dev, dtype=torch.float32)
-        # conv_last (64 -> 1): tcgen05 implicit GEMM with N = 16 (one real column), fp32 result straight from TMEM
-        wf_l, _, bp_l = conv_weights(w_last, b_last, 16, 64)
-        capi.conv3x3_igemm(capi.CEPI_OUT1, B, up * H, up * W, 64, 16, 1, u1, wf_l, bp_l, out)
+        # conv_last (64 -> 1): one useful output column makes the tensor-core form (N = 16) instruction-rate bound (613 us at
+        # 512^2 x 16); the row-walking CUDA-core kernel streams the input once
+        capi.conv_out1_fwd(u1, w_last.detach(), b_last.detach(), out, B, up * H, up * W, 64)
         if any(ctx.needs_input_grad):
             ctx.saved = (body, res, t64, u0, u1)
             ctx.params = (w_ab, b_ab, w_bu, b_bu, w_u0, b_u0, w_u2, b_u2, w_last, b_last)

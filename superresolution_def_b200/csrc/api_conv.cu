@@ -266,7 +266,10 @@ extern "C" int srk_conv_out1_fwd(const void* x, const float* w, const float* bia
                                  void* stream_) {
   if (C != 64) return fail(SRK_ERR_UNSUPPORTED, "conv_out1: 64 input channels");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  conv_out1_fwd_kernel<64><<<num_sms() * 8, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), w, bias, y, B, H, W);
+  if (H % 4 == 0)
+    conv_out1_fwd_rows_kernel<64><<<num_sms() * 3, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), w, bias, y, B, H, W, 64);
+  else
+    conv_out1_fwd_kernel<64><<<num_sms() * 8, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), w, bias, y, B, H, W);
   SRK_LAUNCHED(1);
   SRK_CUDA_OK(cudaGetLastError());
   return SRK_OK;
@@ -277,11 +280,15 @@ extern "C" int srk_conv_out1_bwd(const float* dy, const void* x, const float* w,
   if (C != 64) return fail(SRK_ERR_UNSUPPORTED, "conv_out1: 64 input channels");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const bool small = (long long)B * H * W * 8 < (1LL << 31);
-  if (small) conv_out1_dgrad_kernel<64, int><<<num_sms() * 8, 256, 0, stream>>>(dy, w, static_cast<__nv_bfloat16*>(dx), B, H, W);
+  const bool rows4 = (H % 4) == 0;   // row-walking kernels: a warp owns four image rows
+  const int seg = 64;
+  if (rows4) conv_out1_dgrad_rows_kernel<64><<<num_sms() * 2, 256, 0, stream>>>(dy, w, static_cast<__nv_bfloat16*>(dx), B, H, W, seg);
+  else if (small) conv_out1_dgrad_kernel<64, int><<<num_sms() * 8, 256, 0, stream>>>(dy, w, static_cast<__nv_bfloat16*>(dx), B, H, W);
   else conv_out1_dgrad_kernel<64, long long><<<num_sms() * 8, 256, 0, stream>>>(dy, w, static_cast<__nv_bfloat16*>(dx), B, H, W);
   SRK_LAUNCHED(1);
   const int grid = num_sms() * 2;
-  if (small) conv_out1_wgrad_kernel<64, int><<<grid, 256, 0, stream>>>(dy, static_cast<const __nv_bfloat16*>(x), ws, B, H, W);
+  if (rows4) conv_out1_wgrad_rows_kernel<64><<<grid, 256, 0, stream>>>(dy, static_cast<const __nv_bfloat16*>(x), ws, B, H, W, seg);
+  else if (small) conv_out1_wgrad_kernel<64, int><<<grid, 256, 0, stream>>>(dy, static_cast<const __nv_bfloat16*>(x), ws, B, H, W);
   else conv_out1_wgrad_kernel<64, long long><<<grid, 256, 0, stream>>>(dy, static_cast<const __nv_bfloat16*>(x), ws, B, H, W);
   SRK_LAUNCHED(1);
   colsum_finish_kernel<<<(64 * 9 + 1 + 127) / 128, 128, 0, stream>>>(ws, grid, 64 * 9 + 1, ws + (size_t)grid * (64 * 9 + 1), 64 * 9 + 1);

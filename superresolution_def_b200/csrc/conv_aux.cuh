@@ -335,6 +335,197 @@ static __global__ void conv_out1_wgrad_kernel(const float* __restrict__ dy, cons
   for (int i = threadIdx.x; i < C * 9 + 1; i += blockDim.x) partial[size_t(blockIdx.x) * (C * 9 + 1) + i] = s_acc[i];
 }
 
+
+// ------------------------------------------------------------------ conv_last backward, row-walking versions (round 2)
+// The two kernels above spend most of their instructions on index arithmetic (two integer divisions and nine four-way
+// bounds tests per 8 outputs) and keep 16 bytes per thread in flight.  Here a warp owns (image, four rows, x segment):
+// lane = (row r = lane / 8, channel group g = lane % 8); a thread walks x with a sliding 3x3 window of dY in registers
+// (three new values per pixel, row validity decided once per task), its 8 x 9 weights (dgrad) or accumulators (wgrad) in
+// registers.  Loads and stores of a warp cover four full 128-byte pixel rows.  H % 4 == 0.
+__device__ __forceinline__ float ldrow(const float* row, int x) { return row ? __ldg(row + x) : 0.f; }
+
+template <int C>
+static __global__ void __launch_bounds__(256) conv_out1_dgrad_rows_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                                       __nv_bfloat16* __restrict__ dx, int B, int H, int W, int seg) {
+  static_assert(C == 64, "lane mapping: 8 channel groups of 8");
+  const int lane = threadIdx.x & 31, g = lane & 7, r = lane >> 3;
+  float wr[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) wr[t][e] = w[(g * 8 + e) * 9 + t];
+  const int nseg = (W + seg - 1) / seg, hq = H >> 2;
+  const long long total = (long long)B * hq * nseg;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long task = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; task < total; task += nwarps) {
+    const int sgm = int(task % nseg);
+    const int yq = int((task / nseg) % hq), b = int(task / ((long long)nseg * hq));
+    const int y = yq * 4 + r, x0 = sgm * seg, x1 = min(W, x0 + seg);
+    const float* rows[3];
+    rows[1] = dy + ((size_t)b * H + y) * W;
+    rows[0] = y > 0 ? rows[1] - W : nullptr;
+    rows[2] = y < H - 1 ? rows[1] + W : nullptr;
+    float d[3][3];   // d[i][j] = dY[y - 1 + i][x - 1 + j]
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      d[i][1] = (x0 > 0) ? ldrow(rows[i], x0 - 1) : 0.f;
+      d[i][2] = ldrow(rows[i], x0);
+    }
+    __nv_bfloat16* out = dx + (((size_t)b * H + y) * W + x0) * C + g * 8;
+    for (int x = x0; x < x1; ++x, out += C) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        d[i][0] = d[i][1];
+        d[i][1] = d[i][2];
+        d[i][2] = (x + 1 < W) ? ldrow(rows[i], x + 1) : 0.f;
+      }
+      float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {   // output pixel q = p - off(t) received x[p] through tap t: dY at (y + 1 - t/3, x + 1 - t%3)
+        const float dv = d[2 - t / 3][2 - t % 3];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = fmaf(dv, wr[t][e], o[e]);
+      }
+      *reinterpret_cast<uint4*>(out) =
+          make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+    }
+  }
+}
+
+// y[p] = bias + sum_tap sum_c x[p + off(tap)][c] * w[c][tap]   (x NHWC bf16, y fp32 [B,H,W]; weights rounded to bf16 like
+// the tensor-core path this replaces: a 64 -> 1 convolution is N = 16 for tcgen05.mma, i.e. 36 M = 128 instructions per 128
+// pixels for one useful column, 613 us at 512^2 x 16).  Same task mapping as above; the 3x3 window holds packed bf16.
+template <int C>
+static __global__ void __launch_bounds__(256, 2) conv_out1_fwd_rows_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                                                                     const float* __restrict__ bias, float* __restrict__ y,
+                                                                     int B, int H, int W, int seg) {
+  static_assert(C == 64, "lane mapping: 8 channel groups of 8");
+  const int lane = threadIdx.x & 31, g = lane & 7, r = lane >> 3;
+  __shared__ __align__(16) float s_w[9][C];   // weights stay in shared memory: 72 more registers would halve the occupancy
+  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) s_w[i / C][i % C] = round_bf16(w[(i % C) * 9 + i / C]);
+  __syncthreads();
+  const float b0 = bias[0];
+  const int nseg = (W + seg - 1) / seg, hq = H >> 2;
+  const long long total = (long long)B * hq * nseg;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+  for (long long task = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; task < total; task += nwarps) {
+    const int sgm = int(task % nseg);
+    const int yq = int((task / nseg) % hq), b = int(task / ((long long)nseg * hq));
+    const int yy = yq * 4 + r, x0 = sgm * seg, x1 = min(W, x0 + seg);
+    const __nv_bfloat16* rows[3];
+    rows[1] = x + ((size_t)b * H + yy) * W * C + g * 8;
+    rows[0] = yy > 0 ? rows[1] - (size_t)W * C : nullptr;
+    rows[2] = yy < H - 1 ? rows[1] + (size_t)W * C : nullptr;
+    auto ld = [&](int i, int xx) { return rows[i] ? *reinterpret_cast<const uint4*>(rows[i] + (size_t)xx * C) : zero4; };
+    uint4 d[3][4];   // d[i][j] = x[yy - 1 + i][xx - 1 + j][8 channels]; column 3 is the load in flight for the next pixel
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      d[i][1] = (x0 > 0) ? ld(i, x0 - 1) : zero4;
+      d[i][2] = ld(i, x0);
+      d[i][3] = (x0 + 1 < W) ? ld(i, x0 + 1) : zero4;
+    }
+    float* out = y + ((size_t)b * H + yy) * W;
+    for (int xx = x0; xx < x1; ++xx) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        d[i][0] = d[i][1];
+        d[i][1] = d[i][2];
+        d[i][2] = d[i][3];
+        d[i][3] = (xx + 2 < W) ? ld(i, xx + 2) : zero4;   // consumed one iteration later
+      }
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const uint4 v = d[t / 3][t % 3];
+        const uint32_t vw[4] = {v.x, v.y, v.z, v.w};
+        const float4 w0 = *reinterpret_cast<const float4*>(&s_w[t][g * 8]), w1 = *reinterpret_cast<const float4*>(&s_w[t][g * 8 + 4]);
+        a0 = fmaf(bf16_lo(vw[0]), w0.x, a0); a1 = fmaf(bf16_hi(vw[0]), w0.y, a1);
+        a0 = fmaf(bf16_lo(vw[1]), w0.z, a0); a1 = fmaf(bf16_hi(vw[1]), w0.w, a1);
+        a0 = fmaf(bf16_lo(vw[2]), w1.x, a0); a1 = fmaf(bf16_hi(vw[2]), w1.y, a1);
+        a0 = fmaf(bf16_lo(vw[3]), w1.z, a0); a1 = fmaf(bf16_hi(vw[3]), w1.w, a1);
+      }
+      float acc = a0 + a1;
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      if (g == 0) out[xx] = acc + b0;
+    }
+  }
+}
+
+// dW[c][tap] = sum_p dY[p - off(tap)] * x[p][c], db = sum_p dY[p]; partial[blockIdx][C*9 + 1]
+template <int C>
+static __global__ void __launch_bounds__(256) conv_out1_wgrad_rows_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                                                                       float* __restrict__ partial, int B, int H, int W, int seg) {
+  static_assert(C == 64, "lane mapping: 8 channel groups of 8");
+  __shared__ float s_acc[C * 9 + 1];
+  for (int i = threadIdx.x; i < C * 9 + 1; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, g = lane & 7, r = lane >> 3;
+  float acc[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[t][e] = 0.f;
+  float accb = 0.f;
+  const int nseg = (W + seg - 1) / seg, hq = H >> 2;
+  const long long total = (long long)B * hq * nseg;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long task = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; task < total; task += nwarps) {
+    const int sgm = int(task % nseg);
+    const int yq = int((task / nseg) % hq), b = int(task / ((long long)nseg * hq));
+    const int y = yq * 4 + r, x0 = sgm * seg, x1 = min(W, x0 + seg);
+    const float* rows[3];
+    rows[1] = dy + ((size_t)b * H + y) * W;
+    rows[0] = y > 0 ? rows[1] - W : nullptr;
+    rows[2] = y < H - 1 ? rows[1] + W : nullptr;
+    float d[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      d[i][1] = (x0 > 0) ? ldrow(rows[i], x0 - 1) : 0.f;
+      d[i][2] = ldrow(rows[i], x0);
+    }
+    const __nv_bfloat16* in = x + (((size_t)b * H + y) * W + x0) * C + g * 8;
+    for (int xb = x0; xb < x1; xb += 4, in += 4 * C) {
+      uint4 xq[4];   // four pixels of this thread's 8 channels in flight
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        xq[k] = (xb + k < x1) ? *reinterpret_cast<const uint4*>(in + k * C) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int xx = xb + k;
+        if (xx < x1) {
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            d[i][0] = d[i][1];
+            d[i][1] = d[i][2];
+            d[i][2] = (xx + 1 < W) ? ldrow(rows[i], xx + 1) : 0.f;
+          }
+          const uint32_t vw[4] = {xq[k].x, xq[k].y, xq[k].z, xq[k].w};
+          float xv[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) xv[e] = (e & 1) ? bf16_hi(vw[e >> 1]) : bf16_lo(vw[e >> 1]);
+          if (g == 0) accb += d[1][1];
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            const float dv = d[2 - t / 3][2 - t % 3];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[t][e] = fmaf(dv, xv[e], acc[t][e]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) atomicAdd(&s_acc[(g * 8 + e) * 9 + t], acc[t][e]);
+  if (g == 0) atomicAdd(&s_acc[C * 9], accb);
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * 9 + 1; i += blockDim.x) partial[size_t(blockIdx.x) * (C * 9 + 1) + i] = s_acc[i];
+}
+
 }  // namespace srk
 
 namespace srk {

@@ -143,6 +143,44 @@ extern "C" int srk_conv3x3_igemm(int epi, int B, int H, int W, int Cin_p, int Co
   ConvMaps maps;
   memset(&maps, 0, sizeof(maps));
   int rc;
+  {
+    // Few output channels (<= 64 real ones here): role-swapped kernel, as in the view entry point below -- the 256 -> 64
+    // input gradients of the two upsampler stages (pixel-shuffled gradient, one strided map per 64-channel chunk) and
+    // conv_before_upsample are UMMA-instruction-rate bound as [pixels x 64] tiles (627 us at 256^2 x 16 for 309 GFLOP).
+    const int hmode = conv_halo_mode();
+    const bool swap_aux = (epi == CEPI_BIAS_RES || epi == CEPI_MASK_LRELU);
+    const bool swap_ok = !out1 && !y_ps && !y2 && n_real > 0 && n_real <= 64 && Cout_p == 64 && H % SWP_TH == 0 && W % SWP_TW == 0 &&
+                         (epi == CEPI_BIAS || epi == CEPI_BIAS_LRELU || swap_aux) && (!swap_aux || Cin_p >= 128);
+    if (hmode != 0 && hmode != 5 && swap_ok) {
+      if (swap_aux && !r) return fail(SRK_ERR_ARG, "conv3x3: epilogue needs an aux tensor");
+      if ((rc = make_act_maps(maps.a, x, B, H, W, Cin_p, x_ps, SWP_BW, SWP_BH))) return rc;
+      if (!x_ps) for (int i = 1; i < 4; ++i) maps.a[i] = maps.a[0];
+      if ((rc = make_tmap_nhwc(&maps.c[0], y, Cout_p, W, H, B, Cout_p, (uint64_t)W * Cout_p, (uint64_t)H * W * Cout_p, 8, 8))) return rc;
+      for (int i = 1; i < 4; ++i) maps.c[i] = maps.c[0];
+      maps.c2 = maps.c[0];
+      maps.r = maps.c[0];
+      if (swap_aux && (rc = make_tmap_nhwc(&maps.r, r, Cout_p, W, H, B, Cout_p, (uint64_t)W * Cout_p, (uint64_t)H * W * Cout_p, 8, 8))) return rc;
+      const bool use64 = swap_m64_mode() != 0;
+      if ((rc = make_tmap_2d(&maps.w, wk, Cout_p, 9 * (uint64_t)Cin_p, 9 * (uint64_t)Cin_p, use64 ? 64 : 128))) return rc;
+      ConvArgs a{};
+      a.B = B; a.H = H; a.W = W; a.Cin_p = Cin_p; a.Cout_p = Cout_p; a.n_real = n_real; a.bias = bias; a.slope = slope;
+      a.alpha = 1.0f; a.a_split = x_ps; a.c_split = 0;
+      if (use64) {
+        switch (epi) {
+          case CEPI_BIAS: return launch_conv_swap<CEPI_BIAS, 64>(maps, a, stream);
+          case CEPI_BIAS_LRELU: return launch_conv_swap<CEPI_BIAS_LRELU, 64>(maps, a, stream);
+          case CEPI_BIAS_RES: return launch_conv_swap<CEPI_BIAS_RES, 64>(maps, a, stream);
+          default: return launch_conv_swap<CEPI_MASK_LRELU, 64>(maps, a, stream);
+        }
+      }
+      switch (epi) {
+        case CEPI_BIAS: return launch_conv_swap<CEPI_BIAS, 128>(maps, a, stream);
+        case CEPI_BIAS_LRELU: return launch_conv_swap<CEPI_BIAS_LRELU, 128>(maps, a, stream);
+        case CEPI_BIAS_RES: return launch_conv_swap<CEPI_BIAS_RES, 128>(maps, a, stream);
+        default: return launch_conv_swap<CEPI_MASK_LRELU, 128>(maps, a, stream);
+      }
+    }
+  }
   if ((rc = make_act_maps(maps.a, x, B, H, W, Cin_p, x_ps, CONV_TW, CONV_TH))) return rc;
   if (out1) {
     for (int i = 0; i < 4; ++i) maps.c[i] = maps.a[0];  // unused: the fp32 output is written with plain stores

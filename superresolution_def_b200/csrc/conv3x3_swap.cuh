@@ -104,7 +104,10 @@ conv3x3_swap_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) 
         for (int kc = 0; kc < kc_per_tap; ++kc) {
           mbar_wait(empty_bar(bs), bph ^ 1u);
           mbar_arrive_expect_tx(full_bar(bs), SWP_B_BYTES);
-          tma_load_4d(smem_base + bs * SWP_B_BYTES, &maps.a[0], full_bar(bs), kc * 64, x0 - 1, y0 - 1, b);
+          if (args.a_split)   // pixel-shuffled input gradient: chunk kc is sub-pixel plane kc (its own strided map)
+            tma_load_4d(smem_base + bs * SWP_B_BYTES, &maps.a[kc & 3], full_bar(bs), 0, x0 - 1, y0 - 1, b);
+          else
+            tma_load_4d(smem_base + bs * SWP_B_BYTES, &maps.a[0], full_bar(bs), kc * 64, x0 - 1, y0 - 1, b);
           if (++bs == SB) { bs = 0; bph ^= 1u; }
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(empty_bar(SB + as), aph ^ 1u);

@@ -632,7 +632,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(args.stats + size_t(nm0 + q * 32) * 2), "n"(32 * 8) : "memory");
           }
           const int cbase = half * PC;                   // `half` is this warp's column part (0..3) here
-          uint4 dres[2 * NPC];                           // this thread's PC columns of X2 (consumed in pass 2)
+          const bool warp_has_pad = __shfl_sync(0xffffffffu, int(cbase + PC > args.n_real), 0) != 0;   // warp-uniform: only the
+          uint4 dres[2 * NPC];                                                                        // last part masks pads                           // this thread's PC columns of X2 (consumed in pass 2)
           {
             const uint4* gp = reinterpret_cast<const uint4*>(args.x2 + size_t(m0 + row) * args.ldx2 + n0 + cbase);
 #pragma unroll
@@ -705,7 +706,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t dx = pack_bf16(x0, x1);   // LayerNorm input gradient, rounded like the reference's bf16 tensor
                 o[e] = pack_bf16(bf16_lo(dw[e]) + bf16_lo(dx), bf16_hi(dw[e]) + bf16_hi(dx));
               }
-              if (c + 8 > args.n_real) {  // group touches pad columns: they must stay exactly zero
+              if (warp_has_pad && c + 8 > args.n_real) {  // group touches pad columns: they must stay exactly zero
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   if (c + 2 * e >= args.n_real) o[e] &= 0xFFFF0000u;

@@ -221,7 +221,7 @@ def roofline_probe(batch: int, peaks):
         ("gemm_tn<192,RES_LN> proj", "gemm_tn_kernel<RES_LN>", 1, lambda: capi.gemm_tn(capi.EPI_RES_LN, x192, w_proj, o192, C2=z192, X1=y192, ln=ln_res), M * 4 * C * E),
         ("gemm_tn<256,GELU2> fc1", "gemm_tn_kernel<GELU2>", 1, lambda: capi.gemm_tn(capi.EPI_GELU2, x192, w_fc1, o768, C2=o768b, ln=ln_gelu), M * (C + 2 * HP) * E),
         ("gemm_tn<192,RES_LN> fc2", "gemm_tn_kernel<RES_LN>", 1, lambda: capi.gemm_tn(capi.EPI_RES_LN, x768, w_fc2, o192, C2=z192, X1=y192, ln=ln_res), M * (HP + 3 * C) * E),
-        ("gemm_tn<256,MUL> fc2 dgrad", "gemm_tn_kernel<MUL>", 1, lambda: capi.gemm_tn(capi.EPI_MUL, x192, w_fc1, o768, X1=y768), M * (C + 2 * HP) * E),
+        ("gemm_tn<192,MUL> fc2 dgrad", "gemm_tn_kernel<MUL>", 1, lambda: capi.gemm_tn(capi.EPI_MUL, x192, w_fc1, o768, X1=y768), M * (C + 2 * HP) * E),
         ("gemm_wgrad<192> fc1/fc2", "gemm_wgrad_kernel", 2, lambda: capi.gemm_wgrad(x768, x192, wg_ws, splits(M, HP), wg_out), M * (HP + C) * E),
         ("gemm_tn<192,LNBWD> fc1 dgrad", "gemm_tn_kernel<LNBWD>", 1, lambda: capi.gemm_tn(capi.EPI_LNBWD, x768, w_fc1t, o192, X1=x192, X2=y192, ln=ln_bwd), M * (HP + 3 * C) * E),
         ("gemm_tn<192,STORE> d_ao", "gemm_tn_kernel<STORE>", 1, lambda: capi.gemm_tn(capi.EPI_STORE, x192, w_proj, o192), M * 2 * C * E),

@@ -561,7 +561,13 @@ def run_ours(args):
             line["comm"]["exposed_comm_ms"] = ms / args.steps - args.single_gpu_ms
             line["comm"]["exposed_note"] = "this run's ms_per_step minus the N=1 ms_per_step passed by --single-gpu-ms"
     if rank == 0:
+        cs = ClockSampler(local)
+        cs.start()
         line["roofline"], line["roofline_kernels"] = roofline_probe(B, peaks)
+        rc = cs.stop()
+        # the probe runs right after the timed steps, i.e. on a GPU that sits at its power cap: compute- / shared-memory-bound
+        # kernels (the attention cores) scale with this clock, HBM-bound ones do not
+        line["roofline"]["clocks_during_probe"] = {"sm_mhz": rc.get("sm_mhz"), "sm_max_mhz": rc.get("sm_max_mhz"), "reasons": rc.get("reasons")}
         # BASELINE.json's metric also names the attention tensor-core utilisation.  Live figure: the MMA work the attention
         # kernels issue (padded head_dim 32, per window 64x64 logits) / CUDA-event time / measured dense bf16 peak; the ncu
         # tensor-pipe counters of this round's captures are quoted next to it.

@@ -545,7 +545,7 @@ static int block_bwd_impl(const SrkBlockDims* d, const SrkGeom* g, const SrkBloc
   BlockGradPtrs gp{grads->norm1_w, grads->norm1_b, grads->rpb_table, grads->qkv_w, grads->qkv_b, grads->proj_w,
                    grads->proj_b,  grads->norm2_w, grads->norm2_b,   grads->fc1_w, grads->fc1_b, grads->fc2_w,
                    grads->fc2_b};
-  SRK_CUDA_OK(launch_pdl(unpack_block_grads_kernel, dim3(296), dim3(256), 0, stream, to_dims(d), us, gp,
+  SRK_CUDA_OK(launch_pdl(unpack_block_grads_kernel, dim3(num_sms() * 8), dim3(256), 0, stream, to_dims(d), us, gp,
                          accumulate ? 1.f : 0.f));
   SRK_LAUNCHED(1);
   SRK_CUDA_OK(cudaGetLastError());

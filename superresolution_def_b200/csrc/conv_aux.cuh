@@ -126,9 +126,9 @@ static __global__ void colsum_ps_kernel(const __nv_bfloat16* __restrict__ dys, i
 static __global__ void conv_in1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                     const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int B, int H, int W,
                                     int C, int Cp) {
-  extern __shared__ float s_w[];  // [Cp][10]: 9 taps + bias
-  for (int i = threadIdx.x; i < Cp * 10; i += blockDim.x) {
-    const int co = i / 10, t = i % 10;
+  extern __shared__ __align__(16) float s_w[];  // [10][Cp]: 9 taps + bias, tap-major (a [Cp][10] layout puts the 24 channel
+  for (int i = threadIdx.x; i < Cp * 10; i += blockDim.x) {   // groups of a warp on two bank sets: 12-way conflicts)
+    const int t = i / Cp, co = i % Cp;
     s_w[i] = (co < C) ? (t < 9 ? w[co * 9 + t] : bias[co]) : 0.f;
   }
   __syncthreads();
@@ -146,13 +146,15 @@ static __global__ void conv_in1_fwd_kernel(const float* __restrict__ x, const fl
       v[t] = (sy >= 0 && sy < H && sx >= 0 && sx < W) ? x[base + (long long)sy * W + sx] : 0.f;
     }
     float o[8];
+    {
+      const float4 b0 = *reinterpret_cast<const float4*>(s_w + 9 * Cp + g * 8), b1 = *reinterpret_cast<const float4*>(s_w + 9 * Cp + g * 8 + 4);
+      o[0] = b0.x; o[1] = b0.y; o[2] = b0.z; o[3] = b0.w; o[4] = b1.x; o[5] = b1.y; o[6] = b1.z; o[7] = b1.w;
+    }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float* ww = s_w + (g * 8 + e) * 10;
-      float a = ww[9];
-#pragma unroll
-      for (int t = 0; t < 9; ++t) a = fmaf(v[t], ww[t], a);
-      o[e] = a;
+    for (int t = 0; t < 9; ++t) {
+      const float4 w0 = *reinterpret_cast<const float4*>(s_w + t * Cp + g * 8), w1 = *reinterpret_cast<const float4*>(s_w + t * Cp + g * 8 + 4);
+      o[0] = fmaf(v[t], w0.x, o[0]); o[1] = fmaf(v[t], w0.y, o[1]); o[2] = fmaf(v[t], w0.z, o[2]); o[3] = fmaf(v[t], w0.w, o[3]);
+      o[4] = fmaf(v[t], w1.x, o[4]); o[5] = fmaf(v[t], w1.y, o[5]); o[6] = fmaf(v[t], w1.z, o[6]); o[7] = fmaf(v[t], w1.w, o[7]);
     }
     *reinterpret_cast<uint4*>(y + p * Cp + g * 8) =
         make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));

@@ -54,3 +54,13 @@ def test_tcgen05_attention_is_the_kernel_that_ran():
 def test_fused_mlp_is_bit_identical_to_the_two_kernel_path():
     r = _run(["tools/gpu_probe_mlp_fused.py", "128", "1024", "18944"], {})
     assert r.returncode == 0 and "ALL OK" in r.stdout, (r.stdout[-3000:], r.stderr[-1500:])
+
+
+def test_measured_alternatives_of_round_2_pass_the_kernel_unit_tests():
+    """SRK_GEMM_BRES=0 (weight tile streamed per output tile instead of resident), SRK_WGRAD_AT=2 (two accumulators per
+    weight-gradient CTA) and SRK_STORE_DACT=0 (gelu' recomputed in the fc2 input-gradient kernel) are A/B switches whose
+    results must stay correct: the unit and block parity suites are re-run with them set."""
+    r = _run(["-m", "pytest", "tests/test_kernels_r2_gpu.py", "tests/test_swin_gpu.py", "-m", "gpu", "-x", "-q"],
+             {"SRK_GEMM_BRES": "0", "SRK_WGRAD_AT": "2", "SRK_STORE_DACT": "0"})
+    assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-2000:])
+    assert " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-2000:]

@@ -19,13 +19,16 @@ constexpr int WG_TOK = 64;                     // tokens per pipeline stage
 constexpr int WG_SUBBOX = 64 * 128;            // one [64 tokens x 64 channels] swizzled box (8 KB)
 
 struct WgradArgs {
-  int T;        // tokens (multiple of 64); split s owns k-iterations [s*I/splits, (s+1)*I/splits), I = T/64
+  int T;        // tokens (multiple of 64); split s owns the 64-token blocks s, s + splits, s + 2 splits, ... of the I = T/64
+                // blocks: all CTAs move through the tensors as one band (like the persistent GEMMs), first to last or,
+                // with `reverse`, last to first
   int Ca, Cb;   // channel counts (Cb == BNW)
   int ca_groups; // ceil(Ca / (AT * 128))
   int splits;
   float* partials;  // [splits][ca_groups * AT * 128][BNW]
   // debug knobs (validated once on hardware, then fixed): descriptor LBO/SBO in bytes
   int lbo_bytes, sbo_bytes;
+  int reverse;
 };
 
 template <int BNW, int AT>
@@ -58,10 +61,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int a_tile = blockIdx.x % args.ca_groups;   // group of AT * 128 channels of A
   const int split = blockIdx.x / args.ca_groups;
   const int total_iters = args.T / WG_TOK;
-  const int it_begin = int((long long)split * total_iters / args.splits);
-  const int it_end = int((long long)(split + 1) * total_iters / args.splits);
-  const int t_begin = it_begin * WG_TOK;
-  const int k_iters = it_end - it_begin;  // >= 1 because splits <= total_iters
+  const int k_iters = (total_iters - split + args.splits - 1) / args.splits;  // >= 1 because splits <= total_iters
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -93,7 +93,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
         const uint32_t sb = sa + 2 * AT * WG_SUBBOX;
-        const int t0 = t_begin + kb * WG_TOK;
+        const int t0 = ((args.reverse ? k_iters - 1 - kb : kb) * args.splits + split) * WG_TOK;
         mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
 #pragma unroll
         for (int b = 0; b < 2 * AT; ++b)   // channels beyond Ca: TMA zero-fills (and still counts the bytes)

@@ -135,7 +135,6 @@ int launch_attn_fwd(const SrkGeom* g, int heads, const void* qkv, int ld_qkv, co
   a.ld_qkv = ld_qkv; a.ld_o = ld_o; a.ones_col = ones_col;
   const int nwin = g->B * (g->H / 8) * (g->W / 8);
   dim3 grid(attn_fwd_gx(nwin, heads), heads);
-  a.reverse = next_direction();
   SRK_CUDA_OK(launch_pdl(win_attn_ws8_fwd_kernel, grid, dim3(ATT_THREADS), 0, stream, a));
   SRK_LAUNCHED(1);
   SRK_CUDA_OK(cudaGetLastError());
@@ -185,7 +184,6 @@ int launch_attn_bwd(const SrkGeom* g, int heads, const void* qkv, int ld_qkv, co
   a.B = g->B; a.H = g->H; a.W = g->W; a.heads = heads; a.shift = g->shift;
   a.ld_qkv = ld_qkv; a.ld_o = ld_o; a.ones_col = -1;
   dim3 grid(gx, heads);
-  a.reverse = next_direction();
   SRK_CUDA_OK(launch_pdl(win_attn_ws8_bwd_kernel, grid, dim3(ATT_THREADS), sizeof(AttnBwdSmem), stream, a));
   SRK_LAUNCHED(1);
   SRK_CUDA_OK(cudaGetLastError());

@@ -25,7 +25,6 @@ static int launch_gemm_tn(const GemmArgs& a, const CUtensorMap& tA, const CUtens
   GemmArgs args = a;
   // K <= 192: B ([BN x K] per N tile) stays resident in shared memory, the ring carries A only (SRK_GEMM_BRES=0: A/B switch)
   static const bool bres_enabled = [] { const char* e = getenv("SRK_GEMM_BRES"); return !(e && e[0] == '0'); }();
-  args.reverse = next_direction();
   args.b_resident = (bres_enabled && Cfg::kResOk && a.K <= 3 * GEMM_BK && grid >= a.N / BN) ? 1 : 0;
   SRK_CUDA_OK(launch_pdl(gemm_tn_kernel<BN, EPI>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, stream, tA, tB, tC, tC2,
                          tX1, tX2, args));
@@ -161,7 +160,7 @@ static int gemm_wgrad_impl(int T, int Ca, int Cb, const void* A, int lda, const 
   const int at = wgrad_at(Ca);
   WgradArgs a{};
   a.T = T; a.Ca = Ca; a.Cb = Cb; a.ca_groups = (Ca + at * 128 - 1) / (at * 128); a.splits = splits; a.partials = workspace;
-  a.lbo_bytes = lbo_bytes; a.sbo_bytes = sbo_bytes; a.reverse = next_direction();
+  a.lbo_bytes = lbo_bytes; a.sbo_bytes = sbo_bytes;
   CUtensorMap tA, tB;
   int rc;
   if ((rc = make_tmap_2d(&tA, A, T, Ca, lda, WG_TOK))) return rc;

@@ -25,7 +25,6 @@ struct AttnArgs {
   int B, H, W, heads, shift;
   int ld_qkv, ld_o;
   int ones_col;               // fwd: column of `out` forced to 1.0 (bias-folding column), -1: none
-  int reverse;                // walk the windows last to first (serpentine order across consecutive kernels, srk_host.h)
   int mask;                   // 1: add HAT's 0/-100 shifted-window mask (hat_arch.py:921-940); SwinIR never masks (:138)
 };
 
@@ -268,9 +267,8 @@ __global__ void __launch_bounds__(ATT_THREADS) win_attn_ws8_fwd_kernel(const Att
   int w = blockIdx.x;
   int buf = 0;
   WinToks tk{0, 0}, tkn{0, 0};
-  auto widx = [&](int w_) { return a.reverse ? nwin - 1 - w_ : w_; };
   if (w < nwin) {
-    tk = window_toks(a, widx(w));
+    tk = window_toks(a, w);
     load_window_tiles(a, tk, smem_u32(s_in[0]), a.qkv, a.ld_qkv, h * 32, nullptr, 0, 0);
   }
   cp_async_commit();
@@ -279,7 +277,7 @@ __global__ void __launch_bounds__(ATT_THREADS) win_attn_ws8_fwd_kernel(const Att
     __syncthreads();   // this window's tiles have landed; every warp is done with the previous window (s_in[buf ^ 1] is free)
     const int wn = w + gridDim.x;
     if (wn < nwin) {
-      tkn = window_toks(a, widx(wn));
+      tkn = window_toks(a, wn);
       load_window_tiles(a, tkn, smem_u32(s_in[buf ^ 1]), a.qkv, a.ld_qkv, h * 32, nullptr, 0, 0);
     }
     cp_async_commit();
@@ -289,7 +287,7 @@ __global__ void __launch_bounds__(ATT_THREADS) win_attn_ws8_fwd_kernel(const Att
     qk_logits(qt, kt, s_bias, r0, lane, s);
     if (masked) {
       bool ly, lx;
-      window_edge_flags(a, widx(w), ly, lx);
+      window_edge_flags(a, w, ly, lx);
       if (ly || lx) add_shift_mask(s, r0, lane, ly, lx);
     }
     softmax_rows(s);
@@ -374,9 +372,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 3) win_attn_ws8_bwd_kernel(const 
   int w = blockIdx.x;
   int buf = 0;
   WinToks tk{0, 0}, tkn{0, 0};
-  auto widx = [&](int w_) { return a.reverse ? nwin - 1 - w_ : w_; };
   if (w < nwin) {
-    tk = window_toks(a, widx(w));
+    tk = window_toks(a, w);
     load_window_tiles(a, tk, smem_u32(sm.in[0]), a.qkv, a.ld_qkv, h * 32, a.dout, a.ld_o, h * 32);
   }
   cp_async_commit();
@@ -387,7 +384,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 3) win_attn_ws8_bwd_kernel(const 
     __syncthreads();   // (1) this window's tiles have landed; every warp is done with the previous window (in[buf ^ 1], P, dS free)
     const int wn = w + gridDim.x;
     if (wn < nwin) {
-      tkn = window_toks(a, widx(wn));
+      tkn = window_toks(a, wn);
       load_window_tiles(a, tkn, smem_u32(sm.in[buf ^ 1]), a.qkv, a.ld_qkv, h * 32, a.dout, a.ld_o, h * 32);
     }
     cp_async_commit();
@@ -399,7 +396,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 3) win_attn_ws8_bwd_kernel(const 
     qk_logits(qt, kt, sm.bias, r0, lane, s);
     if (masked) {
       bool ly, lx;
-      window_edge_flags(a, widx(w), ly, lx);
+      window_edge_flags(a, w, ly, lx);
       if (ly || lx) add_shift_mask(s, r0, lane, ly, lx);
     }
     softmax_rows(s);  // s = P (fp32)

@@ -53,8 +53,6 @@ struct GemmArgs {
   int rows_per_scale;
   const __nv_bfloat16* x2;  // EPI_LNBWD: the residual-gradient tensor X2 [M, ldx2] (read straight from global memory)
   int ldx2;
-  int reverse;        // walk the M tiles from the last row block to the first (serpentine order across consecutive kernels:
-                      // a kernel that starts where its producer stopped finds that part of its input still in the 126 MB L2)
   int b_resident;     // K <= 192: every CTA keeps ONE N tile of B ([BN x K], loaded once) in shared memory and walks M tiles
                       // only; the operand ring then holds A boxes alone (twice to six times as many bytes of A in flight)
 };
@@ -218,7 +216,6 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // Tile walk: tile = blockIdx.x + i * tile_step, (m, n) = (tile / n_tiles, tile % n_tiles).  Resident mode keeps n fixed
   // per CTA: the CTAs with the same n (every n_tiles-th one) share the M tiles among themselves.
   const int tile_step = bres ? ((int(gridDim.x) - int(blockIdx.x) % n_tiles + n_tiles - 1) / n_tiles) * n_tiles : int(gridDim.x);
-  auto tile_m0 = [&](int tile) { const int mt = tile / n_tiles; return (args.reverse ? m_tiles - 1 - mt : mt) * GEMM_BM; };
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -275,7 +272,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < k_iters; ++kb) tma_load_2d(smem_base + kb * (BN * 128), &tmB, bres_bar, kb * GEMM_BK, n0);
       }
       for (int tile = blockIdx.x; tile < num_tiles; tile += tile_step) {
-        const int m0 = tile_m0(tile);
+        const int m0 = (tile / n_tiles) * GEMM_BM;
         const int n0 = (tile % n_tiles) * BN;
         for (int kb = 0; kb < Cfg::kAccs * k_iters; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -331,7 +328,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       uint32_t g = 0;   // global box counter: the epilogue warps walk the same sequence
       for (int tile = blockIdx.x; tile < num_tiles; tile += tile_step) {
-        const int m0 = tile_m0(tile);
+        const int m0 = (tile / n_tiles) * GEMM_BM;
         const int n0 = (tile % n_tiles) * BN;
         for (int j = 0; j < NBOX; ++j, ++g) {
           const uint32_t slot = g % Cfg::kOutSlots;
@@ -352,7 +349,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (lane == 0) {
         uint32_t g = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += tile_step) {
-          const int m0 = tile_m0(tile);
+          const int m0 = (tile / n_tiles) * GEMM_BM;
           const int n0 = (tile % n_tiles) * BN;
           for (int j = 0; j < NBOX; ++j, ++g) {
             const uint32_t slot = g % Cfg::kAuxSlots;
@@ -390,14 +387,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // aux prefetch for the first tile (row epilogues)
     if constexpr (EPI == EPI_RES_LN || EPI == EPI_LNBWD) {
       if (elected && blockIdx.x < num_tiles) {
-        const int m0 = tile_m0(blockIdx.x), n0 = (blockIdx.x % n_tiles) * BN;
+        const int m0 = (blockIdx.x / n_tiles) * GEMM_BM, n0 = (blockIdx.x % n_tiles) * BN;
         mbar_arrive_expect_tx(aux_bar(0), NBOX * BOX_BYTES);
         for (int b = 0; b < NBOX; ++b) tma_load_2d(epi_base + b * BOX_BYTES, &tmX1, aux_bar(0), n0 + b * 64, m0);
       }
     }
 
     for (int tile = blockIdx.x; tile < num_tiles; tile += tile_step, ++it) {
-      const int m0 = tile_m0(tile);
+      const int m0 = (tile / n_tiles) * GEMM_BM;
       const int n0 = (tile % n_tiles) * BN;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
@@ -560,7 +557,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_store_commit();
             tma_store_wait_read<0>();  // v and the previous tile's LN output have left shared memory
             if (next_tile < num_tiles) {  // prefetch the next tile's residual under this tile's passes 2 and 3
-              const int nm0 = tile_m0(next_tile), nn0 = (next_tile % n_tiles) * BN;
+              const int nm0 = (next_tile / n_tiles) * GEMM_BM, nn0 = (next_tile % n_tiles) * BN;
               mbar_arrive_expect_tx(aux_bar(0), NBOX * BOX_BYTES);
               for (int b = 0; b < NBOX; ++b) tma_load_2d(T0 + b * BOX_BYTES, &tmX1, aux_bar(0), nn0 + b * 64, nm0);
             }
@@ -622,14 +619,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (elected) {
             tma_store_wait_read<0>();   // the previous tile's result has left the other buffer
             if (next_tile < num_tiles) {
-              const int nm0 = tile_m0(next_tile), nn0 = (next_tile % n_tiles) * BN;
+              const int nm0 = (next_tile / n_tiles) * GEMM_BM, nn0 = (next_tile % n_tiles) * BN;
               const uint32_t Tn = epi_base + uint32_t((it + 1) & 1) * (NBOX * BOX_BYTES);
               mbar_arrive_expect_tx(aux_bar((it + 1) & 1), NBOX * BOX_BYTES);
               for (int b = 0; b < NBOX; ++b) tma_load_2d(Tn + b * BOX_BYTES, &tmX1, aux_bar((it + 1) & 1), nn0 + b * 64, nm0);
             }
           }
           if (half == 0 && next_tile < num_tiles) {   // next tile's X2 row and row statistics -> L2 (they are read from
-            const int nm0 = tile_m0(next_tile), nn0 = (next_tile % n_tiles) * BN;   // global memory at its start)
+            const int nm0 = (next_tile / n_tiles) * GEMM_BM, nn0 = (next_tile % n_tiles) * BN;   // global memory at its start)
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(args.x2 + size_t(nm0 + row) * args.ldx2 + nn0), "n"(BN * 2) : "memory");
             if (lane == 0)
               asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(args.stats + size_t(nm0 + q * 32) * 2), "n"(32 * 8) : "memory");

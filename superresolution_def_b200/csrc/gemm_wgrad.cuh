@@ -20,15 +20,14 @@ constexpr int WG_SUBBOX = 64 * 128;            // one [64 tokens x 64 channels] 
 
 struct WgradArgs {
   int T;        // tokens (multiple of 64); split s owns the 64-token blocks s, s + splits, s + 2 splits, ... of the I = T/64
-                // blocks: all CTAs move through the tensors as one band (like the persistent GEMMs), first to last or,
-                // with `reverse`, last to first
+                // blocks: all CTAs move through the tensors as one band, like the persistent GEMMs (adjacent CTAs read
+                // adjacent 8 KB pieces at the same time: fc 87.4 -> 84.9 us, qkv 75.9 -> 72.6 us)
   int Ca, Cb;   // channel counts (Cb == BNW)
   int ca_groups; // ceil(Ca / (AT * 128))
   int splits;
   float* partials;  // [splits][ca_groups * AT * 128][BNW]
   // debug knobs (validated once on hardware, then fixed): descriptor LBO/SBO in bytes
   int lbo_bytes, sbo_bytes;
-  int reverse;
 };
 
 template <int BNW, int AT>
@@ -93,7 +92,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
         const uint32_t sb = sa + 2 * AT * WG_SUBBOX;
-        const int t0 = ((args.reverse ? k_iters - 1 - kb : kb) * args.splits + split) * WG_TOK;
+        const int t0 = (kb * args.splits + split) * WG_TOK;
         mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
 #pragma unroll
         for (int b = 0; b < 2 * AT; ++b)   // channels beyond Ca: TMA zero-fills (and still counts the bytes)

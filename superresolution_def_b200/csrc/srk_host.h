@@ -4,8 +4,6 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
-#include <cstdlib>
-#include <atomic>
 #include <string.h>
 #include <stdlib.h>
 
@@ -133,17 +131,6 @@ struct DeviceOnce {
   bool need() const { return ((mask.load(std::memory_order_acquire) >> cur()) & 1ull) == 0; }
   void done() { mask.fetch_or(1ull << cur(), std::memory_order_release); }
 };
-
-// Serpentine traversal: consecutive launches of the streaming kernels (GEMMs, weight gradients, window attention) alternate
-// between first-to-last and last-to-first tile order, so that a consumer starts on the rows its producer wrote last -- the
-// part of the tensor that is still in L2.  Pure scheduling: results do not depend on it.  Measured on the SwinIR step
-// (same box, alternating runs): 62.86 / 63.52 ms with it, 63.11 / 63.46 ms without -- no gain (the consumers are not bound by
-// those first HBM reads), so it is off unless SRK_SERPENTINE=1.
-inline int next_direction() {
-  static const bool on = [] { const char* e = getenv("SRK_SERPENTINE"); return e && e[0] == '1'; }();
-  static std::atomic<unsigned> counter{0};
-  return on ? int(counter.fetch_add(1, std::memory_order_relaxed) & 1u) : 0;
-}
 
 // api_gemm.cu: weight-gradient GEMM that leaves its per-split partials in `workspace` (no reduce kernel)
 int gemm_wgrad_partials(int T, int Ca, int Cb, const void* A, int lda, const void* B, int ldb, float* workspace, int splits,

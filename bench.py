@@ -195,7 +195,9 @@ def roofline_probe(batch: int, peaks):
     rnd = lambda *shape: torch.randn(*shape, device=dev, generator=g).to(bf)  # noqa: E731
     x192, y192, z192, o192 = rnd(M, C), rnd(M, C), rnd(M, C), torch.empty(M, C, device=dev, dtype=bf)
     x576, o576 = rnd(M, QW), torch.empty(M, QW, device=dev, dtype=bf)
-    x768, y768, o768, o768b = rnd(M, HP), rnd(M, HP), torch.empty(M, HP, device=dev, dtype=bf), torch.empty(M, HP, device=dev, dtype=bf)
+    x768, o768 = rnd(M, HP), torch.empty(M, HP, device=dev, dtype=bf)
+    # gelu' is stored as fp16 (second output of GELU2, multiplier of MUL)
+    y768, o768b = torch.randn(M, HP, device=dev, generator=g).to(torch.float16), torch.empty(M, HP, device=dev, dtype=torch.float16)
     w = lambda n, k: (torch.randn(n, k, device=dev, generator=g) / k ** 0.5).to(bf)  # noqa: E731
     w_qkv, w_proj, w_fc1, w_fc2, w_fc1t, w_qkvt = w(QW, C), w(C, C), w(HP, C), w(C, HP), w(C, HP), w(C, QW)
     stats = torch.empty(M, 2, device=dev)

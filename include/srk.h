@@ -30,8 +30,9 @@ long long srk_launch_count(void);
 
 /* ---- epilogues of srk_gemm_tn (values match csrc/gemm_tn.cuh) ---- */
 #define SRK_EPI_STORE 0  /* C = bf16(acc)                                                       */
-#define SRK_EPI_GELU2 1  /* C = gelu(u), C2 = gelu'(u)  — Mlp.act, architecture_swin.py:20       */
-#define SRK_EPI_MUL 2    /* C = acc * X1               — backward of Mlp.act                    */
+#define SRK_EPI_GELU2 1  /* C = gelu(u) (bf16), C2 = gelu'(u) stored as FP16 — Mlp.act, architecture_swin.py:20; C2 is an
+                            opaque 2-byte-per-element tensor whose only consumer is SRK_EPI_MUL              */
+#define SRK_EPI_MUL 2    /* C = bf16(acc) * X1, X1 = the FP16 gelu' tensor of SRK_EPI_GELU2 — backward of Mlp.act */
 #define SRK_EPI_RES_LN 3 /* C = acc + X1, C2 = LN(C)    — residual :149-150 + norm :127,150     */
 #define SRK_EPI_LNBWD 4  /* C = X2 + LNbackward(acc)    — backward of the same                  */
 #define SRK_EPI_GELU1 5  /* C = gelu(u)                 — Mlp.act when gelu'(u) is recomputed by MULG   */
@@ -120,7 +121,7 @@ typedef struct SrkBlockActs {
   void* xn2;         /* [T,Cp] LayerNorm2(x_mid)                                      */
   float* stats2;     /* [T,2]                                                         */
   void* act;         /* [T,Hp] gelu(fc1)                                              */
-  void* dact;        /* [T,Hp] gelu'(fc1), or NULL: not stored, the backward recomputes it (SRK_EPI_MULG) */
+  void* dact;        /* [T,Hp] gelu'(fc1) as FP16, or NULL: not stored, the backward recomputes it (SRK_EPI_MULG) */
   void* x_out;       /* [T,Cp] x_mid + fc2(act)                                       */
   void* xn_out;      /* [T,Cp] LayerNorm_next(x_out): next block's norm1 or the model's final norm */
   float* stats_out;  /* [T,2]                                                         */

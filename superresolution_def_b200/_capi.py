@@ -109,8 +109,10 @@ def gemm_tn(epi, A, B, C, C2=None, X1=None, X2=None, ln: SrkLnArgs | None = None
     M, K = A.shape
     N = B.shape[0]
     assert B.shape[1] == K and tuple(C.shape) == (M, N)
-    for t in (A, B, C, C2, X1, X2):
-        assert t is None or t.dtype == torch.bfloat16
+    # gelu' travels as fp16: the second output of EPI_GELU2 and the multiplier of EPI_MUL (include/srk.h)
+    f16 = {EPI_GELU2: ("C2",), EPI_MUL: ("X1",)}.get(epi, ())
+    for name, t in (("A", A), ("B", B), ("C", C), ("C2", C2), ("X1", X1), ("X2", X2)):
+        assert t is None or t.dtype == (torch.float16 if name in f16 else torch.bfloat16), (name, t.dtype)
     rc = _gemm_tn(epi, M, N, K, _ptr(A), _ld(A), _ptr(B), _ld(B), _ptr(C), _ld(C), _ptr(C2), _ld(C2),
                   _ptr(X1), _ld(X1), _ptr(X2), _ld(X2), ctypes.byref(ln) if ln is not None else None, _stream())
     _check(rc, "srk_gemm_tn")
@@ -129,8 +131,9 @@ def mlp_fwd(xn2, w1, w2, resid, act, dact, x_out, xn_out, hid_ones_col: int, ln:
     T, Cp = xn2.shape
     Hp = w1.shape[0]
     assert tuple(w1.shape) == (Hp, Cp) and tuple(w2.shape) == (Cp, Hp)
-    for t in (xn2, w1, w2, resid, act, dact, x_out, xn_out):
+    for t in (xn2, w1, w2, resid, act, x_out, xn_out):
         assert t is None or (t.dtype == torch.bfloat16 and t.is_contiguous())
+    assert dact is None or (dact.dtype == torch.float16 and dact.is_contiguous())   # gelu' is stored as fp16
     rc = _mlp_fwd(T, Cp, Hp, _ptr(xn2), _ptr(w1), _ptr(w2), _ptr(resid), _ptr(act), _ptr(dact), _ptr(x_out), _ptr(xn_out),
                   hid_ones_col, ctypes.byref(ln), _stream())
     _check(rc, "srk_mlp_fwd")

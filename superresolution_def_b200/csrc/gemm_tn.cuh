@@ -30,8 +30,8 @@ constexpr int BOX_BYTES = 128 * 128;  // one [128 rows x 64 bf16] swizzled box
 
 enum GemmEpilogue : int {
   EPI_STORE = 0,   // C = bf16(acc)
-  EPI_GELU2 = 1,   // C = gelu(u), C2 = gelu'(u), u = bf16(acc)                 (fc1 forward)
-  EPI_MUL = 2,     // C = bf16(acc * X1)                                        (fc2 dgrad -> dU)
+  EPI_GELU2 = 1,   // C = gelu(u) (bf16), C2 = gelu'(u) stored as FP16 (11 significant bits, no conversion)   (fc1 forward)
+  EPI_MUL = 2,     // C = bf16(bf16(acc) * X1), X1 = the FP16 gelu' tensor GELU2 stored   (fc2 dgrad -> dU)
   EPI_RES_LN = 3,  // C = v = bf16(bf16(acc) + X1); C2 = LayerNorm(v)           (proj / fc2 forward)
   EPI_LNBWD = 4,   // C = X2 + LayerNormBackward(acc | X1, stats)               (fc1 / qkv dgrad)
   EPI_GELU1 = 5,   // C = gelu(u), u = acc                 (fc1 forward when the backward recomputes gelu', see MULG)
@@ -116,8 +116,8 @@ __device__ __forceinline__ void gelu_pair(float u, float& a, float& g) {
 // bf16 spacing of the stored value wherever the value exceeds 0.25 and below 2.5e-4 in Phi elsewhere (the bound the fp32
 // path already has from tanh.approx).  u^2 is clamped instead of u (t = min(u^2, 64)): beyond |u| = 8 the tanh argument is
 // u * P(64) = 1.84 u >= 14.7, i.e. tanh = +-1, Phi in {0, 1}, gelu' = Phi exactly.
-// Returns gelu(u) and gelu'(u) for the pair (x0, x1) as packed bf16x2 words.
-__device__ __forceinline__ void gelu_pair_h2(float x0, float x1, uint32_t& a_bf, uint32_t& g_bf) {
+// Returns gelu(u) as a packed bf16x2 word (a GEMM operand) and gelu'(u) as the packed fp16x2 word it was computed in.
+__device__ __forceinline__ void gelu_pair_h2(float x0, float x1, uint32_t& a_bf, uint32_t& g_h2) {
   const __half2 a0 = __float2half2_rn(7.97703653e-01f), a1 = __float2half2_rn(3.68205808e-02f), a2 = __float2half2_rn(-3.20923304e-04f);
   const __half2 d0 = __float2half2_rn(0.5f * 7.97703653e-01f), d1 = __float2half2_rn(1.5f * 3.68205808e-02f), d2 = __float2half2_rn(2.5f * -3.20923304e-04f);
   const __half2 half_ = __float2half2_rn(0.5f), one_ = __float2half2_rn(1.0f);
@@ -133,9 +133,9 @@ __device__ __forceinline__ void gelu_pair_h2(float x0, float x1, uint32_t& a_bf,
   const __half2 a = __hmul2(u, cdf);
   const __half2 s1 = __hfma2(__hneg2(th), th, one_);
   const __half2 g = __hfma2(__hmul2(u, s1), dp, cdf);
-  const float2 af = __half22float2(a), gf = __half22float2(g);
+  const float2 af = __half22float2(a);
   a_bf = pack_bf16(af.x, af.y);
-  g_bf = pack_bf16(gf.x, gf.y);
+  g_h2 = *reinterpret_cast<const uint32_t*>(&g);   // gelu' is only ever read back by EPI_MUL: it stays fp16
 }
 
 // Transposing butterfly: on entry lane l holds v[0..31] (32 columns of its row); on exit v[0] of
@@ -450,8 +450,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
               uint32_t o[4];
 #pragma unroll
-              for (int e = 0; e < 4; ++e)
-                o[e] = pack_bf16(round_bf16(v[2 * e]) * bf16_lo(gw[e]), round_bf16(v[2 * e + 1]) * bf16_hi(gw[e]));
+              for (int e = 0; e < 4; ++e) {
+                const float2 gf = __half22float2(*reinterpret_cast<const __half2*>(&gw[e]));
+                o[e] = pack_bf16(round_bf16(v[2 * e]) * gf.x, round_bf16(v[2 * e + 1]) * gf.y);
+              }
               sts128(out0 + off, make_uint4(o[0], o[1], o[2], o[3]));
             } else if constexpr (EPI == EPI_MULG) {
               const int col0 = n0 + j * 64 + ch * 8;
@@ -485,12 +487,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               uint32_t a[4], g[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) gelu_pair_h2(v[2 * e], v[2 * e + 1], a[e], g[e]);
-              const int col0 = n0 + j * 64 + ch * 8;
-              if (args.ones_col >= col0 && args.ones_col < col0 + 8) {   // constant 1.0 column (bias folding): act = 1, gelu' = 0
+              const unsigned rel = unsigned(args.ones_col - (n0 + j * 64 + ch * 8));   // warp-uniform: one test per 8 columns
+              if (rel < 8u) {   // constant 1.0 column (bias folding): act = 1, gelu' = 0
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  if (col0 + 2 * e == args.ones_col) { a[e] = (a[e] & 0xFFFF0000u) | 0x3F80u; g[e] &= 0xFFFF0000u; }
-                  if (col0 + 2 * e + 1 == args.ones_col) { a[e] = (a[e] & 0x0000FFFFu) | 0x3F800000u; g[e] &= 0x0000FFFFu; }
+                  if (rel == unsigned(2 * e)) { a[e] = (a[e] & 0xFFFF0000u) | 0x3F80u; g[e] &= 0xFFFF0000u; }
+                  if (rel == unsigned(2 * e + 1)) { a[e] = (a[e] & 0x0000FFFFu) | 0x3F800000u; g[e] &= 0x0000FFFFu; }
                 }
               }
               sts128(out0 + off, make_uint4(a[0], a[1], a[2], a[3]));

@@ -171,7 +171,7 @@ def _alloc_acts(cfg: BlockCfg, T: int, device) -> dict:
             "x_out": e(cfg.Cp), "xn_out": e(cfg.Cp),
             "stats_out": torch.empty(T, 2, device=device, dtype=torch.float32)}
     if STORE_GELU_GRAD:
-        acts["dact"] = e(cfg.Hp)
+        acts["dact"] = torch.empty(T, cfg.Hp, device=device, dtype=torch.float16)   # gelu'(u): fp16, read only by EPI_MUL
     return acts
 
 
@@ -391,7 +391,7 @@ class MlpFunction(torch.autograd.Function):
         w = _partial_weights(cfg, x.device, fc1_w=fc1_w, fc1_b=fc1_b, fc2_w=fc2_w, fc2_b=fc2_b)
         xp = _pack_rows(x2, cfg.Cp, C, Tp)
         act = torch.empty(Tp, cfg.Hp, device=x.device, dtype=BF16)
-        dact = torch.empty_like(act)
+        dact = torch.empty_like(act, dtype=torch.float16)   # gelu'(u) is stored as fp16 (EPI_GELU2 / EPI_MUL contract)
         capi.gemm_tn(capi.EPI_GELU2, xp, w["fc1_f"].view(cfg.Hp, cfg.Cp), act, C2=dact,
                      ln=capi.make_ln_args(cfg.Hp, hid, None))
         y = torch.empty(Tp, cfg.Cp, device=x.device, dtype=BF16)

@@ -54,14 +54,14 @@ def test_gemm_gelu2_and_mul(M):
     A = torch.randn(M, K, device="cuda").to(bf)
     B = (torch.randn(N, K, device="cuda") / math.sqrt(K)).to(bf)
     C = torch.empty(M, N, device="cuda", dtype=bf)
-    C2 = torch.empty_like(C)
+    C2 = torch.empty_like(C, dtype=torch.float16)   # gelu' is stored as fp16
     capi.gemm_tn(capi.EPI_GELU2, A, B, C, C2=C2, ln=capi.make_ln_args(N, 720, None))
     u = A.float() @ B.float().t()
     a, g = _gelu_ref(u)
     a[:, 720], g[:, 720] = 1.0, 0.0
-    assert rel_l2(C, a) < 4e-3 and rel_l2(C2, g) < 5e-3, (rel_l2(C, a), rel_l2(C2, g))
+    assert rel_l2(C, a) < 4e-3 and rel_l2(C2, g) < 3e-3, (rel_l2(C, a), rel_l2(C2, g))
     assert (C[:, 720].float() == 1).all() and (C2[:, 720].float() == 0).all()
-    X1 = torch.randn(M, N, device="cuda").to(bf)
+    X1 = torch.randn(M, N, device="cuda").to(torch.float16)
     D = torch.empty(M, N, device="cuda", dtype=bf)
     capi.gemm_tn(capi.EPI_MUL, A, B, D, X1=X1)
     assert rel_l2(D, u.to(bf).float() * X1.float()) < 4e-3

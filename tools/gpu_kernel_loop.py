@@ -13,12 +13,12 @@ torch.manual_seed(0)
 reps = 3
 if which == "gelu2":
     A = torch.randn(T, 192, device=dev).to(bf); W = (torch.randn(768, 192, device=dev) / 14).to(bf)
-    C = torch.empty(T, 768, device=dev, dtype=bf); C2 = torch.empty_like(C)
+    C = torch.empty(T, 768, device=dev, dtype=bf); C2 = torch.empty_like(C, dtype=torch.float16)
     ln = capi.make_ln_args(768, 720, None)
     for _ in range(reps): capi.gemm_tn(capi.EPI_GELU2, A, W, C, C2=C2, ln=ln)
 elif which == "mul":
     A = torch.randn(T, 192, device=dev).to(bf); W = (torch.randn(768, 192, device=dev) / 14).to(bf)
-    X1 = torch.randn(T, 768, device=dev).to(bf); C = torch.empty(T, 768, device=dev, dtype=bf)
+    X1 = torch.randn(T, 768, device=dev).to(torch.float16); C = torch.empty(T, 768, device=dev, dtype=bf)
     for _ in range(reps): capi.gemm_tn(capi.EPI_MUL, A, W, C, X1=X1)
 elif which == "qkv":
     A = torch.randn(T, 192, device=dev).to(bf); W = (torch.randn(576, 192, device=dev) / 14).to(bf)

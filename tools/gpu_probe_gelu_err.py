@@ -11,7 +11,7 @@ M, N, K = 8192, 768, 192
 for scale in (1.0, 3.0):
     A = (torch.randn(M, K, device=dev) * scale).to(bf)
     B = (torch.randn(N, K, device=dev) / math.sqrt(K)).to(bf)
-    C = torch.zeros(M, N, device=dev, dtype=bf); C2 = torch.zeros_like(C)
+    C = torch.zeros(M, N, device=dev, dtype=bf); C2 = torch.zeros_like(C, dtype=torch.float16)
     capi.gemm_tn(capi.EPI_GELU2, A, B, C, C2=C2, ln=capi.make_ln_args(N, -1, None))
     torch.cuda.synchronize()
     u = (A.double() @ B.double().t())

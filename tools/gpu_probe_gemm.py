@@ -54,7 +54,7 @@ def case_gelu_mul():
     M, N, K = 1024, 768, 192
     A = torch.randn(M, K, device=dev).to(bf)
     B = (torch.randn(N, K, device=dev) / math.sqrt(K)).to(bf)
-    C = torch.zeros(M, N, device=dev, dtype=bf); C2 = torch.zeros_like(C)
+    C = torch.zeros(M, N, device=dev, dtype=bf); C2 = torch.zeros_like(C, dtype=torch.float16)
     ln = capi.make_ln_args(N, 720, None)
     capi.gemm_tn(capi.EPI_GELU2, A, B, C, C2=C2, ln=ln)
     torch.cuda.synchronize()
@@ -62,7 +62,7 @@ def case_gelu_mul():
     a, g = gelu_ref(u)
     a[:, 720] = 1; g[:, 720] = 0
     stat("gelu2.a", C, a); stat("gelu2.g", C2, g)
-    X1 = torch.randn(M, N, device=dev).to(bf)
+    X1 = torch.randn(M, N, device=dev).to(torch.float16)
     capi.gemm_tn(capi.EPI_MUL, A, B, C, X1=X1)
     torch.cuda.synchronize()
     stat("mul", C, u * X1.float())

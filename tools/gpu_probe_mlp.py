@@ -11,7 +11,8 @@ rnd = lambda *s: torch.randn(*s, device=dev, generator=g).to(bf)
 xn2, gout = rnd(T, C), rnd(T, C)
 w1 = (torch.randn(HP, C, device=dev, generator=g) / 14).to(bf)
 w2t = (torch.randn(HP, C, device=dev, generator=g) / 28).to(bf)
-act, dact, du, du2 = (torch.empty(T, HP, device=dev, dtype=bf) for _ in range(4))
+act, du, du2 = (torch.empty(T, HP, device=dev, dtype=bf) for _ in range(3))
+dact = torch.empty(T, HP, device=dev, dtype=torch.float16)   # gelu' is stored as fp16
 ln = capi.make_ln_args(HP, 720, None)
 
 

@@ -21,8 +21,9 @@ def run(T, Hp=768, C=180, hidden=720, time_it=False, drop=False):
     gam, bet = 1 + 0.3 * torch.randn(C, device=dev, generator=g), 0.2 * torch.randn(C, device=dev, generator=g)
     rs = (torch.rand(max(1, T // 256), device=dev, generator=g) > 0.3).float() / 0.7 if drop else None
     e = lambda w: torch.full((T, w), float("nan"), device=dev, dtype=bf)  # noqa: E731
-    ref = dict(act=e(Hp), dact=e(Hp), x=e(Cp), xn=e(Cp), st=torch.empty(T, 2, device=dev))
-    got = dict(act=e(Hp), dact=e(Hp), x=e(Cp), xn=e(Cp), st=torch.empty(T, 2, device=dev))
+    eh = lambda w: torch.full((T, w), float("nan"), device=dev, dtype=torch.float16)  # noqa: E731  (gelu' is stored as fp16)
+    ref = dict(act=e(Hp), dact=eh(Hp), x=e(Cp), xn=e(Cp), st=torch.empty(T, 2, device=dev))
+    got = dict(act=e(Hp), dact=eh(Hp), x=e(Cp), xn=e(Cp), st=torch.empty(T, 2, device=dev))
 
     def unfused(o):
         capi.gemm_tn(capi.EPI_GELU2, xn2, w1, o["act"], C2=o["dact"], ln=capi.make_ln_args(Hp, hidden, None))

@@ -4,6 +4,7 @@
 // stream; it never allocates or synchronises.
 #include "attn_oca8.cuh"
 #include "attn_tc8.cuh"
+#include "attn_tc16.cuh"
 #include "cab_aux.cuh"
 #include "block_aux.cuh"
 #include "srk_host.h"
@@ -209,6 +210,32 @@ int launch_attn16_fwd_t(const Attn16Args& a, cudaStream_t stream) {
   return SRK_OK;
 }
 
+// Window-16 forward on tcgen05 / TMEM / TMA (attn_tc16.cuh): the default for every shape the HAT models produce (even head
+// count, packed q|k|v rows, window-aligned image).  SRK_ATTN16_TC=0 selects the mma.sync kernel (A/B measurements, tests).
+bool attn16_tc_eligible(const SrkGeom* g, int heads, int ld_qkv, int ld_o) {
+  const char* e = getenv("SRK_ATTN16_TC");
+  if (e && e[0] == '0') return false;
+  return g->ws == 16 && (g->shift == 0 || g->shift == 8) && (heads % 2) == 0 && ld_qkv >= 3 * heads * 32 && ld_o >= heads * 32 &&
+         g->H % 16 == 0 && g->W % 16 == 0;
+}
+template <int MODE>
+int launch_attn16_tc_fwd_t(const CUtensorMap& tm, const Attn16Args& a, cudaStream_t stream) {
+  using G = TC16<MODE>;
+  static DeviceOnce configured;
+  if (configured.need()) {
+    SRK_CUDA_OK(cudaFuncSetAttribute(win_attn_tc16_fwd_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM));
+    configured.done();
+  }
+  const int nwin = a.B * (a.H / 16) * (a.W / 16), nhp = a.heads / 2;
+  int gx = num_sms() / nhp;
+  if (gx > nwin) gx = nwin;
+  if (gx < 1) gx = 1;
+  win_attn_tc16_fwd_kernel<MODE><<<dim3(gx, nhp), TC16_THREADS, G::SMEM, stream>>>(tm, a);
+  SRK_LAUNCHED(1);
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
 int attn16_bwd_gx(int nwin, int heads) {
   int gx = num_sms() / heads;
   if (gx > nwin) gx = nwin;
@@ -312,6 +339,13 @@ int attn16_fwd(const SrkGeom* g, int mode, int heads, const void* qkv, int ld_qk
     SRK_LAUNCHED(1);
     SRK_CUDA_OK(cudaGetLastError());
     return SRK_OK;
+  }
+  if (attn16_tc_eligible(g, heads, ld_qkv, ld_out)) {
+    CUtensorMap tm;
+    const int rc = make_tmap_nhwc(&tm, qkv, ld_qkv, g->W, g->H, g->B, ld_qkv, (uint64_t)g->W * ld_qkv,
+                                  (uint64_t)g->H * g->W * ld_qkv, 8, 8);
+    if (rc) return rc;
+    return mode == MODE_SELF ? launch_attn16_tc_fwd_t<MODE_SELF>(tm, a, stream) : launch_attn16_tc_fwd_t<MODE_OCA>(tm, a, stream);
   }
   return mode == MODE_SELF ? launch_attn16_fwd_t<MODE_SELF>(a, stream) : launch_attn16_fwd_t<MODE_OCA>(a, stream);
 }

@@ -57,6 +57,21 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
+// Non-blocking probe (mbarrier.try_wait may suspend the thread for a system-dependent time before it reports "not yet";
+// an event loop that serves several barriers must not sleep on one of them).
+__device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 #if SRK_WATCHDOG
   uint32_t spins = 0;

@@ -284,18 +284,23 @@ win_attn_tc16_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const Attn16
           mbar_wait(s_full(l), uint32_t(n_run) & 1u);
           tc_fence_after();
           // ---- pass 1: row maximum of the raw logits -> an upper bound of the biased, masked row maximum
-          float mx = -INFINITY;
+          float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;   // four independent chains
 #pragma unroll 1
           for (int jj = 0; jj < G::PCH; ++jj) {
             uint32_t sv[64];
             tmem_ld_x64(tm_lane + uint32_t(jj * 64), sv);
             tmem_ld_wait();
 #pragma unroll
-            for (int e = 0; e < 64; e += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])));
+            for (int e = 0; e < 64; e += 8) {
+              mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])));
+              mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sv[e + 2]), __uint_as_float(sv[e + 3])));
+              mx2 = fmaxf(mx2, fmaxf(__uint_as_float(sv[e + 4]), __uint_as_float(sv[e + 5])));
+              mx3 = fmaxf(mx3, fmaxf(__uint_as_float(sv[e + 6]), __uint_as_float(sv[e + 7])));
+            }
           }
-          const float ml2 = fmaf(mx, kLog2e, tmax);
+          const float ml2 = fmaf(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)), kLog2e, tmax);
           // ---- pass 2: P chunk by chunk
-          float sum = 0.f;
+          float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
 #pragma unroll 1
           for (int jj = 0; jj < G::PCH; ++jj, ++c_run) {
             const int cj = part * G::PCH + jj;   // chunk of the key window: SELF quadrant (cj >> 1, cj & 1), OCA (cj / 3, cj % 3)
@@ -316,7 +321,7 @@ win_attn_tc16_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const Attn16
               const int koff = (e >> 3) * TC16_TSTRIDE + (e & 7);
               const float bias = (MODE == MODE_SELF) ? tj[-koff] : tj[koff];
               const float p = fast_ex2(fmaf(__uint_as_float(sv[e]), kLog2e, bias + cb));
-              sum += p;
+              if ((e & 3) == 0) sum0 += p; else if ((e & 3) == 1) sum1 += p; else if ((e & 3) == 2) sum2 += p; else sum3 += p;
               sv[e] = __float_as_uint(p);
             }
             const int slot = c_run % G::PSLOTS;
@@ -336,6 +341,7 @@ win_attn_tc16_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const Attn16
             if (lane == 0) mbar_arrive(p_full(l, slot));
           }
           // ---- O of this part
+          const float sum = (sum0 + sum1) + (sum2 + sum3);
           mbar_wait(o_full(l), uint32_t(n_run) & 1u);
           tc_fence_after();
           uint32_t ov[32];

@@ -64,3 +64,79 @@ def test_measured_alternatives_of_round_2_pass_the_kernel_unit_tests():
              {"SRK_GEMM_BRES": "0", "SRK_WGRAD_AT": "2", "SRK_STORE_DACT": "0"})
     assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-2000:])
     assert " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-2000:]
+
+
+# ---- window 16 (HAT): the tcgen05 / TMEM / TMA forward kernel (csrc/attn_tc16.cuh) IS the default dispatch; the mma.sync
+# kernel (SRK_ATTN16_TC=0, read per call) stays as the A/B partner.  test_hat_gpu.py compares the default against torch / the
+# oracle; here the two kernels are compared with each other on the shapes the HAT models produce, incl. ragged image sizes,
+# the masked last window row / column of a shifted block and OCAB windows whose 24x24 halo leaves the image on every side.
+@pytest.mark.parametrize("mode,shift", [("self", 0), ("self", 8), ("oca", 0)])
+@pytest.mark.parametrize("shape", [(1, 16, 16), (2, 32, 48), (1, 64, 64), (3, 48, 16)])
+def test_window16_forward_tcgen05_matches_mma_sync(mode, shift, shape):
+    import torch
+    from superresolution_def_b200 import _capi as capi
+    B, H, W = shape
+    heads, T = 6, B * H * W
+    g = torch.Generator(device="cuda").manual_seed(11 + shift + H)
+    qkv = torch.zeros(T, 3, heads, 32, device="cuda")
+    qkv[..., :30] = torch.randn(T, 3, heads, 30, device="cuda", generator=g) * 1.5
+    qkv = qkv.view(T, 576).to(torch.bfloat16)
+    m = capi.ATTN_SELF if mode == "self" else capi.ATTN_OCA
+    table = torch.randn(961 if mode == "self" else 1521, heads, device="cuda", generator=g)
+    res = {}
+    old = os.environ.get("SRK_ATTN16_TC")
+    try:
+        for tc in ("0", "1"):
+            os.environ["SRK_ATTN16_TC"] = tc
+            out = torch.full((T, heads * 32), float("nan"), device="cuda", dtype=torch.bfloat16)
+            lse = torch.full((heads, T), float("nan"), device="cuda")
+            n0 = capi.launch_count()
+            capi.win_attn16_fwd(capi.SrkGeom(B, H, W, 16, shift), m, heads, qkv, table, out, lse, ones_col=30)
+            torch.cuda.synchronize()
+            assert capi.launch_count() == n0 + 1
+            res[tc] = (out.float(), lse)
+    finally:
+        if old is None:
+            os.environ.pop("SRK_ATTN16_TC", None)
+        else:
+            os.environ["SRK_ATTN16_TC"] = old
+    (o0, l0), (o1, l1) = res["0"], res["1"]
+    assert torch.isfinite(o1).all() and torch.isfinite(l1).all()
+    rel = ((o1 - o0).norm() / o0.norm()).item()
+    # both kernels round P to bf16 before P V (different summation order): agreement to bf16 rounding, tolerance 6e-3 rel-L2
+    # on the output, 2e-3 absolute on the row log-sum-exp (fp32 in both)
+    assert rel < 6e-3, rel
+    assert (l1 - l0).abs().max().item() < 2e-3
+    assert (o1[:, 30] == 1).all(), "bias-folding column of head 0"
+    assert not torch.equal(o0, o1), "SRK_ATTN16_TC did not change the dispatch"
+
+
+def test_window16_forward_tcgen05_large_logits_and_wide_bias_range():
+    """The tcgen05 kernel subtracts an UPPER BOUND of the row maximum (raw-logit row max + table max) instead of the exact
+    maximum; logits of +-150 with a bias table spanning +-30 (far beyond anything a trained HAT produces) must neither
+    overflow nor flush a row to zero: output and log-sum-exp stay finite and agree with the mma.sync kernel."""
+    import torch
+    from superresolution_def_b200 import _capi as capi
+    B, H, W, heads = 1, 32, 32, 6
+    T = B * H * W
+    g = torch.Generator(device="cuda").manual_seed(5)
+    qkv = torch.zeros(T, 3, heads, 32, device="cuda")
+    qkv[..., :30] = torch.randn(T, 3, heads, 30, device="cuda", generator=g)
+    qkv[:, :2] *= 5.0   # q, k: logits ~ N(0, 137^2)
+    qkv = qkv.view(T, 576).to(torch.bfloat16)
+    table = torch.randn(961, heads, device="cuda", generator=g) * 10.0
+    res = {}
+    try:
+        for tc in ("0", "1"):
+            os.environ["SRK_ATTN16_TC"] = tc
+            out = torch.full((T, heads * 32), float("nan"), device="cuda", dtype=torch.bfloat16)
+            lse = torch.full((heads, T), float("nan"), device="cuda")
+            capi.win_attn16_fwd(capi.SrkGeom(B, H, W, 16, 8), capi.ATTN_SELF, heads, qkv, table, out, lse, ones_col=-1)
+            torch.cuda.synchronize()
+            res[tc] = (out.float(), lse)
+    finally:
+        os.environ.pop("SRK_ATTN16_TC", None)
+    (o0, l0), (o1, l1) = res["0"], res["1"]
+    assert torch.isfinite(o1).all() and torch.isfinite(l1).all()
+    assert ((o1 - o0).norm() / o0.norm()).item() < 1e-2
+    assert ((l1 - l0).abs() / l0.abs().clamp_min(1.0)).max().item() < 1e-4

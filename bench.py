@@ -298,7 +298,7 @@ def run_gan(args):
     mb, accum = args.batch or 2, 4
     torch.manual_seed(0)
     net_g = SwinIR(**MODEL_KW).to(dev)
-    net_d = UNetDiscriminatorSN(num_in_ch=1, num_feat=64).to(dev).to(memory_format=torch.channels_last)
+    net_d = UNetDiscriminatorSN(num_in_ch=1, num_feat=64).to(dev)
     DDP = torch.nn.parallel.DistributedDataParallel
     net_g = DDP(net_g, device_ids=[local], output_device=local, find_unused_parameters=True)
     net_d = DDP(net_d, device_ids=[local], output_device=local, find_unused_parameters=False)
@@ -345,13 +345,13 @@ def run_gan(args):
     per_step = world * mb * accum
     line = {"metric": "SwinIR + UNetDiscriminatorSN GAN train patches/s (128x128 -> 512x512)", "value": per_step * args.steps / (ms * 1e-3),
             "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 (generator kernels) / fp16 autocast (discriminator, VGG)",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 (generator and discriminator kernels) / fp16 autocast (VGG loss network)",
             "data": "synthetic",
             "config": {"workload": f"train_swin.py micro-step semantics: D step + G step, RaGAN + L1 + VGG-perceptual (seeded VGG-19), DDP over NCCL, "
                                    f"micro-batch {mb} x {accum} accumulation per optimizer step (BASELINE configs[3])",
                        "global_batch": per_step, "parallelism": f"dp{world}", "launch": "eager (as the script)",
                        "l2": "two input batches rotated; activations of every forward exceed L2",
-                       "discriminator": "interface mirror on stock ATen/cuDNN (channels_last); generator = libsrk"},
+                       "discriminator": "libsrk (disc_engine: 4x4 stride-2 convolutions / transposed convolutions as tcgen05 GEMMs over patch matrices); generator = libsrk; VGG-19 loss network = stock ATen/cuDNN"},
             "e2e": {"value": per_step * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": accum * mb * (128 * 128 + 512 * 512) * 4, "d2h_bytes_per_step": accum * 8},
             "gpu_launches": launches, "clocks": clocks, "loss_g": float(out_e[0]), "loss_d": float(out_e[1]),

@@ -303,6 +303,40 @@ int srk_cab_se_bwd(const void* g, const void* y, int B, int HW, int C, int Cp, i
                    float* dw1, float* db1, float* dw2, float* db2, void* stream);
 
 /* ======================================================================================================
+ * UNetDiscriminatorSN (models/discriminator_swin.py:43-84, models/discriminator_hat.py:8-49):
+ * the eight 4x4 / stride-2 / pad-1 convolutions and transposed convolutions run on srk_gemm_tn / srk_gemm_wgrad through a
+ * patch matrix; the 3x3 layers reuse srk_conv_in1_*, srk_conv3x3_igemm / _wgrad and srk_conv_out1_*.
+ *   Conv2d(4,2,1) + LeakyReLU          y  = srk_gemm_tn_lrelu(patches(x), Wf)          Wf [Cout, 16*Cin], k = (ky*4+kx)*Cin + ci
+ *   its input gradient                 dx = fold(srk_gemm_tn(STORE, dy_pre, Wt))        Wt [16*Cin, Cout]
+ *   ConvTranspose2d(4,2,1) + LeakyReLU y  = fold(srk_gemm_tn(STORE, x, Wu), LRELU)      Wu [16*Cout, Cin]
+ *   its input gradient                 dx = srk_gemm_tn(STORE, patches(dy * mask), Wd)  Wd [Cin, 16*Cout]
+ *   weight gradients                   srk_gemm_wgrad(patches, dy_pre) / (x, patches)
+ * ====================================================================================================== */
+
+/* C[M,N] = bf16(leaky_relu(A[M,K] * B[N,K]^T, slope)); same kernel and shape rules as srk_gemm_tn(SRK_EPI_STORE). */
+#define SRK_EPI_LRELU 7
+int srk_gemm_tn_lrelu(int M, int N, int K, const void* A, int lda, const void* B, int ldb, void* C, int ldc, float slope,
+                      void* stream);
+
+/* patches [B*(H/2)*(W/2), 16*x->C] bf16 (contiguous) = the 4x4 / stride-2 / pad-1 patches of the NHWC view x [B,H,W,C];
+ * if f != NULL the gathered value is x * (f > 0 ? 1 : slope) (LeakyReLU backward applied to a gradient image while it is
+ * gathered; f = the forward activation at the same pixels).  Replaces the unfold inside nn.Conv2d(.., 4, 2, 1)
+ * (discriminator_swin.py:10,52) and inside the input gradient of nn.ConvTranspose2d(.., 4, 2, 1) (:25). */
+int srk_disc_patches_k4s2(const SrkView* x, const SrkView* f, float slope, int B, int H, int W, void* patches, void* stream);
+
+#define SRK_FOLD_NONE 0  /* y = fold(taps) + add                                     */
+#define SRK_FOLD_LRELU 1 /* y = leaky_relu(fold(taps) + add, slope)                  */
+#define SRK_FOLD_MASK 2  /* y = (fold(taps) + add) * (f > 0 ? 1 : slope)             */
+/* Fold of a tap matrix [B*Hi*Wi, 16*y->C] (bf16, contiguous) onto the NHWC view y [B,2Hi,2Wi,C]: every output pixel sums
+ * the (at most four) taps that reach it — gather form, deterministic, no atomics; add (optional view, same channels) is
+ * added before the activation.  This is nn.ConvTranspose2d(.., 4, 2, 1) after its GEMM (:25) and the input gradient of
+ * nn.Conv2d(.., 4, 2, 1) (:10), with the skip-connection gradient of torch.cat (:40) as `add`. */
+int srk_disc_fold_k4s2(const void* taps, int B, int Hi, int Wi, const SrkView* add, const SrkView* f, int act, float slope,
+                       const SrkView* y, void* stream);
+/* y = leaky_relu(y, slope) in place on a view (nn.LeakyReLU(0.2, inplace=True) after the 1 -> nf convolution, :49-50) */
+int srk_view_lrelu(const SrkView* y, long long npix, float slope, void* stream);
+
+/* ======================================================================================================
  * Data formats on either side of the path: 16-bit image planes.
  * ====================================================================================================== */
 

@@ -570,3 +570,47 @@ def img1_pack(x, y8):
 
 def img1_unpack(x8, y):
     _check(_img1_unpack(_ptr(x8), _ptr(y), y.numel(), _stream()), "srk_img1_unpack")
+
+
+# ---------------------------------------------------------------------------------------------------
+# UNetDiscriminatorSN helpers (include/srk.h): patch gather / fold around the tcgen05 GEMMs
+# ---------------------------------------------------------------------------------------------------
+EPI_LRELU = 7
+FOLD_NONE, FOLD_LRELU, FOLD_MASK = 0, 1, 2
+
+_gemm_tn_lrelu = _sig("srk_gemm_tn_lrelu", [c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_float,
+                                            c_void_p])
+_disc_patches = _sig("srk_disc_patches_k4s2", [POINTER(SrkView), POINTER(SrkView), c_float, c_int, c_int, c_int, c_void_p,
+                                               c_void_p])
+_disc_fold = _sig("srk_disc_fold_k4s2", [c_void_p, c_int, c_int, c_int, POINTER(SrkView), POINTER(SrkView), c_int, c_float,
+                                         POINTER(SrkView), c_void_p])
+_view_lrelu = _sig("srk_view_lrelu", [POINTER(SrkView), c_longlong, c_float, c_void_p])
+
+
+def gemm_tn_lrelu(A, B, C, slope):
+    """C[M,N] = bf16(leaky_relu(A[M,K] @ B[N,K]^T, slope)); bf16 2-D row-major operands (last stride 1)."""
+    M, K = A.shape
+    N = B.shape[0]
+    assert B.shape[1] == K and tuple(C.shape) == (M, N)
+    for t in (A, B, C):
+        assert t.dtype == torch.bfloat16
+    _check(_gemm_tn_lrelu(M, N, K, _ptr(A), _ld(A), _ptr(B), _ld(B), _ptr(C), _ld(C), slope, _stream()), "srk_gemm_tn_lrelu")
+
+
+def disc_patches_k4s2(x: SrkView, f: SrkView | None, slope, B, H, W, patches):
+    """patches [>= B*(H/2)*(W/2), 16*C] bf16 contiguous <- 4x4 / stride-2 / pad-1 patches of the NHWC view x (masked by f)."""
+    assert patches.dtype == torch.bfloat16 and patches.is_contiguous() and patches.shape[1] == 16 * x.C
+    assert patches.shape[0] >= B * (H // 2) * (W // 2)
+    _check(_disc_patches(_vref(x), _vref(f), slope, B, H, W, _ptr(patches), _stream()), "srk_disc_patches_k4s2")
+
+
+def disc_fold_k4s2(taps, B, Hi, Wi, y: SrkView, add: SrkView | None = None, f: SrkView | None = None, act=FOLD_NONE,
+                   slope=0.2):
+    """NHWC view y [B, 2Hi, 2Wi, C] <- act(fold(taps [>= B*Hi*Wi, 16*C]) + add)."""
+    assert taps.dtype == torch.bfloat16 and taps.is_contiguous() and taps.shape[1] == 16 * y.C
+    assert taps.shape[0] >= B * Hi * Wi
+    _check(_disc_fold(_ptr(taps), B, Hi, Wi, _vref(add), _vref(f), act, slope, _vref(y), _stream()), "srk_disc_fold_k4s2")
+
+
+def view_lrelu(y: SrkView, npix, slope):
+    _check(_view_lrelu(_vref(y), npix, slope, _stream()), "srk_view_lrelu")

@@ -289,8 +289,11 @@ extern "C" int srk_conv_in1_fwd(const float* x, const float* w, const float* bia
 extern "C" int srk_conv_in1_wgrad(const float* x, const void* dy, float* ws, float* dw, float* db, int B, int H, int W,
                                   int C, int Cp, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const int grid = num_sms();
-  const int threads = (Cp / 8) * 8;  // 8 pixels in flight per block
+  // 8 pixels in flight per block at the generators' widths (Cp = 192 / 64 at 128^2); the discriminator's first layer
+  // (Cp = 64 at 512^2: 16x the pixels) gets 32 pixel lanes per block and four blocks per SM
+  const bool wide = Cp <= 64 && (long long)B * H * W >= (1 << 18);
+  const int grid = wide ? num_sms() * 4 : num_sms();
+  const int threads = (Cp / 8) * (wide ? 32 : 8);
   conv_in1_wgrad_kernel<<<grid, threads, Cp * 10 * sizeof(float), stream>>>(x, static_cast<const __nv_bfloat16*>(dy), ws,
                                                                             B, H, W, Cp);
   SRK_LAUNCHED(1);

@@ -59,9 +59,9 @@ extern "C" int srk_gemm_grid(int M, int N) {
   return tiles < num_sms() ? tiles : num_sms();
 }
 
-extern "C" int srk_gemm_tn(int epi, int M, int N, int K, const void* A, int lda, const void* B, int ldb, void* C,
-                           int ldc, void* C2, int ldc2, const void* X1, int ldx1, const void* X2, int ldx2,
-                           const SrkLnArgs* ln, void* stream_) {
+static int gemm_tn_impl(int epi, int M, int N, int K, const void* A, int lda, const void* B, int ldb, void* C,
+                        int ldc, void* C2, int ldc2, const void* X1, int ldx1, const void* X2, int ldx2,
+                        const SrkLnArgs* ln, float slope, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (M <= 0 || N <= 0 || K <= 0 || M % GEMM_BM != 0 || K % GEMM_BK != 0)
     return fail(SRK_ERR_ARG, "srk_gemm_tn: M must be a multiple of 128 and K of 64");
@@ -71,7 +71,7 @@ extern "C" int srk_gemm_tn(int epi, int M, int N, int K, const void* A, int lda,
   GemmArgs a{};
   a.M = M; a.N = N; a.K = K;
   a.n_real = N; a.ones_col = -1; a.gamma = nullptr; a.beta = nullptr; a.stats = nullptr; a.partials = nullptr;
-  a.eps = 1e-5f; a.row_scale = nullptr; a.rows_per_scale = 1;
+  a.eps = 1e-5f; a.row_scale = nullptr; a.rows_per_scale = 1; a.slope = slope;
   if (ln) {
     a.n_real = ln->n_real; a.ones_col = ln->ones_col; a.gamma = ln->gamma; a.beta = ln->beta;
     a.stats = ln->stats; a.partials = ln->partials; a.eps = ln->eps;
@@ -107,6 +107,10 @@ extern "C" int srk_gemm_tn(int epi, int M, int N, int K, const void* A, int lda,
   SRK_CASE(128, EPI_STORE)
   SRK_CASE(192, EPI_STORE)
   SRK_CASE(256, EPI_STORE)
+  SRK_CASE(64, EPI_LRELU)
+  SRK_CASE(128, EPI_LRELU)
+  SRK_CASE(192, EPI_LRELU)
+  SRK_CASE(256, EPI_LRELU)
   SRK_CASE(128, EPI_GELU2)
   SRK_CASE(256, EPI_GELU2)
   SRK_CASE(128, EPI_MUL)
@@ -121,6 +125,18 @@ extern "C" int srk_gemm_tn(int epi, int M, int N, int K, const void* A, int lda,
   SRK_CASE(192, EPI_LNBWD)
 #undef SRK_CASE
   return fail(SRK_ERR_UNSUPPORTED, "srk_gemm_tn: no kernel instance for (BN, epilogue)");
+}
+
+extern "C" int srk_gemm_tn(int epi, int M, int N, int K, const void* A, int lda, const void* B, int ldb, void* C,
+                           int ldc, void* C2, int ldc2, const void* X1, int ldx1, const void* X2, int ldx2,
+                           const SrkLnArgs* ln, void* stream) {
+  if (epi == EPI_LRELU) return fail(SRK_ERR_ARG, "srk_gemm_tn: SRK_EPI_LRELU is served by srk_gemm_tn_lrelu (it carries the slope)");
+  return gemm_tn_impl(epi, M, N, K, A, lda, B, ldb, C, ldc, C2, ldc2, X1, ldx1, X2, ldx2, ln, 0.f, stream);
+}
+
+extern "C" int srk_gemm_tn_lrelu(int M, int N, int K, const void* A, int lda, const void* B, int ldb, void* C, int ldc,
+                                 float slope, void* stream) {
+  return gemm_tn_impl(EPI_LRELU, M, N, K, A, lda, B, ldb, C, ldc, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, slope, stream);
 }
 
 template <int BNW, int AT>

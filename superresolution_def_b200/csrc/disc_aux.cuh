@@ -1,0 +1,141 @@
+// disc_aux.cuh — patch gather / scatter-free fold for the 4x4, stride-2, pad-1 convolutions and transposed convolutions of
+// UNetDiscriminatorSN (models/discriminator_swin.py:10, :25, :52; models/discriminator_hat.py:8-49), so that all eight of
+// them run on the persistent tcgen05 GEMM (gemm_tn.cuh) and their weight gradients on the MN-major tcgen05 GEMM
+// (gemm_wgrad.cuh):
+//
+//   Conv2d(4,2,1)           y  = lrelu( patches(x) @ Wf^T )          patches: [B*H/2*W/2, 16*C], k = (ky*4 + kx)*C + c
+//   its input gradient      dx = fold( dy_pre @ Wt^T )               fold: every input pixel sums its (at most) 4 taps
+//   ConvTranspose2d(4,2,1)  y  = lrelu( fold( x @ Wu^T ) )           (the transposed convolution IS the fold of a GEMM)
+//   its input gradient      dx = patches(dy_pre) @ Wd^T
+//
+// Both helpers are pure HBM streams (16-byte vectors, channel-contiguous): the patch matrix is 4x the activation it is
+// gathered from, which at the discriminator's sizes (<= 268 MB at 512^2 x 2) costs less than the launch of a dedicated
+// implicit-GEMM kernel family would save; LeakyReLU and its backward mask ride on the passes that exist anyway.
+#pragma once
+#include "srk_ptx.cuh"
+
+namespace srk {
+
+__device__ __forceinline__ void bf16x8_to_f32(const uint4& v, float (&f)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { f[2 * e] = bf16_lo(w[e]); f[2 * e + 1] = bf16_hi(w[e]); }
+}
+__device__ __forceinline__ uint4 f32_to_bf16x8(const float (&f)[8]) {
+  return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+}
+
+// patches[m][(ky*4+kx)*C + c] = g[b][2*oy-1+ky][2*ox-1+kx][c]  (zero outside the image), m = (b*Ho + oy)*Wo + ox,
+// g = x, or x * (f > 0 ? 1 : slope) when f is given (LeakyReLU backward applied while gathering a gradient image).
+// One thread per 16-byte vector of the patch matrix: its linear index IS the destination offset.
+static __global__ void __launch_bounds__(256) disc_patches_k4s2_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
+                                                                       const __nv_bfloat16* __restrict__ f, int ldf, float slope,
+                                                                       int B, int H, int W, int C,
+                                                                       __nv_bfloat16* __restrict__ patches) {
+  const int groups = C >> 3;
+  const int Ho = H >> 1, Wo = W >> 1;
+  const long long total = (long long)B * Ho * Wo * 16 * groups;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int cg = int(idx % groups);
+    long long t = idx / groups;
+    const int tap = int(t & 15);
+    t >>= 4;
+    const int ox = int(t % Wo);
+    t /= Wo;
+    const int oy = int(t % Ho);
+    const int b = int(t / Ho);
+    const int iy = 2 * oy - 1 + (tap >> 2), ix = 2 * ox - 1 + (tap & 3);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+      const long long pix = ((long long)b * H + iy) * W + ix;
+      v = *reinterpret_cast<const uint4*>(x + pix * ldx + cg * 8);
+      if (f != nullptr) {
+        const uint4 fv = *reinterpret_cast<const uint4*>(f + pix * ldf + cg * 8);
+        float xv[8], fw[8];
+        bf16x8_to_f32(v, xv);
+        bf16x8_to_f32(fv, fw);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) xv[e] = fw[e] > 0.f ? xv[e] : xv[e] * slope;
+        v = f32_to_bf16x8(xv);
+      }
+    }
+    *reinterpret_cast<uint4*>(patches + idx * 8) = v;
+  }
+}
+
+// Fold of a [B*Hi*Wi, 16*C] tap matrix onto the [B, 2Hi, 2Wi, C] image (gather form, no atomics):
+//   y[b][Y][X][c] = sum over (ky, kx) with (Y+1-ky), (X+1-kx) even and in range of taps[(b, (Y+1-ky)/2, (X+1-kx)/2)][(ky*4+kx)*C + c]
+//   then  + add (optional)  then  act: 0 none, 1 LeakyReLU(slope), 2 multiply by (f > 0 ? 1 : slope)  (LeakyReLU backward).
+enum { DISC_ACT_NONE = 0, DISC_ACT_LRELU = 1, DISC_ACT_MASK = 2 };
+static __global__ void __launch_bounds__(256) disc_fold_k4s2_kernel(const __nv_bfloat16* __restrict__ taps, int B, int Hi, int Wi, int C,
+                                                                    const __nv_bfloat16* __restrict__ add, int ldadd,
+                                                                    const __nv_bfloat16* __restrict__ f, int ldf, int act, float slope,
+                                                                    __nv_bfloat16* __restrict__ y, int ldy) {
+  const int groups = C >> 3;
+  const int Ho = 2 * Hi, Wo = 2 * Wi;
+  const long long total = (long long)B * Ho * Wo * groups;
+  const long long row = 16LL * C;   // elements per row of the tap matrix
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int cg = int(idx % groups);
+    const long long pix = idx / groups;
+    const int X = int(pix % Wo);
+    const int Y = int((pix / Wo) % Ho);
+    const int b = int(pix / ((long long)Wo * Ho));
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int ky0 = (Y + 1) & 1, kx0 = (X + 1) & 1;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int ky = ky0 + 2 * a;
+      const int ny = Y + 1 - ky;          // even by construction; may be -2 at the top border
+      const int iy = ny >> 1;
+      if (ny < 0 || iy >= Hi) continue;
+#pragma unroll
+      for (int c2 = 0; c2 < 2; ++c2) {
+        const int kx = kx0 + 2 * c2;
+        const int nx = X + 1 - kx;
+        const int ix = nx >> 1;
+        if (nx < 0 || ix >= Wi) continue;
+        const long long m = ((long long)b * Hi + iy) * Wi + ix;
+        const uint4 v = *reinterpret_cast<const uint4*>(taps + m * row + (long long)(ky * 4 + kx) * C + cg * 8);
+        float fv[8];
+        bf16x8_to_f32(v, fv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += fv[e];
+      }
+    }
+    if (add != nullptr) {
+      float av[8];
+      bf16x8_to_f32(*reinterpret_cast<const uint4*>(add + pix * ldadd + cg * 8), av);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += av[e];
+    }
+    if (act == DISC_ACT_LRELU) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = acc[e] > 0.f ? acc[e] : acc[e] * slope;
+    } else if (act == DISC_ACT_MASK) {
+      float fw[8];
+      bf16x8_to_f32(*reinterpret_cast<const uint4*>(f + pix * ldf + cg * 8), fw);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = fw[e] > 0.f ? acc[e] : acc[e] * slope;
+    }
+    *reinterpret_cast<uint4*>(y + pix * ldy + cg * 8) = f32_to_bf16x8(acc);
+  }
+}
+
+// y[:, :C] = leaky_relu(y[:, :C], slope) in place (after the 1 -> nf convolution, discriminator_swin.py:49-50)
+static __global__ void __launch_bounds__(256) view_lrelu_kernel(__nv_bfloat16* __restrict__ y, int ldy, int C, long long npix, float slope) {
+  const int groups = C >> 3;
+  const long long total = npix * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / groups;
+    const int c = int(i - p * groups) * 8;
+    uint4* yp = reinterpret_cast<uint4*>(y + p * ldy + c);
+    float v[8];
+    bf16x8_to_f32(*yp, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = v[e] > 0.f ? v[e] : v[e] * slope;
+    *yp = f32_to_bf16x8(v);
+  }
+}
+
+}  // namespace srk

@@ -38,6 +38,8 @@ enum GemmEpilogue : int {
   EPI_MULG = 6,    // two GEMMs of the same shape per tile: acc0 = A B^T, acc1 = A2 B2^T (A2 -> tmX1, B2 -> tmX2);
                    // C = bf16(bf16(acc0) * bf16(gelu'(acc1)))   (fc2 dgrad -> dU with u = xn2 W1^T recomputed on the
                    // tensor cores instead of reading a stored gelu'(u): the block is HBM-bound, the MMA pipe is idle)
+  EPI_LRELU = 7,   // C = bf16(leaky_relu(acc, slope))    (4x4 stride-2 convolutions of UNetDiscriminatorSN as GEMMs over
+                   // gathered patches: models/discriminator_swin.py:10-11; slope = GemmArgs::slope)
 };
 
 struct GemmArgs {
@@ -53,13 +55,15 @@ struct GemmArgs {
   int rows_per_scale;
   const __nv_bfloat16* x2;  // EPI_LNBWD: the residual-gradient tensor X2 [M, ldx2] (read straight from global memory)
   int ldx2;
+  float slope;        // EPI_LRELU: negative slope
   int b_resident;     // K <= 192: every CTA keeps ONE N tile of B ([BN x K], loaded once) in shared memory and walks M tiles
                       // only; the operand ring then holds A boxes alone (twice to six times as many bytes of A in flight)
 };
 
 template <int BN, int EPI>
 struct GemmCfg {
-  static constexpr bool kBoxEpi = (EPI == EPI_STORE || EPI == EPI_GELU2 || EPI == EPI_MUL || EPI == EPI_GELU1 || EPI == EPI_MULG);
+  static constexpr bool kBoxEpi = (EPI == EPI_STORE || EPI == EPI_GELU2 || EPI == EPI_MUL || EPI == EPI_GELU1 || EPI == EPI_MULG ||
+                                    EPI == EPI_LRELU);
   static constexpr int kAccs = (EPI == EPI_MULG) ? 2 : 1;  // accumulators per tile (each double-buffered in TMEM)
   static constexpr int kEpiWarps = (kBoxEpi || EPI == EPI_LNBWD) ? 16 : 8;
   static constexpr int kEpiThreads = 32 * kEpiWarps;
@@ -443,6 +447,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[i * 8 + e]);
             if constexpr (EPI == EPI_STORE) {
+              sts128(out0 + off, make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
+                                            pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7])));
+            } else if constexpr (EPI == EPI_LRELU) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = v[e] > 0.f ? v[e] : v[e] * args.slope;
               sts128(out0 + off, make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
                                             pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7])));
             } else if constexpr (EPI == EPI_MUL) {

@@ -1,15 +1,19 @@
-"""GAN side of `train_swin.py` (BASELINE configs[3]): interface mirrors of the discriminator and the loss modules the
-script builds, plus its micro-step, so that the SwinIR generator mirror can be exercised and timed in the exact training
-arrangement — DDP(find_unused_parameters=True) generator, DDP discriminator, fp16 autocast + GradScaler, requires_grad
-toggling, RaGAN losses, gradient accumulation, EMA.
+"""GAN side of `train_swin.py` (BASELINE configs[3]): the discriminator and the loss modules the script builds, plus its
+micro-step, so that the SwinIR generator mirror can be exercised and timed in the exact training arrangement —
+DDP(find_unused_parameters=True) generator, DDP discriminator, fp16 autocast + GradScaler, requires_grad toggling, RaGAN
+losses, gradient accumulation, EMA.
 
-Scope note: this module is the *harness* around the hot path.  `UNetDiscriminatorSN` keeps the
-reference's module tree (`models/discriminator_swin.py:43-84`: same attribute names, registration order and spectral-norm
-parametrisation, so `state_dict()` round-trips with strict=True and a reference checkpoint's `net_d` loads), but its
-arithmetic is stock ATen (cuDNN convolutions in channels_last) — no libsrk kernel exists for the 4x4 stride-2 / transposed
-convolutions yet; the generator inside the same step is the libsrk path.  The VGG feature extractor of the perceptual loss
-(`utils/losses_train_swin.py:6-43`) cannot download its ImageNet weights here: it is seeded random, which leaves the
-arithmetic (and the cost) of the loss unchanged.
+`UNetDiscriminatorSN` keeps the reference's module tree (`models/discriminator_swin.py:43-84`: same
+attribute names, registration order and spectral-norm hooks, so `state_dict()` round-trips with strict=True and a reference
+checkpoint's `net_d` loads); its forward and backward run on libsrk (`disc_engine.py`: the 4x4 stride-2 convolutions and
+transposed convolutions as tcgen05 GEMMs over a patch matrix / followed by a fold, the 3x3 layers on the generators'
+kernels).  Spectral normalisation itself is the reference's own hook (power iteration on the weight matrix): parameter
+preparation, executed by torch exactly as in the reference.  There is no CPU path: the ATen restatement lives in
+`oracle/discriminator_oracle.py` and is test infrastructure only.
+
+The loss modules are interface mirrors (losses are out of scope).  The VGG feature extractor of the
+perceptual loss (`utils/losses_train_swin.py:6-43`) cannot download its ImageNet weights here: it is seeded random, which
+leaves the arithmetic (and the cost) of the loss unchanged.
 """
 from __future__ import annotations
 
@@ -17,6 +21,15 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 from torch.nn.utils import spectral_norm
+
+
+def _sn_weight(m):
+    """W / sigma(W) of a spectral_norm-wrapped layer, computed by the reference's own forward pre-hook
+    (torch.nn.utils.spectral_norm: one power iteration in training mode, none in eval mode; u is updated in place) —
+    the hook normally fires inside `m.forward`, which the libsrk path never calls."""
+    for hook in m._forward_pre_hooks.values():
+        hook(m, None)
+    return m.weight
 
 
 class UNetConv2(nn.Module):
@@ -30,7 +43,7 @@ class UNetConv2(nn.Module):
         self.model = nn.Sequential(*layers)
 
     def forward(self, x):
-        return self.model(x)
+        raise RuntimeError("UNetConv2 is executed by UNetDiscriminatorSN.forward (disc_engine); it has no stand-alone path")
 
 
 class UNetUpBlock(nn.Module):
@@ -45,14 +58,12 @@ class UNetUpBlock(nn.Module):
         self.model = nn.Sequential(*layers)
 
     def forward(self, x, skip_input):
-        x = self.model(x)
-        if x.shape[-2:] != skip_input.shape[-2:]:
-            x = F.interpolate(x, size=skip_input.shape[-2:], mode="bilinear", align_corners=True)
-        return torch.cat((x, skip_input), 1)
+        raise RuntimeError("UNetUpBlock is executed by UNetDiscriminatorSN.forward (disc_engine); it has no stand-alone path")
 
 
 class UNetDiscriminatorSN(nn.Module):
-    """U-Net discriminator with spectral normalisation (discriminator_swin.py:43-84): per-pixel real/fake logits."""
+    """U-Net discriminator with spectral normalisation (discriminator_swin.py:43-84): per-pixel real/fake logits at half
+    the input resolution.  Forward / backward = one libsrk autograd node (disc_engine.UNetDiscriminatorFunction)."""
 
     def __init__(self, num_in_ch=1, num_feat=64, skip_connection=True):
         super().__init__()
@@ -71,17 +82,15 @@ class UNetDiscriminatorSN(nn.Module):
         self.final_conv = nn.Sequential(spectral_norm(nn.Conv2d(nf * 2, nf, 3, 1, 1, bias=False)), nn.LeakyReLU(0.2, inplace=True),
                                         spectral_norm(nn.Conv2d(nf, 1, 3, 1, 1, bias=False)))
 
+    def _convs(self):
+        """the 12 spectrally normalised layers in forward order (discriminator_swin.py:72-84)"""
+        return [self.conv0[0], self.conv0[2], self.conv1.model[0], self.conv2.model[0], self.conv3.model[0],
+                self.conv4.model[0], self.up1.model[0], self.up2.model[0], self.up3.model[0], self.up4.model[0],
+                self.final_conv[0], self.final_conv[2]]
+
     def forward(self, x):
-        x0 = self.conv0(x)
-        x1 = self.conv1(x0)
-        x2 = self.conv2(x1)
-        x3 = self.conv3(x2)
-        x4 = self.conv4(x3)
-        d = self.up1(x4, x3)
-        d = self.up2(d, x2)
-        d = self.up3(d, x1)
-        d = self.up4(d, x0)
-        return self.final_conv(d)
+        from . import disc_engine
+        return disc_engine.unet_discriminator(x, [_sn_weight(m) for m in self._convs()])
 
 
 class RelativeGANLoss(nn.Module):

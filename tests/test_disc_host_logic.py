@@ -1,0 +1,187 @@
+"""CPU test of the discriminator's HOST logic (superresolution_def_b200/disc_engine.py): buffer layout per U-Net level,
+channel-slice views standing in for torch.cat, weight operand layouts, orientation / un-permutation of the weight-gradient
+GEMMs, which gradient feeds which fold.  Every libsrk entry point the engine calls is replaced by a torch restatement of its
+documented contract (include/srk.h) in fp32 — so the autograd node must reproduce the oracle's logits and all 13 gradients
+to fp32 round-off; any indexing mistake shows up as an O(1) error.  The kernels themselves are checked on the GPU
+(tests/test_disc_gpu.py): this file never touches CUDA."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.util import rel_l2
+
+
+class _View:
+    def __init__(self, t, c0, C):
+        self.t, self.c0, self.C = t, c0, C
+
+    def get(self, n):
+        return self.t[:n, self.c0:self.c0 + self.C]
+
+    def put(self, n, v):
+        self.t[:n, self.c0:self.c0 + self.C] = v
+
+
+def _nchw(v, B, H, W):
+    return v.get(B * H * W).reshape(B, H, W, v.C).permute(0, 3, 1, 2)
+
+
+def _rows(img):   # [B,C,H,W] -> [B*H*W, C]
+    return img.permute(0, 2, 3, 1).reshape(-1, img.shape[1])
+
+
+@pytest.fixture
+def engine(monkeypatch):
+    from superresolution_def_b200 import disc_engine as de
+    capi = de.capi
+    monkeypatch.setattr(de, "BF16", torch.float32)
+    weights = {}
+
+    def patches(x, f, slope, B, H, W, p):
+        src = _nchw(x, B, H, W)
+        if f is not None:
+            src = torch.where(_nchw(f, B, H, W) > 0, src, src * slope)
+        M = B * (H // 2) * (W // 2)
+        p[:M] = F.unfold(src, 4, stride=2, padding=1).reshape(B, x.C, 16, -1).permute(0, 3, 2, 1).reshape(M, 16 * x.C)
+
+    def fold(taps, B, Hi, Wi, y, add=None, f=None, act=0, slope=0.2):
+        C = y.C
+        cols = taps[:B * Hi * Wi].reshape(B, Hi * Wi, 16, C).permute(0, 3, 2, 1).reshape(B, C * 16, Hi * Wi)
+        w = F.fold(cols, (2 * Hi, 2 * Wi), 4, stride=2, padding=1)
+        if add is not None:
+            w = w + _nchw(add, B, 2 * Hi, 2 * Wi)
+        if act == capi.FOLD_LRELU:
+            w = torch.where(w > 0, w, w * slope)
+        elif act == capi.FOLD_MASK:
+            w = torch.where(_nchw(f, B, 2 * Hi, 2 * Wi) > 0, w, w * slope)
+        y.put(B * 4 * Hi * Wi, _rows(w))
+
+    def gemm_tn(epi, A, B, C, **kw):
+        assert epi == capi.EPI_STORE and A.shape[0] % 128 == 0 and A.shape[1] % 64 == 0 and B.shape[0] % 64 == 0
+        C.copy_(A @ B.t())
+
+    def gemm_tn_lrelu(A, B, C, slope):
+        assert A.shape[0] % 128 == 0 and A.shape[1] % 64 == 0 and B.shape[0] % 64 == 0
+        C.copy_(F.leaky_relu(A @ B.t(), slope))
+
+    def view_lrelu(y, n, slope):
+        y.put(n, F.leaky_relu(y.get(n), slope))
+
+    def view_lrelu_mask(g, f, n, slope, colsum=None):
+        assert g.C <= 256
+        g.put(n, torch.where(f.get(n) > 0, g.get(n), g.get(n) * slope))
+
+    def conv_in1_fwd(x, w, b, y, B, H, W, C, Cp):
+        y[:B * H * W] = _rows(F.conv2d(x.reshape(B, 1, H, W), w, b, 1, 1))
+
+    @torch.enable_grad()
+    def conv_in1_wgrad(x, dy, dw, db, B, H, W, C, Cp):
+        w = torch.zeros(C, 1, 3, 3, requires_grad=True)
+        F.conv2d(x.reshape(B, 1, H, W), w, None, 1, 1).backward(dy[:B * H * W].reshape(B, H, W, C).permute(0, 3, 1, 2))
+        dw.copy_(w.grad)
+
+    def conv_out1_fwd(x, w, b, y, B, H, W, C):
+        y.copy_(F.conv2d(x[:B * H * W].reshape(B, H, W, C).permute(0, 3, 1, 2), w, b, 1, 1))
+
+    @torch.enable_grad()
+    def conv_out1_bwd(dy, x, w, dx, dw, db, B, H, W, C):
+        xi = x[:B * H * W].reshape(B, H, W, C).permute(0, 3, 1, 2).clone().requires_grad_(True)
+        ww = w.clone().requires_grad_(True)
+        F.conv2d(xi, ww, None, 1, 1).backward(dy)
+        dx[:B * H * W] = _rows(xi.grad)
+        dw.copy_(ww.grad)
+
+    def prep(w, b, Cout_p, Cin_p, ps, wf, wt, bp):
+        assert b is None and not ps and tuple(w.shape) == (Cout_p, Cin_p, 3, 3)
+        weights[wf.data_ptr()] = ("fwd", w.clone())
+        weights[wt.data_ptr()] = ("dgrad", w.clone())
+        bp.zero_()
+
+    def igemm(epi, B, H, W, Cin_p, Cout_p, n_real, x, wk, bias, y, x_ps=False, y_ps=False, y2=None, r=None, slope=0.01):
+        kind, w = weights[wk.data_ptr()]
+        xi = x[:B * H * W].reshape(B, H, W, Cin_p).permute(0, 3, 1, 2)
+        if epi == capi.CEPI_BIAS_LRELU:
+            assert kind == "fwd"
+            o = F.leaky_relu(F.conv2d(xi, w, None, 1, 1), slope)
+        else:
+            assert epi == capi.CEPI_BIAS and kind == "dgrad" and bias is None
+            o = F.conv_transpose2d(xi, w, None, 1, 1)
+        y[:B * H * W] = _rows(o)
+
+    @torch.enable_grad()
+    def conv3x3_wgrad(B, H, W, Cin, Cout, Cin_p, Cout_p, ps, dy, x, dw):
+        w = torch.zeros(Cout, Cin, 3, 3, requires_grad=True)
+        F.conv2d(x[:B * H * W].reshape(B, H, W, Cin).permute(0, 3, 1, 2), w, None, 1, 1).backward(
+            dy[:B * H * W].reshape(B, H, W, Cout).permute(0, 3, 1, 2))
+        dw.copy_(w.grad)
+
+    def gemm_wgrad(A, B, ws, splits, out):
+        assert A.shape[0] % 64 == 0 and B.shape[1] in (64, 128, 192, 256)
+        out[:A.shape[1]] = A.t() @ B
+
+    for name, fn in dict(view=lambda t, c0=0, C=None: _View(t, c0, t.shape[1] - c0 if C is None else C),
+                         disc_patches_k4s2=patches, disc_fold_k4s2=fold, gemm_tn=gemm_tn, gemm_tn_lrelu=gemm_tn_lrelu,
+                         view_lrelu=view_lrelu, view_lrelu_mask=view_lrelu_mask, conv_in1_fwd=conv_in1_fwd,
+                         conv_in1_wgrad=conv_in1_wgrad, conv_out1_fwd=conv_out1_fwd, conv_out1_bwd=conv_out1_bwd,
+                         conv3x3_prep_weights=prep, conv3x3_igemm=igemm, conv3x3_wgrad=conv3x3_wgrad, gemm_wgrad=gemm_wgrad,
+                         wgrad_splits=lambda T, Ca: 1, wgrad_workspace_elems=lambda a, b, c: 1,
+                         _ws=lambda n, d: torch.empty(1)).items():
+        monkeypatch.setattr(capi, name, fn)
+    return de
+
+
+def _weights():
+    nf = 64
+    shapes = [(nf, 1, 3, 3), (nf, nf, 4, 4), (2 * nf, nf, 4, 4), (4 * nf, 2 * nf, 4, 4), (8 * nf, 4 * nf, 4, 4), (8 * nf, 8 * nf, 4, 4),
+              (8 * nf, 8 * nf, 4, 4), (16 * nf, 4 * nf, 4, 4), (8 * nf, 2 * nf, 4, 4), (4 * nf, nf, 4, 4), (nf, 2 * nf, 3, 3), (1, nf, 3, 3)]
+    g = torch.Generator().manual_seed(0)
+    ws = []
+    for i, s in enumerate(shapes):
+        transposed = 6 <= i <= 9
+        fan_in = (s[0] if transposed else s[1]) * s[2] * s[3] / (4 if transposed else 1)
+        ws.append(torch.randn(s, generator=g) * 1.6 * fan_in ** -0.5)
+    return ws
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 64, 96), (3, 32, 32)])
+def test_engine_host_logic_reproduces_the_oracle_in_fp32(engine, B, H, W):
+    from oracle.discriminator_oracle import unet_discriminator_forward
+    ws = _weights()
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(B, 1, H, W, generator=g)
+    dout = torch.randn(B, 1, H // 2, W // 2, generator=g)
+
+    def run(fn):
+        xs = x.clone().requires_grad_(True)
+        wl = [w.clone().requires_grad_(True) for w in ws]
+        out = fn(xs, wl)
+        out.backward(dout)
+        return out.detach(), [xs.grad] + [w.grad for w in wl]
+
+    o_ref, g_ref = run(unet_discriminator_forward)
+    o_my, g_my = run(lambda xs, wl: engine.UNetDiscriminatorFunction.apply(xs, *wl))
+    assert rel_l2(o_my, o_ref) < 1e-5
+    for i, (a, b) in enumerate(zip(g_my, g_ref)):
+        assert a.shape == b.shape and rel_l2(a, b) < 1e-4, (i, rel_l2(a, b))
+
+
+def test_engine_returns_only_the_requested_gradients(engine):
+    ws = _weights()
+    x = torch.rand(1, 1, 32, 32)
+    xs = x.clone().requires_grad_(True)
+    out = engine.UNetDiscriminatorFunction.apply(xs, *ws)          # G step: frozen parameters
+    out.mean().backward()
+    assert xs.grad is not None and xs.grad.abs().max() > 0
+    wl = [w.clone().requires_grad_(True) for w in ws]
+    engine.UNetDiscriminatorFunction.apply(x, *wl).mean().backward()   # D step: detached image
+    assert all(w.grad is not None and w.grad.shape == w.shape for w in wl)
+    assert not engine.UNetDiscriminatorFunction.apply(x, *ws).requires_grad
+    with pytest.raises(Exception):
+        engine.UNetDiscriminatorFunction.apply(torch.rand(1, 1, 48, 64), *ws)
+
+
+def test_public_entry_refuses_cpu_tensors():
+    from superresolution_def_b200 import disc_engine as de
+    from superresolution_def_b200._capi import SrkError
+    with pytest.raises(SrkError):
+        de.unet_discriminator(torch.rand(1, 1, 32, 32), _weights())

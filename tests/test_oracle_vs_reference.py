@@ -153,27 +153,44 @@ def test_hybrid_module_schema_and_oracle_match_reference():
     assert rel_l2(got, want) < 2e-5, rel_l2(got, want)
 
 
-def test_discriminator_mirror_equals_the_reference_module():
-    """superresolution_def_b200.gan.UNetDiscriminatorSN vs models/discriminator_swin.py:43-84 imported unmodified: same
-    state_dict keys / shapes / order (spectral-norm weight_orig, weight_u, weight_v included), strict load both ways, and
-    identical logits on CPU in eval mode (no power iteration) and in train mode (one power iteration on both sides)."""
+def test_discriminator_oracle_equals_the_reference_module():
+    """oracle.discriminator_oracle.UNetDiscriminatorSN vs models/discriminator_swin.py:43-84 imported unmodified, and the
+    product mirror's schema: same state_dict keys / shapes / order (spectral-norm weight_orig, weight_u, weight_v
+    included), strict load in every direction, identical logits and gradients on CPU in eval mode (no power iteration)
+    and in train mode (one power iteration on both sides); the functional oracle (what the libsrk path is compared with on
+    the GPU) equals the module form on the hook-normalised weights."""
     _ref_mod()
     from models.discriminator_swin import UNetDiscriminatorSN as RefD
+    from oracle.discriminator_oracle import UNetDiscriminatorSN as OraD, unet_discriminator_forward
     from superresolution_def_b200.gan import UNetDiscriminatorSN
     torch.manual_seed(0)
     ref = RefD(num_in_ch=1, num_feat=16)
+    ora = OraD(num_in_ch=1, num_feat=16)
     mine = UNetDiscriminatorSN(num_in_ch=1, num_feat=16)
     sd = ref.state_dict()
-    assert [(k, tuple(v.shape)) for k, v in sd.items()] == [(k, tuple(v.shape)) for k, v in mine.state_dict().items()]
-    mine.load_state_dict(sd, strict=True)
-    ref.load_state_dict(mine.state_dict(), strict=True)
+    for m in (ora, mine):
+        assert [(k, tuple(v.shape)) for k, v in sd.items()] == [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+        assert [n for n, _ in ref.named_parameters()] == [n for n, _ in m.named_parameters()]
+        m.load_state_dict(sd, strict=True)
+        ref.load_state_dict(m.state_dict(), strict=True)
     x = torch.rand(2, 1, 64, 64)
-    ref.eval(); mine.eval()
+    ref.eval(); ora.eval(); mine.eval()
     with torch.no_grad():
-        assert torch.equal(mine(x), ref(x))
-    ref.train(); mine.train()
-    a, b = mine(x), ref(x)
+        want = ref(x)
+        assert torch.equal(ora(x), want)
+        # the product mirror hands exactly these weights to libsrk (its own forward needs the GPU)
+        from superresolution_def_b200.gan import _sn_weight
+        assert torch.equal(unet_discriminator_forward(x, [_sn_weight(m) for m in mine._convs()]), want)
+    ref.train(); ora.train()
+    a, b = ora(x), ref(x)
     assert torch.equal(a, b)
     a.mean().backward(); b.mean().backward()
-    for (n, p), (_, q) in zip(mine.named_parameters(), ref.named_parameters()):
+    for (n, p), (_, q) in zip(ora.named_parameters(), ref.named_parameters()):
         assert torch.equal(p.grad, q.grad), n
+    # train mode: the mirror's hook call performs the same single power iteration as the reference's forward did
+    mine.train()
+    w_mine = [_sn_weight(m) for m in mine._convs()]
+    for k in sd:
+        if k.endswith("weight_u"):
+            assert torch.equal(mine.state_dict()[k], ref.state_dict()[k]), k
+    assert torch.equal(unet_discriminator_forward(x, w_mine), b)

@@ -333,6 +333,17 @@ int srk_disc_patches_k4s2(const SrkView* x, const SrkView* f, float slope, int B
  * nn.Conv2d(.., 4, 2, 1) (:10), with the skip-connection gradient of torch.cat (:40) as `add`. */
 int srk_disc_fold_k4s2(const void* taps, int B, int Hi, int Wi, const SrkView* add, const SrkView* f, int act, float slope,
                        const SrkView* y, void* stream);
+/* Operand forms of a 4x4 weight W [P][Q][4][4] fp32: a [P, 16*Q] bf16 with column (ky*4+kx)*Q + q, and at = a^T [16*Q, P]
+ * (may be NULL).  nn.Conv2d: P = Cout, Q = Cin (a = Wf, at = Wt); nn.ConvTranspose2d: P = Cin, Q = Cout (a = Wd, at = Wu).
+ * P, Q multiples of 32. */
+int srk_disc_prep_w4(const float* w, int P, int Q, void* a, void* at, void* stream);
+/* Weight gradient of a 4x4 layer in the parameter's own layout: dw [Cb][R][4][4] fp32, dw[c][r][ky][kx] =
+ * sum_t A[t][(ky*4+kx)*R + r] * B[t][c]  (A [T, 16*R], B [T, Cb] bf16, T % 64 == 0; Cb 64 / 128 / 192 / 256 or a multiple of
+ * 256).  nn.Conv2d: A = patches(x), B = dy_pre, R = Cin; nn.ConvTranspose2d: A = patches(dy_pre), B = x, R = Cout.
+ * srk_gemm_wgrad per 256 columns of B, the token splits folded by the un-permuting kernel (no reduce launch, no copy).
+ * ws: srk_disc_wgrad4_ws_floats floats. */
+int srk_disc_wgrad4(int T, int R, int Cb, const void* A, int lda, const void* B, int ldb, float* ws, float* dw, void* stream);
+long long srk_disc_wgrad4_ws_floats(int T, int R, int Cb);
 /* y = leaky_relu(y, slope) in place on a view (nn.LeakyReLU(0.2, inplace=True) after the 1 -> nf convolution, :49-50) */
 int srk_view_lrelu(const SrkView* y, long long npix, float slope, void* stream);
 

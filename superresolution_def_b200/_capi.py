@@ -614,3 +614,27 @@ def disc_fold_k4s2(taps, B, Hi, Wi, y: SrkView, add: SrkView | None = None, f: S
 
 def view_lrelu(y: SrkView, npix, slope):
     _check(_view_lrelu(_vref(y), npix, slope, _stream()), "srk_view_lrelu")
+
+
+_disc_prep_w4 = _sig("srk_disc_prep_w4", [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p])
+_disc_wgrad4 = _sig("srk_disc_wgrad4", [c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p])
+lib.srk_disc_wgrad4_ws_floats.restype = c_longlong
+lib.srk_disc_wgrad4_ws_floats.argtypes = [c_int, c_int, c_int]
+
+
+def disc_prep_w4(w, a, at=None):
+    """w [P,Q,4,4] fp32 -> a [P,16Q] bf16 (column (ky*4+kx)*Q + q) and at = a^T."""
+    P, Q = w.shape[0], w.shape[1]
+    assert w.dtype == torch.float32 and w.is_contiguous() and tuple(w.shape[2:]) == (4, 4)
+    assert a.dtype == torch.bfloat16 and a.is_contiguous() and a.numel() == 16 * P * Q
+    assert at is None or (at.dtype == torch.bfloat16 and at.is_contiguous() and at.numel() == 16 * P * Q)
+    _check(_disc_prep_w4(_ptr(w), P, Q, _ptr(a), _ptr(at), _stream()), "srk_disc_prep_w4")
+
+
+def disc_wgrad4(A, B, R, dw):
+    """dw [Cb,R,4,4] fp32 = un-permuted A[T,16R]^T @ B[T,Cb]."""
+    T, Cb = B.shape
+    assert tuple(A.shape) == (T, 16 * R) and A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
+    assert dw.dtype == torch.float32 and dw.is_contiguous() and dw.numel() == 16 * R * Cb
+    ws = _ws(int(lib.srk_disc_wgrad4_ws_floats(T, R, Cb)), A.device)
+    _check(_disc_wgrad4(T, R, Cb, _ptr(A), _ld(A), _ptr(B), _ld(B), _ptr(ws), _ptr(dw), _stream()), "srk_disc_wgrad4")

@@ -279,8 +279,13 @@ extern "C" long long srk_small_ws_floats(void) { return (long long)num_sms() * 2
 extern "C" int srk_conv_in1_fwd(const float* x, const float* w, const float* bias, void* y, int B, int H, int W, int C,
                                 int Cp, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  conv_in1_fwd_kernel<<<num_sms() * 8, 256, Cp * 10 * sizeof(float), stream>>>(x, w, bias, static_cast<__nv_bfloat16*>(y),
-                                                                               B, H, W, C, Cp);
+  const bool small = (long long)B * H * W * (Cp / 8) + (long long)num_sms() * 8 * 256 < (1LL << 32);
+  if (small)
+    conv_in1_fwd_kernel<unsigned><<<num_sms() * 8, 256, Cp * 10 * sizeof(float), stream>>>(x, w, bias, static_cast<__nv_bfloat16*>(y),
+                                                                                       B, H, W, C, Cp);
+  else
+    conv_in1_fwd_kernel<unsigned long long><<<num_sms() * 8, 256, Cp * 10 * sizeof(float), stream>>>(
+        x, w, bias, static_cast<__nv_bfloat16*>(y), B, H, W, C, Cp);
   SRK_LAUNCHED(1);
   SRK_CUDA_OK(cudaGetLastError());
   return SRK_OK;
@@ -294,8 +299,12 @@ extern "C" int srk_conv_in1_wgrad(const float* x, const void* dy, float* ws, flo
   const bool wide = Cp <= 64 && (long long)B * H * W >= (1 << 18);
   const int grid = wide ? num_sms() * 4 : num_sms();
   const int threads = (Cp / 8) * (wide ? 32 : 8);
-  conv_in1_wgrad_kernel<<<grid, threads, Cp * 10 * sizeof(float), stream>>>(x, static_cast<const __nv_bfloat16*>(dy), ws,
-                                                                            B, H, W, Cp);
+  if ((long long)B * H * W + (long long)grid * threads < (1LL << 32))
+    conv_in1_wgrad_kernel<unsigned><<<grid, threads, Cp * 10 * sizeof(float), stream>>>(x, static_cast<const __nv_bfloat16*>(dy), ws,
+                                                                                    B, H, W, Cp);
+  else
+    conv_in1_wgrad_kernel<unsigned long long><<<grid, threads, Cp * 10 * sizeof(float), stream>>>(
+        x, static_cast<const __nv_bfloat16*>(dy), ws, B, H, W, Cp);
   SRK_LAUNCHED(1);
   conv_in1_wgrad_finish_kernel<<<(C * 10 + 127) / 128, 128, 0, stream>>>(ws, grid, C, Cp, dw, db);
   SRK_LAUNCHED(1);

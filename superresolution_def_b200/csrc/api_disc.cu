@@ -28,9 +28,15 @@ extern "C" int srk_disc_patches_k4s2(const SrkView* x, const SrkView* f, float s
   if (B <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1) || !patches || (reinterpret_cast<uintptr_t>(patches) & 15))
     return fail(SRK_ERR_ARG, "disc_patches: even H and W and a 16-byte aligned patch matrix required");
   const long long vectors = (long long)B * (H / 2) * (W / 2) * 16 * (x->C / 8);
-  disc_patches_k4s2_kernel<<<stream_grid(vectors), 256, 0, stream>>>(
-      static_cast<const __nv_bfloat16*>(x->ptr), x->pitch, f ? static_cast<const __nv_bfloat16*>(f->ptr) : nullptr,
-      f ? f->pitch : 0, slope, B, H, W, x->C, static_cast<__nv_bfloat16*>(patches));
+  const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x->ptr);
+  const __nv_bfloat16* fp = f ? static_cast<const __nv_bfloat16*>(f->ptr) : nullptr;
+  // + one grid stride of headroom so that the 32-bit loop counter cannot wrap
+  if (vectors + (long long)num_sms() * 16 * 256 < (1LL << 32))
+    disc_patches_k4s2_kernel<unsigned><<<stream_grid(vectors), 256, 0, stream>>>(xp, x->pitch, fp, f ? f->pitch : 0, slope, B, H, W,
+                                                                             x->C, static_cast<__nv_bfloat16*>(patches));
+  else
+    disc_patches_k4s2_kernel<unsigned long long><<<stream_grid(vectors), 256, 0, stream>>>(xp, x->pitch, fp, f ? f->pitch : 0, slope, B,
+                                                                                       H, W, x->C, static_cast<__nv_bfloat16*>(patches));
   SRK_LAUNCHED(1);
   SRK_CUDA_OK(cudaGetLastError());
   return SRK_OK;
@@ -49,10 +55,17 @@ extern "C" int srk_disc_fold_k4s2(const void* taps, int B, int Hi, int Wi, const
   }
   if (B <= 0 || Hi <= 0 || Wi <= 0 || !taps || (reinterpret_cast<uintptr_t>(taps) & 15)) return fail(SRK_ERR_ARG, "disc_fold: shape / pointer");
   const long long vectors = (long long)B * (2 * Hi) * (2 * Wi) * (y->C / 8);
-  disc_fold_k4s2_kernel<<<stream_grid(vectors), 256, 0, stream>>>(
-      static_cast<const __nv_bfloat16*>(taps), B, Hi, Wi, y->C, add ? static_cast<const __nv_bfloat16*>(add->ptr) : nullptr,
-      add ? add->pitch : 0, (act == DISC_ACT_MASK) ? static_cast<const __nv_bfloat16*>(f->ptr) : nullptr,
-      (act == DISC_ACT_MASK) ? f->pitch : 0, act, slope, static_cast<__nv_bfloat16*>(const_cast<void*>(y->ptr)), y->pitch);
+  const __nv_bfloat16* ap = add ? static_cast<const __nv_bfloat16*>(add->ptr) : nullptr;
+  const __nv_bfloat16* fp = (act == DISC_ACT_MASK) ? static_cast<const __nv_bfloat16*>(f->ptr) : nullptr;
+  const int ldf = (act == DISC_ACT_MASK) ? f->pitch : 0;
+  __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(const_cast<void*>(y->ptr));
+  if (vectors + (long long)num_sms() * 16 * 256 < (1LL << 32))
+    disc_fold_k4s2_kernel<unsigned><<<stream_grid(vectors), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(taps), B, Hi, Wi, y->C, ap,
+                                                                          add ? add->pitch : 0, fp, ldf, act, slope, yp, y->pitch);
+  else
+    disc_fold_k4s2_kernel<unsigned long long><<<stream_grid(vectors), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(taps), B, Hi, Wi,
+                                                                                    y->C, ap, add ? add->pitch : 0, fp, ldf, act, slope,
+                                                                                    yp, y->pitch);
   SRK_LAUNCHED(1);
   SRK_CUDA_OK(cudaGetLastError());
   return SRK_OK;
@@ -66,6 +79,48 @@ extern "C" int srk_view_lrelu(const SrkView* y, long long npix, float slope, voi
   view_lrelu_kernel<<<stream_grid(npix * (y->C / 8)), 256, 0, stream>>>(static_cast<__nv_bfloat16*>(const_cast<void*>(y->ptr)),
                                                                        y->pitch, y->C, npix, slope);
   SRK_LAUNCHED(1);
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+extern "C" int srk_disc_prep_w4(const float* w, int P, int Q, void* a, void* at, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!w || !a || P <= 0 || Q <= 0 || P % 32 || Q % 32 || (reinterpret_cast<uintptr_t>(w) & 15))
+    return fail(SRK_ERR_ARG, "disc_prep_w4: P and Q must be multiples of 32, w 16-byte aligned");
+  disc_prep_w4_kernel<<<stream_grid((long long)P * Q), 256, 0, stream>>>(w, P, Q, static_cast<__nv_bfloat16*>(a));
+  SRK_LAUNCHED(1);
+  if (at) {
+    const long long tiles = (long long)(P / 32) * (16 * Q / 32);
+    const long long cap = (long long)num_sms() * 8;
+    transpose_bf16_kernel<<<int(tiles < cap ? tiles : cap), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(a), P, 16 * Q,
+                                                                             static_cast<__nv_bfloat16*>(at));
+    SRK_LAUNCHED(1);
+  }
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+extern "C" long long srk_disc_wgrad4_ws_floats(int T, int R, int Cb) {
+  const int Ca = 16 * R;
+  const int cb = Cb < 256 ? Cb : 256;
+  return srk_gemm_wgrad_workspace_elems(Ca, cb, srk_gemm_wgrad_splits(T, Ca));
+}
+
+extern "C" int srk_disc_wgrad4(int T, int R, int Cb, const void* A, int lda, const void* B, int ldb, float* ws, float* dw,
+                               void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!A || !B || !ws || !dw || R <= 0 || R % 8 || Cb <= 0 || (Cb > 256 && Cb % 256) || (reinterpret_cast<uintptr_t>(dw) & 15))
+    return fail(SRK_ERR_ARG, "disc_wgrad4: Cb must be 64 / 128 / 192 / 256 or a multiple of 256");
+  const int Ca = 16 * R;
+  const int splits = srk_gemm_wgrad_splits(T, Ca);
+  const int ca_pad = ((Ca + 127) / 128) * 128;
+  for (int c0 = 0; c0 < Cb; c0 += 256) {
+    const int cb = (Cb - c0) < 256 ? (Cb - c0) : 256;
+    int rc = gemm_wgrad_partials(T, Ca, cb, A, lda, static_cast<const __nv_bfloat16*>(B) + c0, ldb, ws, splits, stream_);
+    if (rc) return rc;
+    disc_unpack_wgrad4_kernel<<<stream_grid((long long)R * cb), 256, 0, stream>>>(ws, splits, (long long)ca_pad * cb, R, cb, c0, dw);
+    SRK_LAUNCHED(1);
+  }
   SRK_CUDA_OK(cudaGetLastError());
   return SRK_OK;
 }

@@ -123,6 +123,9 @@ static __global__ void colsum_ps_kernel(const __nv_bfloat16* __restrict__ dys, i
 
 // ------------------------------------------------------------------ conv_first: Cin = 1 -> C, output token-major
 // y[p][co] = b[co] + sum_tap x[p + tap] * w[co][tap];  y: [B*H*W, Cp] bf16 (pads zero), x: [B,H,W] fp32
+// Idx: unsigned when B*H*W*Cp/8 fits 32 bits (the 64-bit divisions of the index decomposition otherwise cost more than
+// the arithmetic: 87 -> us at 512^2 x 2 x 64 channels, the discriminator's first layer)
+template <typename Idx>
 static __global__ void conv_in1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                     const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int B, int H, int W,
                                     int C, int Cp) {
@@ -132,12 +135,14 @@ static __global__ void conv_in1_fwd_kernel(const float* __restrict__ x, const fl
     s_w[i] = (co < C) ? (t < 9 ? w[co * 9 + t] : bias[co]) : 0.f;
   }
   __syncthreads();
-  const int groups = Cp / 8;
-  const long long total = (long long)B * H * W * groups;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+  const Idx groups = Idx(Cp / 8);
+  const Idx total = Idx(B) * H * W * groups;
+  for (Idx idx = Idx(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += Idx(gridDim.x) * blockDim.x) {
     const int g = int(idx % groups);
-    const long long p = idx / groups;
-    const int xx = int(p % W), yy = int((p / W) % H);
+    const Idx pi = idx / groups;
+    const Idx ri = pi / Idx(W);
+    const int xx = int(pi - ri * Idx(W)), yy = int(ri % Idx(H));
+    const long long p = (long long)pi;
     const long long base = p - (long long)yy * W - xx;  // start of image b
     float v[9];
 #pragma unroll
@@ -162,6 +167,7 @@ static __global__ void conv_in1_fwd_kernel(const float* __restrict__ x, const fl
 }
 
 // dW[co][tap] = sum_p dY[p][co] * x[p+tap], db[co] = sum_p dY[p][co]; partial[blockIdx][Cp][10]
+template <typename Idx>
 static __global__ void conv_in1_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                                       float* __restrict__ partial, int B, int H, int W, int Cp) {
   extern __shared__ float s_acc[];  // [Cp][10]
@@ -175,10 +181,12 @@ static __global__ void conv_in1_wgrad_kernel(const float* __restrict__ x, const 
   for (int e = 0; e < 8; ++e)
 #pragma unroll
     for (int t = 0; t < 10; ++t) acc[e][t] = 0.f;
-  const long long npix = (long long)B * H * W;
+  const Idx npix = Idx(B) * H * W;
   if (pl < pix_per_block) {
-    for (long long p = (long long)blockIdx.x * pix_per_block + pl; p < npix; p += (long long)gridDim.x * pix_per_block) {
-      const int xx = int(p % W), yy = int((p / W) % H);
+    for (Idx pi = Idx(blockIdx.x) * pix_per_block + pl; pi < npix; pi += Idx(gridDim.x) * pix_per_block) {
+      const Idx ri = pi / Idx(W);
+      const int xx = int(pi - ri * Idx(W)), yy = int(ri % Idx(H));
+      const long long p = (long long)pi;
       const long long base = p - (long long)yy * W - xx;
       float v[10];
 #pragma unroll

@@ -28,16 +28,19 @@ __device__ __forceinline__ uint4 f32_to_bf16x8(const float (&f)[8]) {
 // patches[m][(ky*4+kx)*C + c] = g[b][2*oy-1+ky][2*ox-1+kx][c]  (zero outside the image), m = (b*Ho + oy)*Wo + ox,
 // g = x, or x * (f > 0 ? 1 : slope) when f is given (LeakyReLU backward applied while gathering a gradient image).
 // One thread per 16-byte vector of the patch matrix: its linear index IS the destination offset.
+// (Idx = unsigned when the vector count fits 32 bits: the four divisions per vector are what bounds this kernel with
+// 64-bit indices — 140 us of integer work for a 268 MB patch matrix against 55 us of HBM time.)
+template <typename Idx>
 static __global__ void __launch_bounds__(256) disc_patches_k4s2_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
                                                                        const __nv_bfloat16* __restrict__ f, int ldf, float slope,
                                                                        int B, int H, int W, int C,
                                                                        __nv_bfloat16* __restrict__ patches) {
-  const int groups = C >> 3;
-  const int Ho = H >> 1, Wo = W >> 1;
-  const long long total = (long long)B * Ho * Wo * 16 * groups;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+  const Idx groups = Idx(C >> 3);
+  const Idx Ho = Idx(H >> 1), Wo = Idx(W >> 1);
+  const Idx total = Idx(B) * Ho * Wo * 16 * groups;
+  for (Idx idx = Idx(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += Idx(gridDim.x) * blockDim.x) {
     const int cg = int(idx % groups);
-    long long t = idx / groups;
+    Idx t = idx / groups;
     const int tap = int(t & 15);
     t >>= 4;
     const int ox = int(t % Wo);
@@ -59,7 +62,7 @@ static __global__ void __launch_bounds__(256) disc_patches_k4s2_kernel(const __n
         v = f32_to_bf16x8(xv);
       }
     }
-    *reinterpret_cast<uint4*>(patches + idx * 8) = v;
+    *reinterpret_cast<uint4*>(patches + (long long)idx * 8) = v;
   }
 }
 
@@ -67,20 +70,23 @@ static __global__ void __launch_bounds__(256) disc_patches_k4s2_kernel(const __n
 //   y[b][Y][X][c] = sum over (ky, kx) with (Y+1-ky), (X+1-kx) even and in range of taps[(b, (Y+1-ky)/2, (X+1-kx)/2)][(ky*4+kx)*C + c]
 //   then  + add (optional)  then  act: 0 none, 1 LeakyReLU(slope), 2 multiply by (f > 0 ? 1 : slope)  (LeakyReLU backward).
 enum { DISC_ACT_NONE = 0, DISC_ACT_LRELU = 1, DISC_ACT_MASK = 2 };
+template <typename Idx>
 static __global__ void __launch_bounds__(256) disc_fold_k4s2_kernel(const __nv_bfloat16* __restrict__ taps, int B, int Hi, int Wi, int C,
                                                                     const __nv_bfloat16* __restrict__ add, int ldadd,
                                                                     const __nv_bfloat16* __restrict__ f, int ldf, int act, float slope,
                                                                     __nv_bfloat16* __restrict__ y, int ldy) {
-  const int groups = C >> 3;
-  const int Ho = 2 * Hi, Wo = 2 * Wi;
-  const long long total = (long long)B * Ho * Wo * groups;
+  const Idx groups = Idx(C >> 3);
+  const Idx Ho = Idx(2 * Hi), Wo = Idx(2 * Wi);
+  const Idx total = Idx(B) * Ho * Wo * groups;
   const long long row = 16LL * C;   // elements per row of the tap matrix
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+  for (Idx idx = Idx(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += Idx(gridDim.x) * blockDim.x) {
     const int cg = int(idx % groups);
-    const long long pix = idx / groups;
-    const int X = int(pix % Wo);
-    const int Y = int((pix / Wo) % Ho);
-    const int b = int(pix / ((long long)Wo * Ho));
+    const Idx pixi = idx / groups;
+    const long long pix = (long long)pixi;
+    const int X = int(pixi % Wo);
+    const Idx rowi = pixi / Wo;
+    const int Y = int(rowi % Ho);
+    const int b = int(rowi / Ho);
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const int ky0 = (Y + 1) & 1, kx0 = (X + 1) & 1;
 #pragma unroll
@@ -135,6 +141,75 @@ static __global__ void __launch_bounds__(256) view_lrelu_kernel(__nv_bfloat16* _
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = v[e] > 0.f ? v[e] : v[e] * slope;
     *yp = f32_to_bf16x8(v);
+  }
+}
+
+}  // namespace srk
+
+namespace srk {
+
+// Operand form of a 4x4 weight: W [P][Q][4][4] fp32 -> A [P][16*Q] bf16 with column k = (ky*4+kx)*Q + q.
+// (Conv2d: P = Cout, Q = Cin, A = Wf; ConvTranspose2d: P = Cin, Q = Cout, A = Wd.)  One thread per (p, q): 64 contiguous
+// bytes in, sixteen 2-byte stores that are contiguous across the warp for each tap.
+static __global__ void __launch_bounds__(256) disc_prep_w4_kernel(const float* __restrict__ w, int P, int Q,
+                                                                  __nv_bfloat16* __restrict__ a) {
+  const long long total = (long long)P * Q;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int q = int(i % Q);
+    const long long p = i / Q;
+    const float4* src = reinterpret_cast<const float4*>(w + i * 16);
+    __nv_bfloat16* dst = a + p * 16 * Q + q;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 v = src[j];
+      dst[(long long)(4 * j + 0) * Q] = __float2bfloat16_rn(v.x);
+      dst[(long long)(4 * j + 1) * Q] = __float2bfloat16_rn(v.y);
+      dst[(long long)(4 * j + 2) * Q] = __float2bfloat16_rn(v.z);
+      dst[(long long)(4 * j + 3) * Q] = __float2bfloat16_rn(v.w);
+    }
+  }
+}
+
+// out [C][R] = in [R][C]^T (bf16), 32 x 32 tiles through padded shared memory; R, C multiples of 32.
+static __global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, int R, int C,
+                                                                    __nv_bfloat16* __restrict__ out) {
+  __shared__ __nv_bfloat16 tile[32][34];
+  const int tiles_c = C / 32;
+  const long long ntiles = (long long)(R / 32) * tiles_c;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int r0 = int(t / tiles_c) * 32, c0 = int(t % tiles_c) * 32;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) tile[ty + 8 * j][tx] = in[(long long)(r0 + ty + 8 * j) * C + c0 + tx];
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[(long long)(c0 + ty + 8 * j) * R + r0 + tx] = tile[tx][ty + 8 * j];
+    __syncthreads();
+  }
+}
+
+// Weight gradient of a 4x4 layer out of the split partials of the MN-major GEMM:
+//   dw[(c * R + rr) * 16 + tap] = sum_s part[s][tap * R + rr][c - c0]      c in [c0, c0 + cb)
+// (Conv2d: rows = patch columns (tap, ci), c = co -> dW[co][ci][ky][kx]; ConvTranspose2d: rows = (tap, co), c = ci ->
+//  dW[ci][co][ky][kx]: the same index map with R = Cin resp. Cout.)  A thread owns one (c, rr) pair: 16 taps = 64
+// contiguous output bytes; across the warp c is the fast index, so the partial reads are contiguous.
+static __global__ void __launch_bounds__(256) disc_unpack_wgrad4_kernel(const float* __restrict__ part, int splits, long long split_stride,
+                                                                        int R, int cb, int c0, float* __restrict__ dw) {
+  const long long total = (long long)R * cb;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = int(i % cb);
+    const int rr = int(i / cb);
+    float acc[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) acc[t] = 0.f;
+    for (int s = 0; s < splits; ++s) {
+      const float* ps = part + s * split_stride + (long long)rr * cb + c;
+#pragma unroll
+      for (int t = 0; t < 16; ++t) acc[t] += ps[(long long)t * R * cb];
+    }
+    float4* dst = reinterpret_cast<float4*>(dw + ((long long)(c0 + c) * R + rr) * 16);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
   }
 }
 

@@ -42,34 +42,22 @@ def _alloc(m: int, c: int, dev) -> torch.Tensor:
     return t
 
 
-def _down_ops(w):
-    """Conv2d weight [Cout, Cin, 4, 4] -> Wf [Cout, 16*Cin] (k = (ky*4+kx)*Cin + ci) and Wt = Wf^T."""
-    co, ci = w.shape[0], w.shape[1]
-    wf = w.detach().permute(0, 2, 3, 1).reshape(co, 16 * ci).to(BF16).contiguous()
-    return wf, wf.t().contiguous()
+def _ops4(w):
+    """4x4 weight [P,Q,4,4] -> (a [P,16Q], a^T [16Q,P]) bf16, column (ky*4+kx)*Q + q.
+    Conv2d [Cout,Cin,4,4]: a = Wf (forward operand), a^T = Wt (input-gradient operand);
+    ConvTranspose2d [Cin,Cout,4,4]: a = Wd (input-gradient operand), a^T = Wu (forward operand)."""
+    P, Q = w.shape[0], w.shape[1]
+    a = torch.empty(P, 16 * Q, device=w.device, dtype=BF16)
+    at = torch.empty(16 * Q, P, device=w.device, dtype=BF16)
+    capi.disc_prep_w4(w.detach().float().contiguous(), a, at)
+    return a, at
 
 
-def _up_ops(w):
-    """ConvTranspose2d weight [Cin, Cout, 4, 4] -> Wu [16*Cout, Cin] (n = (ky*4+kx)*Cout + co) and Wd = Wu^T."""
-    ci, co = w.shape[0], w.shape[1]
-    wd = w.detach().permute(0, 2, 3, 1).reshape(ci, 16 * co).to(BF16).contiguous()
-    return wd.t().contiguous(), wd
-
-
-def _wgrad(A, B2d):
-    """A[T,Ca]^T @ B[T,Cb] -> fp32 [Ca, Cb]; Cb is walked in <= 256-column pieces (srk_gemm_wgrad's tile)."""
-    T, Ca = A.shape
-    Cb = B2d.shape[1]
-    out = torch.empty(Ca, Cb, device=A.device, dtype=torch.float32)
-    ca_pad = (Ca + 127) // 128 * 128
-    for c0 in range(0, Cb, 256):
-        cb = min(256, Cb - c0)
-        splits = capi.wgrad_splits(T, Ca)
-        ws = capi._ws(capi.wgrad_workspace_elems(Ca, cb, splits), A.device)
-        piece = torch.empty(ca_pad, cb, device=A.device, dtype=torch.float32)
-        capi.gemm_wgrad(A, B2d[:, c0:c0 + cb], ws, splits, piece)
-        out[:, c0:c0 + cb] = piece[:Ca]
-    return out
+def _wgrad(A, B2d, R):
+    """dw [Cb,R,4,4] fp32, dw[c][r][ky][kx] = sum_t A[t][(ky*4+kx)*R + r] * B[t][c]: the parameter's own layout."""
+    dw = torch.empty(B2d.shape[1], R, 4, 4, device=A.device, dtype=torch.float32)
+    capi.disc_wgrad4(A, B2d, R, dw)
+    return dw
 
 
 class UNetDiscriminatorFunction(torch.autograd.Function):
@@ -103,14 +91,18 @@ class UNetDiscriminatorFunction(torch.autograd.Function):
         cat2 = _alloc(M[3], 512, dev)    # d2 (256) | x2 (256)
         cat1 = _alloc(M[4], 1024, dev)   # d1 (512) | x3 (512)
         x4 = _alloc(M[5], 512, dev)
-        ops_d = [_down_ops(w) for w in (w0b, w1, w2, w3, w4)]
-        ops_u = [_up_ops(w) for w in (u1, u2, u3, u4)]
+        ops_d = [_ops4(w) for w in (w0b, w1, w2, w3, w4)]              # (Wf, Wt)
+        ops_u = [_ops4(w)[::-1] for w in (u1, u2, u3, u4)]            # (Wu, Wd)
+        keep_patches = any(ctx.needs_input_grad[1:])   # the weight gradients read the forward's patch matrices again
+        saved_patches = []
 
         def down(src, c0, cin_, lvl, wf, dst, d0):
             """level lvl [B,Hs,Ws,cin_] (channels c0.. of src) -> level lvl+1, written into channels d0.. of dst"""
             p = _alloc(M[lvl + 1], 16 * cin_, dev)
             capi.disc_patches_k4s2(V(src, c0, cin_), None, SLOPE, B, Hs[lvl], Ws[lvl], p)
             capi.gemm_tn_lrelu(p, wf, dst[:, d0:d0 + wf.shape[0]], SLOPE)
+            if keep_patches:
+                saved_patches.append(p)
 
         down(a0, 0, 64, 0, ops_d[0][0], cat4, 64)       # x0
         down(cat4, 64, 64, 1, ops_d[1][0], cat3, 128)   # x1 (conv1 :55)
@@ -144,6 +136,7 @@ class UNetDiscriminatorFunction(torch.autograd.Function):
         if any(ctx.needs_input_grad):
             ctx.acts = (xf, a0, cat4, cat3, cat2, cat1, x4, f1a)
             ctx.ops = (ops_d, ops_u, wt_f1, w_last, w0a.detach().float().contiguous())
+            ctx.patches = saved_patches
             ctx.meta = (B, Hs, Ws, M, x.dtype)
             ctx.wshapes = [tuple(w.shape) for w in (w0a, w0b, w1, w2, w3, w4, u1, u2, u3, u4, wf1, wf2)]
         return out
@@ -154,6 +147,7 @@ class UNetDiscriminatorFunction(torch.autograd.Function):
             raise capi.SrkError("UNetDiscriminatorFunction: second backward through the same forward (activations were released)")
         xf, a0, cat4, cat3, cat2, cat1, x4, f1a = ctx.acts
         ops_d, ops_u, wt_f1, w_last, w0a = ctx.ops
+        patches = ctx.patches
         B, Hs, Ws, M, x_dtype = ctx.meta
         need = ctx.needs_input_grad
         need_x, need_w = need[0], any(need[1:])
@@ -186,7 +180,7 @@ class UNetDiscriminatorFunction(torch.autograd.Function):
             capi.gemm_tn(capi.EPI_STORE, g, wd, d_src)
             dw = None
             if need_w:   # dW[ci,co,ky,kx] = sum_m src[m,ci] g[m,(ky,kx,co)]
-                dw = _wgrad(g, src).view(4, 4, cout, cin_).permute(3, 2, 0, 1).contiguous()
+                dw = _wgrad(g, src, cout)
             return d_src, dw
 
         d_cat3, dw_u4 = up_bwd(d_cat4, cat4, 2, cat3, ops_u[3][1])
@@ -200,10 +194,8 @@ class UNetDiscriminatorFunction(torch.autograd.Function):
         def down_bwd(d_pre, lvl, src, c0, cin_, wt, add, a0_):
             dw = None
             if need_w:   # dW[co,ci,ky,kx] = sum_m d_pre[m,co] patches[m,(ky,kx,ci)]
-                p = _alloc(M[lvl + 1], 16 * cin_, dev)
-                capi.disc_patches_k4s2(V(src, c0, cin_), None, SLOPE, B, Hs[lvl], Ws[lvl], p)
-                dw = _wgrad(p, d_pre).view(4, 4, cin_, d_pre.shape[1]).permute(3, 2, 0, 1).contiguous()
-                del p
+                dw = _wgrad(patches[lvl], d_pre, cin_)   # the forward's patch matrix of this level (kept, not re-gathered)
+                patches[lvl] = None
             taps = torch.empty(d_pre.shape[0], 16 * cin_, device=dev, dtype=BF16)
             capi.gemm_tn(capi.EPI_STORE, d_pre, wt, taps)
             d_src = _alloc(M[lvl], cin_, dev)
@@ -229,7 +221,7 @@ class UNetDiscriminatorFunction(torch.autograd.Function):
             dx = torch.empty(B, 1, Hs[0], Ws[0], device=dev, dtype=f32)
             capi.conv_out1_fwd(d_a0, w_flip, torch.zeros(1, device=dev, dtype=f32), dx, B, Hs[0], Ws[0], 64)
             dx = dx.to(x_dtype)
-        ctx.acts = None
+        ctx.acts = ctx.patches = None
         grads = (dw0a, dw0b, dw1, dw2, dw3, dw4, dw_u1, dw_u2, dw_u3, dw_u4, dw_f1, dw_f2 if need_w else None)
         grads = tuple(g if n else None for g, n in zip(grads, need[1:]))
         return (dx,) + grads

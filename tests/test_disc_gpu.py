@@ -89,6 +89,28 @@ def test_gemm_lrelu_epilogue(M, N, K, ldc):
         assert torch.all(C[:, :ldc - N] == 0)
 
 
+@pytest.mark.parametrize("P,Q", [(64, 64), (512, 256), (1024, 256)])
+def test_weight_operand_forms_are_bit_exact(P, Q):
+    from superresolution_def_b200 import _capi as capi
+    w = _mk((P, Q, 4, 4), seed=8)
+    a = torch.empty(P, 16 * Q, device="cuda", dtype=BF)
+    at = torch.empty(16 * Q, P, device="cuda", dtype=BF)
+    capi.disc_prep_w4(w, a, at)
+    want = w.permute(0, 2, 3, 1).reshape(P, 16 * Q).to(BF)
+    assert torch.equal(a, want) and torch.equal(at, want.t())
+
+
+@pytest.mark.parametrize("T,R,Cb", [(256, 64, 64), (512, 128, 512), (192, 512, 1024), (2048, 64, 128)])
+def test_wgrad4_is_the_unpermuted_matmul(T, R, Cb):
+    from superresolution_def_b200 import _capi as capi
+    A = _mk((T, 16 * R), seed=9).to(BF)
+    Bm = _mk((T, 2 * Cb), seed=10).to(BF)[:, Cb:]          # a channel slice with a row pitch, as the level buffers are
+    dw = torch.empty(Cb, R, 4, 4, device="cuda")
+    capi.disc_wgrad4(A, Bm, R, dw)
+    want = (A.float().t() @ Bm.float()).view(4, 4, R, Cb).permute(3, 2, 0, 1)
+    assert rel_l2(dw, want) < 1e-5, rel_l2(dw, want)      # fp32 accumulation of exact bf16 products: summation order only
+
+
 def _weights(seed=0):
     nf = 64
     shapes = [(nf, 1, 3, 3), (nf, nf, 4, 4), (2 * nf, nf, 4, 4), (4 * nf, 2 * nf, 4, 4), (8 * nf, 4 * nf, 4, 4), (8 * nf, 8 * nf, 4, 4),

@@ -115,17 +115,24 @@ def engine(monkeypatch):
             dy[:B * H * W].reshape(B, H, W, Cout).permute(0, 3, 1, 2))
         dw.copy_(w.grad)
 
-    def gemm_wgrad(A, B, ws, splits, out):
-        assert A.shape[0] % 64 == 0 and B.shape[1] in (64, 128, 192, 256)
-        out[:A.shape[1]] = A.t() @ B
+    def disc_prep_w4(w, a, at=None):
+        P, Q = w.shape[0], w.shape[1]
+        assert P % 32 == 0 and Q % 32 == 0
+        a.copy_(w.permute(0, 2, 3, 1).reshape(P, 16 * Q))
+        if at is not None:
+            at.copy_(a.t())
+
+    def disc_wgrad4(A, B, R, dw):
+        T, Cb = B.shape
+        assert T % 64 == 0 and tuple(A.shape) == (T, 16 * R) and (Cb in (64, 128, 192, 256) or Cb % 256 == 0)
+        dw.copy_((A.t() @ B).view(4, 4, R, Cb).permute(3, 2, 0, 1))
 
     for name, fn in dict(view=lambda t, c0=0, C=None: _View(t, c0, t.shape[1] - c0 if C is None else C),
                          disc_patches_k4s2=patches, disc_fold_k4s2=fold, gemm_tn=gemm_tn, gemm_tn_lrelu=gemm_tn_lrelu,
                          view_lrelu=view_lrelu, view_lrelu_mask=view_lrelu_mask, conv_in1_fwd=conv_in1_fwd,
                          conv_in1_wgrad=conv_in1_wgrad, conv_out1_fwd=conv_out1_fwd, conv_out1_bwd=conv_out1_bwd,
-                         conv3x3_prep_weights=prep, conv3x3_igemm=igemm, conv3x3_wgrad=conv3x3_wgrad, gemm_wgrad=gemm_wgrad,
-                         wgrad_splits=lambda T, Ca: 1, wgrad_workspace_elems=lambda a, b, c: 1,
-                         _ws=lambda n, d: torch.empty(1)).items():
+                         conv3x3_prep_weights=prep, conv3x3_igemm=igemm, conv3x3_wgrad=conv3x3_wgrad, disc_prep_w4=disc_prep_w4,
+                         disc_wgrad4=disc_wgrad4).items():
         monkeypatch.setattr(capi, name, fn)
     return de
 

@@ -69,7 +69,7 @@ def test_gan_micro_steps_like_train_swin():
     try:
         torch.manual_seed(0)
         g = SwinIR(upscale=4, in_chans=1, img_size=32, window_size=8, embed_dim=180, depths=[2], num_heads=[6], mlp_ratio=2).cuda()
-        d = UNetDiscriminatorSN(num_in_ch=1, num_feat=16).cuda()
+        d = UNetDiscriminatorSN(num_in_ch=1, num_feat=64).cuda()
         DDP = torch.nn.parallel.DistributedDataParallel
         g = DDP(g, device_ids=[0], find_unused_parameters=True)
         d = DDP(d, device_ids=[0], find_unused_parameters=False)
@@ -121,7 +121,7 @@ def test_hybrid_train_and_infer_like_train_hat_and_infer_hat(tmp_path, monkeypat
         net_ema = HybridHATRealESRGAN(**kw).cuda()
         for p in net_ema.parameters():
             p.requires_grad = False
-        net_d = UNetDiscriminatorSN(num_in_ch=1, num_feat=16).cuda()
+        net_d = UNetDiscriminatorSN(num_in_ch=1, num_feat=64).cuda()
         DDP = torch.nn.parallel.DistributedDataParallel
         net_g = DDP(net_g, device_ids=[0], find_unused_parameters=False)
         net_d = DDP(net_d, device_ids=[0])

@@ -335,8 +335,9 @@ int srk_disc_fold_k4s2(const void* taps, int B, int Hi, int Wi, const SrkView* a
                        const SrkView* y, void* stream);
 /* Operand forms of a 4x4 weight W [P][Q][4][4] fp32: a [P, 16*Q] bf16 with column (ky*4+kx)*Q + q, and at = a^T [16*Q, P]
  * (may be NULL).  nn.Conv2d: P = Cout, Q = Cin (a = Wf, at = Wt); nn.ConvTranspose2d: P = Cin, Q = Cout (a = Wd, at = Wu).
- * P, Q multiples of 32. */
-int srk_disc_prep_w4(const float* w, int P, int Q, void* a, void* at, void* stream);
+ * P, Q multiples of 32.  sigma (device pointer to one float, may be NULL): the operands hold W / sigma — spectral
+ * normalisation folded into the packing. */
+int srk_disc_prep_w4(const float* w, int P, int Q, const float* sigma, void* a, void* at, void* stream);
 /* Weight gradient of a 4x4 layer in the parameter's own layout: dw [Cb][R][4][4] fp32, dw[c][r][ky][kx] =
  * sum_t A[t][(ky*4+kx)*R + r] * B[t][c]  (A [T, 16*R], B [T, Cb] bf16, T % 64 == 0; Cb 64 / 128 / 192 / 256 or a multiple of
  * 256).  nn.Conv2d: A = patches(x), B = dy_pre, R = Cin; nn.ConvTranspose2d: A = patches(dy_pre), B = x, R = Cout.
@@ -346,6 +347,28 @@ int srk_disc_wgrad4(int T, int R, int Cb, const void* A, int lda, const void* B,
 long long srk_disc_wgrad4_ws_floats(int T, int R, int Cb);
 /* y = leaky_relu(y, slope) in place on a view (nn.LeakyReLU(0.2, inplace=True) after the 1 -> nf convolution, :49-50) */
 int srk_view_lrelu(const SrkView* y, long long npix, float slope, void* stream);
+
+/* torch.nn.utils.spectral_norm (discriminator_swin.py:10,25,49-52,67-69; torch/nn/utils/spectral_norm.py) on the weight
+ * W [A][B][KK] fp32 (KK = kh*kw) seen as the matrix Wm [U][V]:  dim 0 (nn.Conv2d): U = A, V = B*KK;  dim 1
+ * (nn.ConvTranspose2d): U = B, V = A*KK.   power_iteration != 0 (module.training):  v <- normalize(Wm^T u),
+ * u <- normalize(Wm v) in place on the module's weight_u / weight_v buffers (normalize = x / max(||x||, eps));  always:
+ * *sigma = u . (Wm v);  w_sn (optional) = W / sigma in fp32.  One call serves all layers of a network (n descriptors,
+ * HOST array).  ws: srk_spectral_norm_ws_floats() floats. */
+typedef struct SrkSnLayer {
+  const float* w; /* weight_orig                                         */
+  float* u;       /* weight_u [U]                                        */
+  float* v;       /* weight_v [V]                                        */
+  int A, B, KK, dim;
+  float* sigma;   /* out: 1 float                                        */
+  float* w_sn;    /* out, optional: W / sigma [A][B][KK] fp32            */
+} SrkSnLayer;
+int srk_spectral_norm(const SrkSnLayer* layers, int n, int power_iteration, float eps, float* ws, void* stream);
+long long srk_spectral_norm_ws_floats(void);
+/* Backward of W_sn = W / sigma(W) with u, v constant (what autograd derives for the hook):
+ *   dw[i] = dw_sn[i] / sigma - (<dw_sn[i], W> / sigma^2) * (u v^T laid out like W);   u, v, sigma as the forward left them.
+ * dw_sn / dw: HOST arrays of n device pointers (a NULL entry skips the layer; dw[i] may alias dw_sn[i]).
+ * ws: srk_spectral_norm_ws_floats() floats. */
+int srk_spectral_norm_bwd(const SrkSnLayer* layers, int n, const float* const* dw_sn, float* const* dw, float* ws, void* stream);
 
 /* ======================================================================================================
  * Data formats on either side of the path: 16-bit image planes.

@@ -616,19 +616,21 @@ def view_lrelu(y: SrkView, npix, slope):
     _check(_view_lrelu(_vref(y), npix, slope, _stream()), "srk_view_lrelu")
 
 
-_disc_prep_w4 = _sig("srk_disc_prep_w4", [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p])
+_disc_prep_w4 = _sig("srk_disc_prep_w4", [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p])
 _disc_wgrad4 = _sig("srk_disc_wgrad4", [c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p])
 lib.srk_disc_wgrad4_ws_floats.restype = c_longlong
 lib.srk_disc_wgrad4_ws_floats.argtypes = [c_int, c_int, c_int]
 
 
-def disc_prep_w4(w, a, at=None):
-    """w [P,Q,4,4] fp32 -> a [P,16Q] bf16 (column (ky*4+kx)*Q + q) and at = a^T."""
+def disc_prep_w4(w, a, at=None, sigma=None):
+    """w [P,Q,4,4] fp32 -> a [P,16Q] bf16 (column (ky*4+kx)*Q + q) and at = a^T; sigma (1-element fp32 CUDA tensor or
+    None): operands of W / sigma."""
     P, Q = w.shape[0], w.shape[1]
     assert w.dtype == torch.float32 and w.is_contiguous() and tuple(w.shape[2:]) == (4, 4)
     assert a.dtype == torch.bfloat16 and a.is_contiguous() and a.numel() == 16 * P * Q
     assert at is None or (at.dtype == torch.bfloat16 and at.is_contiguous() and at.numel() == 16 * P * Q)
-    _check(_disc_prep_w4(_ptr(w), P, Q, _ptr(a), _ptr(at), _stream()), "srk_disc_prep_w4")
+    assert sigma is None or (sigma.dtype == torch.float32 and sigma.numel() == 1)
+    _check(_disc_prep_w4(_ptr(w), P, Q, _ptr(sigma), _ptr(a), _ptr(at), _stream()), "srk_disc_prep_w4")
 
 
 def disc_wgrad4(A, B, R, dw):
@@ -638,3 +640,44 @@ def disc_wgrad4(A, B, R, dw):
     assert dw.dtype == torch.float32 and dw.is_contiguous() and dw.numel() == 16 * R * Cb
     ws = _ws(int(lib.srk_disc_wgrad4_ws_floats(T, R, Cb)), A.device)
     _check(_disc_wgrad4(T, R, Cb, _ptr(A), _ld(A), _ptr(B), _ld(B), _ptr(ws), _ptr(dw), _stream()), "srk_disc_wgrad4")
+
+
+class SrkSnLayer(Structure):
+    _fields_ = [("w", c_void_p), ("u", c_void_p), ("v", c_void_p), ("A", c_int), ("B", c_int), ("KK", c_int), ("dim", c_int),
+                ("sigma", c_void_p), ("w_sn", c_void_p)]
+
+
+_spectral_norm = _sig("srk_spectral_norm", [POINTER(SrkSnLayer), c_int, c_int, c_float, c_void_p, c_void_p])
+_spectral_norm_bwd = _sig("srk_spectral_norm_bwd", [POINTER(SrkSnLayer), c_int, POINTER(c_void_p), POINTER(c_void_p), c_void_p,
+                                                    c_void_p])
+lib.srk_spectral_norm_ws_floats.restype = c_longlong
+
+
+def sn_layers(ws, us, vs, dims, sigmas, w_sn=None):
+    """HOST descriptor array for srk_spectral_norm: ws / us / vs = weight_orig / weight_u / weight_v tensors, dims[i] = the
+    `dim` spectral_norm used (0 Conv2d, 1 ConvTranspose2d), sigmas = fp32 CUDA tensor [n], w_sn[i] = optional fp32 output."""
+    n = len(ws)
+    arr = (SrkSnLayer * n)()
+    for i, (w, u, v, dm) in enumerate(zip(ws, us, vs, dims)):
+        assert w.dtype == torch.float32 and w.is_contiguous() and w.dim() == 4 and u.dtype == torch.float32 and v.dtype == torch.float32
+        A, B, KK = w.shape[0], w.shape[1], w.shape[2] * w.shape[3]
+        assert u.is_contiguous() and v.is_contiguous() and u.numel() == (A if dm == 0 else B) and v.numel() == (B if dm == 0 else A) * KK
+        o = None if w_sn is None else w_sn[i]
+        assert o is None or (o.dtype == torch.float32 and o.is_contiguous() and o.numel() == w.numel())
+        arr[i] = SrkSnLayer(_ptr(w), _ptr(u), _ptr(v), A, B, KK, dm, sigmas.data_ptr() + 4 * i, _ptr(o))
+    return arr
+
+
+def spectral_norm(layers, power_iteration: bool, eps: float, device):
+    ws = _ws(int(lib.srk_spectral_norm_ws_floats()), device)
+    _check(_spectral_norm(layers, len(layers), int(power_iteration), eps, _ptr(ws), _stream()), "srk_spectral_norm")
+
+
+def spectral_norm_bwd(layers, dw_sn, dw, device):
+    """dw_sn / dw: lists of fp32 CUDA tensors or None (layer skipped); dw[i] may be dw_sn[i]."""
+    n = len(layers)
+    a, b = (c_void_p * n)(), (c_void_p * n)()
+    for i in range(n):
+        a[i], b[i] = _ptr(dw_sn[i]), _ptr(dw[i])
+    ws = _ws(int(lib.srk_spectral_norm_ws_floats()), device)
+    _check(_spectral_norm_bwd(layers, n, a, b, _ptr(ws), _stream()), "srk_spectral_norm_bwd")

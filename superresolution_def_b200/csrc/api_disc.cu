@@ -1,6 +1,7 @@
 // api_disc.cu — C-ABI entry points for the data movement around the discriminator's 4x4 stride-2 (transposed)
 // convolutions (disc_aux.cuh).  The arithmetic itself is srk_gemm_tn / srk_gemm_tn_lrelu / srk_gemm_wgrad.
 #include "disc_aux.cuh"
+#include "spectral_norm.cuh"
 #include "srk_host.h"
 
 using namespace srk;
@@ -27,7 +28,7 @@ extern "C" int srk_disc_patches_k4s2(const SrkView* x, const SrkView* f, float s
   if (f && ((rc = check_view(f, "disc_patches: f view")) || f->C != x->C)) return rc ? rc : fail(SRK_ERR_ARG, "disc_patches: f and x differ in channels");
   if (B <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1) || !patches || (reinterpret_cast<uintptr_t>(patches) & 15))
     return fail(SRK_ERR_ARG, "disc_patches: even H and W and a 16-byte aligned patch matrix required");
-  const long long vectors = (long long)B * (H / 2) * (W / 2) * 16 * (x->C / 8);
+  const long long vectors = (long long)B * (H / 2) * (W / 2) * (x->C / 8);   // threads: one per (patch row, 8-channel group)
   const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x->ptr);
   const __nv_bfloat16* fp = f ? static_cast<const __nv_bfloat16*>(f->ptr) : nullptr;
   // + one grid stride of headroom so that the 32-bit loop counter cannot wrap
@@ -83,11 +84,11 @@ extern "C" int srk_view_lrelu(const SrkView* y, long long npix, float slope, voi
   return SRK_OK;
 }
 
-extern "C" int srk_disc_prep_w4(const float* w, int P, int Q, void* a, void* at, void* stream_) {
+extern "C" int srk_disc_prep_w4(const float* w, int P, int Q, const float* sigma, void* a, void* at, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!w || !a || P <= 0 || Q <= 0 || P % 32 || Q % 32 || (reinterpret_cast<uintptr_t>(w) & 15))
     return fail(SRK_ERR_ARG, "disc_prep_w4: P and Q must be multiples of 32, w 16-byte aligned");
-  disc_prep_w4_kernel<<<stream_grid((long long)P * Q), 256, 0, stream>>>(w, P, Q, static_cast<__nv_bfloat16*>(a));
+  disc_prep_w4_kernel<<<stream_grid((long long)P * Q), 256, 0, stream>>>(w, P, Q, sigma, static_cast<__nv_bfloat16*>(a));
   SRK_LAUNCHED(1);
   if (at) {
     const long long tiles = (long long)(P / 32) * (16 * Q / 32);
@@ -120,6 +121,78 @@ extern "C" int srk_disc_wgrad4(int T, int R, int Cb, const void* A, int lda, con
     if (rc) return rc;
     disc_unpack_wgrad4_kernel<<<stream_grid((long long)R * cb), 256, 0, stream>>>(ws, splits, (long long)ca_pad * cb, R, cb, c0, dw);
     SRK_LAUNCHED(1);
+  }
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// torch.nn.utils.spectral_norm (spectral_norm.cuh)
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+constexpr long long SN_WS_FLOATS = 1LL << 19;
+int sn_check(const SrkSnLayer& l) {
+  if (!l.w || !l.u || !l.v || !l.sigma || l.A <= 0 || l.B <= 0 || l.KK <= 0 || (l.dim != 0 && l.dim != 1))
+    return fail(SRK_ERR_ARG, "spectral_norm: layer descriptor (w, u, v, sigma, A, B, KK, dim)");
+  return SRK_OK;
+}
+}  // namespace
+
+extern "C" long long srk_spectral_norm_ws_floats(void) { return SN_WS_FLOATS; }
+
+extern "C" int srk_spectral_norm(const SrkSnLayer* layers, int n, int power_iteration, float eps, float* ws, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!layers || n <= 0 || !ws) return fail(SRK_ERR_ARG, "spectral_norm: null argument");
+  for (int i = 0; i < n; ++i) {
+    const SrkSnLayer& l = layers[i];
+    int rc = sn_check(l);
+    if (rc) return rc;
+    const SnDims d{l.A, l.B, l.KK, l.dim};
+    const int U = l.dim == 0 ? l.A : l.B;
+    const int V = (l.dim == 0 ? l.B : l.A) * l.KK;
+    const int nb = (V + 255) / 256;
+    int splits = (2 * num_sms() + nb - 1) / nb;
+    if (splits > U) splits = U;
+    if (splits < 1) splits = 1;
+    if ((long long)(splits + 1) * V + U + nb > SN_WS_FLOATS) return fail(SRK_ERR_UNSUPPORTED, "spectral_norm: layer too large for the workspace");
+    float* t_raw = ws + (long long)splits * V;   // [V]
+    float* s_raw = t_raw + V;                    // [U]
+    float* ssq = s_raw + U;                      // [nb]
+    if (power_iteration) {
+      sn_t_partial_kernel<<<dim3(nb, splits), 256, 0, stream>>>(l.w, l.u, d, U, V, ws);
+      sn_t_reduce_kernel<<<nb, 256, 0, stream>>>(ws, splits, V, t_raw, ssq);
+      SRK_LAUNCHED(2);
+    }
+    sn_s_rows_kernel<<<U, 256, 0, stream>>>(l.w, l.v, power_iteration ? t_raw : nullptr, ssq, nb, eps, d, V, s_raw);
+    sn_s_finish_kernel<<<1, 256, 0, stream>>>(s_raw, U, eps, power_iteration ? 1 : 0, l.u, l.sigma);
+    SRK_LAUNCHED(2);
+    if (l.w_sn) {
+      const long long cnt = (long long)l.A * l.B * l.KK;
+      sn_scale_kernel<<<stream_grid(cnt), 256, 0, stream>>>(l.w, cnt, l.sigma, l.w_sn);
+      SRK_LAUNCHED(1);
+    }
+  }
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+extern "C" int srk_spectral_norm_bwd(const SrkSnLayer* layers, int n, const float* const* dw_sn, float* const* dw, float* ws,
+                                     void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!layers || n <= 0 || !dw_sn || !dw || !ws) return fail(SRK_ERR_ARG, "spectral_norm_bwd: null argument");
+  for (int i = 0; i < n; ++i) {
+    const SrkSnLayer& l = layers[i];
+    if (!dw_sn[i] || !dw[i]) continue;   // this layer's gradient was not requested
+    int rc = sn_check(l);
+    if (rc) return rc;
+    const SnDims d{l.A, l.B, l.KK, l.dim};
+    const long long cnt = (long long)l.A * l.B * l.KK;
+    int g = stream_grid(cnt);
+    if (g > 1024) g = 1024;
+    float* part = ws + (long long)(i & 1) * 1024;   // two slots: layer i+1's partials must not overwrite what layer i's apply reads
+    sn_dot_partial_kernel<<<g, 256, 0, stream>>>(dw_sn[i], l.w, cnt, part);
+    sn_bwd_apply_kernel<<<stream_grid(cnt), 256, 0, stream>>>(dw_sn[i], part, g, l.sigma, l.u, l.v, d, dw[i]);
+    SRK_LAUNCHED(2);
   }
   SRK_CUDA_OK(cudaGetLastError());
   return SRK_OK;

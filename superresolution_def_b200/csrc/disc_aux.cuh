@@ -27,9 +27,10 @@ __device__ __forceinline__ uint4 f32_to_bf16x8(const float (&f)[8]) {
 
 // patches[m][(ky*4+kx)*C + c] = g[b][2*oy-1+ky][2*ox-1+kx][c]  (zero outside the image), m = (b*Ho + oy)*Wo + ox,
 // g = x, or x * (f > 0 ? 1 : slope) when f is given (LeakyReLU backward applied while gathering a gradient image).
-// One thread per 16-byte vector of the patch matrix: its linear index IS the destination offset.
-// (Idx = unsigned when the vector count fits 32 bits: the four divisions per vector are what bounds this kernel with
-// 64-bit indices — 140 us of integer work for a 268 MB patch matrix against 55 us of HBM time.)
+// One thread per (patch row m, 8-channel group): the index decomposition is paid once for sixteen 16-byte vectors, whose
+// loads are independent (16 in flight per thread) and whose stores are C*2-byte contiguous runs across the channel lanes.
+// (First version: one thread per vector with 64-bit divisions — 140 us of integer work for the 268 MB patch matrix of the
+// first stride-2 layer against 55 us of HBM time; 32-bit indices halved the kernel, this form removes the rest.)
 template <typename Idx>
 static __global__ void __launch_bounds__(256) disc_patches_k4s2_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
                                                                        const __nv_bfloat16* __restrict__ f, int ldf, float slope,
@@ -37,32 +38,42 @@ static __global__ void __launch_bounds__(256) disc_patches_k4s2_kernel(const __n
                                                                        __nv_bfloat16* __restrict__ patches) {
   const Idx groups = Idx(C >> 3);
   const Idx Ho = Idx(H >> 1), Wo = Idx(W >> 1);
-  const Idx total = Idx(B) * Ho * Wo * 16 * groups;
+  const Idx total = Idx(B) * Ho * Wo * groups;
   for (Idx idx = Idx(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += Idx(gridDim.x) * blockDim.x) {
-    const int cg = int(idx % groups);
-    Idx t = idx / groups;
-    const int tap = int(t & 15);
-    t >>= 4;
-    const int ox = int(t % Wo);
-    t /= Wo;
-    const int oy = int(t % Ho);
-    const int b = int(t / Ho);
-    const int iy = 2 * oy - 1 + (tap >> 2), ix = 2 * ox - 1 + (tap & 3);
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
-      const long long pix = ((long long)b * H + iy) * W + ix;
-      v = *reinterpret_cast<const uint4*>(x + pix * ldx + cg * 8);
-      if (f != nullptr) {
-        const uint4 fv = *reinterpret_cast<const uint4*>(f + pix * ldf + cg * 8);
-        float xv[8], fw[8];
-        bf16x8_to_f32(v, xv);
-        bf16x8_to_f32(fv, fw);
+    const Idx m = idx / groups;
+    const int cg = int(idx - m * groups);
+    const Idx r = m / Wo;
+    const int ox = int(m - r * Wo);
+    const int oy = int(r % Ho);
+    const int b = int(r / Ho);
+    const int iy0 = 2 * oy - 1, ix0 = 2 * ox - 1;
+    const __nv_bfloat16* xb = x + ((long long)b * H * W) * ldx + cg * 8;
+    const __nv_bfloat16* fb = f ? f + ((long long)b * H * W) * ldf + cg * 8 : nullptr;
+    uint4 v[16];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) xv[e] = fw[e] > 0.f ? xv[e] : xv[e] * slope;
-        v = f32_to_bf16x8(xv);
+    for (int tap = 0; tap < 16; ++tap) {
+      const int iy = iy0 + (tap >> 2), ix = ix0 + (tap & 3);
+      v[tap] = make_uint4(0u, 0u, 0u, 0u);
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v[tap] = *reinterpret_cast<const uint4*>(xb + (long long)(iy * W + ix) * ldx);
+    }
+    if (fb != nullptr) {
+#pragma unroll
+      for (int tap = 0; tap < 16; ++tap) {
+        const int iy = iy0 + (tap >> 2), ix = ix0 + (tap & 3);
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+          const uint4 fv = *reinterpret_cast<const uint4*>(fb + (long long)(iy * W + ix) * ldf);
+          float xv[8], fw[8];
+          bf16x8_to_f32(v[tap], xv);
+          bf16x8_to_f32(fv, fw);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) xv[e] = fw[e] > 0.f ? xv[e] : xv[e] * slope;
+          v[tap] = f32_to_bf16x8(xv);
+        }
       }
     }
-    *reinterpret_cast<uint4*>(patches + (long long)idx * 8) = v;
+    __nv_bfloat16* dst = patches + (long long)m * 16 * C + cg * 8;
+#pragma unroll
+    for (int tap = 0; tap < 16; ++tap) *reinterpret_cast<uint4*>(dst + tap * C) = v[tap];
   }
 }
 
@@ -151,8 +162,9 @@ namespace srk {
 // Operand form of a 4x4 weight: W [P][Q][4][4] fp32 -> A [P][16*Q] bf16 with column k = (ky*4+kx)*Q + q.
 // (Conv2d: P = Cout, Q = Cin, A = Wf; ConvTranspose2d: P = Cin, Q = Cout, A = Wd.)  One thread per (p, q): 64 contiguous
 // bytes in, sixteen 2-byte stores that are contiguous across the warp for each tap.
-static __global__ void __launch_bounds__(256) disc_prep_w4_kernel(const float* __restrict__ w, int P, int Q,
+static __global__ void __launch_bounds__(256) disc_prep_w4_kernel(const float* __restrict__ w, int P, int Q, const float* __restrict__ sigma,
                                                                   __nv_bfloat16* __restrict__ a) {
+  const float sc = sigma ? 1.f / *sigma : 1.f;   // spectral normalisation folded into the packing: W / sigma
   const long long total = (long long)P * Q;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int q = int(i % Q);
@@ -162,10 +174,10 @@ static __global__ void __launch_bounds__(256) disc_prep_w4_kernel(const float* _
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float4 v = src[j];
-      dst[(long long)(4 * j + 0) * Q] = __float2bfloat16_rn(v.x);
-      dst[(long long)(4 * j + 1) * Q] = __float2bfloat16_rn(v.y);
-      dst[(long long)(4 * j + 2) * Q] = __float2bfloat16_rn(v.z);
-      dst[(long long)(4 * j + 3) * Q] = __float2bfloat16_rn(v.w);
+      dst[(long long)(4 * j + 0) * Q] = __float2bfloat16_rn(v.x * sc);
+      dst[(long long)(4 * j + 1) * Q] = __float2bfloat16_rn(v.y * sc);
+      dst[(long long)(4 * j + 2) * Q] = __float2bfloat16_rn(v.z * sc);
+      dst[(long long)(4 * j + 3) * Q] = __float2bfloat16_rn(v.w * sc);
     }
   }
 }

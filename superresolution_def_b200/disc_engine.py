@@ -42,15 +42,20 @@ def _alloc(m: int, c: int, dev) -> torch.Tensor:
     return t
 
 
-def _ops4(w):
-    """4x4 weight [P,Q,4,4] -> (a [P,16Q], a^T [16Q,P]) bf16, column (ky*4+kx)*Q + q.
+def _ops4(w, sigma=None):
+    """4x4 weight [P,Q,4,4] fp32 -> (a [P,16Q], a^T [16Q,P]) bf16 of W / sigma, column (ky*4+kx)*Q + q.
     Conv2d [Cout,Cin,4,4]: a = Wf (forward operand), a^T = Wt (input-gradient operand);
     ConvTranspose2d [Cin,Cout,4,4]: a = Wd (input-gradient operand), a^T = Wu (forward operand)."""
     P, Q = w.shape[0], w.shape[1]
     a = torch.empty(P, 16 * Q, device=w.device, dtype=BF16)
     at = torch.empty(16 * Q, P, device=w.device, dtype=BF16)
-    capi.disc_prep_w4(w.detach().float().contiguous(), a, at)
+    capi.disc_prep_w4(w, a, at, sigma)
     return a, at
+
+
+# the `dim` torch.nn.utils.spectral_norm picks per layer: 0 for nn.Conv2d, 1 for nn.ConvTranspose2d (the four up blocks)
+SN_DIMS = (0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 0, 0)
+_SMALL = (0, 10, 11)   # the 3x3 layers: their kernels take fp32 filters, so W / sigma is materialised for them
 
 
 def _wgrad(A, B2d, R):
@@ -64,15 +69,38 @@ class UNetDiscriminatorFunction(torch.autograd.Function):
     """x [B,1,H,W] -> logits [B,1,H/2,W/2] (UNetDiscriminatorSN.forward, discriminator_swin.py:72-84)."""
 
     @staticmethod
-    def forward(ctx, x, w0a, w0b, w1, w2, w3, w4, u1, u2, u3, u4, wf1, wf2):
+    def forward(ctx, x, sn, *weights):
+        """weights: the 12 convolution weights in forward order.  sn is None: they are used as given (already normalised);
+        sn = dict(u=[...], v=[...], training=bool, eps=float): they are the `weight_orig` parameters and spectral
+        normalisation (one power iteration on u / v in place when training, sigma, W / sigma) runs here on libsrk."""
         B, cin, H, W = x.shape
+        if len(weights) != 12:
+            raise capi.SrkError("UNetDiscriminatorSN has 12 convolutions")
+        dev = x.device
+        weights = [w.detach().float().contiguous() for w in weights]
+        sig = [None] * 12
+        small = {i: weights[i] for i in _SMALL}
+        sn_ctx = None
+        if sn is not None:
+            sigmas = torch.empty(12, device=dev, dtype=torch.float32)
+            w_sn = [torch.empty_like(weights[i]) if i in _SMALL else None for i in range(12)]
+            capi.spectral_norm(capi.sn_layers(weights, sn["u"], sn["v"], SN_DIMS, sigmas, w_sn), sn["training"], sn["eps"], dev)
+            sig = [sigmas[i:i + 1] for i in range(12)]
+            small = {i: w_sn[i] for i in _SMALL}
+            if any(ctx.needs_input_grad[2:]):
+                # u and v as this forward left them (the hook clones them for the same reason: a second forward before
+                # the backward runs another power iteration in place)
+                sizes = [t.numel() for t in sn["u"]] + [t.numel() for t in sn["v"]]
+                flat = torch.cat([t.reshape(-1) for t in list(sn["u"]) + list(sn["v"])])
+                parts = list(torch.split(flat, sizes))
+                sn_ctx = (parts[:12], parts[12:], sigmas)
+        w0a, w0b, w1, w2, w3, w4, u1, u2, u3, u4, wf1, wf2 = weights
         nf = w0a.shape[0]
         if cin != 1 or nf != 64 or wf2.shape[0] != 1:
             raise capi.SrkError("discriminator kernels are specialised for num_in_ch=1, num_feat=64 (the scripts' only configuration)")
         if H % 32 or W % 32:
             raise capi.SrkError("UNetDiscriminatorSN: H and W must be multiples of 32 (the bilinear resize of UNetUpBlock, "
                                 "discriminator_swin.py:36-38, is not implemented)")
-        dev = x.device
         f32 = torch.float32
         xf = x.detach().contiguous().float().reshape(B, H, W)
         Hs = [H >> i for i in range(6)]
@@ -83,7 +111,7 @@ class UNetDiscriminatorFunction(torch.autograd.Function):
 
         # conv0: 1 -> 64 3x3 + LeakyReLU, then 64 -> 64 4x4 s2 + LeakyReLU (:48-53)
         a0 = _alloc(M[0], 64, dev)
-        capi.conv_in1_fwd(xf, w0a.detach().float().contiguous(), zeros64, a0, B, H, W, 64, 64)
+        capi.conv_in1_fwd(xf, small[0], zeros64, a0, B, H, W, 64, 64)
         capi.view_lrelu(V(a0), M[0], SLOPE)
         # one buffer per level: [decoder output | encoder skip] = torch.cat((x, skip_input), 1) (:40)
         cat4 = _alloc(M[1], 128, dev)    # d4 (64)  | x0 (64)
@@ -91,9 +119,9 @@ class UNetDiscriminatorFunction(torch.autograd.Function):
         cat2 = _alloc(M[3], 512, dev)    # d2 (256) | x2 (256)
         cat1 = _alloc(M[4], 1024, dev)   # d1 (512) | x3 (512)
         x4 = _alloc(M[5], 512, dev)
-        ops_d = [_ops4(w) for w in (w0b, w1, w2, w3, w4)]              # (Wf, Wt)
-        ops_u = [_ops4(w)[::-1] for w in (u1, u2, u3, u4)]            # (Wu, Wd)
-        keep_patches = any(ctx.needs_input_grad[1:])   # the weight gradients read the forward's patch matrices again
+        ops_d = [_ops4(weights[i], sig[i]) for i in range(1, 6)]         # (Wf, Wt)
+        ops_u = [_ops4(weights[i], sig[i])[::-1] for i in range(6, 10)]  # (Wu, Wd)
+        keep_patches = any(ctx.needs_input_grad[2:])   # the weight gradients read the forward's patch matrices again
         saved_patches = []
 
         def down(src, c0, cin_, lvl, wf, dst, d0):
@@ -126,19 +154,19 @@ class UNetDiscriminatorFunction(torch.autograd.Function):
         wk_f1 = torch.empty(64 * 9 * 128, device=dev, dtype=BF16)
         wt_f1 = torch.empty(128 * 9 * 64, device=dev, dtype=BF16)
         b_f1 = torch.empty(64, device=dev, dtype=f32)
-        capi.conv3x3_prep_weights(wf1.detach().float().contiguous(), None, 64, 128, False, wk_f1, wt_f1, b_f1)
+        capi.conv3x3_prep_weights(small[10], None, 64, 128, False, wk_f1, wt_f1, b_f1)
         f1a = _alloc(M[1], 64, dev)
         capi.conv3x3_igemm(capi.CEPI_BIAS_LRELU, B, Hs[1], Ws[1], 128, 64, 64, cat4, wk_f1, b_f1, f1a, slope=SLOPE)
         out = torch.empty(B, 1, Hs[1], Ws[1], device=dev, dtype=f32)
-        w_last = wf2.detach().float().contiguous()
+        w_last = small[11]
         capi.conv_out1_fwd(f1a, w_last, torch.zeros(1, device=dev, dtype=f32), out, B, Hs[1], Ws[1], 64)
 
         if any(ctx.needs_input_grad):
             ctx.acts = (xf, a0, cat4, cat3, cat2, cat1, x4, f1a)
-            ctx.ops = (ops_d, ops_u, wt_f1, w_last, w0a.detach().float().contiguous())
+            ctx.ops = (ops_d, ops_u, wt_f1, w_last, small[0])
+            ctx.sn = (sn_ctx, weights if sn_ctx is not None else None)
             ctx.patches = saved_patches
             ctx.meta = (B, Hs, Ws, M, x.dtype)
-            ctx.wshapes = [tuple(w.shape) for w in (w0a, w0b, w1, w2, w3, w4, u1, u2, u3, u4, wf1, wf2)]
         return out
 
     @staticmethod
@@ -150,7 +178,7 @@ class UNetDiscriminatorFunction(torch.autograd.Function):
         patches = ctx.patches
         B, Hs, Ws, M, x_dtype = ctx.meta
         need = ctx.needs_input_grad
-        need_x, need_w = need[0], any(need[1:])
+        need_x, need_w = need[0], any(need[2:])
         dev = dout.device
         f32 = torch.float32
         V = capi.view
@@ -221,14 +249,28 @@ class UNetDiscriminatorFunction(torch.autograd.Function):
             dx = torch.empty(B, 1, Hs[0], Ws[0], device=dev, dtype=f32)
             capi.conv_out1_fwd(d_a0, w_flip, torch.zeros(1, device=dev, dtype=f32), dx, B, Hs[0], Ws[0], 64)
             dx = dx.to(x_dtype)
-        ctx.acts = ctx.patches = None
-        grads = (dw0a, dw0b, dw1, dw2, dw3, dw4, dw_u1, dw_u2, dw_u3, dw_u4, dw_f1, dw_f2 if need_w else None)
-        grads = tuple(g if n else None for g, n in zip(grads, need[1:]))
-        return (dx,) + grads
+        grads = [dw0a, dw0b, dw1, dw2, dw3, dw4, dw_u1, dw_u2, dw_u3, dw_u4, dw_f1, dw_f2 if need_w else None]
+        grads = [g if n else None for g, n in zip(grads, need[2:])]
+        sn_ctx, w_orig = ctx.sn
+        if sn_ctx is not None and need_w:
+            # through W / sigma(W) back to weight_orig, in place on the gradients just computed
+            us, vs, sigmas = sn_ctx
+            capi.spectral_norm_bwd(capi.sn_layers(w_orig, us, vs, SN_DIMS, sigmas), grads, grads, dev)
+        ctx.acts = ctx.patches = ctx.sn = None
+        return (dx, None) + tuple(grads)
 
 
 def unet_discriminator(x, weights):
-    """weights: the 12 (spectrally normalised) conv weights in forward order."""
+    """weights: the 12 (already spectrally normalised) conv weights in forward order."""
     if not x.is_cuda:
         raise capi.SrkError("UNetDiscriminatorSN runs on CUDA (sm_100a) only; there is no CPU path")
-    return UNetDiscriminatorFunction.apply(x, *weights)
+    return UNetDiscriminatorFunction.apply(x, None, *weights)
+
+
+def unet_discriminator_sn(x, weight_orig, weight_u, weight_v, training: bool, eps: float = 1e-12):
+    """The module path: `weight_orig` parameters + the spectral-norm buffers, normalised on libsrk (srk_spectral_norm); u and v
+    are updated in place when `training`, exactly as torch.nn.utils.spectral_norm's forward pre-hook does."""
+    if not x.is_cuda:
+        raise capi.SrkError("UNetDiscriminatorSN runs on CUDA (sm_100a) only; there is no CPU path")
+    sn = dict(u=list(weight_u), v=list(weight_v), training=bool(training), eps=float(eps))
+    return UNetDiscriminatorFunction.apply(x, sn, *weight_orig)

@@ -7,8 +7,9 @@ losses, gradient accumulation, EMA.
 attribute names, registration order and spectral-norm hooks, so `state_dict()` round-trips with strict=True and a reference
 checkpoint's `net_d` loads); its forward and backward run on libsrk (`disc_engine.py`: the 4x4 stride-2 convolutions and
 transposed convolutions as tcgen05 GEMMs over a patch matrix / followed by a fold, the 3x3 layers on the generators'
-kernels).  Spectral normalisation itself is the reference's own hook (power iteration on the weight matrix): parameter
-preparation, executed by torch exactly as in the reference.  There is no CPU path: the ATen restatement lives in
+kernels).  Spectral normalisation (one power iteration on the `weight_u` / `weight_v` buffers when training, sigma, W / sigma
+and its backward) is `srk_spectral_norm` / `srk_spectral_norm_bwd`: same buffers, same update rule as the hook that
+`spectral_norm()` installs (which only fires inside `Conv2d.forward`, never called here).  There is no CPU path: the ATen restatement lives in
 `oracle/discriminator_oracle.py` and is test infrastructure only.
 
 The loss modules are interface mirrors (losses are out of scope).  The VGG feature extractor of the
@@ -90,7 +91,12 @@ class UNetDiscriminatorSN(nn.Module):
 
     def forward(self, x):
         from . import disc_engine
-        return disc_engine.unet_discriminator(x, [_sn_weight(m) for m in self._convs()])
+        convs = self._convs()
+        if len({m.training for m in convs}) != 1:
+            raise RuntimeError("UNetDiscriminatorSN: mixed train / eval modes across the spectral-norm layers are not supported")
+        eps = next(iter(convs[0]._forward_pre_hooks.values())).eps
+        return disc_engine.unet_discriminator_sn(x, [m.weight_orig for m in convs], [m.weight_u for m in convs],
+                                                 [m.weight_v for m in convs], convs[0].training, eps)
 
 
 class RelativeGANLoss(nn.Module):

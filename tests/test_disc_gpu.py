@@ -111,6 +111,44 @@ def test_wgrad4_is_the_unpermuted_matmul(T, R, Cb):
     assert rel_l2(dw, want) < 1e-5, rel_l2(dw, want)      # fp32 accumulation of exact bf16 products: summation order only
 
 
+@pytest.mark.parametrize("shape,dim", [((512, 256, 4, 4), 0), ((1024, 256, 4, 4), 1), ((64, 1, 3, 3), 0), ((1, 64, 3, 3), 0),
+                                       ((64, 128, 3, 3), 0), ((256, 128, 4, 4), 1)])
+def test_spectral_norm_kernels(shape, dim):
+    """srk_spectral_norm / srk_spectral_norm_bwd against the formulas of torch.nn.utils.spectral_norm in fp64:
+    v <- normalize(Wm^T u), u <- normalize(Wm v), sigma = u . Wm v, W / sigma; backward with u, v constant."""
+    from superresolution_def_b200 import _capi as capi
+    w = _mk(shape, 0.05, seed=11)
+    U = shape[0] if dim == 0 else shape[1]
+    V = w.numel() // U
+    u0 = torch.nn.functional.normalize(_mk((U,), seed=12), dim=0)
+    v0 = torch.nn.functional.normalize(_mk((V,), seed=13), dim=0)
+    wm = (w if dim == 0 else w.permute(1, 0, 2, 3)).reshape(U, V).double()
+    for train in (True, False):
+        u, v = u0.clone(), v0.clone()
+        sig = torch.zeros(1, device="cuda")
+        w_sn = torch.empty_like(w)
+        layers = capi.sn_layers([w], [u], [v], [dim], sig, [w_sn])
+        capi.spectral_norm(layers, train, 1e-12, w.device)
+        ur, vr = u0.double(), v0.double()
+        if train:
+            vr = torch.nn.functional.normalize(wm.t() @ ur, dim=0)
+            ur = torch.nn.functional.normalize(wm @ vr, dim=0)
+        sr = ur @ (wm @ vr)
+        assert rel_l2(u, ur) < 1e-5 and rel_l2(v, vr) < 1e-5, (train, rel_l2(u, ur), rel_l2(v, vr))
+        assert abs(sig.item() / sr.item() - 1) < 1e-5
+        assert rel_l2(w_sn, w.double() / sr) < 1e-5
+        g = _mk(shape, seed=14)
+        wd = w.double().requires_grad_(True)
+        wmd = (wd if dim == 0 else wd.permute(1, 0, 2, 3)).reshape(U, V)
+        ((wd / (ur @ (wmd @ vr))) * g.double()).sum().backward()
+        dw = torch.empty_like(w)
+        capi.spectral_norm_bwd(layers, [g], [dw], w.device)
+        assert rel_l2(dw, wd.grad) < 2e-5, (train, rel_l2(dw, wd.grad))
+        g2 = g.clone()
+        capi.spectral_norm_bwd(layers, [g2], [g2], w.device)      # in place, as the engine calls it
+        assert torch.equal(g2, dw)
+
+
 def _weights(seed=0):
     nf = 64
     shapes = [(nf, 1, 3, 3), (nf, nf, 4, 4), (2 * nf, nf, 4, 4), (4 * nf, 2 * nf, 4, 4), (8 * nf, 4 * nf, 4, 4), (8 * nf, 8 * nf, 4, 4),
@@ -185,15 +223,18 @@ def test_module_mirror_matches_oracle_module_train_mode():
     ora = OraD(1, 64).cuda().train()
     ora_ac = OraD(1, 64).cuda().train()          # the same module under bf16 autocast: the yardstick for the gradients
     mine = UNetDiscriminatorSN(1, 64).cuda().train()
+    x = torch.rand(2, 1, 128, 128, device="cuda")
+    with torch.no_grad():
+        for _ in range(3):      # leave the random initial u / v behind (sigma ~ 1e-3 per layer otherwise)
+            ora(x)
     mine.load_state_dict(ora.state_dict(), strict=True)
     ora_ac.load_state_dict(ora.state_dict(), strict=True)
-    x = torch.rand(2, 1, 128, 128, device="cuda")
     a, b = mine(x), ora(x)
     with torch.autocast("cuda", dtype=BF):
         c = ora_ac(x)
     for k, v in ora.state_dict().items():
-        if k.endswith("weight_u") or k.endswith("weight_v"):
-            assert torch.equal(mine.state_dict()[k], v), k   # same single power iteration
+        if k.endswith("weight_u") or k.endswith("weight_v"):   # the same single power iteration, srk_spectral_norm vs the hook
+            assert rel_l2(mine.state_dict()[k], v) < 1e-5, (k, rel_l2(mine.state_dict()[k], v))
     assert rel_l2(a, b) < 2e-2 and rel_l2(a, b) < 1.6 * rel_l2(c, b) + 5e-3, (rel_l2(a, b), rel_l2(c, b))
     g = torch.randn_like(b)
     a.backward(g); b.backward(g); c.float().backward(g)
@@ -205,6 +246,7 @@ def test_module_mirror_matches_oracle_module_train_mode():
             bad.append((n, e_my, e_ac))
     assert not bad, bad
     # eval mode: no power iteration, buffers unchanged
+    mine.load_state_dict(ora.state_dict(), strict=True)
     mine.eval(); ora.eval()
     u0 = mine.conv1.model[0].weight_u.clone()
     with torch.no_grad():

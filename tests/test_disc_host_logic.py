@@ -115,10 +115,10 @@ def engine(monkeypatch):
             dy[:B * H * W].reshape(B, H, W, Cout).permute(0, 3, 1, 2))
         dw.copy_(w.grad)
 
-    def disc_prep_w4(w, a, at=None):
+    def disc_prep_w4(w, a, at=None, sigma=None):
         P, Q = w.shape[0], w.shape[1]
-        assert P % 32 == 0 and Q % 32 == 0
-        a.copy_(w.permute(0, 2, 3, 1).reshape(P, 16 * Q))
+        assert P % 32 == 0 and Q % 32 == 0 and w.dtype == torch.float32 and w.is_contiguous()
+        a.copy_(w.permute(0, 2, 3, 1).reshape(P, 16 * Q) / (1.0 if sigma is None else sigma))
         if at is not None:
             at.copy_(a.t())
 
@@ -127,7 +127,37 @@ def engine(monkeypatch):
         assert T % 64 == 0 and tuple(A.shape) == (T, 16 * R) and (Cb in (64, 128, 192, 256) or Cb % 256 == 0)
         dw.copy_((A.t() @ B).view(4, 4, R, Cb).permute(3, 2, 0, 1))
 
-    for name, fn in dict(view=lambda t, c0=0, C=None: _View(t, c0, t.shape[1] - c0 if C is None else C),
+    # srk_spectral_norm / _bwd restated from their contract in include/srk.h (NOT from torch's hook: the test below compares
+    # the result with the hook-driven oracle module)
+    def sn_layers(ws, us, vs, dims, sigmas, w_sn=None):
+        return [(w, u, v, dm, sigmas, i, None if w_sn is None else w_sn[i]) for i, (w, u, v, dm) in enumerate(zip(ws, us, vs, dims))]
+
+    def _mat(w, dm):
+        return w.reshape(w.shape[0], -1) if dm == 0 else w.permute(1, 0, 2, 3).reshape(w.shape[1], -1)
+
+    def spectral_norm(layers, power_iteration, eps, device):
+        for w, u, v, dm, sigmas, i, out in layers:
+            wm = _mat(w, dm)
+            if power_iteration:
+                t = wm.t() @ u
+                v.copy_(t / t.norm().clamp_min(eps))
+            s_ = wm @ v
+            if power_iteration:
+                u.copy_(s_ / s_.norm().clamp_min(eps))
+            sigmas[i] = u @ s_
+            if out is not None:
+                out.copy_(w / sigmas[i])
+
+    def spectral_norm_bwd(layers, dw_sn, dw, device):
+        for (w, u, v, dm, sigmas, i, _), g, o in zip(layers, dw_sn, dw):
+            if g is None:
+                continue
+            sg = sigmas[i]
+            uv = torch.outer(u, v)
+            uv = uv.reshape(w.shape) if dm == 0 else uv.reshape(w.shape[1], w.shape[0], *w.shape[2:]).permute(1, 0, 2, 3)
+            o.copy_(g / sg - ((g * w).sum() / sg ** 2) * uv)
+
+    for name, fn in dict(sn_layers=sn_layers, spectral_norm=spectral_norm, spectral_norm_bwd=spectral_norm_bwd, view=lambda t, c0=0, C=None: _View(t, c0, t.shape[1] - c0 if C is None else C),
                          disc_patches_k4s2=patches, disc_fold_k4s2=fold, gemm_tn=gemm_tn, gemm_tn_lrelu=gemm_tn_lrelu,
                          view_lrelu=view_lrelu, view_lrelu_mask=view_lrelu_mask, conv_in1_fwd=conv_in1_fwd,
                          conv_in1_wgrad=conv_in1_wgrad, conv_out1_fwd=conv_out1_fwd, conv_out1_bwd=conv_out1_bwd,
@@ -166,7 +196,7 @@ def test_engine_host_logic_reproduces_the_oracle_in_fp32(engine, B, H, W):
         return out.detach(), [xs.grad] + [w.grad for w in wl]
 
     o_ref, g_ref = run(unet_discriminator_forward)
-    o_my, g_my = run(lambda xs, wl: engine.UNetDiscriminatorFunction.apply(xs, *wl))
+    o_my, g_my = run(lambda xs, wl: engine.UNetDiscriminatorFunction.apply(xs, None, *wl))
     assert rel_l2(o_my, o_ref) < 1e-5
     for i, (a, b) in enumerate(zip(g_my, g_ref)):
         assert a.shape == b.shape and rel_l2(a, b) < 1e-4, (i, rel_l2(a, b))
@@ -176,15 +206,48 @@ def test_engine_returns_only_the_requested_gradients(engine):
     ws = _weights()
     x = torch.rand(1, 1, 32, 32)
     xs = x.clone().requires_grad_(True)
-    out = engine.UNetDiscriminatorFunction.apply(xs, *ws)          # G step: frozen parameters
+    out = engine.UNetDiscriminatorFunction.apply(xs, None, *ws)          # G step: frozen parameters
     out.mean().backward()
     assert xs.grad is not None and xs.grad.abs().max() > 0
     wl = [w.clone().requires_grad_(True) for w in ws]
-    engine.UNetDiscriminatorFunction.apply(x, *wl).mean().backward()   # D step: detached image
+    engine.UNetDiscriminatorFunction.apply(x, None, *wl).mean().backward()   # D step: detached image
     assert all(w.grad is not None and w.grad.shape == w.shape for w in wl)
-    assert not engine.UNetDiscriminatorFunction.apply(x, *ws).requires_grad
+    assert not engine.UNetDiscriminatorFunction.apply(x, None, *ws).requires_grad
     with pytest.raises(Exception):
-        engine.UNetDiscriminatorFunction.apply(torch.rand(1, 1, 48, 64), *ws)
+        engine.UNetDiscriminatorFunction.apply(torch.rand(1, 1, 48, 64), None, *ws)
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_spectral_norm_path_matches_the_hook_driven_oracle_module(engine, training):
+    """weight_orig / weight_u / weight_v in, as gan.UNetDiscriminatorSN.forward passes them: logits, weight_orig gradients
+    and the in-place buffer update equal the oracle module driven by torch.nn.utils.spectral_norm's own hook — across TWO
+    forwards before the backward (the D step runs D(hr) and D(sr) first: the second power iteration must not disturb the
+    first forward's backward)."""
+    from oracle.discriminator_oracle import UNetDiscriminatorSN as OraD
+    torch.manual_seed(3)
+    ora, twin = OraD(1, 64), OraD(1, 64)
+    with torch.no_grad():   # a few power iterations first: with the random initial u / v, sigma is ~1e-3 per layer and the
+        for _ in range(3):  # logits of the 12-layer stack overflow any meaningful comparison
+            ora(torch.rand(1, 1, 32, 32))
+    twin.load_state_dict(ora.state_dict())
+    ora.train(training); twin.train(training)
+    convs = twin.convs()
+    x1, x2 = torch.rand(1, 1, 32, 32), torch.rand(1, 1, 32, 32)
+
+    def mine(x):
+        sn = dict(u=[m.weight_u for m in convs], v=[m.weight_v for m in convs], training=training, eps=1e-12)
+        return engine.UNetDiscriminatorFunction.apply(x, sn, *[m.weight_orig for m in convs])
+
+    a1, a2 = mine(x1), mine(x2)
+    b1, b2 = ora(x1), ora(x2)
+    assert rel_l2(a1, b1) < 1e-5 and rel_l2(a2, b2) < 1e-5
+    for k, v in ora.state_dict().items():
+        if k.endswith("weight_u") or k.endswith("weight_v"):
+            assert rel_l2(twin.state_dict()[k], v) < 1e-5, k
+    (a1.mean() + 2 * a2.mean()).backward()
+    (b1.mean() + 2 * b2.mean()).backward()
+    for (n, p), (_, q) in zip(twin.named_parameters(), ora.named_parameters()):
+        assert p.grad is not None and rel_l2(p.grad, q.grad) < 2e-4, (n, rel_l2(p.grad, q.grad))
 
 
 def test_public_entry_refuses_cpu_tensors():

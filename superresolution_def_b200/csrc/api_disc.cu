@@ -119,7 +119,7 @@ extern "C" int srk_disc_wgrad4(int T, int R, int Cb, const void* A, int lda, con
     const int cb = (Cb - c0) < 256 ? (Cb - c0) : 256;
     int rc = gemm_wgrad_partials(T, Ca, cb, A, lda, static_cast<const __nv_bfloat16*>(B) + c0, ldb, ws, splits, stream_);
     if (rc) return rc;
-    disc_unpack_wgrad4_kernel<<<stream_grid((long long)R * cb), 256, 0, stream>>>(ws, splits, (long long)ca_pad * cb, R, cb, c0, dw);
+    disc_unpack_wgrad4_kernel<<<stream_grid(4LL * R * cb), 256, 0, stream>>>(ws, splits, (long long)ca_pad * cb, R, cb, c0, dw);
     SRK_LAUNCHED(1);
   }
   SRK_CUDA_OK(cudaGetLastError());

@@ -207,21 +207,24 @@ static __global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_b
 // contiguous output bytes; across the warp c is the fast index, so the partial reads are contiguous.
 static __global__ void __launch_bounds__(256) disc_unpack_wgrad4_kernel(const float* __restrict__ part, int splits, long long split_stride,
                                                                         int R, int cb, int c0, float* __restrict__ dw) {
-  const long long total = (long long)R * cb;
+  // one thread per (c, rr, group of four taps): c is the fast index (contiguous partial reads), four times the threads of a
+  // (c, rr) mapping — the first version ran 64-512 blocks with 16 x splits dependent-latency loads each (6-17 % of DRAM
+  // throughput under ncu)
+  const long long total = 4LL * R * cb;
+  const long long tap_stride = (long long)R * cb;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = int(i % cb);
-    const int rr = int(i / cb);
-    float acc[16];
-#pragma unroll
-    for (int t = 0; t < 16; ++t) acc[t] = 0.f;
+    const long long t = i / cb;
+    const int rr = int(t % R);
+    const int q = int(t / R);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* p0 = part + (long long)(4 * q) * tap_stride + (long long)rr * cb + c;
     for (int s = 0; s < splits; ++s) {
-      const float* ps = part + s * split_stride + (long long)rr * cb + c;
+      const float* ps = p0 + s * split_stride;
 #pragma unroll
-      for (int t = 0; t < 16; ++t) acc[t] += ps[(long long)t * R * cb];
+      for (int k = 0; k < 4; ++k) acc[k] += ps[k * tap_stride];
     }
-    float4* dst = reinterpret_cast<float4*>(dw + ((long long)(c0 + c) * R + rr) * 16);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+    *reinterpret_cast<float4*>(dw + ((long long)(c0 + c) * R + rr) * 16 + 4 * q) = make_float4(acc[0], acc[1], acc[2], acc[3]);
   }
 }
 

@@ -348,6 +348,12 @@ long long srk_disc_wgrad4_ws_floats(int T, int R, int Cb);
 /* y = leaky_relu(y, slope) in place on a view (nn.LeakyReLU(0.2, inplace=True) after the 1 -> nf convolution, :49-50) */
 int srk_view_lrelu(const SrkView* y, long long npix, float slope, void* stream);
 
+/* F.interpolate(scale_factor=2, mode='bilinear', align_corners=False) on NHWC views (models/discriminator_hat.py:31,36,41):
+ * y [B,2H,2W,C] = resize(x + s), s optional (the skip connection added just before the resize, :35,:40); and its adjoint
+ * dx [B,H,W,C] from dy [B,2H,2W,C] (gather form, deterministic). */
+int srk_bilinear2x_fwd(const SrkView* x, const SrkView* s, const SrkView* y, int B, int H, int W, void* stream);
+int srk_bilinear2x_bwd(const SrkView* dy, const SrkView* dx, int B, int H, int W, void* stream);
+
 /* torch.nn.utils.spectral_norm (discriminator_swin.py:10,25,49-52,67-69; torch/nn/utils/spectral_norm.py) on the weight
  * W [A][B][KK] fp32 (KK = kh*kw) seen as the matrix Wm [U][V]:  dim 0 (nn.Conv2d): U = A, V = B*KK;  dim 1
  * (nn.ConvTranspose2d): U = B, V = A*KK.   power_iteration != 0 (module.training):  v <- normalize(Wm^T u),

@@ -110,3 +110,71 @@ class UNetDiscriminatorSN(nn.Module):
         d = self.up3(d, x1)
         d = self.up4(d, x0)
         return self.final_conv(d)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# models/discriminator_hat.py:8-49 (the discriminator of train_hat.py): functional restatement on normalised weights and the
+# module form.  Pinned by tests/test_oracle_vs_reference.py::test_hat_discriminator_oracle_equals_the_reference_module
+# (the reference file imported unmodified through tools/ref_shim.py, which supplies basicsr's arithmetic-free registry).
+# ----------------------------------------------------------------------------------------------------------------------
+def unet_discriminator_hat_forward(x, w, b0, b9, skip=True):
+    """w = conv0 .. conv9 weights (conv1 .. conv8 normalised), b0 / b9 the biases of the two plain convolutions."""
+    lr = lambda t: F.leaky_relu(t, SLOPE)
+    up = lambda t: F.interpolate(t, scale_factor=2, mode="bilinear", align_corners=False)
+    x0 = lr(F.conv2d(x, w[0], b0, 1, 1))          # :26
+    x1 = lr(F.conv2d(x0, w[1], None, 2, 1))
+    x2 = lr(F.conv2d(x1, w[2], None, 2, 1))
+    x3 = lr(F.conv2d(x2, w[3], None, 2, 1))       # :29
+    x4 = lr(F.conv2d(up(x3), w[4], None, 1, 1))   # :31-32
+    if skip:
+        x4 = x4 + x2
+    x5 = lr(F.conv2d(up(x4), w[5], None, 1, 1))   # :36-37
+    if skip:
+        x5 = x5 + x1
+    x6 = lr(F.conv2d(up(x5), w[6], None, 1, 1))   # :41-42
+    if skip:
+        x6 = x6 + x0
+    out = lr(F.conv2d(x6, w[7], None, 1, 1))      # :47
+    out = lr(F.conv2d(out, w[8], None, 1, 1))
+    return F.conv2d(out, w[9], b9, 1, 1)          # :49
+
+
+class UNetDiscriminatorSNHat(nn.Module):
+    def __init__(self, num_in_ch, num_feat=64, skip_connection=True):
+        super().__init__()
+        self.skip_connection = skip_connection
+        norm = spectral_norm
+        self.conv0 = nn.Conv2d(num_in_ch, num_feat, kernel_size=3, stride=1, padding=1)
+        self.conv1 = norm(nn.Conv2d(num_feat, num_feat * 2, 4, 2, 1, bias=False))
+        self.conv2 = norm(nn.Conv2d(num_feat * 2, num_feat * 4, 4, 2, 1, bias=False))
+        self.conv3 = norm(nn.Conv2d(num_feat * 4, num_feat * 8, 4, 2, 1, bias=False))
+        self.conv4 = norm(nn.Conv2d(num_feat * 8, num_feat * 4, 3, 1, 1, bias=False))
+        self.conv5 = norm(nn.Conv2d(num_feat * 4, num_feat * 2, 3, 1, 1, bias=False))
+        self.conv6 = norm(nn.Conv2d(num_feat * 2, num_feat, 3, 1, 1, bias=False))
+        self.conv7 = norm(nn.Conv2d(num_feat, num_feat, 3, 1, 1, bias=False))
+        self.conv8 = norm(nn.Conv2d(num_feat, num_feat, 3, 1, 1, bias=False))
+        self.conv9 = nn.Conv2d(num_feat, 1, 3, 1, 1)
+
+    def convs(self):
+        return [self.conv0, self.conv1, self.conv2, self.conv3, self.conv4, self.conv5, self.conv6, self.conv7, self.conv8,
+                self.conv9]
+
+    def forward(self, x):
+        lr = lambda t: F.leaky_relu(t, negative_slope=SLOPE, inplace=True)
+        up = lambda t: F.interpolate(t, scale_factor=2, mode="bilinear", align_corners=False)
+        x0 = lr(self.conv0(x))
+        x1 = lr(self.conv1(x0))
+        x2 = lr(self.conv2(x1))
+        x3 = lr(self.conv3(x2))
+        x4 = lr(self.conv4(up(x3)))
+        if self.skip_connection:
+            x4 = x4 + x2
+        x5 = lr(self.conv5(up(x4)))
+        if self.skip_connection:
+            x5 = x5 + x1
+        x6 = lr(self.conv6(up(x5)))
+        if self.skip_connection:
+            x6 = x6 + x0
+        out = lr(self.conv7(x6))
+        out = lr(self.conv8(out))
+        return self.conv9(out)

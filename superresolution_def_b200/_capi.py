@@ -681,3 +681,16 @@ def spectral_norm_bwd(layers, dw_sn, dw, device):
         a[i], b[i] = _ptr(dw_sn[i]), _ptr(dw[i])
     ws = _ws(int(lib.srk_spectral_norm_ws_floats()), device)
     _check(_spectral_norm_bwd(layers, n, a, b, _ptr(ws), _stream()), "srk_spectral_norm_bwd")
+
+
+_bilinear2x_fwd = _sig("srk_bilinear2x_fwd", [POINTER(SrkView), POINTER(SrkView), POINTER(SrkView), c_int, c_int, c_int, c_void_p])
+_bilinear2x_bwd = _sig("srk_bilinear2x_bwd", [POINTER(SrkView), POINTER(SrkView), c_int, c_int, c_int, c_void_p])
+
+
+def bilinear2x_fwd(x: SrkView, s: SrkView | None, y: SrkView, B, H, W):
+    """y [B,2H,2W,C] = bilinear x2 (align_corners=False) of (x + s) on NHWC views."""
+    _check(_bilinear2x_fwd(_vref(x), _vref(s), _vref(y), B, H, W, _stream()), "srk_bilinear2x_fwd")
+
+
+def bilinear2x_bwd(dy: SrkView, dx: SrkView, B, H, W):
+    _check(_bilinear2x_bwd(_vref(dy), _vref(dx), B, H, W, _stream()), "srk_bilinear2x_bwd")

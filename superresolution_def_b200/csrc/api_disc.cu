@@ -197,3 +197,35 @@ extern "C" int srk_spectral_norm_bwd(const SrkSnLayer* layers, int n, const floa
   SRK_CUDA_OK(cudaGetLastError());
   return SRK_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// models/discriminator_hat.py: bilinear x2 resize between the decoder's 3x3 convolutions
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int srk_bilinear2x_fwd(const SrkView* x, const SrkView* s, const SrkView* y, int B, int H, int W, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc;
+  if ((rc = check_view(x, "bilinear2x_fwd: x view")) || (rc = check_view(y, "bilinear2x_fwd: y view"))) return rc;
+  if (s && ((rc = check_view(s, "bilinear2x_fwd: s view")) || s->C != x->C)) return rc ? rc : fail(SRK_ERR_ARG, "bilinear2x_fwd: s and x differ in channels");
+  if (x->C != y->C || B <= 0 || H <= 0 || W <= 0) return fail(SRK_ERR_ARG, "bilinear2x_fwd: shape");
+  const long long vectors = (long long)B * 4 * H * W * (x->C / 8);
+  bilinear2x_fwd_kernel<<<stream_grid(vectors), 256, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(x->ptr), x->pitch, s ? static_cast<const __nv_bfloat16*>(s->ptr) : nullptr, s ? s->pitch : 0,
+      static_cast<__nv_bfloat16*>(const_cast<void*>(y->ptr)), y->pitch, B, H, W, x->C);
+  SRK_LAUNCHED(1);
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+extern "C" int srk_bilinear2x_bwd(const SrkView* dy, const SrkView* dx, int B, int H, int W, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc;
+  if ((rc = check_view(dy, "bilinear2x_bwd: dy view")) || (rc = check_view(dx, "bilinear2x_bwd: dx view"))) return rc;
+  if (dx->C != dy->C || B <= 0 || H <= 0 || W <= 0) return fail(SRK_ERR_ARG, "bilinear2x_bwd: shape");
+  const long long vectors = (long long)B * H * W * (dx->C / 8);
+  bilinear2x_bwd_kernel<<<stream_grid(vectors), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(dy->ptr), dy->pitch,
+                                                                 static_cast<__nv_bfloat16*>(const_cast<void*>(dx->ptr)), dx->pitch, B, H, W,
+                                                                 dx->C);
+  SRK_LAUNCHED(1);
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}

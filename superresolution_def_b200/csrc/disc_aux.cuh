@@ -229,3 +229,99 @@ static __global__ void __launch_bounds__(256) disc_unpack_wgrad4_kernel(const fl
 }
 
 }  // namespace srk
+
+namespace srk {
+
+// F.interpolate(scale_factor=2, mode='bilinear', align_corners=False) on NHWC bf16 (models/discriminator_hat.py:31,36,41):
+// output row Y reads input rows (i0, i1) with weights (w0, 1 - w0):  src = Y/2 - 0.25 clamped at 0, i1 clamped at H-1, i.e.
+//   Y = 2i:   0.25 x[max(i-1, 0)] + 0.75 x[i]          Y = 2i+1:   0.75 x[i] + 0.25 x[min(i+1, H-1)]
+__device__ __forceinline__ void bil2_taps(int Y, int H, int& i0, int& i1, float& w0) {
+  const int i = Y >> 1;
+  if (Y & 1) { i0 = i; i1 = (i + 1 < H) ? i + 1 : H - 1; w0 = 0.75f; }
+  else { i0 = (i > 0) ? i - 1 : 0; i1 = i; w0 = 0.25f; }
+}
+// weight of input index i in output index Y (0 when Y is outside [0, 2H) or does not read i)
+__device__ __forceinline__ float bil2_weight(int Y, int i, int H) {
+  if (Y < 0 || Y >= 2 * H) return 0.f;
+  int i0, i1;
+  float w0;
+  bil2_taps(Y, H, i0, i1, w0);
+  return (i0 == i ? w0 : 0.f) + (i1 == i ? 1.f - w0 : 0.f);
+}
+
+// y [B,2H,2W,C] = bilinear2x(x + s)   (s optional: the skip connection added before the resize, discriminator_hat.py:35,40)
+static __global__ void __launch_bounds__(256) bilinear2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16* __restrict__ s,
+                                                                    int lds, __nv_bfloat16* __restrict__ y, int ldy, int B, int H, int W, int C) {
+  const unsigned groups = unsigned(C >> 3);
+  const unsigned Wo = 2u * W, Ho = 2u * H;
+  const unsigned long long total = (unsigned long long)B * Ho * Wo * groups;
+  for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned cg = unsigned(idx % groups);
+    const unsigned long long pix = idx / groups;
+    const int X = int(pix % Wo);
+    const unsigned long long rowi = pix / Wo;
+    const int Y = int(rowi % Ho);
+    const long long b = (long long)(rowi / Ho);
+    int y0, y1, x0, x1;
+    float wy, wx;
+    bil2_taps(Y, H, y0, y1, wy);
+    bil2_taps(X, W, x0, x1, wx);
+    const long long base = b * H * W;
+    const long long p[4] = {base + (long long)y0 * W + x0, base + (long long)y0 * W + x1, base + (long long)y1 * W + x0,
+                            base + (long long)y1 * W + x1};
+    const float wt[4] = {wy * wx, wy * (1.f - wx), (1.f - wy) * wx, (1.f - wy) * (1.f - wx)};
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float v[8];
+      bf16x8_to_f32(*reinterpret_cast<const uint4*>(x + p[k] * ldx + cg * 8), v);
+      if (s != nullptr) {
+        float sv[8];
+        bf16x8_to_f32(*reinterpret_cast<const uint4*>(s + p[k] * lds + cg * 8), sv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] += sv[e];
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = fmaf(wt[k], v[e], acc[e]);
+    }
+    *reinterpret_cast<uint4*>(y + (long long)pix * ldy + cg * 8) = f32_to_bf16x8(acc);
+  }
+}
+
+// dx [B,H,W,C] = adjoint of bilinear2x applied to dy [B,2H,2W,C]  (gather form: <= 4 x 4 output pixels read an input pixel)
+static __global__ void __launch_bounds__(256) bilinear2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, __nv_bfloat16* __restrict__ dx,
+                                                                    int lddx, int B, int H, int W, int C) {
+  const unsigned groups = unsigned(C >> 3);
+  const unsigned long long total = (unsigned long long)B * H * W * groups;
+  for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned cg = unsigned(idx % groups);
+    const unsigned long long pix = idx / groups;
+    const int j = int(pix % unsigned(W));
+    const unsigned long long rowi = pix / unsigned(W);
+    const int i = int(rowi % unsigned(H));
+    const long long b = (long long)(rowi / unsigned(H));
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int a = -1; a <= 2; ++a) {
+      const int Y = 2 * i + a;
+      const float wy = bil2_weight(Y, i, H);
+      if (wy == 0.f) continue;
+#pragma unroll
+      for (int c = -1; c <= 2; ++c) {
+        const int X = 2 * j + c;
+        const float wx = bil2_weight(X, j, W);
+        if (wx == 0.f) continue;
+        float v[8];
+        bf16x8_to_f32(*reinterpret_cast<const uint4*>(dy + ((b * 2 * H + Y) * 2 * W + X) * lddy + cg * 8), v);
+        const float wgt = wy * wx;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(wgt, v[e], acc[e]);
+      }
+    }
+    *reinterpret_cast<uint4*>(dx + (long long)pix * lddx + cg * 8) = f32_to_bf16x8(acc);
+  }
+}
+
+}  // namespace srk

@@ -252,3 +252,113 @@ def test_module_mirror_matches_oracle_module_train_mode():
     with torch.no_grad():
         assert rel_l2(mine(x), ora(x)) < 2e-2
     assert torch.equal(mine.conv1.model[0].weight_u, u0)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# models/discriminator_hat.py (the discriminator of train_hat.py)
+# ----------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,W,Ct,c0,C", [(2, 4, 4, 64, 0, 64), (1, 8, 16, 512, 256, 256), (3, 1, 2, 128, 0, 128)])
+def test_bilinear2x_kernels_match_interpolate(B, H, W, Ct, c0, C):
+    from superresolution_def_b200 import _capi as capi
+    x = _mk((B * H * W, Ct), seed=21).to(BF)
+    s = _mk((B * H * W, Ct), seed=22).to(BF)
+    for with_s in (False, True):
+        y = torch.zeros(B * 4 * H * W, C, device="cuda", dtype=BF)
+        capi.bilinear2x_fwd(capi.view(x, c0, C), capi.view(s, c0, C) if with_s else None, capi.view(y), B, H, W)
+        src = _nchw(x, B, H, W, c0, C) + (_nchw(s, B, H, W, c0, C) if with_s else 0)
+        want = F.interpolate(src, scale_factor=2, mode="bilinear", align_corners=False)
+        got = _nchw(y, B, 2 * H, 2 * W, 0, C)
+        assert rel_l2(got, want.to(BF)) < 2e-3 and max_abs(got, want) <= 2.0 ** -7 * want.abs().max().item(), with_s
+    dy = _mk((B * 4 * H * W, C), seed=23).to(BF)
+    dx = torch.zeros(B * H * W, Ct, device="cuda", dtype=BF)
+    capi.bilinear2x_bwd(capi.view(dy), capi.view(dx, c0, C), B, H, W)
+    z = torch.zeros(B, C, H, W, device="cuda", requires_grad=True)
+    F.interpolate(z, scale_factor=2, mode="bilinear", align_corners=False).backward(_nchw(dy, B, 2 * H, 2 * W, 0, C))
+    got = _nchw(dx, B, H, W, c0, C)
+    assert rel_l2(got, z.grad.to(BF)) < 2e-3 and max_abs(got, z.grad) <= 2.0 ** -7 * z.grad.abs().max().item()
+    if c0:
+        assert torch.all(dx[:, :c0] == 0)
+
+
+def _hat_weights(seed=0):
+    nf = 64
+    shapes = [(nf, 1, 3, 3), (2 * nf, nf, 4, 4), (4 * nf, 2 * nf, 4, 4), (8 * nf, 4 * nf, 4, 4), (4 * nf, 8 * nf, 3, 3),
+              (2 * nf, 4 * nf, 3, 3), (nf, 2 * nf, 3, 3), (nf, nf, 3, 3), (nf, nf, 3, 3), (1, nf, 3, 3)]
+    ws = [_mk(s, 1.6 * (s[1] * s[2] * s[3]) ** -0.5, seed=seed + i) for i, s in enumerate(shapes)]
+    return ws, _mk((nf,), 0.2, seed=seed + 20), _mk((1,), 0.2, seed=seed + 21)
+
+
+@pytest.mark.parametrize("B,H,W,skip", [(2, 64, 64, True), (1, 32, 128, False), (1, 512, 512, True)])
+def test_hat_discriminator_matches_oracle(B, H, W, skip):
+    """forward + image gradient + all weight and bias gradients of models/discriminator_hat.py's network; (1, 512, 512) is
+    the shape train_hat.py runs.  Same yardstick as the swin variant: the ATen sequence under bf16 autocast."""
+    from oracle.discriminator_oracle import unet_discriminator_hat_forward
+    from superresolution_def_b200.disc_engine import unet_discriminator_hat
+    ws, b0, b9 = _hat_weights()
+    x = torch.rand(B, 1, H, W, generator=torch.Generator().manual_seed(98)).cuda()
+    dout = _mk((B, 1, H, W), seed=51)
+
+    def run(fn, autocast):
+        xs = x.clone().requires_grad_(True)
+        wl = [w.clone().requires_grad_(True) for w in ws]
+        bl = [b0.clone().requires_grad_(True), b9.clone().requires_grad_(True)]
+        with torch.autocast("cuda", dtype=BF, enabled=autocast):
+            out = fn(xs, wl, bl[0], bl[1], skip)
+        out.float().backward(dout)
+        return out.detach().float(), [xs.grad, bl[0].grad, bl[1].grad] + [w.grad for w in wl]
+
+    o_ref, g_ref = run(unet_discriminator_hat_forward, False)
+    o_ac, g_ac = run(unet_discriminator_hat_forward, True)
+    o_my, g_my = run(unet_discriminator_hat, False)
+    assert o_my.shape == o_ref.shape and o_my.dtype == torch.float32
+    e_out, e_ac = rel_l2(o_my, o_ref), rel_l2(o_ac, o_ref)
+    print(f"hat logits rel-L2 {e_out:.4f} (autocast oracle {e_ac:.4f}) max-abs {max_abs(o_my, o_ref):.4f} on {o_ref.abs().max().item():.3f}")
+    assert e_out < 2e-2 and e_out < 1.6 * e_ac + 5e-3
+    names = ["x", "conv0.bias", "conv9.bias"] + [f"conv{i}" for i in range(10)]
+    bad = []
+    for n, a, b, r in zip(names, g_my, g_ac, g_ref):
+        assert a is not None and a.shape == r.shape and a.dtype == r.dtype, n
+        ea, eb = rel_l2(a, r), rel_l2(b, r)
+        ma, mb, top = max_abs(a, r), max_abs(b, r), r.abs().max().item()
+        print(f"  grad {n:10s} rel-L2 {ea:.4f} (autocast oracle {eb:.4f})  max-abs {ma:.3e} ({mb:.3e}) on {top:.3e}")
+        if not (ea < 2.0 * eb + 5e-3 and ma < 2.0 * mb + 5e-3 * top):
+            bad.append((n, ea, eb, ma, mb))
+    assert not bad, bad
+
+
+def test_hat_module_mirror_matches_oracle_module():
+    from oracle.discriminator_oracle import UNetDiscriminatorSNHat as OraD
+    from superresolution_def_b200.discriminator_hat import UNetDiscriminatorSN
+    torch.manual_seed(6)
+    ora = OraD(1, 64).cuda().train()
+    ora_ac = OraD(1, 64).cuda().train()
+    mine = UNetDiscriminatorSN(1, 64).cuda().train()
+    x = torch.rand(1, 1, 128, 128, device="cuda")
+    with torch.no_grad():
+        for _ in range(3):
+            ora(x)
+    mine.load_state_dict(ora.state_dict(), strict=True)
+    ora_ac.load_state_dict(ora.state_dict(), strict=True)
+    xs = x.clone().requires_grad_(True)
+    a, b = mine(xs), ora(x)
+    with torch.autocast("cuda", dtype=BF):
+        c = ora_ac(x)
+    for k, v in ora.state_dict().items():
+        if k.endswith("weight_u") or k.endswith("weight_v"):
+            assert rel_l2(mine.state_dict()[k], v) < 1e-5, k
+    assert a.shape == b.shape and rel_l2(a, b) < 2e-2 and rel_l2(a, b) < 1.6 * rel_l2(c, b) + 5e-3, (rel_l2(a, b), rel_l2(c, b))
+    g = torch.randn_like(b)
+    a.backward(g); b.backward(g); c.float().backward(g)
+    assert xs.grad is not None and xs.grad.shape == x.shape
+    bad = []
+    for (n, p), (_, q), (_, r) in zip(mine.named_parameters(), ora.named_parameters(), ora_ac.named_parameters()):
+        assert p.grad is not None and p.grad.shape == q.grad.shape, n
+        e_my, e_ac = rel_l2(p.grad, q.grad), rel_l2(r.grad, q.grad)
+        if not e_my < 2.0 * e_ac + 5e-3:
+            bad.append((n, e_my, e_ac))
+    assert not bad, bad
+    for p in mine.parameters():      # G step of train_hat.py:223-241: frozen discriminator, gradient to the image only
+        p.requires_grad = False
+    xs2 = x.clone().requires_grad_(True)
+    mine(xs2).mean().backward()
+    assert xs2.grad is not None and xs2.grad.abs().max() > 0 and all(p.grad is not None for p in mine.parameters())

@@ -194,3 +194,39 @@ def test_discriminator_oracle_equals_the_reference_module():
         if k.endswith("weight_u"):
             assert torch.equal(mine.state_dict()[k], ref.state_dict()[k]), k
     assert torch.equal(unet_discriminator_forward(x, w_mine), b)
+
+
+def test_hat_discriminator_oracle_equals_the_reference_module():
+    """oracle.discriminator_oracle.UNetDiscriminatorSNHat vs models/discriminator_hat.py:8-49 imported unmodified (basicsr's
+    registry decorator supplied by tools/ref_shim.py), and the product mirror's schema: same state_dict keys / shapes /
+    order, strict load in every direction, identical logits and gradients on CPU in eval and train mode, with and without
+    the skip connections; the functional oracle equals the module form on the hook-normalised weights."""
+    from tools import ref_shim
+    ref_shim.install()
+    from models.discriminator_hat import UNetDiscriminatorSN as RefD
+    from oracle.discriminator_oracle import UNetDiscriminatorSNHat as OraD, unet_discriminator_hat_forward
+    from superresolution_def_b200.discriminator_hat import UNetDiscriminatorSN
+    for skip in (True, False):
+        torch.manual_seed(0)
+        ref = RefD(num_in_ch=1, num_feat=16, skip_connection=skip)
+        ora = OraD(num_in_ch=1, num_feat=16, skip_connection=skip)
+        mine = UNetDiscriminatorSN(num_in_ch=1, num_feat=16, skip_connection=skip)
+        sd = ref.state_dict()
+        for m in (ora, mine):
+            assert [(k, tuple(v.shape)) for k, v in sd.items()] == [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+            assert [n for n, _ in ref.named_parameters()] == [n for n, _ in m.named_parameters()]
+            m.load_state_dict(sd, strict=True)
+            ref.load_state_dict(m.state_dict(), strict=True)
+        x = torch.rand(2, 1, 32, 32)
+        ref.eval(); ora.eval()
+        with torch.no_grad():
+            want = ref(x)
+            assert torch.equal(ora(x), want)
+            w = [c.weight for c in ora.convs()]   # after the forward: the hook-normalised weights of conv1 .. conv8
+            assert torch.equal(unet_discriminator_hat_forward(x, w, ora.conv0.bias, ora.conv9.bias, skip), want)
+        ref.train(); ora.train()
+        a, b = ora(x), ref(x)
+        assert torch.equal(a, b)
+        a.mean().backward(); b.mean().backward()
+        for (n, p), (_, q) in zip(ora.named_parameters(), ref.named_parameters()):
+            assert torch.equal(p.grad, q.grad), n

@@ -25,6 +25,8 @@ def main():
     from oracle.discriminator_oracle import UNetDiscriminatorSN as OraD
     from superresolution_def_b200.gan import UNetDiscriminatorSN
     from superresolution_def_b200 import _capi as capi
+    if len(sys.argv) > 1 and sys.argv[1] == "hat":
+        return main_hat()
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 2
     torch.manual_seed(0)
     mine = UNetDiscriminatorSN(1, 64).cuda().train()
@@ -92,6 +94,47 @@ def main():
     ora_cl.load_state_dict(mine.state_dict())
     steps(ora_cl, "aten_fp16_autocast_channels_last", True)
     gpu_busy(ora_cl, "aten_fp16_autocast_channels_last")
+    print(json.dumps(res))
+
+
+def main_hat():
+    """models/discriminator_hat.py at train_hat.py's shape (BATCH_SIZE = 1, 512^2, fp32 training script: no autocast)."""
+    from oracle.discriminator_oracle import UNetDiscriminatorSNHat as OraD
+    from superresolution_def_b200.discriminator_hat import UNetDiscriminatorSN
+    torch.manual_seed(0)
+    mine = UNetDiscriminatorSN(1, 64).cuda().train()
+    x = torch.rand(1, 1, 512, 512, device="cuda")
+    res = {"shape": [1, 1, 512, 512], "variant": "models/discriminator_hat.py"}
+
+    def steps(net, tag, autocast):
+        def d_step():
+            for p in net.parameters():
+                p.requires_grad = True
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                out = net(x)
+            out.float().mean().backward()
+            net.zero_grad(set_to_none=True)
+
+        xs = x.clone().requires_grad_(True)
+
+        def g_step():
+            for p in net.parameters():
+                p.requires_grad = False
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                out = net(xs)
+            out.float().mean().backward()
+            xs.grad = None
+
+        res[tag] = {"d_step_ms": _time(d_step), "g_step_ms": _time(g_step)}
+
+    steps(mine, "libsrk", False)
+    ora = OraD(1, 64).cuda().train()
+    ora.load_state_dict(mine.state_dict())
+    steps(ora, "aten_fp32_as_the_script", False)
+    steps(ora, "aten_bf16_autocast", True)
+    ora_cl = OraD(1, 64).cuda().train().to(memory_format=torch.channels_last)
+    ora_cl.load_state_dict(mine.state_dict())
+    steps(ora_cl, "aten_bf16_autocast_channels_last", True)
     print(json.dumps(res))
 
 

@@ -83,7 +83,10 @@ def _check(rc: int, what: str) -> None:
 
 
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    # the raw handle of torch's current stream; torch.cuda.current_stream().cuda_stream builds a Stream object per call
+    # (device-index resolution, lazy-init and availability checks: ~26 % of the host time of an eager discriminator step,
+    # tools/gpu_disc_hostprof.py), and every libsrk call needs it
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
 def _ptr(t):

@@ -19,6 +19,7 @@
 //   S   [128 x 128] = Q_hf K_part^T, K = 32 (two K = 16 steps; the two heads are +64 B sub-ranges of the same swizzled rows).
 //   P   per 64-key chunk: p = 2^(s*log2e + bias' + mask' - m'), m' = (row max of s)*log2e + (max of the bias table) >= the
 //                    true row maximum of the part, so p <= 1 without a second pass over the bias; bf16 [128 x 64] -> smem.
+//                    (the row max is taken over s*log2e + mask': the mask is constant per 64-key chunk.)
 //   O   [128 x 64] += P_chunk V_chunk (V as an MN-major operand straight from its token-major boxes, both heads'
 //                    channels; the 32 columns of the lane's head are read back).  O overwrites columns 0..63 of the lane's
 //                    S buffer: chunk 0 of S is dead once its P chunk has been handed over.
@@ -284,9 +285,13 @@ win_attn_tc16_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const Attn16
           mbar_wait(s_full(l), uint32_t(n_run) & 1u);
           tc_fence_after();
           // ---- pass 1: row maximum of the raw logits -> an upper bound of the biased, masked row maximum
-          float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;   // four independent chains
+          // (the shift mask is constant over a 64-key chunk, so it enters the bound per chunk: without it a row whose largest
+          //  raw logit sits on a masked key would be normalised against a maximum 100 too high, and with logits spread
+          //  over hundreds the whole row underflows: sum = 0, 0 * inf = NaN in the output)
+          float mrow = -INFINITY;
 #pragma unroll 1
           for (int jj = 0; jj < G::PCH; ++jj) {
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;   // four independent chains
             uint32_t sv[64];
             tmem_ld_x64(tm_lane + uint32_t(jj * 64), sv);
             tmem_ld_wait();
@@ -297,8 +302,14 @@ win_attn_tc16_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const Attn16
               mx2 = fmaxf(mx2, fmaxf(__uint_as_float(sv[e + 4]), __uint_as_float(sv[e + 5])));
               mx3 = fmaxf(mx3, fmaxf(__uint_as_float(sv[e + 6]), __uint_as_float(sv[e + 7])));
             }
+            float mqc = 0.f;
+            if (MODE == MODE_SELF) {
+              const int cj = part * G::PCH + jj;
+              mqc = (cj == 0) ? mq[0] : (cj == 1) ? mq[1] : (cj == 2) ? mq[2] : mq[3];
+            }
+            mrow = fmaxf(mrow, fmaf(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)), kLog2e, mqc));
           }
-          const float ml2 = fmaf(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)), kLog2e, tmax);
+          const float ml2 = mrow + tmax;
           // ---- pass 2: P chunk by chunk
           float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
 #pragma unroll 1

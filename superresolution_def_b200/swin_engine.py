@@ -63,10 +63,21 @@ class BlockCfg:
         return cfg
 
 
+_BLOCK_PARAM_PATHS = tuple(tuple(k.split(".")) for k in BLOCK_PARAM_KEYS)
+
+
 def block_params_of(block: torch.nn.Module) -> list[torch.Tensor]:
-    """The 13 parameters of a SwinTransformerBlock-shaped module, in the C ABI's order."""
-    sd = dict(block.named_parameters())
-    return [sd[k] for k in BLOCK_PARAM_KEYS]
+    """The 13 parameters of a SwinTransformerBlock-shaped module, in the C ABI's order, resolved by attribute path
+    (`dict(block.named_parameters())` walks the module tree in Python on every forward of every block).  Measured with
+    tools/gpu_swinir_hostprof.py: the eager step at micro-batch 2 is device-bound (12.5 ms of kernels behind 11.6 ms of
+    host time), so this only matters for the launch queue's slack, not for the step time."""
+    out = []
+    for path in _BLOCK_PARAM_PATHS:
+        o = block
+        for a in path:
+            o = getattr(o, a)
+        out.append(o)
+    return out
 
 
 class _WeightCache:

@@ -58,7 +58,11 @@ class ChannelAttention(nn.Module):
                                        nn.Sigmoid())
 
     def forward(self, x):
-        raise capi.SrkError("ChannelAttention runs fused inside CAB / HAB (srk_cab_se_fwd); call those instead")
+        """x: (B, C, H, W) -> x * attention(x) (:56-58).  Inside CAB / HAB the same kernels run fused on token-major data."""
+        if not x.is_cuda:
+            raise capi.SrkError("libsrk ChannelAttention runs on CUDA only")
+        a = self.attention
+        return heng.ChannelAttentionFunction.apply(x, a[1].weight, a[1].bias, a[3].weight, a[3].bias)
 
 
 class CAB(nn.Module):

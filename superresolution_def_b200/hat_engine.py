@@ -240,6 +240,49 @@ class LayerNormTokensFunction(torch.autograd.Function):
         return dx, dgamma, dbeta, None, None
 
 
+class ChannelAttentionFunction(torch.autograd.Function):
+    """Stand-alone ChannelAttention.forward on an NCHW tensor (hat_arch.py:40-58): x * sigmoid(W2 relu(W1 avgpool(x) + b1) + b2)
+    on the kernels of the fused path (srk_cab_se_fwd / _bwd with a zero shortcut and alpha = 1); the NCHW <-> token-major
+    packing is torch indexing.  Inside CAB / HAB the same kernels run without this detour."""
+
+    @staticmethod
+    def forward(ctx, x, s1w, s1b, s2w, s2b):
+        B, C, H, W = x.shape
+        if C >= 192:
+            raise capi.SrkError("libsrk ChannelAttention: fewer than 192 channels")
+        dev, T, Cp = x.device, B * H * W, 192
+        S = s1w.shape[0]
+        for t in (s1w, s1b, s2w, s2b):
+            eng._check_param(t)
+        xt = torch.zeros(T, Cp, device=dev, dtype=BF16)
+        xt[:, :C] = x.permute(0, 2, 3, 1).reshape(T, C).to(BF16)
+        pool = torch.empty(B, C, device=dev, dtype=torch.float32)
+        hidden = torch.empty(B, S, device=dev, dtype=torch.float32)
+        scale = torch.empty(B, C, device=dev, dtype=torch.float32)
+        zero = torch.zeros(T, Cp, device=dev, dtype=BF16)
+        out = torch.empty(T, Cp, device=dev, dtype=BF16)
+        capi.cab_se_fwd(xt, zero, B, H * W, C, S, s1w.detach(), s1b.detach(), s2w.detach(), s2b.detach(), 1.0, pool, hidden,
+                        scale, out)
+        ctx.saved = (xt, pool, hidden, scale)
+        ctx.meta = (B, C, H, W, S, x.dtype)
+        ctx.params = (s1w, s1b, s2w, s2b)
+        return out[:, :C].reshape(B, H, W, C).permute(0, 3, 1, 2).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xt, pool, hidden, scale = ctx.saved
+        B, C, H, W, S, dtype = ctx.meta
+        s1w, s1b, s2w, s2b = ctx.params
+        dev, T, Cp = dy.device, B * H * W, 192
+        g = torch.zeros(T, Cp, device=dev, dtype=BF16)
+        g[:, :C] = dy.permute(0, 2, 3, 1).reshape(T, C).to(BF16)
+        dxt = torch.empty(T, Cp, device=dev, dtype=BF16)
+        ds1w, ds1b, ds2w, ds2b = (torch.empty_like(t) for t in (s1w, s1b, s2w, s2b))
+        capi.cab_se_bwd(g, xt, B, H * W, C, S, s1w.detach(), s2w.detach(), 1.0, pool, hidden, scale, dxt, ds1w, ds1b, ds2w,
+                        ds2b)
+        return dxt[:, :C].reshape(B, H, W, C).permute(0, 3, 1, 2).to(dtype), ds1w, ds1b, ds2w, ds2b
+
+
 class CabFunction(torch.autograd.Function):
     """Stand-alone CAB.forward on an NCHW tensor (reference CAB / ChannelAttention, hat_arch.py:40-74): conv3x3 -> GELU ->
     conv3x3 -> x * sigmoid(W2 relu(W1 avgpool(x))).  Same kernels as the fused HAB path; only the NCHW <-> token-major

@@ -235,6 +235,25 @@ def test_hat_small_matches_oracle():
     assert not bad, bad
 
 
+def test_standalone_channel_attention_module():
+    """ChannelAttention.forward(x NCHW) on its own (reference hat_arch.py:40-58): output, input gradient and the four
+    squeeze / excite parameter gradients vs the oracle."""
+    from superresolution_def_b200.hat_arch import ChannelAttention
+    ho = _ho()
+    torch.manual_seed(21)
+    ca = randomize_(ChannelAttention(180, 30), seed=22).cuda()
+    x = torch.randn(2, 180, 16, 24, device="cuda")
+    xm, xr = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    sd = _sd_of(ca)
+    got, ref = ca(xm), ho.channel_attention(xr, sd, "")
+    assert got.shape == ref.shape and got.dtype == ref.dtype and rel_l2(got, ref) < OUT_TOL, rel_l2(got, ref)
+    w = torch.randn_like(ref)
+    (got * w).sum().backward(); (ref * w).sum().backward()
+    assert rel_l2(xm.grad, xr.grad) < GRAD_TOL, rel_l2(xm.grad, xr.grad)
+    bad = {n: round(rel_l2(p.grad, sd[n].grad), 4) for n, p in ca.named_parameters() if rel_l2(p.grad, sd[n].grad) > GRAD_TOL}
+    assert not bad, bad
+
+
 def test_standalone_cab_and_window_attention_modules():
     """CAB.forward(x NCHW) and HAT's WindowAttention.forward(x, rpi, mask=None) called on their own
     (reference hat_arch.py:61-74, :129-196): outputs + every gradient vs the oracle."""

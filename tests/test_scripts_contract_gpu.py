@@ -107,7 +107,8 @@ def test_hybrid_train_and_infer_like_train_hat_and_infer_hat(tmp_path, monkeypat
     checkpoint with 'module.' prefixes -> shape auto-detection -> strict load -> eval forward -> 16-bit TIFF."""
     import warnings
     from superresolution_def_b200.hybridmodels_hat import HybridHATRealESRGAN
-    from superresolution_def_b200.gan import UNetDiscriminatorSN, CombinedGANLoss, DiscriminatorLoss
+    from superresolution_def_b200.discriminator_hat import UNetDiscriminatorSN      # train_hat.py:26
+    from superresolution_def_b200.gan import CombinedGANLoss, DiscriminatorLoss
     from superresolution_def_b200.input_pipeline import save_as_tiff16, read_tiff_u16
     from superresolution_def_b200 import swin_engine as eng
     monkeypatch.setattr(eng, "_fp32_warned", False)

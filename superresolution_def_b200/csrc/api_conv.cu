@@ -280,7 +280,10 @@ extern "C" int srk_conv_in1_fwd(const float* x, const float* w, const float* bia
                                 int Cp, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const bool small = (long long)B * H * W * (Cp / 8) + (long long)num_sms() * 8 * 256 < (1LL << 32);
-  if (small)
+  if (small && W % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0)
+    conv_in1_fwd_x4_kernel<unsigned><<<num_sms() * 8, 256, Cp * 10 * sizeof(float), stream>>>(x, w, bias, static_cast<__nv_bfloat16*>(y),
+                                                                                          B, H, W, C, Cp);
+  else if (small)
     conv_in1_fwd_kernel<unsigned><<<num_sms() * 8, 256, Cp * 10 * sizeof(float), stream>>>(x, w, bias, static_cast<__nv_bfloat16*>(y),
                                                                                        B, H, W, C, Cp);
   else
@@ -295,10 +298,11 @@ extern "C" int srk_conv_in1_wgrad(const float* x, const void* dy, float* ws, flo
                                   int C, int Cp, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   // 8 pixels in flight per block at the generators' widths (Cp = 192 / 64 at 128^2); the discriminator's first layer
-  // (Cp = 64 at 512^2: 16x the pixels) gets 32 pixel lanes per block and four blocks per SM
+  // (Cp = 64 at 512^2: 16x the pixels) gets 16 pixel lanes per block and three (resident) blocks per SM
   const bool wide = Cp <= 64 && (long long)B * H * W >= (1 << 18);
-  const int grid = wide ? num_sms() * 4 : num_sms();
-  const int threads = (Cp / 8) * (wide ? 32 : 8);
+  // (130 registers per thread: 128-thread blocks keep three of them resident per SM)
+  const int grid = wide ? num_sms() * 3 : num_sms();   // one resident wave: the 80 shared-memory atomics per thread of the epilogue are paid once
+  const int threads = (Cp / 8) * (wide ? 16 : 8);
   if ((long long)B * H * W + (long long)grid * threads < (1LL << 32))
     conv_in1_wgrad_kernel<unsigned><<<grid, threads, Cp * 10 * sizeof(float), stream>>>(x, static_cast<const __nv_bfloat16*>(dy), ws,
                                                                                     B, H, W, Cp);
@@ -306,7 +310,7 @@ extern "C" int srk_conv_in1_wgrad(const float* x, const void* dy, float* ws, flo
     conv_in1_wgrad_kernel<unsigned long long><<<grid, threads, Cp * 10 * sizeof(float), stream>>>(
         x, static_cast<const __nv_bfloat16*>(dy), ws, B, H, W, Cp);
   SRK_LAUNCHED(1);
-  conv_in1_wgrad_finish_kernel<<<(C * 10 + 127) / 128, 128, 0, stream>>>(ws, grid, C, Cp, dw, db);
+  conv_in1_wgrad_finish_kernel<<<(C * 10 * 32 + 255) / 256, 256, 0, stream>>>(ws, grid, C, Cp, dw, db);
   SRK_LAUNCHED(1);
   SRK_CUDA_OK(cudaGetLastError());
   return SRK_OK;

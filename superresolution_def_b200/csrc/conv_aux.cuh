@@ -166,6 +166,70 @@ static __global__ void conv_in1_fwd_kernel(const float* __restrict__ x, const fl
   }
 }
 
+// Same arithmetic (bias first, taps in the same order: bit-identical results), four horizontally adjacent pixels per thread:
+// the 18 LDS.128 of the filter taps are paid once per four pixels instead of once per pixel, and the 3 x 6 input window is
+// three float4 + six scalar loads.  At 512^2 (the discriminators' first layer) the one-pixel kernel is bound by exactly
+// those shared-memory reads (87 us for a 67 MB output).  W % 4 == 0.
+template <typename Idx>
+static __global__ void __launch_bounds__(256) conv_in1_fwd_x4_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                     const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
+                                                                     int B, int H, int W, int C, int Cp) {
+  extern __shared__ __align__(16) float s_w[];  // [10][Cp]: 9 taps + bias, tap-major
+  for (int i = threadIdx.x; i < Cp * 10; i += blockDim.x) {
+    const int t = i / Cp, co = i % Cp;
+    s_w[i] = (co < C) ? (t < 9 ? w[co * 9 + t] : bias[co]) : 0.f;
+  }
+  __syncthreads();
+  const Idx groups = Idx(Cp / 8);
+  const Idx Wq = Idx(W / 4);
+  const Idx total = Idx(B) * H * Wq * groups;
+  for (Idx idx = Idx(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += Idx(gridDim.x) * blockDim.x) {
+    const int g = int(idx % groups);
+    const Idx q = idx / groups;
+    const Idx r = q / Wq;
+    const int xx0 = int(q - r * Wq) * 4, yy = int(r % Idx(H));
+    const long long img = (long long)(r / Idx(H)) * H * W;
+    float v[3][6];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int sy = yy + dy - 1;
+      if (sy >= 0 && sy < H) {
+        const float* row = x + img + (long long)sy * W + xx0;
+        const float4 m = *reinterpret_cast<const float4*>(row);
+        v[dy][0] = (xx0 > 0) ? row[-1] : 0.f;
+        v[dy][1] = m.x; v[dy][2] = m.y; v[dy][3] = m.z; v[dy][4] = m.w;
+        v[dy][5] = (xx0 + 4 < W) ? row[4] : 0.f;
+      } else {
+#pragma unroll
+        for (int dx = 0; dx < 6; ++dx) v[dy][dx] = 0.f;
+      }
+    }
+    float o[4][8];
+    {
+      const float4 b0 = *reinterpret_cast<const float4*>(s_w + 9 * Cp + g * 8), b1 = *reinterpret_cast<const float4*>(s_w + 9 * Cp + g * 8 + 4);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        o[p][0] = b0.x; o[p][1] = b0.y; o[p][2] = b0.z; o[p][3] = b0.w; o[p][4] = b1.x; o[p][5] = b1.y; o[p][6] = b1.z; o[p][7] = b1.w;
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float4 w0 = *reinterpret_cast<const float4*>(s_w + t * Cp + g * 8), w1 = *reinterpret_cast<const float4*>(s_w + t * Cp + g * 8 + 4);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const float xv = v[t / 3][t % 3 + p];
+        o[p][0] = fmaf(xv, w0.x, o[p][0]); o[p][1] = fmaf(xv, w0.y, o[p][1]); o[p][2] = fmaf(xv, w0.z, o[p][2]); o[p][3] = fmaf(xv, w0.w, o[p][3]);
+        o[p][4] = fmaf(xv, w1.x, o[p][4]); o[p][5] = fmaf(xv, w1.y, o[p][5]); o[p][6] = fmaf(xv, w1.z, o[p][6]); o[p][7] = fmaf(xv, w1.w, o[p][7]);
+      }
+    }
+    __nv_bfloat16* dst = y + (img + (long long)yy * W + xx0) * Cp + g * 8;
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+      *reinterpret_cast<uint4*>(dst + (long long)p * Cp) =
+          make_uint4(pack_bf16(o[p][0], o[p][1]), pack_bf16(o[p][2], o[p][3]), pack_bf16(o[p][4], o[p][5]), pack_bf16(o[p][6], o[p][7]));
+  }
+}
+
 // dW[co][tap] = sum_p dY[p][co] * x[p+tap], db[co] = sum_p dY[p][co]; partial[blockIdx][Cp][10]
 template <typename Idx>
 static __global__ void conv_in1_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
@@ -183,26 +247,45 @@ static __global__ void conv_in1_wgrad_kernel(const float* __restrict__ x, const 
     for (int t = 0; t < 10; ++t) acc[e][t] = 0.f;
   const Idx npix = Idx(B) * H * W;
   if (pl < pix_per_block) {
-    for (Idx pi = Idx(blockIdx.x) * pix_per_block + pl; pi < npix; pi += Idx(gridDim.x) * pix_per_block) {
+    // two pixels per iteration: both pixels' ten loads are issued before the 160 FMAs (the one-pixel loop was bound by the
+    // latency of its dependent load -> FMA chain: 128 us for 67 MB at 512^2)
+    const Idx stride = Idx(gridDim.x) * pix_per_block;
+    auto load = [&](Idx pi, float (&v)[9], uint4& d) {
       const Idx ri = pi / Idx(W);
       const int xx = int(pi - ri * Idx(W)), yy = int(ri % Idx(H));
       const long long p = (long long)pi;
       const long long base = p - (long long)yy * W - xx;
-      float v[10];
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
         const int sy = yy + t / 3 - 1, sx = xx + t % 3 - 1;
         v[t] = (sy >= 0 && sy < H && sx >= 0 && sx < W) ? x[base + (long long)sy * W + sx] : 0.f;
       }
-      v[9] = 1.f;
-      const uint4 d = *reinterpret_cast<const uint4*>(dy + p * Cp + g * 8);
+      d = *reinterpret_cast<const uint4*>(dy + p * Cp + g * 8);
+    };
+    auto fma_all = [&](const float (&v)[9], const uint4& d) {
       const uint32_t dw[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const float dv = (e & 1) ? bf16_hi(dw[e >> 1]) : bf16_lo(dw[e >> 1]);
 #pragma unroll
-        for (int t = 0; t < 10; ++t) acc[e][t] = fmaf(dv, v[t], acc[e][t]);
+        for (int t = 0; t < 9; ++t) acc[e][t] = fmaf(dv, v[t], acc[e][t]);
+        acc[e][9] += dv;
       }
+    };
+    Idx pi = Idx(blockIdx.x) * pix_per_block + pl;
+    for (; pi + stride < npix; pi += 2 * stride) {
+      float va[9], vb[9];
+      uint4 da, db_;
+      load(pi, va, da);
+      load(pi + stride, vb, db_);
+      fma_all(va, da);
+      fma_all(vb, db_);
+    }
+    if (pi < npix) {
+      float va[9];
+      uint4 da;
+      load(pi, va, da);
+      fma_all(va, da);
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e)
@@ -212,14 +295,21 @@ static __global__ void conv_in1_wgrad_kernel(const float* __restrict__ x, const 
   __syncthreads();
   for (int i = threadIdx.x; i < Cp * 10; i += blockDim.x) partial[size_t(blockIdx.x) * Cp * 10 + i] = s_acc[i];
 }
+// one warp per output element: lanes stride over the per-block partials (592 of them for the discriminator's first layer: the
+// one-thread-per-output loop took 36 us of dependent loads)
 static __global__ void conv_in1_wgrad_finish_kernel(const float* __restrict__ partial, int nparts, int C, int Cp,
                                              float* __restrict__ dw, float* __restrict__ db) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (i >= C * 10) return;
   const int co = i / 10, t = i % 10;
   float acc = 0.f;
-  for (int k = 0; k < nparts; ++k) acc += partial[size_t(k) * Cp * 10 + i];
-  if (t < 9) dw[co * 9 + t] = acc; else db[co] = acc;
+  for (int k = lane; k < nparts; k += 32) acc += partial[size_t(k) * Cp * 10 + i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    if (t < 9) dw[co * 9 + t] = acc; else db[co] = acc;
+  }
 }
 
 // ------------------------------------------------------------------ conv_last: C(=64) -> 1, NHWC bf16 in, fp32 out

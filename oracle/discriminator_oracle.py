@@ -13,7 +13,8 @@ hooks) whose state_dict is interchangeable with the reference's and with the pro
 Parity pin: tests/test_oracle_vs_reference.py::test_discriminator_oracle_equals_the_reference_module runs this module and the
 unmodified reference on the same weights and input on CPU and requires identical logits and gradients (torch.equal), in
 eval mode and in train mode (one power iteration on both sides); the functional form is pinned against the module form in
-the same test.
+the same test.  tests/golden/disc_swin_tiny.pt / disc_hat_tiny.pt (tools/make_golden.py disc) hold reference outputs and gradients
+for machines without the reference (tests/test_disc_oracle_golden.py).
 """
 from __future__ import annotations
 

@@ -142,8 +142,34 @@ def hat_fixtures():
                f"{OUT}/hybrid_tiny.pt")
 
 
+def disc_fixtures():
+    """Both U-Net discriminators (models/discriminator_swin.py, models/discriminator_hat.py) at num_feat = 8, in train mode
+    (one power iteration inside the forward) after three warm-up forwards; the fixture holds the state BEFORE the recorded
+    forward, the logits, the state's spectral-norm buffers AFTER it and every gradient."""
+    from tools import ref_shim
+    ref_shim.install()
+    from models.discriminator_swin import UNetDiscriminatorSN as SwinD
+    from models.discriminator_hat import UNetDiscriminatorSN as HatD
+    for name, cls, kw in (("disc_swin_tiny", SwinD, dict(num_in_ch=1, num_feat=8)), ("disc_hat_tiny", HatD, dict(num_in_ch=1, num_feat=8))):
+        torch.manual_seed(31)
+        d = cls(**kw).train()
+        with torch.no_grad():
+            for _ in range(3):
+                d(torch.rand(1, 1, 32, 32))
+        sd0 = {k: v.clone() for k, v in d.state_dict().items()}
+        x = torch.rand(2, 1, 64, 32, requires_grad=True)
+        y = d(x)
+        w = torch.randn_like(y)
+        g, gx = grads_of(d, y, w, x)
+        sd1 = {k: v.clone() for k, v in d.state_dict().items() if k.endswith("weight_u") or k.endswith("weight_v")}
+        torch.save({"kw": kw, "sd": sd0, "x": x.detach(), "y": y.detach(), "w": w, "grads": g, "gx": gx, "sn_after": sd1},
+                   f"{OUT}/{name}.pt")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["swin", "hat"]
+    which = sys.argv[1:] or ["swin", "hat", "disc"]
+    if "disc" in which:
+        disc_fixtures()
     if "swin" in which:
         swin_fixtures()
     if "hat" in which:

@@ -1,4 +1,6 @@
-"""UNetDiscriminatorSN forward / backward on libsrk (models/discriminator_swin.py:43-84).
+"""Both U-Net discriminators forward / backward on libsrk: models/discriminator_swin.py:43-84
+(`UNetDiscriminatorFunction`, described first) and models/discriminator_hat.py:8-49 (`UNetDiscriminatorHatFunction`, second
+half of this file).
 
 One autograd node for the whole U-Net, NHWC bf16 activations, fp32 accumulation:
 
@@ -12,9 +14,11 @@ One autograd node for the whole U-Net, NHWC bf16 activations, fp32 accumulation:
 * the 1 -> 64 head (:49), the 128 -> 64 (:67) and 64 -> 1 (:69) 3x3 layers reuse the generators' kernels
   (`srk_conv_in1_*`, `srk_conv3x3_igemm` / `_wgrad`, `srk_conv_out1_*`).
 
-Spectral normalisation (torch.nn.utils.spectral_norm, :10,25,49-52,67-69) is parameter preparation: the caller (gan.py) runs
-the reference's own power-iteration hook and hands the normalised weights in; autograd carries the weight gradients
-returned here back through W / sigma to `weight_orig`.
+Spectral normalisation (torch.nn.utils.spectral_norm, :10,25,49-52,67-69) runs inside the node too when the caller hands in
+the `weight_orig` parameters and the `weight_u` / `weight_v` buffers (`unet_discriminator_sn`, what gan.py does):
+`srk_spectral_norm` performs the hook's power iteration in place on the buffers, 1 / sigma is folded into the bf16 operand
+packing, and `srk_spectral_norm_bwd` maps the gradients back to `weight_orig`.  `unet_discriminator` takes already
+normalised weights (tests).
 
 The bilinear resize of UNetUpBlock (:36-38) only triggers when an encoder level has odd size; inputs must therefore be
 multiples of 32 pixels (the reference scripts feed 512^2) — anything else raises.

@@ -64,3 +64,34 @@ def test_fp32_policy_is_loud_and_controllable(monkeypatch):
     with torch.autocast("cpu", dtype=torch.bfloat16):
         eng.check_precision(x)          # autocast on: the reference computes in reduced precision too
     eng.check_precision(x.to(torch.bfloat16))
+
+
+def _prototypes():
+    """{symbol: parameter count} parsed from include/srk.h (comments stripped; `void` = 0 parameters)."""
+    text = (ROOT / "include" / "srk.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"^\s*#.*$", "", text, flags=re.M)
+    protos = {}
+    for m in re.finditer(r"\b(srk_[a-z0-9_]+)\s*\(([^;{}]*?)\)\s*;", text, flags=re.S):
+        params = m.group(2).strip()
+        protos[m.group(1)] = 0 if params in ("", "void") else params.count(",") + 1
+    return protos
+
+
+def test_ctypes_signatures_match_the_header_arity():
+    """Every entry point bound in _capi.py with explicit argtypes passes as many arguments as its prototype in include/srk.h
+    declares: a prototype changed on one side only (an extra pointer, a dropped flag) would otherwise shift every following
+    argument silently — ctypes cannot see C prototypes."""
+    from superresolution_def_b200 import _capi as capi
+    protos = _prototypes()
+    assert len(protos) >= 50, len(protos)
+    checked, bad = 0, []
+    for name, n in protos.items():
+        fn = getattr(capi.lib, name)
+        if fn.argtypes is None:
+            continue
+        checked += 1
+        if len(fn.argtypes) != n:
+            bad.append((name, len(fn.argtypes), n))
+    assert not bad, bad
+    assert checked >= 45, checked
